@@ -1,0 +1,80 @@
+"""Deterministic synthetic inputs / weights shared by the golden generator, the tests, smoke() and bench.py.
+
+TEST INFRASTRUCTURE.  Everything is regenerated from integer seeds with CPU generators, so the same tensors
+are obtained in the authoring container and on the GPU box (same image, same torch build).
+"""
+import hashlib
+
+import numpy as np
+import torch
+
+SEED = 88  # the reference's SEED, utils/defaults.yaml:1
+
+
+def make_image(batch, seed=SEED):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, 3, 256, 256, generator=g)
+
+
+def init_state_dict(template_sd, seed=SEED):
+    """Deterministic, well-conditioned random weights for every key of a reference-layout state_dict."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in template_sd:
+        t = template_sd[k]
+        if k.endswith('num_batches_tracked'):
+            out[k] = torch.zeros_like(t)
+        elif k.endswith('running_mean'):
+            out[k] = torch.randn(t.shape, generator=g) * 0.1
+        elif k.endswith('running_var'):
+            out[k] = torch.rand(t.shape, generator=g) * 0.5 + 0.75
+        elif k == 'decoder.dense_coor' or k == 'decoder.unsample_layer.weight':
+            out[k] = t.clone().float()
+        elif t.dim() == 1:
+            if k.endswith('.weight'):      # norm scales
+                out[k] = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
+            else:                           # biases / norm shifts
+                out[k] = 0.05 * torch.randn(t.shape, generator=g)
+        else:
+            fan_in = t[0].numel()
+            if 'position_embeddings' in k:
+                out[k] = 0.5 * torch.randn(t.shape, generator=g)
+            else:
+                out[k] = torch.randn(t.shape, generator=g) * (1.6 / fan_in) ** 0.5
+    return out
+
+
+def checksum(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd[k].detach().cpu().numpy()).tobytes())
+    return h.hexdigest()
+
+
+def make_labels(batch, seed=SEED):
+    """Synthetic labels of SURVEY 8(d) for calc_loss_GCN."""
+    g = torch.Generator().manual_seed(seed + 1)
+    r = lambda *s: torch.randn(*s, generator=g)
+    u = lambda *s: torch.rand(*s, generator=g)
+    return {'v3d_l': r(batch, 778, 3) * 0.05, 'v3d_r': r(batch, 778, 3) * 0.05,
+            'v2d_l': u(batch, 778, 2) * 256, 'v2d_r': u(batch, 778, 2) * 256, 'root_rel': r(batch, 3) * 0.05}
+
+
+def make_loss_assets(assets, mano_l, mano_r):
+    from . import model_ref
+    out = {}
+    for side, m in (('left', mano_l), ('right', mano_r)):
+        jr = m['J_regressor']
+        jr = np.asarray(jr.todense()) if hasattr(jr, 'todense') else np.asarray(jr)
+        out[side] = {'J21': model_ref.make_joint_regressor(torch.from_numpy(jr.astype(np.float32))),
+                     'faces': torch.from_numpy(np.asarray(m['f']).astype(np.int64)),
+                     'perm': [int(v) for v in assets[side + '_graph']['graph_perm']]}
+    return out
+
+
+def make_mano_inputs(batch, ncomps=45, seed=SEED):
+    g = torch.Generator().manual_seed(seed + 2)
+    return {'axis': torch.rand(batch, 3, generator=g), 'pose_pca': torch.rand(batch, ncomps, generator=g),
+            'pose_axis': torch.rand(batch, 45, generator=g) * 0.8, 'shape': torch.rand(batch, 10, generator=g),
+            'trans': torch.rand(batch, 3, generator=g), 'scale': torch.rand(batch, generator=g) + 0.5}

@@ -1,0 +1,131 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (imported in place from /root/reference).
+
+Run in the authoring container only:   python -m oracle.make_golden
+The reference's own tests contain no golden vectors for this path; these fixtures, produced
+by the reference code itself on seeded synthetic inputs, are what pins the oracle (tests/test_oracle_golden.py)
+and, through it, the CUDA path.  Synthetic assets are used so that nothing derived from the licence-restricted
+MANO files is committed.
+"""
+import os
+import pickle
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import fixtures, ref_bridge as rb   # noqa: E402
+from renderih_b200 import assets as rih_assets  # noqa: E402  (asset *generator* only: no kernels involved)
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def write_synthetic_asset_dir(tmp, seed=0):
+    a = rih_assets.synthetic_assets(seed)
+    for side in ('left', 'right'):
+        with open(os.path.join(tmp, 'graph_%s.pkl' % side), 'wb') as f:
+            pickle.dump(a[side + '_graph'], f)
+    with open(os.path.join(tmp, 'v_color.pkl'), 'wb') as f:
+        pickle.dump(a['dense_coor'], f)
+    with open(os.path.join(tmp, 'upsample.pkl'), 'wb') as f:
+        pickle.dump(a['upsample'], f)
+    os.makedirs(os.path.join(tmp, 'mano'), exist_ok=True)
+    for side in ('left', 'right'):
+        with open(os.path.join(tmp, 'mano', 'MANO_%s.pkl' % side.upper()), 'wb') as f:
+            pickle.dump(rih_assets.synthetic_mano(seed, side), f)
+    return a
+
+
+def flat(out):
+    result, params, hlist, other = out
+    d = {}
+    for side in ('left', 'right'):
+        d['verts3d_' + side] = result['verts3d'][side]
+        d['verts2d_' + side] = result['verts2d'][side]
+        d['scale_' + side] = params['scale'][side]
+        d['trans2d_' + side] = params['trans2d'][side]
+        d['v3c_' + side] = hlist[0]['verts3d'][side]
+        d['v2c_' + side] = hlist[0]['verts2d'][side]
+        d['v3list_' + side] = other['verts3d_MANO_list'][side][0]
+        d['v2list_' + side] = other['verts2d_MANO_list'][side][0]
+    for k in ('hms', 'mask', 'dense'):
+        d[k + '_sub'] = other[k][:, :, ::8, ::8].contiguous()
+        d[k + '_mean'] = other[k].mean(dim=(2, 3))
+    return {k: v.detach().clone() for k, v in d.items()}
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ns = rb.import_reference()
+    with tempfile.TemporaryDirectory() as tmp:
+        a = write_synthetic_asset_dir(tmp, 0)
+        # ---------------- model forward (eval) and forward+backward (train, dropout 0)
+        ref, cfg = rb.build_reference_model(asset_dir=tmp, dropout=0.0)
+        sd = fixtures.init_state_dict(ref.state_dict())
+        ref.load_state_dict(sd)
+        B = 2
+        img = fixtures.make_image(B)
+        ref.eval()
+        with torch.no_grad():
+            out_eval = flat(ref(img))
+        gold = {'weights_sha256': fixtures.checksum(sd), 'batch': B, 'seed': fixtures.SEED, 'torch': torch.__version__,
+                'eval': out_eval}
+        # training-mode forward + calc_loss_GCN backward, through the reference's own loss code
+        ref.train()
+        for p in ref.parameters():
+            p.requires_grad_(True)
+        ref.decoder.unsample_layer.weight.requires_grad_(False)   # freeze_upsample (core/lijun_trainer.py:115-116)
+        out = ref(img)
+        labels = fixtures.make_labels(B)
+        manoL = ns.mano.ManoLayer(os.path.join(tmp, 'mano', 'MANO_LEFT.pkl'), center_idx=None)
+        manoR = ns.mano.ManoLayer(os.path.join(tmp, 'mano', 'MANO_RIGHT.pkl'), center_idx=None)
+        gl = ns.loss.GraphLoss(manoL.J_regressor, manoL.get_faces(), level=4, device='cpu')
+        gr = ns.loss.GraphLoss(manoR.J_regressor, manoR.get_faces(), level=4, device='cpu')
+        z = torch.zeros(B, 21, 3)
+        loss, _, mano_d, coarse_d = ns.loss.calc_loss_GCN(
+            cfg, 0, gl, gr, ref.decoder.converter['left'], ref.decoder.converter['right'],
+            out[0], out[1], out[2], out[3], None, None, None,
+            labels['v2d_l'], z[..., :2], labels['v2d_r'], z[..., :2], labels['v3d_l'], z, labels['v3d_r'], z,
+            labels['root_rel'], 256, upsample_weight=None)
+        loss.backward()
+        grads = {}
+        for k, p in ref.named_parameters():
+            if p.grad is None:
+                continue
+            g = p.grad
+            grads[k] = {'norm': float(g.norm()), 'sum': float(g.sum())}
+            if g.numel() <= 4096:
+                grads[k]['full'] = g.detach().clone()
+        gold['train'] = {'out': flat(out), 'loss': float(loss), 'grads': grads,
+                         'bn1_running_mean': ref.encoder.resnet.bn1.running_mean.detach().clone(),
+                         'bn1_running_var': ref.encoder.resnet.bn1.running_var.detach().clone(),
+                         'no_grad_keys': [k for k, p in ref.named_parameters() if p.grad is None]}
+        torch.save(gold, os.path.join(GOLD, 'model_synth_b2.pt'))
+        print('model golden: loss %.6f, %d grads, eval |v3d_l| max %.4f' % (float(loss), len(grads), float(out_eval['verts3d_left'].abs().max())))
+
+        # ---------------- ManoLayer goldens on the synthetic MANO tensors
+        mg = {'cases': []}
+        inp = fixtures.make_mano_inputs(5)
+        root = ns.mano.rodrigues_batch(inp['axis'])
+        for side in ('left', 'right'):
+            path = os.path.join(tmp, 'mano', 'MANO_%s.pkl' % side.upper())
+            for cfgc in ({'center_idx': 9, 'use_pca': True, 'new_skel': False, 'ncomps': 45, 'ts': True},
+                         {'center_idx': None, 'use_pca': True, 'new_skel': True, 'ncomps': 30, 'ts': False},
+                         {'center_idx': 0, 'use_pca': False, 'new_skel': False, 'ncomps': 0, 'ts': True}):
+                layer = ns.mano.ManoLayer(path, center_idx=cfgc['center_idx'], use_pca=cfgc['use_pca'], new_skel=cfgc['new_skel'])
+                if cfgc['use_pca']:
+                    pose = inp['pose_pca'][:, :cfgc['ncomps']]
+                else:
+                    pose = layer.axis2Rmat(inp['pose_axis'])
+                tr, sc = (inp['trans'], inp['scale']) if cfgc['ts'] else (None, None)
+                v, j = layer(root, pose, inp['shape'], tr, sc)
+                mg['cases'].append({'side': side, 'cfg': cfgc, 'v': v.clone(), 'j': j.clone()})
+        mg['rodrigues'] = root.clone()
+        torch.save(mg, os.path.join(GOLD, 'mano_synth.pt'))
+        print('mano golden: %d cases' % len(mg['cases']))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,313 @@
+"""CPU oracle: functional restatement of `models.model.HandNET_GCN.forward` (reference models/model.py:25-37).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Plain torch fp32 ops on a reference-layout state_dict, NCHW.
+Pinned against the UNMODIFIED reference imported in the authoring container (oracle/make_golden.py writes
+tests/golden/*.pt; tests/test_oracle_golden.py re-checks them on every run).  The reference's own tests hold no
+golden vectors for this path, so these self-generated fixtures are the only pin.
+
+Every function cites the reference lines it follows.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+IMG_SIZE = 256  # dataset/dataset_utils.py:4
+
+
+def _bn(x, sd, pre, training, momentum=0.1, eps=1e-5):
+    """nn.BatchNorm2d; in training mode batch statistics are used and running stats in `sd` are updated in place."""
+    return F.batch_norm(x, sd[pre + '.running_mean'], sd[pre + '.running_var'], sd[pre + '.weight'], sd[pre + '.bias'],
+                        training, momentum, eps)
+
+
+def _ln(x, sd, pre):
+    return F.layer_norm(x, (x.shape[-1],), sd[pre + '.weight'], sd[pre + '.bias'], 1e-6)
+
+
+def _lin(x, sd, pre):
+    return F.linear(x, sd[pre + '.weight'], sd.get(pre + '.bias'))
+
+
+def _drop(x, p, training):
+    return F.dropout(x, p, training) if (training and p > 0) else x
+
+
+# ---------------------------------------------------------------- encoder: models/encoder.py:107-126 + torchvision Bottleneck
+def _bottleneck(x, sd, pre, stride, has_ds, tr):
+    out = F.relu(_bn(F.conv2d(x, sd[pre + '.conv1.weight']), sd, pre + '.bn1', tr))
+    out = F.relu(_bn(F.conv2d(out, sd[pre + '.conv2.weight'], stride=stride, padding=1), sd, pre + '.bn2', tr))
+    out = _bn(F.conv2d(out, sd[pre + '.conv3.weight']), sd, pre + '.bn3', tr)
+    idt = x
+    if has_ds:
+        idt = _bn(F.conv2d(x, sd[pre + '.downsample.0.weight'], stride=stride), sd, pre + '.downsample.1', tr)
+    return F.relu(out + idt)
+
+
+def _simple_decoder(x, sd, pre, tr):
+    """ResNetSimple_decoder.forward, models/encoder.py:58-64: flat 1x1 then 3x (bilinear x2, 3x3 conv, ReLU, BN)."""
+    fmaps = []
+    x = _bn(F.relu(F.conv2d(x, sd[pre + '.models.0.0.weight'])), sd, pre + '.models.0.2', tr)
+    fmaps.append(x)
+    for i in (1, 2, 3):
+        x = F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True)
+        x = _bn(F.relu(F.conv2d(x, sd['%s.models.%d.1.weight' % (pre, i)], padding=1)), sd, '%s.models.%d.3' % (pre, i), tr)
+        fmaps.append(x)
+    out = F.conv2d(x, sd[pre + '.final_layer.weight'], sd[pre + '.final_layer.bias'])
+    return out, fmaps
+
+
+def encoder_forward(sd, img, tr, blocks=(3, 4, 6, 3)):
+    p = 'encoder.resnet'
+    x = F.relu(_bn(F.conv2d(img, sd[p + '.conv1.weight'], stride=2, padding=3), sd, p + '.bn1', tr))
+    x = F.max_pool2d(x, 3, 2, 1)
+    feats = []
+    for li, nb in enumerate(blocks):
+        for bi in range(nb):
+            stride = 2 if (bi == 0 and li > 0) else 1
+            x = _bottleneck(x, sd, '%s.layer%d.%d' % (p, li + 1, bi), stride, bi == 0, tr)
+        feats.append(x)
+    x4, x3, x2, x1 = feats
+    hms, hms_f = _simple_decoder(x1, sd, 'encoder.hms_decoder', tr)
+    out, dp_f = _simple_decoder(x1, sd, 'encoder.dp_decoder', tr)
+    return hms, out[:, :2], out[:, 2:], [x1, x2, x3, x4], hms_f, dp_f
+
+
+def mid_forward(sd, img_f, hms_f, dp_f, tr):
+    """resnet_mid.forward, models/encoder.py:165-173 (conv1x1 helper = Conv -> ReLU -> BN, model_zoo/__init__.py:56-62)"""
+    gf = F.adaptive_avg_pool2d(img_f[0], 1).flatten(1)
+    fmaps = []
+    for i in range(4):
+        x = torch.cat((hms_f[i], dp_f[i]), 1)
+        if i > 0:
+            x = torch.cat((x, img_f[i]), 1)
+        fmaps.append(_bn(F.relu(F.conv2d(x, sd['mid_model.convs.%d.0.weight' % i])), sd, 'mid_model.convs.%d.2' % i, tr))
+    return gf, fmaps
+
+
+# ---------------------------------------------------------------- decoder blocks
+def graph_conv_cheby(x, sd, pre, L, K=2):
+    """models/model_attn/gcn.py:34-69 (dense Laplacian product, Fin x K interleave)"""
+    B, V, Fin = x.shape
+    x0 = x.permute(1, 2, 0).contiguous().view(V, Fin * B)
+    xs = [x0]
+    if K > 1:
+        x1 = torch.mm(L, x0)
+        xs.append(x1)
+    for _ in range(2, K):
+        x2 = 2 * torch.mm(L, x1) - x0
+        xs.append(x2)
+        x0, x1 = x1, x2
+    xx = torch.stack(xs, 0).view(K, V, Fin, B).permute(3, 1, 2, 0).contiguous().view(B * V, Fin * K)
+    return _lin(xx, sd, pre).view(B, V, -1)
+
+
+def gcn_resblock(x, sd, pre, L, p, tr):
+    """GCN_ResBlock.forward, gcn.py:99-110 -- relu(norm1(x)) is discarded by the reference (103-104)."""
+    x1 = graph_conv_cheby(x, sd, pre + '.fc1', L)
+    x1 = F.relu(_ln(x1, sd, pre + '.norm2'))
+    x1 = graph_conv_cheby(x1, sd, pre + '.fc2', L)
+    x1 = _drop(x1, p, tr)
+    x2 = _lin(x, sd, pre + '.shortcut')
+    return _ln(x1 + x2, sd, pre + '.norm3')
+
+
+def graph_layer(x, sd, pre, L, p, tr, n=4):
+    """GraphLayer.forward, gcn.py:132-138"""
+    for i in range(n):
+        x = gcn_resblock(x, sd, '%s.GCN_blocks.%d' % (pre, i), L, p, tr)
+        if i != n - 1:
+            x = F.relu(x)
+    return x
+
+
+def mlp_res(x, sd, pre, p, tr):
+    """MLP_res_block.forward, self_attn.py:27-33"""
+    h = _ln(x, sd, pre + '.layer_norm')
+    h = _drop(F.relu(_lin(h, sd, pre + '.fc1')), p, tr)
+    return x + _drop(_lin(h, sd, pre + '.fc2'), p, tr)
+
+
+def _heads(t, B, H):
+    return t.view(B, -1, H, t.shape[-1] // H).transpose(1, 2)
+
+
+def self_attn(x, sd, pre, p, tr, H=4):
+    """SelfAttn.forward, self_attn.py:63-85"""
+    B, V, f = x.shape
+    xn = _ln(x, sd, pre + '.layer_norm')
+    q, k, v = (_heads(_lin(xn, sd, pre + n), B, H) for n in ('.w_qs', '.w_ks', '.w_vs'))
+    attn = torch.matmul(q, k.transpose(-1, -2)) / (f // H) ** 0.5
+    attn = _drop(F.softmax(attn, -1), p, tr)
+    out = torch.matmul(attn, v).transpose(1, 2).contiguous().view(B, V, -1)
+    x = x + _drop(_lin(out, sd, pre + '.fc'), p, tr)
+    return mlp_res(x, sd, pre + '.ff', p, tr)
+
+
+def img_ex(img, verts_f, sd, pre, p, tr):
+    """img_ex.forward, img_attn.py:111-115 -> img_feat_to_grid (51-67) + img_attn (79-92)"""
+    B = img.shape[0]
+    w = sd[pre + '.encoder.proj.weight']
+    g = F.relu(F.conv2d(img, w, sd[pre + '.encoder.proj.bias'], stride=w.shape[-1]))
+    g = g.view(B, g.shape[1], -1).transpose(-1, -2) + sd[pre + '.encoder.position_embeddings.weight'][None]
+    g = self_attn(g, sd, pre + '.encoder.self_attn', p, tr)
+    V = verts_f.shape[1]
+    x = torch.cat([verts_f, _lin(g, sd, pre + '.attn.fc')], 1)
+    return self_attn(x, sd, pre + '.attn.Attn', p, tr)[:, :V]
+
+
+def inter_attn(Lf, Rf, sd, pre, p, tr, H=4):
+    """inter_attn.forward, inter_attn.py:73-123"""
+    Lf = self_attn(Lf, sd, pre + '.L_self_attn_layer', p, tr)
+    Rf = self_attn(Rf, sd, pre + '.R_self_attn_layer', p, tr)
+    B, V, f = Lf.shape
+    L2, R2 = _ln(Lf, sd, pre + '.layer_norm1'), _ln(Rf, sd, pre + '.layer_norm2')
+    Lq, Lk, Lv = (_heads(_lin(L2, sd, pre + n), B, H) for n in ('.w_qs', '.w_ks', '.w_vs'))
+    Rq, Rk, Rv = (_heads(_lin(R2, sd, pre + n), B, H) for n in ('.w_qs', '.w_ks', '.w_vs'))
+    nrm = (f // H) ** 0.5
+    a_R2L = _drop(F.softmax(torch.matmul(Lq, Rk.transpose(-1, -2)) / nrm, -1), p, tr)
+    a_L2R = _drop(F.softmax(torch.matmul(Rq, Lk.transpose(-1, -2)) / nrm, -1), p, tr)
+    f_L2R = torch.matmul(a_L2R, Lv).transpose(1, 2).contiguous().view(B, V, -1)
+    f_R2L = torch.matmul(a_R2L, Rv).transpose(1, 2).contiguous().view(B, V, -1)
+    f_L2R = _drop(_lin(f_L2R, sd, pre + '.fc'), p, tr)
+    f_R2L = _drop(_lin(f_R2L, sd, pre + '.fc'), p, tr)
+    return mlp_res(Lf + f_R2L, sd, pre + '.ffL', p, tr), mlp_res(Rf + f_L2R, sd, pre + '.ffR', p, tr)
+
+
+def graph_upsample(x, p):
+    """DualGraph.py:11-18 (nearest xp on the vertex axis)"""
+    return x.repeat_interleave(p, dim=1) if p > 1 else x
+
+
+def projection_batch(scale, trans2d, label3d, img_size=IMG_SIZE):
+    """utils/manoutils.py:26-44"""
+    scale = (scale * img_size)[:, None, None]
+    trans2d = (trans2d * img_size / 2 + img_size / 2)[:, None]
+    return scale * label3d[..., :2] + trans2d
+
+
+def prepare_assets(assets):
+    """Dense Laplacians of the 3 decoder levels (gcn.py:79-86) + permutations, from the raw asset dicts."""
+    out = {}
+    for side in ('left', 'right'):
+        g = assets[side + '_graph']
+        Ls = list(g['coarsen_graphs_L'])[::-1]           # decoder.py:53-54
+        out[side] = {
+            'L': [torch.from_numpy(np.asarray(L.todense() if hasattr(L, 'todense') else L, dtype=np.float32)) for L in Ls[:3]],
+            'perm': [int(v) for v in g['graph_perm']],
+            'perm_rev': np.asarray(g['graph_perm_reverse'])[:778],
+            'vNum_all': Ls[-1].shape[0],
+        }
+    return out
+
+
+def decoder_forward(sd, A, gf, fmaps, p, tr):
+    """decoder.forward, models/decoder.py:128-174"""
+    fmaps = fmaps[:-1]
+    B = gf.shape[0]
+    dc = sd['decoder.dense_coor'][None].repeat(B, 1, 1) * 2 - 1
+    feats = {}
+    for side, name in (('left', 'decoder.gf_layer_left'), ('right', 'decoder.gf_layer_right')):
+        pe = dc[:, A[side]['perm']]                                        # vert_to_GCN
+        pe = F.avg_pool1d(pe.permute(0, 2, 1), pe.shape[1] // 63).permute(0, 2, 1)   # graph_avg_pool
+        g = _ln(_lin(gf, sd, name + '.0'), sd, name + '.1')
+        feats[side] = torch.cat([g[:, None].repeat(1, 63, 1), pe], -1)
+    Lf, Rf = feats['left'], feats['right']
+    for i in range(3):
+        pre = 'decoder.dual_gcn.layers.%d' % i
+        emb = sd[pre + '.position_embeddings.weight'][None]
+        Lf, Rf = Lf + emb, Rf + emb
+        Lf = graph_layer(Lf, sd, pre + '.graph_left', A['left']['L'][i], p, tr)
+        Rf = graph_layer(Rf, sd, pre + '.graph_right', A['right']['L'][i], p, tr)
+        Lf = img_ex(fmaps[i], Lf, sd, pre + '.img_ex_left', p, tr)
+        Rf = img_ex(fmaps[i], Rf, sd, pre + '.img_ex_right', p, tr)
+        Lf, Rf = inter_attn(Lf, Rf, sd, pre + '.attn', p, tr)
+        if i != 2:
+            Lf, Rf = graph_upsample(Lf, 2), graph_upsample(Rf, 2)
+    scale, trans2d, v3, v2 = {}, {}, {}, {}
+    result = {'verts3d': {}, 'verts2d': {}}
+    for side, f in (('left', Lf), ('right', Rf)):
+        t = _lin(f.transpose(-1, -2), sd, 'decoder.avg_head')[..., 0]
+        t = _lin(t, sd, 'decoder.params_head')
+        scale[side], trans2d[side] = t[:, 0], t[:, 1:]
+        v3[side] = _lin(f, sd, 'decoder.coord_head')
+        v2[side] = projection_batch(scale[side], trans2d[side], v3[side])
+        up = F.linear(v3[side].transpose(1, 2), sd['decoder.unsample_layer.weight']).transpose(1, 2)
+        result['verts3d'][side] = up
+        result['verts2d'][side] = projection_batch(scale[side], trans2d[side], up)
+    other = {'verts3d_MANO_list': {'left': [], 'right': []}, 'verts2d_MANO_list': {'left': [], 'right': []}}
+    for side in ('left', 'right'):
+        pr, va = A[side]['perm_rev'], A[side]['vNum_all']
+        other['verts3d_MANO_list'][side].append(graph_upsample(v3[side], va // v3[side].shape[1])[:, pr])
+        other['verts2d_MANO_list'][side].append(graph_upsample(v2[side], va // v2[side].shape[1])[:, pr])
+    return result, {'scale': scale, 'trans2d': trans2d}, [{'verts3d': v3, 'verts2d': v2}], other
+
+
+def model_forward(sd, assets_prepared, img, training=False, dropout=0.0):
+    """HandNET_GCN.forward, models/model.py:25-37.  `sd` maps reference state_dict keys to tensors (BN running
+    statistics are updated in place when training=True, exactly like nn.BatchNorm2d)."""
+    hms, mask, dp, img_f, hms_f, dp_f = encoder_forward(sd, img, training)
+    gf, fmaps = mid_forward(sd, img_f, hms_f, dp_f, training)
+    result, params, hlist, other = decoder_forward(sd, assets_prepared, gf, fmaps, dropout, training)
+    other['hms'], other['mask'], other['dense'] = hms, mask, dp
+    return result, params, hlist, other
+
+
+# ---------------------------------------------------------------- loss: core/Loss.py:20-277 (calc_loss_GCN), epoch < NORM_EPOCH
+def make_joint_regressor(J_regressor16):
+    """GraphLoss.process_J_regressor, core/Loss.py:38-53"""
+    J = J_regressor16.clone().float()
+    tips = torch.zeros(5, J.shape[1])
+    for i, v in enumerate((745, 317, 444, 556, 673)):
+        tips[i, v] = 1.0
+    J = torch.cat([J, tips], 0)
+    order = [0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20]
+    return J[order].contiguous()
+
+
+def _edges(v, faces):
+    e = v[:, faces]
+    return torch.stack([e[:, :, 0] - e[:, :, 1], e[:, :, 1] - e[:, :, 2], e[:, :, 2] - e[:, :, 0]], 2)
+
+
+def graph_loss_side(J21, faces, perm, v3d_gt, v2d_gt, v3d_pred, v2d_pred, v3dList, v2dList, img_size=IMG_SIZE, level=5):
+    """GraphLoss.calc_loss, core/Loss.py:128-162 + calc_mano_loss 103-115"""
+    sl1, mse = F.smooth_l1_loss, F.mse_loss
+    d = {}
+    d['vert2d_loss'] = mse(v2d_pred / img_size * 2 - 1, v2d_gt / img_size * 2 - 1)
+    d['vert3d_loss'] = sl1(v3d_pred, v3d_gt)
+    d['joint_loss'] = sl1(torch.matmul(J21, v3d_pred), torch.matmul(J21, v3d_gt))
+    eg, ep = _edges(v3d_gt, faces), _edges(v3d_pred, faces)
+    n_gt = F.normalize(torch.cross(eg[:, :, 0], eg[:, :, 1], dim=-1), dim=-1).unsqueeze(2)
+    t = torch.sum(F.normalize(ep, dim=-1) * n_gt, -1)
+    d['norm_loss'] = sl1(t, torch.zeros_like(t))
+    d['edge_loss'] = sl1(torch.linalg.norm(ep, dim=-1), torch.linalg.norm(eg, dim=-1))
+    v3g, v2g = v3d_gt[:, perm], v2d_gt[:, perm]
+    gts3, gts2 = [], []
+    for _ in range(level):
+        gts3.append(v3g); gts2.append(v2g)
+        v3g = F.avg_pool1d(v3g.permute(0, 2, 1), 2).permute(0, 2, 1)
+        v2g = F.avg_pool1d(v2g.permute(0, 2, 1), 2).permute(0, 2, 1)
+    c3, c2 = [], []
+    for a3, a2 in zip(v3dList, v2dList):
+        j = [g.shape[1] for g in gts3].index(a3.shape[1])
+        c3.append(sl1(a3, gts3[j]))
+        c2.append(mse(a2 / img_size * 2 - 1, gts2[j] / img_size * 2 - 1))
+    return d, {'v3d_loss': c3, 'v2d_loss': c2}
+
+
+def calc_loss_GCN(out, labels, loss_assets, epoch=0, w3d=100., w2d=50., w_norm=10., w_edge=2000., norm_epoch=50):
+    """calc_loss_GCN, core/Loss.py:201-277 (aux loss disabled at :213, upsample_weight=None path)."""
+    result, params, hlist, other = out
+    v3d_r = labels['v3d_r'] + labels['root_rel'][:, None]
+    sides = {}
+    for side, v3g, v2g in (('left', labels['v3d_l'], labels['v2d_l']), ('right', v3d_r, labels['v2d_r'])):
+        la = loss_assets[side]
+        sides[side] = graph_loss_side(la['J21'], la['faces'], la['perm'], v3g, v2g, result['verts3d'][side], result['verts2d'][side],
+                                      [h['verts3d'][side] for h in hlist], [h['verts2d'][side] for h in hlist])
+    m = {k: (sides['left'][0][k] + sides['right'][0][k]) / 2 for k in sides['left'][0]}
+    alpha = 0 if epoch < norm_epoch else 1
+    total = w3d * m['vert3d_loss'] + w2d * m['vert2d_loss'] + w3d * m['joint_loss'] + w_norm * m['norm_loss'] + alpha * w_edge * m['edge_loss']
+    for i in range(len(sides['left'][1]['v3d_loss'])):
+        total = total + w3d * (sides['left'][1]['v3d_loss'][i] + sides['right'][1]['v3d_loss'][i]) / 2 \
+                      + w2d * (sides['left'][1]['v2d_loss'][i] + sides['right'][1]['v2d_loss'][i]) / 2
+    return total

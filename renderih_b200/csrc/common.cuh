@@ -1,0 +1,70 @@
+// Common helpers for the renderih_b200 C-ABI CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define RIH_API extern "C" __attribute__((visibility("default")))
+
+namespace rih {
+
+// ---- error convention: 0 = ok, non-zero + rih_last_error() ----
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define RIH_REQUIRE(cond, ...)                        \
+  do {                                                \
+    if (!(cond)) {                                    \
+      rih::set_error(__VA_ARGS__);                    \
+      return 1;                                       \
+    }                                                 \
+  } while (0)
+
+#define RIH_CUDA(call)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) {                                                 \
+      rih::set_error("%s failed: %s", #call, cudaGetErrorString(e__));        \
+      return 2;                                                               \
+    }                                                                         \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Counter-based RNG for dropout masks (stateless: regenerated in backward from the same key).
+__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+// keep-scale for dropout: returns 0 (dropped) or 1/(1-p)
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, uint32_t thresh, float inv_keep) {
+  return hash_u32(seed, idx) >= thresh ? inv_keep : 0.f;
+}
+static inline uint32_t dropout_thresh(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}
+
+}  // namespace rih

@@ -1,0 +1,407 @@
+// NHWC image-side elementwise / reduction kernels: BatchNorm (train+eval), max-pool, bilinear x2,
+// global average pool, layout conversion. All tensors are fp32 [rows, C] with an explicit row stride.
+#include "common.cuh"
+using namespace rih;
+
+// ============================================================== layout conversion
+// NCHW [N,C,H,W] -> NHWC [N,H,W,Cp] (channels >= C zero-filled). reference input layout: models/model.py:25
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int C, int HW, int Cp, int ldy) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z;
+  int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? x[((size_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < Cp) y[((size_t)n * HW + p) * ldy + c] = tile[threadIdx.x][i];
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int C, int HW, int ldx, int c_off) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z;
+  int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? x[((size_t)n * HW + p) * ldx + c_off + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) y[((size_t)n * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+RIH_API int rih_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int Cp, int ldy, cudaStream_t s) {
+  RIH_REQUIRE(Cp >= C && ldy >= Cp, "nchw_to_nhwc: bad channel padding");
+  dim3 grid(cdiv(HW, 32), cdiv(Cp, 32), N), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, s>>>(x, y, N, C, HW, Cp, ldy);
+  return check_launch("nchw_to_nhwc");
+}
+// y NCHW [N,C,HW] <- channels [c_off, c_off+C) of x NHWC
+RIH_API int rih_nhwc_to_nchw(const float* x, float* y, int N, int C, int HW, int ldx, int c_off, cudaStream_t s) {
+  dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, s>>>(x, y, N, C, HW, ldx, c_off);
+  return check_launch("nhwc_to_nchw");
+}
+
+// generic strided 2-D copy / add:  y[r, 0:C] (+)= x[r, 0:C]
+__global__ void copy2d_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, long long rows, int C, int acc) {
+  long long total = rows * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / C; int c = (int)(i - r * C);
+    float v = x[r * ldx + c];
+    float* q = y + r * ldy + c;
+    *q = acc ? (*q + v) : v;
+  }
+}
+RIH_API int rih_copy2d(const float* x, int ldx, float* y, int ldy, long long rows, int C, int accumulate, cudaStream_t s) {
+  if (rows * C == 0) return 0;
+  int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
+  copy2d_kernel<<<grid, 256, 0, s>>>(x, ldx, y, ldy, rows, C, accumulate);
+  return check_launch("copy2d");
+}
+
+// ============================================================== BatchNorm
+// column statistics over M rows: partial sums in double, atomically merged.  ws = double[2*C] (zeroed here)
+__global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int C, int rows_per_cta, double* __restrict__ ws) {
+  int c = blockIdx.x * 32 + threadIdx.x;
+  int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  double s = 0.0, ss = 0.0;
+  if (c < C) {
+    for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      float v = x[(size_t)r * ld + c];
+      s += v; ss += (double)v * v;
+    }
+  }
+  __shared__ double sh[2][8][33];
+  sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) { s += sh[0][i][threadIdx.x]; ss += sh[1][i][threadIdx.x]; }
+    atomicAdd(ws + c, s); atomicAdd(ws + C + c, ss);
+  }
+}
+// mean / rstd and running-stat update (torch.nn.BatchNorm2d training semantics: momentum, unbiased running var)
+__global__ void bn_finalize_kernel(const double* __restrict__ ws, int M, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m = ws[c] / M;
+  double var = ws[C + c] / M - m * m;
+  if (var < 0) var = 0;
+  mean[c] = (float)m;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    double unbiased = M > 1 ? var * M / (M - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+__global__ void bn_eval_prep_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, float eps,
+                                    float* __restrict__ mean, float* __restrict__ rstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = rm[c];
+  rstd[c] = 1.f / sqrtf(rv[c] + eps);
+}
+RIH_API int rih_bn_stats(const float* x, int ld, int M, int C, float eps, float momentum, double* ws,
+                         float* mean, float* rstd, float* running_mean, float* running_var, cudaStream_t s) {
+  RIH_REQUIRE(M > 0 && C > 0, "bn_stats: empty");
+  RIH_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, s));
+  int gx = cdiv(C, 32);
+  int target = cdiv(148 * 8, gx);
+  int rows_per_cta = max(64, cdiv(M, target));
+  dim3 grid(gx, cdiv(M, rows_per_cta)), block(32, 8);
+  bn_stats_kernel<<<grid, block, 0, s>>>(x, ld, M, C, rows_per_cta, ws);
+  if (int e = check_launch("bn_stats")) return e;
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(ws, M, C, eps, momentum, mean, rstd, running_mean, running_var);
+  return check_launch("bn_finalize");
+}
+RIH_API int rih_bn_eval_prep(const float* rm, const float* rv, int C, float eps, float* mean, float* rstd, cudaStream_t s) {
+  bn_eval_prep_kernel<<<cdiv(C, 128), 128, 0, s>>>(rm, rv, C, eps, mean, rstd);
+  return check_launch("bn_eval_prep");
+}
+
+// y = (x-mean)*rstd*gamma+beta (+res) (relu).   C % 4 == 0, all row strides % 4 == 0
+__global__ void bn_apply_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ res, int ldr, float* __restrict__ y, int ldy,
+                                long long M, int C4, int relu) {
+  long long total = M * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / C4; int c = (int)(i - r * C4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    float4 o;
+    o.x = (v.x - mu.x) * rs.x * g.x + b.x; o.y = (v.y - mu.y) * rs.y * g.y + b.y;
+    o.z = (v.z - mu.z) * rs.z * g.z + b.z; o.w = (v.w - mu.w) * rs.w * g.w + b.w;
+    if (res) {
+      float4 q = *reinterpret_cast<const float4*>(res + r * ldr + c);
+      o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+    }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    *reinterpret_cast<float4*>(y + r * ldy + c) = o;
+  }
+}
+RIH_API int rih_bn_apply(const float* x, int ldx, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                         const float* res, int ldr, float* y, int ldy, long long M, int C, int relu, cudaStream_t s) {
+  RIH_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (!res || ldr % 4 == 0), "bn_apply: needs C,ld %% 4 == 0");
+  long long total = M * (C / 4);
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  bn_apply_kernel<<<grid, 256, 0, s>>>(x, ldx, mean, rstd, gamma, beta, res, ldr, y, ldy, M, C / 4, relu);
+  return check_launch("bn_apply");
+}
+
+// backward pass 1: g = dy * (y > 0 if relu);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+                                     const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     int M, int C, int rows_per_cta, int relu, double* __restrict__ ws) {
+  int c = blockIdx.x * 32 + threadIdx.x;
+  int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  double s = 0.0, sx = 0.0;
+  if (c < C) {
+    float mu = mean[c], rs = rstd[c];
+    for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      float g = dy[(size_t)r * lddy + c];
+      if (relu && !(y[(size_t)r * ldy + c] > 0.f)) g = 0.f;
+      float xh = (x[(size_t)r * ldx + c] - mu) * rs;
+      s += g; sx += (double)g * xh;
+    }
+  }
+  __shared__ double sh[2][8][33];
+  sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = sx;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) { s += sh[0][i][threadIdx.x]; sx += sh[1][i][threadIdx.x]; }
+    atomicAdd(ws + c, s); atomicAdd(ws + C + c, sx);
+  }
+}
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, int C, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ sum_g, float* __restrict__ sum_gx, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = (float)ws[c], sx = (float)ws[C + c];
+  sum_g[c] = s; sum_gx[c] = sx;
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + sx : sx;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + s : s;
+}
+// backward pass 2: dx = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) [train] ; dres (+)= g ; optional mask by (x>0) for Conv->ReLU->BN
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+                                    const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
+                                    float* __restrict__ dx, int lddx, float* __restrict__ dres, int lddr, int dres_acc,
+                                    long long M, int C4, int relu, int training, int mask_input) {
+  long long total = M * C4;
+  float invM = 1.f / (float)M;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / C4; int c = (int)(i - r * C4) * 4;
+    float4 g4 = *reinterpret_cast<const float4*>(dy + r * lddy + c);
+    float g[4] = {g4.x, g4.y, g4.z, g4.w};
+    if (relu) {
+      float4 y4 = *reinterpret_cast<const float4*>(y + r * ldy + c);
+      if (!(y4.x > 0.f)) g[0] = 0.f; if (!(y4.y > 0.f)) g[1] = 0.f;
+      if (!(y4.z > 0.f)) g[2] = 0.f; if (!(y4.w > 0.f)) g[3] = 0.f;
+    }
+    if (dres) {
+      float* q = dres + r * lddr + c;
+      if (dres_acc) { float4 o = *reinterpret_cast<float4*>(q); o.x += g[0]; o.y += g[1]; o.z += g[2]; o.w += g[3]; *reinterpret_cast<float4*>(q) = o; }
+      else *reinterpret_cast<float4*>(q) = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    float4 x4 = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float rs = rstd[c + j], ga = gamma[c + j];
+      float t;
+      if (training) {
+        float xh = (xv[j] - mean[c + j]) * rs;
+        t = ga * rs * (g[j] - sum_g[c + j] * invM - xh * sum_gx[c + j] * invM);
+      } else {
+        t = ga * rs * g[j];
+      }
+      if (mask_input && !(xv[j] > 0.f)) t = 0.f;
+      o[j] = t;
+    }
+    *reinterpret_cast<float4*>(dx + r * lddx + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+// ws: double[2C]; tmp: float[2C] (sum_g, sum_gx)
+RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const float* x, int ldx,
+                       const float* mean, const float* rstd, const float* gamma,
+                       float* dx, int lddx, float* dres, int lddr, int dres_acc,
+                       float* dgamma, float* dbeta, int param_acc,
+                       long long M, int C, int relu, int training, int mask_input,
+                       double* ws, float* tmp, cudaStream_t s) {
+  RIH_REQUIRE(C % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0, "bn_bwd: needs C,ld %% 4 == 0");
+  RIH_REQUIRE(M < (1ll << 31), "bn_bwd: too many rows");
+  RIH_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, s));
+  int gx = cdiv(C, 32);
+  int target = cdiv(148 * 8, gx);
+  int rows_per_cta = max(64, cdiv(M, target));
+  dim3 grid(gx, cdiv(M, rows_per_cta)), block(32, 8);
+  bn_bwd_reduce_kernel<<<grid, block, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, (int)M, C, rows_per_cta, relu, ws);
+  if (int e = check_launch("bn_bwd_reduce")) return e;
+  bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(ws, C, dgamma, dbeta, tmp, tmp + C, param_acc);
+  if (int e = check_launch("bn_bwd_finalize")) return e;
+  long long total = M * (C / 4);
+  int g2 = (int)min((long long)148 * 16, (total + 255) / 256);
+  bn_bwd_apply_kernel<<<g2, 256, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, tmp, tmp + C, dx, lddx, dres, lddr, dres_acc,
+                                         M, C / 4, relu, training, mask_input);
+  return check_launch("bn_bwd_apply");
+}
+
+// relu backward in place/out of place for Conv->ReLU fused epilogues: dx = dy * (y > 0)
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, float* __restrict__ dx, int lddx,
+                                long long rows, int C) {
+  long long total = rows * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / C; int c = (int)(i - r * C);
+    dx[r * lddx + c] = y[r * ldy + c] > 0.f ? dy[r * lddy + c] : 0.f;
+  }
+}
+RIH_API int rih_relu_bwd(const float* dy, int lddy, const float* y, int ldy, float* dx, int lddx, long long rows, int C, cudaStream_t s) {
+  if (rows * C == 0) return 0;
+  int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
+  relu_bwd_kernel<<<grid, 256, 0, s>>>(dy, lddy, y, ldy, dx, lddx, rows, C);
+  return check_launch("relu_bwd");
+}
+
+// ============================================================== max-pool 3x3 / stride 2 / pad 1 (torchvision stem)
+// first-max-wins in (r,s) scan order, matching ATen max_pool2d; idx stores r*3+s (uint8)
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ idx,
+                                   int N, int H, int W, int C, int Ho, int Wo) {
+  long long total = (long long)N * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long long t = i / C; int ow = (int)(t % Wo); t /= Wo; int oh = (int)(t % Ho); int n = (int)(t / Ho);
+    float best = -INFINITY; int bi = -1;
+    for (int r = 0; r < 3; ++r) {
+      int ih = oh * 2 - 1 + r; if ((unsigned)ih >= (unsigned)H) continue;
+      for (int s = 0; s < 3; ++s) {
+        int iw = ow * 2 - 1 + s; if ((unsigned)iw >= (unsigned)W) continue;
+        float v = x[((size_t)(n * H + ih) * W + iw) * C + c];
+        if (bi < 0 || v > best || isnan(v)) { best = v; bi = r * 3 + s; }
+      }
+    }
+    y[i] = best; idx[i] = (unsigned char)bi;
+  }
+}
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ idx, float* __restrict__ dx,
+                                   int N, int H, int W, int C, int Ho, int Wo) {
+  long long total = (long long)N * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long long t = i / C; int iw = (int)(t % W); t /= W; int ih = (int)(t % H); int n = (int)(t / H);
+    float acc = 0.f;
+    for (int r = 0; r < 3; ++r) {
+      int a = ih + 1 - r; if (a < 0 || (a & 1)) continue; int oh = a >> 1; if (oh >= Ho) continue;
+      for (int s = 0; s < 3; ++s) {
+        int b = iw + 1 - s; if (b < 0 || (b & 1)) continue; int ow = b >> 1; if (ow >= Wo) continue;
+        size_t o = ((size_t)(n * Ho + oh) * Wo + ow) * C + c;
+        if (idx[o] == r * 3 + s) acc += dy[o];
+      }
+    }
+    dx[i] = acc;
+  }
+}
+RIH_API int rih_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int N, int H, int W, int C, cudaStream_t s) {
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  long long total = (long long)N * Ho * Wo * C;
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  maxpool_fwd_kernel<<<grid, 256, 0, s>>>(x, y, idx, N, H, W, C, Ho, Wo);
+  return check_launch("maxpool_fwd");
+}
+RIH_API int rih_maxpool3x3s2_bwd(const float* dy, const unsigned char* idx, float* dx, int N, int H, int W, int C, cudaStream_t s) {
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  long long total = (long long)N * H * W * C;
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  maxpool_bwd_kernel<<<grid, 256, 0, s>>>(dy, idx, dx, N, H, W, C, Ho, Wo);
+  return check_launch("maxpool_bwd");
+}
+
+// ============================================================== bilinear x2, align_corners=True (models/encoder.py:51)
+__device__ __forceinline__ void bil_coord(int o, float scale, int in, int& i0, int& i1, float& l1) {
+  float src = scale * (float)o;
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+  l1 = src - (float)i0;
+}
+__global__ void bilinear2x_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int N, int H, int W, int C) {
+  int Ho = 2 * H, Wo = 2 * W;
+  float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  long long total = (long long)N * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long long t = i / C; int ow = (int)(t % Wo); t /= Wo; int oh = (int)(t % Ho); int n = (int)(t / Ho);
+    int h0, h1, w0, w1; float lh, lw;
+    bil_coord(oh, sh, H, h0, h1, lh); bil_coord(ow, sw, W, w0, w1, lw);
+    float hh = 1.f - lh, ww = 1.f - lw;
+    const float* b = x + (size_t)n * H * W * ldx + c;
+    float v = hh * (ww * b[((size_t)h0 * W + w0) * ldx] + lw * b[((size_t)h0 * W + w1) * ldx]) +
+              lh * (ww * b[((size_t)h1 * W + w0) * ldx] + lw * b[((size_t)h1 * W + w1) * ldx]);
+    y[((size_t)(n * Ho + oh) * Wo + ow) * ldy + c] = v;
+  }
+}
+__global__ void bilinear2x_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx, int N, int H, int W, int C) {
+  int Ho = 2 * H, Wo = 2 * W;
+  float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  long long total = (long long)N * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long long t = i / C; int ow = (int)(t % Wo); t /= Wo; int oh = (int)(t % Ho); int n = (int)(t / Ho);
+    int h0, h1, w0, w1; float lh, lw;
+    bil_coord(oh, sh, H, h0, h1, lh); bil_coord(ow, sw, W, w0, w1, lw);
+    float hh = 1.f - lh, ww = 1.f - lw;
+    float g = dy[((size_t)(n * Ho + oh) * Wo + ow) * lddy + c];
+    float* b = dx + (size_t)n * H * W * lddx + c;
+    atomicAdd(b + ((size_t)h0 * W + w0) * lddx, hh * ww * g);
+    atomicAdd(b + ((size_t)h0 * W + w1) * lddx, hh * lw * g);
+    atomicAdd(b + ((size_t)h1 * W + w0) * lddx, lh * ww * g);
+    atomicAdd(b + ((size_t)h1 * W + w1) * lddx, lh * lw * g);
+  }
+}
+RIH_API int rih_bilinear2x_fwd(const float* x, int ldx, float* y, int ldy, int N, int H, int W, int C, cudaStream_t s) {
+  long long total = (long long)N * 4 * H * W * C;
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  bilinear2x_fwd_kernel<<<grid, 256, 0, s>>>(x, ldx, y, ldy, N, H, W, C);
+  return check_launch("bilinear2x_fwd");
+}
+// dx must be zero-initialised by the caller (scatter-add)
+RIH_API int rih_bilinear2x_bwd(const float* dy, int lddy, float* dx, int lddx, int N, int H, int W, int C, cudaStream_t s) {
+  long long total = (long long)N * 4 * H * W * C;
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  bilinear2x_bwd_kernel<<<grid, 256, 0, s>>>(dy, lddy, dx, lddx, N, H, W, C);
+  return check_launch("bilinear2x_bwd");
+}
+
+// ============================================================== global average pool [N, HW, C] -> [N, C]
+__global__ void gap_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int N, int HW, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  int n = i / C, c = i - n * C;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += x[((size_t)n * HW + p) * ldx + c];
+  y[i] = s / (float)HW;
+}
+__global__ void gap_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int lddx, int N, int HW, int C, int acc) {
+  long long total = (long long)N * HW * C;
+  float inv = 1.f / (float)HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long long t = i / C; int n = (int)(t / HW);
+    float v = dy[(size_t)n * C + c] * inv;
+    float* q = dx + t * lddx + c;
+    *q = acc ? *q + v : v;
+  }
+}
+RIH_API int rih_gap_fwd(const float* x, int ldx, float* y, int N, int HW, int C, cudaStream_t s) {
+  gap_fwd_kernel<<<cdiv((long long)N * C, 256), 256, 0, s>>>(x, ldx, y, N, HW, C);
+  return check_launch("gap_fwd");
+}
+RIH_API int rih_gap_bwd(const float* dy, float* dx, int lddx, int N, int HW, int C, int accumulate, cudaStream_t s) {
+  long long total = (long long)N * HW * C;
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  gap_bwd_kernel<<<grid, 256, 0, s>>>(dy, dx, lddx, N, HW, C, accumulate);
+  return check_launch("gap_bwd");
+}

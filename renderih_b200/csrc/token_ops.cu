@@ -1,0 +1,347 @@
+// Token-side kernels of the DualGraph decoder: LayerNorm, Chebyshev SpMM (+[x, Lx] interleave),
+// position-embedding add (+ nearest x2 vertex upsample), column sums, dropout, global-feature broadcast.
+#include "common.cuh"
+using namespace rih;
+
+// ============================================================== LayerNorm
+// reference call sites (eps 1e-6): models/model_attn/gcn.py:91-97,103-110 ; self_attn.py:20,60 ; decoder.py:91-93
+// y = LN(a (+ b)) * gamma + beta, optional ReLU.  One warp per row.
+__global__ void layernorm_fwd_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ y, int ldy, float* __restrict__ mean, float* __restrict__ rstd,
+                                     int M, int F, float eps, int relu) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < M; r += nwarps) {
+    const float* pa = a + (size_t)r * lda;
+    const float* pb = b ? b + (size_t)r * ldb : nullptr;
+    float s = 0.f;
+    for (int c = lane; c < F; c += 32) s += pa[c] + (pb ? pb[c] : 0.f);
+    float mu = warp_sum(s) / (float)F;
+    float ss = 0.f;
+    for (int c = lane; c < F; c += 32) { float d = pa[c] + (pb ? pb[c] : 0.f) - mu; ss += d * d; }
+    float rs = 1.f / sqrtf(warp_sum(ss) / (float)F + eps);
+    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+    float* py = y + (size_t)r * ldy;
+    for (int c = lane; c < F; c += 32) {
+      float v = (pa[c] + (pb ? pb[c] : 0.f) - mu) * rs * gamma[c] + beta[c];
+      py[c] = relu ? fmaxf(v, 0.f) : v;
+    }
+  }
+}
+RIH_API int rih_layernorm_fwd(const float* a, int lda, const float* b, int ldb, const float* gamma, const float* beta,
+                              float* y, int ldy, float* mean, float* rstd, int M, int F, float eps, int relu, cudaStream_t s) {
+  if (M == 0) return 0;
+  int grid = min(148 * 8, cdiv(M, 8));
+  layernorm_fwd_kernel<<<grid, 256, 0, s>>>(a, lda, b, ldb, gamma, beta, y, ldy, mean, rstd, M, F, eps, relu);
+  return check_launch("layernorm_fwd");
+}
+
+// dx = rstd * (g*gamma - mean_c(g*gamma) - xhat * mean_c(g*gamma*xhat)), g = dy * (y>0 if relu)
+// dgamma += sum_r g*xhat ; dbeta += sum_r g        (F <= 32*LN_MAXC)
+constexpr int LN_MAXC = 16;
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ a, int lda,
+                                     const float* __restrict__ b, int ldb, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     float* __restrict__ dx, int lddx, int dx_acc, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     int M, int F, int relu) {
+  int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int warp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+  int nwarps = gridDim.x * (blockDim.x >> 5);
+  float ag[LN_MAXC], ab[LN_MAXC];
+#pragma unroll
+  for (int j = 0; j < LN_MAXC; ++j) { ag[j] = 0.f; ab[j] = 0.f; }
+  for (int r = warp; r < M; r += nwarps) {
+    const float* pa = a + (size_t)r * lda;
+    const float* pb = b ? b + (size_t)r * ldb : nullptr;
+    const float* pg = dy + (size_t)r * lddy;
+    float mu = mean[r], rs = rstd[r];
+    float s1 = 0.f, s2 = 0.f;
+    float gg[LN_MAXC], xh[LN_MAXC];
+#pragma unroll
+    for (int j = 0; j < LN_MAXC; ++j) {
+      int c = lane + 32 * j;
+      gg[j] = 0.f; xh[j] = 0.f;
+      if (c < F) {
+        float x = pa[c] + (pb ? pb[c] : 0.f);
+        float h = (x - mu) * rs;
+        float g = pg[c];
+        if (relu && !(h * gamma[c] + beta[c] > 0.f)) g = 0.f;
+        ag[j] += g * h; ab[j] += g;
+        float gw = g * gamma[c];
+        gg[j] = gw; xh[j] = h;
+        s1 += gw; s2 += gw * h;
+      }
+    }
+    s1 = warp_sum(s1) / (float)F; s2 = warp_sum(s2) / (float)F;
+    float* pd = dx + (size_t)r * lddx;
+#pragma unroll
+    for (int j = 0; j < LN_MAXC; ++j) {
+      int c = lane + 32 * j;
+      if (c < F) {
+        float v = rs * (gg[j] - s1 - xh[j] * s2);
+        pd[c] = dx_acc ? pd[c] + v : v;
+      }
+    }
+  }
+  // CTA reduction of the parameter gradients, then one atomicAdd per column per CTA
+  __shared__ float sg[8][32 * LN_MAXC + 1];
+  __shared__ float sb[8][32 * LN_MAXC + 1];
+#pragma unroll
+  for (int j = 0; j < LN_MAXC; ++j) { sg[warp_in_cta][lane + 32 * j] = ag[j]; sb[warp_in_cta][lane + 32 * j] = ab[j]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    float g = 0.f, bb = 0.f;
+    for (int w = 0; w < 8; ++w) { g += sg[w][c]; bb += sb[w][c]; }
+    if (dgamma) atomicAdd(dgamma + c, g);
+    if (dbeta) atomicAdd(dbeta + c, bb);
+  }
+}
+// dgamma / dbeta are ACCUMULATED into (caller zeroes them at step start)
+RIH_API int rih_layernorm_bwd(const float* dy, int lddy, const float* a, int lda, const float* b, int ldb,
+                              const float* gamma, const float* beta, const float* mean, const float* rstd,
+                              float* dx, int lddx, int dx_acc, float* dgamma, float* dbeta, int M, int F, int relu, cudaStream_t s) {
+  RIH_REQUIRE(F <= 32 * LN_MAXC, "layernorm_bwd: F=%d exceeds %d", F, 32 * LN_MAXC);
+  if (M == 0) return 0;
+  int grid = min(148 * 2, cdiv(M, 8));
+  layernorm_bwd_kernel<<<grid, 256, 0, s>>>(dy, lddy, a, lda, b, ldb, gamma, beta, mean, rstd, dx, lddx, dx_acc, dgamma, dbeta, M, F, relu);
+  return check_launch("layernorm_bwd");
+}
+
+// ============================================================== Chebyshev K=2 basis: out[b,v,f,0] = x[b,v,f]; out[b,v,f,1] = (L x)[b,v,f]
+// reference: graph_conv_cheby, models/model_attn/gcn.py:34-69 (dense torch.mm(L, x0) at :54 and the Fin x K interleave at :61-63)
+__global__ void cheb_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                const float* __restrict__ val, float* __restrict__ out, int B, int V, int F) {
+  long long total = (long long)B * V * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F); long long t = i / F; int v = (int)(t % V); int b = (int)(t / V);
+    const float* xb = x + (size_t)b * V * ldx + f;
+    float acc = 0.f;
+    for (int e = rowptr[v]; e < rowptr[v + 1]; ++e) acc = fmaf(val[e], xb[(size_t)col[e] * ldx], acc);
+    reinterpret_cast<float2*>(out)[i] = make_float2(xb[(size_t)v * ldx], acc);
+  }
+}
+// dx[b,v,f] (+)= d[b,v,f,0] + sum_u L[u,v] d[b,u,f,1]   (CSR of L^T passed in)
+__global__ void cheb_bwd_kernel(const float* __restrict__ d, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                const float* __restrict__ val, float* __restrict__ dx, int lddx, int acc_flag, int B, int V, int F) {
+  long long total = (long long)B * V * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F); long long t = i / F; int v = (int)(t % V); int b = (int)(t / V);
+    const float* db = d + (size_t)b * V * F * 2 + 2 * f;
+    float acc = db[(size_t)v * F * 2];
+    for (int e = rowptr[v]; e < rowptr[v + 1]; ++e) acc = fmaf(val[e], db[(size_t)col[e] * F * 2 + 1], acc);
+    float* q = dx + ((size_t)b * V + v) * lddx + f;
+    *q = acc_flag ? *q + acc : acc;
+  }
+}
+RIH_API int rih_cheb_fwd(const float* x, int ldx, const int* rowptr, const int* col, const float* val, float* out,
+                         int B, int V, int F, cudaStream_t s) {
+  long long total = (long long)B * V * F;
+  if (total == 0) return 0;
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  cheb_fwd_kernel<<<grid, 256, 0, s>>>(x, ldx, rowptr, col, val, out, B, V, F);
+  return check_launch("cheb_fwd");
+}
+RIH_API int rih_cheb_bwd(const float* d, const int* rowptrT, const int* colT, const float* valT, float* dx, int lddx, int accumulate,
+                         int B, int V, int F, cudaStream_t s) {
+  long long total = (long long)B * V * F;
+  if (total == 0) return 0;
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  cheb_bwd_kernel<<<grid, 256, 0, s>>>(d, rowptrT, colT, valT, dx, lddx, accumulate, B, V, F);
+  return check_launch("cheb_bwd");
+}
+
+// ============================================================== y[b,u,:] = x[b,u/p,:] + emb[u,:]
+// reference: position_embeddings add, models/model_attn/DualGraph.py:76-80 ; graph_upsample(x,2) DualGraph.py:11-18,135-137 ;
+//            grid position embeddings, img_attn.py:57-63
+__global__ void posemb_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ emb, float* __restrict__ y, int ldy,
+                                  int B, int U, int F, int p) {
+  long long total = (long long)B * U * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F); long long t = i / F; int u = (int)(t % U); int b = (int)(t / U);
+    y[((size_t)b * U + u) * ldy + f] = x[((size_t)b * (U / p) + u / p) * ldx + f] + emb[(size_t)u * F + f];
+  }
+}
+// dx[b,v,:] = sum_{i<p} dy[b,p*v+i,:]
+__global__ void posemb_bwd_x_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx, int B, int U, int F, int p) {
+  int V = U / p;
+  long long total = (long long)B * V * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F); long long t = i / F; int v = (int)(t % V); int b = (int)(t / V);
+    float acc = 0.f;
+    for (int j = 0; j < p; ++j) acc += dy[((size_t)b * U + p * v + j) * lddy + f];
+    dx[((size_t)b * V + v) * lddx + f] = acc;
+  }
+}
+// demb[u,:] += sum_b dy[b,u,:]
+__global__ void posemb_bwd_emb_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ demb, int B, int U, int F) {
+  long long total = (long long)U * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F); int u = (int)(i / F);
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += dy[((size_t)b * U + u) * lddy + f];
+    demb[i] += acc;
+  }
+}
+RIH_API int rih_posemb_fwd(const float* x, int ldx, const float* emb, float* y, int ldy, int B, int U, int F, int p, cudaStream_t s) {
+  RIH_REQUIRE(p >= 1 && U % p == 0, "posemb_fwd: U %% p != 0");
+  long long total = (long long)B * U * F;
+  if (total == 0) return 0;
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  posemb_fwd_kernel<<<grid, 256, 0, s>>>(x, ldx, emb, y, ldy, B, U, F, p);
+  return check_launch("posemb_fwd");
+}
+RIH_API int rih_posemb_bwd(const float* dy, int lddy, float* dx, int lddx, float* demb, int B, int U, int F, int p, cudaStream_t s) {
+  RIH_REQUIRE(p >= 1 && U % p == 0, "posemb_bwd: U %% p != 0");
+  if (dx) {
+    long long total = (long long)B * (U / p) * F;
+    int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+    posemb_bwd_x_kernel<<<grid, 256, 0, s>>>(dy, lddy, dx, lddx, B, U, F, p);
+    if (int e = check_launch("posemb_bwd_x")) return e;
+  }
+  if (demb) {
+    long long total = (long long)U * F;
+    int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+    posemb_bwd_emb_kernel<<<grid, 256, 0, s>>>(dy, lddy, demb, B, U, F);
+    if (int e = check_launch("posemb_bwd_emb")) return e;
+  }
+  return 0;
+}
+
+// ============================================================== column sum: out[n] (+)= sum_m x[m,n]   (bias gradients)
+__global__ void colsum_kernel(const float* __restrict__ x, int ld, int M, int N, int rows_per_cta, float* __restrict__ out) {
+  int c = blockIdx.x * 32 + threadIdx.x;
+  int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float s = 0.f;
+  if (c < N) for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) s += x[(size_t)r * ld + c];
+  __shared__ float sh[8][33];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    for (int i = 1; i < 8; ++i) s += sh[i][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+RIH_API int rih_colsum(const float* x, int ld, int M, int N, float* out, int accumulate, cudaStream_t s) {
+  if (!accumulate) RIH_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, s));
+  if (M == 0) return 0;
+  int gx = cdiv(N, 32);
+  int target = cdiv(148 * 4, gx);
+  int rows_per_cta = max(32, cdiv(M, target));
+  dim3 grid(gx, cdiv(M, rows_per_cta)), block(32, 8);
+  colsum_kernel<<<grid, block, 0, s>>>(x, ld, M, N, rows_per_cta, out);
+  return check_launch("colsum");
+}
+
+// ============================================================== dropout (stateless counter RNG, device-resident seed)
+// mask index = row*C + col over the logical [rows, C] tensor; seed = *seed_ptr + site*const  (same map as the GEMM epilogue)
+__global__ void dropout_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, long long rows, int C,
+                               const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
+  long long total = rows * C;
+  unsigned long long seed = *seed_ptr + site * 0xD1B54A32D192ED03ull;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / C; int c = (int)(i - r * C);
+    y[r * ldy + c] = x[r * ldx + c] * dropout_scale(seed, (uint64_t)i, thresh, inv_keep);
+  }
+}
+// forward and backward are the same map (dx = dy * keep_scale)
+RIH_API int rih_dropout(const float* x, int ldx, float* y, int ldy, long long rows, int C, float p,
+                        const unsigned long long* seed_ptr, unsigned long long site, cudaStream_t s) {
+  if (rows * C == 0) return 0;
+  RIH_REQUIRE(p > 0.f && p < 1.f && seed_ptr, "dropout: p out of range or missing seed");
+  int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
+  dropout_kernel<<<grid, 256, 0, s>>>(x, ldx, y, ldy, rows, C, seed_ptr, site, dropout_thresh(p), 1.f / (1.f - p));
+  return check_launch("dropout");
+}
+// backward pre-pass of a fused GEMM epilogue  y = dropout(relu(z)) (+res):  g = dy * keep_scale * (y_pre_res > 0 if relu)
+// (y given is the stored output; only valid with relu when no residual was added)
+__global__ void epilogue_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, float* __restrict__ g, int ldg,
+                                    long long rows, int C, int relu, const unsigned long long* __restrict__ seed_ptr, unsigned long long site,
+                                    uint32_t thresh, float inv_keep) {
+  long long total = rows * C;
+  unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / C; int c = (int)(i - r * C);
+    float v = dy[r * lddy + c];
+    if (thresh) v *= dropout_scale(seed, (uint64_t)i, thresh, inv_keep);
+    if (relu && !(y[r * ldy + c] > 0.f)) v = 0.f;
+    g[r * ldg + c] = v;
+  }
+}
+RIH_API int rih_epilogue_bwd(const float* dy, int lddy, const float* y, int ldy, float* g, int ldg, long long rows, int C, int relu,
+                             float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, cudaStream_t s) {
+  if (rows * C == 0) return 0;
+  RIH_REQUIRE(dropout_p == 0.f || (seed_ptr && dropout_p < 1.f), "epilogue_bwd: dropout needs a device seed");
+  int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
+  epilogue_bwd_kernel<<<grid, 256, 0, s>>>(dy, lddy, y, ldy, g, ldg, rows, C, relu, seed_ptr, site,
+                                           dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u, dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f);
+  return check_launch("epilogue_bwd");
+}
+__global__ void seed_advance_kernel(unsigned long long* seed) { *seed = *seed * 6364136223846793005ull + 1442695040888963407ull; }
+RIH_API int rih_seed_advance(unsigned long long* seed_ptr, cudaStream_t s) {
+  seed_advance_kernel<<<1, 1, 0, s>>>(seed_ptr);
+  return check_launch("seed_advance");
+}
+
+// ============================================================== decoder entry: Lf[b,v,0:G] = g[b,:], Lf[b,v,G:G+3] = pe[v,:], + emb[v,:]
+// reference: models/decoder.py:132-135 (repeat + cat) fused with the level-0 position-embedding add (DualGraph.py:76-80)
+__global__ void gf_broadcast_fwd_kernel(const float* __restrict__ g, const float* __restrict__ pe, const float* __restrict__ emb,
+                                        float* __restrict__ y, int B, int V, int G) {
+  int F = G + 3;
+  long long total = (long long)B * V * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(i % F); long long t = i / F; int v = (int)(t % V); int b = (int)(t / V);
+    float base = f < G ? g[(size_t)b * G + f] : pe[v * 3 + (f - G)];
+    y[i] = base + emb[(size_t)v * F + f];
+  }
+}
+// dg[b,f] = sum_v dy[b,v,f] (f<G) ; demb[v,f] += sum_b dy[b,v,f]
+__global__ void gf_broadcast_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dg, int B, int V, int G) {
+  int F = G + 3;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * G) return;
+  int b = i / G, f = i - b * G;
+  float acc = 0.f;
+  for (int v = 0; v < V; ++v) acc += dy[((size_t)b * V + v) * F + f];
+  dg[i] = acc;
+}
+RIH_API int rih_gf_broadcast_fwd(const float* g, const float* pe, const float* emb, float* y, int B, int V, int G, cudaStream_t s) {
+  long long total = (long long)B * V * (G + 3);
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  gf_broadcast_fwd_kernel<<<grid, 256, 0, s>>>(g, pe, emb, y, B, V, G);
+  return check_launch("gf_broadcast_fwd");
+}
+RIH_API int rih_gf_broadcast_bwd(const float* dy, float* dg, float* demb, int B, int V, int G, cudaStream_t s) {
+  gf_broadcast_bwd_kernel<<<cdiv((long long)B * G, 256), 256, 0, s>>>(dy, dg, B, V, G);
+  if (int e = check_launch("gf_broadcast_bwd")) return e;
+  if (demb) {
+    long long total = (long long)V * (G + 3);
+    int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+    posemb_bwd_emb_kernel<<<grid, 256, 0, s>>>(dy, G + 3, demb, B, V, G + 3);
+    if (int e = check_launch("gf_broadcast_bwd_emb")) return e;
+  }
+  return 0;
+}
+
+// ============================================================== fused AdamW over a flat fp32 buffer (torch.optim.AdamW semantics)
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float pi = p[i] * (1.f - lr * wd);
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+RIH_API int rih_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                           float eps, float weight_decay, int step, float grad_scale, cudaStream_t s) {
+  if (n == 0) return 0;
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2 = 1.f - powf(beta2, (float)step);
+  int grid = (int)min((long long)148 * 16, (n + 255) / 256);
+  adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  return check_launch("adamw");
+}

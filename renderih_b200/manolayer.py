@@ -1,0 +1,122 @@
+"""B200-native drop-in for the reference's `models/manolayer.py` ManoLayer (FK + LBS), lines 100-322.
+
+Same constructor / forward contract; forward is ONE fused CUDA kernel (csrc/mano.cu).  Inputs on the CPU
+(the reference's dataset code calls the layer with CPU tensors, dataset/interhand.py:102-109) are staged to
+the GPU and the outputs are returned on the input's device -- the arithmetic always runs on the GPU.
+"""
+import ctypes
+
+import numpy as np
+import torch
+from torch.nn import Module
+
+from . import ops
+from .assets import load_mano_dict
+from ._lib import call
+
+
+def rodrigues_batch(axis):
+    """models/manolayer.py:32-48 (helper used by callers to build root rotations)."""
+    bs = axis.shape[0]
+    Imat = torch.eye(3, dtype=axis.dtype, device=axis.device).repeat(bs, 1, 1)
+    angle = torch.norm(axis, p=2, dim=1, keepdim=True) + 1e-8
+    axes = axis / angle
+    sin = torch.sin(angle).unsqueeze(2)
+    cos = torch.cos(angle).unsqueeze(2)
+    L = torch.zeros((bs, 3, 3), dtype=axis.dtype, device=axis.device)
+    L[:, 2, 1] = axes[:, 0]; L[:, 1, 2] = -axes[:, 0]
+    L[:, 0, 2] = axes[:, 1]; L[:, 2, 0] = -axes[:, 1]
+    L[:, 1, 0] = axes[:, 2]; L[:, 0, 1] = -axes[:, 2]
+    return Imat + sin * L + (1 - cos) * L.bmm(L)
+
+
+class ManoLayer(Module):
+    def __init__(self, manoPath, center_idx=9, use_pca=True, new_skel=False, device=None):
+        super().__init__()
+        self.center_idx = center_idx
+        self.use_pca = use_pca
+        self.new_skel = new_skel
+        manoData = manoPath if isinstance(manoPath, dict) else load_mano_dict(manoPath)
+        self.new_order = [0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20]
+        f32 = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32)))
+        self.register_buffer('hands_components', f32(manoData['hands_components']))
+        self.register_buffer('hands_components_inv', torch.inverse(self.hands_components))
+        jr = manoData['J_regressor']
+        jr = np.asarray(jr.todense()) if hasattr(jr, 'todense') else np.asarray(jr)
+        self.register_buffer('J_regressor', f32(jr), persistent=False)
+        self.register_buffer('J_zero', f32(manoData['J']), persistent=False)
+        self.register_buffer('weights', f32(manoData['weights']), persistent=False)
+        self.register_buffer('posedirs', f32(manoData['posedirs']), persistent=False)
+        self.register_buffer('v_template', f32(manoData['v_template']), persistent=False)
+        self.register_buffer('shapedirs', f32(manoData['shapedirs']), persistent=False)
+        self.register_buffer('hands_mean', f32(manoData['hands_mean']), persistent=False)
+        self.faces = manoData['f']
+        self.parent = [-1] + [int(manoData['kintree_table'][0, i]) for i in range(1, 16)]
+        self._parent_arr = (ctypes.c_int * 16)(*[max(p, 0) for p in self.parent])
+        self._derived = None
+        self._run_device = device
+
+    def get_faces(self):
+        return self.faces
+
+    def train(self, mode=True):   # the reference overrides these without recursing (manolayer.py:157-161)
+        self.is_train = mode
+
+    def eval(self):
+        self.train(False)
+
+    # ---- parameter conversions (manolayer.py:163-215); light host-side helpers, not on the hot path
+    def pca2axis(self, pca):
+        return pca.mm(self.hands_components[:pca.shape[1]]) + self.hands_mean
+
+    def pca2Rmat(self, pca):
+        return self.axis2Rmat(self.pca2axis(pca))
+
+    def axis2Rmat(self, axis):
+        return rodrigues_batch(axis.view(-1, 3)).view(-1, 15, 3, 3)
+
+    def axis2pca(self, axis):
+        return (axis - self.hands_mean).mm(self.hands_components_inv)
+
+    # ---- device-side constant tables (transposed for coalesced reads); rebuilt if a buffer is mutated in place
+    def _tables(self, device):
+        bufs = (self.hands_components, self.hands_mean, self.shapedirs, self.posedirs, self.v_template, self.J_regressor, self.weights)
+        key = (device,) + tuple((b._version, b.data_ptr()) for b in bufs)
+        if self._derived is None or self._derived[0] != key:
+            t = [self.hands_components.to(device).contiguous(), self.hands_mean.to(device).contiguous(),
+                 self.shapedirs.to(device).reshape(2334, 10).t().contiguous(),     # [10][2334]
+                 self.posedirs.to(device).reshape(2334, 135).t().contiguous(),     # [135][2334]
+                 self.v_template.to(device).reshape(2334).contiguous(),
+                 self.J_regressor.to(device).contiguous(), self.weights.to(device).contiguous()]
+            arr = (ctypes.c_void_p * 7)(*[x.data_ptr() for x in t])
+            self._derived = (key, t, arr)
+        return self._derived[2]
+
+    def forward(self, root_rotation, pose, shape, trans=None, scale=None):
+        in_dev = root_rotation.device
+        if in_dev.type == 'cuda':
+            dev = in_dev
+        else:
+            if not torch.cuda.is_available():
+                raise RuntimeError('renderih_b200.ManoLayer needs a CUDA device (sm_100a); there is no CPU fallback')
+            dev = torch.device(self._run_device or 'cuda')
+        f = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        R, P, S, T, C = f(root_rotation), f(pose), f(shape), f(trans), f(scale)
+        bs = R.shape[0]
+        if self.use_pca:
+            ncomps = P.shape[1]
+            assert P.dim() == 2 and ncomps <= 45
+        else:
+            ncomps = 0
+            assert tuple(P.shape[1:]) == (15, 3, 3)
+        assert S.shape == (bs, 10)
+        v = torch.empty((bs, 778, 3), device=dev, dtype=torch.float32)
+        j = torch.empty((bs, 21, 3), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            tables = self._tables(dev)
+            call('rih_mano_fwd', tables, self._parent_arr, R.data_ptr(), P.data_ptr(), int(self.use_pca), ncomps, S.data_ptr(),
+                 ops._p(T), ops._p(C), -1 if self.center_idx is None else int(self.center_idx), int(self.new_skel),
+                 v.data_ptr(), j.data_ptr(), bs, torch.cuda.current_stream(dev).cuda_stream)
+        if in_dev != dev:
+            v, j = v.to(in_dev), j.to(in_dev)
+        return v, j

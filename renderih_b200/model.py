@@ -1,0 +1,594 @@
+"""B200-native drop-in for the reference's `models.model.HandNET_GCN` (models/model.py:18-60).
+
+Same constructor contract (`load_model(cfg)`), same forward signature and 4-tuple result structure, same
+1093 state_dict keys (so released checkpoints load) -- but `forward` runs hand-written sm_100a kernels from
+librih_b200.so through `renderih_b200.ops`.  torch.nn modules are used ONLY as parameter containers (their
+own forward is never called); feature maps are NHWC row matrices [N*H*W, C], tokens are [B*V, F].
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .assets import load_model_assets
+from .config import load_cfg
+
+IMG_SIZE = 256  # dataset/dataset_utils.py:4
+
+
+class GraphCSR:
+    """Sparse rescaled Laplacian L (and L^T) on the device.  The reference densifies it (gcn.py:79-86) and calls
+    torch.mm (gcn.py:54); here it stays CSR (<= 11 nnz per row) and feeds a fused SpMM + [x, Lx] interleave."""
+
+    def __init__(self, L):
+        import scipy.sparse as sp
+        if isinstance(L, np.ndarray):
+            L = sp.csr_matrix(L)
+        L = sp.csr_matrix(L).astype(np.float32)
+        L.sort_indices()
+        LT = sp.csr_matrix(L.T)
+        LT.sort_indices()
+        self.V = L.shape[0]
+        self._host = [np.asarray(L.indptr, np.int32), np.asarray(L.indices, np.int32), np.asarray(L.data, np.float32),
+                      np.asarray(LT.indptr, np.int32), np.asarray(LT.indices, np.int32), np.asarray(LT.data, np.float32)]
+        self.device = None
+
+    def to(self, device):
+        if self.device != device:
+            t = [torch.from_numpy(a).to(device) for a in self._host]
+            self.rowptr, self.col, self.val, self.rowptr_t, self.col_t, self.val_t = t
+            self.device = device
+        return self
+
+    def dense(self):
+        import scipy.sparse as sp
+        return torch.from_numpy(sp.csr_matrix((self._host[2], self._host[1], self._host[0]), shape=(self.V, self.V)).toarray())
+
+
+def _cl(conv):
+    """Store a Conv2d weight channels_last so its memory is [Cout, R, S, Cin] (what the kernels read)."""
+    conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)
+    return conv
+
+
+# ============================================================================ encoder (models/encoder.py:21-173)
+def _conv_bn(x, conv, bn, N, H, W, training, relu=True, res=None):
+    """torchvision order Conv -> BN -> (+res) -> ReLU"""
+    k = conv.kernel_size[0]
+    y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0])
+    Ho = (H + 2 * conv.padding[0] - k) // conv.stride[0] + 1
+    y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, res=res, training=training,
+                      momentum=bn.momentum, eps=bn.eps, relu=relu)
+    return y, Ho
+
+
+def _conv_relu_bn(x, conv, bn, N, H, W, training):
+    """repo order Conv -> ReLU -> BN (models/model_zoo/__init__.py:56-82, models/encoder.py:52-54)"""
+    y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], relu=True,
+                   relu_masked_by_consumer=True)
+    return ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training=training,
+                         momentum=bn.momentum, eps=bn.eps, relu=False, mask_input=True)
+
+
+class ResNetSimple_decoder(nn.Module):
+    """models/encoder.py:21-64"""
+
+    def __init__(self, expansion=4, fDim=(256, 256, 256, 256), direction=('flat', 'up', 'up', 'up'), out_dim=3):
+        super().__init__()
+        self.models = nn.ModuleList()
+        fDim = [512 * expansion] + list(fDim)
+        self.direction = list(direction)
+        for i, d in enumerate(direction):
+            k = 1 if d == 'flat' else 3
+            layers = []
+            if d == 'up':
+                layers.append(nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True))
+            layers.append(_cl(nn.Conv2d(fDim[i], fDim[i + 1], kernel_size=k, stride=1, padding=k // 2, bias=False)))
+            layers.append(nn.ReLU(inplace=True))
+            layers.append(nn.BatchNorm2d(fDim[i + 1]))
+            self.models.append(nn.Sequential(*layers))
+        self.final_layer = _cl(nn.Conv2d(fDim[-1], out_dim, kernel_size=1, stride=1, padding=0))
+
+    def forward(self, x, N, H):
+        fmaps = []
+        for i, seq in enumerate(self.models):
+            if self.direction[i] == 'up':
+                x = ops.bilinear2x(x, N, H, H)
+                H = 2 * H
+                conv, bn = seq[1], seq[3]
+            else:
+                conv, bn = seq[0], seq[2]
+            x = _conv_relu_bn(x, conv, bn, N, H, H, self.training)
+            fmaps.append((x, H))
+        out = ops.conv2d(x, self.final_layer.weight, self.final_layer.bias, N, H, H)
+        return out, fmaps, H
+
+
+class ResNetSimple(nn.Module):
+    """models/encoder.py:67-126 (torchvision trunk used as a parameter container only)"""
+
+    def __init__(self, model_type='resnet50', fmapDim=(128, 128, 128, 128), handNum=2, heatmapDim=21):
+        super().__init__()
+        import torchvision.models as tvm
+        assert model_type in ('resnet50', 'resnet101', 'resnet152'), 'bottleneck ResNets only'
+        self.resnet = getattr(tvm, model_type)(weights=None)
+        self.expansion = 4
+        for m in self.resnet.modules():
+            if isinstance(m, nn.Conv2d):
+                _cl(m)
+        self.hms_decoder = ResNetSimple_decoder(self.expansion, fmapDim, ('flat', 'up', 'up', 'up'), heatmapDim * handNum)
+        self.dp_decoder = ResNetSimple_decoder(self.expansion, fmapDim, ('flat', 'up', 'up', 'up'), handNum + 3 * handNum)
+        self.handNum = handNum
+
+    def _bottleneck(self, blk, x, N, H):
+        tr = self.training
+        out, _ = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr)
+        out, Ho = _conv_bn(out, blk.conv2, blk.bn2, N, H, H, tr)
+        if blk.downsample is not None:
+            identity, _ = _conv_bn(x, blk.downsample[0], blk.downsample[1], N, H, H, tr, relu=False)
+        else:
+            identity = x
+        out, _ = _conv_bn(out, blk.conv3, blk.bn3, N, Ho, Ho, tr, relu=True, res=identity)
+        return out, Ho
+
+    def forward(self, img):
+        N, C, H, W = img.shape
+        assert H == W
+        r = self.resnet
+        x = ops.nchw_to_nhwc(img)
+        x, H = _conv_bn(x, r.conv1, r.bn1, N, H, H, self.training)
+        x = ops.maxpool3x3s2(x, N, H, H)
+        H = (H - 1) // 2 + 1
+        feats = []
+        for layer in (r.layer1, r.layer2, r.layer3, r.layer4):
+            for blk in layer:
+                x, H = self._bottleneck(blk, x, N, H)
+            feats.append((x, H))
+        x4, x3, x2, x1 = feats
+        img_fmaps = [x1, x2, x3, x4]
+        hms, hms_fmaps, Hh = self.hms_decoder(x1[0], N, x1[1])
+        out, dp_fmaps, _ = self.dp_decoder(x1[0], N, x1[1])
+        hms = ops.nhwc_to_nchw(hms, N, Hh, Hh)
+        mask = ops.nhwc_to_nchw(out, N, Hh, Hh, 0, self.handNum)
+        dp = ops.nhwc_to_nchw(out, N, Hh, Hh, self.handNum, out.shape[1] - self.handNum)
+        return hms, mask, dp, img_fmaps, hms_fmaps, dp_fmaps
+
+
+class resnet_mid(nn.Module):
+    """models/encoder.py:129-173"""
+
+    def __init__(self, model_type='resnet50', in_fmapDim=(128, 128, 128, 128), out_fmapDim=(256, 256, 256, 256)):
+        super().__init__()
+        self.expansion = 4
+        self.img_fmaps_dim = [512 * 4, 256 * 4, 128 * 4, 64 * 4]
+        self.convs = nn.ModuleList()
+        for i in range(len(out_fmapDim)):
+            inDim = 2 * in_fmapDim[i] + (self.img_fmaps_dim[i] if i > 0 else 0)
+            self.convs.append(nn.Sequential(_cl(nn.Conv2d(inDim, out_fmapDim[i], kernel_size=1, bias=False)),
+                                            nn.ReLU(inplace=True), nn.BatchNorm2d(out_fmapDim[i])))
+        self.global_feature_dim = 512 * 4
+        self.fmaps_dim = list(out_fmapDim)
+
+    def get_info(self):
+        return {'global_feature_dim': self.global_feature_dim, 'fmaps_dim': self.fmaps_dim}
+
+    def forward(self, img_fmaps, hms_fmaps, dp_fmaps, N):
+        x1, H1 = img_fmaps[0]
+        global_feature = ops.global_avgpool(x1, N, H1 * H1)
+        fmaps = []
+        for i, seq in enumerate(self.convs):
+            parts = [hms_fmaps[i][0], dp_fmaps[i][0]]
+            if i > 0:
+                parts.append(img_fmaps[i][0])
+            H = hms_fmaps[i][1]
+            x = ops.concat_channels(parts)
+            fmaps.append((_conv_relu_bn(x, seq[0], seq[2], N, H, H, self.training), H))
+        return global_feature, fmaps
+
+
+# ============================================================================ decoder blocks (models/model_attn/*.py)
+class GCN_ResBlock(nn.Module):
+    """models/model_attn/gcn.py:72-110 -- note norm1 is computed-and-discarded by the reference (103-104): it is a
+    dead parameter here too (kept for state_dict parity, receives no gradient)."""
+
+    def __init__(self, in_dim, out_dim, mid_dim, graph, graph_k, drop_out):
+        super().__init__()
+        assert graph_k == 2, 'Chebyshev order K=2 only (reference default utils/defaults.yaml:20)'
+        self.graph = graph
+        self.in_dim = in_dim
+        self.norm1 = nn.LayerNorm(in_dim, eps=1e-6)
+        self.fc1 = nn.Linear(in_dim * graph_k, mid_dim)
+        self.norm2 = nn.LayerNorm(out_dim, eps=1e-6)
+        self.fc2 = nn.Linear(mid_dim * graph_k, out_dim)
+        self.shortcut = nn.Linear(in_dim, out_dim)
+        self.norm3 = nn.LayerNorm(out_dim, eps=1e-6)
+        self.p = drop_out
+
+    def forward(self, x, B, V, relu_out):
+        g = self.graph.to(x.device)
+        p = self.p if self.training else 0.0
+        c = ops.cheb(x, g, B, V)
+        x1 = ops.linear(c, self.fc1.weight, self.fc1.bias)
+        x1 = ops.layernorm(x1, self.norm2.weight, self.norm2.bias, relu=True)
+        c = ops.cheb(x1, g, B, V)
+        x1 = ops.linear(c, self.fc2.weight, self.fc2.bias, p_drop=p)
+        x2 = ops.linear(x, self.shortcut.weight, self.shortcut.bias)
+        return ops.layernorm(x1, self.norm3.weight, self.norm3.bias, b=x2, relu=relu_out)
+
+
+class GraphLayer(nn.Module):
+    """models/model_attn/gcn.py:113-138"""
+
+    def __init__(self, in_dim, out_dim, graph, graph_k, graph_layer_num, drop_out):
+        super().__init__()
+        self.GCN_blocks = nn.ModuleList([GCN_ResBlock(in_dim, out_dim, out_dim, graph, graph_k, drop_out)])
+        for _ in range(graph_layer_num - 1):
+            self.GCN_blocks.append(GCN_ResBlock(out_dim, out_dim, out_dim, graph, graph_k, drop_out))
+
+    def forward(self, x, B, V):
+        n = len(self.GCN_blocks)
+        for i, blk in enumerate(self.GCN_blocks):
+            x = blk(x, B, V, relu_out=(i != n - 1))
+        return x
+
+
+class MLP_res_block(nn.Module):
+    """models/model_attn/self_attn.py:17-33"""
+
+    def __init__(self, in_dim, hid_dim, dropout):
+        super().__init__()
+        self.layer_norm = nn.LayerNorm(in_dim, eps=1e-6)
+        self.fc1 = nn.Linear(in_dim, hid_dim)
+        self.fc2 = nn.Linear(hid_dim, in_dim)
+        self.p = dropout
+
+    def forward(self, x):
+        p = self.p if self.training else 0.0
+        h = ops.layernorm(x, self.layer_norm.weight, self.layer_norm.bias)
+        h = ops.linear(h, self.fc1.weight, self.fc1.bias, relu=True, p_drop=p)
+        return ops.linear(h, self.fc2.weight, self.fc2.bias, res=x, p_drop=p)
+
+
+class SelfAttn(nn.Module):
+    """models/model_attn/self_attn.py:36-85"""
+
+    def __init__(self, f_dim, hid_dim=None, n_heads=4, dropout=0.1):
+        super().__init__()
+        d = f_dim // n_heads
+        hid_dim = hid_dim or f_dim
+        self.n_heads, self.f_dim = n_heads, f_dim
+        self.w_qs = nn.Linear(f_dim, n_heads * d)
+        self.w_ks = nn.Linear(f_dim, n_heads * d)
+        self.w_vs = nn.Linear(f_dim, n_heads * d)
+        self.layer_norm = nn.LayerNorm(f_dim, eps=1e-6)
+        self.fc = nn.Linear(n_heads * d, f_dim)
+        self.ff = MLP_res_block(f_dim, hid_dim, dropout)
+        self.p = dropout
+
+    def forward(self, x, B, S):
+        p = self.p if self.training else 0.0
+        xn = ops.layernorm(x, self.layer_norm.weight, self.layer_norm.bias)
+        q = ops.linear(xn, self.w_qs.weight, self.w_qs.bias)
+        k = ops.linear(xn, self.w_ks.weight, self.w_ks.bias)
+        v = ops.linear(xn, self.w_vs.weight, self.w_vs.bias)
+        o = ops.attention(q, k, v, B, self.n_heads, S, S, p_drop=p)
+        x = ops.linear(o, self.fc.weight, self.fc.bias, res=x, p_drop=p)
+        return self.ff(x)
+
+    def forward_query_subset(self, verts_f, extra_f, B, V, E):
+        """SelfAttn over cat([verts (V), extra (E)]) keeping only the V vertex rows (img_attn.py:86-90):
+        rows >= V are only ever used as keys/values, so Q / fc / MLP run on the vertex rows alone -- exact."""
+        p = self.p if self.training else 0.0
+        vn = ops.layernorm(verts_f, self.layer_norm.weight, self.layer_norm.bias)
+        en = ops.layernorm(extra_f, self.layer_norm.weight, self.layer_norm.bias)
+        xn = ops.concat_rows(vn, en, B, V, E)
+        q = ops.linear(vn, self.w_qs.weight, self.w_qs.bias)
+        k = ops.linear(xn, self.w_ks.weight, self.w_ks.bias)
+        v = ops.linear(xn, self.w_vs.weight, self.w_vs.bias)
+        o = ops.attention(q, k, v, B, self.n_heads, V, V + E, p_drop=p)
+        x = ops.linear(o, self.fc.weight, self.fc.bias, res=verts_f, p_drop=p)
+        return self.ff(x)
+
+
+class img_feat_to_grid(nn.Module):
+    """models/model_attn/img_attn.py:37-67"""
+
+    def __init__(self, img_size, img_f_dim, grid_size, grid_f_dim, n_heads, dropout):
+        super().__init__()
+        self.img_size, self.grid_size, self.grid_f_dim = img_size, grid_size, grid_f_dim
+        self.position_embeddings = nn.Embedding(grid_size * grid_size, grid_f_dim)
+        patch = img_size // grid_size
+        self.proj = _cl(nn.Conv2d(img_f_dim, grid_f_dim, kernel_size=patch, stride=patch))
+        self.self_attn = SelfAttn(grid_f_dim, n_heads=n_heads, hid_dim=grid_f_dim, dropout=dropout)
+
+    def forward(self, img, B):
+        x, H = img
+        assert H == self.img_size
+        G = self.grid_size * self.grid_size
+        g = ops.conv2d(x, self.proj.weight, self.proj.bias, B, H, H, stride=self.proj.stride[0], pad=0, relu=True)
+        g = ops.posemb(g, self.position_embeddings.weight, B, G, 1)
+        return self.self_attn(g, B, G)
+
+
+class img_attn(nn.Module):
+    """models/model_attn/img_attn.py:70-92"""
+
+    def __init__(self, verts_f_dim, img_f_dim, n_heads, dropout):
+        super().__init__()
+        self.fc = nn.Linear(img_f_dim, verts_f_dim)
+        self.Attn = SelfAttn(verts_f_dim, n_heads=n_heads, hid_dim=verts_f_dim, dropout=dropout)
+
+    def forward(self, verts_f, img_f, B, V, G):
+        img_f = ops.linear(img_f, self.fc.weight, self.fc.bias)
+        return self.Attn.forward_query_subset(verts_f, img_f, B, V, G)
+
+
+class img_ex(nn.Module):
+    """models/model_attn/img_attn.py:95-115"""
+
+    def __init__(self, img_size, img_f_dim, grid_size, grid_f_dim, verts_f_dim, n_heads, dropout):
+        super().__init__()
+        self.encoder = img_feat_to_grid(img_size, img_f_dim, grid_size, grid_f_dim, n_heads, dropout)
+        self.attn = img_attn(verts_f_dim, grid_f_dim, n_heads, dropout)
+        self.G = grid_size * grid_size
+
+    def forward(self, img, verts_f, B, V):
+        grid = self.encoder(img, B)
+        return self.attn(verts_f, grid, B, V, self.G)
+
+
+class inter_attn(nn.Module):
+    """models/model_attn/inter_attn.py:36-123 (w_qs/w_ks/w_vs/fc are shared between the two hands)"""
+
+    def __init__(self, f_dim, n_heads=4, dropout=0.1):
+        super().__init__()
+        self.L_self_attn_layer = SelfAttn(f_dim, n_heads=n_heads, hid_dim=f_dim, dropout=dropout)
+        self.R_self_attn_layer = SelfAttn(f_dim, n_heads=n_heads, hid_dim=f_dim, dropout=dropout)
+        d = f_dim // n_heads
+        self.n_heads = n_heads
+        self.w_qs = nn.Linear(f_dim, n_heads * d)
+        self.w_ks = nn.Linear(f_dim, n_heads * d)
+        self.w_vs = nn.Linear(f_dim, n_heads * d)
+        self.fc = nn.Linear(n_heads * d, f_dim)
+        self.layer_norm1 = nn.LayerNorm(f_dim, eps=1e-6)
+        self.layer_norm2 = nn.LayerNorm(f_dim, eps=1e-6)
+        self.ffL = MLP_res_block(f_dim, f_dim, dropout)
+        self.ffR = MLP_res_block(f_dim, f_dim, dropout)
+        self.p = dropout
+
+    def forward(self, Lf, Rf, B, V):
+        p = self.p if self.training else 0.0
+        Lf = self.L_self_attn_layer(Lf, B, V)
+        Rf = self.R_self_attn_layer(Rf, B, V)
+        L2 = ops.layernorm(Lf, self.layer_norm1.weight, self.layer_norm1.bias)
+        R2 = ops.layernorm(Rf, self.layer_norm2.weight, self.layer_norm2.bias)
+        Lq = ops.linear(L2, self.w_qs.weight, self.w_qs.bias)
+        Lk = ops.linear(L2, self.w_ks.weight, self.w_ks.bias)
+        Lv = ops.linear(L2, self.w_vs.weight, self.w_vs.bias)
+        Rq = ops.linear(R2, self.w_qs.weight, self.w_qs.bias)
+        Rk = ops.linear(R2, self.w_ks.weight, self.w_ks.bias)
+        Rv = ops.linear(R2, self.w_vs.weight, self.w_vs.bias)
+        H = self.n_heads
+        # reference order of the two dropout1 draws: attn_R2L then attn_L2R (inter_attn.py:101-102)
+        feat_R2L = ops.attention(Lq, Rk, Rv, B, H, V, V, p_drop=p)
+        feat_L2R = ops.attention(Rq, Lk, Lv, B, H, V, V, p_drop=p)
+        xR = ops.linear(feat_L2R, self.fc.weight, self.fc.bias, res=Rf, p_drop=p)
+        xL = ops.linear(feat_R2L, self.fc.weight, self.fc.bias, res=Lf, p_drop=p)
+        return self.ffL(xL), self.ffR(xR)
+
+
+class DualGraphLayer(nn.Module):
+    """models/model_attn/DualGraph.py:21-91 (the position-embedding add is fused into the caller's entry kernel)"""
+
+    def __init__(self, verts_in_dim, verts_out_dim, graph_L, graph_R, graph_k, graph_layer_num, img_size, img_f_dim,
+                 grid_size, grid_f_dim, n_heads, dropout):
+        super().__init__()
+        self.verts_num = graph_L.V
+        self.verts_in_dim = verts_in_dim
+        self.position_embeddings = nn.Embedding(self.verts_num, verts_in_dim)
+        self.graph_left = GraphLayer(verts_in_dim, verts_out_dim, graph_L, graph_k, graph_layer_num, dropout)
+        self.graph_right = GraphLayer(verts_in_dim, verts_out_dim, graph_R, graph_k, graph_layer_num, dropout)
+        self.img_ex_left = img_ex(img_size, img_f_dim, grid_size, grid_f_dim, verts_out_dim, n_heads, dropout)
+        self.img_ex_right = img_ex(img_size, img_f_dim, grid_size, grid_f_dim, verts_out_dim, n_heads, dropout)
+        self.attn = inter_attn(verts_out_dim, n_heads=n_heads, dropout=dropout)
+
+    def forward(self, Lf, Rf, img_f, B):
+        """Lf/Rf already carry `+ position_embeddings` (added by the entry / upsample kernels)."""
+        V = self.verts_num
+        Lf = self.graph_left(Lf, B, V)
+        Rf = self.graph_right(Rf, B, V)
+        Lf = self.img_ex_left(img_f, Lf, B, V)
+        Rf = self.img_ex_right(img_f, Rf, B, V)
+        return self.attn(Lf, Rf, B, V)
+
+
+class DualGraph(nn.Module):
+    """models/model_attn/DualGraph.py:94-139"""
+
+    def __init__(self, verts_in_dim, verts_out_dim, graphs_L, graphs_R, graph_k, graph_layer_num, img_size, img_f_dim,
+                 grid_size, grid_f_dim, n_heads, dropout):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        for i in range(len(verts_in_dim)):
+            self.layers.append(DualGraphLayer(verts_in_dim[i], verts_out_dim[i], graphs_L[i], graphs_R[i], graph_k[i],
+                                              graph_layer_num[i], img_size[i], img_f_dim[i], grid_size[i], grid_f_dim[i],
+                                              n_heads, dropout))
+
+    def forward(self, Lf, Rf, img_f_list, B):
+        for i, layer in enumerate(self.layers):
+            if i > 0:  # graph_upsample(x, 2) of the previous level + this level's position embeddings
+                emb = layer.position_embeddings.weight
+                Lf = ops.posemb(Lf, emb, B, layer.verts_num, 2)
+                Rf = ops.posemb(Rf, emb, B, layer.verts_num, 2)
+            Lf, Rf = layer(Lf, Rf, img_f_list[i], B)
+        return Lf, Rf
+
+
+class GCN_vert_convert:
+    """models/model_zoo/__init__.py:85-96"""
+
+    def __init__(self, vertex_num, graph_perm_reverse, graph_perm):
+        self.graph_perm_reverse = np.asarray(graph_perm_reverse)[:vertex_num]
+        self.graph_perm = list(graph_perm)
+
+    def vert_to_GCN(self, x):
+        return x[:, self.graph_perm]
+
+    def GCN_to_vert(self, x):
+        return x[:, self.graph_perm_reverse]
+
+
+class decoder(nn.Module):
+    """models/decoder.py:29-174"""
+
+    def __init__(self, global_feature_dim, f_in_Dim, f_out_Dim, gcn_in_dim, gcn_out_dim, graph_k, graph_layer_num,
+                 left_graph_dict, right_graph_dict, vertex_num=778, dense_coor=None, num_attn_heads=4,
+                 upsample_weight=None, dropout=0.05):
+        super().__init__()
+        f_in_Dim = list(f_in_Dim)[:-1]
+        gd = {'left': left_graph_dict, 'right': right_graph_dict}
+        graph_L = {}
+        for side in ('left', 'right'):
+            Ls = list(gd[side]['coarsen_graphs_L'])
+            Ls.reverse()                      # decoder.py:53-54 (we reverse a copy; the reference mutates the dict)
+            graph_L[side] = Ls
+        self.vNum_in = graph_L['left'][0].shape[0]
+        self.vNum_out = graph_L['left'][2].shape[0]
+        self.vNum_all = graph_L['left'][-1].shape[0]
+        self.vNum_mano = vertex_num
+        self.gf_dim = global_feature_dim
+        self.gcn_in_dim, self.gcn_out_dim = list(gcn_in_dim), list(gcn_out_dim)
+        self.register_buffer('dense_coor', torch.from_numpy(np.asarray(dense_coor)).float())
+        self.converter = {s: GCN_vert_convert(self.vNum_mano, gd[s]['graph_perm_reverse'], gd[s]['graph_perm'])
+                          for s in ('left', 'right')}
+        graphs = {s: [GraphCSR(L) for L in graph_L[s][:3]] for s in ('left', 'right')}
+        self.dual_gcn = DualGraph(self.gcn_in_dim, self.gcn_out_dim, graphs['left'], graphs['right'],
+                                  [graph_k] * 3, [graph_layer_num] * 3, [8, 16, 32], f_in_Dim, [8, 8, 8], list(f_out_Dim),
+                                  num_attn_heads, dropout)
+        self.gf_layer_left = nn.Sequential(nn.Linear(self.gf_dim, self.gcn_in_dim[0] - 3),
+                                           nn.LayerNorm(self.gcn_in_dim[0] - 3, eps=1e-6))
+        self.gf_layer_right = nn.Sequential(nn.Linear(self.gf_dim, self.gcn_in_dim[0] - 3),
+                                            nn.LayerNorm(self.gcn_in_dim[0] - 3, eps=1e-6))
+        self.unsample_layer = nn.Linear(self.vNum_out, self.vNum_mano, bias=False)
+        self.coord_head = nn.Linear(self.gcn_out_dim[-1], 3)
+        self.avg_head = nn.Linear(self.vNum_out, 1)
+        self.params_head = nn.Linear(self.gcn_out_dim[-1], 3)
+        if upsample_weight is not None:
+            self.unsample_layer.weight.data.copy_(torch.as_tensor(upsample_weight).float())
+        self._pe_cache = None
+        self._idx_cache = {}
+
+    def get_upsample_weight(self):
+        return self.unsample_layer.weight.data
+
+    def get_converter(self):
+        return self.converter
+
+    def _hand_pe(self):
+        """decoder.get_hand_pe (decoder.py:118-126): input independent -> computed once per dense_coor version."""
+        dc = self.dense_coor
+        key = (dc._version, dc.device, dc.data_ptr())
+        if self._pe_cache is None or self._pe_cache[0] != key:
+            host = dc.detach().float().cpu() * 2 - 1
+            pes = []
+            for side in ('left', 'right'):
+                pe = host[self.converter[side].graph_perm]                       # vert_to_GCN
+                p = pe.shape[0] // self.vNum_in
+                pe = pe.view(self.vNum_in, p, 3).mean(dim=1)                     # graph_avg_pool(p)
+                pes.append(pe.contiguous().to(dc.device))
+            self._pe_cache = (key, pes)
+        return self._pe_cache[1]
+
+    def _rev_idx(self, side, device):
+        k = (side, device)
+        if k not in self._idx_cache:
+            self._idx_cache[k] = torch.from_numpy(np.asarray(self.converter[side].graph_perm_reverse, np.int32)).to(device)
+        return self._idx_cache[k]
+
+    def forward(self, x, fmaps):
+        assert x.shape[1] == self.gf_dim
+        fmaps = fmaps[:-1]
+        B = x.shape[0]
+        pel, per = self._hand_pe()
+        emb0 = self.dual_gcn.layers[0].position_embeddings.weight
+        feats = []
+        for seq, pe in ((self.gf_layer_left, pel), (self.gf_layer_right, per)):
+            g = ops.linear(x, seq[0].weight, seq[0].bias)
+            g = ops.layernorm(g, seq[1].weight, seq[1].bias)
+            feats.append(ops.gf_broadcast(g, pe, emb0, B, self.vNum_in))
+        Lf, Rf = self.dual_gcn(feats[0], feats[1], fmaps, B)
+
+        scale, trans2d, verts3d, verts2d = {}, {}, {}, {}
+        result = {'verts3d': {}, 'verts2d': {}}
+        for side, f in (('left', Lf), ('right', Rf)):
+            s, t, v3c, v2c, v3, v2 = ops.decoder_tail(
+                f, self.avg_head.weight.view(-1), self.avg_head.bias, self.params_head.weight, self.params_head.bias,
+                self.coord_head.weight, self.coord_head.bias, self.unsample_layer.weight, B, self.vNum_out, float(IMG_SIZE))
+            scale[side], trans2d[side] = s, t
+            verts3d[side], verts2d[side] = v3c, v2c
+            result['verts3d'][side], result['verts2d'][side] = v3, v2
+        paramsDict = {'scale': scale, 'trans2d': trans2d}
+        handDictList = [{'verts3d': verts3d, 'verts2d': verts2d}]
+        otherInfo = {'verts3d_MANO_list': {'left': [], 'right': []}, 'verts2d_MANO_list': {'left': [], 'right': []}}
+        div = self.vNum_all // self.vNum_out
+        for side in ('left', 'right'):
+            idx = self._rev_idx(side, x.device)
+            otherInfo['verts3d_MANO_list'][side].append(ops.gather_rows(verts3d[side], idx, div))
+            otherInfo['verts2d_MANO_list'][side].append(ops.gather_rows(verts2d[side], idx, div))
+        return result, paramsDict, handDictList, otherInfo
+
+
+# ============================================================================ model (models/model.py:18-60)
+class HandNET_GCN(nn.Module):
+    def __init__(self, encoder, mid_model, decoder):
+        super().__init__()
+        self.encoder = encoder
+        self.mid_model = mid_model
+        self.decoder = decoder
+
+    def forward(self, img):
+        if not (isinstance(img, torch.Tensor) and img.is_cuda):
+            raise RuntimeError('renderih_b200.HandNET_GCN runs only on CUDA (sm_100a) tensors; there is no CPU fallback')
+        if img.dtype != torch.float32:
+            raise RuntimeError('renderih_b200.HandNET_GCN expects float32 images')
+        ops.seed_state.begin_forward()
+        if self.training:
+            ops.seed_state.advance(img.device)
+        N = img.shape[0]
+        hms, mask, dp, img_fmaps, hms_fmaps, dp_fmaps = self.encoder(img)
+        global_feature, fmaps = self.mid_model(img_fmaps, hms_fmaps, dp_fmaps, N)
+        result, paramsDict, handDictList, otherInfo = self.decoder(global_feature, fmaps)
+        if hms is not None:
+            otherInfo['hms'] = hms
+        if mask is not None:
+            otherInfo['mask'] = mask
+        if dp is not None:
+            otherInfo['dense'] = dp
+        return result, paramsDict, handDictList, otherInfo
+
+
+def load_encoder(cfg):
+    et = cfg.MODEL.ENCODER_TYPE
+    if 'resnet' in et:
+        enc = ResNetSimple(model_type=et, fmapDim=[128, 128, 128, 128], handNum=2, heatmapDim=21)
+        mid = resnet_mid(model_type=et, in_fmapDim=[128, 128, 128, 128], out_fmapDim=cfg.MODEL.DECONV_DIMS)
+        return enc, mid
+    raise NotImplementedError('encoder %r: HRNet-w48 (BASELINE config 5) is the next scope row, see DESIGN.md' % et)
+
+
+def load_decoder(cfg, encoder_info, assets=None, asset_root=None):
+    a = assets if assets is not None else load_model_assets(cfg, asset_root)
+    return decoder(global_feature_dim=encoder_info['global_feature_dim'], f_in_Dim=encoder_info['fmaps_dim'],
+                   f_out_Dim=cfg.MODEL.IMG_DIMS, gcn_in_dim=cfg.MODEL.GCN_IN_DIM, gcn_out_dim=cfg.MODEL.GCN_OUT_DIM,
+                   graph_k=cfg.MODEL.graph_k, graph_layer_num=cfg.MODEL.graph_layer_num, vertex_num=778,
+                   dense_coor=a['dense_coor'], left_graph_dict=a['left_graph'], right_graph_dict=a['right_graph'],
+                   num_attn_heads=4, upsample_weight=a['upsample'], dropout=cfg.TRAIN.dropout)
+
+
+def load_model(cfg=None, assets=None, asset_root=None):
+    """`models.model.load_model(cfg)` (models/model.py:40-60).  cfg: path | CfgNode-like | None (defaults)."""
+    if cfg is None or isinstance(cfg, str):
+        cfg = load_cfg(cfg)
+    encoder, mid_model = load_encoder(cfg)
+    dec = load_decoder(cfg, mid_model.get_info(), assets=assets, asset_root=asset_root)
+    return HandNET_GCN(encoder, mid_model, dec)

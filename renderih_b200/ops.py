@@ -1,0 +1,691 @@
+"""Autograd operators over the C-ABI CUDA kernels (raw pointers + current CUDA stream).
+
+Every operator here launches hand-written sm_100a kernels from librih_b200.so; torch is used only for
+memory (caching allocator), autograd bookkeeping and streams.  There is no CPU / eager fallback: tensors
+must be fp32 CUDA tensors, otherwise a RuntimeError is raised.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+call = _lib.call
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _check(t, name='tensor'):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise RuntimeError('renderih_b200: %s must be a float32 CUDA tensor (got %s on %s); there is no CPU fallback'
+                           % (name, t.dtype, t.device))
+    return t
+
+
+def _rows(t):
+    """2-D row-major view contract: [rows, C], unit column stride, row stride = ld."""
+    _check(t)
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise RuntimeError('renderih_b200: expected a [rows, C] tensor with unit column stride, got shape %s strides %s'
+                           % (tuple(t.shape), t.stride()))
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+# ----------------------------------------------------------------------------- dropout seed (device resident)
+class _SeedState:
+    """Device-resident base seed advanced once per step (so CUDA-graph replays draw fresh masks)."""
+    def __init__(self):
+        self.tensors = {}
+        self.site = 0
+
+    def ptr(self, device):
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in self.tensors:
+            self.tensors[key] = torch.tensor([0x243F6A8885A308D3 & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=device)
+        return self.tensors[key].data_ptr()
+
+    def manual_seed(self, seed, device):
+        self.ptr(device)
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        self.tensors[key].fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
+
+    def advance(self, device):
+        call('rih_seed_advance', self.ptr(device), _stream())
+
+    def begin_forward(self):
+        self.site = 0
+
+    def next_site(self):
+        self.site += 1
+        return self.site
+
+
+seed_state = _SeedState()
+
+
+# ----------------------------------------------------------------------------- Linear
+class LinearFn(Function):
+    """y = dropout(relu(x @ w^T + b)) + res  -- torch.nn.Linear call sites of models/model_attn/*.py, models/decoder.py"""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu, res, p_drop, site):
+        x = _rows(x); _check(w, 'weight')
+        M, K = x.shape
+        N = w.shape[0]
+        assert w.shape[1] == K and w.stride(1) == 1
+        assert not (relu and res is not None)
+        y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+        if res is not None:
+            res = _rows(res)
+        sp = seed_state.ptr(x.device) if p_drop > 0 else None
+        call('rih_linear_fwd', _p(x), _ld(x), _p(w), w.stride(0), _p(b), _p(y), N, M, N, K, int(relu), 0,
+             _p(res), _ld(res) if res is not None else 0, float(p_drop), sp, site, _stream())
+        ctx.save_for_backward(x, w, y if (relu or p_drop > 0) else None)
+        ctx.meta = (relu, p_drop, site, b is not None, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        relu, p_drop, site, has_b, has_res = ctx.meta
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        M, K = x.shape
+        N = w.shape[0]
+        s = _stream()
+        g = dy
+        if relu or p_drop > 0:
+            g = torch.empty((M, N), device=dy.device, dtype=torch.float32)
+            call('rih_epilogue_bwd', _p(dy), _ld(dy), _p(y), N, _p(g), N, M, N, int(relu), float(p_drop),
+                 seed_state.ptr(dy.device) if p_drop > 0 else None, site, s)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), device=dy.device, dtype=torch.float32)
+            call('rih_linear_dgrad', _p(g), _ld(g), _p(w), w.stride(0), _p(dx), K, M, N, K, 0, s)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((N, K), device=dy.device, dtype=torch.float32)
+            call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(dw), K, M, N, K, 0, s)
+        if has_b and ctx.needs_input_grad[2]:
+            db = torch.empty((N,), device=dy.device, dtype=torch.float32)
+            call('rih_colsum', _p(g), _ld(g), M, N, _p(db), 0, s)
+        dres = dy if (has_res and ctx.needs_input_grad[4]) else None
+        return dx, dw, db, None, dres, None, None
+
+
+def linear(x, w, b=None, relu=False, res=None, p_drop=0.0):
+    site = seed_state.next_site() if p_drop > 0 else 0
+    return LinearFn.apply(x, w, b, relu, res, p_drop, site)
+
+
+# ----------------------------------------------------------------------------- LayerNorm
+class LayerNormFn(Function):
+    """y = LN(a (+ b)) (relu)  -- nn.LayerNorm(eps=1e-6) sites, e.g. models/model_attn/gcn.py:105,110"""
+
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, eps, relu):
+        a = _rows(a)
+        if b is not None:
+            b = _rows(b)
+        M, F = a.shape
+        y = torch.empty((M, F), device=a.device, dtype=torch.float32)
+        mean = torch.empty((M,), device=a.device, dtype=torch.float32)
+        rstd = torch.empty((M,), device=a.device, dtype=torch.float32)
+        call('rih_layernorm_fwd', _p(a), _ld(a), _p(b), _ld(b) if b is not None else 0, _p(gamma), _p(beta), _p(y), F,
+             _p(mean), _p(rstd), M, F, float(eps), int(relu), _stream())
+        ctx.save_for_backward(a, b, gamma, beta, mean, rstd)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b, gamma, beta, mean, rstd = ctx.saved_tensors
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        M, F = a.shape
+        dx = torch.empty((M, F), device=dy.device, dtype=torch.float32)
+        dgamma = torch.zeros((F,), device=dy.device, dtype=torch.float32)
+        dbeta = torch.zeros((F,), device=dy.device, dtype=torch.float32)
+        call('rih_layernorm_bwd', _p(dy), _ld(dy), _p(a), _ld(a), _p(b), _ld(b) if b is not None else 0, _p(gamma), _p(beta),
+             _p(mean), _p(rstd), _p(dx), F, 0, _p(dgamma), _p(dbeta), M, F, int(ctx.relu), _stream())
+        return dx, (dx if b is not None else None), dgamma, dbeta, None, None
+
+
+def layernorm(a, gamma, beta, b=None, eps=1e-6, relu=False):
+    return LayerNormFn.apply(a, b, gamma, beta, eps, relu)
+
+
+# ----------------------------------------------------------------------------- Chebyshev basis (K=2)
+class ChebFn(Function):
+    """[x, Lx] interleaved along features -- graph_conv_cheby, models/model_attn/gcn.py:34-69"""
+
+    @staticmethod
+    def forward(ctx, x, graph, B, V):
+        x = _rows(x)
+        F = x.shape[1]
+        assert x.shape[0] == B * V
+        out = torch.empty((B * V, 2 * F), device=x.device, dtype=torch.float32)
+        call('rih_cheb_fwd', _p(x), _ld(x), _p(graph.rowptr), _p(graph.col), _p(graph.val), _p(out), B, V, F, _stream())
+        ctx.graph, ctx.dims = graph, (B, V, F)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        B, V, F = ctx.dims
+        g = ctx.graph
+        d = d.contiguous()
+        dx = torch.empty((B * V, F), device=d.device, dtype=torch.float32)
+        call('rih_cheb_bwd', _p(d), _p(g.rowptr_t), _p(g.col_t), _p(g.val_t), _p(dx), F, 0, B, V, F, _stream())
+        return dx, None, None, None
+
+
+def cheb(x, graph, B, V):
+    return ChebFn.apply(x, graph, B, V)
+
+
+# ----------------------------------------------------------------------------- position embedding (+ nearest vertex upsample)
+class PosEmbFn(Function):
+    """y[b,u] = x[b,u//p] + emb[u]  -- DualGraph.py:76-80 (+ graph_upsample :135-137), img_attn.py:57-63"""
+
+    @staticmethod
+    def forward(ctx, x, emb, B, U, p):
+        x = _rows(x)
+        F = x.shape[1]
+        assert x.shape[0] == B * (U // p) and emb.shape == (U, F) and emb.is_contiguous()
+        y = torch.empty((B * U, F), device=x.device, dtype=torch.float32)
+        call('rih_posemb_fwd', _p(x), _ld(x), _p(emb), _p(y), F, B, U, F, p, _stream())
+        ctx.dims = (B, U, F, p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, U, F, p = ctx.dims
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        dx = demb = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((B * (U // p), F), device=dy.device, dtype=torch.float32)
+        if ctx.needs_input_grad[1]:
+            demb = torch.zeros((U, F), device=dy.device, dtype=torch.float32)
+        call('rih_posemb_bwd', _p(dy), _ld(dy), _p(dx), F, _p(demb), B, U, F, p, _stream())
+        return dx, demb, None, None, None
+
+
+def posemb(x, emb, B, U, p=1):
+    return PosEmbFn.apply(x, emb, B, U, p)
+
+
+# ----------------------------------------------------------------------------- attention core
+class AttnFn(Function):
+    """softmax(Q K^T / sqrt(d)) V with probability dropout -- self_attn.py:63-76, inter_attn.py:90-105"""
+
+    @staticmethod
+    def forward(ctx, q, k, v, B, H, Sq, Sk, p_drop, site):
+        q, k, v = _rows(q), _rows(k), _rows(v)
+        HD = q.shape[1]
+        d = HD // H
+        assert q.shape[0] == B * Sq and k.shape[0] == B * Sk and v.shape[0] == B * Sk
+        o = torch.empty((B * Sq, HD), device=q.device, dtype=torch.float32)
+        lse = torch.empty((B * H * Sq,), device=q.device, dtype=torch.float32)
+        scale = 1.0 / (d ** 0.5)
+        sp = seed_state.ptr(q.device) if p_drop > 0 else None
+        call('rih_attn_fwd', _p(q), Sq * _ld(q), _ld(q), _p(k), Sk * _ld(k), _ld(k), _p(v), Sk * _ld(v), _ld(v),
+             _p(o), Sq * HD, HD, _p(lse), B, H, Sq, Sk, d, scale, float(p_drop), sp, site, _stream())
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.meta = (B, H, Sq, Sk, d, scale, p_drop, site)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        B, H, Sq, Sk, d, scale, p_drop, site = ctx.meta
+        do = _rows(do.contiguous() if do.stride(-1) != 1 else do)
+        HD = H * d
+        dq = torch.empty((B * Sq, HD), device=do.device, dtype=torch.float32)
+        dk = torch.empty((B * Sk, HD), device=do.device, dtype=torch.float32)
+        dv = torch.empty((B * Sk, HD), device=do.device, dtype=torch.float32)
+        sp = seed_state.ptr(do.device) if p_drop > 0 else None
+        call('rih_attn_bwd', _p(q), Sq * _ld(q), _ld(q), _p(k), Sk * _ld(k), _ld(k), _p(v), Sk * _ld(v), _ld(v),
+             _p(o), Sq * HD, HD, _p(do), Sq * _ld(do), _ld(do), _p(lse),
+             _p(dq), Sq * HD, HD, _p(dk), Sk * HD, HD, _p(dv), Sk * HD, HD,
+             B, H, Sq, Sk, d, scale, float(p_drop), sp, site, _stream())
+        return dq, dk, dv, None, None, None, None, None, None
+
+
+def attention(q, k, v, B, H, Sq, Sk, p_drop=0.0):
+    site = seed_state.next_site() if p_drop > 0 else 0
+    return AttnFn.apply(q, k, v, B, H, Sq, Sk, p_drop, site)
+
+
+# ----------------------------------------------------------------------------- dropout (stand-alone)
+class DropoutFn(Function):
+    @staticmethod
+    def forward(ctx, x, p, site):
+        x = _rows(x)
+        M, C = x.shape
+        y = torch.empty((M, C), device=x.device, dtype=torch.float32)
+        call('rih_dropout', _p(x), _ld(x), _p(y), C, M, C, float(p), seed_state.ptr(x.device), site, _stream())
+        ctx.meta = (p, site)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, site = ctx.meta
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        M, C = dy.shape
+        dx = torch.empty((M, C), device=dy.device, dtype=torch.float32)
+        call('rih_dropout', _p(dy), _ld(dy), _p(dx), C, M, C, float(p), seed_state.ptr(dy.device), site, _stream())
+        return dx, None, None
+
+
+def dropout(x, p):
+    if p <= 0:
+        return x
+    return DropoutFn.apply(x, p, seed_state.next_site())
+
+
+# ----------------------------------------------------------------------------- decoder entry / tail
+class GfBroadcastFn(Function):
+    """Lf[b,v,:] = cat(g[b,:], pe[v,:]) + emb[v,:]  -- models/decoder.py:132-135 + DualGraph.py:76-80"""
+
+    @staticmethod
+    def forward(ctx, g, pe, emb, B, V):
+        g = _check(g).contiguous()
+        G = g.shape[1]
+        y = torch.empty((B * V, G + 3), device=g.device, dtype=torch.float32)
+        call('rih_gf_broadcast_fwd', _p(g), _p(pe), _p(emb), _p(y), B, V, G, _stream())
+        ctx.dims = (B, V, G)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, V, G = ctx.dims
+        dy = dy.contiguous()
+        dg = torch.empty((B, G), device=dy.device, dtype=torch.float32)
+        demb = torch.zeros((V, G + 3), device=dy.device, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+        call('rih_gf_broadcast_bwd', _p(dy), _p(dg), _p(demb), B, V, G, _stream())
+        return dg, None, demb, None, None
+
+
+def gf_broadcast(g, pe, emb, B, V):
+    return GfBroadcastFn.apply(g, pe, emb, B, V)
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+class TailFn(Function):
+    """avg_head/params_head/coord_head/unsample_layer/projection_batch -- models/decoder.py:139-159"""
+
+    @staticmethod
+    def forward(ctx, Lf, avg_w, avg_b, par_w, par_b, coord_w, coord_b, U, B, V, img):
+        Lf = _rows(Lf)
+        F = Lf.shape[1]
+        Nv = U.shape[0]
+        dev = Lf.device
+        prm = torch.empty((B, 3), device=dev); temp = torch.empty((B, F), device=dev)
+        v3c = torch.empty((B, V, 3), device=dev); v2c = torch.empty((B, V, 2), device=dev)
+        v3 = torch.empty((B, Nv, 3), device=dev); v2 = torch.empty((B, Nv, 2), device=dev)
+        params = [avg_w, avg_b, par_w, par_b, coord_w, coord_b, U]
+        for t in params:
+            assert t.is_contiguous()
+        call('rih_tail_fwd', _ptr_array(params), _p(Lf), _ld(Lf), B, V, F, Nv, float(img), _p(prm), _p(temp), _p(v3c), _p(v2c),
+             _p(v3), _p(v2), _stream())
+        ctx.save_for_backward(Lf, avg_w, avg_b, par_w, par_b, coord_w, coord_b, U, prm, temp, v3c, v3)
+        ctx.dims = (B, V, F, Nv, img)
+        scale = prm[:, 0]
+        trans = prm[:, 1:]
+        return scale, trans, v3c, v2c, v3, v2
+
+    @staticmethod
+    def backward(ctx, d_scale, d_trans, d_v3c, d_v2c, d_v3, d_v2):
+        Lf, avg_w, avg_b, par_w, par_b, coord_w, coord_b, U, prm, temp, v3c, v3 = ctx.saved_tensors
+        B, V, F, Nv, img = ctx.dims
+        dev = Lf.device
+
+        def c(t):
+            return None if t is None else t.contiguous()
+        d_scale, d_trans, d_v3c, d_v2c, d_v3, d_v2 = map(c, (d_scale, d_trans, d_v3c, d_v2c, d_v3, d_v2))
+        params = [avg_w, avg_b, par_w, par_b, coord_w, coord_b, U]
+        grads = []
+        for i, t in enumerate(params):
+            grads.append(torch.zeros_like(t) if ctx.needs_input_grad[1 + i] else None)
+        dLf = torch.empty((B * V, F), device=dev, dtype=torch.float32)
+        call('rih_tail_bwd', _ptr_array(params), _ptr_array(grads), _p(Lf), _ld(Lf), B, V, F, Nv, float(img), _p(prm), _p(temp),
+             _p(v3c), _p(v3), _p(d_scale), _p(d_trans), _p(d_v3c), _p(d_v2c), _p(d_v3), _p(d_v2), _p(dLf), F, _stream())
+        return (dLf,) + tuple(grads) + (None, None, None)
+
+
+def decoder_tail(Lf, avg_w, avg_b, par_w, par_b, coord_w, coord_b, U, B, V, img):
+    return TailFn.apply(Lf, avg_w, avg_b, par_w, par_b, coord_w, coord_b, U, B, V, img)
+
+
+class GatherRowsFn(Function):
+    """y[b,i,:] = x[b, idx[i]//div, :] -- graph_upsample(p) + GCN_to_vert, models/decoder.py:165-172"""
+
+    @staticmethod
+    def forward(ctx, x, idx, div):
+        x = _check(x).contiguous()
+        B, Vin, C = x.shape
+        Vout = idx.numel()
+        y = torch.empty((B, Vout, C), device=x.device, dtype=torch.float32)
+        call('rih_gather_rows', _p(x), _p(idx), _p(y), B, Vin, Vout, C, div, _stream())
+        ctx.idx, ctx.dims = idx, (B, Vin, Vout, C, div)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, Vin, Vout, C, div = ctx.dims
+        dy = dy.contiguous()
+        dx = torch.zeros((B, Vin, C), device=dy.device, dtype=torch.float32)
+        call('rih_scatter_rows_add', _p(dy), _p(ctx.idx), _p(dx), B, Vin, Vout, C, div, _stream())
+        return dx, None, None
+
+
+def gather_rows(x, idx, div=1):
+    return GatherRowsFn.apply(x, idx, div)
+
+
+# ----------------------------------------------------------------------------- image side (NHWC rows)
+def _geom(N, H, W, Cin, Cout, R, S, stride, pad, ldx, ldy):
+    Ho = (H + 2 * pad - R) // stride + 1
+    Wo = (W + 2 * pad - S) // stride + 1
+    return (ctypes.c_int * 13)(N, H, W, Cin, Ho, Wo, Cout, R, S, stride, pad, ldx, ldy), Ho, Wo
+
+
+def _w_phys(w):
+    """Conv2d weight [Cout,Cin,R,S] must be channels_last so that memory is [Cout,R,S,Cin]."""
+    if w.dim() != 4 or not w.permute(0, 2, 3, 1).is_contiguous():
+        raise RuntimeError('renderih_b200: conv weight must be a channels_last [Cout,Cin,R,S] tensor')
+    return w
+
+
+class Conv2dFn(Function):
+    """NHWC conv (+bias)(+relu) -- nn.Conv2d sites of models/encoder.py, torchvision resnet, img_attn.py:48"""
+
+    @staticmethod
+    def forward(ctx, x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer):
+        x = _rows(x); _w_phys(_check(w, 'weight'))
+        Cout, Cin, R, S = w.shape
+        assert x.shape == (N * H * W, Cin), (x.shape, N, H, W, Cin)
+        g, Ho, Wo = _geom(N, H, W, Cin, Cout, R, S, stride, pad, _ld(x), Cout)
+        y = torch.empty((N * Ho * Wo, Cout), device=x.device, dtype=torch.float32)
+        call('rih_conv2d_fwd', _p(x), _p(w), _p(b), _p(y), g, int(relu), _stream())
+        need_y = relu and not relu_masked_by_consumer
+        ctx.save_for_backward(x, w, y if need_y else None)
+        ctx.meta = (N, H, W, stride, pad, need_y, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        N, H, W, stride, pad, need_y, has_b = ctx.meta
+        Cout, Cin, R, S = w.shape
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        s = _stream()
+        if need_y:
+            g_ = torch.empty_like(y)
+            call('rih_relu_bwd', _p(dy), _ld(dy), _p(y), Cout, _p(g_), Cout, y.shape[0], Cout, s)
+            dy = g_
+        g, Ho, Wo = _geom(N, H, W, Cin, Cout, R, S, stride, pad, Cin, _ld(dy))
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((N * H * W, Cin), device=dy.device, dtype=torch.float32)
+            call('rih_conv2d_dgrad', _p(dy), _p(w), _p(dx), g, 0, s)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            g2, _, _ = _geom(N, H, W, Cin, Cout, R, S, stride, pad, _ld(x), _ld(dy))
+            call('rih_conv2d_wgrad', _p(dy), _p(x), _p(dw), g2, 0, s)
+        if has_b and ctx.needs_input_grad[2]:
+            db = torch.empty((Cout,), device=dy.device, dtype=torch.float32)
+            call('rih_colsum', _p(dy), _ld(dy), dy.shape[0], Cout, _p(db), 0, s)
+        return dx, dw, db, None, None, None, None, None, None, None
+
+
+def conv2d(x, w, b, N, H, W, stride=1, pad=0, relu=False, relu_masked_by_consumer=False):
+    return Conv2dFn.apply(x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer)
+
+
+class BatchNormFn(Function):
+    """BatchNorm2d over NHWC rows (+residual)(+relu); training uses per-rank batch statistics (no SyncBN)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, rmean, rvar, res, training, momentum, eps, relu, mask_input):
+        x = _rows(x)
+        M, C = x.shape
+        dev = x.device
+        mean = torch.empty((C,), device=dev); rstd = torch.empty((C,), device=dev)
+        s = _stream()
+        if training:
+            ws = torch.empty((2 * C,), device=dev, dtype=torch.float64)
+            call('rih_bn_stats', _p(x), _ld(x), M, C, float(eps), float(momentum), _p(ws), _p(mean), _p(rstd), _p(rmean), _p(rvar), s)
+        else:
+            call('rih_bn_eval_prep', _p(rmean), _p(rvar), C, float(eps), _p(mean), _p(rstd), s)
+        y = torch.empty((M, C), device=dev, dtype=torch.float32)
+        if res is not None:
+            res = _rows(res)
+        call('rih_bn_apply', _p(x), _ld(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(res), _ld(res) if res is not None else 0,
+             _p(y), C, M, C, int(relu), s)
+        ctx.save_for_backward(x, gamma, mean, rstd, y if relu else None)
+        ctx.meta = (training, relu, mask_input, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd, y = ctx.saved_tensors
+        training, relu, mask_input, has_res = ctx.meta
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        M, C = x.shape
+        dev = dy.device
+        dx = torch.empty((M, C), device=dev)
+        dres = torch.empty((M, C), device=dev) if (has_res and ctx.needs_input_grad[5]) else None
+        dgamma = torch.empty((C,), device=dev); dbeta = torch.empty((C,), device=dev)
+        ws = torch.empty((2 * C,), device=dev, dtype=torch.float64)
+        tmp = torch.empty((2 * C,), device=dev)
+        call('rih_bn_bwd', _p(dy), _ld(dy), _p(y), C, _p(x), _ld(x), _p(mean), _p(rstd), _p(gamma),
+             _p(dx), C, _p(dres), C, 0, _p(dgamma), _p(dbeta), 0, M, C, int(relu), int(training), int(mask_input),
+             _p(ws), _p(tmp), _stream())
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
+
+
+def batchnorm(x, gamma, beta, rmean, rvar, res=None, training=True, momentum=0.1, eps=1e-5, relu=False, mask_input=False):
+    return BatchNormFn.apply(x, gamma, beta, rmean, rvar, res, training, momentum, eps, relu, mask_input)
+
+
+class MaxPoolFn(Function):
+    """3x3 / stride 2 / pad 1 max-pool of the torchvision stem (NHWC)."""
+
+    @staticmethod
+    def forward(ctx, x, N, H, W):
+        x = _check(x).contiguous()
+        C = x.shape[1]
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((N * Ho * Wo, C), device=x.device)
+        idx = torch.empty((N * Ho * Wo, C), device=x.device, dtype=torch.uint8)
+        call('rih_maxpool3x3s2_fwd', _p(x), _p(y), idx.data_ptr(), N, H, W, C, _stream())
+        ctx.save_for_backward(idx)
+        ctx.dims = (N, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        N, H, W, C = ctx.dims
+        dy = dy.contiguous()
+        dx = torch.empty((N * H * W, C), device=dy.device)
+        call('rih_maxpool3x3s2_bwd', _p(dy), idx.data_ptr(), _p(dx), N, H, W, C, _stream())
+        return dx, None, None, None
+
+
+def maxpool3x3s2(x, N, H, W):
+    return MaxPoolFn.apply(x, N, H, W)
+
+
+class Bilinear2xFn(Function):
+    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) -- models/encoder.py:51"""
+
+    @staticmethod
+    def forward(ctx, x, N, H, W):
+        x = _rows(x)
+        C = x.shape[1]
+        y = torch.empty((N * 4 * H * W, C), device=x.device)
+        call('rih_bilinear2x_fwd', _p(x), _ld(x), _p(y), C, N, H, W, C, _stream())
+        ctx.dims = (N, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, C = ctx.dims
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        dx = torch.zeros((N * H * W, C), device=dy.device)
+        call('rih_bilinear2x_bwd', _p(dy), _ld(dy), _p(dx), C, N, H, W, C, _stream())
+        return dx, None, None, None
+
+
+def bilinear2x(x, N, H, W):
+    return Bilinear2xFn.apply(x, N, H, W)
+
+
+class GapFn(Function):
+    """AdaptiveAvgPool2d(1)+Flatten -- models/encoder.py:153-156,166"""
+
+    @staticmethod
+    def forward(ctx, x, N, HW):
+        x = _rows(x)
+        C = x.shape[1]
+        y = torch.empty((N, C), device=x.device)
+        call('rih_gap_fwd', _p(x), _ld(x), _p(y), N, HW, C, _stream())
+        ctx.dims = (N, HW, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, HW, C = ctx.dims
+        dy = dy.contiguous()
+        dx = torch.empty((N * HW, C), device=dy.device)
+        call('rih_gap_bwd', _p(dy), _p(dx), C, N, HW, C, 0, _stream())
+        return dx, None, None
+
+
+def global_avgpool(x, N, HW):
+    return GapFn.apply(x, N, HW)
+
+
+class ConcatFn(Function):
+    """channel concat of NHWC row tensors -- torch.cat(dim=1) in resnet_mid.forward, models/encoder.py:169-171"""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        M = xs[0].shape[0]
+        widths = [x.shape[1] for x in xs]
+        C = sum(widths)
+        y = torch.empty((M, C), device=xs[0].device)
+        off = 0
+        s = _stream()
+        for x in xs:
+            x = _rows(x)
+            call('rih_copy2d', _p(x), _ld(x), y.data_ptr() + 4 * off, C, M, x.shape[1], 0, s)
+            off += x.shape[1]
+        ctx.widths = widths
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        outs = []
+        off = 0
+        for w in ctx.widths:
+            outs.append(dy[:, off:off + w])
+            off += w
+        return tuple(outs)
+
+
+def concat_channels(xs):
+    return ConcatFn.apply(*xs)
+
+
+class ConcatRowsFn(Function):
+    """per-batch token concat: y[b] = cat(x1[b] (V1 rows), x2[b] (V2 rows)) -- img_attn.py:86"""
+
+    @staticmethod
+    def forward(ctx, x1, x2, B, V1, V2):
+        x1, x2 = _rows(x1), _rows(x2)
+        F = x1.shape[1]
+        y = torch.empty((B * (V1 + V2), F), device=x1.device)
+        s = _stream()
+        # view y as [B, (V1+V2)*F] and copy the [B, V1*F] / [B, V2*F] blocks (sources must be contiguous)
+        x1c, x2c = x1.contiguous(), x2.contiguous()
+        call('rih_copy2d', _p(x1c), V1 * F, _p(y), (V1 + V2) * F, B, V1 * F, 0, s)
+        call('rih_copy2d', _p(x2c), V2 * F, y.data_ptr() + 4 * V1 * F, (V1 + V2) * F, B, V2 * F, 0, s)
+        ctx.dims = (B, V1, V2, F)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, V1, V2, F = ctx.dims
+        d3 = dy.contiguous().view(B, V1 + V2, F)
+        d1 = torch.empty((B * V1, F), device=dy.device)
+        d2 = torch.empty((B * V2, F), device=dy.device)
+        s = _stream()
+        call('rih_copy2d', _p(d3), (V1 + V2) * F, _p(d1), V1 * F, B, V1 * F, 0, s)
+        call('rih_copy2d', d3.data_ptr() + 4 * V1 * F, (V1 + V2) * F, _p(d2), V2 * F, B, V2 * F, 0, s)
+        return d1, d2, None, None, None
+
+
+def concat_rows(x1, x2, B, V1, V2):
+    return ConcatRowsFn.apply(x1, x2, B, V1, V2)
+
+
+class NchwToNhwcFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _check(x).contiguous()
+        N, C, H, W = x.shape
+        y = torch.empty((N * H * W, C), device=x.device)
+        call('rih_nchw_to_nhwc', _p(x), _p(y), N, C, H * W, C, C, _stream())
+        ctx.dims = (N, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, H, W = ctx.dims
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        dx = torch.empty((N, C, H, W), device=dy.device)
+        call('rih_nhwc_to_nchw', _p(dy), _p(dx), N, C, H * W, _ld(dy), 0, _stream())
+        return dx
+
+
+def nchw_to_nhwc(x):
+    return NchwToNhwcFn.apply(x)
+
+
+class NhwcToNchwFn(Function):
+    @staticmethod
+    def forward(ctx, x, N, H, W, c_off, C):
+        x = _rows(x)
+        y = torch.empty((N, C, H, W), device=x.device)
+        call('rih_nhwc_to_nchw', _p(x), _p(y), N, C, H * W, _ld(x), c_off, _stream())
+        ctx.dims = (N, H, W, c_off, C, x.shape[1])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, c_off, C, Ctot = ctx.dims
+        dy = dy.contiguous()
+        dx = torch.zeros((N * H * W, Ctot), device=dy.device)
+        call('rih_nchw_to_nhwc', _p(dy), dx.data_ptr() + 4 * c_off, N, C, H * W, C, Ctot, _stream())
+        return dx, None, None, None, None, None
+
+
+def nhwc_to_nchw(x, N, H, W, c_off=0, C=None):
+    return NhwcToNchwFn.apply(x, N, H, W, c_off, x.shape[1] if C is None else C)

@@ -1,0 +1,111 @@
+"""Pin the CPU oracle (oracle/model_ref.py, oracle/mano_ref.py) to the golden vectors produced by the UNMODIFIED
+reference (oracle/make_golden.py).  CPU only.  Tolerances are float32 round-off of differently associated ops."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures, mano_ref, model_ref
+from renderih_b200 import assets as rih_assets
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+RTOL = 2e-5   # relative to the tensor's max magnitude
+
+
+def rel_err(a, b):
+    a, b = torch.as_tensor(a).detach().double(), torch.as_tensor(b).detach().double()
+    return float(((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).detach())
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return torch.load(os.path.join(GOLD, 'model_synth_b2.pt'), weights_only=False)
+
+
+@pytest.fixture(scope='module')
+def setup(gold):
+    from renderih_b200.model import load_model
+    a = rih_assets.synthetic_assets(0)
+    tmpl = load_model(assets=a).state_dict()
+    sd = fixtures.init_state_dict(tmpl)
+    assert fixtures.checksum(sd) == gold['weights_sha256'], 'deterministic weight init drifted from the golden run'
+    return a, sd
+
+
+def flat(out):
+    result, params, hlist, other = out
+    d = {}
+    for side in ('left', 'right'):
+        d['verts3d_' + side] = result['verts3d'][side]; d['verts2d_' + side] = result['verts2d'][side]
+        d['scale_' + side] = params['scale'][side]; d['trans2d_' + side] = params['trans2d'][side]
+        d['v3c_' + side] = hlist[0]['verts3d'][side]; d['v2c_' + side] = hlist[0]['verts2d'][side]
+        d['v3list_' + side] = other['verts3d_MANO_list'][side][0]; d['v2list_' + side] = other['verts2d_MANO_list'][side][0]
+    for k in ('hms', 'mask', 'dense'):
+        d[k + '_sub'] = other[k][:, :, ::8, ::8]; d[k + '_mean'] = other[k].mean(dim=(2, 3))
+    return d
+
+
+def test_oracle_eval_forward_matches_reference_golden(gold, setup):
+    a, sd = setup
+    sd = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        out = flat(model_ref.model_forward(sd, model_ref.prepare_assets(a), fixtures.make_image(gold['batch']), training=False))
+    for k, v in gold['eval'].items():
+        assert out[k].shape == v.shape, k
+        assert rel_err(out[k], v) < RTOL, (k, rel_err(out[k], v))
+
+
+def test_oracle_train_forward_backward_matches_reference_golden(gold, setup):
+    a, sd = setup
+    sd = {k: v.clone() for k, v in sd.items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and 'running_' not in k and k not in ('decoder.dense_coor', 'decoder.unsample_layer.weight'):
+            v.requires_grad_(True)
+    out = model_ref.model_forward(sd, model_ref.prepare_assets(a), fixtures.make_image(gold['batch']), training=True, dropout=0.0)
+    fo = flat(out)
+    for k, v in gold['train']['out'].items():
+        assert rel_err(fo[k], v) < RTOL, (k, rel_err(fo[k], v))
+    la = fixtures.make_loss_assets(a, rih_assets.synthetic_mano(0, 'left'), rih_assets.synthetic_mano(0, 'right'))
+    loss = model_ref.calc_loss_GCN(out, fixtures.make_labels(gold['batch']), la)
+    assert abs(float(loss) - gold['train']['loss']) / gold['train']['loss'] < 1e-5
+    loss.backward()
+    assert rel_err(sd['encoder.resnet.bn1.running_mean'], gold['train']['bn1_running_mean']) < RTOL
+    assert rel_err(sd['encoder.resnet.bn1.running_var'], gold['train']['bn1_running_var']) < RTOL
+    for k in gold['train']['no_grad_keys']:
+        g = sd[k].grad
+        assert g is None or float(g.abs().max()) == 0.0, k
+    worst = 0.0
+    for k, g in gold['train']['grads'].items():
+        mine = sd[k].grad
+        assert mine is not None, k
+        if k.endswith('w_ks.bias'):
+            # a key bias shifts every score of a query row equally: softmax-invariant, the true gradient is 0
+            # and both sides hold only round-off noise
+            assert float(mine.norm()) < 1e-3 * (1.0 + float(sd[k.replace('w_ks.bias', 'w_qs.bias')].grad.norm())), k
+            continue
+        e = abs(float(mine.norm()) - g['norm']) / max(g['norm'], 1e-6)
+        worst = max(worst, e)
+        assert e < 2e-3, (k, e)
+        if 'full' in g and g['norm'] > 1e-3:
+            assert rel_err(mine, g['full']) < 2e-3, k
+
+
+def test_mano_oracle_matches_reference_golden():
+    mg = torch.load(os.path.join(GOLD, 'mano_synth.pt'), weights_only=False)
+    inp = fixtures.make_mano_inputs(5)
+    root = mano_ref.rodrigues(inp['axis'].numpy())
+    assert np.abs(root - mg['rodrigues'].numpy()).max() < 1e-6
+    for case in mg['cases']:
+        c = case['cfg']
+        m = rih_assets.synthetic_mano(0, case['side'])
+        m = dict(m); m['J_regressor'] = np.asarray(m['J_regressor'].todense())
+        if c['use_pca']:
+            pose = inp['pose_pca'][:, :c['ncomps']].numpy()
+        else:
+            pose = mano_ref.rodrigues(inp['pose_axis'].numpy().reshape(-1, 3)).reshape(-1, 15, 3, 3)
+        tr, sc = (inp['trans'].numpy(), inp['scale'].numpy()) if c['ts'] else (None, None)
+        v, j = mano_ref.mano_forward(m, root, pose, inp['shape'].numpy(), tr, sc, use_pca=c['use_pca'],
+                                     center_idx=c['center_idx'], new_skel=c['new_skel'])
+        assert np.abs(v - case['v'].numpy()).max() < 2e-6, case['cfg']
+        assert np.abs(j - case['j'].numpy()).max() < 2e-6, case['cfg']
