@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Benchmark of the RenderIH hot path on B200: images/sec of one training step (forward + calc_loss_GCN + backward +
+AdamW, + one NCCL gradient all-reduce when N > 1) at batch 64 per GPU, 256x256 synthetic images (BASELINE.json configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W            # ours (torchrun launches N ranks for N > 1)
+    python bench.py --impl reference ...                     # the reference algorithm's CPU port on the host cores
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = device-timed images/s with inputs resident in
+HBM, e2e = same step driven through the public API from pinned HOST buffers (H2D copy of every batch + D2H loss read),
+roofline = the dominant kernel timed alone with CUDA events, cpu_baseline = the oracle port on a bounded CPU sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_IMG_FWD_BWD = 50.450e9   # FlopCounterMode on the reference, ResNet50 cfg
+FLOPS_PER_IMG_FWD = 17.721e9
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='images per GPU (reference TRAIN.BATCH_SIZE)')
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--gemm-mode', default='simt', choices=['simt', 'tf32', 'tf32x3'], help='arithmetic of 1x1-conv / Linear GEMMs')
+    ap.add_argument('--cpu-batch', type=int, default=4, help='bounded CPU sample size for cpu_baseline / --impl reference')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return {'hbm_gbs': p['hbm_gbs'], 'tflops': p['bf16_tflops'], 'tflops_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                'src': 'measured (MEASURED_PEAKS.json)'}
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'tflops': 1590.0, 'tflops_sustained': 1400.0, 'src': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_port_step_time(batch, steps=1, warmup=0):
+    """The reference algorithm's CPU port (oracle/model_ref.py): forward + calc_loss_GCN + backward, fp32, all host threads."""
+    import torch
+    from oracle import fixtures, model_ref
+    from renderih_b200 import assets as A
+    from renderih_b200.model import load_model
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    a = A.synthetic_assets(0)
+    sd = fixtures.init_state_dict(load_model(assets=a).state_dict())
+    for k, v in sd.items():
+        if v.is_floating_point() and 'running_' not in k and k not in ('decoder.dense_coor', 'decoder.unsample_layer.weight'):
+            v.requires_grad_(True)
+    Ap = model_ref.prepare_assets(a)
+    la = fixtures.make_loss_assets(a, A.synthetic_mano(0, 'left'), A.synthetic_mano(0, 'right'))
+    img, labels = fixtures.make_image(batch), fixtures.make_labels(batch)
+    times = []
+    for i in range(warmup + steps):
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        out = model_ref.model_forward(sd, Ap, img, training=True, dropout=0.05)
+        loss = model_ref.calc_loss_GCN(out, labels, la)
+        loss.backward()
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    return sum(times) / len(times), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    t, cores = cpu_port_step_time(args.cpu_batch, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    v = args.cpu_batch / t
+    line = {'impl': 'reference', 'metric': 'images/sec fwd+bwd (calc_loss_GCN) @256x256', 'value': v, 'unit': 'images/s',
+            'n_gpus': args.gpus, 'steps': max(1, args.steps), 'warmup': min(1, args.warmup), 'ms_per_step': t * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'HandNET_GCN ResNet50 cfg, fwd+calc_loss_GCN+bwd, CPU sample batch %d of the batch-64 workload' % args.cpu_batch},
+            'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                             'sample': 'batch %d fwd+bwd, oracle/model_ref.py on torch CPU fp32, %d threads' % (args.cpu_batch, cores)},
+            'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def dominant_kernel_roofline(torch, batch, pk):
+    """Time the single most expensive kernel of the step alone: the 3x3 128->128 conv at 64x64 (2.42 GF/img fwd)."""
+    from renderih_b200 import ops
+    N, H, C = batch, 64, 128
+    x = torch.randn(N * H * H, C, device='cuda')
+    w = (torch.randn(C, C, 3, 3, device='cuda') * 0.03).contiguous(memory_format=torch.channels_last)
+    for _ in range(3):
+        ops.conv2d(x, w, None, N, H, H, stride=1, pad=1)
+    torch.cuda.synchronize()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.conv2d(x, w, None, N, H, H, stride=1, pad=1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * N * H * H * C * 9 * C
+    ach = flops / (ms * 1e-3) / 1e12
+    return {'bound': 'tensor', 'kernel': 'conv3x3 128->128 @64x64 (gemm_simt_kernel<128,128,ConvFwdA>)', 'achieved': ach, 'peak': pk['tflops'],
+            'unit': 'TFLOP/s', 'frac': ach / pk['tflops'], 'traffic': None, 'ms_per_launch': ms,
+            'algorithmic_flops_per_launch': flops, 'peak_source': pk['src'] + ' bf16 dense burst'}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device: there is no CPU fallback for the product path'
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from renderih_b200 import _lib, assets as A
+    from renderih_b200.config import load_cfg
+    from renderih_b200.loss import GraphLoss, calc_loss_GCN
+    from renderih_b200.model import load_model
+    from renderih_b200.train import TrainStep
+    _lib.load()
+    from renderih_b200 import ops as _ops
+    _ops.set_gemm_mode(args.gemm_mode, args.gemm_mode)
+    cfg = load_cfg()
+    a = A.synthetic_assets(0)
+    torch.manual_seed(cfg.SEED)
+    model = load_model(cfg, assets=a).cuda().train()          # train mode: batch-stat BN, dropout 0.05 (reference defaults)
+    model.decoder.unsample_layer.weight.requires_grad_(False)   # MODEL.freeze_upsample
+    B = args.batch
+    g = torch.Generator().manual_seed(cfg.SEED + rank)
+    host_imgs = [torch.randn(B, 3, 256, 256, generator=g).pin_memory() for _ in range(2)]
+    lab = {k: (torch.randn(*s, generator=g) * 0.05).cuda() for k, s in (('v3d_l', (B, 778, 3)), ('v3d_r', (B, 778, 3)), ('root_rel', (B, 3)))}
+    lab.update({k: (torch.rand(B, 778, 2, generator=g) * 256).cuda() for k in ('v2d_l', 'v2d_r')})
+    ml, mr = A.synthetic_mano(0, 'left'), A.synthetic_mano(0, 'right')
+    jl = torch.from_numpy(__import__('numpy').asarray(ml['J_regressor'].todense(), dtype='float32'))
+    jr = torch.from_numpy(__import__('numpy').asarray(mr['J_regressor'].todense(), dtype='float32'))
+    gl, gr = GraphLoss(jl, ml['f'], 4, 'cuda'), GraphLoss(jr, mr['f'], 4, 'cuda')
+    conv = model.decoder.converter
+    z = torch.zeros(B, 21, 3, device='cuda')
+
+    def loss_fn(out):
+        return calc_loss_GCN(cfg, 0, gl, gr, conv['left'], conv['right'], out[0], out[1], out[2], out[3], None, None, None,
+                             lab['v2d_l'], z[..., :2], lab['v2d_r'], z[..., :2], lab['v3d_l'], z, lab['v3d_r'], z, lab['root_rel'], 256)[0]
+
+    step = TrainStep(model, loss_fn, host_imgs[0].cuda(), lr=cfg.TRAIN.LR, weight_decay=cfg.TRAIN.weight_decay, use_graph=not args.no_graph)
+    c0 = _lib.CALLS[0]
+    step._eager()
+    torch.cuda.synchronize()
+    calls_per_step = _lib.CALLS[0] - c0
+    if not args.no_graph:
+        step.capture(warmup=2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for i in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(lambda i: step(), args.steps)                       # inputs already resident in HBM
+    losses = []
+
+    def e2e_step(i):
+        loss = step(host_imgs[i % len(host_imgs)])                       # H2D of the batch from pinned memory, every step
+        losses.append(float(loss))                                       # D2H read of the step's result
+
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    roof = dominant_kernel_roofline(torch, B, pk)
+    total_imgs = B * world
+    value = total_imgs / (ms_dev * 1e-3)
+    e2e = total_imgs / (ms_e2e * 1e-3)
+    line = {'metric': 'images/sec fwd+bwd @batch64 256x256 (training step: fwd + calc_loss_GCN + bwd + AdamW%s)' % (' + NCCL grad all-reduce' if world > 1 else ''),
+            'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_dev,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if args.gemm_mode == 'simt' else 'tf32 (1x1 conv / Linear GEMMs on tcgen05, fp32 accumulate; rest f32)', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE.json configs[2]: HandNET_GCN ResNet50 cfg, batch %d/GPU, 256x256, train mode (batch-stat BN, dropout 0.05), '
+                                   'random-init weights, synthetic graph/MANO assets' % B,
+                       'global_batch': total_imgs, 'parallelism': 'dp%d' % world, 'cuda_graph': not args.no_graph,
+                       'l2': 'per-step working set (activations, several GB) >> 126 MB L2; no explicit flush needed',
+                       'algorithmic_gflop_per_image': FLOPS_PER_IMG_FWD_BWD / 1e9},
+            'achieved_tflops': value * FLOPS_PER_IMG_FWD_BWD / 1e12,
+            'e2e': {'value': e2e, 'unit': 'images/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': B * 3 * 256 * 256 * 4, 'd2h_bytes_per_step': 4},
+            'gpu_launches': calls_per_step * args.steps, 'launches_per_step': calls_per_step,
+            'clocks': clocks, 'roofline': roof, 'last_loss': losses[-1] if losses else None}
+    if not args.skip_cpu_baseline and world == 1:
+        t, cores = cpu_port_step_time(args.cpu_batch, steps=1, warmup=0)
+        line['cpu_baseline'] = {'value': args.cpu_batch / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                'sample': 'batch %d fwd+calc_loss_GCN+bwd once, oracle/model_ref.py (torch CPU fp32, %d threads)' % (args.cpu_batch, cores)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -42,6 +42,7 @@ def parse_header(path=HEADER):
 
 
 _lib = None
+CALLS = [0]   # number of C-ABI kernel-launching calls issued by this process (bench.py reports it as gpu_launches)
 
 
 def lib_path():
@@ -74,6 +75,7 @@ def load():
 def call(name, *args):
     """Invoke a C-ABI entry point; raise RuntimeError(rih_last_error()) on a non-zero status."""
     lib = _lib if _lib is not None else load()
+    CALLS[0] += 1
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError('%s failed (status %d): %s' % (name, rc, lib.rih_last_error().decode()))

@@ -6,6 +6,32 @@
 
 using namespace rih;
 
+namespace rih { namespace tc {
+int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long ldb, int b_mn, Epilogue ep, int M, int N, int K,
+              int allow_splitk, cudaStream_t s);
+bool conv_tc_supported(const ConvGeom& g, int which);
+void set_nsplit(int n);
+int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g, cudaStream_t s);
+int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom& g, cudaStream_t s);
+int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom& g, cudaStream_t s);
+} }
+
+// Arithmetic mode of the GEMM-class ops: 0 = SIMT fp32 (exact), 1 = tcgen05 TF32 multiplicands / fp32 accumulate,
+// 2 = tcgen05 3xTF32 (hi/lo split in shared memory, fp32-faithful).
+// index 0: convolutions (the reference's cuDNN path runs TF32 by default on this GPU), index 1: nn.Linear GEMMs.
+static int g_mode[2] = {0, 0};
+RIH_API int rih_set_gemm_mode(int conv_mode, int linear_mode) {
+  RIH_REQUIRE(conv_mode >= 0 && conv_mode <= 2 && linear_mode >= 0 && linear_mode <= 2, "set_gemm_mode: modes must be 0 (simt), 1 (tf32) or 2 (tf32x3)");
+  g_mode[0] = conv_mode; g_mode[1] = linear_mode;
+  return 0;
+}
+static inline bool use_tc(int which) {
+  if (g_mode[which] == 0) return false;
+  tc::set_nsplit(g_mode[which] == 2 ? 3 : 1);
+  return true;
+}
+static inline bool tc_ok(const void* p, long long ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0); }
+
 static inline int is_vec_ok(const void* p, int ld) {
   return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0);
 }
@@ -23,6 +49,8 @@ RIH_API int rih_linear_fwd(const float* x, int ldx, const float* w, int ldw, con
     RIH_REQUIRE(seed_ptr != nullptr && dropout_p < 1.f, "linear_fwd: dropout needs a device seed and p < 1");
     ep.seed_ptr = seed_ptr; ep.site = site; ep.thresh = dropout_thresh(dropout_p); ep.inv_keep = 1.f / (1.f - dropout_p);
   }
+  if (use_tc(1) && M >= 64 && tc_ok(x, ldx) && tc_ok(w, ldw))
+    return tc::gemm_tf32(x, ldx, 0, w, ldw, 0, ep, M, N, K, 0, stream);
   return launch_gemm_simt(a, b, ep, M, N, K, 0, stream, "linear_fwd");
 }
 
@@ -33,6 +61,8 @@ RIH_API int rih_linear_dgrad(const float* dy, int lddy, const float* w, int ldw,
   DenseK a{dy, lddy, M, is_vec_ok(dy, lddy) && (N % 4 == 0)};
   DenseMN b{w, ldw, K, is_vec_ok(w, ldw)};
   Epilogue ep = make_epilogue(dx, lddx, M, K, nullptr, 0, accumulate ? 1 : 0);
+  if (use_tc(1) && M >= 64 && tc_ok(dy, lddy) && tc_ok(w, ldw))
+    return tc::gemm_tf32(dy, lddy, 0, w, ldw, 1, ep, M, K, N, 0, stream);
   return launch_gemm_simt(a, b, ep, M, K, N, 0, stream, "linear_dgrad");
 }
 
@@ -43,6 +73,8 @@ RIH_API int rih_linear_wgrad(const float* dy, int lddy, const float* x, int ldx,
   DenseMN a{dy, lddy, N, is_vec_ok(dy, lddy)};
   DenseMN b{x, ldx, K, is_vec_ok(x, ldx)};
   Epilogue ep = make_epilogue(dw, lddw, N, K, nullptr, 0, accumulate ? 1 : 0);
+  if (use_tc(1) && M >= 64 && N >= 16 && tc_ok(dy, lddy) && tc_ok(x, ldx))
+    return tc::gemm_tf32(dy, lddy, 1, x, ldx, 1, ep, N, K, M, 1, stream);
   return launch_gemm_simt(a, b, ep, N, K, M, 1, stream, "linear_wgrad");
 }
 
@@ -68,8 +100,11 @@ RIH_API int rih_conv2d_fwd(const float* x, const float* w, const float* bias, fl
   Epilogue ep = make_epilogue(y, g.ldy, (int)M, g.Cout, bias, relu, 0);
   if (g.R == 1 && g.S == 1 && g.stride == 1 && g.pad == 0) {
     DenseK a{x, g.ldx, (int)M, is_vec_ok(x, g.ldx) && (K % 4 == 0)};
+    if (use_tc(0) && tc_ok(x, g.ldx) && tc_ok(w, K))
+      return tc::gemm_tf32(x, g.ldx, 0, w, K, 0, ep, (int)M, g.Cout, K, 0, stream);
     return launch_gemm_simt(a, b, ep, (int)M, g.Cout, K, 0, stream, "conv1x1_fwd");
   }
+  if (use_tc(0) && tc_ok(x, g.ldx) && tc_ok(w, K) && tc::conv_tc_supported(g, 0)) return tc::conv_fwd_tf32(x, w, ep, g, stream);
   ConvFwdA a{x, g, (int)M, is_vec_ok(x, g.ldx) && (g.Cin % 4 == 0)};
   return launch_gemm_simt(a, b, ep, (int)M, g.Cout, K, 0, stream, "conv2d_fwd");
 }
@@ -86,8 +121,11 @@ RIH_API int rih_conv2d_dgrad(const float* dy, const float* w, float* dx, const i
   if (g.R == 1 && g.S == 1 && g.stride == 1 && g.pad == 0) {
     DenseK a{dy, g.ldy, (int)M, is_vec_ok(dy, g.ldy) && (g.Cout % 4 == 0)};
     DenseMN b{w, g.Cin, g.Cin, is_vec_ok(w, g.Cin)};
+    if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(w, g.Cin))
+      return tc::gemm_tf32(dy, g.ldy, 0, w, g.Cin, 1, ep, (int)M, g.Cin, g.Cout, 0, stream);
     return launch_gemm_simt(a, b, ep, (int)M, g.Cin, g.Cout, 0, stream, "conv1x1_dgrad");
   }
+  if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(w, g.Cin) && tc::conv_tc_supported(g, 1)) return tc::conv_dgrad_tf32(dy, w, ep, g, stream);
   ConvDgradA a{dy, g, (int)M, is_vec_ok(dy, g.ldy) && (g.Cout % 4 == 0)};
   ConvDgradB b{w, g, g.Cin, is_vec_ok(w, g.Cin)};
   return launch_gemm_simt(a, b, ep, (int)M, g.Cin, K, 0, stream, "conv2d_dgrad");
@@ -105,8 +143,11 @@ RIH_API int rih_conv2d_wgrad(const float* dy, const float* x, float* dw, const i
   Epilogue ep = make_epilogue(dw, Kn, g.Cout, Kn, nullptr, 0, accumulate ? 1 : 0);
   if (g.R == 1 && g.S == 1 && g.stride == 1 && g.pad == 0) {
     DenseMN b{x, g.ldx, g.Cin, is_vec_ok(x, g.ldx)};
+    if (use_tc(0) && g.Cout >= 16 && tc_ok(dy, g.ldy) && tc_ok(x, g.ldx))
+      return tc::gemm_tf32(dy, g.ldy, 1, x, g.ldx, 1, ep, g.Cout, Kn, (int)P, 1, stream);
     return launch_gemm_simt(a, b, ep, g.Cout, Kn, (int)P, 1, stream, "conv1x1_wgrad");
   }
+  if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(x, g.ldx) && tc::conv_tc_supported(g, 2)) return tc::conv_wgrad_tf32(dy, x, ep, g, stream);
   ConvWgradB b{x, g, Kn, is_vec_ok(x, g.ldx) && (g.Cin % 4 == 0)};
   return launch_gemm_simt(a, b, ep, g.Cout, Kn, (int)P, 1, stream, "conv2d_wgrad");
 }

@@ -1,0 +1,187 @@
+// Host launchers + C-ABI for the tcgen05 TF32 GEMM / implicit-GEMM convolution (see gemm_tc.cuh).
+#include "gemm_tc.cuh"
+
+namespace rih {
+namespace tc {
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows, bool atom32) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 1; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4)) { set_error("tensor map: base/ld not 16-byte aligned"); return 1; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld); return 1; }
+  return 0;
+}
+
+int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int C, long long ld, int bw, int bh, int bn, bool atom32) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 1; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4)) { set_error("tensor map: base/ld not 16-byte aligned"); return 1; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4};
+  cuuint32_t box[4] = {32u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(4d) failed (%d) N=%d H=%d W=%d C=%d ld=%lld box=%d,%d,%d", (int)r, N, H, W, C, ld, bw, bh, bn); return 1; }
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
+static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep, const Producer& prod, int M, int N, int num_kb, int splits,
+                      int kb_per_split, cudaStream_t s) {
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Producer, NSPLIT>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN, NSPLIT>()) != cudaSuccess) {
+      set_error("gemm_tc: cannot raise dynamic shared memory to %d", smem_bytes<BN, NSPLIT>());
+      return 2;
+    }
+    attr = true;
+  }
+  dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
+  kern<<<grid, THREADS, smem_bytes<BN, NSPLIT>(), s>>>(ta, tb, ep, prod, num_kb, kb_per_split);
+  return check_launch("gemm_tc");
+}
+static int g_nsplit = 1;   // set per call by the dispatchers below (1 = TF32, 3 = 3xTF32)
+template <int BN, bool A_MN, bool B_MN, class Producer>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep, const Producer& prod, int M, int N, int num_kb, int splits,
+                      int kb_per_split, cudaStream_t s) {
+  if (g_nsplit == 3) return launch_one<BN, A_MN, B_MN, Producer, 3>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s);
+  return launch_one<BN, A_MN, B_MN, Producer, 1>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s);
+}
+void set_nsplit(int n) { g_nsplit = (n == 3) ? 3 : 1; }
+
+// split-K planning over k-blocks of 32; switches the epilogue to atomic accumulation when splitting
+static void plan_splitk(Epilogue& ep, int M, int N, int BN, int num_kb, int allow, int& splits, int& kb_per_split, cudaStream_t s) {
+  long long tiles = (long long)cdiv(M, BM) * cdiv(N, BN);
+  splits = 1;
+  if (allow && tiles < 148 && num_kb >= 32) {
+    splits = (int)((296 + tiles - 1) / tiles);
+    int maxs = num_kb / 16;
+    if (splits > maxs) splits = maxs;
+    if (splits > 128) splits = 128;
+    if (splits < 1) splits = 1;
+  }
+  kb_per_split = cdiv(num_kb, splits);
+  splits = cdiv(num_kb, kb_per_split);
+  if (splits > 1) {
+    if (ep.mode == 0) {
+      if (ep.ldc == N) cudaMemsetAsync(ep.c, 0, (size_t)M * N * sizeof(float), s);
+      else cudaMemset2DAsync(ep.c, (size_t)ep.ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
+    }
+    ep.mode = 2;
+  }
+}
+
+// a: K-major [M,K] (a_mn=0) or MN-major [K,M] (a_mn=1); b likewise with N.
+int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long ldb, int b_mn, Epilogue ep, int M, int N, int K,
+              int allow_splitk, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return 0;
+  CUtensorMap ta, tb;
+  int BN = (N > 64) ? 128 : 64;
+  if (a_mn ? make_tmap_2d(&ta, a, K, M, lda, 32, true) : make_tmap_2d(&ta, a, M, K, lda, BM)) return 1;
+  if (b_mn ? make_tmap_2d(&tb, b, K, N, ldb, 32, true) : make_tmap_2d(&tb, b, N, K, ldb, BN)) return 1;
+  int num_kb = cdiv(K, BK), splits, kps;
+  plan_splitk(ep, M, N, BN, num_kb, allow_splitk, splits, kps, s);
+#define RIH_TC_CASE(bn, am, bm)                                                              \
+  if (BN == bn && a_mn == am && b_mn == bm) {                                                \
+    DenseProducer<bn, am != 0, bm != 0> prod{0};                                             \
+    return launch_cfg<bn, am != 0, bm != 0>(ta, tb, ep, prod, M, N, num_kb, splits, kps, s); \
+  }
+  RIH_TC_CASE(128, 0, 0) RIH_TC_CASE(64, 0, 0)
+  RIH_TC_CASE(128, 0, 1) RIH_TC_CASE(64, 0, 1)
+  RIH_TC_CASE(128, 1, 1) RIH_TC_CASE(64, 1, 1)
+#undef RIH_TC_CASE
+  set_error("gemm_tf32: unsupported configuration");
+  return 1;
+}
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// Can the stride-1 convolution run on the tcgen05 implicit-GEMM path?
+bool conv_tc_supported(const ConvGeom& g, int which /*0 fwd, 1 dgrad, 2 wgrad*/) {
+  if (g.stride != 1) return false;
+  if (g.Cin % 32 || g.Cout % 32) return false;
+  if (g.ldx % 4 || g.ldy % 4) return false;
+  if (which == 0) return pow2(g.Wo) && pow2(g.Ho) && g.Wo <= 128 && ((long long)g.N * g.Ho * g.Wo) % BM == 0 && (g.Wo * g.Ho >= BM || BM % (g.Wo * g.Ho) == 0);
+  if (which == 1) return pow2(g.W) && pow2(g.H) && g.W <= 128 && ((long long)g.N * g.H * g.W) % BM == 0 && (g.W * g.H >= BM || BM % (g.W * g.H) == 0);
+  return pow2(g.Wo) && pow2(g.Ho) && (g.Ho * g.Wo) % 32 == 0 && g.Cin % 64 == 0;
+}
+
+int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g, cudaStream_t s) {
+  const int M = g.N * g.Ho * g.Wo, BN = (g.Cout > 64) ? 128 : 64;
+  const int tile_h = (BM / g.Wo) < g.Ho ? (BM / g.Wo) : g.Ho;
+  const int tile_n = BM / (g.Wo * tile_h);
+  CUtensorMap ta, tb;
+  if (make_tmap_nhwc(&ta, x, g.N, g.H, g.W, g.Cin, g.ldx, g.Wo, tile_h, tile_n, false)) return 1;
+  if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, BN)) return 1;
+  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, 0};
+  const int num_kb = g.R * g.S * (g.Cin / BK);
+  if (BN == 128) { ConvFwdProducer<128> p{cg}; return launch_cfg<128, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
+  ConvFwdProducer<64> p{cg};
+  return launch_cfg<64, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s);
+}
+
+int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom& g, cudaStream_t s) {
+  const int M = g.N * g.H * g.W, BN = (g.Cin > 64) ? 128 : 64;
+  const int tile_h = (BM / g.W) < g.H ? (BM / g.W) : g.H;
+  const int tile_n = BM / (g.W * tile_h);
+  CUtensorMap ta, tb;
+  if (make_tmap_nhwc(&ta, dy, g.N, g.Ho, g.Wo, g.Cout, g.ldy, g.W, tile_h, tile_n, false)) return 1;
+  if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, 32, true)) return 1;
+  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, 0};
+  const int num_kb = g.R * g.S * (g.Cout / BK);
+  if (BN == 128) { ConvDgradProducer<128> p{cg}; return launch_cfg<128, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s); }
+  ConvDgradProducer<64> p{cg};
+  return launch_cfg<64, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s);
+}
+
+int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom& g, cudaStream_t s) {
+  const int P = g.N * g.Ho * g.Wo, Nn = g.R * g.S * g.Cin, BN = (g.Cin % 128 == 0) ? 128 : 64;
+  const int bw = g.Wo < 32 ? g.Wo : 32, bh = 32 / bw;
+  CUtensorMap ta, tb;
+  if (make_tmap_2d(&ta, dy, P, g.Cout, g.ldy, 32, true)) return 1;
+  if (make_tmap_nhwc(&tb, x, g.N, g.H, g.W, g.Cin, g.ldx, bw, bh, 1, true)) return 1;
+  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, 0, 0};
+  int num_kb = P / BK, splits, kps;
+  plan_splitk(ep, g.Cout, Nn, BN, num_kb, 1, splits, kps, s);
+  if (BN == 128) { ConvWgradProducer<128> p{cg}; return launch_cfg<128, true, true>(ta, tb, ep, p, g.Cout, Nn, num_kb, splits, kps, s); }
+  ConvWgradProducer<64> p{cg};
+  return launch_cfg<64, true, true>(ta, tb, ep, p, g.Cout, Nn, num_kb, splits, kps, s);
+}
+
+}  // namespace tc
+}  // namespace rih
+
+using namespace rih;
+
+// Raw tcgen05 GEMM entry point (testing / benchmarking of the tensor-core path in isolation):
+//   c[M,N] (+)= op(a) * op(b)^T ; a_mn/b_mn select MN-major ([K,M] / [K,N] row-major) operands.
+RIH_API int rih_gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long ldb, int b_mn, float* c, int ldc,
+                          int M, int N, int K, const float* bias, int relu, int accumulate, int allow_splitk, int nsplit, cudaStream_t stream) {
+  RIH_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_tf32: bad shape");
+  RIH_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_tf32: nsplit must be 1 (TF32) or 3 (3xTF32)");
+  tc::set_nsplit(nsplit);
+  Epilogue ep = make_epilogue(c, ldc, M, N, bias, relu, accumulate ? 1 : 0);
+  return tc::gemm_tf32(a, lda, a_mn, b, ldb, b_mn, ep, M, N, K, allow_splitk, stream);
+}

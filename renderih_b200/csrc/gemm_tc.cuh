@@ -1,0 +1,332 @@
+// tcgen05 (5th-gen tensor core) TF32 GEMM for sm_100a: TMA -> 128B-swizzled shared memory -> tcgen05.mma with the
+// fp32 accumulator in TMEM -> tcgen05.ld epilogue.  Hand-written PTX, no CUTLASS.
+//   D[M,N] (+)= A(M x K) * B(N x K)^T,  fp32 storage, TF32 multiplicands, fp32 accumulation.
+// Operand tiles are [rows x 128 bytes] TMA boxes with SWIZZLE_128B; the same box format serves
+//   K-major  operands (rows = M/N index, 32 consecutive k per row)          and
+//   MN-major operands (rows = k index, 32 consecutive m/n per row; one box per 32-wide m/n chunk).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_simt.cuh"   // Epilogue
+
+namespace rih {
+namespace tc {
+
+constexpr int BM = 128;          // UMMA M
+constexpr int BK = 32;           // fp32 elements per stage row = 128 bytes = one swizzle span
+constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction
+constexpr int THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// tcgen05 shared-memory matrix descriptor (PTX ISA "matrix descriptor", sm_100 version bit set), SWIZZLE_128B.
+//   bits [0,14)  start address >> 4      bits [16,30) leading byte offset >> 4
+//   bits [32,46) stride byte offset >> 4 bits [46,48) version = 1     bits [61,64) layout type (2 = SWIZZLE_128B)
+//   layout type 1 = SWIZZLE_128B_BASE32B (32-byte swizzle atoms: the only layout tcgen05 accepts for MN-major TF32 operands)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// instruction descriptor for kind::tf32, fp32 accumulate, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n, bool a_mn, bool b_mn) {
+  return (1u << 4)            // D format F32
+       | (2u << 7)            // A format TF32
+       | (2u << 10)           // B format TF32
+       | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
+       | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// NSPLIT = 1: single-pass TF32.  NSPLIT = 3: error-compensated "3xTF32": every operand tile is split in shared memory into
+// hi = tf32-truncated value and lo = value - hi (exact), and D += hi*hi + lo*hi + hi*lo  (fp32-faithful, ~1e-6 relative).
+template <int BN, int NSPLIT> __host__ __device__ constexpr int stage_bytes() { return (BM * 128 + BN * 128) * (NSPLIT == 3 ? 2 : 1); }
+template <int BN, int NSPLIT> __host__ __device__ constexpr int num_stages() { return NSPLIT == 3 ? (BN >= 128 ? 3 : 4) : (BN >= 128 ? 3 : 4); }
+template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() { return num_stages<BN, NSPLIT>() * stage_bytes<BN, NSPLIT>() + 1024 + 256; }
+
+// ---------------------------------------------------------------- producers (TMA issue logic, one elected lane)
+// Each producer loads, for k-block `kb`, the A tile (BM x 32) to `sa` and the B tile (BN x 32) to `sb`.
+// Tiles are made of 128-byte rows; MN-major operands are split into 32-wide chunks of BK rows (4 KB apart).
+template <int BN, bool A_MN, bool B_MN>
+struct DenseProducer {
+  int kbeg;
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+    const int k0 = kb * BK;
+    if constexpr (!A_MN) tma_load_2d(sa, ta, k0, m0, bar);
+    else {
+#pragma unroll
+      for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, k0, bar);
+    }
+    if constexpr (!B_MN) tma_load_2d(sb, tb, k0, n0, bar);
+    else {
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, n0 + c * 32, k0, bar);
+    }
+  }
+};
+
+struct ConvTcGeom {
+  int Cin, Cout, R, S, pad;
+  int H, W, Ho, Wo;        // input / output spatial size (stride 1 only)
+  int tile_h;              // fwd/dgrad: rows of the 128-pixel tile (tile_w == full width); tile images = 128/(tile_w*tile_h)
+  int kbeg;                // wgrad: first pixel of this split
+};
+
+// forward: A = shifted NHWC input boxes (4-D map {C,W,H,N}), B = weights [Cout][R*S*Cin] (K-major 2-D map)
+template <int BN>
+struct ConvFwdProducer {
+  ConvTcGeom g;
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+    const int cpb = g.Cin / BK;
+    const int tap = kb / cpb, c0 = (kb - tap * cpb) * BK;
+    const int r = tap / g.S, s = tap - r * g.S;
+    const int P = g.Ho * g.Wo;
+    const int n = m0 / P, oh0 = (m0 - n * P) / g.Wo;
+    tma_load_4d(sa, ta, c0, s - g.pad, oh0 + r - g.pad, n, bar);
+    tma_load_2d(sb, tb, kb * BK, n0, bar);
+  }
+};
+// dgrad (stride 1): A = shifted dY boxes (4-D map over [N,Ho,Wo,Cout]), B = weights as MN-major chunks {32 c, 32 co}
+template <int BN>
+struct ConvDgradProducer {
+  ConvTcGeom g;
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+    const int cpb = g.Cout / BK;
+    const int tap = kb / cpb, co0 = (kb - tap * cpb) * BK;
+    const int r = tap / g.S, s = tap - r * g.S;
+    const int P = g.H * g.W;
+    const int n = m0 / P, ih0 = (m0 - n * P) / g.W;
+    tma_load_4d(sa, ta, co0, g.pad - s, ih0 + g.pad - r, n, bar);
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, tap * g.Cin + n0 + c * 32, co0, bar);
+  }
+};
+// wgrad: A = dY as MN-major chunks {32 co, 32 pixels}, B = shifted input boxes of 32 pixels as MN-major chunks {32 c, 32 pixels}
+template <int BN>
+struct ConvWgradProducer {
+  ConvTcGeom g;
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+    const int p0 = kb * BK;
+    const int P = g.Ho * g.Wo;
+    const int n = p0 / P, rem = p0 - n * P;
+    const int oh = rem / g.Wo, ow = rem - oh * g.Wo;
+    const int tap = n0 / g.Cin, cbase = n0 - tap * g.Cin;
+    const int r = tap / g.S, s = tap - r * g.S;
+#pragma unroll
+    for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) tma_load_4d(sb + c * (BK * 128), tb, cbase + c * 32, ow + s - g.pad, oh + r - g.pad, n, bar);
+  }
+};
+
+// ---------------------------------------------------------------- the kernel
+template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
+__global__ void __launch_bounds__(THREADS)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Epilogue ep, Producer prod, int num_kb_total,
+               int kb_per_split) {
+  constexpr int STAGES = num_stages<BN, NSPLIT>();
+  constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, AB_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = stage_bytes<BN, NSPLIT>();   // [A | B] (+ [A_lo | B_lo] when NSPLIT == 3)
+  constexpr uint32_t IDESC = make_idesc_tf32(BN, A_MN, B_MN);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                 // [STAGES] TMA bytes landed
+  uint64_t* empty = bars + STAGES;       // [STAGES] MMAs finished reading the stage
+  uint64_t* ready = bars + 2 * STAGES;   // [STAGES] hi/lo split written (NSPLIT == 3 only)
+  uint64_t* tmem_full = bars + 3 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb_beg = blockIdx.z * kb_per_split;
+  const int num_kb = min(num_kb_total - kb_beg, kb_per_split);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 128); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], AB_BYTES);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        prod.load(&tmap_a, &tmap_b, kb_beg + kb, m0, n0, sa, sa + A_BYTES, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(NSPLIT == 3 ? &ready[s] : &full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major (SWIZZLE_128B): 8-row groups are 1024 B apart (SBO), a K step of 8 tf32 = +32 B inside the swizzle span.
+          // MN-major (SWIZZLE_128B_BASE32B, TMA 128B_ATOM_32B): 32-wide m/n chunks are BK*128 B apart (LBO), 4-row k groups
+          // are 512 B apart (SBO), a K step of 8 rows = +1024 B.
+          uint64_t ad = A_MN ? make_smem_desc(sa + k * 1024, BK * 128, 512, 1) : make_smem_desc(sa + k * 32, 16, 1024, 2);
+          uint64_t bd = B_MN ? make_smem_desc(sb + k * 1024, BK * 128, 512, 1) : make_smem_desc(sb + k * 32, 16, 1024, 2);
+          umma_tf32(tmem_base, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+          if constexpr (NSPLIT == 3) {
+            // descriptors address in 16-byte units: the lo copies sit AB_BYTES after the hi tiles
+            const uint64_t lo_off = (uint64_t)(AB_BYTES >> 4);
+            umma_tf32(tmem_base, ad + lo_off, bd, IDESC, 1u);   // lo(A) * hi(B)
+            umma_tf32(tmem_base, ad, bd + lo_off, IDESC, 1u);   // hi(A) * lo(B)
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // warps 2..5: (NSPLIT == 3) hi/lo splitter during the main loop, then the epilogue.
+    if constexpr (NSPLIT == 3) {
+      const int t = threadIdx.x - 64;   // 0..127
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        uint4* hi = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES);
+        uint4* lo = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + AB_BYTES);
+#pragma unroll 4
+        for (int i = t; i < AB_BYTES / 16; i += 128) {
+          uint4 v = hi[i];
+          uint4 h = make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u);
+          uint4 l;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          hi[i] = h;
+          lo[i] = l;
+        }
+        fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&ready[s]);
+      }
+    }
+    // TMEM lane quarters (warp % 4)
+    const int q = warp & 3;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int m = m0 + q * 32 + lane;
+    if (num_kb > 0) {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          ep.store4(m, n0 + c * 32 + j * 4, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+
+// 2-D fp32 tensor map over a row-major [rows, cols] matrix with row stride ld (elements); box = {32 cols, box_rows}.
+int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows, bool atom32 = false);
+// 4-D fp32 tensor map over an NHWC tensor [N,H,W,C] with pixel stride ld; box = {32 channels, bw, bh, bn}.
+int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int C, long long ld, int bw, int bh, int bn, bool atom32);
+
+}  // namespace tc
+}  // namespace rih

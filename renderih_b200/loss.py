@@ -1,0 +1,100 @@
+"""Training loss of the hot path: `GraphLoss` + `calc_loss_GCN` (reference core/Loss.py:20-277), same call signatures.
+
+This is the *caller side* of the model: small [B,778,3] tensors, expressed with torch ops on
+the tensors' device so that autograd feeds d(result) into the CUDA backward.  Fusing it into one kernel is the next
+scope row; it contains no GEMM-class work.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+class GraphLoss:
+    """core/Loss.py:20-175"""
+
+    def __init__(self, J_regressor, faces, level=4, device='cuda', upsample_weight=None):
+        self.device = device
+        self.level = level + 1
+        J = J_regressor.clone().detach().float()
+        tips = torch.zeros_like(J[:5])
+        for i, v in enumerate((745, 317, 444, 556, 673)):      # Loss.py:40-45
+            tips[i, v] = 1.0
+        J = torch.cat([J, tips], 0)
+        order = [0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20]
+        self.J_regressor = J[order].contiguous().to(device)
+        self.faces = torch.from_numpy(np.asarray(faces).astype(np.int64)).to(device)
+        self.upsample_weight = None if upsample_weight is None else torch.as_tensor(upsample_weight).float().to(device)
+
+    @staticmethod
+    def _smooth_l1(a, b):
+        return F.smooth_l1_loss(a, b)
+
+    def mesh_downsample(self, feat, p=2):
+        return F.avg_pool1d(feat.permute(0, 2, 1), p).permute(0, 2, 1)
+
+    def _edges(self, v):
+        e = v[:, self.faces]
+        return torch.stack([e[:, :, 0] - e[:, :, 1], e[:, :, 1] - e[:, :, 2], e[:, :, 2] - e[:, :, 0]], 2)
+
+    def norm_loss(self, verts_pred, verts_gt):
+        eg, ep = self._edges(verts_gt), self._edges(verts_pred)
+        n = F.normalize(torch.cross(eg[:, :, 0], eg[:, :, 1], dim=-1), dim=-1).unsqueeze(2)
+        t = torch.sum(F.normalize(ep, dim=-1) * n, dim=-1)
+        return self._smooth_l1(t, torch.zeros_like(t))
+
+    def edge_loss(self, verts_pred, verts_gt):
+        return self._smooth_l1(torch.linalg.norm(self._edges(verts_pred), dim=-1), torch.linalg.norm(self._edges(verts_gt), dim=-1))
+
+    def calc_mano_loss(self, v3d_pred, v2d_pred, v3d_gt, v2d_gt, img_size):
+        d = {}
+        d['vert2d_loss'] = F.mse_loss(v2d_pred / img_size * 2 - 1, v2d_gt / img_size * 2 - 1)
+        d['vert3d_loss'] = self._smooth_l1(v3d_pred, v3d_gt)
+        d['joint_loss'] = self._smooth_l1(torch.matmul(self.J_regressor, v3d_pred), torch.matmul(self.J_regressor, v3d_gt))
+        d['norm_loss'] = self.norm_loss(v3d_pred, v3d_gt)
+        d['edge_loss'] = self.edge_loss(v3d_pred, v3d_gt)
+        return d
+
+    def upsample_weight_loss(self, w):
+        x = w - self.upsample_weight
+        return self._smooth_l1(x, torch.zeros_like(x))
+
+    def calc_loss(self, converter, v3d_gt, v2d_gt, v3d_pred, v2d_pred, v3dList, v2dList, img_size):
+        mano = self.calc_mano_loss(v3d_pred, v2d_pred, v3d_gt, v2d_gt, img_size)
+        v3g, v2g = converter.vert_to_GCN(v3d_gt), converter.vert_to_GCN(v2d_gt)
+        g3, g2 = [], []
+        for _ in range(self.level):
+            g3.append(v3g); g2.append(v2g)
+            v3g, v2g = self.mesh_downsample(v3g), self.mesh_downsample(v2g)
+        coarse = {'v3d_loss': [], 'v2d_loss': []}
+        for a3, a2 in zip(v3dList, v2dList):
+            j = [g.shape[1] for g in g3].index(a3.shape[1])
+            coarse['v3d_loss'].append(self._smooth_l1(a3, g3[j]))
+            coarse['v2d_loss'].append(F.mse_loss(a2 / img_size * 2 - 1, g2[j] / img_size * 2 - 1))
+        return mano, coarse
+
+
+def calc_loss_GCN(cfg, epoch, graph_loss_left, graph_loss_right, converter_left, converter_right,
+                  result, paramsDict, handDictList, otherInfo, mask, dense, hms,
+                  v2d_l, j2d_l, v2d_r, j2d_r, v3d_l, j3d_l, v3d_r, j3d_r, root_rel, img_size, upsample_weight=None):
+    """core/Loss.py:201-277 (the auxiliary mask/dense/heat-map loss is disabled in the reference at line 213)."""
+    aux = {'total_loss': 0}
+    v3d_r = v3d_r + root_rel.unsqueeze(1)
+    outs = {}
+    for side, gl, conv, v3g, v2g in (('left', graph_loss_left, converter_left, v3d_l, v2d_l),
+                                     ('right', graph_loss_right, converter_right, v3d_r, v2d_r)):
+        outs[side] = gl.calc_loss(conv, v3g, v2g, result['verts3d'][side], result['verts2d'][side],
+                                  [h['verts3d'][side] for h in handDictList], [h['verts2d'][side] for h in handDictList], img_size)
+    mano = {k: (outs['left'][0][k] + outs['right'][0][k]) / 2 for k in outs['left'][0]}
+    coarse = {k: [(a + b) / 2 for a, b in zip(outs['left'][1][k], outs['right'][1][k])] for k in outs['left'][1]}
+    w = cfg.LOSS_WEIGHT
+    alpha = 0 if epoch < w.GRAPH.NORM.NORM_EPOCH else 1
+    if upsample_weight is not None:
+        mano['upsample_norm_loss'] = graph_loss_left.upsample_weight_loss(upsample_weight)
+    else:
+        mano['upsample_norm_loss'] = torch.zeros_like(mano['vert3d_loss'])
+    total = w.DATA.LABEL_3D * mano['vert3d_loss'] + w.DATA.LABEL_2D * mano['vert2d_loss'] + w.DATA.LABEL_3D * mano['joint_loss'] \
+        + w.GRAPH.NORM.NORMAL * mano['norm_loss'] + alpha * w.GRAPH.NORM.EDGE * mano['edge_loss']
+    for i in range(len(coarse['v3d_loss'])):
+        total = total + w.DATA.LABEL_3D * coarse['v3d_loss'][i] + w.DATA.LABEL_2D * coarse['v2d_loss'][i]
+    total = total + w.NORM.UPSAMPLE * mano['upsample_norm_loss']
+    return total, aux, mano, coarse

@@ -425,17 +425,25 @@ class DualGraph(nn.Module):
 
 
 class GCN_vert_convert:
-    """models/model_zoo/__init__.py:85-96"""
+    """models/model_zoo/__init__.py:85-96 (index tensors are cached per device so the gathers are CUDA-graph capturable)"""
 
     def __init__(self, vertex_num, graph_perm_reverse, graph_perm):
         self.graph_perm_reverse = np.asarray(graph_perm_reverse)[:vertex_num]
         self.graph_perm = list(graph_perm)
+        self._cache = {}
+
+    def _idx(self, which, device):
+        k = (which, str(device))
+        if k not in self._cache:
+            src = self.graph_perm if which == 'perm' else self.graph_perm_reverse
+            self._cache[k] = torch.as_tensor(np.asarray(src, dtype=np.int64)).to(device)
+        return self._cache[k]
 
     def vert_to_GCN(self, x):
-        return x[:, self.graph_perm]
+        return x[:, self._idx('perm', x.device)]
 
     def GCN_to_vert(self, x):
-        return x[:, self.graph_perm_reverse]
+        return x[:, self._idx('rev', x.device)]
 
 
 class decoder(nn.Module):

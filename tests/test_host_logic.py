@@ -1,0 +1,129 @@
+"""Host-side logic that needs no GPU: module structure / state_dict contract, config, asset generators, fail-loud
+behaviour, flat parameter buffers and the 2-rank gradient exchange (gloo)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from renderih_b200 import assets as A
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.fixture(scope='module')
+def model():
+    from renderih_b200.model import load_model
+    return load_model(assets=A.synthetic_assets(0))
+
+
+def test_state_dict_contract(model):
+    sd = model.state_dict()
+    assert len(sd) == 1093                                   # SURVEY.md section 5 (checkpoint / resume)
+    assert sum(p.numel() for p in model.parameters()) == 39037091
+    gold = torch.load(os.path.join(GOLD, 'model_synth_b2.pt'), weights_only=False)
+    names = dict(model.named_parameters())
+    for k in list(gold['train']['grads']) + gold['train']['no_grad_keys']:   # every reference parameter name exists here
+        assert k in names, k
+    assert sd['decoder.dense_coor'].shape == (778, 3) and sd['decoder.unsample_layer.weight'].shape == (778, 252)
+    assert 'decoder.dual_gcn.layers.0.graph_left.GCN_blocks.0.graph_L' not in sd      # persistent=False in the reference
+    for m in model.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            assert m.weight.permute(0, 2, 3, 1).is_contiguous()       # kernels read [Cout,R,S,Cin]
+    sd2 = {('module.' + k): v for k, v in sd.items()}                  # DDP-prefixed checkpoints (eval_interhand.py:241-250)
+    model.load_state_dict({k[7:]: v for k, v in sd2.items()})
+    assert model.encoder.resnet.layer1[0].conv2.weight.permute(0, 2, 3, 1).is_contiguous()
+
+
+def test_reference_attribute_surface(model):
+    d = model.decoder
+    assert d.get_upsample_weight().shape == (778, 252)
+    x = torch.arange(2 * 778 * 3, dtype=torch.float32).view(2, 778, 3)
+    g = d.converter['left'].vert_to_GCN(x)
+    assert g.shape == (2, 1008, 3)
+    assert torch.equal(d.converter['left'].GCN_to_vert(g), x)
+    assert d.vNum_in == 63 and d.vNum_out == 252 and d.vNum_all == 1008
+    assert hasattr(model, 'encoder') and hasattr(model, 'mid_model')
+
+
+def test_no_cpu_fallback(model):
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 3, 256, 256))
+    from renderih_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.linear(torch.zeros(2, 4), torch.zeros(3, 4))
+    if not torch.cuda.is_available():
+        from renderih_b200.manolayer import ManoLayer
+        layer = ManoLayer(A.synthetic_mano(0))
+        with pytest.raises(RuntimeError):
+            layer(torch.eye(3)[None], torch.zeros(1, 45), torch.zeros(1, 10))
+
+
+def test_config_and_hrnet_gate(tmp_path):
+    from renderih_b200.config import load_cfg
+    from renderih_b200.model import load_model
+    cfg = load_cfg()
+    assert cfg.MODEL.GCN_IN_DIM == [512, 256, 128] and cfg.TRAIN.dropout == 0.05 and cfg.SEED == 88
+    p = tmp_path / 'c.yaml'
+    p.write_text('MODEL:\n  ENCODER_TYPE: hrnet48\nTRAIN:\n  dropout: 0.0\n')
+    cfg2 = load_cfg(str(p))
+    assert cfg2.TRAIN.dropout == 0.0 and cfg2.MODEL.graph_k == 2
+    with pytest.raises(NotImplementedError):
+        load_model(cfg2, assets=A.synthetic_assets(0))
+
+
+def test_graph_csr_matches_dense():
+    from renderih_b200.model import GraphCSR
+    L = A.synthetic_assets(1)['left_graph']['coarsen_graphs_L'][3]
+    g = GraphCSR(L)
+    d = g.dense().numpy()
+    assert np.allclose(d, np.asarray(L.todense(), dtype=np.float32))
+    rp, ci, va, rpt, cit, vat = g._host
+    dt = np.zeros_like(d)
+    for r in range(g.V):
+        dt[r, cit[rpt[r]:rpt[r + 1]]] = vat[rpt[r]:rpt[r + 1]]
+    assert np.allclose(dt, d.T)
+    assert (np.diff(rp) <= 16).all()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from renderih_b200.train import FlatParams
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(8, 4, 3)
+    conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)
+    lin = torch.nn.Linear(5, 3)
+    params = list(conv.parameters()) + list(lin.parameters())
+    before = [p.detach().clone() for p in params]
+    fp = FlatParams(params)
+    for p, b in zip(params, before):
+        assert torch.equal(p, b) and p.stride() == b.stride()           # re-homing preserves values and strides
+    fp.zero_grad()
+    x = torch.full((2, 8, 6, 6), float(rank + 1))
+    (conv(x).sum() + lin(torch.full((2, 5), float(rank + 1))).sum()).backward()
+    local = fp.grad.clone()
+    assert params[0].grad.data_ptr() == fp.grad.data_ptr()               # autograd accumulated in place into the flat buffer
+    w = fp.all_reduce()
+    assert w == world
+    out[rank] = (local, fp.grad.clone())
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_two_ranks_gloo():
+    """N>1 path: the ONE exchange of a step is a sum all-reduce of the flat gradient buffer."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    l0, r0 = out[0]
+    l1, r1 = out[1]
+    assert torch.allclose(r0, l0 + l1) and torch.allclose(r1, l0 + l1)
+    assert not torch.allclose(l0, l1)
