@@ -11,9 +11,10 @@ int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long
               int allow_splitk, cudaStream_t s);
 bool conv_tc_supported(const ConvGeom& g, int which);
 void set_nsplit(int n);
-int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g, cudaStream_t s);
-int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom& g, cudaStream_t s);
-int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom& g, cudaStream_t s);
+long long conv_tc_workspace(const ConvGeom& g, int which);
+int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s);
+int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s);
+int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s);
 } }
 
 // Arithmetic mode of the GEMM-class ops: 0 = SIMT fp32 (exact), 1 = tcgen05 TF32 multiplicands / fp32 accumulate,
@@ -89,8 +90,17 @@ static int parse_geom(const int* g, ConvGeom& o) {
 
 // NHWC conv forward. geom = {N,H,W,Cin,Ho,Wo,Cout,R,S,stride,pad,ldx,ldy}
 // reference: nn.Conv2d call sites models/encoder.py:52,108-116 ; torchvision resnet bottlenecks
+// Workspace (in floats) the tensor-core path of conv `which` (0 fwd, 1 dgrad, 2 wgrad) needs for this geometry in the
+// current gemm mode; 0 when none.  Stored to *floats.
+RIH_API int rih_conv2d_workspace(const int* geom, int which, long long* floats) {
+  ConvGeom g;
+  RIH_REQUIRE(parse_geom(geom, g) == 0, "conv2d_workspace: inconsistent geometry");
+  *floats = (g_mode[0] != 0 && tc::conv_tc_supported(g, which)) ? tc::conv_tc_workspace(g, which) : 0;
+  return 0;
+}
+
 RIH_API int rih_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, const int* geom,
-                           int relu, cudaStream_t stream) {
+                           int relu, float* ws, cudaStream_t stream) {
   ConvGeom g;
   RIH_REQUIRE(parse_geom(geom, g) == 0, "conv2d_fwd: inconsistent geometry");
   long long M = (long long)g.N * g.Ho * g.Wo;
@@ -104,14 +114,14 @@ RIH_API int rih_conv2d_fwd(const float* x, const float* w, const float* bias, fl
       return tc::gemm_tf32(x, g.ldx, 0, w, K, 0, ep, (int)M, g.Cout, K, 0, stream);
     return launch_gemm_simt(a, b, ep, (int)M, g.Cout, K, 0, stream, "conv1x1_fwd");
   }
-  if (use_tc(0) && tc_ok(x, g.ldx) && tc_ok(w, K) && tc::conv_tc_supported(g, 0)) return tc::conv_fwd_tf32(x, w, ep, g, stream);
+  if (use_tc(0) && tc_ok(x, g.ldx) && tc_ok(w, K) && tc::conv_tc_supported(g, 0) && (g.stride == 1 || ws)) return tc::conv_fwd_tf32(x, w, ep, g, ws, stream);
   ConvFwdA a{x, g, (int)M, is_vec_ok(x, g.ldx) && (g.Cin % 4 == 0)};
   return launch_gemm_simt(a, b, ep, (int)M, g.Cout, K, 0, stream, "conv2d_fwd");
 }
 
 // dx[N,H,W,Cin] (+)= conv_transpose(dy, w)
 RIH_API int rih_conv2d_dgrad(const float* dy, const float* w, float* dx, const int* geom, int accumulate,
-                             cudaStream_t stream) {
+                             float* ws, cudaStream_t stream) {
   ConvGeom g;
   RIH_REQUIRE(parse_geom(geom, g) == 0, "conv2d_dgrad: inconsistent geometry");
   long long M = (long long)g.N * g.H * g.W;
@@ -125,7 +135,7 @@ RIH_API int rih_conv2d_dgrad(const float* dy, const float* w, float* dx, const i
       return tc::gemm_tf32(dy, g.ldy, 0, w, g.Cin, 1, ep, (int)M, g.Cin, g.Cout, 0, stream);
     return launch_gemm_simt(a, b, ep, (int)M, g.Cin, g.Cout, 0, stream, "conv1x1_dgrad");
   }
-  if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(w, g.Cin) && tc::conv_tc_supported(g, 1)) return tc::conv_dgrad_tf32(dy, w, ep, g, stream);
+  if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(w, g.Cin) && tc::conv_tc_supported(g, 1) && (g.stride == 1 || ws)) return tc::conv_dgrad_tf32(dy, w, ep, g, ws, stream);
   ConvDgradA a{dy, g, (int)M, is_vec_ok(dy, g.ldy) && (g.Cout % 4 == 0)};
   ConvDgradB b{w, g, g.Cin, is_vec_ok(w, g.Cin)};
   return launch_gemm_simt(a, b, ep, (int)M, g.Cin, K, 0, stream, "conv2d_dgrad");
@@ -133,7 +143,7 @@ RIH_API int rih_conv2d_dgrad(const float* dy, const float* w, float* dx, const i
 
 // dw[Cout,R,S,Cin] (+)= sum_pixels dy (x) x
 RIH_API int rih_conv2d_wgrad(const float* dy, const float* x, float* dw, const int* geom, int accumulate,
-                             cudaStream_t stream) {
+                             float* ws, cudaStream_t stream) {
   ConvGeom g;
   RIH_REQUIRE(parse_geom(geom, g) == 0, "conv2d_wgrad: inconsistent geometry");
   long long P = (long long)g.N * g.Ho * g.Wo;
@@ -147,7 +157,7 @@ RIH_API int rih_conv2d_wgrad(const float* dy, const float* x, float* dw, const i
       return tc::gemm_tf32(dy, g.ldy, 1, x, g.ldx, 1, ep, g.Cout, Kn, (int)P, 1, stream);
     return launch_gemm_simt(a, b, ep, g.Cout, Kn, (int)P, 1, stream, "conv1x1_wgrad");
   }
-  if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(x, g.ldx) && tc::conv_tc_supported(g, 2)) return tc::conv_wgrad_tf32(dy, x, ep, g, stream);
+  if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(x, g.ldx) && tc::conv_tc_supported(g, 2) && (g.stride == 1 || ws)) return tc::conv_wgrad_tf32(dy, x, ep, g, ws, stream);
   ConvWgradB b{x, g, Kn, is_vec_ok(x, g.ldx) && (g.Cin % 4 == 0)};
   return launch_gemm_simt(a, b, ep, g.Cout, Kn, (int)P, 1, stream, "conv2d_wgrad");
 }

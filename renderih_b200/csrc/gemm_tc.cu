@@ -119,8 +119,11 @@ int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long
 static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // Can the stride-1 convolution run on the tcgen05 implicit-GEMM path?
+// stride 2 is supported for even H, W through a parity-stacked copy of the input (fwd, wgrad) and a zero-inserted copy of
+// dY (dgrad); both need caller-provided workspace (conv_tc_workspace).
 bool conv_tc_supported(const ConvGeom& g, int which /*0 fwd, 1 dgrad, 2 wgrad*/) {
-  if (g.stride != 1) return false;
+  if (g.stride != 1 && g.stride != 2) return false;
+  if (g.stride == 2 && ((g.H | g.W) & 1 || g.Ho * 2 != g.H || g.Wo * 2 != g.W || g.R != g.S || (g.R != 1 && g.R != 3) || g.pad != g.R / 2)) return false;
   if (g.Cin % 32 || g.Cout % 32) return false;
   if (g.ldx % 4 || g.ldy % 4) return false;
   if (which == 0) return pow2(g.Wo) && pow2(g.Ho) && g.Wo <= 128 && ((long long)g.N * g.Ho * g.Wo) % BM == 0 && (g.Wo * g.Ho >= BM || BM % (g.Wo * g.Ho) == 0);
@@ -128,21 +131,41 @@ bool conv_tc_supported(const ConvGeom& g, int which /*0 fwd, 1 dgrad, 2 wgrad*/)
   return pow2(g.Wo) && pow2(g.Ho) && (g.Ho * g.Wo) % 32 == 0 && g.Cin % 64 == 0;
 }
 
-int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g, cudaStream_t s) {
+long long conv_tc_workspace(const ConvGeom& g, int which) {
+  if (g.stride != 2) return 0;
+  if (which == 1) return (long long)g.N * g.H * g.W * g.Cout;   // zero-inserted dY
+  return (long long)g.N * g.H * g.W * g.Cin;                    // parity-stacked x
+}
+extern "C" int rih_parity_stack(const float* x, int ldx, float* xp, int N, int H, int W, int C, cudaStream_t s);
+extern "C" int rih_dilate2x(const float* y, int ldy, float* yd, int N, int Ho, int Wo, int C, cudaStream_t s);
+
+int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s) {
   const int M = g.N * g.Ho * g.Wo, BN = (g.Cout > 64) ? 128 : 64;
   const int tile_h = (BM / g.Wo) < g.Ho ? (BM / g.Wo) : g.Ho;
   const int tile_n = BM / (g.Wo * tile_h);
   CUtensorMap ta, tb;
-  if (make_tmap_nhwc(&ta, x, g.N, g.H, g.W, g.Cin, g.ldx, g.Wo, tile_h, tile_n, false)) return 1;
+  if (g.stride == 2) {
+    if (!ws) { set_error("conv_fwd_tf32: stride-2 path needs workspace"); return 1; }
+    if (int e = rih_parity_stack(x, g.ldx, ws, g.N, g.H, g.W, g.Cin, s)) return e;
+    if (make_tmap_nhwc(&ta, ws, 4 * g.N, g.H / 2, g.W / 2, g.Cin, g.Cin, g.Wo, tile_h, tile_n, false)) return 1;
+  } else {
+    if (make_tmap_nhwc(&ta, x, g.N, g.H, g.W, g.Cin, g.ldx, g.Wo, tile_h, tile_n, false)) return 1;
+  }
   if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, BN)) return 1;
-  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, 0};
+  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, g.stride == 2 ? g.N : 0};
   const int num_kb = g.R * g.S * (g.Cin / BK);
   if (BN == 128) { ConvFwdProducer<128> p{cg}; return launch_cfg<128, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
   ConvFwdProducer<64> p{cg};
   return launch_cfg<64, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s);
 }
 
-int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom& g, cudaStream_t s) {
+int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom& g0, float* ws, cudaStream_t s) {
+  ConvGeom g = g0;
+  if (g0.stride == 2) {   // zero-insert dY, then it is a stride-1 dgrad over an H x W "output"
+    if (!ws) { set_error("conv_dgrad_tf32: stride-2 path needs workspace"); return 1; }
+    if (int e = rih_dilate2x(dy, g0.ldy, ws, g0.N, g0.Ho, g0.Wo, g0.Cout, s)) return e;
+    dy = ws; g.stride = 1; g.Ho = g0.H; g.Wo = g0.W; g.ldy = g0.Cout;
+  }
   const int M = g.N * g.H * g.W, BN = (g.Cin > 64) ? 128 : 64;
   const int tile_h = (BM / g.W) < g.H ? (BM / g.W) : g.H;
   const int tile_n = BM / (g.W * tile_h);
@@ -156,13 +179,19 @@ int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom
   return launch_cfg<64, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s);
 }
 
-int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom& g, cudaStream_t s) {
+int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s) {
   const int P = g.N * g.Ho * g.Wo, Nn = g.R * g.S * g.Cin, BN = (g.Cin % 128 == 0) ? 128 : 64;
   const int bw = g.Wo < 32 ? g.Wo : 32, bh = 32 / bw;
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, dy, P, g.Cout, g.ldy, 32, true)) return 1;
-  if (make_tmap_nhwc(&tb, x, g.N, g.H, g.W, g.Cin, g.ldx, bw, bh, 1, true)) return 1;
-  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, 0, 0};
+  if (g.stride == 2) {
+    if (!ws) { set_error("conv_wgrad_tf32: stride-2 path needs workspace"); return 1; }
+    if (int e = rih_parity_stack(x, g.ldx, ws, g.N, g.H, g.W, g.Cin, s)) return e;
+    if (make_tmap_nhwc(&tb, ws, 4 * g.N, g.H / 2, g.W / 2, g.Cin, g.Cin, bw, bh, 1, true)) return 1;
+  } else {
+    if (make_tmap_nhwc(&tb, x, g.N, g.H, g.W, g.Cin, g.ldx, bw, bh, 1, true)) return 1;
+  }
+  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, 0, g.stride == 2 ? g.N : 0};
   int num_kb = P / BK, splits, kps;
   plan_splitk(ep, g.Cout, Nn, BN, num_kb, 1, splits, kps, s);
   if (BN == 128) { ConvWgradProducer<128> p{cg}; return launch_cfg<128, true, true>(ta, tb, ep, p, g.Cout, Nn, num_kb, splits, kps, s); }

@@ -110,7 +110,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // NSPLIT = 1: single-pass TF32.  NSPLIT = 3: error-compensated "3xTF32": every operand tile is split in shared memory into
-// hi = tf32-truncated value and lo = value - hi (exact), and D += hi*hi + lo*hi + hi*lo  (fp32-faithful, ~1e-6 relative).
+// hi = value rounded to TF32 and lo = value - hi (exact in fp32), and D += hi*hi + lo*hi + hi*lo  (fp32-faithful).
 template <int BN, int NSPLIT> __host__ __device__ constexpr int stage_bytes() { return (BM * 128 + BN * 128) * (NSPLIT == 3 ? 2 : 1); }
 template <int BN, int NSPLIT> __host__ __device__ constexpr int num_stages() { return NSPLIT == 3 ? (BN >= 128 ? 3 : 4) : (BN >= 128 ? 3 : 4); }
 template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() { return num_stages<BN, NSPLIT>() * stage_bytes<BN, NSPLIT>() + 1024 + 256; }
@@ -140,8 +140,14 @@ struct ConvTcGeom {
   int Cin, Cout, R, S, pad;
   int H, W, Ho, Wo;        // input / output spatial size (stride 1 only)
   int tile_h;              // fwd/dgrad: rows of the 128-pixel tile (tile_w == full width); tile images = 128/(tile_w*tile_h)
-  int kbeg;                // wgrad: first pixel of this split
+  int s2_images;           // > 0: stride-2 convolution reading the parity-stacked input [4*N, H/2, W/2, C]; value = N
 };
+// stride 2: input row 2*o + r - pad = 2*(o + shift) + parity
+__device__ __forceinline__ void s2_tap(int r, int pad, int& parity, int& shift) {
+  const int t = r - pad;
+  parity = t & 1;
+  shift = (t - parity) >> 1;
+}
 
 // forward: A = shifted NHWC input boxes (4-D map {C,W,H,N}), B = weights [Cout][R*S*Cin] (K-major 2-D map)
 template <int BN>
@@ -153,7 +159,14 @@ struct ConvFwdProducer {
     const int r = tap / g.S, s = tap - r * g.S;
     const int P = g.Ho * g.Wo;
     const int n = m0 / P, oh0 = (m0 - n * P) / g.Wo;
-    tma_load_4d(sa, ta, c0, s - g.pad, oh0 + r - g.pad, n, bar);
+    if (g.s2_images > 0) {
+      int ph, dh, pw, dw_;
+      s2_tap(r, g.pad, ph, dh);
+      s2_tap(s, g.pad, pw, dw_);
+      tma_load_4d(sa, ta, c0, dw_, oh0 + dh, (ph * 2 + pw) * g.s2_images + n, bar);
+    } else {
+      tma_load_4d(sa, ta, c0, s - g.pad, oh0 + r - g.pad, n, bar);
+    }
     tma_load_2d(sb, tb, kb * BK, n0, bar);
   }
 };
@@ -185,8 +198,15 @@ struct ConvWgradProducer {
     const int r = tap / g.S, s = tap - r * g.S;
 #pragma unroll
     for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
+    int cw = ow + s - g.pad, ch = oh + r - g.pad, cn = n;
+    if (g.s2_images > 0) {
+      int ph, dh, pw, dw_;
+      s2_tap(r, g.pad, ph, dh);
+      s2_tap(s, g.pad, pw, dw_);
+      cw = ow + dw_; ch = oh + dh; cn = (ph * 2 + pw) * g.s2_images + n;
+    }
 #pragma unroll
-    for (int c = 0; c < BN / 32; ++c) tma_load_4d(sb + c * (BK * 128), tb, cbase + c * 32, ow + s - g.pad, oh + r - g.pad, n, bar);
+    for (int c = 0; c < BN / 32; ++c) tma_load_4d(sb + c * (BK * 128), tb, cbase + c * 32, cw, ch, cn, bar);
   }
 };
 
@@ -281,7 +301,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll 4
         for (int i = t; i < AB_BYTES / 16; i += 128) {
           uint4 v = hi[i];
-          uint4 h = make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u);
+          // hi = round-to-nearest TF32 (10-bit mantissa): unbiased, so the dropped lo*lo term and the hardware's truncation of lo
+          // do not accumulate coherently over K
+          uint4 h = make_uint4((v.x + 0x1000u) & 0xFFFFE000u, (v.y + 0x1000u) & 0xFFFFE000u, (v.z + 0x1000u) & 0xFFFFE000u, (v.w + 0x1000u) & 0xFFFFE000u);
           uint4 l;
           l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
           l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));

@@ -405,3 +405,64 @@ RIH_API int rih_gap_bwd(const float* dy, float* dx, int lddx, int N, int HW, int
   gap_bwd_kernel<<<grid, 256, 0, s>>>(dy, dx, lddx, N, HW, C, accumulate);
   return check_launch("gap_bwd");
 }
+
+// ============================================================== stride-2 helpers for the tensor-core convolution path
+// parity stack: xp[(ph*2+pw)*N + n, i, j, :] = x[n, 2i+ph, 2j+pw, :]   (space-to-depth by pixel parity, H and W even)
+__global__ void parity_stack_kernel(const float* __restrict__ x, int ldx, float* __restrict__ xp, int N, int H, int W, int C4) {
+  const int H2 = H / 2, W2 = W / 2;
+  long long total = (long long)N * H * W * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4); long long t = i / C4; int w = (int)(t % W); t /= W; int h = (int)(t % H); int n = (int)(t / H);
+    float4 v = *reinterpret_cast<const float4*>(x + ((size_t)(n * H + h) * W + w) * ldx + c * 4);
+    int p = (h & 1) * 2 + (w & 1);
+    *reinterpret_cast<float4*>(xp + ((((size_t)p * N + n) * H2 + (h >> 1)) * W2 + (w >> 1)) * (size_t)(C4 * 4) + c * 4) = v;
+  }
+}
+RIH_API int rih_parity_stack(const float* x, int ldx, float* xp, int N, int H, int W, int C, cudaStream_t s) {
+  RIH_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0 && ldx % 4 == 0, "parity_stack: H, W must be even and C, ld multiples of 4");
+  long long total = (long long)N * H * W * (C / 4);
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  parity_stack_kernel<<<grid, 256, 0, s>>>(x, ldx, xp, N, H, W, C / 4);
+  return check_launch("parity_stack");
+}
+// zero insertion: yd[n, 2i, 2j, :] = y[n, i, j, :], 0 elsewhere (yd is [N, 2Ho, 2Wo, C] contiguous)
+__global__ void dilate2x_kernel(const float* __restrict__ y, int ldy, float* __restrict__ yd, int N, int Ho, int Wo, int C4) {
+  const int H = 2 * Ho, W = 2 * Wo;
+  long long total = (long long)N * H * W * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4); long long t = i / C4; int w = (int)(t % W); t /= W; int h = (int)(t % H); int n = (int)(t / H);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!((h | w) & 1)) v = *reinterpret_cast<const float4*>(y + ((size_t)(n * Ho + (h >> 1)) * Wo + (w >> 1)) * ldy + c * 4);
+    reinterpret_cast<float4*>(yd)[i] = v;
+  }
+}
+RIH_API int rih_dilate2x(const float* y, int ldy, float* yd, int N, int Ho, int Wo, int C, cudaStream_t s) {
+  RIH_REQUIRE(C % 4 == 0 && ldy % 4 == 0, "dilate2x: C, ld must be multiples of 4");
+  long long total = (long long)N * 4 * Ho * Wo * (C / 4);
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  dilate2x_kernel<<<grid, 256, 0, s>>>(y, ldy, yd, N, Ho, Wo, C / 4);
+  return check_launch("dilate2x");
+}
+
+// ============================================================== non-overlapping patches (kernel == stride): im2col without blow-up
+// P[(n,gh,gw), (r,s,c)] = x[n, p*gh+r, p*gw+s, c]   -- img_feat_to_grid.proj, models/model_attn/img_attn.py:48,60
+__global__ void patchify_kernel(const float* __restrict__ x, int ldx, float* __restrict__ P, int N, int H, int W, int C4, int p, int scatter) {
+  const int gh_n = H / p, gw_n = W / p;
+  long long total = (long long)N * H * W * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4); long long t = i / C4; int s_ = (int)(t % p); t /= p; int r = (int)(t % p); t /= p;
+    int gw = (int)(t % gw_n); t /= gw_n; int gh = (int)(t % gh_n); int n = (int)(t / gh_n);
+    float* px = const_cast<float*>(x) + ((size_t)(n * H + gh * p + r) * W + gw * p + s_) * ldx + c * 4;
+    float* pp = P + (size_t)i * 4;
+    if (!scatter) *reinterpret_cast<float4*>(pp) = *reinterpret_cast<const float4*>(px);
+    else *reinterpret_cast<float4*>(px) = *reinterpret_cast<const float4*>(pp);
+  }
+}
+// scatter = 0: P <- patches of x ; scatter = 1: x <- P (the exact inverse; used for the gradient)
+RIH_API int rih_patchify(float* x, int ldx, float* P, int N, int H, int W, int C, int p, int scatter, cudaStream_t s) {
+  RIH_REQUIRE(p >= 1 && H % p == 0 && W % p == 0 && C % 4 == 0 && ldx % 4 == 0, "patchify: bad geometry");
+  long long total = (long long)N * H * W * (C / 4);
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  patchify_kernel<<<grid, 256, 0, s>>>(x, ldx, P, N, H, W, C / 4, p, scatter);
+  return check_launch("patchify");
+}

@@ -78,6 +78,46 @@ class ManoLayer(Module):
     def axis2pca(self, axis):
         return (axis - self.hands_mean).mm(self.hands_components_inv)
 
+    def Rmat2pca(self, R):
+        return self.axis2pca(self.Rmat2axis(R))
+
+    def Rmat2axis(self, R):
+        """manolayer.py:186-215 (rotation matrix -> axis-angle with the reference's clamping / quadrant fix-ups)"""
+        R = R.view(-1, 3, 3)
+        temp = (R - R.permute(0, 2, 1)) / 2
+        L = temp[:, [2, 0, 1], [1, 2, 0]]
+        sin = torch.norm(L, dim=1, keepdim=False)
+        L = L / (sin.unsqueeze(-1) + 1e-8)
+        temp = (R + R.permute(0, 2, 1)) / 2
+        temp = temp - torch.eye(3, dtype=R.dtype, device=R.device)
+        temp2 = torch.matmul(L.unsqueeze(-1), L.unsqueeze(1))
+        temp2 = temp2 - torch.eye(3, dtype=R.dtype, device=R.device)
+        temp = temp[:, 0, 0] + temp[:, 1, 1] + temp[:, 2, 2]
+        temp2 = temp2[:, 0, 0] + temp2[:, 1, 1] + temp2[:, 2, 2]
+        cos = 1 - temp / (temp2 + 1e-8)
+        sin = torch.clamp(sin, min=-1 + 1e-7, max=1 - 1e-7)
+        theta = torch.asin(sin)
+        theta2 = theta.clone()
+        idx1 = (cos < 0) & (sin > 0)
+        idx2 = (cos < 0) & (sin < 0)
+        theta2[idx1] = 3.14159 - theta[idx1]
+        theta2[idx2] = -3.14159 - theta[idx2]
+        return (theta2.unsqueeze(-1) * L).view(-1, 45)
+
+    @staticmethod
+    def buildSE3_batch(R, t):
+        """manolayer.py:229-238"""
+        bs = R.shape[0]
+        pad = torch.zeros((bs, 1, 4), dtype=R.dtype, device=R.device)
+        pad[:, 0, 3] = 1.0
+        return torch.cat([torch.cat([R, t], 2), pad], 1)
+
+    @staticmethod
+    def SE3_apply(SE3, v):
+        """manolayer.py:240-248"""
+        pad = torch.ones((v.shape[0], 1), dtype=v.dtype, device=v.device)
+        return SE3.bmm(torch.cat([v, pad], 1).unsqueeze(2))[:, :3, 0]
+
     # ---- device-side constant tables (transposed for coalesced reads); rebuilt if a buffer is mutated in place
     def _tables(self, device):
         bufs = (self.hands_components, self.hands_mean, self.shapedirs, self.posedirs, self.v_template, self.J_regressor, self.weights)

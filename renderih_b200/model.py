@@ -305,7 +305,13 @@ class img_feat_to_grid(nn.Module):
         x, H = img
         assert H == self.img_size
         G = self.grid_size * self.grid_size
-        g = ops.conv2d(x, self.proj.weight, self.proj.bias, B, H, H, stride=self.proj.stride[0], pad=0, relu=True)
+        p = self.proj.stride[0]
+        if p > 1 and x.shape[1] % 4 == 0:
+            # kernel == stride: patches are disjoint, so im2col is a pure re-ordering and the conv is ONE dense GEMM
+            w2d = self.proj.weight.permute(0, 2, 3, 1).reshape(self.proj.weight.shape[0], -1)   # view of the channels_last weight
+            g = ops.linear(ops.patchify(x, B, H, H, p), w2d, self.proj.bias, relu=True)
+        else:
+            g = ops.conv2d(x, self.proj.weight, self.proj.bias, B, H, H, stride=p, pad=0, relu=True)
         g = ops.posemb(g, self.position_embeddings.weight, B, G, 1)
         return self.self_attn(g, B, G)
 

@@ -52,6 +52,37 @@ def _ld(t):
     return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
 
 
+# ----------------------------------------------------------------------------- direct parameter-gradient accumulation
+# train.FlatParams registers every trainable tensor's gradient view here (keyed by the parameter's data pointer).  A backward
+# that finds its weight registered accumulates straight into that buffer (kernels have accumulate flags / atomics) and
+# returns None to autograd, which removes one torch add kernel (AccumulateGrad) per parameter per step.
+GRAD_TARGETS = {}
+
+
+def register_grad_target(param, grad):
+    import weakref
+    GRAD_TARGETS[param.data_ptr()] = (grad, weakref.ref(param))
+
+
+def clear_grad_targets():
+    GRAD_TARGETS.clear()
+
+
+def _gt(t):
+    """Registered flat-gradient view for the parameter whose storage starts where `t` does (t may be a 2-D view of it)."""
+    if t is None:
+        return None
+    e = GRAD_TARGETS.get(t.data_ptr())
+    if e is None:
+        return None
+    grad, ref = e
+    p = ref()
+    if p is None or p.data_ptr() != t.data_ptr() or p.grad is None or p.grad.data_ptr() != grad.data_ptr() or p.numel() != t.numel():
+        GRAD_TARGETS.pop(t.data_ptr(), None)    # stale registration (owner gone or re-homed): fall back to autograd
+        return None
+    return grad
+
+
 # ----------------------------------------------------------------------------- dropout seed (device resident)
 class _SeedState:
     """Device-resident base seed advanced once per step (so CUDA-graph replays draw fresh masks)."""
@@ -103,6 +134,7 @@ class LinearFn(Function):
              _p(res), _ld(res) if res is not None else 0, float(p_drop), sp, site, _stream())
         ctx.save_for_backward(x, w, y if (relu or p_drop > 0) else None)
         ctx.meta = (relu, p_drop, site, b is not None, res is not None)
+        ctx.bias_ref = b
         return y
 
     @staticmethod
@@ -123,11 +155,19 @@ class LinearFn(Function):
             dx = torch.empty((M, K), device=dy.device, dtype=torch.float32)
             call('rih_linear_dgrad', _p(g), _ld(g), _p(w), w.stride(0), _p(dx), K, M, N, K, 0, s)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty((N, K), device=dy.device, dtype=torch.float32)
-            call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(dw), K, M, N, K, 0, s)
+            tgt = _gt(w)
+            if tgt is not None:
+                call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(tgt), w.stride(0), M, N, K, 1, s)
+            else:
+                dw = torch.empty((N, K), device=dy.device, dtype=torch.float32)
+                call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(dw), K, M, N, K, 0, s)
         if has_b and ctx.needs_input_grad[2]:
-            db = torch.empty((N,), device=dy.device, dtype=torch.float32)
-            call('rih_colsum', _p(g), _ld(g), M, N, _p(db), 0, s)
+            tgt = _gt(ctx.bias_ref)
+            if tgt is not None:
+                call('rih_colsum', _p(g), _ld(g), M, N, _p(tgt), 1, s)
+            else:
+                db = torch.empty((N,), device=dy.device, dtype=torch.float32)
+                call('rih_colsum', _p(g), _ld(g), M, N, _p(db), 0, s)
         dres = dy if (has_res and ctx.needs_input_grad[4]) else None
         return dx, dw, db, None, dres, None, None
 
@@ -162,10 +202,14 @@ class LayerNormFn(Function):
         dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
         M, F = a.shape
         dx = torch.empty((M, F), device=dy.device, dtype=torch.float32)
-        dgamma = torch.zeros((F,), device=dy.device, dtype=torch.float32)
-        dbeta = torch.zeros((F,), device=dy.device, dtype=torch.float32)
+        tg, tb = _gt(gamma), _gt(beta)
+        direct = tg is not None and tb is not None
+        dgamma = tg if direct else torch.zeros((F,), device=dy.device, dtype=torch.float32)
+        dbeta = tb if direct else torch.zeros((F,), device=dy.device, dtype=torch.float32)
         call('rih_layernorm_bwd', _p(dy), _ld(dy), _p(a), _ld(a), _p(b), _ld(b) if b is not None else 0, _p(gamma), _p(beta),
              _p(mean), _p(rstd), _p(dx), F, 0, _p(dgamma), _p(dbeta), M, F, int(ctx.relu), _stream())
+        if direct:
+            dgamma = dbeta = None
         return dx, (dx if b is not None else None), dgamma, dbeta, None, None
 
 
@@ -213,6 +257,7 @@ class PosEmbFn(Function):
         y = torch.empty((B * U, F), device=x.device, dtype=torch.float32)
         call('rih_posemb_fwd', _p(x), _ld(x), _p(emb), _p(y), F, B, U, F, p, _stream())
         ctx.dims = (B, U, F, p)
+        ctx.emb_ref = emb
         return y
 
     @staticmethod
@@ -222,10 +267,11 @@ class PosEmbFn(Function):
         dx = demb = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((B * (U // p), F), device=dy.device, dtype=torch.float32)
+        tgt = _gt(ctx.emb_ref)
         if ctx.needs_input_grad[1]:
-            demb = torch.zeros((U, F), device=dy.device, dtype=torch.float32)
+            demb = tgt if tgt is not None else torch.zeros((U, F), device=dy.device, dtype=torch.float32)
         call('rih_posemb_bwd', _p(dy), _ld(dy), _p(dx), F, _p(demb), B, U, F, p, _stream())
-        return dx, demb, None, None, None
+        return dx, (None if tgt is not None else demb), None, None, None
 
 
 def posemb(x, emb, B, U, p=1):
@@ -414,6 +460,13 @@ def _geom(N, H, W, Cin, Cout, R, S, stride, pad, ldx, ldy):
     return (ctypes.c_int * 13)(N, H, W, Cin, Ho, Wo, Cout, R, S, stride, pad, ldx, ldy), Ho, Wo
 
 
+def _conv_ws(g, which, device):
+    """Workspace the tensor-core path needs for this geometry (stride-2 parity stack / zero-inserted dY); None if none."""
+    n = ctypes.c_longlong(0)
+    call('rih_conv2d_workspace', g, which, ctypes.byref(n))
+    return torch.empty(n.value, device=device, dtype=torch.float32) if n.value > 0 else None
+
+
 def _w_phys(w):
     """Conv2d weight [Cout,Cin,R,S] must be channels_last so that memory is [Cout,R,S,Cin]."""
     if w.dim() != 4 or not w.permute(0, 2, 3, 1).is_contiguous():
@@ -431,10 +484,11 @@ class Conv2dFn(Function):
         assert x.shape == (N * H * W, Cin), (x.shape, N, H, W, Cin)
         g, Ho, Wo = _geom(N, H, W, Cin, Cout, R, S, stride, pad, _ld(x), Cout)
         y = torch.empty((N * Ho * Wo, Cout), device=x.device, dtype=torch.float32)
-        call('rih_conv2d_fwd', _p(x), _p(w), _p(b), _p(y), g, int(relu), _stream())
+        call('rih_conv2d_fwd', _p(x), _p(w), _p(b), _p(y), g, int(relu), _p(_conv_ws(g, 0, x.device)), _stream())
         need_y = relu and not relu_masked_by_consumer
         ctx.save_for_backward(x, w, y if need_y else None)
         ctx.meta = (N, H, W, stride, pad, need_y, b is not None)
+        ctx.bias_ref = b
         return y
 
     @staticmethod
@@ -452,19 +506,53 @@ class Conv2dFn(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((N * H * W, Cin), device=dy.device, dtype=torch.float32)
-            call('rih_conv2d_dgrad', _p(dy), _p(w), _p(dx), g, 0, s)
+            call('rih_conv2d_dgrad', _p(dy), _p(w), _p(dx), g, 0, _p(_conv_ws(g, 1, dy.device)), s)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
             g2, _, _ = _geom(N, H, W, Cin, Cout, R, S, stride, pad, _ld(x), _ld(dy))
-            call('rih_conv2d_wgrad', _p(dy), _p(x), _p(dw), g2, 0, s)
+            tgt = _gt(w)
+            if tgt is not None:
+                call('rih_conv2d_wgrad', _p(dy), _p(x), _p(tgt), g2, 1, _p(_conv_ws(g2, 2, dy.device)), s)
+            else:
+                dw = torch.empty_like(w)
+                call('rih_conv2d_wgrad', _p(dy), _p(x), _p(dw), g2, 0, _p(_conv_ws(g2, 2, dy.device)), s)
         if has_b and ctx.needs_input_grad[2]:
-            db = torch.empty((Cout,), device=dy.device, dtype=torch.float32)
-            call('rih_colsum', _p(dy), _ld(dy), dy.shape[0], Cout, _p(db), 0, s)
+            tgt = _gt(ctx.bias_ref)
+            if tgt is not None:
+                call('rih_colsum', _p(dy), _ld(dy), dy.shape[0], Cout, _p(tgt), 1, s)
+            else:
+                db = torch.empty((Cout,), device=dy.device, dtype=torch.float32)
+                call('rih_colsum', _p(dy), _ld(dy), dy.shape[0], Cout, _p(db), 0, s)
         return dx, dw, db, None, None, None, None, None, None, None
 
 
 def conv2d(x, w, b, N, H, W, stride=1, pad=0, relu=False, relu_masked_by_consumer=False):
     return Conv2dFn.apply(x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer)
+
+
+class PatchifyFn(Function):
+    """Non-overlapping p x p patches as rows: [N*H*W, C] -> [N*(H/p)*(W/p), p*p*C]  (kernel == stride convolutions of
+    img_feat_to_grid, models/model_attn/img_attn.py:46-48,60, become one dense GEMM)."""
+
+    @staticmethod
+    def forward(ctx, x, N, H, W, p):
+        x = _rows(x)
+        C = x.shape[1]
+        P = torch.empty((N * (H // p) * (W // p), p * p * C), device=x.device, dtype=torch.float32)
+        call('rih_patchify', _p(x), _ld(x), _p(P), N, H, W, C, p, 0, _stream())
+        ctx.dims = (N, H, W, C, p)
+        return P
+
+    @staticmethod
+    def backward(ctx, dP):
+        N, H, W, C, p = ctx.dims
+        dP = dP.contiguous()
+        dx = torch.empty((N * H * W, C), device=dP.device, dtype=torch.float32)
+        call('rih_patchify', _p(dx), C, _p(dP), N, H, W, C, p, 1, _stream())
+        return dx, None, None, None, None
+
+
+def patchify(x, N, H, W, p):
+    return PatchifyFn.apply(x, N, H, W, p)
 
 
 class BatchNormFn(Function):
@@ -489,6 +577,7 @@ class BatchNormFn(Function):
              _p(y), C, M, C, int(relu), s)
         ctx.save_for_backward(x, gamma, mean, rstd, y if relu else None)
         ctx.meta = (training, relu, mask_input, res is not None)
+        ctx.beta_ref = beta
         return y
 
     @staticmethod
@@ -500,12 +589,17 @@ class BatchNormFn(Function):
         dev = dy.device
         dx = torch.empty((M, C), device=dev)
         dres = torch.empty((M, C), device=dev) if (has_res and ctx.needs_input_grad[5]) else None
-        dgamma = torch.empty((C,), device=dev); dbeta = torch.empty((C,), device=dev)
+        tg, tb = _gt(gamma), _gt(ctx.beta_ref)
+        direct = tg is not None and tb is not None
+        dgamma = tg if direct else torch.empty((C,), device=dev)
+        dbeta = tb if direct else torch.empty((C,), device=dev)
         ws = torch.empty((2 * C,), device=dev, dtype=torch.float64)
         tmp = torch.empty((2 * C,), device=dev)
         call('rih_bn_bwd', _p(dy), _ld(dy), _p(y), C, _p(x), _ld(x), _p(mean), _p(rstd), _p(gamma),
-             _p(dx), C, _p(dres), C, 0, _p(dgamma), _p(dbeta), 0, M, C, int(relu), int(training), int(mask_input),
+             _p(dx), C, _p(dres), C, 0, _p(dgamma), _p(dbeta), int(direct), M, C, int(relu), int(training), int(mask_input),
              _p(ws), _p(tmp), _stream())
+        if direct:
+            dgamma = dbeta = None
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
 
 

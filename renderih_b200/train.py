@@ -42,6 +42,8 @@ class FlatParams:
             view.copy_(p.data)
             p.data = view
             p.grad = torch.as_strided(self.grad, p.shape, p.stride(), off)
+            if p.is_cuda:
+                ops.register_grad_target(p, p.grad)   # backward kernels accumulate straight into the flat gradient
 
     def zero_grad(self):
         self.grad.zero_()
