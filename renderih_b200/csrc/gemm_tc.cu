@@ -24,9 +24,14 @@ int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, long long 
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    cudaFree(0);   // this thread (e.g. an autograd worker) has no driver context bound yet: let the runtime bind the primary one
+  }
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld); return 1; }
   return 0;
 }
@@ -39,13 +44,20 @@ int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int
   cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4};
   cuuint32_t box[4] = {32u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    cudaFree(0);
+  }
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(4d) failed (%d) N=%d H=%d W=%d C=%d ld=%lld box=%d,%d,%d", (int)r, N, H, W, C, ld, bw, bh, bn); return 1; }
   return 0;
 }
 
+static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
+void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep, const Producer& prod, int M, int N, int num_kb, int splits,
                       int kb_per_split, cudaStream_t s) {
@@ -59,7 +71,16 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep,
     attr = true;
   }
   dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
-  kern<<<grid, THREADS, smem_bytes<BN, NSPLIT>(), s>>>(ta, tb, ep, prod, num_kb, kb_per_split);
+  // TMA-store epilogue whenever the output is a 16-byte aligned matrix and no residual has to be read back
+  CUtensorMap tc_;
+  int tma_epi = 0;
+  if (!ep.res && ((reinterpret_cast<uintptr_t>(ep.c) & 15) == 0) && (ep.ldc % 4 == 0) && g_tma_epilogue) {
+    if (make_tmap_2d(&tc_, ep.c, M, N, ep.ldc, BM)) return 1;
+    tma_epi = 1;
+  } else {
+    tc_ = ta;
+  }
+  kern<<<grid, THREADS, smem_bytes<BN, NSPLIT>(), s>>>(ta, tb, tc_, ep, prod, num_kb, kb_per_split, tma_epi);
   return check_launch("gemm_tc");
 }
 static int g_nsplit = 1;   // set per call by the dispatchers below (1 = TF32, 3 = 3xTF32)
@@ -209,8 +230,12 @@ using namespace rih;
 RIH_API int rih_gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long ldb, int b_mn, float* c, int ldc,
                           int M, int N, int K, const float* bias, int relu, int accumulate, int allow_splitk, int nsplit, cudaStream_t stream) {
   RIH_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_tf32: bad shape");
-  RIH_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_tf32: nsplit must be 1 (TF32) or 3 (3xTF32)");
+  RIH_REQUIRE(nsplit == 1 || nsplit == 3 || nsplit == -1 || nsplit == -3, "gemm_tf32: nsplit must be 1 (TF32) or 3 (3xTF32); negative = per-thread-store epilogue");
+  tc::set_tma_epilogue(nsplit > 0);
+  if (nsplit < 0) nsplit = -nsplit;
   tc::set_nsplit(nsplit);
   Epilogue ep = make_epilogue(c, ldc, M, N, bias, relu, accumulate ? 1 : 0);
-  return tc::gemm_tf32(a, lda, a_mn, b, ldb, b_mn, ep, M, N, K, allow_splitk, stream);
+  int rc = tc::gemm_tf32(a, lda, a_mn, b, ldb, b_mn, ep, M, N, K, allow_splitk, stream);
+  tc::set_tma_epilogue(1);
+  return rc;
 }

@@ -58,6 +58,20 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
+// TMA store of a [rows x 128 B] shared-memory tile (plain or += reduction); bulk-group completion.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -113,7 +127,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // hi = value rounded to TF32 and lo = value - hi (exact in fp32), and D += hi*hi + lo*hi + hi*lo  (fp32-faithful).
 template <int BN, int NSPLIT> __host__ __device__ constexpr int stage_bytes() { return (BM * 128 + BN * 128) * (NSPLIT == 3 ? 2 : 1); }
 template <int BN, int NSPLIT> __host__ __device__ constexpr int num_stages() { return NSPLIT == 3 ? (BN >= 128 ? 3 : 4) : (BN >= 128 ? 3 : 4); }
-template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() { return num_stages<BN, NSPLIT>() * stage_bytes<BN, NSPLIT>() + 1024 + 256; }
+constexpr int EPI_STAGING_BYTES = 2 * BM * 128;   // two [128 x 32 fp32] staging tiles for the TMA-store epilogue
+template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() {
+  return num_stages<BN, NSPLIT>() * stage_bytes<BN, NSPLIT>() + EPI_STAGING_BYTES + 1024 + 256;
+}
 
 // ---------------------------------------------------------------- producers (TMA issue logic, one elected lane)
 // Each producer loads, for k-block `kb`, the A tile (BM x 32) to `sa` and the B tile (BN x 32) to `sb`.
@@ -211,17 +228,20 @@ struct ConvWgradProducer {
 };
 
 // ---------------------------------------------------------------- the kernel
+// tma_epi != 0: the epilogue stages 32-column chunks in 128B-swizzled shared memory and writes them with TMA stores
+// (cp.reduce.async.bulk ... .add for accumulate / split-K), fully coalesced and clipped at the tensor edge by the hardware.
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
 __global__ void __launch_bounds__(THREADS)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Epilogue ep, Producer prod, int num_kb_total,
-               int kb_per_split) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_c,
+               Epilogue ep, Producer prod, int num_kb_total, int kb_per_split, int tma_epi) {
   constexpr int STAGES = num_stages<BN, NSPLIT>();
   constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, AB_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGE_BYTES = stage_bytes<BN, NSPLIT>();   // [A | B] (+ [A_lo | B_lo] when NSPLIT == 3)
   constexpr uint32_t IDESC = make_idesc_tf32(BN, A_MN, B_MN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_STAGING_BYTES);
   uint64_t* full = bars;                 // [STAGES] TMA bytes landed
   uint64_t* empty = bars + STAGES;       // [STAGES] MMAs finished reading the stage
   uint64_t* ready = bars + 2 * STAGES;   // [STAGES] hi/lo split written (NSPLIT == 3 only)
@@ -236,6 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (tma_epi) tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 128); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -320,8 +341,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int q = warp & 3;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int m = m0 + q * 32 + lane;
-    if (num_kb > 0) {
+    const int rr = q * 32 + lane;       // row inside the tile
+    const int m = m0 + rr;
+    if (num_kb > 0 && tma_epi) {
+      const bool elected = (threadIdx.x == 64);
+      const unsigned long long dseed = ep.thresh ? (*ep.seed_ptr + ep.site * 0xD1B54A32D192ED03ull) : 0ull;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        const int nb = n0 + c * 32;
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] += __ldg(ep.bias + nb + j);
+        }
+        if (ep.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (ep.thresh) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= dropout_scale(dseed, (uint64_t)m * ep.N + nb + j, ep.thresh, ep.inv_keep);
+        }
+        if (c >= 2) {                    // staging buffer (c & 1) must have been read out by its previous TMA store
+          if (elected) tma_store_wait_read<1>();
+          epi_bar_sync();
+        }
+        uint8_t* buf = staging + (c & 1) * (BM * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)      // 16-byte chunk j of row rr lives at chunk (j ^ (rr & 7)): the SWIZZLE_128B pattern
+          *reinterpret_cast<float4*>(buf + rr * 128 + ((j ^ (rr & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async();
+        epi_bar_sync();
+        if (elected) {
+          if (ep.mode == 0) tma_store_2d(&tmap_c, buf, nb, m0);
+          else tma_reduce_add_2d(&tmap_c, buf, nb, m0);
+          tma_store_commit();
+        }
+      }
+      if (elected) tma_store_wait<0>();
+    } else if (num_kb > 0) {
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
