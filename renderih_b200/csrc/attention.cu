@@ -1,109 +1,200 @@
 // Fused multi-head attention core (SIMT fp32, exact softmax): O = dropout(softmax(Q K^T * scale)) V
-// One CTA per (batch, head): the whole K/V of a head (<= 512 keys, d <= 64) lives in shared memory.
+// One CTA per (batch, head[, query split]): the whole K/V of a head (<= 512 keys, d <= 128, d % 4 == 0) lives in shared
+// memory; each warp processes a block of query rows at once with register blocking and 128-bit shared-memory reads.
 // reference: SelfAttn.self_attn  models/model_attn/self_attn.py:63-76 ; inter_attn.inter_attn  inter_attn.py:73-123
 // Tensor addressing: element (b, row, h, dd) of T is  T + b*T_bs + row*ldT + h*d + dd.
 #include "common.cuh"
 using namespace rih;
 
-constexpr int ATT_MAXJ = 16;   // keys per lane -> Sk <= 512
 constexpr int ATT_WARPS = 8;
 
+__device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ void axpy4(float4& acc, float p, float4 v) {
+  acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y); acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
+}
+
+// Shared-memory geometry shared by forward and backward:
+//   key-like tiles [rows][d + 4] (row stride 16-byte aligned, conflict-free LDS.128 across consecutive rows)
+//   G = d/4 feature groups per lane set, JS = 32/G interleaved row splits for the P.V-type accumulations
+//   probabilities are stored permuted as p[(j % JS) * T + j / JS] so that a lane's rows are contiguous
+struct AttGeo {
+  int d, dp, G, JS, Skr, T;   // Skr = keys rounded up to 32, T = Skr / JS
+};
+__device__ __forceinline__ AttGeo make_geo(int d, int Sk) {
+  AttGeo g;
+  g.d = d; g.dp = d + 4; g.G = d / 4; if (g.G > 32) g.G = 32;
+  g.JS = 32 / g.G; g.Skr = (Sk + 31) & ~31; g.T = g.Skr / g.JS;
+  return g;
+}
+
+// acc[r] (+)= sum_j p[r][perm(j)] * M[j][g*4 .. g*4+3] for the lane's row split; then butterfly-reduce over splits.
+template <int R>
+__device__ __forceinline__ void pv_accumulate(const float* __restrict__ M, int ldm, const float* __restrict__ p, int pstride,
+                                              const AttGeo& g, int lane, float4 (&acc)[R]) {
+  const int gi = lane % g.G, js = lane / g.G;
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < g.T; t += 4) {
+    float4 p4[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) p4[r] = *reinterpret_cast<const float4*>(p + r * pstride + js * g.T + t);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = js + g.JS * (t + u);
+      const float4 v = *reinterpret_cast<const float4*>(M + (size_t)j * ldm + gi * 4);
+#pragma unroll
+      for (int r = 0; r < R; ++r) axpy4(acc[r], (u == 0 ? p4[r].x : u == 1 ? p4[r].y : u == 2 ? p4[r].z : p4[r].w), v);
+    }
+  }
+  for (int off = g.G; off < 32; off <<= 1) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, off); acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, off);
+      acc[r].z += __shfl_xor_sync(0xffffffffu, acc[r].z, off); acc[r].w += __shfl_xor_sync(0xffffffffu, acc[r].w, off);
+    }
+  }
+}
+
+template <int MAXJ>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_fwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const float* __restrict__ k, long long k_bs, int ldk,
                 const float* __restrict__ v, long long v_bs, int ldv, float* __restrict__ o, long long o_bs, int ldo,
                 float* __restrict__ lse, int H, int Sq, int Sk, int d, float scale, int rows_per_cta,
                 const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
+  constexpr int R = 4;
   const unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
-  extern __shared__ float smem[];
-  const int dp = d + 1;
-  float* Ks = smem;                    // [Sk][d+1]
-  float* Vs = Ks + (size_t)Sk * dp;    // [Sk][d]
-  float* qs = Vs + (size_t)Sk * d;     // [W][d]
-  float* ps = qs + ATT_WARPS * d;      // [W][Sk]
+  extern __shared__ __align__(16) float smem[];
+  const AttGeo g = make_geo(d, Sk);
+  float* Ks = smem;                               // [Skr][dp]  (rows >= Sk zero)
+  float* Vs = Ks + (size_t)g.Skr * g.dp;          // [Skr][dp]
+  float* qs = Vs + (size_t)g.Skr * g.dp;          // [W][R][d]
+  float* ps = qs + ATT_WARPS * R * d;             // [W][R][Skr]
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* kb = k + (size_t)b * k_bs + h * d;
   const float* vb = v + (size_t)b * v_bs + h * d;
-  for (int i = tid; i < Sk * d; i += blockDim.x) {
-    int j = i / d, dd = i - j * d;
-    Ks[j * dp + dd] = kb[(size_t)j * ldk + dd];
-    Vs[j * d + dd] = vb[(size_t)j * ldv + dd];
+  const int d4 = d / 4;
+  for (int i = tid; i < g.Skr * d4; i += blockDim.x) {
+    int j = i / d4, c = (i - j * d4) * 4;
+    float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+    if (j < Sk) {
+      kk = *reinterpret_cast<const float4*>(kb + (size_t)j * ldk + c);
+      vv = *reinterpret_cast<const float4*>(vb + (size_t)j * ldv + c);
+    }
+    *reinterpret_cast<float4*>(Ks + j * g.dp + c) = kk;
+    *reinterpret_cast<float4*>(Vs + j * g.dp + c) = vv;
   }
   __syncthreads();
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(Sq, r0 + rows_per_cta);
-  float* myq = qs + warp * d;
-  float* myp = ps + (size_t)warp * Sk;
-  for (int i = r0 + warp; i < r1; i += ATT_WARPS) {
-    const float* qrow = q + (size_t)b * q_bs + (size_t)i * ldq + h * d;
-    for (int dd = lane; dd < d; dd += 32) myq[dd] = qrow[dd];
+  float* myq = qs + warp * R * d;
+  float* myp = ps + (size_t)warp * R * g.Skr;
+  for (int i0 = r0 + warp * R; i0 < r1; i0 += ATT_WARPS * R) {
+    for (int e = lane; e < R * d4; e += 32) {
+      int r = e / d4, c = (e - r * d4) * 4;
+      int i = min(i0 + r, r1 - 1);
+      *reinterpret_cast<float4*>(myq + r * d + c) = *reinterpret_cast<const float4*>(q + (size_t)b * q_bs + (size_t)i * ldq + h * d + c);
+    }
     __syncwarp();
-    float s[ATT_MAXJ];
-    float mx = -INFINITY;
+    float s[R][MAXJ];
 #pragma unroll
-    for (int jj = 0; jj < ATT_MAXJ; ++jj) {
-      int j = lane + 32 * jj;
-      s[jj] = -INFINITY;
-      if (j < Sk) {
-        float acc = 0.f;
-        const float* kr = Ks + j * dp;
-        for (int dd = 0; dd < d; ++dd) acc = fmaf(myq[dd], kr[dd], acc);
-        s[jj] = acc * scale;
-        mx = fmaxf(mx, s[jj]);
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int jj = 0; jj < MAXJ; ++jj) s[r][jj] = 0.f;
+    for (int c = 0; c < d; c += 4) {
+      float4 q4[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) q4[r] = *reinterpret_cast<const float4*>(myq + r * d + c);
+#pragma unroll
+      for (int jj = 0; jj < MAXJ; ++jj) {
+        const int j = lane + 32 * jj;
+        if (j < g.Skr) {
+          const float4 k4 = *reinterpret_cast<const float4*>(Ks + j * g.dp + c);
+#pragma unroll
+          for (int r = 0; r < R; ++r) s[r][jj] = dot4(q4[r], k4, s[r][jj]);
+        }
       }
     }
-    mx = warp_max(mx);
-    float sum = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < ATT_MAXJ; ++jj) {
-      int j = lane + 32 * jj;
-      if (j < Sk) { s[jj] = expf(s[jj] - mx); sum += s[jj]; }
-    }
-    sum = warp_sum(sum);
-    float inv = 1.f / sum;
-    size_t drop_base = ((size_t)bh * Sq + i) * Sk;
+    for (int r = 0; r < R; ++r) {
+      float mx = -INFINITY;
 #pragma unroll
-    for (int jj = 0; jj < ATT_MAXJ; ++jj) {
-      int j = lane + 32 * jj;
-      if (j < Sk) {
-        float p = s[jj] * inv;
-        if (thresh) p *= dropout_scale(seed, drop_base + j, thresh, inv_keep);
-        myp[j] = p;
+      for (int jj = 0; jj < MAXJ; ++jj) {
+        const int j = lane + 32 * jj;
+        s[r][jj] = (j < Sk) ? s[r][jj] * scale : -INFINITY;
+        mx = fmaxf(mx, s[r][jj]);
       }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < MAXJ; ++jj) {
+        const int j = lane + 32 * jj;
+        s[r][jj] = (j < Sk) ? expf(s[r][jj] - mx) : 0.f;
+        sum += s[r][jj];
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.f / sum;
+      const int i = i0 + r;
+      const size_t drop_base = ((size_t)bh * Sq + i) * Sk;
+#pragma unroll
+      for (int jj = 0; jj < MAXJ; ++jj) {
+        const int j = lane + 32 * jj;
+        if (j < g.Skr) {
+          float p = s[r][jj] * inv;
+          if (thresh && j < Sk) p *= dropout_scale(seed, drop_base + j, thresh, inv_keep);
+          myp[r * g.Skr + (j % g.JS) * g.T + j / g.JS] = p;
+        }
+      }
+      if (lane == 0 && lse && i < r1) lse[(size_t)bh * Sq + i] = mx + logf(sum);
     }
-    if (lane == 0 && lse) lse[(size_t)bh * Sq + i] = mx + logf(sum);
     __syncwarp();
-    float* orow = o + (size_t)b * o_bs + (size_t)i * ldo + h * d;
-    for (int dd = lane; dd < d; dd += 32) {
-      float acc = 0.f;
-      for (int j = 0; j < Sk; ++j) acc = fmaf(myp[j], Vs[j * d + dd], acc);
-      orow[dd] = acc;
+    float4 acc[R];
+    pv_accumulate<R>(Vs, g.dp, myp, g.Skr, g, lane, acc);
+    if (lane < g.G) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (i0 + r < r1) *reinterpret_cast<float4*>(o + (size_t)b * o_bs + (size_t)(i0 + r) * ldo + h * d + lane * 4) = acc[r];
     }
     __syncwarp();
   }
 }
+
+static bool att_aligned(const void* p, long long bs, int ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (bs % 4 == 0) && (ld % 4 == 0); }
 
 RIH_API int rih_attn_fwd(const float* q, long long q_bs, int ldq, const float* k, long long k_bs, int ldk,
                          const float* v, long long v_bs, int ldv, float* o, long long o_bs, int ldo, float* lse,
                          int B, int H, int Sq, int Sk, int d, float scale, float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, cudaStream_t s) {
-  RIH_REQUIRE(Sk > 0 && Sk <= 32 * ATT_MAXJ, "attn_fwd: Sk=%d unsupported (max %d)", Sk, 32 * ATT_MAXJ);
-  RIH_REQUIRE(d > 0 && d <= 128, "attn_fwd: head dim %d unsupported", d);
+  RIH_REQUIRE(Sk > 0 && Sk <= 512, "attn_fwd: Sk=%d unsupported (max 512)", Sk);
+  RIH_REQUIRE(d > 0 && d <= 128 && d % 4 == 0, "attn_fwd: head dim %d unsupported (multiple of 4, <= 128)", d);
+  RIH_REQUIRE(att_aligned(q, q_bs, ldq) && att_aligned(k, k_bs, ldk) && att_aligned(v, v_bs, ldv) && att_aligned(o, o_bs, ldo),
+              "attn_fwd: operands must be 16-byte aligned with strides that are multiples of 4 floats");
   if (B * H == 0 || Sq == 0) return 0;
-  size_t smem = sizeof(float) * ((size_t)Sk * (d + 1) + (size_t)Sk * d + ATT_WARPS * d + (size_t)ATT_WARPS * Sk);
+  const int Skr = (Sk + 31) & ~31;
+  size_t smem = sizeof(float) * (2 * (size_t)Skr * (d + 4) + ATT_WARPS * 4 * d + (size_t)ATT_WARPS * 4 * Skr);
   RIH_REQUIRE(smem <= 227 * 1024, "attn_fwd: shared memory %zu too large", smem);
-  static bool attr_set = false;
-  if (!attr_set) { RIH_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
   int ysplit = 1;
-  while (B * H * ysplit < 148 * 2 && Sq / (ysplit * 2) >= 16) ysplit *= 2;
+  while (B * H * ysplit < 148 * 2 && Sq / (ysplit * 2) >= 32) ysplit *= 2;
   int rows_per_cta = cdiv(Sq, ysplit);
+  rows_per_cta = (rows_per_cta + 3) & ~3;
   dim3 grid(B * H, cdiv(Sq, rows_per_cta));
   uint32_t thresh = dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u;
-  attn_fwd_kernel<<<grid, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, lse, H, Sq, Sk, d, scale,
-                                                     rows_per_cta, seed_ptr, site, thresh, dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f);
+  float ik = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  static bool attr10 = false, attr16 = false;
+  if (Skr <= 320) {
+    if (!attr10) { RIH_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr10 = true; }
+    attn_fwd_kernel<10><<<grid, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, lse, H, Sq, Sk, d, scale, rows_per_cta, seed_ptr, site, thresh, ik);
+  } else {
+    if (!attr16) { RIH_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr16 = true; }
+    attn_fwd_kernel<16><<<grid, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, lse, H, Sq, Sk, d, scale, rows_per_cta, seed_ptr, site, thresh, ik);
+  }
   return check_launch("attn_fwd");
 }
 
 // ------------------------------------------------------------------ backward
-// Phase A (warp per query): dQ.  Phase B (warp per key): dK, dV.  No atomics, deterministic.
+// Phase A (warp per block of R query rows): dS -> dQ = scale * dS K.
+// Phase B (warp per block of R key rows)  : P~^T, dS^T -> dV = P~^T dO, dK = scale * dS^T Q.  No atomics, deterministic.
+template <int MAXJ>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_bwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const float* __restrict__ k, long long k_bs, int ldk,
                 const float* __restrict__ v, long long v_bs, int ldv, const float* __restrict__ o, long long o_bs, int ldo,
@@ -111,92 +202,179 @@ attn_bwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const floa
                 float* __restrict__ dq, long long dq_bs, int lddq, float* __restrict__ dk, long long dk_bs, int lddk,
                 float* __restrict__ dv, long long dv_bs, int lddv,
                 int H, int Sq, int Sk, int d, float scale, const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
+  constexpr int R = 2;
   const unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
-  extern __shared__ float smem[];
-  const int dp = d + 1;
-  const int Smax = max(Sq, Sk);
-  float* Qs = smem;                       // [Sq][dp]
-  float* dOs = Qs + (size_t)Sq * dp;      // [Sq][dp]
-  float* Ks = dOs + (size_t)Sq * dp;      // [Sk][dp]
-  float* Vs = Ks + (size_t)Sk * dp;       // [Sk][dp]
-  float* Dl = Vs + (size_t)Sk * dp;       // [Sq]
-  float* Ls = Dl + Sq;                    // [Sq]
-  float* w1 = Ls + Sq;                    // [W][Smax]
-  float* w2 = w1 + (size_t)ATT_WARPS * Smax;  // [W][Smax]
+  extern __shared__ __align__(16) float smem[];
+  const AttGeo gk = make_geo(d, Sk);   // splits over keys (phase A accumulations)
+  const AttGeo gq = make_geo(d, Sq);   // splits over queries (phase B accumulations)
+  const int Smax = max(gk.Skr, gq.Skr);
+  const int dp = d + 4, d4 = d / 4;
+  float* Qs = smem;                              // [Sqr][dp]
+  float* dOs = Qs + (size_t)gq.Skr * dp;         // [Sqr][dp]
+  float* Ks = dOs + (size_t)gq.Skr * dp;         // [Skr][dp]
+  float* Vs = Ks + (size_t)gk.Skr * dp;          // [Skr][dp]
+  float* Dl = Vs + (size_t)gk.Skr * dp;          // [Sqr]
+  float* Ls = Dl + gq.Skr;                       // [Sqr]
+  float* w1 = Ls + gq.Skr;                       // [W][R][Smax]
+  float* w2 = w1 + (size_t)ATT_WARPS * R * Smax; // [W][R][Smax]
+  float* rw = w2 + (size_t)ATT_WARPS * R * Smax; // [W][2][R][d]  row operands of the current block
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* qb = q + (size_t)b * q_bs + h * d;
   const float* dob = dout + (size_t)b * do_bs + h * d;
   const float* kb = k + (size_t)b * k_bs + h * d;
   const float* vb = v + (size_t)b * v_bs + h * d;
-  for (int i = tid; i < Sq * d; i += blockDim.x) {
-    int r = i / d, dd = i - r * d;
-    Qs[r * dp + dd] = qb[(size_t)r * ldq + dd];
-    dOs[r * dp + dd] = dob[(size_t)r * lddo + dd];
+  for (int i = tid; i < gq.Skr * d4; i += blockDim.x) {
+    int r = i / d4, c = (i - r * d4) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bb = a;
+    if (r < Sq) { a = *reinterpret_cast<const float4*>(qb + (size_t)r * ldq + c); bb = *reinterpret_cast<const float4*>(dob + (size_t)r * lddo + c); }
+    *reinterpret_cast<float4*>(Qs + r * dp + c) = a;
+    *reinterpret_cast<float4*>(dOs + r * dp + c) = bb;
   }
-  for (int i = tid; i < Sk * d; i += blockDim.x) {
-    int r = i / d, dd = i - r * d;
-    Ks[r * dp + dd] = kb[(size_t)r * ldk + dd];
-    Vs[r * dp + dd] = vb[(size_t)r * ldv + dd];
+  for (int i = tid; i < gk.Skr * d4; i += blockDim.x) {
+    int r = i / d4, c = (i - r * d4) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bb = a;
+    if (r < Sk) { a = *reinterpret_cast<const float4*>(kb + (size_t)r * ldk + c); bb = *reinterpret_cast<const float4*>(vb + (size_t)r * ldv + c); }
+    *reinterpret_cast<float4*>(Ks + r * dp + c) = a;
+    *reinterpret_cast<float4*>(Vs + r * dp + c) = bb;
   }
-  // D_i = sum_dd dO_i * O_i
-  for (int i = warp; i < Sq; i += ATT_WARPS) {
-    const float* orow = o + (size_t)b * o_bs + (size_t)i * ldo + h * d;
-    const float* drow = dob + (size_t)i * lddo;
+  for (int i = warp; i < gq.Skr; i += ATT_WARPS) {
     float acc = 0.f;
-    for (int dd = lane; dd < d; dd += 32) acc += orow[dd] * drow[dd];
+    if (i < Sq) {
+      const float* orow = o + (size_t)b * o_bs + (size_t)i * ldo + h * d;
+      const float* drow = dob + (size_t)i * lddo;
+      for (int dd = lane; dd < d; dd += 32) acc += orow[dd] * drow[dd];
+    }
     acc = warp_sum(acc);
-    if (lane == 0) { Dl[i] = acc; Ls[i] = lse[(size_t)bh * Sq + i]; }
+    if (lane == 0) { Dl[i] = acc; Ls[i] = (i < Sq) ? lse[(size_t)bh * Sq + i] : 0.f; }
   }
   __syncthreads();
-  float* my1 = w1 + (size_t)warp * Smax;
-  float* my2 = w2 + (size_t)warp * Smax;
-  // ---- phase A: dQ_i = scale * sum_j dS_ij K_j
-  for (int i = warp; i < Sq; i += ATT_WARPS) {
-    const float* qr = Qs + i * dp;
-    const float* dr = dOs + i * dp;
-    float Li = Ls[i], Di = Dl[i];
-    size_t drop_base = ((size_t)bh * Sq + i) * Sk;
-    for (int j = lane; j < Sk; j += 32) {
-      const float* kr = Ks + j * dp;
-      const float* vr = Vs + j * dp;
-      float sc = 0.f, dpt = 0.f;
-      for (int dd = 0; dd < d; ++dd) { sc = fmaf(qr[dd], kr[dd], sc); dpt = fmaf(dr[dd], vr[dd], dpt); }
-      float p = expf(sc * scale - Li);
-      float m = thresh ? dropout_scale(seed, drop_base + j, thresh, inv_keep) : 1.f;
-      my1[j] = p * (m * dpt - Di);
+  float* my1 = w1 + (size_t)warp * R * Smax;
+  float* my2 = w2 + (size_t)warp * R * Smax;
+  float* ra = rw + warp * 2 * R * d;      // [R][d] first row operand
+  float* rb = ra + R * d;                 // [R][d] second row operand
+  // ---------------- phase A: query-row blocks
+  for (int i0 = warp * R; i0 < Sq; i0 += ATT_WARPS * R) {
+    for (int e = lane; e < R * d4; e += 32) {
+      int r = e / d4, c = (e - r * d4) * 4;
+      int i = min(i0 + r, Sq - 1);
+      *reinterpret_cast<float4*>(ra + r * d + c) = *reinterpret_cast<const float4*>(Qs + i * dp + c);
+      *reinterpret_cast<float4*>(rb + r * d + c) = *reinterpret_cast<const float4*>(dOs + i * dp + c);
     }
     __syncwarp();
-    float* dqr = dq + (size_t)b * dq_bs + (size_t)i * lddq + h * d;
-    for (int dd = lane; dd < d; dd += 32) {
-      float acc = 0.f;
-      for (int j = 0; j < Sk; ++j) acc = fmaf(my1[j], Ks[j * dp + dd], acc);
-      dqr[dd] = acc * scale;
+    float sc[R][MAXJ], dpt[R][MAXJ];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int jj = 0; jj < MAXJ; ++jj) { sc[r][jj] = 0.f; dpt[r][jj] = 0.f; }
+    for (int c = 0; c < d; c += 4) {
+      float4 q4[R], g4[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) { q4[r] = *reinterpret_cast<const float4*>(ra + r * d + c); g4[r] = *reinterpret_cast<const float4*>(rb + r * d + c); }
+#pragma unroll
+      for (int jj = 0; jj < MAXJ; ++jj) {
+        const int j = lane + 32 * jj;
+        if (j < gk.Skr) {
+          const float4 k4 = *reinterpret_cast<const float4*>(Ks + j * dp + c);
+          const float4 v4 = *reinterpret_cast<const float4*>(Vs + j * dp + c);
+#pragma unroll
+          for (int r = 0; r < R; ++r) { sc[r][jj] = dot4(q4[r], k4, sc[r][jj]); dpt[r][jj] = dot4(g4[r], v4, dpt[r][jj]); }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = min(i0 + r, Sq - 1);
+      const float Li = Ls[i], Di = Dl[i];
+      const size_t drop_base = ((size_t)bh * Sq + i) * Sk;
+#pragma unroll
+      for (int jj = 0; jj < MAXJ; ++jj) {
+        const int j = lane + 32 * jj;
+        if (j < gk.Skr) {
+          float dsv = 0.f;
+          if (j < Sk) {
+            const float p = expf(sc[r][jj] * scale - Li);
+            const float m = thresh ? dropout_scale(seed, drop_base + j, thresh, inv_keep) : 1.f;
+            dsv = p * (m * dpt[r][jj] - Di);
+          }
+          my1[r * Smax + (j % gk.JS) * gk.T + j / gk.JS] = dsv;
+        }
+      }
+    }
+    __syncwarp();
+    float4 acc[R];
+    pv_accumulate<R>(Ks, dp, my1, Smax, gk, lane, acc);
+    if (lane < gk.G) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (i0 + r < Sq) {
+          float4 t = acc[r]; t.x *= scale; t.y *= scale; t.z *= scale; t.w *= scale;
+          *reinterpret_cast<float4*>(dq + (size_t)b * dq_bs + (size_t)(i0 + r) * lddq + h * d + lane * 4) = t;
+        }
     }
     __syncwarp();
   }
-  // ---- phase B: dV_j = sum_i Pt_ij dO_i ; dK_j = scale * sum_i dS_ij Q_i
-  for (int j = warp; j < Sk; j += ATT_WARPS) {
-    const float* kr = Ks + j * dp;
-    const float* vr = Vs + j * dp;
-    for (int i = lane; i < Sq; i += 32) {
-      const float* qr = Qs + i * dp;
-      const float* dr = dOs + i * dp;
-      float sc = 0.f, dpt = 0.f;
-      for (int dd = 0; dd < d; ++dd) { sc = fmaf(qr[dd], kr[dd], sc); dpt = fmaf(dr[dd], vr[dd], dpt); }
-      float p = expf(sc * scale - Ls[i]);
-      float m = thresh ? dropout_scale(seed, ((size_t)bh * Sq + i) * Sk + j, thresh, inv_keep) : 1.f;
-      my1[i] = p * m;
-      my2[i] = p * (m * dpt - Dl[i]);
+  // ---------------- phase B: key-row blocks
+  for (int j0 = warp * R; j0 < Sk; j0 += ATT_WARPS * R) {
+    for (int e = lane; e < R * d4; e += 32) {
+      int r = e / d4, c = (e - r * d4) * 4;
+      int j = min(j0 + r, Sk - 1);
+      *reinterpret_cast<float4*>(ra + r * d + c) = *reinterpret_cast<const float4*>(Ks + j * dp + c);
+      *reinterpret_cast<float4*>(rb + r * d + c) = *reinterpret_cast<const float4*>(Vs + j * dp + c);
     }
     __syncwarp();
-    float* dkr = dk + (size_t)b * dk_bs + (size_t)j * lddk + h * d;
-    float* dvr = dv + (size_t)b * dv_bs + (size_t)j * lddv + h * d;
-    for (int dd = lane; dd < d; dd += 32) {
-      float ak = 0.f, av = 0.f;
-      for (int i = 0; i < Sq; ++i) { av = fmaf(my1[i], dOs[i * dp + dd], av); ak = fmaf(my2[i], Qs[i * dp + dd], ak); }
-      dkr[dd] = ak * scale;
-      dvr[dd] = av;
+    float sc[R][MAXJ], dpt[R][MAXJ];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int ii = 0; ii < MAXJ; ++ii) { sc[r][ii] = 0.f; dpt[r][ii] = 0.f; }
+    for (int c = 0; c < d; c += 4) {
+      float4 k4[R], v4[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) { k4[r] = *reinterpret_cast<const float4*>(ra + r * d + c); v4[r] = *reinterpret_cast<const float4*>(rb + r * d + c); }
+#pragma unroll
+      for (int ii = 0; ii < MAXJ; ++ii) {
+        const int i = lane + 32 * ii;
+        if (i < gq.Skr) {
+          const float4 q4 = *reinterpret_cast<const float4*>(Qs + i * dp + c);
+          const float4 g4 = *reinterpret_cast<const float4*>(dOs + i * dp + c);
+#pragma unroll
+          for (int r = 0; r < R; ++r) { sc[r][ii] = dot4(q4, k4[r], sc[r][ii]); dpt[r][ii] = dot4(g4, v4[r], dpt[r][ii]); }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int j = min(j0 + r, Sk - 1);
+#pragma unroll
+      for (int ii = 0; ii < MAXJ; ++ii) {
+        const int i = lane + 32 * ii;
+        if (i < gq.Skr) {
+          float pt = 0.f, dsv = 0.f;
+          if (i < Sq) {
+            const float p = expf(sc[r][ii] * scale - Ls[i]);
+            const float m = thresh ? dropout_scale(seed, ((size_t)bh * Sq + i) * Sk + j, thresh, inv_keep) : 1.f;
+            pt = p * m;
+            dsv = p * (m * dpt[r][ii] - Dl[i]);
+          }
+          const int pi = (i % gq.JS) * gq.T + i / gq.JS;
+          my1[r * Smax + pi] = pt;
+          my2[r * Smax + pi] = dsv;
+        }
+      }
+    }
+    __syncwarp();
+    float4 av[R], ak[R];
+    pv_accumulate<R>(dOs, dp, my1, Smax, gq, lane, av);
+    pv_accumulate<R>(Qs, dp, my2, Smax, gq, lane, ak);
+    if (lane < gq.G) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (j0 + r < Sk) {
+          float4 t = ak[r]; t.x *= scale; t.y *= scale; t.z *= scale; t.w *= scale;
+          *reinterpret_cast<float4*>(dk + (size_t)b * dk_bs + (size_t)(j0 + r) * lddk + h * d + lane * 4) = t;
+          *reinterpret_cast<float4*>(dv + (size_t)b * dv_bs + (size_t)(j0 + r) * lddv + h * d + lane * 4) = av[r];
+        }
     }
     __syncwarp();
   }
@@ -207,16 +385,26 @@ RIH_API int rih_attn_bwd(const float* q, long long q_bs, int ldq, const float* k
                          const float* dout, long long do_bs, int lddo, const float* lse,
                          float* dq, long long dq_bs, int lddq, float* dk, long long dk_bs, int lddk, float* dv, long long dv_bs, int lddv,
                          int B, int H, int Sq, int Sk, int d, float scale, float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, cudaStream_t s) {
-  RIH_REQUIRE(d > 0 && d <= 128, "attn_bwd: head dim %d unsupported", d);
+  RIH_REQUIRE(d > 0 && d <= 128 && d % 4 == 0, "attn_bwd: head dim %d unsupported (multiple of 4, <= 128)", d);
+  RIH_REQUIRE(Sk <= 512 && Sq <= 512, "attn_bwd: sequence length above 512 unsupported (Sq=%d Sk=%d)", Sq, Sk);
+  RIH_REQUIRE(att_aligned(q, q_bs, ldq) && att_aligned(k, k_bs, ldk) && att_aligned(v, v_bs, ldv) && att_aligned(o, o_bs, ldo) &&
+              att_aligned(dout, do_bs, lddo) && att_aligned(dq, dq_bs, lddq) && att_aligned(dk, dk_bs, lddk) && att_aligned(dv, dv_bs, lddv),
+              "attn_bwd: operands must be 16-byte aligned with strides that are multiples of 4 floats");
   if (B * H == 0 || Sq == 0 || Sk == 0) return 0;
-  int Smax = Sq > Sk ? Sq : Sk;
-  size_t smem = sizeof(float) * ((size_t)(2 * Sq + 2 * Sk) * (d + 1) + 2 * (size_t)Sq + 2 * (size_t)ATT_WARPS * Smax);
+  const int Sqr = (Sq + 31) & ~31, Skr = (Sk + 31) & ~31, Smax = Sqr > Skr ? Sqr : Skr;
+  size_t smem = sizeof(float) * ((size_t)(2 * Sqr + 2 * Skr) * (d + 4) + 2 * (size_t)Sqr + 2 * (size_t)ATT_WARPS * 2 * Smax + (size_t)ATT_WARPS * 4 * d);
   RIH_REQUIRE(smem <= 227 * 1024, "attn_bwd: shared memory %zu too large (Sq=%d Sk=%d d=%d)", smem, Sq, Sk, d);
-  static bool attr_set = false;
-  if (!attr_set) { RIH_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
   uint32_t thresh = dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u;
-  attn_bwd_kernel<<<B * H, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, dout, do_bs, lddo, lse,
-                                                      dq, dq_bs, lddq, dk, dk_bs, lddk, dv, dv_bs, lddv, H, Sq, Sk, d, scale, seed_ptr, site, thresh,
-                                                      dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f);
+  float ik = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  static bool attr10 = false, attr16 = false;
+  if (Smax <= 320) {
+    if (!attr10) { RIH_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr10 = true; }
+    attn_bwd_kernel<10><<<B * H, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, dout, do_bs, lddo, lse,
+                                                             dq, dq_bs, lddq, dk, dk_bs, lddk, dv, dv_bs, lddv, H, Sq, Sk, d, scale, seed_ptr, site, thresh, ik);
+  } else {
+    if (!attr16) { RIH_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr16 = true; }
+    attn_bwd_kernel<16><<<B * H, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, dout, do_bs, lddo, lse,
+                                                             dq, dq_bs, lddq, dk, dk_bs, lddk, dv, dv_bs, lddv, H, Sq, Sk, d, scale, seed_ptr, site, thresh, ik);
+  }
   return check_launch("attn_bwd");
 }

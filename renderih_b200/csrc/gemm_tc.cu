@@ -56,6 +56,8 @@ int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int
   return 0;
 }
 
+static int g_persistent = 1;     // 0 = one CTA per tile (non-persistent kernel; debug / comparison)
+void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
 void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
@@ -79,6 +81,24 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep,
     tma_epi = 1;
   } else {
     tc_ = ta;
+  }
+  if (g_persistent) {
+    auto pk = gemm_tc_persistent_kernel<BN, A_MN, B_MN, Producer, NSPLIT>;
+    static bool pattr = false;
+    if (!pattr) {
+      if (cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN, NSPLIT>()) != cudaSuccess) {
+        set_error("gemm_tc(persistent): cannot raise dynamic shared memory to %d", smem_bytes<BN, NSPLIT>());
+        return 2;
+      }
+      pattr = true;
+    }
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+    const int tiles_n = cdiv(N, BN), tiles_m = cdiv(M, BM);
+    const long long total = (long long)tiles_n * tiles_m * splits;
+    const int ctas = (int)(total < num_sms ? total : num_sms);
+    pk<<<ctas, persistent_threads<NSPLIT>(), smem_bytes<BN, NSPLIT>(), s>>>(ta, tb, tc_, ep, prod, num_kb, kb_per_split, tiles_m, tiles_n, splits, tma_epi);
+    return check_launch("gemm_tc_persistent");
   }
   kern<<<grid, THREADS, smem_bytes<BN, NSPLIT>(), s>>>(ta, tb, tc_, ep, prod, num_kb, kb_per_split, tma_epi);
   return check_launch("gemm_tc");
@@ -230,12 +250,18 @@ using namespace rih;
 RIH_API int rih_gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long ldb, int b_mn, float* c, int ldc,
                           int M, int N, int K, const float* bias, int relu, int accumulate, int allow_splitk, int nsplit, cudaStream_t stream) {
   RIH_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_tf32: bad shape");
-  RIH_REQUIRE(nsplit == 1 || nsplit == 3 || nsplit == -1 || nsplit == -3, "gemm_tf32: nsplit must be 1 (TF32) or 3 (3xTF32); negative = per-thread-store epilogue");
+  // nsplit: 1 = TF32, 3 = 3xTF32.  Debug variants: negative = per-thread-store epilogue, +10 = non-persistent kernel.
+  int v = nsplit < 0 ? -nsplit : nsplit;
+  const int nonpersistent = v >= 10;
+  if (nonpersistent) v -= 10;
+  RIH_REQUIRE(v == 1 || v == 3, "gemm_tf32: nsplit must be 1 (TF32) or 3 (3xTF32)");
   tc::set_tma_epilogue(nsplit > 0);
-  if (nsplit < 0) nsplit = -nsplit;
+  tc::set_persistent(!nonpersistent);
+  nsplit = v;
   tc::set_nsplit(nsplit);
   Epilogue ep = make_epilogue(c, ldc, M, N, bias, relu, accumulate ? 1 : 0);
   int rc = tc::gemm_tf32(a, lda, a_mn, b, ldb, b_mn, ep, M, N, K, allow_splitk, stream);
   tc::set_tma_epilogue(1);
+  tc::set_persistent(1);
   return rc;
 }

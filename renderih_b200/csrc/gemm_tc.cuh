@@ -398,6 +398,211 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------- persistent variant
+// One CTA per SM loops over output tiles (static round-robin).  The shared-memory stage ring runs continuously across
+// tiles, the accumulator is double-buffered in TMEM (2 x BN columns) and the epilogue has its own four warps, so the
+// TMA stores of tile i overlap the loads / MMAs of tile i+1 and the per-CTA prologue (TMEM allocation, barrier init,
+// descriptor fetch) is paid once per SM instead of once per tile.
+//   warp 0 = TMA producer | warp 1 = MMA issuer + TMEM owner | warps 2..5 = hi/lo splitter (NSPLIT == 3 only) |
+//   last 4 warps = epilogue (TMEM -> registers -> swizzled smem -> TMA store / reduce-add)
+template <int NSPLIT> __host__ __device__ constexpr int persistent_threads() { return NSPLIT == 3 ? 320 : 192; }
+
+template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
+__global__ void __launch_bounds__(persistent_threads<NSPLIT>())
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_c,
+                          Epilogue ep, Producer prod, int num_kb_total, int kb_per_split, int tiles_m, int tiles_n, int splits, int tma_epi) {
+  constexpr int STAGES = num_stages<BN, NSPLIT>();
+  constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, AB_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = stage_bytes<BN, NSPLIT>();
+  constexpr uint32_t IDESC = make_idesc_tf32(BN, A_MN, B_MN);
+  constexpr int EPI_WARP0 = (NSPLIT == 3) ? 6 : 2;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_STAGING_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* ready = bars + 2 * STAGES;
+  uint64_t* tmem_full = bars + 3 * STAGES;       // [2]
+  uint64_t* tmem_empty = bars + 3 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = tiles_m * tiles_n * splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    if (tma_epi) tma_prefetch_desc(&tmap_c);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int t, int& m0, int& n0, int& kb_beg, int& nkb) {
+    const int ni = t % tiles_n;
+    const int r = t / tiles_n;
+    const int mi = r % tiles_m;
+    const int z = r / tiles_m;
+    m0 = mi * BM; n0 = ni * BN;
+    kb_beg = z * kb_per_split;
+    nkb = min(num_kb_total - kb_beg, kb_per_split);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0, kb_beg, nkb;
+        tile_coords(t, m0, n0, kb_beg, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], AB_BYTES);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          prod.load(&tmap_a, &tmap_b, kb_beg + kb, m0, n0, sa, sa + A_BYTES, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, tc = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+        int m0, n0, kb_beg, nkb;
+        tile_coords(t, m0, n0, kb_beg, nkb);
+        const uint32_t acc = tc & 1, aph = (tc >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], aph ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(NSPLIT == 3 ? &ready[s] : &full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            uint64_t ad = A_MN ? make_smem_desc(sa + k * 1024, BK * 128, 512, 1) : make_smem_desc(sa + k * 32, 16, 1024, 2);
+            uint64_t bd = B_MN ? make_smem_desc(sb + k * 1024, BK * 128, 512, 1) : make_smem_desc(sb + k * 32, 16, 1024, 2);
+            umma_tf32(tmem_d, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+            if constexpr (NSPLIT == 3) {
+              const uint64_t lo_off = (uint64_t)(AB_BYTES >> 4);
+              umma_tf32(tmem_d, ad + lo_off, bd, IDESC, 1u);
+              umma_tf32(tmem_d, ad, bd + lo_off, IDESC, 1u);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (NSPLIT == 3 && warp < EPI_WARP0) {
+    // hi/lo splitter warps 2..5
+    const int tsp = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int m0, n0, kb_beg, nkb;
+      tile_coords(t, m0, n0, kb_beg, nkb);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        uint4* hi = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES);
+        uint4* lo = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + AB_BYTES);
+#pragma unroll 4
+        for (int i = tsp; i < AB_BYTES / 16; i += 128) {
+          uint4 v = hi[i];
+          uint4 h = make_uint4((v.x + 0x1000u) & 0xFFFFE000u, (v.y + 0x1000u) & 0xFFFFE000u, (v.z + 0x1000u) & 0xFFFFE000u, (v.w + 0x1000u) & 0xFFFFE000u);
+          uint4 l;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          hi[i] = h;
+          lo[i] = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(&ready[s]);
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    const int q = warp & 3;
+    const int rr = q * 32 + lane;
+    const bool elected = (threadIdx.x == EPI_WARP0 * 32);
+    const unsigned long long dseed = ep.thresh ? (*ep.seed_ptr + ep.site * 0xD1B54A32D192ED03ull) : 0ull;
+    uint32_t tc = 0, cc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+      int m0, n0, kb_beg, nkb;
+      tile_coords(t, m0, n0, kb_beg, nkb);
+      const uint32_t acc = tc & 1, aph = (tc >> 1) & 1;
+      mbar_wait(&tmem_full[acc], aph);
+      tc_fence_after();
+      const int m = m0 + rr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        if (c == BN / 32 - 1) {        // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        const int nb = n0 + c * 32;
+        if (tma_epi) {
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] += __ldg(ep.bias + nb + j);
+          }
+          if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (ep.thresh) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= dropout_scale(dseed, (uint64_t)m * ep.N + nb + j, ep.thresh, ep.inv_keep);
+          }
+          if (cc >= 2) {
+            if (elected) tma_store_wait_read<1>();
+            epi_bar_sync();
+          }
+          uint8_t* buf = staging + (cc & 1) * (BM * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(buf + rr * 128 + ((j ^ (rr & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async();
+          epi_bar_sync();
+          if (elected) {
+            if (ep.mode == 0) tma_store_2d(&tmap_c, buf, nb, m0);
+            else tma_reduce_add_2d(&tmap_c, buf, nb, m0);
+            tma_store_commit();
+          }
+          ++cc;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ep.store4(m, nb + j * 4, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        }
+      }
+    }
+    if (elected && tma_epi) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
