@@ -22,10 +22,12 @@ __device__ __forceinline__ void axpy4(float4& acc, float p, float4 v) {
 struct AttGeo {
   int d, dp, G, JS, Skr, T;   // Skr = keys rounded up to 32, T = Skr / JS
 };
-__device__ __forceinline__ AttGeo make_geo(int d, int Sk) {
+__host__ __device__ __forceinline__ AttGeo make_geo(int d, int Sk) {
   AttGeo g;
   g.d = d; g.dp = d + 4; g.G = d / 4; if (g.G > 32) g.G = 32;
-  g.JS = 32 / g.G; g.Skr = (Sk + 31) & ~31; g.T = g.Skr / g.JS;
+  g.JS = 32 / g.G;
+  const int q = (4 * g.JS > 32) ? 4 * g.JS : 32;      // rows padded so that T = Skr / JS is a multiple of 4 (float4 reads of p)
+  g.Skr = ((Sk + q - 1) / q) * q; g.T = g.Skr / g.JS;
   return g;
 }
 
@@ -170,7 +172,7 @@ RIH_API int rih_attn_fwd(const float* q, long long q_bs, int ldq, const float* k
   RIH_REQUIRE(att_aligned(q, q_bs, ldq) && att_aligned(k, k_bs, ldk) && att_aligned(v, v_bs, ldv) && att_aligned(o, o_bs, ldo),
               "attn_fwd: operands must be 16-byte aligned with strides that are multiples of 4 floats");
   if (B * H == 0 || Sq == 0) return 0;
-  const int Skr = (Sk + 31) & ~31;
+  const int Skr = make_geo(d, Sk).Skr;
   size_t smem = sizeof(float) * (2 * (size_t)Skr * (d + 4) + ATT_WARPS * 4 * d + (size_t)ATT_WARPS * 4 * Skr);
   RIH_REQUIRE(smem <= 227 * 1024, "attn_fwd: shared memory %zu too large", smem);
   int ysplit = 1;
@@ -391,7 +393,7 @@ RIH_API int rih_attn_bwd(const float* q, long long q_bs, int ldq, const float* k
               att_aligned(dout, do_bs, lddo) && att_aligned(dq, dq_bs, lddq) && att_aligned(dk, dk_bs, lddk) && att_aligned(dv, dv_bs, lddv),
               "attn_bwd: operands must be 16-byte aligned with strides that are multiples of 4 floats");
   if (B * H == 0 || Sq == 0 || Sk == 0) return 0;
-  const int Sqr = (Sq + 31) & ~31, Skr = (Sk + 31) & ~31, Smax = Sqr > Skr ? Sqr : Skr;
+  const int Sqr = make_geo(d, Sq).Skr, Skr = make_geo(d, Sk).Skr, Smax = Sqr > Skr ? Sqr : Skr;
   size_t smem = sizeof(float) * ((size_t)(2 * Sqr + 2 * Skr) * (d + 4) + 2 * (size_t)Sqr + 2 * (size_t)ATT_WARPS * 2 * Smax + (size_t)ATT_WARPS * 4 * d);
   RIH_REQUIRE(smem <= 227 * 1024, "attn_bwd: shared memory %zu too large (Sq=%d Sk=%d d=%d)", smem, Sq, Sk, d);
   uint32_t thresh = dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u;
