@@ -32,7 +32,9 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='images per GPU (reference TRAIN.BATCH_SIZE)')
     ap.add_argument('--no-graph', action='store_true')
-    ap.add_argument('--gemm-mode', default='simt', choices=['simt', 'tf32', 'tf32x3'], help='arithmetic of 1x1-conv / Linear GEMMs')
+    ap.add_argument('--gemm-mode', default='ref', choices=['ref', 'simt', 'tf32', 'tf32rn', 'tf32x3'],
+                    help="arithmetic of the conv / Linear GEMMs; 'ref' = the reference's own GPU numerics class: TF32 (round-to-nearest) "
+                         "convolutions as cuDNN runs them by default + fp32-faithful (3xTF32) nn.Linear GEMMs")
     ap.add_argument('--cpu-batch', type=int, default=4, help='bounded CPU sample size for cpu_baseline / --impl reference')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -94,7 +96,7 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def cpu_port_step_time(batch, steps=1, warmup=0):
+def cpu_port_step_time(batch, steps=1, warmup=0, budget_s=1e9):
     """The reference algorithm's CPU port (oracle/model_ref.py): forward + calc_loss_GCN + backward, fp32, all host threads."""
     import torch
     from oracle import fixtures, model_ref
@@ -111,7 +113,10 @@ def cpu_port_step_time(batch, steps=1, warmup=0):
     la = fixtures.make_loss_assets(a, A.synthetic_mano(0, 'left'), A.synthetic_mano(0, 'right'))
     img, labels = fixtures.make_image(batch), fixtures.make_labels(batch)
     times = []
+    t_begin = time.perf_counter()
     for i in range(warmup + steps):
+        if times and time.perf_counter() - t_begin > budget_s:
+            break
         for v in sd.values():
             v.grad = None
         t0 = time.perf_counter()
@@ -121,17 +126,18 @@ def cpu_port_step_time(batch, steps=1, warmup=0):
         t1 = time.perf_counter()
         if i >= warmup:
             times.append(t1 - t0)
-    return sum(times) / len(times), cores
+    return sum(times) / len(times), cores, len(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    t, cores = cpu_port_step_time(args.cpu_batch, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    # bounded: the CPU port needs tens of seconds per step on a big host, so at most ~3 steps / ~150 s are timed
+    t, cores, nsteps = cpu_port_step_time(args.cpu_batch, steps=max(1, min(args.steps, 3)), warmup=0, budget_s=150.0)
     v = args.cpu_batch / t
     line = {'impl': 'reference', 'metric': 'images/sec fwd+bwd (calc_loss_GCN) @256x256', 'value': v, 'unit': 'images/s',
-            'n_gpus': args.gpus, 'steps': max(1, args.steps), 'warmup': min(1, args.warmup), 'ms_per_step': t * 1e3,
+            'n_gpus': args.gpus, 'steps': nsteps, 'warmup': 0, 'ms_per_step': t * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'HandNET_GCN ResNet50 cfg, fwd+calc_loss_GCN+bwd, CPU sample batch %d of the batch-64 workload' % args.cpu_batch},
             'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
@@ -140,8 +146,10 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def dominant_kernel_roofline(torch, batch, pk):
-    """Time the single most expensive kernel of the step alone: the 3x3 128->128 conv at 64x64 (2.42 GF/img fwd)."""
+def dominant_kernel_roofline(torch, batch, pk, conv_mode):
+    """Time the single most expensive kernel of the step alone: the 3x3 128->128 conv at 64x64 (2.42 GF/img fwd),
+    in the arithmetic mode the step runs its convolutions in.  `traffic` = DRAM bytes per launch of that kernel from the
+    committed `ncu --set full` capture (profiles/r01_roofline_kernel.json), when present."""
     from renderih_b200 import ops
     N, H, C = batch, 64, 128
     x = torch.randn(N * H * H, C, device='cuda')
@@ -159,9 +167,18 @@ def dominant_kernel_roofline(torch, batch, pk):
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * N * H * H * C * 9 * C
     ach = flops / (ms * 1e-3) / 1e12
-    return {'bound': 'tensor', 'kernel': 'conv3x3 128->128 @64x64 (gemm_simt_kernel<128,128,ConvFwdA>)', 'achieved': ach, 'peak': pk['tflops'],
-            'unit': 'TFLOP/s', 'frac': ach / pk['tflops'], 'traffic': None, 'ms_per_launch': ms,
-            'algorithmic_flops_per_launch': flops, 'peak_source': pk['src'] + ' bf16 dense burst'}
+    kname = {'simt': 'gemm_simt_kernel<128,128,8,8,ConvFwdA,DenseK>', 'tf32': 'gemm_tc_persistent_kernel<128,0,0,ConvFwdProducer<128>,1>',
+             'tf32rn': 'gemm_tc_persistent_kernel<128,0,0,ConvFwdProducer<128>,2>', 'tf32x3': 'gemm_tc_persistent_kernel<128,0,0,ConvFwdProducer<128>,3>'}[conv_mode]
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_roofline_kernel.json')) as f:
+            traffic = json.load(f).get(conv_mode, {}).get('dram_bytes_per_launch')
+    except Exception:
+        pass
+    return {'bound': 'tensor', 'kernel': 'conv3x3 128->128 @64x64 batch %d fwd (%s)' % (batch, kname), 'achieved': ach, 'peak': pk['tflops'],
+            'unit': 'TFLOP/s', 'frac': ach / pk['tflops'], 'traffic': traffic, 'ms_per_launch': ms,
+            'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': 4.0 * (2 * N * H * H * C + 9 * C * C),
+            'peak_source': pk['src'] + ' bf16 dense burst (TF32 tensor peak is half of it)'}
 
 
 def run_ours(args):
@@ -181,7 +198,8 @@ def run_ours(args):
     from renderih_b200.train import TrainStep
     _lib.load()
     from renderih_b200 import ops as _ops
-    _ops.set_gemm_mode(args.gemm_mode, args.gemm_mode)
+    conv_mode, lin_mode = ('tf32rn', 'tf32x3') if args.gemm_mode == 'ref' else (args.gemm_mode, args.gemm_mode)
+    _ops.set_gemm_mode(conv_mode, lin_mode)
     cfg = load_cfg()
     a = A.synthetic_assets(0)
     torch.manual_seed(cfg.SEED)
@@ -250,13 +268,15 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     pk = peaks()
-    roof = dominant_kernel_roofline(torch, B, pk)
+    roof = dominant_kernel_roofline(torch, B, pk, conv_mode)
     total_imgs = B * world
     value = total_imgs / (ms_dev * 1e-3)
     e2e = total_imgs / (ms_e2e * 1e-3)
     line = {'metric': 'images/sec fwd+bwd @batch64 256x256 (training step: fwd + calc_loss_GCN + bwd + AdamW%s)' % (' + NCCL grad all-reduce' if world > 1 else ''),
             'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_dev,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if args.gemm_mode == 'simt' else 'tf32 (1x1 conv / Linear GEMMs on tcgen05, fp32 accumulate; rest f32)', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': {'simt': 'f32', 'ref': 'f32 storage; tcgen05 TF32(rn) convolutions (cuDNN-default class of the reference) + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate',
+                      'tf32': 'tf32 (truncating) conv+Linear, fp32 accumulate/storage', 'tf32rn': 'tf32 (rn) conv+Linear, fp32 accumulate/storage',
+                      'tf32x3': '3xTF32 (fp32-faithful) conv+Linear, fp32 accumulate/storage'}[args.gemm_mode], 'data': 'synthetic',
             'config': {'workload': 'BASELINE.json configs[2]: HandNET_GCN ResNet50 cfg, batch %d/GPU, 256x256, train mode (batch-stat BN, dropout 0.05), '
                                    'random-init weights, synthetic graph/MANO assets' % B,
                        'global_batch': total_imgs, 'parallelism': 'dp%d' % world, 'cuda_graph': not args.no_graph,
@@ -267,7 +287,7 @@ def run_ours(args):
             'gpu_launches': calls_per_step * args.steps, 'launches_per_step': calls_per_step,
             'clocks': clocks, 'roofline': roof, 'last_loss': losses[-1] if losses else None}
     if not args.skip_cpu_baseline and world == 1:
-        t, cores = cpu_port_step_time(args.cpu_batch, steps=1, warmup=0)
+        t, cores, _ = cpu_port_step_time(args.cpu_batch, steps=1, warmup=0)
         line['cpu_baseline'] = {'value': args.cpu_batch / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                                 'sample': 'batch %d fwd+calc_loss_GCN+bwd once, oracle/model_ref.py (torch CPU fp32, %d threads)' % (args.cpu_batch, cores)}
     print(json.dumps(line))

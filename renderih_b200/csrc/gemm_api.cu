@@ -11,6 +11,7 @@ int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long
               int allow_splitk, cudaStream_t s);
 bool conv_tc_supported(const ConvGeom& g, int which);
 void set_nsplit(int n);
+extern int g_stats_fused;
 long long conv_tc_workspace(const ConvGeom& g, int which);
 int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s);
 int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s);
@@ -18,17 +19,18 @@ int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom
 } }
 
 // Arithmetic mode of the GEMM-class ops: 0 = SIMT fp32 (exact), 1 = tcgen05 TF32 multiplicands / fp32 accumulate,
-// 2 = tcgen05 3xTF32 (hi/lo split in shared memory, fp32-faithful).
+// 2 = tcgen05 3xTF32 (hi/lo split in shared memory, fp32-faithful), 3 = tcgen05 TF32 with round-to-nearest operand
+// conversion in shared memory (single MMA pass, unbiased -- the cuDNN / cuBLAS TF32 convention).
 // index 0: convolutions (the reference's cuDNN path runs TF32 by default on this GPU), index 1: nn.Linear GEMMs.
 static int g_mode[2] = {0, 0};
 RIH_API int rih_set_gemm_mode(int conv_mode, int linear_mode) {
-  RIH_REQUIRE(conv_mode >= 0 && conv_mode <= 2 && linear_mode >= 0 && linear_mode <= 2, "set_gemm_mode: modes must be 0 (simt), 1 (tf32) or 2 (tf32x3)");
+  RIH_REQUIRE(conv_mode >= 0 && conv_mode <= 3 && linear_mode >= 0 && linear_mode <= 3, "set_gemm_mode: modes must be 0 (simt), 1 (tf32), 2 (tf32x3) or 3 (tf32rn)");
   g_mode[0] = conv_mode; g_mode[1] = linear_mode;
   return 0;
 }
 static inline bool use_tc(int which) {
   if (g_mode[which] == 0) return false;
-  tc::set_nsplit(g_mode[which] == 2 ? 3 : 1);
+  tc::set_nsplit(g_mode[which] == 2 ? 3 : (g_mode[which] == 3 ? 2 : 1));
   return true;
 }
 static inline bool tc_ok(const void* p, long long ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0); }
@@ -99,15 +101,30 @@ RIH_API int rih_conv2d_workspace(const int* geom, int which, long long* floats) 
   return 0;
 }
 
+extern "C" int rih_bn_colstats(const float* x, int ld, int M, int C, double* ws, cudaStream_t s);
+static int conv2d_fwd_impl(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, int relu, float* ws, double* stats,
+                           cudaStream_t stream);
+
+// `stats` (optional, double[2*Cout]): receives the per-channel sum and sum of squares of the stored output (the following
+// BatchNorm's batch statistics) -- accumulated inside the GEMM epilogue on the tensor-core path, by a separate pass otherwise.
 RIH_API int rih_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, const int* geom,
-                           int relu, float* ws, cudaStream_t stream) {
+                           int relu, float* ws, double* stats, cudaStream_t stream) {
   ConvGeom g;
   RIH_REQUIRE(parse_geom(geom, g) == 0, "conv2d_fwd: inconsistent geometry");
+  if (stats) RIH_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * g.Cout, stream));
+  tc::g_stats_fused = 0;
+  if (int e = conv2d_fwd_impl(x, w, bias, y, g, relu, ws, stats, stream)) return e;
+  if (stats && !tc::g_stats_fused) return rih_bn_colstats(y, g.ldy, g.N * g.Ho * g.Wo, g.Cout, stats, stream);
+  return 0;
+}
+static int conv2d_fwd_impl(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, int relu, float* ws, double* stats,
+                           cudaStream_t stream) {
   long long M = (long long)g.N * g.Ho * g.Wo;
   int K = g.R * g.S * g.Cin;
   RIH_REQUIRE(M < (1ll << 31), "conv2d_fwd: too many output pixels");
   DenseK b{w, K, g.Cout, is_vec_ok(w, K)};
   Epilogue ep = make_epilogue(y, g.ldy, (int)M, g.Cout, bias, relu, 0);
+  ep.stats = stats;
   if (g.R == 1 && g.S == 1 && g.stride == 1 && g.pad == 0) {
     DenseK a{x, g.ldx, (int)M, is_vec_ok(x, g.ldx) && (K % 4 == 0)};
     if (use_tc(0) && tc_ok(x, g.ldx) && tc_ok(w, K))

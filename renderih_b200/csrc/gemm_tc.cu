@@ -56,6 +56,7 @@ int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int
   return 0;
 }
 
+int g_stats_fused = 0;            // set by the launcher when the epilogue accumulated ep.stats (fused BatchNorm statistics)
 static int g_persistent = 1;     // 0 = one CTA per tile (non-persistent kernel; debug / comparison)
 void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
@@ -97,9 +98,12 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep,
     const int tiles_n = cdiv(N, BN), tiles_m = cdiv(M, BM);
     const long long total = (long long)tiles_n * tiles_m * splits;
     const int ctas = (int)(total < num_sms ? total : num_sms);
+    if (ep.stats && !(tma_epi && splits == 1)) ep.stats = nullptr;
+    g_stats_fused = ep.stats != nullptr;
     pk<<<ctas, persistent_threads<NSPLIT>(), smem_bytes<BN, NSPLIT>(), s>>>(ta, tb, tc_, ep, prod, num_kb, kb_per_split, tiles_m, tiles_n, splits, tma_epi);
     return check_launch("gemm_tc_persistent");
   }
+  g_stats_fused = 0;
   kern<<<grid, THREADS, smem_bytes<BN, NSPLIT>(), s>>>(ta, tb, tc_, ep, prod, num_kb, kb_per_split, tma_epi);
   return check_launch("gemm_tc");
 }
@@ -108,9 +112,10 @@ template <int BN, bool A_MN, bool B_MN, class Producer>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep, const Producer& prod, int M, int N, int num_kb, int splits,
                       int kb_per_split, cudaStream_t s) {
   if (g_nsplit == 3) return launch_one<BN, A_MN, B_MN, Producer, 3>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s);
+  if (g_nsplit == 2 && g_persistent) return launch_one<BN, A_MN, B_MN, Producer, 2>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s);
   return launch_one<BN, A_MN, B_MN, Producer, 1>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s);
 }
-void set_nsplit(int n) { g_nsplit = (n == 3) ? 3 : 1; }
+void set_nsplit(int n) { g_nsplit = (n == 3) ? 3 : (n == 2 ? 2 : 1); }
 
 // split-K planning over k-blocks of 32; switches the epilogue to atomic accumulation when splitting
 static void plan_splitk(Epilogue& ep, int M, int N, int BN, int num_kb, int allow, int& splits, int& kb_per_split, cudaStream_t s) {
@@ -254,7 +259,7 @@ RIH_API int rih_gemm_tf32(const float* a, long long lda, int a_mn, const float* 
   int v = nsplit < 0 ? -nsplit : nsplit;
   const int nonpersistent = v >= 10;
   if (nonpersistent) v -= 10;
-  RIH_REQUIRE(v == 1 || v == 3, "gemm_tf32: nsplit must be 1 (TF32) or 3 (3xTF32)");
+  RIH_REQUIRE(v == 1 || v == 2 || v == 3, "gemm_tf32: nsplit must be 1 (TF32, truncating), 2 (TF32, round-to-nearest) or 3 (3xTF32)");
   tc::set_tma_epilogue(nsplit > 0);
   tc::set_persistent(!nonpersistent);
   nsplit = v;

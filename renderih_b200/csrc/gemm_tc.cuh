@@ -123,7 +123,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// NSPLIT = 1: single-pass TF32.  NSPLIT = 3: error-compensated "3xTF32": every operand tile is split in shared memory into
+// NSPLIT = 1: single-pass TF32 (hardware truncates the fp32 operands).  NSPLIT = 2: single-pass TF32 with the operands
+// rounded to nearest in shared memory first (unbiased, what cuDNN/cuBLAS TF32 do).  NSPLIT = 3: error-compensated "3xTF32": every operand tile is split in shared memory into
 // hi = value rounded to TF32 and lo = value - hi (exact in fp32), and D += hi*hi + lo*hi + hi*lo  (fp32-faithful).
 template <int BN, int NSPLIT> __host__ __device__ constexpr int stage_bytes() { return (BM * 128 + BN * 128) * (NSPLIT == 3 ? 2 : 1); }
 template <int BN, int NSPLIT> __host__ __device__ constexpr int num_stages() { return NSPLIT == 3 ? (BN >= 128 ? 3 : 4) : (BN >= 128 ? 3 : 4); }
@@ -405,7 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // descriptor fetch) is paid once per SM instead of once per tile.
 //   warp 0 = TMA producer | warp 1 = MMA issuer + TMEM owner | warps 2..5 = hi/lo splitter (NSPLIT == 3 only) |
 //   last 4 warps = epilogue (TMEM -> registers -> swizzled smem -> TMA store / reduce-add)
-template <int NSPLIT> __host__ __device__ constexpr int persistent_threads() { return NSPLIT == 3 ? 320 : 192; }
+template <int NSPLIT> __host__ __device__ constexpr int persistent_threads() { return NSPLIT >= 2 ? 320 : 192; }
 
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
 __global__ void __launch_bounds__(persistent_threads<NSPLIT>())
@@ -415,7 +416,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, AB_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGE_BYTES = stage_bytes<BN, NSPLIT>();
   constexpr uint32_t IDESC = make_idesc_tf32(BN, A_MN, B_MN);
-  constexpr int EPI_WARP0 = (NSPLIT == 3) ? 6 : 2;
+  constexpr int EPI_WARP0 = (NSPLIT >= 2) ? 6 : 2;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -487,7 +488,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(NSPLIT == 3 ? &ready[s] : &full[s], ph);
+          mbar_wait(NSPLIT >= 2 ? &ready[s] : &full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
@@ -507,7 +508,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         umma_commit(&tmem_full[acc]);
       }
     }
-  } else if (NSPLIT == 3 && warp < EPI_WARP0) {
+  } else if (NSPLIT >= 2 && warp < EPI_WARP0) {
     // hi/lo splitter warps 2..5
     const int tsp = threadIdx.x - 64;
     uint32_t it = 0;
@@ -530,7 +531,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
           l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
           hi[i] = h;
-          lo[i] = l;
+          if constexpr (NSPLIT == 3) lo[i] = l;
         }
         fence_proxy_async();
         mbar_arrive(&ready[s]);
@@ -585,6 +586,20 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             if (ep.mode == 0) tma_store_2d(&tmap_c, buf, nb, m0);
             else tma_reduce_add_2d(&tmap_c, buf, nb, m0);
             tma_store_commit();
+          }
+          if (ep.stats) {
+            // fused BatchNorm statistics: this warp sums column `lane` of the chunk over its 32 rows straight from the staging
+            // tile (one 128-byte row per LDS wavefront: conflict-free), then one fp64 atomic pair per column per warp
+            const int col = nb + lane;
+            float sm = 0.f, sq = 0.f;
+            const int rows_valid = min(32, ep.M - (m0 + q * 32));
+            const int jc = lane >> 2, wi = lane & 3;
+            for (int r = 0; r < rows_valid; ++r) {
+              const int row = q * 32 + r;
+              const float x = *reinterpret_cast<const float*>(buf + row * 128 + ((jc ^ (row & 7)) << 4) + wi * 4);
+              sm += x; sq = fmaf(x, x, sq);
+            }
+            if (col < ep.N && rows_valid > 0) { atomicAdd(ep.stats + col, (double)sm); atomicAdd(ep.stats + ep.N + col, (double)sq); }
           }
           ++cc;
         } else {

@@ -107,18 +107,27 @@ __global__ void bn_eval_prep_kernel(const float* __restrict__ rm, const float* _
   mean[c] = rm[c];
   rstd[c] = 1.f / sqrtf(rv[c] + eps);
 }
-RIH_API int rih_bn_stats(const float* x, int ld, int M, int C, float eps, float momentum, double* ws,
-                         float* mean, float* rstd, float* running_mean, float* running_var, cudaStream_t s) {
-  RIH_REQUIRE(M > 0 && C > 0, "bn_stats: empty");
+// column sums / sums of squares of x into ws[0:C], ws[C:2C] (fp64; ws is zeroed here)
+RIH_API int rih_bn_colstats(const float* x, int ld, int M, int C, double* ws, cudaStream_t s) {
+  RIH_REQUIRE(M > 0 && C > 0, "bn_colstats: empty");
   RIH_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, s));
   int gx = cdiv(C, 32);
   int target = cdiv(148 * 8, gx);
   int rows_per_cta = max(64, cdiv(M, target));
   dim3 grid(gx, cdiv(M, rows_per_cta)), block(32, 8);
   bn_stats_kernel<<<grid, block, 0, s>>>(x, ld, M, C, rows_per_cta, ws);
-  if (int e = check_launch("bn_stats")) return e;
+  return check_launch("bn_stats");
+}
+// mean / rstd (+ running statistics update) from column sums produced by rih_bn_colstats or by a convolution's fused epilogue
+RIH_API int rih_bn_finalize(const double* ws, int M, int C, float eps, float momentum, float* mean, float* rstd,
+                            float* running_mean, float* running_var, cudaStream_t s) {
   bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(ws, M, C, eps, momentum, mean, rstd, running_mean, running_var);
   return check_launch("bn_finalize");
+}
+RIH_API int rih_bn_stats(const float* x, int ld, int M, int C, float eps, float momentum, double* ws,
+                         float* mean, float* rstd, float* running_mean, float* running_var, cudaStream_t s) {
+  if (int e = rih_bn_colstats(x, ld, M, C, ws, s)) return e;
+  return rih_bn_finalize(ws, M, C, eps, momentum, mean, rstd, running_mean, running_var, s);
 }
 RIH_API int rih_bn_eval_prep(const float* rm, const float* rv, int C, float eps, float* mean, float* rstd, cudaStream_t s) {
   bn_eval_prep_kernel<<<cdiv(C, 128), 128, 0, s>>>(rm, rv, C, eps, mean, rstd);

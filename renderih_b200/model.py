@@ -55,19 +55,21 @@ def _cl(conv):
 def _conv_bn(x, conv, bn, N, H, W, training, relu=True, res=None):
     """torchvision order Conv -> BN -> (+res) -> ReLU"""
     k = conv.kernel_size[0]
-    y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0])
+    stats = torch.empty(2 * conv.out_channels, device=x.device, dtype=torch.float64) if training else None
+    y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], stats=stats)
     Ho = (H + 2 * conv.padding[0] - k) // conv.stride[0] + 1
     y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, res=res, training=training,
-                      momentum=bn.momentum, eps=bn.eps, relu=relu)
+                      momentum=bn.momentum, eps=bn.eps, relu=relu, stats=stats)
     return y, Ho
 
 
 def _conv_relu_bn(x, conv, bn, N, H, W, training):
     """repo order Conv -> ReLU -> BN (models/model_zoo/__init__.py:56-82, models/encoder.py:52-54)"""
+    stats = torch.empty(2 * conv.out_channels, device=x.device, dtype=torch.float64) if training else None
     y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], relu=True,
-                   relu_masked_by_consumer=True)
+                   relu_masked_by_consumer=True, stats=stats)
     return ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training=training,
-                         momentum=bn.momentum, eps=bn.eps, relu=False, mask_input=True)
+                         momentum=bn.momentum, eps=bn.eps, relu=False, mask_input=True, stats=stats)
 
 
 class ResNetSimple_decoder(nn.Module):

@@ -14,12 +14,13 @@ from . import _lib
 call = _lib.call
 
 
-GEMM_MODES = {'simt': 0, 'tf32': 1, 'tf32x3': 2}
+GEMM_MODES = {'simt': 0, 'tf32': 1, 'tf32x3': 2, 'tf32rn': 3}
 
 
 def set_gemm_mode(conv='simt', linear='simt'):
     """Arithmetic of the GEMM-class kernels: 'simt' = exact fp32 CUDA-core path, 'tf32' = tcgen05 tensor cores with TF32
     multiplicands and fp32 accumulation (what the reference's cuDNN convolutions use by default on this GPU),
+    'tf32rn' = TF32 with the operands rounded to nearest in shared memory before the MMA (unbiased; the cuDNN convention),
     'tf32x3' = the same tensor-core kernels with an in-kernel hi/lo operand split and 3 MMAs per step (fp32-faithful)."""
     call('rih_set_gemm_mode', GEMM_MODES[conv], GEMM_MODES[linear])
 
@@ -478,13 +479,13 @@ class Conv2dFn(Function):
     """NHWC conv (+bias)(+relu) -- nn.Conv2d sites of models/encoder.py, torchvision resnet, img_attn.py:48"""
 
     @staticmethod
-    def forward(ctx, x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer):
+    def forward(ctx, x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer, stats):
         x = _rows(x); _w_phys(_check(w, 'weight'))
         Cout, Cin, R, S = w.shape
         assert x.shape == (N * H * W, Cin), (x.shape, N, H, W, Cin)
         g, Ho, Wo = _geom(N, H, W, Cin, Cout, R, S, stride, pad, _ld(x), Cout)
         y = torch.empty((N * Ho * Wo, Cout), device=x.device, dtype=torch.float32)
-        call('rih_conv2d_fwd', _p(x), _p(w), _p(b), _p(y), g, int(relu), _p(_conv_ws(g, 0, x.device)), _stream())
+        call('rih_conv2d_fwd', _p(x), _p(w), _p(b), _p(y), g, int(relu), _p(_conv_ws(g, 0, x.device)), _p(stats), _stream())
         need_y = relu and not relu_masked_by_consumer
         ctx.save_for_backward(x, w, y if need_y else None)
         ctx.meta = (N, H, W, stride, pad, need_y, b is not None)
@@ -522,11 +523,12 @@ class Conv2dFn(Function):
             else:
                 db = torch.empty((Cout,), device=dy.device, dtype=torch.float32)
                 call('rih_colsum', _p(dy), _ld(dy), dy.shape[0], Cout, _p(db), 0, s)
-        return dx, dw, db, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None
 
 
-def conv2d(x, w, b, N, H, W, stride=1, pad=0, relu=False, relu_masked_by_consumer=False):
-    return Conv2dFn.apply(x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer)
+def conv2d(x, w, b, N, H, W, stride=1, pad=0, relu=False, relu_masked_by_consumer=False, stats=None):
+    """stats: optional float64 [2*Cout] buffer that receives the output's per-channel sum / sum of squares (fused BN statistics)."""
+    return Conv2dFn.apply(x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer, stats)
 
 
 class PatchifyFn(Function):
@@ -559,13 +561,15 @@ class BatchNormFn(Function):
     """BatchNorm2d over NHWC rows (+residual)(+relu); training uses per-rank batch statistics (no SyncBN)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, rmean, rvar, res, training, momentum, eps, relu, mask_input):
+    def forward(ctx, x, gamma, beta, rmean, rvar, res, training, momentum, eps, relu, mask_input, stats):
         x = _rows(x)
         M, C = x.shape
         dev = x.device
         mean = torch.empty((C,), device=dev); rstd = torch.empty((C,), device=dev)
         s = _stream()
-        if training:
+        if training and stats is not None:    # column sums already produced by the convolution's epilogue
+            call('rih_bn_finalize', _p(stats), M, C, float(eps), float(momentum), _p(mean), _p(rstd), _p(rmean), _p(rvar), s)
+        elif training:
             ws = torch.empty((2 * C,), device=dev, dtype=torch.float64)
             call('rih_bn_stats', _p(x), _ld(x), M, C, float(eps), float(momentum), _p(ws), _p(mean), _p(rstd), _p(rmean), _p(rvar), s)
         else:
@@ -600,11 +604,11 @@ class BatchNormFn(Function):
              _p(ws), _p(tmp), _stream())
         if direct:
             dgamma = dbeta = None
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
 
 
-def batchnorm(x, gamma, beta, rmean, rvar, res=None, training=True, momentum=0.1, eps=1e-5, relu=False, mask_input=False):
-    return BatchNormFn.apply(x, gamma, beta, rmean, rvar, res, training, momentum, eps, relu, mask_input)
+def batchnorm(x, gamma, beta, rmean, rvar, res=None, training=True, momentum=0.1, eps=1e-5, relu=False, mask_input=False, stats=None):
+    return BatchNormFn.apply(x, gamma, beta, rmean, rvar, res, training, momentum, eps, relu, mask_input, stats)
 
 
 class MaxPoolFn(Function):

@@ -111,6 +111,26 @@ def test_forward_eval_tensor_core_tf32_mode(gold, setup):
         assert e < 5e-2, (k, e)
 
 
+def test_forward_eval_reference_numerics_class_mode(gold, setup):
+    """bench.py's default arithmetic: TF32 (round-to-nearest) convolutions -- what the reference's cuDNN convolutions do on
+    this GPU by default -- and fp32-faithful 3xTF32 nn.Linear GEMMs.  Stated tolerance: 1e-2 relative to each tensor's max."""
+    from renderih_b200 import ops
+    a, sd, model = setup
+    model.load_state_dict(sd)
+    model.eval()
+    img = fixtures.make_image(gold['batch'])
+    ops.set_gemm_mode('tf32rn', 'tf32x3')
+    try:
+        with torch.no_grad():
+            out = flat(model(img.cuda()))
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+    errs = {k: rel_err(out[k], v) for k, v in gold['eval'].items()}
+    print('ref-class (tf32rn conv + 3xTF32 linear) eval rel errs vs reference golden:', {k: '%.2e' % e for k, e in errs.items()})
+    for k, e in errs.items():
+        assert e < 1e-2, (k, e)
+
+
 def test_forward_eval_tensor_core_3xtf32_mode(gold, setup):
     """tcgen05 with the in-kernel hi/lo split (3 MMAs per step): fp32-faithful tensor-core arithmetic.
     Stated tolerance: 1e-3 relative to each tensor's max magnitude (measured 3e-5 ... 4.5e-4: limited by the tensor core's

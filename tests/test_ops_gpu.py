@@ -126,6 +126,24 @@ def test_conv_relu_bn_order(ops):
         check(a, r, 2e-4, 'conv-relu-bn d' + n)
 
 
+@pytest.mark.parametrize('mode', ['simt', 'tf32x3'])
+def test_conv_bn_fused_statistics(ops, mode):
+    """BatchNorm batch statistics accumulated inside the convolution's epilogue == statistics of a separate pass."""
+    N, H, C, Co = 3, 16, 64, 160      # 768 pixels (6 row tiles), Cout not a multiple of the 128-wide tile
+    x = T(N, C, H, H, grad=False)
+    w = (torch.randn(Co, C, 1, 1) * 0.1).to(DEV).contiguous(memory_format=torch.channels_last)
+    xr = x.permute(0, 2, 3, 1).contiguous().reshape(-1, C)
+    stats = torch.full((2 * Co,), 7.0, device=DEV, dtype=torch.float64)
+    ops.set_gemm_mode(mode, mode)
+    try:
+        y = ops.conv2d(xr, w, None, N, H, H, relu=True, relu_masked_by_consumer=True, stats=stats)
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+    torch.cuda.synchronize()
+    check(stats[:Co].float(), y.double().sum(0).float(), 1e-5, 'fused column sums')
+    check(stats[Co:].float(), (y.double() ** 2).sum(0).float(), 1e-5, 'fused column sums of squares')
+
+
 @pytest.mark.parametrize('training', [True, False])
 def test_batchnorm_residual_relu(ops, training):
     M, C = 2048, 256
@@ -417,3 +435,19 @@ def test_gemm_3xtf32_is_fp32_faithful(M, N, K, a_mn, b_mn):
     e32 = rel(A_ @ B_.t(), ref)
     print('3xtf32 gemm %dx%dx%d (a_mn=%d b_mn=%d): rel err %.2e   (torch fp32 matmul: %.2e)' % (M, N, K, a_mn, b_mn, e, e32))
     assert e < 2e-5, e   # limited by the tensor core's internal (truncating) accumulation over K, not by the operand split
+
+
+def test_gemm_tf32_round_to_nearest_is_unbiased():
+    """NSPLIT=2: operands rounded to nearest TF32 in shared memory (cuDNN/cuBLAS convention) -> smaller, unbiased error
+    than the hardware's truncation."""
+    from renderih_b200._lib import call
+    M, N, K = 2048, 256, 1024
+    a, b = (T(M, K, grad=False).abs() + 0.1), (T(N, K, seed=1, grad=False).abs() + 0.1)     # all-positive: truncation bias shows
+    ref = a.double() @ b.double().t()
+    errs = {}
+    for ns in (1, 2):
+        c = torch.empty((M, N), device=DEV)
+        call('rih_gemm_tf32', a.data_ptr(), K, 0, b.data_ptr(), K, 0, c.data_ptr(), N, M, N, K, None, 0, 0, 0, ns, torch.cuda.current_stream().cuda_stream)
+        errs[ns] = float(((c.double() - ref) / ref).mean())
+    print('mean signed relative error: truncating %.2e, round-to-nearest %.2e' % (errs[1], errs[2]))
+    assert abs(errs[2]) < 2e-5 and abs(errs[1]) > 1e-4

@@ -25,7 +25,8 @@ def main():
     from renderih_b200.loss import GraphLoss, calc_loss_GCN
     from renderih_b200.model import load_model
     from renderih_b200.train import FlatParams, trainable_used_params
-    ops.set_gemm_mode(args.gemm_mode, args.gemm_mode)
+    cm, lm = ('tf32rn', 'tf32x3') if args.gemm_mode == 'ref' else (args.gemm_mode, args.gemm_mode)
+    ops.set_gemm_mode(cm, lm)
     cfg = load_cfg()
     a = A.synthetic_assets(0)
     torch.manual_seed(88)
