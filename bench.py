@@ -32,7 +32,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='images per GPU (reference TRAIN.BATCH_SIZE)')
     ap.add_argument('--no-graph', action='store_true')
-    ap.add_argument('--gemm-mode', default='ref', choices=['ref', 'simt', 'tf32', 'tf32rn', 'tf32x3'],
+    ap.add_argument('--gemm-mode', default='ref', choices=['ref', 'ref2', 'simt', 'tf32', 'tf32rn', 'tf32c', 'tf32x3'],
                     help="arithmetic of the conv / Linear GEMMs; 'ref' = the reference's own GPU numerics class: TF32 (round-to-nearest) "
                          "convolutions as cuDNN runs them by default + fp32-faithful (3xTF32) nn.Linear GEMMs")
     ap.add_argument('--cpu-batch', type=int, default=4, help='bounded CPU sample size for cpu_baseline / --impl reference')
@@ -167,7 +167,7 @@ def dominant_kernel_roofline(torch, batch, pk, conv_mode):
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * N * H * H * C * 9 * C
     ach = flops / (ms * 1e-3) / 1e12
-    kname = {'simt': 'gemm_simt_kernel<128,128,8,8,ConvFwdA,DenseK>', 'tf32': 'gemm_tc_persistent_kernel<128,0,0,ConvFwdProducer<128>,1>',
+    kname = {'tf32c': 'gemm_tc_persistent_kernel<128,0,0,ConvFwdProducer<128>,1>', 'simt': 'gemm_simt_kernel<128,128,8,8,ConvFwdA,DenseK>', 'tf32': 'gemm_tc_persistent_kernel<128,0,0,ConvFwdProducer<128>,1>',
              'tf32rn': 'gemm_tc_persistent_kernel<128,0,0,ConvFwdProducer<128>,2>', 'tf32x3': 'gemm_tc_persistent_kernel<128,0,0,ConvFwdProducer<128>,3>'}[conv_mode]
     traffic = None
     try:
@@ -198,7 +198,7 @@ def run_ours(args):
     from renderih_b200.train import TrainStep
     _lib.load()
     from renderih_b200 import ops as _ops
-    conv_mode, lin_mode = ('tf32rn', 'tf32x3') if args.gemm_mode == 'ref' else (args.gemm_mode, args.gemm_mode)
+    conv_mode, lin_mode = {'ref': ('tf32rn', 'tf32x3'), 'ref2': ('tf32c', 'tf32x3')}.get(args.gemm_mode, (args.gemm_mode, args.gemm_mode))
     _ops.set_gemm_mode(conv_mode, lin_mode)
     cfg = load_cfg()
     a = A.synthetic_assets(0)
@@ -275,7 +275,8 @@ def run_ours(args):
     line = {'metric': 'images/sec fwd+bwd @batch64 256x256 (training step: fwd + calc_loss_GCN + bwd + AdamW%s)' % (' + NCCL grad all-reduce' if world > 1 else ''),
             'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_dev,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': {'simt': 'f32', 'ref': 'f32 storage; tcgen05 TF32(rn) convolutions (cuDNN-default class of the reference) + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate',
-                      'tf32': 'tf32 (truncating) conv+Linear, fp32 accumulate/storage', 'tf32rn': 'tf32 (rn) conv+Linear, fp32 accumulate/storage',
+                      'tf32': 'tf32 (truncating) conv+Linear, fp32 accumulate/storage', 'tf32c': 'tf32 (truncating, mean-compensated) conv+Linear, fp32 accumulate/storage',
+                      'ref2': 'f32 storage; tcgen05 TF32 (truncating, mean-compensated) convolutions + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate', 'tf32rn': 'tf32 (rn) conv+Linear, fp32 accumulate/storage',
                       'tf32x3': '3xTF32 (fp32-faithful) conv+Linear, fp32 accumulate/storage'}[args.gemm_mode], 'data': 'synthetic',
             'config': {'workload': 'BASELINE.json configs[2]: HandNET_GCN ResNet50 cfg, batch %d/GPU, 256x256, train mode (batch-stat BN, dropout 0.05), '
                                    'random-init weights, synthetic graph/MANO assets' % B,

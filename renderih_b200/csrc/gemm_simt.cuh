@@ -163,6 +163,7 @@ struct Epilogue {
   const float* res; int ldres;                 // optional residual added after activation/dropout
   const unsigned long long* seed_ptr;          // dropout: device-resident base seed (CUDA-graph friendly)
   unsigned long long site; uint32_t thresh; float inv_keep;
+  float scale;                                 // accumulator scale applied first (1 = none; bias-compensated truncating TF32 uses 1 + 7.05e-4)
   double* stats;                               // optional [2*N] column sum / sum of squares of the stored values (fused BatchNorm statistics)
   __device__ __forceinline__ void store4(int m, int n, float4 v) const {
     if (m >= M || n >= N) return;
@@ -172,7 +173,7 @@ struct Epilogue {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (n + i >= N) break;
-      float t = r[i];
+      float t = r[i] * scale;
       if (bias) t += __ldg(bias + n + i);
       if (relu) t = fmaxf(t, 0.f);
       if (thresh) t *= dropout_scale(seed, (uint64_t)m * N + n + i, thresh, inv_keep);
@@ -185,7 +186,7 @@ struct Epilogue {
 };
 static inline Epilogue make_epilogue(float* c, int ldc, int M, int N, const float* bias, int relu, int mode) {
   Epilogue e; e.c = c; e.ldc = ldc; e.M = M; e.N = N; e.bias = bias; e.relu = relu; e.mode = mode;
-  e.res = nullptr; e.ldres = 0; e.seed_ptr = nullptr; e.site = 0; e.thresh = 0; e.inv_keep = 1.f; e.stats = nullptr;
+  e.res = nullptr; e.ldres = 0; e.seed_ptr = nullptr; e.site = 0; e.thresh = 0; e.inv_keep = 1.f; e.stats = nullptr; e.scale = 1.f;
   return e;
 }
 

@@ -107,10 +107,13 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep,
   kern<<<grid, THREADS, smem_bytes<BN, NSPLIT>(), s>>>(ta, tb, tc_, ep, prod, num_kb, kb_per_split, tma_epi);
   return check_launch("gemm_tc");
 }
-static int g_nsplit = 1;   // set per call by the dispatchers below (1 = TF32, 3 = 3xTF32)
+static int g_nsplit = 1;   // set per call by the dispatchers below (1 = TF32, 2 = TF32 rn, 3 = 3xTF32)
+static float g_scale = 1.f; // accumulator scale (bias-compensated truncating TF32)
+void set_acc_scale(float s) { g_scale = s; }
 template <int BN, bool A_MN, bool B_MN, class Producer>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep, const Producer& prod, int M, int N, int num_kb, int splits,
                       int kb_per_split, cudaStream_t s) {
+  ep.scale = g_scale;
   if (g_nsplit == 3) return launch_one<BN, A_MN, B_MN, Producer, 3>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s);
   if (g_nsplit == 2 && g_persistent) return launch_one<BN, A_MN, B_MN, Producer, 2>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s);
   return launch_one<BN, A_MN, B_MN, Producer, 1>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s);

@@ -352,6 +352,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
         const int nb = n0 + c * 32;
+        if (ep.scale != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= ep.scale;
+        }
         if (ep.bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] += __ldg(ep.bias + nb + j);
@@ -560,6 +564,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         }
         const int nb = n0 + c * 32;
         if (tma_epi) {
+          if (ep.scale != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ep.scale;
+          }
           if (ep.bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] += __ldg(ep.bias + nb + j);

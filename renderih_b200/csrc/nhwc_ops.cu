@@ -50,7 +50,7 @@ RIH_API int rih_nhwc_to_nchw(const float* x, float* y, int N, int C, int HW, int
 __global__ void copy2d_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, long long rows, int C, int acc) {
   long long total = rows * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / C; int c = (int)(i - r * C);
+    long long r; int c; divmod(i, C, total < (1ll << 32), r, c);
     float v = x[r * ldx + c];
     float* q = y + r * ldy + c;
     *q = acc ? (*q + v) : v;
@@ -141,7 +141,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, int ldx, const floa
                                 long long M, int C4, int relu) {
   long long total = M * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / C4; int c = (int)(i - r * C4) * 4;
+    long long r; int c; divmod(i, C4, total < (1ll << 32), r, c); c *= 4;
     float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
     float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
     float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
@@ -207,7 +207,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, cons
   long long total = M * C4;
   float invM = 1.f / (float)M;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / C4; int c = (int)(i - r * C4) * 4;
+    long long r; int c; divmod(i, C4, total < (1ll << 32), r, c); c *= 4;
     float4 g4 = *reinterpret_cast<const float4*>(dy + r * lddy + c);
     float g[4] = {g4.x, g4.y, g4.z, g4.w};
     if (relu) {
@@ -269,7 +269,7 @@ __global__ void relu_bwd_kernel(const float* __restrict__ dy, int lddy, const fl
                                 long long rows, int C) {
   long long total = rows * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / C; int c = (int)(i - r * C);
+    long long r; int c; divmod(i, C, total < (1ll << 32), r, c);
     dx[r * lddx + c] = y[r * ldy + c] > 0.f ? dy[r * lddy + c] : 0.f;
   }
 }

@@ -240,7 +240,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, int ldx, float* __re
   long long total = rows * C;
   unsigned long long seed = *seed_ptr + site * 0xD1B54A32D192ED03ull;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / C; int c = (int)(i - r * C);
+    long long r; int c; divmod(i, C, total < (1ll << 32), r, c);
     y[r * ldy + c] = x[r * ldx + c] * dropout_scale(seed, (uint64_t)i, thresh, inv_keep);
   }
 }
@@ -261,7 +261,7 @@ __global__ void epilogue_bwd_kernel(const float* __restrict__ dy, int lddy, cons
   long long total = rows * C;
   unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / C; int c = (int)(i - r * C);
+    long long r; int c; divmod(i, C, total < (1ll << 32), r, c);
     float v = dy[r * lddy + c];
     if (thresh) v *= dropout_scale(seed, (uint64_t)i, thresh, inv_keep);
     if (relu && !(y[r * ldy + c] > 0.f)) v = 0.f;

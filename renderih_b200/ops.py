@@ -14,12 +14,13 @@ from . import _lib
 call = _lib.call
 
 
-GEMM_MODES = {'simt': 0, 'tf32': 1, 'tf32x3': 2, 'tf32rn': 3}
+GEMM_MODES = {'simt': 0, 'tf32': 1, 'tf32x3': 2, 'tf32rn': 3, 'tf32c': 4}
 
 
 def set_gemm_mode(conv='simt', linear='simt'):
     """Arithmetic of the GEMM-class kernels: 'simt' = exact fp32 CUDA-core path, 'tf32' = tcgen05 tensor cores with TF32
     multiplicands and fp32 accumulation (what the reference's cuDNN convolutions use by default on this GPU),
+    'tf32c' = truncating TF32 whose mean shrinkage (7.05e-4) is compensated in the epilogue (RN-equivalent error statistics),
     'tf32rn' = TF32 with the operands rounded to nearest in shared memory before the MMA (unbiased; the cuDNN convention),
     'tf32x3' = the same tensor-core kernels with an in-kernel hi/lo operand split and 3 MMAs per step (fp32-faithful)."""
     call('rih_set_gemm_mode', GEMM_MODES[conv], GEMM_MODES[linear])

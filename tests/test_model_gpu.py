@@ -131,6 +131,26 @@ def test_forward_eval_reference_numerics_class_mode(gold, setup):
         assert e < 1e-2, (k, e)
 
 
+def test_forward_eval_mean_compensated_truncating_tf32(gold, setup):
+    """'tf32c' convolutions (truncating TF32 + 7.05e-4 mean compensation in the epilogue) + 3xTF32 Linears: must be as accurate as
+    the round-to-nearest variant (stated tolerance 1e-2, same as the reference-numerics-class mode)."""
+    from renderih_b200 import ops
+    a, sd, model = setup
+    model.load_state_dict(sd)
+    model.eval()
+    img = fixtures.make_image(gold['batch'])
+    ops.set_gemm_mode('tf32c', 'tf32x3')
+    try:
+        with torch.no_grad():
+            out = flat(model(img.cuda()))
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+    errs = {k: rel_err(out[k], v) for k, v in gold['eval'].items()}
+    print('tf32c conv + 3xTF32 linear eval rel errs vs reference golden:', {k: '%.2e' % e for k, e in errs.items()})
+    for k, e in errs.items():
+        assert e < 1e-2, (k, e)
+
+
 def test_forward_eval_tensor_core_3xtf32_mode(gold, setup):
     """tcgen05 with the in-kernel hi/lo split (3 MMAs per step): fp32-faithful tensor-core arithmetic.
     Stated tolerance: 1e-3 relative to each tensor's max magnitude (measured 3e-5 ... 4.5e-4: limited by the tensor core's
