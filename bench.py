@@ -32,9 +32,11 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='images per GPU (reference TRAIN.BATCH_SIZE)')
     ap.add_argument('--no-graph', action='store_true')
-    ap.add_argument('--gemm-mode', default='ref', choices=['ref', 'ref2', 'simt', 'tf32', 'tf32rn', 'tf32c', 'tf32x3'],
-                    help="arithmetic of the conv / Linear GEMMs; 'ref' = the reference's own GPU numerics class: TF32 (round-to-nearest) "
-                         "convolutions as cuDNN runs them by default + fp32-faithful (3xTF32) nn.Linear GEMMs")
+    ap.add_argument('--gemm-mode', default='ref', choices=['ref', 'refrn', 'simt', 'tf32', 'tf32rn', 'tf32c', 'tf32x3'],
+                    help="arithmetic of the conv / Linear GEMMs; 'ref' = the reference's own GPU numerics class: TF32 convolutions (as "
+                         "cuDNN runs them by default; here truncating TF32 with the 7.05e-4 mean shrinkage compensated in the epilogue, "
+                         "measured as accurate as round-to-nearest) + fp32-faithful (3xTF32) nn.Linear GEMMs; 'refrn' = same with "
+                         "round-to-nearest TF32 convolutions")
     ap.add_argument('--cpu-batch', type=int, default=4, help='bounded CPU sample size for cpu_baseline / --impl reference')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -198,7 +200,7 @@ def run_ours(args):
     from renderih_b200.train import TrainStep
     _lib.load()
     from renderih_b200 import ops as _ops
-    conv_mode, lin_mode = {'ref': ('tf32rn', 'tf32x3'), 'ref2': ('tf32c', 'tf32x3')}.get(args.gemm_mode, (args.gemm_mode, args.gemm_mode))
+    conv_mode, lin_mode = {'ref': ('tf32c', 'tf32x3'), 'refrn': ('tf32rn', 'tf32x3')}.get(args.gemm_mode, (args.gemm_mode, args.gemm_mode))
     _ops.set_gemm_mode(conv_mode, lin_mode)
     cfg = load_cfg()
     a = A.synthetic_assets(0)
@@ -274,9 +276,9 @@ def run_ours(args):
     e2e = total_imgs / (ms_e2e * 1e-3)
     line = {'metric': 'images/sec fwd+bwd @batch64 256x256 (training step: fwd + calc_loss_GCN + bwd + AdamW%s)' % (' + NCCL grad all-reduce' if world > 1 else ''),
             'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_dev,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': {'simt': 'f32', 'ref': 'f32 storage; tcgen05 TF32(rn) convolutions (cuDNN-default class of the reference) + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': {'simt': 'f32', 'refrn': 'f32 storage; tcgen05 TF32(rn) convolutions (cuDNN-default class of the reference) + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate',
                       'tf32': 'tf32 (truncating) conv+Linear, fp32 accumulate/storage', 'tf32c': 'tf32 (truncating, mean-compensated) conv+Linear, fp32 accumulate/storage',
-                      'ref2': 'f32 storage; tcgen05 TF32 (truncating, mean-compensated) convolutions + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate', 'tf32rn': 'tf32 (rn) conv+Linear, fp32 accumulate/storage',
+                      'ref': 'f32 storage; tcgen05 TF32 convolutions (truncating + mean-compensated: the accuracy class of the reference\'s cuDNN-TF32 default, measured) + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate', 'tf32rn': 'tf32 (rn) conv+Linear, fp32 accumulate/storage',
                       'tf32x3': '3xTF32 (fp32-faithful) conv+Linear, fp32 accumulate/storage'}[args.gemm_mode], 'data': 'synthetic',
             'config': {'workload': 'BASELINE.json configs[2]: HandNET_GCN ResNet50 cfg, batch %d/GPU, 256x256, train mode (batch-stat BN, dropout 0.05), '
                                    'random-init weights, synthetic graph/MANO assets' % B,

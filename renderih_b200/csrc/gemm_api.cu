@@ -39,6 +39,10 @@ static inline bool use_tc(int which) {
   tc::set_acc_scale(g_mode[which] == 4 ? 1.000705f : 1.f);
   return true;
 }
+extern "C" int rih_bn_colstats(const float* x, int ld, int M, int C, double* ws, cudaStream_t s);
+static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
+                           int M, int N, int K, int relu, int accumulate, const float* res, int ldres,
+                           float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, double* stats, cudaStream_t stream);
 static inline bool tc_ok(const void* p, long long ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0); }
 
 static inline int is_vec_ok(const void* p, int ld) {
@@ -48,12 +52,25 @@ static inline int is_vec_ok(const void* p, int ld) {
 // y[M,N] = x[M,K] @ w[N,K]^T (+bias) (+residual) (relu) ; reference: torch.nn.Linear (e.g. models/model_attn/gcn.py:92-96)
 RIH_API int rih_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
                            int M, int N, int K, int relu, int accumulate, const float* res, int ldres,
-                           float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, cudaStream_t stream) {
+                           float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, double* stats, cudaStream_t stream) {
   RIH_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_fwd: bad shape M=%d N=%d K=%d", M, N, K);
+  if (stats) {   // fused BatchNorm statistics of the output (see rih_conv2d_fwd)
+    RIH_REQUIRE(!accumulate && !res, "linear_fwd: stats need a plain store epilogue");
+    RIH_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N, stream));
+  }
+  tc::g_stats_fused = 0;
+  int rc = linear_fwd_impl(x, ldx, w, ldw, bias, y, ldy, M, N, K, relu, accumulate, res, ldres, dropout_p, seed_ptr, site, stats, stream);
+  if (rc) return rc;
+  if (stats && !tc::g_stats_fused) return rih_bn_colstats(y, ldy, M, N, stats, stream);
+  return 0;
+}
+static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
+                           int M, int N, int K, int relu, int accumulate, const float* res, int ldres,
+                           float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, double* stats, cudaStream_t stream) {
   DenseK a{x, ldx, M, is_vec_ok(x, ldx) && (K % 4 == 0)};
   DenseK b{w, ldw, N, is_vec_ok(w, ldw) && (K % 4 == 0)};
   Epilogue ep = make_epilogue(y, ldy, M, N, bias, relu, accumulate ? 1 : 0);
-  ep.res = res; ep.ldres = ldres;
+  ep.res = res; ep.ldres = ldres; ep.stats = stats;
   if (dropout_p > 0.f) {
     RIH_REQUIRE(seed_ptr != nullptr && dropout_p < 1.f, "linear_fwd: dropout needs a device seed and p < 1");
     ep.seed_ptr = seed_ptr; ep.site = site; ep.thresh = dropout_thresh(dropout_p); ep.inv_keep = 1.f / (1.f - dropout_p);
@@ -107,7 +124,6 @@ RIH_API int rih_conv2d_workspace(const int* geom, int which, long long* floats) 
   return 0;
 }
 
-extern "C" int rih_bn_colstats(const float* x, int ld, int M, int C, double* ws, cudaStream_t s);
 static int conv2d_fwd_impl(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, int relu, float* ws, double* stats,
                            cudaStream_t stream);
 

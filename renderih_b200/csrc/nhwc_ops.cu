@@ -166,27 +166,39 @@ RIH_API int rih_bn_apply(const float* x, int ldx, const float* mean, const float
 }
 
 // backward pass 1: g = dy * (y > 0 if relu);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat
-__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
-                                     const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     int M, int C, int rows_per_cta, int relu, double* __restrict__ ws) {
-  int c = blockIdx.x * 32 + threadIdx.x;
-  int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
-  double s = 0.0, sx = 0.0;
+// block = 8 channel quads (32 channels, float4 loads) x 32 row lanes; fp64 accumulation, one fp64 atomic pair per channel per CTA
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+                     const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     int M, int C, int rows_per_cta, int relu, double* __restrict__ ws) {
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int c = blockIdx.x * 32 + tx * 4;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
   if (c < C) {
-    float mu = mean[c], rs = rstd[c];
-    for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-      float g = dy[(size_t)r * lddy + c];
-      if (relu && !(y[(size_t)r * ldy + c] > 0.f)) g = 0.f;
-      float xh = (x[(size_t)r * ldx + c] - mu) * rs;
-      s += g; sx += (double)g * xh;
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    for (int r = r0 + ty; r < r1; r += 32) {
+      float4 g = *reinterpret_cast<const float4*>(dy + (size_t)r * lddy + c);
+      if (relu) {
+        const float4 yy = *reinterpret_cast<const float4*>(y + (size_t)r * ldy + c);
+        if (!(yy.x > 0.f)) g.x = 0.f; if (!(yy.y > 0.f)) g.y = 0.f; if (!(yy.z > 0.f)) g.z = 0.f; if (!(yy.w > 0.f)) g.w = 0.f;
+      }
+      const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * ldx + c);
+      s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
+      sx[0] += (double)g.x * ((xv.x - mu.x) * rs.x); sx[1] += (double)g.y * ((xv.y - mu.y) * rs.y);
+      sx[2] += (double)g.z * ((xv.z - mu.z) * rs.z); sx[3] += (double)g.w * ((xv.w - mu.w) * rs.w);
     }
   }
-  __shared__ double sh[2][8][33];
-  sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = sx;
+  __shared__ double sh[2][32][33];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { sh[0][ty][tx * 4 + i] = s[i]; sh[1][ty][tx * 4 + i] = sx[i]; }
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    for (int i = 1; i < 8; ++i) { s += sh[0][i][threadIdx.x]; sx += sh[1][i][threadIdx.x]; }
-    atomicAdd(ws + c, s); atomicAdd(ws + C + c, sx);
+  if (threadIdx.x < 64) {
+    const int which = threadIdx.x >> 5, col = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int i = 0; i < 32; ++i) acc += sh[which][i][col];
+    const int cc = blockIdx.x * 32 + col;
+    if (cc < C) atomicAdd(ws + which * C + cc, acc);
   }
 }
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, int C, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -252,8 +264,8 @@ RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const
   int gx = cdiv(C, 32);
   int target = cdiv(148 * 8, gx);
   int rows_per_cta = max(64, cdiv(M, target));
-  dim3 grid(gx, cdiv(M, rows_per_cta)), block(32, 8);
-  bn_bwd_reduce_kernel<<<grid, block, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, (int)M, C, rows_per_cta, relu, ws);
+  dim3 grid(gx, cdiv(M, rows_per_cta));
+  bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, (int)M, C, rows_per_cta, relu, ws);
   if (int e = check_launch("bn_bwd_reduce")) return e;
   bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(ws, C, dgamma, dbeta, tmp, tmp + C, param_acc);
   if (int e = check_launch("bn_bwd_finalize")) return e;
@@ -474,4 +486,35 @@ RIH_API int rih_patchify(float* x, int ldx, float* P, int N, int H, int W, int C
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
   patchify_kernel<<<grid, 256, 0, s>>>(x, ldx, P, N, H, W, C / 4, p, scatter);
   return check_launch("patchify");
+}
+
+// ============================================================== explicit im2col for few-channel convolutions (the 7x7/2 RGB stem)
+// A[(n,oh,ow), (r,s,c)] = x[n, oh*stride+r-pad, ow*stride+s-pad, c] (0 outside), columns >= R*S*C zero-padded up to Kpad.
+// With Cin = 3 the implicit-GEMM gathers cannot be vectorised or fed by TMA; materialising the 147(+13)-wide rows once lets the
+// stem run as a dense tensor-core GEMM (forward) and a dense split-K GEMM (weight gradient).
+__global__ void im2col_kernel(const float* __restrict__ x, int ldx, float* __restrict__ A, int N, int H, int W, int C, int Ho, int Wo,
+                              int R, int S, int stride, int pad, int Kpad) {
+  const long long total = (long long)N * Ho * Wo * Kpad;
+  const bool small = total < (1ll << 32);
+  const int K = R * S * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long m; int k;
+    divmod(i, Kpad, small, m, k);
+    float v = 0.f;
+    if (k < K) {
+      const int c = k % C, rs = k / C, s_ = rs % S, r = rs / S;
+      const int ow = (int)(m % Wo); const long long t = m / Wo; const int oh = (int)(t % Ho), n = (int)(t / Ho);
+      const int ih = oh * stride - pad + r, iw = ow * stride - pad + s_;
+      if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) v = x[((size_t)(n * H + ih) * W + iw) * ldx + c];
+    }
+    A[i] = v;
+  }
+}
+RIH_API int rih_im2col(const float* x, int ldx, float* A, int N, int H, int W, int C, int R, int S, int stride, int pad, int Kpad, cudaStream_t s) {
+  RIH_REQUIRE(Kpad >= R * S * C && Kpad % 4 == 0, "im2col: Kpad must be a multiple of 4 and >= R*S*C");
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * Kpad;
+  int grid = (int)min((long long)148 * 32, (total + 255) / 256);
+  im2col_kernel<<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
+  return check_launch("im2col");
 }

@@ -122,6 +122,23 @@ class ResNetSimple(nn.Module):
         self.dp_decoder = ResNetSimple_decoder(self.expansion, fmapDim, ('flat', 'up', 'up', 'up'), handNum + 3 * handNum)
         self.handNum = handNum
 
+    def _stem(self, x, N, H, needs_input_grad):
+        """conv1 7x7/2 (3 -> 64) + bn1 + ReLU.  With 3 input channels an implicit GEMM cannot be vectorised or fed by TMA, so
+        (when the image needs no gradient) the input is im2col'ed once to 160-wide rows and the conv runs as a dense GEMM."""
+        r = self.resnet
+        conv, bn = r.conv1, r.bn1
+        if needs_input_grad or not self.training:
+            return _conv_bn(x, conv, bn, N, H, H, self.training)
+        Cout, Cin, R, S = conv.weight.shape
+        K, Kpad = R * S * Cin, (R * S * Cin + 31) // 32 * 32
+        A = ops.im2col(x, N, H, H, R, S, conv.stride[0], conv.padding[0], Kpad)
+        w2d = torch.nn.functional.pad(conv.weight.permute(0, 2, 3, 1).reshape(Cout, K), (0, Kpad - K))   # tiny (64 x 160)
+        stats = torch.empty(2 * Cout, device=x.device, dtype=torch.float64)
+        y = ops.linear(A, w2d, None, stats=stats)
+        y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training=True, momentum=bn.momentum, eps=bn.eps,
+                          relu=True, stats=stats)
+        return y, (H + 2 * conv.padding[0] - R) // conv.stride[0] + 1
+
     def _bottleneck(self, blk, x, N, H):
         tr = self.training
         out, _ = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr)
@@ -138,7 +155,7 @@ class ResNetSimple(nn.Module):
         assert H == W
         r = self.resnet
         x = ops.nchw_to_nhwc(img)
-        x, H = _conv_bn(x, r.conv1, r.bn1, N, H, H, self.training)
+        x, H = self._stem(x, N, H, img.requires_grad)
         x = ops.maxpool3x3s2(x, N, H, H)
         H = (H - 1) // 2 + 1
         feats = []

@@ -122,7 +122,7 @@ class LinearFn(Function):
     """y = dropout(relu(x @ w^T + b)) + res  -- torch.nn.Linear call sites of models/model_attn/*.py, models/decoder.py"""
 
     @staticmethod
-    def forward(ctx, x, w, b, relu, res, p_drop, site):
+    def forward(ctx, x, w, b, relu, res, p_drop, site, stats=None):
         x = _rows(x); _check(w, 'weight')
         M, K = x.shape
         N = w.shape[0]
@@ -133,7 +133,7 @@ class LinearFn(Function):
             res = _rows(res)
         sp = seed_state.ptr(x.device) if p_drop > 0 else None
         call('rih_linear_fwd', _p(x), _ld(x), _p(w), w.stride(0), _p(b), _p(y), N, M, N, K, int(relu), 0,
-             _p(res), _ld(res) if res is not None else 0, float(p_drop), sp, site, _stream())
+             _p(res), _ld(res) if res is not None else 0, float(p_drop), sp, site, _p(stats), _stream())
         ctx.save_for_backward(x, w, y if (relu or p_drop > 0) else None)
         ctx.meta = (relu, p_drop, site, b is not None, res is not None)
         ctx.bias_ref = b
@@ -171,12 +171,13 @@ class LinearFn(Function):
                 db = torch.empty((N,), device=dy.device, dtype=torch.float32)
                 call('rih_colsum', _p(g), _ld(g), M, N, _p(db), 0, s)
         dres = dy if (has_res and ctx.needs_input_grad[4]) else None
-        return dx, dw, db, None, dres, None, None
+        return dx, dw, db, None, dres, None, None, None
 
 
-def linear(x, w, b=None, relu=False, res=None, p_drop=0.0):
+def linear(x, w, b=None, relu=False, res=None, p_drop=0.0, stats=None):
+    """stats: optional float64 [2*N] buffer receiving the output's column sums / sums of squares (fused BN statistics)."""
     site = seed_state.next_site() if p_drop > 0 else 0
-    return LinearFn.apply(x, w, b, relu, res, p_drop, site)
+    return LinearFn.apply(x, w, b, relu, res, p_drop, site, stats)
 
 
 # ----------------------------------------------------------------------------- LayerNorm
@@ -556,6 +557,28 @@ class PatchifyFn(Function):
 
 def patchify(x, N, H, W, p):
     return PatchifyFn.apply(x, N, H, W, p)
+
+
+class Im2colFn(Function):
+    """Explicit im2col of a few-channel input (the RGB stem): [N*H*W, C] -> [N*Ho*Wo, Kpad]; no gradient w.r.t. the image."""
+
+    @staticmethod
+    def forward(ctx, x, N, H, W, R, S, stride, pad, Kpad):
+        x = _rows(x)
+        C = x.shape[1]
+        Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+        A = torch.empty((N * Ho * Wo, Kpad), device=x.device, dtype=torch.float32)
+        call('rih_im2col', _p(x), _ld(x), _p(A), N, H, W, C, R, S, stride, pad, Kpad, _stream())
+        return A
+
+    @staticmethod
+    def backward(ctx, dA):
+        raise RuntimeError('renderih_b200: im2col has no input gradient (use it only on inputs that do not require grad)')
+
+
+def im2col(x, N, H, W, R, S, stride, pad, Kpad):
+    assert not x.requires_grad
+    return Im2colFn.apply(x, N, H, W, R, S, stride, pad, Kpad)
 
 
 class BatchNormFn(Function):

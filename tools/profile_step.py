@@ -25,7 +25,7 @@ def main():
     from renderih_b200.loss import GraphLoss, calc_loss_GCN
     from renderih_b200.model import load_model
     from renderih_b200.train import FlatParams, trainable_used_params
-    cm, lm = {'ref': ('tf32rn', 'tf32x3'), 'ref2': ('tf32c', 'tf32x3')}.get(args.gemm_mode, (args.gemm_mode, args.gemm_mode))
+    cm, lm = {'ref': ('tf32c', 'tf32x3'), 'refrn': ('tf32rn', 'tf32x3')}.get(args.gemm_mode, (args.gemm_mode, args.gemm_mode))
     ops.set_gemm_mode(cm, lm)
     cfg = load_cfg()
     a = A.synthetic_assets(0)
