@@ -57,6 +57,8 @@ int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int
 }
 
 int g_stats_fused = 0;            // set by the launcher when the epilogue accumulated ep.stats (fused BatchNorm statistics)
+static int g_wide_tiles = 1;     // 128 x 256 output tiles when N % 256 == 0
+void set_wide_tiles(int on) { g_wide_tiles = on ? 1 : 0; }
 static int g_persistent = 1;     // 0 = one CTA per tile (non-persistent kernel; debug / comparison)
 void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
@@ -148,6 +150,8 @@ int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long
   if (M <= 0 || N <= 0) return 0;
   CUtensorMap ta, tb;
   int BN = (N > 64) ? 128 : 64;
+  // 128 x 256 tiles (full 512 TMEM columns with double buffering) when N allows: each A tile is fetched once per 256 columns
+  if (g_persistent && g_wide_tiles && N % 256 == 0 && (long long)cdiv(M, BM) * (N / 256) >= 120) BN = 256;
   if (a_mn ? make_tmap_2d(&ta, a, K, M, lda, 32, true) : make_tmap_2d(&ta, a, M, K, lda, BM)) return 1;
   if (b_mn ? make_tmap_2d(&tb, b, K, N, ldb, 32, true) : make_tmap_2d(&tb, b, N, K, ldb, BN)) return 1;
   int num_kb = cdiv(K, BK), splits, kps;
@@ -157,6 +161,7 @@ int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long
     DenseProducer<bn, am != 0, bm != 0> prod{0};                                             \
     return launch_cfg<bn, am != 0, bm != 0>(ta, tb, ep, prod, M, N, num_kb, splits, kps, s); \
   }
+  RIH_TC_CASE(256, 0, 0) RIH_TC_CASE(256, 0, 1) RIH_TC_CASE(256, 1, 1)
   RIH_TC_CASE(128, 0, 0) RIH_TC_CASE(64, 0, 0)
   RIH_TC_CASE(128, 0, 1) RIH_TC_CASE(64, 0, 1)
   RIH_TC_CASE(128, 1, 1) RIH_TC_CASE(64, 1, 1)
@@ -189,7 +194,9 @@ extern "C" int rih_parity_stack(const float* x, int ldx, float* xp, int N, int H
 extern "C" int rih_dilate2x(const float* y, int ldy, float* yd, int N, int Ho, int Wo, int C, cudaStream_t s);
 
 int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s) {
-  const int M = g.N * g.Ho * g.Wo, BN = (g.Cout > 64) ? 128 : 64;
+  const int M = g.N * g.Ho * g.Wo;
+  int BN = (g.Cout > 64) ? 128 : 64;
+  if (g_persistent && g_wide_tiles && g.Cout % 256 == 0 && (long long)(M / BM) * (g.Cout / 256) >= 120) BN = 256;
   const int tile_h = (BM / g.Wo) < g.Ho ? (BM / g.Wo) : g.Ho;
   const int tile_n = BM / (g.Wo * tile_h);
   CUtensorMap ta, tb;
@@ -203,6 +210,7 @@ int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g
   if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, BN)) return 1;
   ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, g.stride == 2 ? g.N : 0};
   const int num_kb = g.R * g.S * (g.Cin / BK);
+  if (BN == 256) { ConvFwdProducer<256> p{cg}; return launch_cfg<256, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
   if (BN == 128) { ConvFwdProducer<128> p{cg}; return launch_cfg<128, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
   ConvFwdProducer<64> p{cg};
   return launch_cfg<64, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s);
@@ -215,7 +223,9 @@ int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom
     if (int e = rih_dilate2x(dy, g0.ldy, ws, g0.N, g0.Ho, g0.Wo, g0.Cout, s)) return e;
     dy = ws; g.stride = 1; g.Ho = g0.H; g.Wo = g0.W; g.ldy = g0.Cout;
   }
-  const int M = g.N * g.H * g.W, BN = (g.Cin > 64) ? 128 : 64;
+  const int M = g.N * g.H * g.W;
+  int BN = (g.Cin > 64) ? 128 : 64;
+  if (g_persistent && g_wide_tiles && g.Cin % 256 == 0 && (long long)(M / BM) * (g.Cin / 256) >= 120) BN = 256;
   const int tile_h = (BM / g.W) < g.H ? (BM / g.W) : g.H;
   const int tile_n = BM / (g.W * tile_h);
   CUtensorMap ta, tb;
@@ -223,6 +233,7 @@ int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom
   if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, 32, true)) return 1;
   ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, 0};
   const int num_kb = g.R * g.S * (g.Cout / BK);
+  if (BN == 256) { ConvDgradProducer<256> p{cg}; return launch_cfg<256, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s); }
   if (BN == 128) { ConvDgradProducer<128> p{cg}; return launch_cfg<128, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s); }
   ConvDgradProducer<64> p{cg};
   return launch_cfg<64, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s);
@@ -260,8 +271,11 @@ RIH_API int rih_gemm_tf32(const float* a, long long lda, int a_mn, const float* 
   RIH_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_tf32: bad shape");
   // nsplit: 1 = TF32, 3 = 3xTF32.  Debug variants: negative = per-thread-store epilogue, +10 = non-persistent kernel.
   int v = nsplit < 0 ? -nsplit : nsplit;
+  const int narrow = v >= 20;
+  if (narrow) v -= 20;
   const int nonpersistent = v >= 10;
   if (nonpersistent) v -= 10;
+  tc::set_wide_tiles(!narrow);
   RIH_REQUIRE(v == 1 || v == 2 || v == 3, "gemm_tf32: nsplit must be 1 (TF32, truncating), 2 (TF32, round-to-nearest) or 3 (3xTF32)");
   tc::set_tma_epilogue(nsplit > 0);
   tc::set_persistent(!nonpersistent);
@@ -271,5 +285,6 @@ RIH_API int rih_gemm_tf32(const float* a, long long lda, int a_mn, const float* 
   int rc = tc::gemm_tf32(a, lda, a_mn, b, ldb, b_mn, ep, M, N, K, allow_splitk, stream);
   tc::set_tma_epilogue(1);
   tc::set_persistent(1);
+  tc::set_wide_tiles(1);
   return rc;
 }

@@ -127,7 +127,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // rounded to nearest in shared memory first (unbiased, what cuDNN/cuBLAS TF32 do).  NSPLIT = 3: error-compensated "3xTF32": every operand tile is split in shared memory into
 // hi = value rounded to TF32 and lo = value - hi (exact in fp32), and D += hi*hi + lo*hi + hi*lo  (fp32-faithful).
 template <int BN, int NSPLIT> __host__ __device__ constexpr int stage_bytes() { return (BM * 128 + BN * 128) * (NSPLIT == 3 ? 2 : 1); }
-template <int BN, int NSPLIT> __host__ __device__ constexpr int num_stages() { return NSPLIT == 3 ? (BN >= 128 ? 3 : 4) : (BN >= 128 ? 3 : 4); }
+template <int BN, int NSPLIT> __host__ __device__ constexpr int num_stages() { return (BN >= 256 && NSPLIT == 3) ? 2 : (BN >= 128 ? 3 : 4); }
 constexpr int EPI_STAGING_BYTES = 2 * BM * 128;   // two [128 x 32 fp32] staging tiles for the TMA-store epilogue
 template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() {
   return num_stages<BN, NSPLIT>() * stage_bytes<BN, NSPLIT>() + EPI_STAGING_BYTES + 1024 + 256;

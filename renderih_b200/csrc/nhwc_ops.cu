@@ -492,8 +492,11 @@ RIH_API int rih_patchify(float* x, int ldx, float* P, int N, int H, int W, int C
 // A[(n,oh,ow), (r,s,c)] = x[n, oh*stride+r-pad, ow*stride+s-pad, c] (0 outside), columns >= R*S*C zero-padded up to Kpad.
 // With Cin = 3 the implicit-GEMM gathers cannot be vectorised or fed by TMA; materialising the 147(+13)-wide rows once lets the
 // stem run as a dense tensor-core GEMM (forward) and a dense split-K GEMM (weight gradient).
-__global__ void im2col_kernel(const float* __restrict__ x, int ldx, float* __restrict__ A, int N, int H, int W, int C, int Ho, int Wo,
-                              int R, int S, int stride, int pad, int Kpad) {
+// TR/TS/TC > 0: compile-time filter shape (constant divisions); 0 = runtime shape
+template <int TR, int TS, int TC>
+__global__ void im2col_kernel(const float* __restrict__ x, int ldx, float* __restrict__ A, int N, int H, int W, int C_, int Ho, int Wo,
+                              int R_, int S_, int stride, int pad, int Kpad) {
+  const int R = TR > 0 ? TR : R_, S = TS > 0 ? TS : S_, C = TC > 0 ? TC : C_;
   const long long total = (long long)N * Ho * Wo * Kpad;
   const bool small = total < (1ll << 32);
   const int K = R * S * C;
@@ -515,6 +518,7 @@ RIH_API int rih_im2col(const float* x, int ldx, float* A, int N, int H, int W, i
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
   const long long total = (long long)N * Ho * Wo * Kpad;
   int grid = (int)min((long long)148 * 32, (total + 255) / 256);
-  im2col_kernel<<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
+  if (R == 7 && S == 7 && C == 3) im2col_kernel<7, 7, 3><<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
+  else im2col_kernel<0, 0, 0><<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
   return check_launch("im2col");
 }

@@ -451,3 +451,19 @@ def test_gemm_tf32_round_to_nearest_is_unbiased():
         errs[ns] = float(((c.double() - ref) / ref).mean())
     print('mean signed relative error: truncating %.2e, round-to-nearest %.2e' % (errs[1], errs[2]))
     assert abs(errs[2]) < 2e-5 and abs(errs[1]) > 1e-4
+
+
+@pytest.mark.parametrize('nsplit', [1, 3])
+def test_gemm_wide_tiles_match_narrow(nsplit):
+    """128x256 output tiles (N % 256 == 0, many tiles) against the 128x128 configuration of the same kernel."""
+    from renderih_b200._lib import call
+    M, N, K = 16384, 512, 192
+    a, b, bias = T(M, K, grad=False), T(N, K, seed=1, grad=False), T(N, seed=2, grad=False)
+    outs = []
+    for code in (nsplit, nsplit + 20):
+        c = torch.empty((M, N), device=DEV)
+        call('rih_gemm_tf32', a.data_ptr(), K, 0, b.data_ptr(), K, 0, c.data_ptr(), N, M, N, K, bias.data_ptr(), 1, 0, 0, code, torch.cuda.current_stream().cuda_stream)
+        outs.append(c)
+    ref = F.relu(a.double() @ b.double().t() + bias.double())
+    assert rel(outs[0], ref) < (3e-3 if nsplit == 1 else 2e-5)
+    assert rel(outs[0], outs[1]) < 1e-6
