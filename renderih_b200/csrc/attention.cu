@@ -7,6 +7,8 @@
 using namespace rih;
 
 constexpr int ATT_WARPS = 8;
+constexpr int ATT_RF = 8;   // query rows per warp block, forward
+constexpr int ATT_RB = 4;   // row block, backward (both phases)
 
 __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
@@ -65,7 +67,7 @@ attn_fwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const floa
                 const float* __restrict__ v, long long v_bs, int ldv, float* __restrict__ o, long long o_bs, int ldo,
                 float* __restrict__ lse, int H, int Sq, int Sk, int d, float scale, int rows_per_cta,
                 const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
-  constexpr int R = 4;
+  constexpr int R = ATT_RF;
   const unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
   extern __shared__ __align__(16) float smem[];
   const AttGeo g = make_geo(d, Sk);
@@ -173,12 +175,12 @@ RIH_API int rih_attn_fwd(const float* q, long long q_bs, int ldq, const float* k
               "attn_fwd: operands must be 16-byte aligned with strides that are multiples of 4 floats");
   if (B * H == 0 || Sq == 0) return 0;
   const int Skr = make_geo(d, Sk).Skr;
-  size_t smem = sizeof(float) * (2 * (size_t)Skr * (d + 4) + ATT_WARPS * 4 * d + (size_t)ATT_WARPS * 4 * Skr);
+  size_t smem = sizeof(float) * (2 * (size_t)Skr * (d + 4) + ATT_WARPS * ATT_RF * d + (size_t)ATT_WARPS * ATT_RF * Skr);
   RIH_REQUIRE(smem <= 227 * 1024, "attn_fwd: shared memory %zu too large", smem);
   int ysplit = 1;
   while (B * H * ysplit < 148 * 2 && Sq / (ysplit * 2) >= 32) ysplit *= 2;
   int rows_per_cta = cdiv(Sq, ysplit);
-  rows_per_cta = (rows_per_cta + 3) & ~3;
+  rows_per_cta = (rows_per_cta + ATT_RF - 1) / ATT_RF * ATT_RF;
   dim3 grid(B * H, cdiv(Sq, rows_per_cta));
   uint32_t thresh = dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u;
   float ik = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
@@ -204,7 +206,7 @@ attn_bwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const floa
                 float* __restrict__ dq, long long dq_bs, int lddq, float* __restrict__ dk, long long dk_bs, int lddk,
                 float* __restrict__ dv, long long dv_bs, int lddv,
                 int H, int Sq, int Sk, int d, float scale, const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
-  constexpr int R = 2;
+  constexpr int R = ATT_RB;
   const unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
   extern __shared__ __align__(16) float smem[];
   const AttGeo gk = make_geo(d, Sk);   // splits over keys (phase A accumulations)
@@ -394,7 +396,7 @@ RIH_API int rih_attn_bwd(const float* q, long long q_bs, int ldq, const float* k
               "attn_bwd: operands must be 16-byte aligned with strides that are multiples of 4 floats");
   if (B * H == 0 || Sq == 0 || Sk == 0) return 0;
   const int Sqr = make_geo(d, Sq).Skr, Skr = make_geo(d, Sk).Skr, Smax = Sqr > Skr ? Sqr : Skr;
-  size_t smem = sizeof(float) * ((size_t)(2 * Sqr + 2 * Skr) * (d + 4) + 2 * (size_t)Sqr + 2 * (size_t)ATT_WARPS * 2 * Smax + (size_t)ATT_WARPS * 4 * d);
+  size_t smem = sizeof(float) * ((size_t)(2 * Sqr + 2 * Skr) * (d + 4) + 2 * (size_t)Sqr + 2 * (size_t)ATT_WARPS * ATT_RB * Smax + (size_t)ATT_WARPS * 2 * ATT_RB * d);
   RIH_REQUIRE(smem <= 227 * 1024, "attn_bwd: shared memory %zu too large (Sq=%d Sk=%d d=%d)", smem, Sq, Sk, d);
   uint32_t thresh = dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u;
   float ik = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
