@@ -20,8 +20,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOPS_PER_IMG_FWD_BWD = 50.450e9   # FlopCounterMode on the reference, ResNet50 cfg
-FLOPS_PER_IMG_FWD = 17.721e9
+# FlopCounterMode on the reference (algorithmic 2*MAC FLOPs per image, forward+backward / forward)
+FLOPS = {'resnet50': (50.450e9, 17.721e9), 'hrnet48': (168.090e9, 56.201e9)}
+FLOPS_PER_IMG_FWD_BWD, FLOPS_PER_IMG_FWD = FLOPS['resnet50']
 
 
 def parse():
@@ -30,7 +31,9 @@ def parse():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=64, help='images per GPU (reference TRAIN.BATCH_SIZE)')
+    ap.add_argument('--batch', type=int, default=None, help='images per GPU (default 64; 32 for --encoder hrnet48 = BASELINE.json configs[4])')
+    ap.add_argument('--encoder', default='resnet50', choices=['resnet50', 'hrnet48'],
+                    help='MODEL.ENCODER_TYPE: resnet50 = BASELINE.json configs[2] (the headline metric), hrnet48 = configs[4]')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--gemm-mode', default='ref', choices=['ref', 'refrn', 'simt', 'tf32', 'tf32rn', 'tf32c', 'tf32x3'],
                     help="arithmetic of the conv / Linear GEMMs; 'ref' = the reference's own GPU numerics class: TF32 convolutions (as "
@@ -39,7 +42,10 @@ def parse():
                          "round-to-nearest TF32 convolutions")
     ap.add_argument('--cpu-batch', type=int, default=4, help='bounded CPU sample size for cpu_baseline / --impl reference')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 32 if a.encoder == 'hrnet48' else 64
+    return a
 
 
 def peaks():
@@ -98,16 +104,55 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def cpu_port_step_time(batch, steps=1, warmup=0, budget_s=1e9):
-    """The reference algorithm's CPU port (oracle/model_ref.py): forward + calc_loss_GCN + backward, fp32, all host threads."""
+def host_cores():
+    """CPU threads this process can actually run on: the scheduler affinity mask, capped by the cgroup CPU quota (a container on
+    a 128-thread host may own far fewer; oversubscribing torch's intra-op pool there makes the CPU baseline tens of times slower
+    than it really is)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:
+            q, per = f.read().split()[:2]
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(per) + 0.999)))
+    except Exception:
+        pass
+    return n
+
+
+def cpu_port_step_time(batch, steps=1, warmup=0, budget_s=1e9, encoder='resnet50'):
+    """The reference algorithm's CPU port (oracle/model_ref.py): forward + calc_loss_GCN + backward, fp32, on the host threads that
+    give it the best throughput (a forward-only calibration pass picks among the usable-core count and its halvings down to 16)."""
     import torch
     from oracle import fixtures, model_ref
     from renderih_b200 import assets as A
+    from renderih_b200.config import load_cfg
     from renderih_b200.model import load_model
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     a = A.synthetic_assets(0)
-    sd = fixtures.init_state_dict(load_model(assets=a).state_dict())
+    cfg = load_cfg()
+    cfg.MODEL.ENCODER_TYPE = encoder
+    sd = fixtures.init_state_dict(load_model(cfg, assets=a).state_dict())
+    avail = host_cores()
+    cands, c = [], avail
+    while c >= 16 and len(cands) < 4:
+        cands.append(c); c //= 2
+    cands = cands or [avail]
+    if len(cands) > 1:
+        Ap0, im0, best = model_ref.prepare_assets(a), fixtures.make_image(batch), None
+        for c in cands:
+            torch.set_num_threads(c)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                model_ref.model_forward({k: v.clone() for k, v in sd.items()}, Ap0, im0, training=True, dropout=0.0)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, c)
+        cores = best[1]
+    else:
+        cores = cands[0]
+    torch.set_num_threads(cores)
     for k, v in sd.items():
         if v.is_floating_point() and 'running_' not in k and k not in ('decoder.dense_coor', 'decoder.unsample_layer.weight'):
             v.requires_grad_(True)
@@ -136,12 +181,12 @@ def run_reference(args):
     if rank != 0:
         return
     # bounded: the CPU port needs tens of seconds per step on a big host, so at most ~3 steps / ~150 s are timed
-    t, cores, nsteps = cpu_port_step_time(args.cpu_batch, steps=max(1, min(args.steps, 3)), warmup=0, budget_s=150.0)
+    t, cores, nsteps = cpu_port_step_time(args.cpu_batch, steps=max(1, min(args.steps, 3)), warmup=0, budget_s=150.0, encoder=args.encoder)
     v = args.cpu_batch / t
     line = {'impl': 'reference', 'metric': 'images/sec fwd+bwd (calc_loss_GCN) @256x256', 'value': v, 'unit': 'images/s',
             'n_gpus': args.gpus, 'steps': nsteps, 'warmup': 0, 'ms_per_step': t * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'HandNET_GCN ResNet50 cfg, fwd+calc_loss_GCN+bwd, CPU sample batch %d of the batch-64 workload' % args.cpu_batch},
+            'config': {'workload': 'HandNET_GCN %s cfg, fwd+calc_loss_GCN+bwd, CPU sample batch %d of the batch-%d workload' % (args.encoder, args.cpu_batch, args.batch)},
             'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                              'sample': 'batch %d fwd+bwd, oracle/model_ref.py on torch CPU fp32, %d threads' % (args.cpu_batch, cores)},
             'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -203,6 +248,8 @@ def run_ours(args):
     conv_mode, lin_mode = {'ref': ('tf32c', 'tf32x3'), 'refrn': ('tf32rn', 'tf32x3')}.get(args.gemm_mode, (args.gemm_mode, args.gemm_mode))
     _ops.set_gemm_mode(conv_mode, lin_mode)
     cfg = load_cfg()
+    cfg.MODEL.ENCODER_TYPE = args.encoder
+    flops_fb = FLOPS[args.encoder][0]
     a = A.synthetic_assets(0)
     torch.manual_seed(cfg.SEED)
     model = load_model(cfg, assets=a).cuda().train()          # train mode: batch-stat BN, dropout 0.05 (reference defaults)
@@ -274,25 +321,25 @@ def run_ours(args):
     total_imgs = B * world
     value = total_imgs / (ms_dev * 1e-3)
     e2e = total_imgs / (ms_e2e * 1e-3)
-    line = {'metric': 'images/sec fwd+bwd @batch64 256x256 (training step: fwd + calc_loss_GCN + bwd + AdamW%s)' % (' + NCCL grad all-reduce' if world > 1 else ''),
+    line = {'metric': 'images/sec fwd+bwd @batch%d 256x256 (training step: fwd + calc_loss_GCN + bwd + AdamW%s)' % (B, ' + NCCL grad all-reduce' if world > 1 else ''),
             'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_dev,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': {'simt': 'f32', 'refrn': 'f32 storage; tcgen05 TF32(rn) convolutions (cuDNN-default class of the reference) + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate',
                       'tf32': 'tf32 (truncating) conv+Linear, fp32 accumulate/storage', 'tf32c': 'tf32 (truncating, mean-compensated) conv+Linear, fp32 accumulate/storage',
                       'ref': 'f32 storage; tcgen05 TF32 convolutions (truncating + mean-compensated: the accuracy class of the reference\'s cuDNN-TF32 default, measured) + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate', 'tf32rn': 'tf32 (rn) conv+Linear, fp32 accumulate/storage',
                       'tf32x3': '3xTF32 (fp32-faithful) conv+Linear, fp32 accumulate/storage'}[args.gemm_mode], 'data': 'synthetic',
-            'config': {'workload': 'BASELINE.json configs[2]: HandNET_GCN ResNet50 cfg, batch %d/GPU, 256x256, train mode (batch-stat BN, dropout 0.05), '
-                                   'random-init weights, synthetic graph/MANO assets' % B,
+            'config': {'workload': 'BASELINE.json configs[%d]: HandNET_GCN %s cfg, batch %d/GPU, 256x256, train mode (batch-stat BN, dropout 0.05), '
+                                   'random-init weights, synthetic graph/MANO assets' % (4 if args.encoder == 'hrnet48' else 2, args.encoder, B),
                        'global_batch': total_imgs, 'parallelism': 'dp%d' % world, 'cuda_graph': not args.no_graph,
                        'l2': 'per-step working set (activations, several GB) >> 126 MB L2; no explicit flush needed',
-                       'algorithmic_gflop_per_image': FLOPS_PER_IMG_FWD_BWD / 1e9},
-            'achieved_tflops': value * FLOPS_PER_IMG_FWD_BWD / 1e12,
+                       'algorithmic_gflop_per_image': flops_fb / 1e9},
+            'achieved_tflops': value * flops_fb / 1e12,
             'e2e': {'value': e2e, 'unit': 'images/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': B * 3 * 256 * 256 * 4, 'd2h_bytes_per_step': 4},
             'gpu_launches': calls_per_step * args.steps, 'launches_per_step': calls_per_step,
             'clocks': clocks, 'roofline': roof, 'last_loss': losses[-1] if losses else None}
     if not args.skip_cpu_baseline and world == 1:
-        t, cores, _ = cpu_port_step_time(args.cpu_batch, steps=1, warmup=0)
+        t, cores, _ = cpu_port_step_time(args.cpu_batch, steps=1, warmup=0, encoder=args.encoder)
         line['cpu_baseline'] = {'value': args.cpu_batch / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                'sample': 'batch %d fwd+calc_loss_GCN+bwd once, oracle/model_ref.py (torch CPU fp32, %d threads)' % (args.cpu_batch, cores)}
+                                'sample': 'batch %d fwd+calc_loss_GCN+bwd once, oracle/model_ref.py (torch CPU fp32, %d of %d usable threads)' % (args.cpu_batch, cores, host_cores())}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -51,81 +51,96 @@ def flat(out):
         d['v3list_' + side] = other['verts3d_MANO_list'][side][0]
         d['v2list_' + side] = other['verts2d_MANO_list'][side][0]
     for k in ('hms', 'mask', 'dense'):
-        d[k + '_sub'] = other[k][:, :, ::8, ::8].contiguous()
-        d[k + '_mean'] = other[k].mean(dim=(2, 3))
+        t = other[k] if other[k].dim() == 4 else other[k][:, None]     # HRnet_encoder returns mask as [B,64,64] (encoder.py:235)
+        d[k + '_sub'] = t[:, :, ::8, ::8].contiguous()
+        d[k + '_mean'] = t.mean(dim=(2, 3))
     return {k: v.detach().clone() for k, v in d.items()}
 
 
-def main():
+def model_golden(ns, tmp, encoder_type, fname, bn_probe):
+    """Eval forward + train-mode forward/backward (dropout 0) of the unmodified reference model with `encoder_type`."""
+    ref, cfg = rb.build_reference_model(asset_dir=tmp, encoder_type=encoder_type, dropout=0.0)
+    sd = fixtures.init_state_dict(ref.state_dict())
+    ref.load_state_dict(sd)
+    B = 2
+    img = fixtures.make_image(B)
+    ref.eval()
+    with torch.no_grad():
+        out_eval = flat(ref(img))
+    gold = {'weights_sha256': fixtures.checksum(sd), 'batch': B, 'seed': fixtures.SEED, 'torch': torch.__version__,
+            'eval': out_eval}
+    # training-mode forward + calc_loss_GCN backward, through the reference's own loss code
+    ref.train()
+    for p in ref.parameters():
+        p.requires_grad_(True)
+    ref.decoder.unsample_layer.weight.requires_grad_(False)   # freeze_upsample (core/lijun_trainer.py:115-116)
+    out = ref(img)
+    labels = fixtures.make_labels(B)
+    manoL = ns.mano.ManoLayer(os.path.join(tmp, 'mano', 'MANO_LEFT.pkl'), center_idx=None)
+    manoR = ns.mano.ManoLayer(os.path.join(tmp, 'mano', 'MANO_RIGHT.pkl'), center_idx=None)
+    gl = ns.loss.GraphLoss(manoL.J_regressor, manoL.get_faces(), level=4, device='cpu')
+    gr = ns.loss.GraphLoss(manoR.J_regressor, manoR.get_faces(), level=4, device='cpu')
+    z = torch.zeros(B, 21, 3)
+    loss, _, mano_d, coarse_d = ns.loss.calc_loss_GCN(
+        cfg, 0, gl, gr, ref.decoder.converter['left'], ref.decoder.converter['right'],
+        out[0], out[1], out[2], out[3], None, None, None,
+        labels['v2d_l'], z[..., :2], labels['v2d_r'], z[..., :2], labels['v3d_l'], z, labels['v3d_r'], z,
+        labels['root_rel'], 256, upsample_weight=None)
+    loss.backward()
+    grads = {}
+    for k, p in ref.named_parameters():
+        if p.grad is None:
+            continue
+        g = p.grad
+        grads[k] = {'norm': float(g.norm()), 'sum': float(g.sum())}
+        if g.numel() <= 4096:
+            grads[k]['full'] = g.detach().clone()
+    bn1 = getattr(ref.encoder, bn_probe).bn1
+    gold['train'] = {'out': flat(out), 'loss': float(loss), 'grads': grads,
+                     'bn1_running_mean': bn1.running_mean.detach().clone(),
+                     'bn1_running_var': bn1.running_var.detach().clone(),
+                     'no_grad_keys': [k for k, p in ref.named_parameters() if p.grad is None]}
+    gold['encoder_type'] = encoder_type
+    torch.save(gold, os.path.join(GOLD, fname))
+    print('%s golden: loss %.6f, %d grads, eval |v3d_l| max %.4f' % (encoder_type, float(loss), len(grads), float(out_eval['verts3d_left'].abs().max())))
+
+
+def mano_golden(ns, tmp):
+    # ---------------- ManoLayer goldens on the synthetic MANO tensors
+    mg = {'cases': []}
+    inp = fixtures.make_mano_inputs(5)
+    root = ns.mano.rodrigues_batch(inp['axis'])
+    for side in ('left', 'right'):
+        path = os.path.join(tmp, 'mano', 'MANO_%s.pkl' % side.upper())
+        for cfgc in ({'center_idx': 9, 'use_pca': True, 'new_skel': False, 'ncomps': 45, 'ts': True},
+                     {'center_idx': None, 'use_pca': True, 'new_skel': True, 'ncomps': 30, 'ts': False},
+                     {'center_idx': 0, 'use_pca': False, 'new_skel': False, 'ncomps': 0, 'ts': True}):
+            layer = ns.mano.ManoLayer(path, center_idx=cfgc['center_idx'], use_pca=cfgc['use_pca'], new_skel=cfgc['new_skel'])
+            if cfgc['use_pca']:
+                pose = inp['pose_pca'][:, :cfgc['ncomps']]
+            else:
+                pose = layer.axis2Rmat(inp['pose_axis'])
+            tr, sc = (inp['trans'], inp['scale']) if cfgc['ts'] else (None, None)
+            v, j = layer(root, pose, inp['shape'], tr, sc)
+            mg['cases'].append({'side': side, 'cfg': cfgc, 'v': v.clone(), 'j': j.clone()})
+    mg['rodrigues'] = root.clone()
+    torch.save(mg, os.path.join(GOLD, 'mano_synth.pt'))
+    print('mano golden: %d cases' % len(mg['cases']))
+
+
+def main(which):
+    """which: any of 'resnet50', 'hrnet48', 'mano' (default: all).  Each golden file is written independently."""
     os.makedirs(GOLD, exist_ok=True)
     ns = rb.import_reference()
     with tempfile.TemporaryDirectory() as tmp:
-        a = write_synthetic_asset_dir(tmp, 0)
-        # ---------------- model forward (eval) and forward+backward (train, dropout 0)
-        ref, cfg = rb.build_reference_model(asset_dir=tmp, dropout=0.0)
-        sd = fixtures.init_state_dict(ref.state_dict())
-        ref.load_state_dict(sd)
-        B = 2
-        img = fixtures.make_image(B)
-        ref.eval()
-        with torch.no_grad():
-            out_eval = flat(ref(img))
-        gold = {'weights_sha256': fixtures.checksum(sd), 'batch': B, 'seed': fixtures.SEED, 'torch': torch.__version__,
-                'eval': out_eval}
-        # training-mode forward + calc_loss_GCN backward, through the reference's own loss code
-        ref.train()
-        for p in ref.parameters():
-            p.requires_grad_(True)
-        ref.decoder.unsample_layer.weight.requires_grad_(False)   # freeze_upsample (core/lijun_trainer.py:115-116)
-        out = ref(img)
-        labels = fixtures.make_labels(B)
-        manoL = ns.mano.ManoLayer(os.path.join(tmp, 'mano', 'MANO_LEFT.pkl'), center_idx=None)
-        manoR = ns.mano.ManoLayer(os.path.join(tmp, 'mano', 'MANO_RIGHT.pkl'), center_idx=None)
-        gl = ns.loss.GraphLoss(manoL.J_regressor, manoL.get_faces(), level=4, device='cpu')
-        gr = ns.loss.GraphLoss(manoR.J_regressor, manoR.get_faces(), level=4, device='cpu')
-        z = torch.zeros(B, 21, 3)
-        loss, _, mano_d, coarse_d = ns.loss.calc_loss_GCN(
-            cfg, 0, gl, gr, ref.decoder.converter['left'], ref.decoder.converter['right'],
-            out[0], out[1], out[2], out[3], None, None, None,
-            labels['v2d_l'], z[..., :2], labels['v2d_r'], z[..., :2], labels['v3d_l'], z, labels['v3d_r'], z,
-            labels['root_rel'], 256, upsample_weight=None)
-        loss.backward()
-        grads = {}
-        for k, p in ref.named_parameters():
-            if p.grad is None:
-                continue
-            g = p.grad
-            grads[k] = {'norm': float(g.norm()), 'sum': float(g.sum())}
-            if g.numel() <= 4096:
-                grads[k]['full'] = g.detach().clone()
-        gold['train'] = {'out': flat(out), 'loss': float(loss), 'grads': grads,
-                         'bn1_running_mean': ref.encoder.resnet.bn1.running_mean.detach().clone(),
-                         'bn1_running_var': ref.encoder.resnet.bn1.running_var.detach().clone(),
-                         'no_grad_keys': [k for k, p in ref.named_parameters() if p.grad is None]}
-        torch.save(gold, os.path.join(GOLD, 'model_synth_b2.pt'))
-        print('model golden: loss %.6f, %d grads, eval |v3d_l| max %.4f' % (float(loss), len(grads), float(out_eval['verts3d_left'].abs().max())))
-
-        # ---------------- ManoLayer goldens on the synthetic MANO tensors
-        mg = {'cases': []}
-        inp = fixtures.make_mano_inputs(5)
-        root = ns.mano.rodrigues_batch(inp['axis'])
-        for side in ('left', 'right'):
-            path = os.path.join(tmp, 'mano', 'MANO_%s.pkl' % side.upper())
-            for cfgc in ({'center_idx': 9, 'use_pca': True, 'new_skel': False, 'ncomps': 45, 'ts': True},
-                         {'center_idx': None, 'use_pca': True, 'new_skel': True, 'ncomps': 30, 'ts': False},
-                         {'center_idx': 0, 'use_pca': False, 'new_skel': False, 'ncomps': 0, 'ts': True}):
-                layer = ns.mano.ManoLayer(path, center_idx=cfgc['center_idx'], use_pca=cfgc['use_pca'], new_skel=cfgc['new_skel'])
-                if cfgc['use_pca']:
-                    pose = inp['pose_pca'][:, :cfgc['ncomps']]
-                else:
-                    pose = layer.axis2Rmat(inp['pose_axis'])
-                tr, sc = (inp['trans'], inp['scale']) if cfgc['ts'] else (None, None)
-                v, j = layer(root, pose, inp['shape'], tr, sc)
-                mg['cases'].append({'side': side, 'cfg': cfgc, 'v': v.clone(), 'j': j.clone()})
-        mg['rodrigues'] = root.clone()
-        torch.save(mg, os.path.join(GOLD, 'mano_synth.pt'))
-        print('mano golden: %d cases' % len(mg['cases']))
+        write_synthetic_asset_dir(tmp, 0)
+        if 'resnet50' in which:
+            model_golden(ns, tmp, 'resnet50', 'model_synth_b2.pt', 'resnet')
+        if 'hrnet48' in which:     # BASELINE config 5 (models/encoder.py:176-352, model_zoo/hrnet.py)
+            model_golden(ns, tmp, 'hrnet48', 'model_hrnet48_synth_b2.pt', 'hrnet')
+        if 'mano' in which:
+            mano_golden(ns, tmp)
 
 
 if __name__ == '__main__':
-    main()
+    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'mano'])

@@ -84,6 +84,113 @@ def mid_forward(sd, img_f, hms_f, dp_f, tr):
     return gf, fmaps
 
 
+# ---------------------------------------------------------------- HRNet encoder: models/model_zoo/hrnet.py + models/encoder.py:176-352
+def _count(sd, pre):
+    """number of consecutive integer children `pre.0`, `pre.1`, ... present in the state dict"""
+    n = 0
+    while any(k.startswith('%s.%d.' % (pre, n)) for k in sd):
+        n += 1
+    return n
+
+
+def _basic_block(x, sd, pre, tr):
+    """BasicBlock.forward, model_zoo/hrnet.py:41-58 (branch blocks never carry a downsample: in == out channels)"""
+    out = F.relu(_bn(F.conv2d(x, sd[pre + '.conv1.weight'], padding=1), sd, pre + '.bn1', tr))
+    out = _bn(F.conv2d(out, sd[pre + '.conv2.weight'], padding=1), sd, pre + '.bn2', tr)
+    return F.relu(out + x)
+
+
+def _conv_bn_seq(x, sd, pre, tr, stride=1, relu=True):
+    """nn.Sequential(Conv2d 3x3 (pre.0), BatchNorm2d (pre.1)[, ReLU]) as used by transitions / fuse layers / downsamp modules"""
+    w = sd[pre + '.0.weight']
+    y = _bn(F.conv2d(x, w, sd.get(pre + '.0.bias'), stride=stride, padding=w.shape[-1] // 2), sd, pre + '.1', tr)
+    return F.relu(y) if relu else y
+
+
+def _hr_module(xs, sd, pre, tr):
+    """HighResolutionModule.forward, model_zoo/hrnet.py:215-232 (fuse layers built at :167-210)"""
+    nb = len(xs)
+    xs = list(xs)
+    for i in range(nb):
+        for b in range(_count(sd, '%s.branches.%d' % (pre, i))):
+            xs[i] = _basic_block(xs[i], sd, '%s.branches.%d.%d' % (pre, i, b), tr)
+    if nb == 1:
+        return xs
+    out = []
+    for i in range(nb):
+        y = None
+        for j in range(nb):
+            fp = '%s.fuse_layers.%d.%d' % (pre, i, j)
+            if j == i:
+                t = xs[j]
+            elif j > i:      # 1x1 conv -> BN -> nearest upsample 2^(j-i)
+                t = _bn(F.conv2d(xs[j], sd[fp + '.0.weight']), sd, fp + '.1', tr)
+                t = F.interpolate(t, scale_factor=2 ** (j - i), mode='nearest')
+            else:            # (i-j) stride-2 3x3 convs, ReLU on all but the last
+                t = xs[j]
+                for k in range(i - j):
+                    t = _conv_bn_seq(t, sd, '%s.%d' % (fp, k), tr, stride=2, relu=(k != i - j - 1))
+            y = t if y is None else y + t
+        out.append(F.relu(y))
+    return out
+
+
+def hrnet_forward(sd, img, tr, p='encoder.hrnet'):
+    """HighResolutionNet.forward (head_type 'none'), model_zoo/hrnet.py:493-527"""
+    x = F.relu(_bn(F.conv2d(img, sd[p + '.conv1.weight'], stride=2, padding=1), sd, p + '.bn1', tr))
+    x = F.relu(_bn(F.conv2d(x, sd[p + '.conv2.weight'], stride=2, padding=1), sd, p + '.bn2', tr))
+    for b in range(_count(sd, p + '.layer1')):
+        x = _bottleneck(x, sd, '%s.layer1.%d' % (p, b), 1, (p + '.layer1.%d.downsample.0.weight' % b) in sd, tr)
+    ys = [x]
+    for stage, trans in (('stage2', 'transition1'), ('stage3', 'transition2'), ('stage4', 'transition3')):
+        nb = _count(sd, '%s.%s.0.branches' % (p, stage))
+        xs = []
+        for i in range(nb):
+            tp = '%s.%s.%d' % (p, trans, i)
+            if i < len(ys):
+                # same-resolution transition: conv3x3+BN+ReLU when the channel count changes (transition1.0), else identity
+                src = ys[i] if stage != 'stage2' else x
+                xs.append(_conv_bn_seq(src, sd, tp, tr) if (tp + '.0.weight') in sd else src)
+            else:
+                t = ys[-1] if stage != 'stage2' else x
+                for j in range(_count(sd, tp)):
+                    t = _conv_bn_seq(t, sd, '%s.%d' % (tp, j), tr, stride=2)
+                xs.append(t)
+        for m in range(_count(sd, '%s.%s' % (p, stage))):
+            xs = _hr_module(xs, sd, '%s.%s.%d' % (p, stage, m), tr)
+        ys = xs
+    return ys
+
+
+def _mask_decoder(x, sd, pre, tr):
+    """HRnet_encoder.mask_decoder, models/encoder.py:207-221: 1x1 conv (bias) -> BN -> ReLU -> 1x1 conv (bias)"""
+    x = F.relu(_bn(F.conv2d(x, sd[pre + '.0.weight'], sd[pre + '.0.bias']), sd, pre + '.1', tr))
+    return F.conv2d(x, sd[pre + '.3.weight'], sd[pre + '.3.bias'])
+
+
+def hrnet_encoder_forward(sd, img, tr):
+    """HRnet_encoder.forward, models/encoder.py:223-240"""
+    ys = hrnet_forward(sd, img, tr)
+    size = ys[0].shape[2:]
+    x = torch.cat([ys[0]] + [F.interpolate(y, size=size, mode='bilinear', align_corners=True) for y in ys[1:]], 1)
+    hms = _mask_decoder(x, sd, 'encoder.hms_decoder', tr)
+    out = _mask_decoder(x, sd, 'encoder.dp_decoder', tr)
+    return hms, out[:, 0], out[:, 1:], ys[::-1], None, None
+
+
+def hrnet_mid_forward(sd, img_f, tr):
+    """hrnet_mid.forward, models/encoder.py:333-352 (img_f is coarse -> fine; the head walks fine -> coarse)"""
+    fmaps = [_bn(F.relu(F.conv2d(img_f[i], sd['mid_model.convs.%d.0.weight' % i])), sd, 'mid_model.convs.%d.2' % i, tr)
+             for i in range(len(img_f))]
+    rev = img_f[::-1]
+    y = _bottleneck(rev[0], sd, 'mid_model.incre_modules.0.0', 1, True, tr)
+    for i in range(len(rev) - 1):
+        y = _bottleneck(rev[i + 1], sd, 'mid_model.incre_modules.%d.0' % (i + 1), 1, True, tr) + \
+            _conv_bn_seq(y, sd, 'mid_model.downsamp_modules.%d' % i, tr, stride=2)
+    y = F.relu(_bn(F.conv2d(y, sd['mid_model.final_layer.0.weight'], sd['mid_model.final_layer.0.bias']), sd, 'mid_model.final_layer.1', tr))
+    return F.avg_pool2d(y, kernel_size=y.shape[2:]).view(y.shape[0], -1), fmaps
+
+
 # ---------------------------------------------------------------- decoder blocks
 def graph_conv_cheby(x, sd, pre, L, K=2):
     """models/model_attn/gcn.py:34-69 (dense Laplacian product, Fin x K interleave)"""
@@ -245,8 +352,12 @@ def decoder_forward(sd, A, gf, fmaps, p, tr):
 def model_forward(sd, assets_prepared, img, training=False, dropout=0.0):
     """HandNET_GCN.forward, models/model.py:25-37.  `sd` maps reference state_dict keys to tensors (BN running
     statistics are updated in place when training=True, exactly like nn.BatchNorm2d)."""
-    hms, mask, dp, img_f, hms_f, dp_f = encoder_forward(sd, img, training)
-    gf, fmaps = mid_forward(sd, img_f, hms_f, dp_f, training)
+    if 'encoder.hrnet.conv1.weight' in sd:      # ENCODER_TYPE: hrnet* (models/encoder.py:365-372)
+        hms, mask, dp, img_f, _, _ = hrnet_encoder_forward(sd, img, training)
+        gf, fmaps = hrnet_mid_forward(sd, img_f, training)
+    else:
+        hms, mask, dp, img_f, hms_f, dp_f = encoder_forward(sd, img, training)
+        gf, fmaps = mid_forward(sd, img_f, hms_f, dp_f, training)
     result, params, hlist, other = decoder_forward(sd, assets_prepared, gf, fmaps, dropout, training)
     other['hms'], other['mask'], other['dense'] = hms, mask, dp
     return result, params, hlist, other

@@ -397,6 +397,154 @@ RIH_API int rih_bilinear2x_bwd(const float* dy, int lddy, float* dx, int lddx, i
   return check_launch("bilinear2x_bwd");
 }
 
+// ============================================================== bilinear x f, align_corners=True, float4 channels
+// F.interpolate(size=(f*H, f*W), mode='bilinear', align_corners=True) of HRnet_encoder.forward (models/encoder.py:227-230): the
+// three coarse HRNet branches are up-sampled x2 / x4 / x8 and written straight into their channel slice of the 720-wide concat
+// buffer (y points at the slice, ldy is the full row stride), so torch.cat (encoder.py:231) costs no extra pass.
+__global__ void bilinear_up4_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int N, int H, int W, int C4, int f) {
+  const int Ho = f * H, Wo = f * W;
+  const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)N * Ho * Wo * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4); long long t = i / C4; int ow = (int)(t % Wo); t /= Wo; int oh = (int)(t % Ho); int n = (int)(t / Ho);
+    int h0, h1, w0, w1; float lh, lw;
+    bil_coord(oh, sh, H, h0, h1, lh); bil_coord(ow, sw, W, w0, w1, lw);
+    const float hh = 1.f - lh, ww = 1.f - lw;
+    const float* b = x + (size_t)n * H * W * ldx + c * 4;
+    const float4 a00 = *reinterpret_cast<const float4*>(b + ((size_t)h0 * W + w0) * ldx), a01 = *reinterpret_cast<const float4*>(b + ((size_t)h0 * W + w1) * ldx);
+    const float4 a10 = *reinterpret_cast<const float4*>(b + ((size_t)h1 * W + w0) * ldx), a11 = *reinterpret_cast<const float4*>(b + ((size_t)h1 * W + w1) * ldx);
+    float4 v;
+    v.x = hh * (ww * a00.x + lw * a01.x) + lh * (ww * a10.x + lw * a11.x);
+    v.y = hh * (ww * a00.y + lw * a01.y) + lh * (ww * a10.y + lw * a11.y);
+    v.z = hh * (ww * a00.z + lw * a01.z) + lh * (ww * a10.z + lw * a11.z);
+    v.w = hh * (ww * a00.w + lw * a01.w) + lh * (ww * a10.w + lw * a11.w);
+    *reinterpret_cast<float4*>(y + ((size_t)(n * Ho + oh) * Wo + ow) * ldy + c * 4) = v;
+  }
+}
+// backward as a gather: every input pixel (h, w) sums the contributions of the output pixels whose interpolation window
+// touches it (rows oh with src(oh) in (h-1, h+1)), no atomics, deterministic.
+__global__ void bilinear_up4_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx, int N, int H, int W, int C4, int f) {
+  const int Ho = f * H, Wo = f * W;
+  const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)N * H * W * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4); long long t = i / C4; int w = (int)(t % W); t /= W; int h = (int)(t % H); int n = (int)(t / H);
+    // candidate output rows: src = sh * oh in (h - 1, h + 1)  ->  oh in ((h-1)/sh, (h+1)/sh); scan a safe superset and test exactly
+    const int oh_lo = max(0, (h - 1) * f - f), oh_hi = min(Ho - 1, (h + 1) * f + f);
+    const int ow_lo = max(0, (w - 1) * f - f), ow_hi = min(Wo - 1, (w + 1) * f + f);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      int h0, h1; float lh;
+      bil_coord(oh, sh, H, h0, h1, lh);
+      float wh = 0.f;
+      if (h0 == h) wh += 1.f - lh;
+      if (h1 == h) wh += lh;
+      if (wh == 0.f) continue;
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        int w0, w1; float lw;
+        bil_coord(ow, sw, W, w0, w1, lw);
+        float wwt = 0.f;
+        if (w0 == w) wwt += 1.f - lw;
+        if (w1 == w) wwt += lw;
+        if (wwt == 0.f) continue;
+        const float4 g = *reinterpret_cast<const float4*>(dy + ((size_t)(n * Ho + oh) * Wo + ow) * lddy + c * 4);
+        const float k = wh * wwt;
+        acc.x = fmaf(k, g.x, acc.x); acc.y = fmaf(k, g.y, acc.y); acc.z = fmaf(k, g.z, acc.z); acc.w = fmaf(k, g.w, acc.w);
+      }
+    }
+    *reinterpret_cast<float4*>(dx + ((size_t)(n * H + h) * W + w) * lddx + c * 4) = acc;
+  }
+}
+RIH_API int rih_bilinear_up_fwd(const float* x, int ldx, float* y, int ldy, int N, int H, int W, int C, int f, cudaStream_t s) {
+  RIH_REQUIRE(f >= 1 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+              "bilinear_up_fwd: needs C, strides multiples of 4 floats and 16-byte aligned pointers (C=%d ldx=%d ldy=%d)", C, ldx, ldy);
+  long long total = (long long)N * f * H * f * W * (C / 4);
+  if (total == 0) return 0;
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  bilinear_up4_fwd_kernel<<<grid, 256, 0, s>>>(x, ldx, y, ldy, N, H, W, C / 4, f);
+  return check_launch("bilinear_up_fwd");
+}
+// dx[N*H*W, C] = adjoint of rih_bilinear_up_fwd applied to dy[N*fH*fW, C] (row stride lddy); overwrites dx
+RIH_API int rih_bilinear_up_bwd(const float* dy, int lddy, float* dx, int lddx, int N, int H, int W, int C, int f, cudaStream_t s) {
+  RIH_REQUIRE(f >= 1 && C % 4 == 0 && lddx % 4 == 0 && lddy % 4 == 0 && ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0,
+              "bilinear_up_bwd: needs C, strides multiples of 4 floats and 16-byte aligned pointers");
+  long long total = (long long)N * H * W * (C / 4);
+  if (total == 0) return 0;
+  int grid = (int)min((long long)148 * 16, (total + 127) / 128);
+  bilinear_up4_bwd_kernel<<<grid, 128, 0, s>>>(dy, lddy, dx, lddx, N, H, W, C / 4, f);
+  return check_launch("bilinear_up_bwd");
+}
+
+// ============================================================== HRNet fuse: y = act(sum_j nearest_up(t_j, f_j))
+// HighResolutionModule.forward (models/model_zoo/hrnet.py:222-230): y = x[0]; y = y + fuse(x[j]) ...; relu(y).  Terms coming from a
+// coarser branch carry nn.Upsample(scale_factor=2^(j-i), mode='nearest') (hrnet.py:185); it is folded into the read index here.
+// Terms are added in list order (the reference's left-to-right association).
+struct FuseTerms { const float* p[4]; int ld[4]; int f[4]; int n; };
+__global__ void fuse_sum_kernel(FuseTerms a, float* __restrict__ y, int ldy, int N, int H, int W, int C4, int relu) {
+  const long long total = (long long)N * H * W * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4); long long t = i / C4; int w = (int)(t % W); t /= W; int h = (int)(t % H); int n = (int)(t / H);
+    float4 acc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < a.n) {
+        const int f = a.f[j], Hj = H / f, Wj = W / f;
+        const float4 v = *reinterpret_cast<const float4*>(a.p[j] + ((size_t)(n * Hj + h / f) * Wj + w / f) * a.ld[j] + c * 4);
+        if (j == 0) acc = v;
+        else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+      }
+    }
+    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    *reinterpret_cast<float4*>(y + ((size_t)(n * H + h) * W + w) * ldy + c * 4) = acc;
+  }
+}
+RIH_API int rih_fuse_sum(const float* const* terms, const int* lds, const int* factors, int nterms, float* y, int ldy,
+                         int N, int H, int W, int C, int relu, cudaStream_t s) {
+  RIH_REQUIRE(nterms >= 1 && nterms <= 4 && C % 4 == 0 && ldy % 4 == 0, "fuse_sum: 1..4 terms, channels multiple of 4");
+  FuseTerms a;
+  a.n = nterms;
+  for (int j = 0; j < 4; ++j) {
+    a.p[j] = j < nterms ? terms[j] : nullptr; a.ld[j] = j < nterms ? lds[j] : 0; a.f[j] = j < nterms ? factors[j] : 1;
+    if (j < nterms) RIH_REQUIRE(a.f[j] >= 1 && H % a.f[j] == 0 && W % a.f[j] == 0 && a.ld[j] % 4 == 0 && (reinterpret_cast<uintptr_t>(a.p[j]) & 15) == 0,
+                                "fuse_sum: term %d has a bad factor / stride / alignment", j);
+  }
+  long long total = (long long)N * H * W * (C / 4);
+  if (total == 0) return 0;
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  fuse_sum_kernel<<<grid, 256, 0, s>>>(a, y, ldy, N, H, W, C / 4, relu);
+  return check_launch("fuse_sum");
+}
+// adjoint of a nearest x f up-sample: dx[n,h,w,:] = sum_{a,b<f} (y > 0 ? dy : 0)[n, f*h+a, f*w+b, :]   (y == nullptr: no mask)
+__global__ void pool_sum_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, float* __restrict__ dx, int lddx,
+                                int N, int H, int W, int C4, int f) {
+  const long long total = (long long)N * H * W * C4;
+  const int Hf = H * f, Wf = W * f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4); long long t = i / C4; int w = (int)(t % W); t /= W; int h = (int)(t % H); int n = (int)(t / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < f; ++a)
+      for (int b = 0; b < f; ++b) {
+        const size_t row = (size_t)(n * Hf + h * f + a) * Wf + w * f + b;
+        float4 g = *reinterpret_cast<const float4*>(dy + row * lddy + c * 4);
+        if (y) {
+          const float4 m = *reinterpret_cast<const float4*>(y + row * ldy + c * 4);
+          g.x = m.x > 0.f ? g.x : 0.f; g.y = m.y > 0.f ? g.y : 0.f; g.z = m.z > 0.f ? g.z : 0.f; g.w = m.w > 0.f ? g.w : 0.f;
+        }
+        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+      }
+    *reinterpret_cast<float4*>(dx + ((size_t)(n * H + h) * W + w) * lddx + c * 4) = acc;
+  }
+}
+// H, W are the COARSE (output) sizes; dy / y are [N, f*H, f*W, C]
+RIH_API int rih_pool_sum(const float* dy, int lddy, const float* y, int ldy, float* dx, int lddx, int N, int H, int W, int C, int f, cudaStream_t s) {
+  RIH_REQUIRE(f >= 1 && C % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && (!y || ldy % 4 == 0), "pool_sum: channels / strides must be multiples of 4");
+  long long total = (long long)N * H * W * (C / 4);
+  if (total == 0) return 0;
+  int grid = (int)min((long long)148 * 16, (total + 127) / 128);
+  pool_sum_kernel<<<grid, 128, 0, s>>>(dy, lddy, y, ldy, dx, lddx, N, H, W, C / 4, f);
+  return check_launch("pool_sum");
+}
+
 // ============================================================== global average pool [N, HW, C] -> [N, C]
 __global__ void gap_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int N, int HW, int C) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -519,6 +667,7 @@ RIH_API int rih_im2col(const float* x, int ldx, float* A, int N, int H, int W, i
   const long long total = (long long)N * Ho * Wo * Kpad;
   int grid = (int)min((long long)148 * 32, (total + 255) / 256);
   if (R == 7 && S == 7 && C == 3) im2col_kernel<7, 7, 3><<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
+  else if (R == 3 && S == 3 && C == 3) im2col_kernel<3, 3, 3><<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);   // HRNet stem
   else im2col_kernel<0, 0, 0><<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
   return check_launch("im2col");
 }

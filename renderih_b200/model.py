@@ -606,7 +606,12 @@ def load_encoder(cfg):
         enc = ResNetSimple(model_type=et, fmapDim=[128, 128, 128, 128], handNum=2, heatmapDim=21)
         mid = resnet_mid(model_type=et, in_fmapDim=[128, 128, 128, 128], out_fmapDim=cfg.MODEL.DECONV_DIMS)
         return enc, mid
-    raise NotImplementedError('encoder %r: HRNet-w48 (BASELINE config 5) is the next scope row, see DESIGN.md' % et)
+    if 'hrnet' in et:                  # models/encoder.py:365-372
+        from .hrnet import HRnet_encoder, hrnet_mid
+        enc = HRnet_encoder(model_type=et, pretrained=getattr(cfg.MODEL, 'ENCODER_PRETRAIN_PATH', ''), handNum=2, heatmapDim=21)
+        mid = hrnet_mid(model_type=et, in_fmapDim=enc.fmaps_dim, out_fmapDim=cfg.MODEL.DECONV_DIMS)
+        return enc, mid
+    raise NotImplementedError('encoder %r: only resnet50/101/152 and hrnet* encoders exist in the reference (models/encoder.py:355-374)' % et)
 
 
 def load_decoder(cfg, encoder_info, assets=None, asset_root=None):

@@ -689,6 +689,104 @@ def bilinear2x(x, N, H, W):
     return Bilinear2xFn.apply(x, N, H, W)
 
 
+class HrConcatFn(Function):
+    """cat([y0, up(y1), up(y2), up(y3)], channels) with bilinear align_corners=True up-sampling to y0's size --
+    HRnet_encoder.forward, models/encoder.py:226-231.  Each branch is interpolated straight into its channel slice."""
+
+    @staticmethod
+    def forward(ctx, N, H0, *xs):
+        xs = [_rows(x) for x in xs]
+        widths = [x.shape[1] for x in xs]
+        Ct = sum(widths)
+        y = torch.empty((N * H0 * H0, Ct), device=xs[0].device)
+        s = _stream()
+        off = 0
+        hs = []
+        for i, x in enumerate(xs):
+            Hi = int(round((x.shape[0] // N) ** 0.5))
+            assert Hi * Hi * N == x.shape[0] and H0 % Hi == 0
+            hs.append(Hi)
+            dst = y.data_ptr() + 4 * off
+            if Hi == H0:
+                call('rih_copy2d', _p(x), _ld(x), dst, Ct, x.shape[0], x.shape[1], 0, s)
+            else:
+                call('rih_bilinear_up_fwd', _p(x), _ld(x), dst, Ct, N, Hi, Hi, x.shape[1], H0 // Hi, s)
+            off += x.shape[1]
+        ctx.meta = (N, H0, widths, hs)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H0, widths, hs = ctx.meta
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        s = _stream()
+        outs = []
+        off = 0
+        for i, (w, Hi) in enumerate(zip(widths, hs)):
+            if not ctx.needs_input_grad[2 + i]:
+                outs.append(None)
+            elif Hi == H0:
+                outs.append(dy[:, off:off + w])
+            else:
+                dx = torch.empty((N * Hi * Hi, w), device=dy.device)
+                call('rih_bilinear_up_bwd', dy.data_ptr() + 4 * off, _ld(dy), _p(dx), w, N, Hi, Hi, w, H0 // Hi, s)
+                outs.append(dx)
+            off += w
+        return (None, None) + tuple(outs)
+
+
+def hr_concat(xs, N, H0):
+    return HrConcatFn.apply(N, H0, *xs)
+
+
+class FuseSumFn(Function):
+    """y = act(t0 + up(t1) + ...), nearest x f_j up-sampling of coarser terms folded into the read --
+    HighResolutionModule.forward fuse sums (models/model_zoo/hrnet.py:222-230) and the `+` of hrnet_mid's head (encoder.py:339-341)."""
+
+    @staticmethod
+    def forward(ctx, N, H, relu, factors, *ts):
+        ts = [_rows(t) for t in ts]
+        C = ts[0].shape[1]
+        y = torch.empty((N * H * H, C), device=ts[0].device)
+        n = len(ts)
+        lds = (ctypes.c_int * n)(*[_ld(t) for t in ts])
+        fs = (ctypes.c_int * n)(*factors)
+        call('rih_fuse_sum', _ptr_array(ts), lds, fs, n, _p(y), C, N, H, H, C, int(relu), _stream())
+        ctx.save_for_backward(y if relu else None)
+        ctx.meta = (N, H, C, relu, tuple(factors))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        N, H, C, relu, factors = ctx.meta
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        s = _stream()
+        g = None
+        outs = []
+        for j, f in enumerate(factors):
+            if not ctx.needs_input_grad[4 + j]:
+                outs.append(None)
+            elif f == 1:
+                if g is None:
+                    if relu:
+                        g = torch.empty((N * H * H, C), device=dy.device)
+                        call('rih_relu_bwd', _p(dy), _ld(dy), _p(y), C, _p(g), C, N * H * H, C, s)
+                    else:
+                        g = dy
+                outs.append(g)
+            else:
+                Hc = H // f
+                dx = torch.empty((N * Hc * Hc, C), device=dy.device)
+                call('rih_pool_sum', _p(dy), _ld(dy), _p(y) if relu else None, C, _p(dx), C, N, Hc, Hc, C, f, s)
+                outs.append(dx)
+        return (None, None, None, None) + tuple(outs)
+
+
+def fuse_sum(terms, factors, N, H, relu=True):
+    return FuseSumFn.apply(N, H, relu, tuple(int(f) for f in factors), *terms)
+
+
 class GapFn(Function):
     """AdaptiveAvgPool2d(1)+Flatten -- models/encoder.py:153-156,166"""
 

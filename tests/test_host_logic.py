@@ -71,6 +71,13 @@ def test_config_and_hrnet_gate(tmp_path):
     p.write_text('MODEL:\n  ENCODER_TYPE: hrnet48\nTRAIN:\n  dropout: 0.0\n')
     cfg2 = load_cfg(str(p))
     assert cfg2.TRAIN.dropout == 0.0 and cfg2.MODEL.graph_k == 2
+    m = load_model(cfg2, assets=A.synthetic_assets(0))        # HRNet-w48 encoder (BASELINE config 5)
+    sd = m.state_dict()
+    assert len(sd) == 2693 and sum(p.numel() for p in m.parameters()) == 88023274      # reference: 2693 keys, 88.02 M parameters
+    assert sd['encoder.hrnet.stage4.2.fuse_layers.3.0.2.0.weight'].shape == (384, 48, 3, 3)
+    assert sd['mid_model.downsamp_modules.2.0.bias'].shape == (1024,) and sd['encoder.hms_decoder.0.weight'].shape == (720, 720, 1, 1)
+    assert m.mid_model.get_info() == {'global_feature_dim': 2048, 'fmaps_dim': [256, 256, 256, 256]}
+    cfg2.MODEL.ENCODER_TYPE = 'vit'
     with pytest.raises(NotImplementedError):
         load_model(cfg2, assets=A.synthetic_assets(0))
 
