@@ -78,3 +78,9 @@ def make_mano_inputs(batch, ncomps=45, seed=SEED):
     return {'axis': torch.rand(batch, 3, generator=g), 'pose_pca': torch.rand(batch, ncomps, generator=g),
             'pose_axis': torch.rand(batch, 45, generator=g) * 0.8, 'shape': torch.rand(batch, 10, generator=g),
             'trans': torch.rand(batch, 3, generator=g), 'scale': torch.rand(batch, generator=g) + 0.5}
+
+
+def make_mano_loss_weights(batch, seed=SEED):
+    """Fixed random cotangents for ManoLayer gradient checks: loss = <v, wv> + <j, wj>."""
+    g = torch.Generator().manual_seed(seed + 3)
+    return torch.randn(batch, 778, 3, generator=g), torch.randn(batch, 21, 3, generator=g)

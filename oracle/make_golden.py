@@ -128,8 +128,35 @@ def mano_golden(ns, tmp):
     print('mano golden: %d cases' % len(mg['cases']))
 
 
+MANO_GRAD_CASES = ({'center_idx': 9, 'use_pca': True, 'new_skel': False, 'ncomps': 45, 'ts': True},
+                   {'center_idx': None, 'use_pca': True, 'new_skel': True, 'ncomps': 30, 'ts': True},
+                   {'center_idx': 0, 'use_pca': False, 'new_skel': True, 'ncomps': 0, 'ts': False})
+
+
+def mano_grad_golden(ns, tmp):
+    """Gradients of the UNMODIFIED reference ManoLayer (torch autograd) for loss = <v, wv> + <j, wj> on the synthetic MANO tensors."""
+    inp = fixtures.make_mano_inputs(5)
+    wv, wj = fixtures.make_mano_loss_weights(5)
+    out = {'cases': []}
+    for side in ('left', 'right'):
+        path = os.path.join(tmp, 'mano', 'MANO_%s.pkl' % side.upper())
+        for cfgc in MANO_GRAD_CASES:
+            layer = ns.mano.ManoLayer(path, center_idx=cfgc['center_idx'], use_pca=cfgc['use_pca'], new_skel=cfgc['new_skel'])
+            root = ns.mano.rodrigues_batch(inp['axis']).clone().requires_grad_(True)
+            pose = (inp['pose_pca'][:, :cfgc['ncomps']] if cfgc['use_pca'] else layer.axis2Rmat(inp['pose_axis'])).clone().requires_grad_(True)
+            shape = inp['shape'].clone().requires_grad_(True)
+            tr = inp['trans'].clone().requires_grad_(True) if cfgc['ts'] else None
+            sc = inp['scale'].clone().requires_grad_(True) if cfgc['ts'] else None
+            v, j = layer(root, pose, shape, tr, sc)
+            ((v * wv).sum() + (j * wj).sum()).backward()
+            out['cases'].append({'side': side, 'cfg': cfgc, 'd_root': root.grad.clone(), 'd_pose': pose.grad.clone(), 'd_shape': shape.grad.clone(),
+                                 'd_trans': None if tr is None else tr.grad.clone(), 'd_scale': None if sc is None else sc.grad.clone()})
+    torch.save(out, os.path.join(GOLD, 'mano_grad_synth.pt'))
+    print('mano gradient golden: %d cases' % len(out['cases']))
+
+
 def main(which):
-    """which: any of 'resnet50', 'hrnet48', 'mano' (default: all).  Each golden file is written independently."""
+    """which: any of 'resnet50', 'hrnet48', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
     os.makedirs(GOLD, exist_ok=True)
     ns = rb.import_reference()
     with tempfile.TemporaryDirectory() as tmp:
@@ -140,7 +167,9 @@ def main(which):
             model_golden(ns, tmp, 'hrnet48', 'model_hrnet48_synth_b2.pt', 'hrnet')
         if 'mano' in which:
             mano_golden(ns, tmp)
+        if 'mano_grad' in which:
+            mano_grad_golden(ns, tmp)
 
 
 if __name__ == '__main__':
-    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'mano'])
+    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'mano', 'mano_grad'])

@@ -61,3 +61,59 @@ def mano_forward(m, root_rotation, pose, shape, trans=None, scale=None, use_pca=
         j[:, 5] = (v_out[:, 63] + v_out[:, 144]) / 2; j[:, 9] = (v_out[:, 271] + v_out[:, 220]) / 2
         j[:, 13] = (v_out[:, 148] + v_out[:, 290]) / 2; j[:, 17] = (v_out[:, 770] + v_out[:, 83]) / 2
     return v_out.astype(np.float32), j.astype(np.float32)
+
+
+def mano_forward_torch(m, root_rotation, pose, shape, trans=None, scale=None, use_pca=True, center_idx=9, new_skel=False, parent=PARENT):
+    """Differentiable torch restatement of the same forward (models/manolayer.py:250-322), used to check the fused backward kernel:
+    gradients come from torch autograd over these plain ops, exactly how the reference obtains them.  Pinned against the unmodified
+    reference's own gradients by tests/golden/mano_grad_synth.pt (oracle/make_golden.py mano_grad)."""
+    import torch
+    dt = root_rotation.dtype
+    f = lambda a: torch.as_tensor(np.asarray(a, np.float64)).to(dt)
+    bs = root_rotation.shape[0]
+    if use_pca:
+        axis = (pose @ f(m['hands_components'])[:pose.shape[1]] + f(m['hands_mean'])).reshape(-1, 3)
+        angle = torch.norm(axis, p=2, dim=1, keepdim=True) + 1e-8                 # :37
+        u = axis / angle
+        L = torch.zeros((axis.shape[0], 3, 3), dtype=dt)
+        L[:, 2, 1] = u[:, 0]; L[:, 1, 2] = -u[:, 0]
+        L[:, 0, 2] = u[:, 1]; L[:, 2, 0] = -u[:, 1]
+        L[:, 1, 0] = u[:, 2]; L[:, 0, 1] = -u[:, 2]
+        rot = (torch.eye(3, dtype=dt)[None] + torch.sin(angle)[..., None] * L + (1 - torch.cos(angle))[..., None] * L.bmm(L)).view(bs, 15, 3, 3)
+    else:
+        rot = pose.reshape(bs, 15, 3, 3)
+    jreg = m['J_regressor']
+    jreg = f(jreg.todense() if hasattr(jreg, 'todense') else jreg)
+    v_shaped = f(m['v_template'])[None] + torch.einsum('vck,bk->bvc', f(m['shapedirs']), shape)
+    j_tpose = torch.einsum('jv,bvc->bjc', jreg, v_shaped)
+    pose_shape = (rot - torch.eye(3, dtype=dt)).reshape(bs, 135)
+    v_tpose = v_shaped + torch.einsum('vck,bk->bvc', f(m['posedirs']), pose_shape)
+    eye = torch.eye(3, dtype=dt)[None]
+    G = []
+    for i in range(16):
+        R = root_rotation if i == 0 else rot[:, i - 1]
+        t = torch.einsum('bij,bj->bi', eye - R, j_tpose[:, i])
+        if i == 0:
+            G.append((R, t))
+        else:
+            PR, Pt = G[parent[i]]
+            G.append((PR.bmm(R), torch.einsum('bij,bj->bi', PR, t) + Pt))
+    js = [j_tpose[:, 0]]
+    for i in range(1, 16):
+        PR, Pt = G[parent[i]]
+        js.append(torch.einsum('bij,bj->bi', PR, j_tpose[:, i]) + Pt)
+    W = f(m['weights'])
+    GR = torch.stack([g[0] for g in G], 1); Gt = torch.stack([g[1] for g in G], 1)
+    TR = torch.einsum('vj,bjrc->bvrc', W, GR); Tt = torch.einsum('vj,bjr->bvr', W, Gt)
+    v_out = torch.einsum('bvrc,bvc->bvr', TR, v_tpose) + Tt
+    j = torch.stack(js + [v_out[:, t] for t in TIPS], 1)[:, NEW_ORDER]
+    if center_idx is not None:
+        c = j[:, center_idx:center_idx + 1]; v_out = v_out - c; j = j - c
+    if scale is not None:
+        v_out = v_out * scale[:, None, None]; j = j * scale[:, None, None]
+    if trans is not None:
+        v_out = v_out + trans[:, None]; j = j + trans[:, None]
+    if new_skel:
+        mids = {5: (63, 144), 9: (271, 220), 13: (148, 290), 17: (770, 83)}
+        j = torch.stack([(v_out[:, mids[k][0]] + v_out[:, mids[k][1]]) / 2 if k in mids else j[:, k] for k in range(21)], 1)
+    return v_out, j

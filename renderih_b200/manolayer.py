@@ -133,6 +133,7 @@ class ManoLayer(Module):
         return self._derived[2]
 
     def forward(self, root_rotation, pose, shape, trans=None, scale=None):
+        """-> (verts [B,778,3], joints [B,21,3]); differentiable w.r.t. every tensor argument (one fused backward kernel)."""
         in_dev = root_rotation.device
         if in_dev.type == 'cuda':
             dev = in_dev
@@ -140,23 +141,59 @@ class ManoLayer(Module):
             if not torch.cuda.is_available():
                 raise RuntimeError('renderih_b200.ManoLayer needs a CUDA device (sm_100a); there is no CPU fallback')
             dev = torch.device(self._run_device or 'cuda')
-        f = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        f = lambda t: None if t is None else t.to(device=dev, dtype=torch.float32)     # keeps the autograd graph
         R, P, S, T, C = f(root_rotation), f(pose), f(shape), f(trans), f(scale)
         bs = R.shape[0]
         if self.use_pca:
-            ncomps = P.shape[1]
-            assert P.dim() == 2 and ncomps <= 45
+            assert P.dim() == 2 and P.shape[1] <= 45
         else:
-            ncomps = 0
             assert tuple(P.shape[1:]) == (15, 3, 3)
         assert S.shape == (bs, 10)
-        v = torch.empty((bs, 778, 3), device=dev, dtype=torch.float32)
-        j = torch.empty((bs, 21, 3), device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
-            tables = self._tables(dev)
-            call('rih_mano_fwd', tables, self._parent_arr, R.data_ptr(), P.data_ptr(), int(self.use_pca), ncomps, S.data_ptr(),
-                 ops._p(T), ops._p(C), -1 if self.center_idx is None else int(self.center_idx), int(self.new_skel),
-                 v.data_ptr(), j.data_ptr(), bs, torch.cuda.current_stream(dev).cuda_stream)
+        v, j = _ManoFn.apply(self, R, P, S, T, C)
         if in_dev != dev:
             v, j = v.to(in_dev), j.to(in_dev)
         return v, j
+
+
+class _ManoFn(torch.autograd.Function):
+    """rih_mano_fwd / rih_mano_bwd (csrc/mano.cu): ManoLayer.forward, models/manolayer.py:250-322, and its gradient."""
+
+    @staticmethod
+    def forward(ctx, layer, R, P, S, T, C):
+        dev = R.device
+        R, P, S = R.contiguous(), P.contiguous(), S.contiguous()
+        T = None if T is None else T.contiguous()
+        C = None if C is None else C.contiguous()
+        bs = R.shape[0]
+        ncomps = P.shape[1] if layer.use_pca else 0
+        v = torch.empty((bs, 778, 3), device=dev, dtype=torch.float32)
+        j = torch.empty((bs, 21, 3), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            tables = layer._tables(dev)
+            call('rih_mano_fwd', tables, layer._parent_arr, R.data_ptr(), P.data_ptr(), int(layer.use_pca), ncomps, S.data_ptr(),
+                 ops._p(T), ops._p(C), -1 if layer.center_idx is None else int(layer.center_idx), int(layer.new_skel),
+                 v.data_ptr(), j.data_ptr(), bs, torch.cuda.current_stream(dev).cuda_stream)
+        ctx.layer = layer
+        ctx.ncomps = ncomps
+        ctx.save_for_backward(R, P, S, T, C)
+        return v, j
+
+    @staticmethod
+    def backward(ctx, gv, gj):
+        R, P, S, T, C = ctx.saved_tensors
+        layer, dev, bs = ctx.layer, R.device, R.shape[0]
+        c = lambda g: None if g is None else g.contiguous().float()
+        gv, gj = c(gv), c(gj)
+        need = ctx.needs_input_grad      # (layer, R, P, S, T, C)
+        dR = torch.empty_like(R) if need[1] else None
+        dP = torch.empty_like(P) if need[2] else None
+        dS = torch.empty_like(S) if need[3] else None
+        dT = torch.empty_like(T) if (T is not None and need[4]) else None
+        dC = torch.empty_like(C) if (C is not None and need[5]) else None
+        with torch.cuda.device(dev):
+            tables = layer._tables(dev)
+            call('rih_mano_bwd', tables, layer._parent_arr, R.data_ptr(), P.data_ptr(), int(layer.use_pca), ctx.ncomps, S.data_ptr(),
+                 ops._p(T), ops._p(C), -1 if layer.center_idx is None else int(layer.center_idx), int(layer.new_skel),
+                 ops._p(gv), ops._p(gj), ops._p(dR), ops._p(dP), ops._p(dS), ops._p(dT), ops._p(dC), bs,
+                 torch.cuda.current_stream(dev).cuda_stream)
+        return None, dR, dP, dS, dT, dC

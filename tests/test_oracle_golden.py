@@ -129,3 +129,36 @@ def test_mano_oracle_matches_reference_golden():
                                      center_idx=c['center_idx'], new_skel=c['new_skel'])
         assert np.abs(v - case['v'].numpy()).max() < 2e-6, case['cfg']
         assert np.abs(j - case['j'].numpy()).max() < 2e-6, case['cfg']
+
+
+def _mano_case_inputs(c, layer_axis2Rmat=None):
+    inp = fixtures.make_mano_inputs(5)
+    root = torch.from_numpy(mano_ref.rodrigues(inp['axis'].numpy()))
+    if c['use_pca']:
+        pose = inp['pose_pca'][:, :c['ncomps']].clone()
+    else:
+        pose = torch.from_numpy(mano_ref.rodrigues(inp['pose_axis'].numpy().reshape(-1, 3)).reshape(-1, 15, 3, 3))
+    tr, sc = (inp['trans'].clone(), inp['scale'].clone()) if c['ts'] else (None, None)
+    return root, pose, inp['shape'].clone(), tr, sc
+
+
+def test_mano_torch_oracle_gradients_match_reference_golden():
+    """The differentiable restatement (oracle/mano_ref.mano_forward_torch) against the UNMODIFIED reference ManoLayer's autograd
+    gradients (tests/golden/mano_grad_synth.pt): 2e-5 relative to each gradient tensor's max."""
+    gg = torch.load(os.path.join(GOLD, 'mano_grad_synth.pt'), weights_only=False)
+    wv, wj = fixtures.make_mano_loss_weights(5)
+    for case in gg['cases']:
+        c = case['cfg']
+        m = rih_assets.synthetic_mano(0, case['side'])
+        leaves = [None if t is None else t.requires_grad_(True) for t in _mano_case_inputs(c)]
+        v, j = mano_ref.mano_forward_torch(m, *leaves, use_pca=c['use_pca'], center_idx=c['center_idx'], new_skel=c['new_skel'])
+        vn, jn = mano_ref.mano_forward(dict(m, J_regressor=np.asarray(m['J_regressor'].todense())), leaves[0].detach().numpy(), leaves[1].detach().numpy(),
+                                       leaves[2].detach().numpy(), None if leaves[3] is None else leaves[3].detach().numpy(),
+                                       None if leaves[4] is None else leaves[4].detach().numpy(), use_pca=c['use_pca'], center_idx=c['center_idx'], new_skel=c['new_skel'])
+        assert np.abs(v.detach().numpy() - vn).max() < 2e-6 and np.abs(j.detach().numpy() - jn).max() < 2e-6
+        ((v * wv).sum() + (j * wj).sum()).backward()
+        for name, t in zip(('d_root', 'd_pose', 'd_shape', 'd_trans', 'd_scale'), leaves):
+            if t is None:
+                assert case[name] is None
+                continue
+            assert rel_err(t.grad, case[name]) < 2e-5, (case['side'], c, name, rel_err(t.grad, case[name]))

@@ -19,6 +19,7 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--gemm-mode', default='simt')
     ap.add_argument('--fwd-only', action='store_true')
+    ap.add_argument('--encoder', default='resnet50', choices=['resnet50', 'hrnet48'])
     args = ap.parse_args()
     from renderih_b200 import assets as A, ops
     from renderih_b200.config import load_cfg
@@ -28,6 +29,7 @@ def main():
     cm, lm = {'ref': ('tf32c', 'tf32x3'), 'refrn': ('tf32rn', 'tf32x3')}.get(args.gemm_mode, (args.gemm_mode, args.gemm_mode))
     ops.set_gemm_mode(cm, lm)
     cfg = load_cfg()
+    cfg.MODEL.ENCODER_TYPE = args.encoder
     a = A.synthetic_assets(0)
     torch.manual_seed(88)
     model = load_model(cfg, assets=a).cuda().train()
