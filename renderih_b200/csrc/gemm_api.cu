@@ -124,6 +124,16 @@ RIH_API int rih_conv2d_workspace(const int* geom, int which, long long* floats) 
   return 0;
 }
 
+// *supported = 1 when convolution pass `which` (0 fwd, 1 dgrad, 2 wgrad) of this geometry runs on the tcgen05 implicit-GEMM path in the
+// current gemm mode (1x1 / stride-1 / pad-0 convolutions are dense GEMMs and always do), 0 when it takes the exact-fp32 SIMT path.
+RIH_API int rih_conv2d_tc_supported(const int* geom, int which, int* supported) {
+  ConvGeom g;
+  RIH_REQUIRE(parse_geom(geom, g) == 0, "conv2d_tc_supported: inconsistent geometry");
+  const bool dense = g.R == 1 && g.S == 1 && g.stride == 1 && g.pad == 0;
+  *supported = (g_mode[0] != 0 && (dense || tc::conv_tc_supported(g, which))) ? 1 : 0;
+  return 0;
+}
+
 static int conv2d_fwd_impl(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, int relu, float* ws, double* stats,
                            cudaStream_t stream);
 

@@ -56,6 +56,26 @@ int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int
   return 0;
 }
 
+// wgrad output dW[Cout][taps][Cin] as a 3-D map, box {32 channels, 1 tap, 128 filters}: a channel chunk is clipped at its own tap
+int make_tmap_wgrad_out(CUtensorMap* map, const float* base, int Cout, int taps, int Cin) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 1; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (Cin % 4)) { set_error("tensor map (wgrad out): base/Cin not 16-byte aligned"); return 1; }
+  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)taps, (cuuint64_t)Cout};
+  cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)taps * Cin * 4};
+  cuuint32_t box[3] = {32u, 1u, (cuuint32_t)BM};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    cudaFree(0);
+  }
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(wgrad out) failed (%d) Cout=%d taps=%d Cin=%d", (int)r, Cout, taps, Cin); return 1; }
+  return 0;
+}
+
 int g_stats_fused = 0;            // set by the launcher when the epilogue accumulated ep.stats (fused BatchNorm statistics)
 static int g_wide_tiles = 1;     // 128 x 256 output tiles when N % 256 == 0
 void set_wide_tiles(int on) { g_wide_tiles = on ? 1 : 0; }
@@ -65,7 +85,7 @@ static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / compar
 void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep, const Producer& prod, int M, int N, int num_kb, int splits,
-                      int kb_per_split, cudaStream_t s) {
+                      int kb_per_split, cudaStream_t s, const CUtensorMap* c_map = nullptr) {
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Producer, NSPLIT>;
   static bool attr = false;
   if (!attr) {
@@ -79,7 +99,11 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep,
   // TMA-store epilogue whenever the output is a 16-byte aligned matrix and no residual has to be read back
   CUtensorMap tc_;
   int tma_epi = 0;
-  if (!ep.res && ((reinterpret_cast<uintptr_t>(ep.c) & 15) == 0) && (ep.ldc % 4 == 0) && g_tma_epilogue) {
+  if (c_map) {       // caller-built output map (3-D wgrad view); only the persistent TMA-store epilogue understands it
+    if (!g_persistent) { set_error("gemm_tc: output-map override needs the persistent kernel"); return 1; }
+    tc_ = *c_map;
+    tma_epi = 1;
+  } else if (!ep.res && ((reinterpret_cast<uintptr_t>(ep.c) & 15) == 0) && (ep.ldc % 4 == 0) && g_tma_epilogue) {
     if (make_tmap_2d(&tc_, ep.c, M, N, ep.ldc, BM)) return 1;
     tma_epi = 1;
   } else {
@@ -114,17 +138,18 @@ static float g_scale = 1.f; // accumulator scale (bias-compensated truncating TF
 void set_acc_scale(float s) { g_scale = s; }
 template <int BN, bool A_MN, bool B_MN, class Producer>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep, const Producer& prod, int M, int N, int num_kb, int splits,
-                      int kb_per_split, cudaStream_t s) {
+                      int kb_per_split, cudaStream_t s, const CUtensorMap* c_map = nullptr) {
   ep.scale = g_scale;
-  if (g_nsplit == 3) return launch_one<BN, A_MN, B_MN, Producer, 3>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s);
-  if (g_nsplit == 2 && g_persistent) return launch_one<BN, A_MN, B_MN, Producer, 2>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s);
-  return launch_one<BN, A_MN, B_MN, Producer, 1>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s);
+  if (g_nsplit == 3) return launch_one<BN, A_MN, B_MN, Producer, 3>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s, c_map);
+  if (g_nsplit == 2 && g_persistent) return launch_one<BN, A_MN, B_MN, Producer, 2>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s, c_map);
+  return launch_one<BN, A_MN, B_MN, Producer, 1>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s, c_map);
 }
 void set_nsplit(int n) { g_nsplit = (n == 3) ? 3 : (n == 2 ? 2 : 1); }
 
 // split-K planning over k-blocks of 32; switches the epilogue to atomic accumulation when splitting
-static void plan_splitk(Epilogue& ep, int M, int N, int BN, int num_kb, int allow, int& splits, int& kb_per_split, cudaStream_t s) {
-  long long tiles = (long long)cdiv(M, BM) * cdiv(N, BN);
+static void plan_splitk(Epilogue& ep, int M, int N, int BN, int num_kb, int allow, int& splits, int& kb_per_split, cudaStream_t s, int N_grid = 0) {
+  // N = real width of the output rows (what a split-K run has to zero); N_grid = width of the tile grid when it differs (padded wgrad taps)
+  long long tiles = (long long)cdiv(M, BM) * cdiv(N_grid ? N_grid : N, BN);
   splits = 1;
   if (allow && tiles < 148 && num_kb >= 32) {
     splits = (int)((296 + tiles - 1) / tiles);
@@ -178,11 +203,13 @@ static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 bool conv_tc_supported(const ConvGeom& g, int which /*0 fwd, 1 dgrad, 2 wgrad*/) {
   if (g.stride != 1 && g.stride != 2) return false;
   if (g.stride == 2 && ((g.H | g.W) & 1 || g.Ho * 2 != g.H || g.Wo * 2 != g.W || g.R != g.S || (g.R != 1 && g.R != 3) || g.pad != g.R / 2)) return false;
-  if (g.Cin % 32 || g.Cout % 32) return false;
+  // channel counts: multiples of 16 from 32 up (HRNet-w48's 48 / 96-wide branches included): a K block / N chunk that sticks out of the
+  // tensor is zero-filled on load and clipped on store by the TMA unit
+  if (g.Cin % 16 || g.Cout % 16 || g.Cin < 32 || g.Cout < 32) return false;
   if (g.ldx % 4 || g.ldy % 4) return false;
   if (which == 0) return pow2(g.Wo) && pow2(g.Ho) && g.Wo <= 128 && ((long long)g.N * g.Ho * g.Wo) % BM == 0 && (g.Wo * g.Ho >= BM || BM % (g.Wo * g.Ho) == 0);
   if (which == 1) return pow2(g.W) && pow2(g.H) && g.W <= 128 && ((long long)g.N * g.H * g.W) % BM == 0 && (g.W * g.H >= BM || BM % (g.W * g.H) == 0);
-  return pow2(g.Wo) && pow2(g.Ho) && (g.Ho * g.Wo) % 32 == 0 && g.Cin % 64 == 0;
+  return pow2(g.Wo) && pow2(g.Ho) && (g.Ho * g.Wo) % 32 == 0 && (g.Cin % 64 == 0 || g_persistent);
 }
 
 long long conv_tc_workspace(const ConvGeom& g, int which) {
@@ -208,8 +235,8 @@ int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g
     if (make_tmap_nhwc(&ta, x, g.N, g.H, g.W, g.Cin, g.ldx, g.Wo, tile_h, tile_n, false)) return 1;
   }
   if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, BN)) return 1;
-  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, g.stride == 2 ? g.N : 0};
-  const int num_kb = g.R * g.S * (g.Cin / BK);
+  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, g.stride == 2 ? g.N : 0, g.Cin};
+  const int num_kb = g.R * g.S * cdiv(g.Cin, BK);
   if (BN == 256) { ConvFwdProducer<256> p{cg}; return launch_cfg<256, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
   if (BN == 128) { ConvFwdProducer<128> p{cg}; return launch_cfg<128, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
   ConvFwdProducer<64> p{cg};
@@ -231,8 +258,8 @@ int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom
   CUtensorMap ta, tb;
   if (make_tmap_nhwc(&ta, dy, g.N, g.Ho, g.Wo, g.Cout, g.ldy, g.W, tile_h, tile_n, false)) return 1;
   if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, 32, true)) return 1;
-  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, 0};
-  const int num_kb = g.R * g.S * (g.Cout / BK);
+  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, 0, g.Cin};
+  const int num_kb = g.R * g.S * cdiv(g.Cout, BK);
   if (BN == 256) { ConvDgradProducer<256> p{cg}; return launch_cfg<256, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s); }
   if (BN == 128) { ConvDgradProducer<128> p{cg}; return launch_cfg<128, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s); }
   ConvDgradProducer<64> p{cg};
@@ -240,9 +267,12 @@ int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom
 }
 
 int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s) {
-  const int P = g.N * g.Ho * g.Wo, Nn = g.R * g.S * g.Cin, BN = (g.Cin % 128 == 0) ? 128 : 64;
+  const int P = g.N * g.Ho * g.Wo, taps = g.R * g.S, Nn = taps * g.Cin, BN = (g.Cin % 128 == 0) ? 128 : 64;
+  // N tiles never straddle a tap: each tap owns ceil(Cin / BN) tiles; when BN does not divide Cin (48, 96, ...) the tile grid is
+  // "virtual" (cin_pad columns per tap) and the epilogue stores through a 3-D map [Cout][taps][Cin] that clips at the tap's edge
+  const int cin_pad = cdiv(g.Cin, BN) * BN, Ngrid = taps * cin_pad;
   const int bw = g.Wo < 32 ? g.Wo : 32, bh = 32 / bw;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tcm;
   if (make_tmap_2d(&ta, dy, P, g.Cout, g.ldy, 32, true)) return 1;
   if (g.stride == 2) {
     if (!ws) { set_error("conv_wgrad_tf32: stride-2 path needs workspace"); return 1; }
@@ -251,12 +281,18 @@ int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom
   } else {
     if (make_tmap_nhwc(&tb, x, g.N, g.H, g.W, g.Cin, g.ldx, bw, bh, 1, true)) return 1;
   }
-  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, 0, g.stride == 2 ? g.N : 0};
+  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, 0, g.stride == 2 ? g.N : 0, cin_pad};
   int num_kb = P / BK, splits, kps;
-  plan_splitk(ep, g.Cout, Nn, BN, num_kb, 1, splits, kps, s);
-  if (BN == 128) { ConvWgradProducer<128> p{cg}; return launch_cfg<128, true, true>(ta, tb, ep, p, g.Cout, Nn, num_kb, splits, kps, s); }
+  plan_splitk(ep, g.Cout, Nn, BN, num_kb, 1, splits, kps, s, Ngrid);
+  const CUtensorMap* cmap = nullptr;
+  if (cin_pad != g.Cin) {
+    if (ep.ldc != Nn) { set_error("conv_wgrad_tf32: padded-tap path needs a dense dW"); return 1; }
+    if (make_tmap_wgrad_out(&tcm, ep.c, g.Cout, taps, g.Cin)) return 1;
+    cmap = &tcm; ep.nv_pad = cin_pad; ep.nv_real = g.Cin;
+  }
+  if (BN == 128) { ConvWgradProducer<128> p{cg}; return launch_cfg<128, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap); }
   ConvWgradProducer<64> p{cg};
-  return launch_cfg<64, true, true>(ta, tb, ep, p, g.Cout, Nn, num_kb, splits, kps, s);
+  return launch_cfg<64, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap);
 }
 
 }  // namespace tc

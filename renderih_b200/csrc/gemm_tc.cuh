@@ -67,6 +67,15 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const 
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
+// 3-D variants (wgrad output viewed as [Cout][taps][Cin] so that a channel chunk is clipped at ITS tap's edge)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
@@ -159,6 +168,7 @@ struct ConvTcGeom {
   int H, W, Ho, Wo;        // input / output spatial size (stride 1 only)
   int tile_h;              // fwd/dgrad: rows of the 128-pixel tile (tile_w == full width); tile images = 128/(tile_w*tile_h)
   int s2_images;           // > 0: stride-2 convolution reading the parity-stacked input [4*N, H/2, W/2, C]; value = N
+  int cin_pad;             // wgrad: columns per tap in the (virtual) N tile grid = ceil(Cin / BN) * BN (== Cin when BN divides Cin)
 };
 // stride 2: input row 2*o + r - pad = 2*(o + shift) + parity
 __device__ __forceinline__ void s2_tap(int r, int pad, int& parity, int& shift) {
@@ -172,7 +182,9 @@ template <int BN>
 struct ConvFwdProducer {
   ConvTcGeom g;
   __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
-    const int cpb = g.Cin / BK;
+    // channel blocks per tap; when Cin % 32 != 0 the last block of a tap is partly out of bounds in the activation map (TMA zero
+    // fill), which also cancels whatever the weight box picks up from the next tap's columns
+    const int cpb = (g.Cin + BK - 1) / BK;
     const int tap = kb / cpb, c0 = (kb - tap * cpb) * BK;
     const int r = tap / g.S, s = tap - r * g.S;
     const int P = g.Ho * g.Wo;
@@ -185,7 +197,7 @@ struct ConvFwdProducer {
     } else {
       tma_load_4d(sa, ta, c0, s - g.pad, oh0 + r - g.pad, n, bar);
     }
-    tma_load_2d(sb, tb, kb * BK, n0, bar);
+    tma_load_2d(sb, tb, tap * g.Cin + c0, n0, bar);
   }
 };
 // dgrad (stride 1): A = shifted dY boxes (4-D map over [N,Ho,Wo,Cout]), B = weights as MN-major chunks {32 c, 32 co}
@@ -193,7 +205,7 @@ template <int BN>
 struct ConvDgradProducer {
   ConvTcGeom g;
   __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
-    const int cpb = g.Cout / BK;
+    const int cpb = (g.Cout + BK - 1) / BK;
     const int tap = kb / cpb, co0 = (kb - tap * cpb) * BK;
     const int r = tap / g.S, s = tap - r * g.S;
     const int P = g.H * g.W;
@@ -212,7 +224,7 @@ struct ConvWgradProducer {
     const int P = g.Ho * g.Wo;
     const int n = p0 / P, rem = p0 - n * P;
     const int oh = rem / g.Wo, ow = rem - oh * g.Wo;
-    const int tap = n0 / g.Cin, cbase = n0 - tap * g.Cin;
+    const int tap = n0 / g.cin_pad, cbase = n0 - tap * g.cin_pad;
     const int r = tap / g.S, s = tap - r * g.S;
 #pragma unroll
     for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
@@ -563,6 +575,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           mbar_arrive(&tmem_empty[acc]);
         }
         const int nb = n0 + c * 32;
+        int sc0 = nb, sc1 = 0;
+        if (ep.nv_pad) {               // virtual wgrad column -> (channel, tap); chunks wholly beyond Cin are skipped (warp-uniform)
+          sc1 = nb / ep.nv_pad; sc0 = nb - sc1 * ep.nv_pad;
+          if (sc0 >= ep.nv_real) continue;
+        }
         if (tma_epi) {
           if (ep.scale != 1.f) {
 #pragma unroll
@@ -591,7 +608,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           fence_proxy_async();
           epi_bar_sync();
           if (elected) {
-            if (ep.mode == 0) tma_store_2d(&tmap_c, buf, nb, m0);
+            if (ep.nv_pad) {
+              if (ep.mode == 0) tma_store_3d(&tmap_c, buf, sc0, sc1, m0);
+              else tma_reduce_add_3d(&tmap_c, buf, sc0, sc1, m0);
+            } else if (ep.mode == 0) tma_store_2d(&tmap_c, buf, nb, m0);
             else tma_reduce_add_2d(&tmap_c, buf, nb, m0);
             tma_store_commit();
           }

@@ -390,6 +390,37 @@ def test_conv2d_stride2_tensor_core(ops, N, H, Cin, Cout, k, mode):
         assert rel(a, r) < tol, (n, rel(a, r))
 
 
+@pytest.mark.parametrize('N,H,Cin,Cout,k,stride', [
+    (2, 64, 48, 48, 3, 1), (2, 32, 96, 96, 3, 1), (4, 16, 192, 192, 3, 1), (2, 8, 384, 384, 3, 1),      # HRNet-w48 branch blocks
+    (2, 64, 256, 48, 3, 1), (2, 64, 48, 128, 3, 1), (2, 16, 80, 208, 3, 1),                              # transition1.0 / odd multiples of 16
+    (2, 64, 48, 48, 3, 2), (2, 64, 48, 96, 3, 2), (4, 32, 96, 192, 3, 2), (2, 64, 256, 96, 3, 2), (4, 16, 192, 384, 3, 2)])   # fuse / transition chains
+def test_conv2d_tensor_core_channels_multiple_of_16(ops, N, H, Cin, Cout, k, stride):
+    """Channel counts that are multiples of 16 but not of 32 / 64 (HRNet-w48: 48, 96 ...) on the tcgen05 path: the K blocks / N chunks that
+    stick out of the tensor are zero-filled (loads) and clipped (stores, 3-D dW map per tap) by the TMA unit.  3xTF32 so that any stray
+    contribution would show: tolerance 1e-4 relative (fp32-faithful), forward, dgrad and wgrad; and the path must really be the tensor-core one."""
+    import ctypes
+    from renderih_b200._lib import call
+    x = T(N, Cin, H, H)
+    w = (torch.randn(Cout, Cin, k, k) * (Cin * k * k) ** -0.5).to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xr = x.permute(0, 2, 3, 1).contiguous().reshape(N * H * H, Cin)
+    ops.set_gemm_mode('tf32x3', 'tf32x3')
+    try:
+        Ho = (H + 2 * (k // 2) - k) // stride + 1
+        geom = (ctypes.c_int * 13)(N, H, H, Cin, Ho, Ho, Cout, k, k, stride, k // 2, Cin, Cout)
+        for which in (0, 1, 2):
+            flag = ctypes.c_int(0)
+            call('rih_conv2d_tc_supported', geom, which, ctypes.byref(flag))
+            assert flag.value == 1, ('not on the tensor-core path', which)
+        y = ops.conv2d(xr, w, None, N, H, H, stride=stride, pad=k // 2)
+        g_ours = grads(y, [x, w])
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+    yr = F.conv2d(x, w, None, stride=stride, padding=k // 2).permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert rel(y, yr) < 1e-4, rel(y, yr)
+    for a, r, n in zip(g_ours, grads(yr, [x, w]), 'xw'):
+        assert rel(a, r) < 1e-4, (n, rel(a, r))
+
+
 @pytest.mark.parametrize('H,p,C,Co', [(32, 4, 256, 64), (16, 2, 256, 128)])
 def test_patchify_linear_equals_patch_conv(ops, H, p, C, Co):
     N = 3
