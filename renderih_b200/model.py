@@ -205,6 +205,45 @@ class resnet_mid(nn.Module):
         return global_feature, fmaps
 
 
+# ============================================================================ two-hand concurrency
+class HandStreams:
+    """The left- and right-hand sub-graphs of a DualGraph level are independent until `inter_attn` mixes them, and each of their
+    kernels (4032 ... 16128 token rows) fills well under half of the 148 SMs.  Running them on two side streams lets the GPU overlap
+    them; under CUDA-graph capture the fork/join becomes two parallel branches of the graph.  autograd replays each backward node on
+    its forward stream, so the backward pass is two-stream as well.  `RIH_HAND_STREAMS=0` disables it (single stream)."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, device):
+        import os
+        if os.environ.get('RIH_HAND_STREAMS', '1') == '0':
+            return None
+        key = (device.type, device.index)
+        if key not in cls._cache:
+            cls._cache[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+        return cls._cache[key]
+
+
+def run_hands(device, fn_left, fn_right):
+    """(fn_left(), fn_right()) -- concurrently on two side streams when enabled.  Every tensor a branch returns is registered with the
+    caching allocator as used by the joining stream (it was allocated on the side stream's pool)."""
+    st = HandStreams.get(device)
+    if st is None:
+        return fn_left(), fn_right()
+    main = torch.cuda.current_stream(device)
+    outs = []
+    for s, fn in zip(st, (fn_left, fn_right)):
+        s.wait_stream(main)
+        with torch.cuda.stream(s):
+            outs.append(fn())
+    for s, o in zip(st, outs):
+        main.wait_stream(s)
+        for t in (o if isinstance(o, (tuple, list)) else (o,)):
+            if torch.is_tensor(t):
+                t.record_stream(main)
+    return outs[0], outs[1]
+
+
 # ============================================================================ decoder blocks (models/model_attn/*.py)
 class GCN_ResBlock(nn.Module):
     """models/model_attn/gcn.py:72-110 -- note norm1 is computed-and-discarded by the reference (103-104): it is a
@@ -383,8 +422,7 @@ class inter_attn(nn.Module):
 
     def forward(self, Lf, Rf, B, V):
         p = self.p if self.training else 0.0
-        Lf = self.L_self_attn_layer(Lf, B, V)
-        Rf = self.R_self_attn_layer(Rf, B, V)
+        Lf, Rf = run_hands(Lf.device, lambda: self.L_self_attn_layer(Lf, B, V), lambda: self.R_self_attn_layer(Rf, B, V))
         L2 = ops.layernorm(Lf, self.layer_norm1.weight, self.layer_norm1.bias)
         R2 = ops.layernorm(Rf, self.layer_norm2.weight, self.layer_norm2.bias)
         Lq = ops.linear(L2, self.w_qs.weight, self.w_qs.bias)
@@ -399,7 +437,7 @@ class inter_attn(nn.Module):
         feat_L2R = ops.attention(Rq, Lk, Lv, B, H, V, V, p_drop=p)
         xR = ops.linear(feat_L2R, self.fc.weight, self.fc.bias, res=Rf, p_drop=p)
         xL = ops.linear(feat_R2L, self.fc.weight, self.fc.bias, res=Lf, p_drop=p)
-        return self.ffL(xL), self.ffR(xR)
+        return run_hands(xL.device, lambda: self.ffL(xL), lambda: self.ffR(xR))
 
 
 class DualGraphLayer(nn.Module):
@@ -420,10 +458,8 @@ class DualGraphLayer(nn.Module):
     def forward(self, Lf, Rf, img_f, B):
         """Lf/Rf already carry `+ position_embeddings` (added by the entry / upsample kernels)."""
         V = self.verts_num
-        Lf = self.graph_left(Lf, B, V)
-        Rf = self.graph_right(Rf, B, V)
-        Lf = self.img_ex_left(img_f, Lf, B, V)
-        Rf = self.img_ex_right(img_f, Rf, B, V)
+        Lf, Rf = run_hands(Lf.device, lambda: self.img_ex_left(img_f, self.graph_left(Lf, B, V), B, V),
+                           lambda: self.img_ex_right(img_f, self.graph_right(Rf, B, V), B, V))
         return self.attn(Lf, Rf, B, V)
 
 
