@@ -7,8 +7,11 @@
 using namespace rih;
 
 constexpr int ATT_WARPS = 8;
-constexpr int ATT_RF = 8;   // query rows per warp block, forward
-constexpr int ATT_RB = 4;   // row block, backward (both phases)
+// query rows per warp block: forward 4 or 8, backward (both phases) 2 or 4 -- more rows amortise the K/V shared-memory reads over
+// more FMAs but cost registers (MAXJ * R score accumulators per lane); chosen per launch from the key count (see att_rows)
+static int g_att_force_rf = 0, g_att_force_rb = 0;   // testing / tuning override (rih_attn_set_row_blocks)
+static inline int att_rows_fwd(int Skr) { return g_att_force_rf ? g_att_force_rf : 4; }      // measured best at all 9 decoder shapes
+static inline int att_rows_bwd(int Smax) { return g_att_force_rb ? g_att_force_rb : 4; }
 
 __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
@@ -23,6 +26,7 @@ __device__ __forceinline__ void axpy4(float4& acc, float p, float4 v) {
 //   probabilities are stored permuted as p[(j % JS) * T + j / JS] so that a lane's rows are contiguous
 struct AttGeo {
   int d, dp, G, JS, Skr, T;   // Skr = keys rounded up to 32, T = Skr / JS
+  int js_shift;               // JS is a power of two (32 / G, G = d / 4 in {1,2,4,8,16,32}) whenever G divides 32
 };
 __host__ __device__ __forceinline__ AttGeo make_geo(int d, int Sk) {
   AttGeo g;
@@ -30,6 +34,7 @@ __host__ __device__ __forceinline__ AttGeo make_geo(int d, int Sk) {
   g.JS = 32 / g.G;
   const int q = (4 * g.JS > 32) ? 4 * g.JS : 32;      // rows padded so that T = Skr / JS is a multiple of 4 (float4 reads of p)
   g.Skr = ((Sk + q - 1) / q) * q; g.T = g.Skr / g.JS;
+  g.js_shift = 0; while ((1 << g.js_shift) < g.JS) ++g.js_shift;
   return g;
 }
 
@@ -61,13 +66,12 @@ __device__ __forceinline__ void pv_accumulate(const float* __restrict__ M, int l
   }
 }
 
-template <int MAXJ>
+template <int MAXJ, int R>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_fwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const float* __restrict__ k, long long k_bs, int ldk,
                 const float* __restrict__ v, long long v_bs, int ldv, float* __restrict__ o, long long o_bs, int ldo,
                 float* __restrict__ lse, int H, int Sq, int Sk, int d, float scale, int rows_per_cta,
                 const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
-  constexpr int R = ATT_RF;
   const unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
   extern __shared__ __align__(16) float smem[];
   const AttGeo g = make_geo(d, Sk);
@@ -147,7 +151,7 @@ attn_fwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const floa
         if (j < g.Skr) {
           float p = s[r][jj] * inv;
           if (thresh && j < Sk) p *= dropout_scale(seed, drop_base + j, thresh, inv_keep);
-          myp[r * g.Skr + (j % g.JS) * g.T + j / g.JS] = p;
+          myp[r * g.Skr + (j & (g.JS - 1)) * g.T + (j >> g.js_shift)] = p;
         }
       }
       if (lane == 0 && lse && i < r1) lse[(size_t)bh * Sq + i] = mx + logf(sum);
@@ -170,35 +174,39 @@ RIH_API int rih_attn_fwd(const float* q, long long q_bs, int ldq, const float* k
                          const float* v, long long v_bs, int ldv, float* o, long long o_bs, int ldo, float* lse,
                          int B, int H, int Sq, int Sk, int d, float scale, float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, cudaStream_t s) {
   RIH_REQUIRE(Sk > 0 && Sk <= 512, "attn_fwd: Sk=%d unsupported (max 512)", Sk);
-  RIH_REQUIRE(d > 0 && d <= 128 && d % 4 == 0, "attn_fwd: head dim %d unsupported (multiple of 4, <= 128)", d);
+  RIH_REQUIRE(d >= 4 && d <= 128 && (d & (d - 1)) == 0, "attn_fwd: head dim %d unsupported (power of two in 4..128)", d);
   RIH_REQUIRE(att_aligned(q, q_bs, ldq) && att_aligned(k, k_bs, ldk) && att_aligned(v, v_bs, ldv) && att_aligned(o, o_bs, ldo),
               "attn_fwd: operands must be 16-byte aligned with strides that are multiples of 4 floats");
   if (B * H == 0 || Sq == 0) return 0;
   const int Skr = make_geo(d, Sk).Skr;
-  size_t smem = sizeof(float) * (2 * (size_t)Skr * (d + 4) + ATT_WARPS * ATT_RF * d + (size_t)ATT_WARPS * ATT_RF * Skr);
+  const int RF = att_rows_fwd(Skr);
+  size_t smem = sizeof(float) * (2 * (size_t)Skr * (d + 4) + ATT_WARPS * RF * d + (size_t)ATT_WARPS * RF * Skr);
   RIH_REQUIRE(smem <= 227 * 1024, "attn_fwd: shared memory %zu too large", smem);
   int ysplit = 1;
   while (B * H * ysplit < 148 * 2 && Sq / (ysplit * 2) >= 32) ysplit *= 2;
   int rows_per_cta = cdiv(Sq, ysplit);
-  rows_per_cta = (rows_per_cta + ATT_RF - 1) / ATT_RF * ATT_RF;
+  rows_per_cta = (rows_per_cta + RF - 1) / RF * RF;
   dim3 grid(B * H, cdiv(Sq, rows_per_cta));
   uint32_t thresh = dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u;
   float ik = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
-  static bool attr10 = false, attr16 = false;
-  if (Skr <= 320) {
-    if (!attr10) { RIH_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr10 = true; }
-    attn_fwd_kernel<10><<<grid, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, lse, H, Sq, Sk, d, scale, rows_per_cta, seed_ptr, site, thresh, ik);
-  } else {
-    if (!attr16) { RIH_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr16 = true; }
-    attn_fwd_kernel<16><<<grid, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, lse, H, Sq, Sk, d, scale, rows_per_cta, seed_ptr, site, thresh, ik);
+#define RIH_ATT_FWD(MJ, RR)                                                                                                            \
+  {                                                                                                                                    \
+    static bool attr = false;                                                                                                          \
+    if (!attr) { RIH_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<MJ, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; } \
+    attn_fwd_kernel<MJ, RR><<<grid, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, lse, H, Sq, Sk, d, scale, \
+                                                                rows_per_cta, seed_ptr, site, thresh, ik);                             \
   }
+  if (Skr <= 128) { if (RF == 8) RIH_ATT_FWD(4, 8) else RIH_ATT_FWD(4, 4) }
+  else if (Skr <= 320) { if (RF == 8) RIH_ATT_FWD(10, 8) else RIH_ATT_FWD(10, 4) }
+  else { if (RF == 8) RIH_ATT_FWD(16, 8) else RIH_ATT_FWD(16, 4) }
+#undef RIH_ATT_FWD
   return check_launch("attn_fwd");
 }
 
 // ------------------------------------------------------------------ backward
 // Phase A (warp per block of R query rows): dS -> dQ = scale * dS K.
 // Phase B (warp per block of R key rows)  : P~^T, dS^T -> dV = P~^T dO, dK = scale * dS^T Q.  No atomics, deterministic.
-template <int MAXJ>
+template <int MAXJ, int R>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_bwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const float* __restrict__ k, long long k_bs, int ldk,
                 const float* __restrict__ v, long long v_bs, int ldv, const float* __restrict__ o, long long o_bs, int ldo,
@@ -206,7 +214,6 @@ attn_bwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const floa
                 float* __restrict__ dq, long long dq_bs, int lddq, float* __restrict__ dk, long long dk_bs, int lddk,
                 float* __restrict__ dv, long long dv_bs, int lddv,
                 int H, int Sq, int Sk, int d, float scale, const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
-  constexpr int R = ATT_RB;
   const unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
   extern __shared__ __align__(16) float smem[];
   const AttGeo gk = make_geo(d, Sk);   // splits over keys (phase A accumulations)
@@ -301,7 +308,7 @@ attn_bwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const floa
             const float m = thresh ? dropout_scale(seed, drop_base + j, thresh, inv_keep) : 1.f;
             dsv = p * (m * dpt[r][jj] - Di);
           }
-          my1[r * Smax + (j % gk.JS) * gk.T + j / gk.JS] = dsv;
+          my1[r * Smax + (j & (gk.JS - 1)) * gk.T + (j >> gk.js_shift)] = dsv;
         }
       }
     }
@@ -319,6 +326,7 @@ attn_bwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const floa
     __syncwarp();
   }
   // ---------------- phase B: key-row blocks
+  const size_t drop_bh = (size_t)bh * Sq * Sk;
   for (int j0 = warp * R; j0 < Sk; j0 += ATT_WARPS * R) {
     for (int e = lane; e < R * d4; e += 32) {
       int r = e / d4, c = (e - r * d4) * 4;
@@ -357,11 +365,11 @@ attn_bwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const floa
           float pt = 0.f, dsv = 0.f;
           if (i < Sq) {
             const float p = expf(sc[r][ii] * scale - Ls[i]);
-            const float m = thresh ? dropout_scale(seed, ((size_t)bh * Sq + i) * Sk + j, thresh, inv_keep) : 1.f;
+            const float m = thresh ? dropout_scale(seed, drop_bh + (uint32_t)(i * Sk + j), thresh, inv_keep) : 1.f;
             pt = p * m;
             dsv = p * (m * dpt[r][ii] - Dl[i]);
           }
-          const int pi = (i % gq.JS) * gq.T + i / gq.JS;
+          const int pi = (i & (gq.JS - 1)) * gq.T + (i >> gq.js_shift);
           my1[r * Smax + pi] = pt;
           my2[r * Smax + pi] = dsv;
         }
@@ -389,26 +397,35 @@ RIH_API int rih_attn_bwd(const float* q, long long q_bs, int ldq, const float* k
                          const float* dout, long long do_bs, int lddo, const float* lse,
                          float* dq, long long dq_bs, int lddq, float* dk, long long dk_bs, int lddk, float* dv, long long dv_bs, int lddv,
                          int B, int H, int Sq, int Sk, int d, float scale, float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, cudaStream_t s) {
-  RIH_REQUIRE(d > 0 && d <= 128 && d % 4 == 0, "attn_bwd: head dim %d unsupported (multiple of 4, <= 128)", d);
+  RIH_REQUIRE(d >= 4 && d <= 128 && (d & (d - 1)) == 0, "attn_bwd: head dim %d unsupported (power of two in 4..128)", d);
   RIH_REQUIRE(Sk <= 512 && Sq <= 512, "attn_bwd: sequence length above 512 unsupported (Sq=%d Sk=%d)", Sq, Sk);
   RIH_REQUIRE(att_aligned(q, q_bs, ldq) && att_aligned(k, k_bs, ldk) && att_aligned(v, v_bs, ldv) && att_aligned(o, o_bs, ldo) &&
               att_aligned(dout, do_bs, lddo) && att_aligned(dq, dq_bs, lddq) && att_aligned(dk, dk_bs, lddk) && att_aligned(dv, dv_bs, lddv),
               "attn_bwd: operands must be 16-byte aligned with strides that are multiples of 4 floats");
   if (B * H == 0 || Sq == 0 || Sk == 0) return 0;
   const int Sqr = make_geo(d, Sq).Skr, Skr = make_geo(d, Sk).Skr, Smax = Sqr > Skr ? Sqr : Skr;
-  size_t smem = sizeof(float) * ((size_t)(2 * Sqr + 2 * Skr) * (d + 4) + 2 * (size_t)Sqr + 2 * (size_t)ATT_WARPS * ATT_RB * Smax + (size_t)ATT_WARPS * 2 * ATT_RB * d);
+  const int RB = att_rows_bwd(Smax);
+  size_t smem = sizeof(float) * ((size_t)(2 * Sqr + 2 * Skr) * (d + 4) + 2 * (size_t)Sqr + 2 * (size_t)ATT_WARPS * RB * Smax + (size_t)ATT_WARPS * 2 * RB * d);
   RIH_REQUIRE(smem <= 227 * 1024, "attn_bwd: shared memory %zu too large (Sq=%d Sk=%d d=%d)", smem, Sq, Sk, d);
   uint32_t thresh = dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u;
   float ik = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
-  static bool attr10 = false, attr16 = false;
-  if (Smax <= 320) {
-    if (!attr10) { RIH_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr10 = true; }
-    attn_bwd_kernel<10><<<B * H, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, dout, do_bs, lddo, lse,
-                                                             dq, dq_bs, lddq, dk, dk_bs, lddk, dv, dv_bs, lddv, H, Sq, Sk, d, scale, seed_ptr, site, thresh, ik);
-  } else {
-    if (!attr16) { RIH_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr16 = true; }
-    attn_bwd_kernel<16><<<B * H, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, dout, do_bs, lddo, lse,
-                                                             dq, dq_bs, lddq, dk, dk_bs, lddk, dv, dv_bs, lddv, H, Sq, Sk, d, scale, seed_ptr, site, thresh, ik);
+#define RIH_ATT_BWD(MJ, RR)                                                                                                            \
+  {                                                                                                                                    \
+    static bool attr = false;                                                                                                          \
+    if (!attr) { RIH_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<MJ, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; } \
+    attn_bwd_kernel<MJ, RR><<<B * H, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, dout, do_bs, lddo, lse, \
+                                                                 dq, dq_bs, lddq, dk, dk_bs, lddk, dv, dv_bs, lddv, H, Sq, Sk, d, scale, seed_ptr, site, thresh, ik); \
   }
+  if (Smax <= 128) { if (RB == 4) RIH_ATT_BWD(4, 4) else RIH_ATT_BWD(4, 2) }
+  else if (Smax <= 320) { if (RB == 4) RIH_ATT_BWD(10, 4) else RIH_ATT_BWD(10, 2) }
+  else { if (RB == 4) RIH_ATT_BWD(16, 4) else RIH_ATT_BWD(16, 2) }
+#undef RIH_ATT_BWD
   return check_launch("attn_bwd");
+}
+
+// Tuning / testing hook: force the per-warp row blocks (forward 4 | 8, backward 2 | 4; 0 = automatic choice from the key count).
+RIH_API int rih_attn_set_row_blocks(int rows_fwd, int rows_bwd) {
+  RIH_REQUIRE((rows_fwd == 0 || rows_fwd == 4 || rows_fwd == 8) && (rows_bwd == 0 || rows_bwd == 2 || rows_bwd == 4), "attn_set_row_blocks: fwd in {0,4,8}, bwd in {0,2,4}");
+  g_att_force_rf = rows_fwd; g_att_force_rb = rows_bwd;
+  return 0;
 }

@@ -58,13 +58,16 @@ __device__ __forceinline__ void divmod(long long i, int d, bool small, long long
   }
 }
 
-// Counter-based RNG for dropout masks (stateless: regenerated in backward from the same key).
+// Counter-based RNG for dropout masks (stateless: regenerated in backward from the same key): murmur3's 32-bit finaliser over the
+// element index xor a per-launch key (8 integer instructions per element; the 64-bit splitmix used before cost ~3x that and showed
+// up in the attention kernels, where a mask is drawn per score).
 __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
+  const uint32_t key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u);
+  uint32_t x = ((uint32_t)idx ^ key) + (uint32_t)(idx >> 32) * 0x85EBCA6Bu;
+  x ^= x >> 16; x *= 0x85EBCA6Bu;
+  x ^= x >> 13; x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
 }
 // keep-scale for dropout: returns 0 (dropped) or 1/(1-p)
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, uint32_t thresh, float inv_keep) {
