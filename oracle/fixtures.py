@@ -28,8 +28,8 @@ def init_state_dict(template_sd, seed=SEED):
             out[k] = torch.randn(t.shape, generator=g) * 0.1
         elif k.endswith('running_var'):
             out[k] = torch.rand(t.shape, generator=g) * 0.5 + 0.75
-        elif k == 'decoder.dense_coor' or k == 'decoder.unsample_layer.weight':
-            out[k] = t.clone().float()
+        elif k == 'decoder.dense_coor' or k == 'decoder.unsample_layer.weight' or '.mano_' in k:
+            out[k] = t.clone().float()      # asset-derived tensors (graph / MANO tables) keep their values
         elif t.dim() == 1:
             if k.endswith('.weight'):      # norm scales
                 out[k] = 1.0 + 0.1 * torch.randn(t.shape, generator=g)

@@ -48,9 +48,10 @@ def flat(out):
         d['trans2d_' + side] = params['trans2d'][side]
         d['v3c_' + side] = hlist[0]['verts3d'][side]
         d['v2c_' + side] = hlist[0]['verts2d'][side]
-        d['v3list_' + side] = other['verts3d_MANO_list'][side][0]
-        d['v2list_' + side] = other['verts2d_MANO_list'][side][0]
-    for k in ('hms', 'mask', 'dense'):
+        if other['verts3d_MANO_list'][side]:
+            d['v3list_' + side] = other['verts3d_MANO_list'][side][0]
+            d['v2list_' + side] = other['verts2d_MANO_list'][side][0]
+    for k in (('hms', 'mask', 'dense') if 'hms' in other else ()):     # the myhand graph variant has no auxiliary maps
         t = other[k] if other[k].dim() == 4 else other[k][:, None]     # HRnet_encoder returns mask as [B,64,64] (encoder.py:235)
         d[k + '_sub'] = t[:, :, ::8, ::8].contiguous()
         d[k + '_mean'] = t.mean(dim=(2, 3))
@@ -58,8 +59,13 @@ def flat(out):
 
 
 def model_golden(ns, tmp, encoder_type, fname, bn_probe):
-    """Eval forward + train-mode forward/backward (dropout 0) of the unmodified reference model with `encoder_type`."""
-    ref, cfg = rb.build_reference_model(asset_dir=tmp, encoder_type=encoder_type, dropout=0.0)
+    """Eval forward + train-mode forward/backward (dropout 0) of the unmodified reference model with `encoder_type`
+    ('graph' = the common/myhand default variant, built through oracle/ref_bridge.build_reference_myhand_model)."""
+    if encoder_type == 'graph':
+        ref, _ = rb.build_reference_myhand_model(tmp, 'graph', dropout=0.0)
+        _, cfg = rb.build_reference_model(asset_dir=tmp, encoder_type='resnet50', dropout=0.0)    # cfg for calc_loss_GCN only
+    else:
+        ref, cfg = rb.build_reference_model(asset_dir=tmp, encoder_type=encoder_type, dropout=0.0)
     sd = fixtures.init_state_dict(ref.state_dict())
     ref.load_state_dict(sd)
     B = 2
@@ -156,7 +162,7 @@ def mano_grad_golden(ns, tmp):
 
 
 def main(which):
-    """which: any of 'resnet50', 'hrnet48', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
+    """which: any of 'resnet50', 'hrnet48', 'graph', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
     os.makedirs(GOLD, exist_ok=True)
     ns = rb.import_reference()
     with tempfile.TemporaryDirectory() as tmp:
@@ -165,6 +171,8 @@ def main(which):
             model_golden(ns, tmp, 'resnet50', 'model_synth_b2.pt', 'resnet')
         if 'hrnet48' in which:     # BASELINE config 5 (models/encoder.py:176-352, model_zoo/hrnet.py)
             model_golden(ns, tmp, 'hrnet48', 'model_hrnet48_synth_b2.pt', 'hrnet')
+        if 'graph' in which:       # common/myhand/lijun_model_graph.load_graph_model
+            model_golden(ns, tmp, 'graph', 'model_graph_synth_b2.pt', 'resnet')
         if 'mano' in which:
             mano_golden(ns, tmp)
         if 'mano_grad' in which:
@@ -172,4 +180,4 @@ def main(which):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'mano', 'mano_grad'])
+    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'graph', 'mano', 'mano_grad'])

@@ -56,6 +56,26 @@ def _simple_decoder(x, sd, pre, tr):
     return out, fmaps
 
 
+def resnet_trunk(sd, img, tr, blocks=(3, 4, 6, 3)):
+    """torchvision ResNet-50 trunk as driven by ResNetSimple.forward (models/encoder.py:107-118 == common/myhand/encoder_lijun.py:91-104)"""
+    p = 'encoder.resnet'
+    x = F.relu(_bn(F.conv2d(img, sd[p + '.conv1.weight'], stride=2, padding=3), sd, p + '.bn1', tr))
+    x = F.max_pool2d(x, 3, 2, 1)
+    feats = []
+    for li, nb in enumerate(blocks):
+        for bi in range(nb):
+            stride = 2 if (bi == 0 and li > 0) else 1
+            x = _bottleneck(x, sd, '%s.layer%d.%d' % (p, li + 1, bi), stride, bi == 0, tr)
+        feats.append(x)
+    return feats[::-1]          # [x1 (8x8), x2, x3, x4 (64x64)]
+
+
+def graph_mid_forward(sd, img_f, tr):
+    """resnet_mid.forward of the myhand variant, common/myhand/encoder_lijun.py:140-146"""
+    gf = F.adaptive_avg_pool2d(img_f[0], 1).flatten(1)
+    return gf, [_bn(F.relu(F.conv2d(img_f[i], sd['mid_model.convs.%d.0.weight' % i])), sd, 'mid_model.convs.%d.2' % i, tr) for i in range(4)]
+
+
 def encoder_forward(sd, img, tr, blocks=(3, 4, 6, 3)):
     p = 'encoder.resnet'
     x = F.relu(_bn(F.conv2d(img, sd[p + '.conv1.weight'], stride=2, padding=3), sd, p + '.bn1', tr))
@@ -218,10 +238,21 @@ def gcn_resblock(x, sd, pre, L, p, tr):
     return _ln(x1 + x2, sd, pre + '.norm3')
 
 
-def graph_layer(x, sd, pre, L, p, tr, n=4):
-    """GraphLayer.forward, gcn.py:132-138"""
+def mlp_graph_block(x, sd, pre, p, tr):
+    """GCN_ResBlock.forward of the myhand variant (no Laplacian), common/myhand/model_attn/DualGraph_lijun.py:46-58"""
+    x1 = _lin(F.relu(_ln(x, sd, pre + '.norm1')), sd, pre + '.fc1')
+    x1 = _lin(F.relu(_ln(x1, sd, pre + '.norm2')), sd, pre + '.fc2')
+    x1 = _drop(x1, p, tr)
+    return _ln(x1 + _lin(x, sd, pre + '.shortcut'), sd, pre + '.norm3')
+
+
+def graph_layer(x, sd, pre, L, p, tr, n=4, variant='intaghand'):
+    """GraphLayer.forward, gcn.py:132-138 (== DualGraph_lijun.py:82-88)"""
     for i in range(n):
-        x = gcn_resblock(x, sd, '%s.GCN_blocks.%d' % (pre, i), L, p, tr)
+        if variant == 'graph':
+            x = mlp_graph_block(x, sd, '%s.GCN_blocks.%d' % (pre, i), p, tr)
+        else:
+            x = gcn_resblock(x, sd, '%s.GCN_blocks.%d' % (pre, i), L, p, tr)
         if i != n - 1:
             x = F.relu(x)
     return x
@@ -262,17 +293,21 @@ def img_ex(img, verts_f, sd, pre, p, tr):
     return self_attn(x, sd, pre + '.attn.Attn', p, tr)[:, :V]
 
 
-def inter_attn(Lf, Rf, sd, pre, p, tr, H=4):
-    """inter_attn.forward, inter_attn.py:73-123"""
+def inter_attn(Lf, Rf, sd, pre, p, tr, H=4, variant='intaghand'):
+    """inter_attn.forward, inter_attn.py:73-123; variant 'graph' = common/myhand/model_attn/inter_attn_lijun.py:73-123 (lines 79-80, 90-91 differ)"""
     Lf = self_attn(Lf, sd, pre + '.L_self_attn_layer', p, tr)
     Rf = self_attn(Rf, sd, pre + '.R_self_attn_layer', p, tr)
     B, V, f = Lf.shape
-    L2, R2 = _ln(Lf, sd, pre + '.layer_norm1'), _ln(Rf, sd, pre + '.layer_norm2')
+    if variant == 'graph':
+        L2, R2 = _ln(Lf + Rf, sd, pre + '.layer_norm1'), _ln(Rf + Lf, sd, pre + '.layer_norm2')
+    else:
+        L2, R2 = _ln(Lf, sd, pre + '.layer_norm1'), _ln(Rf, sd, pre + '.layer_norm2')
     Lq, Lk, Lv = (_heads(_lin(L2, sd, pre + n), B, H) for n in ('.w_qs', '.w_ks', '.w_vs'))
     Rq, Rk, Rv = (_heads(_lin(R2, sd, pre + n), B, H) for n in ('.w_qs', '.w_ks', '.w_vs'))
     nrm = (f // H) ** 0.5
-    a_R2L = _drop(F.softmax(torch.matmul(Lq, Rk.transpose(-1, -2)) / nrm, -1), p, tr)
-    a_L2R = _drop(F.softmax(torch.matmul(Rq, Lk.transpose(-1, -2)) / nrm, -1), p, tr)
+    kL, kR = (Lk, Rk) if variant == 'graph' else (Rk, Lk)      # keys paired with Lq / Rq
+    a_R2L = _drop(F.softmax(torch.matmul(Lq, kL.transpose(-1, -2)) / nrm, -1), p, tr)
+    a_L2R = _drop(F.softmax(torch.matmul(Rq, kR.transpose(-1, -2)) / nrm, -1), p, tr)
     f_L2R = torch.matmul(a_L2R, Lv).transpose(1, 2).contiguous().view(B, V, -1)
     f_R2L = torch.matmul(a_R2L, Rv).transpose(1, 2).contiguous().view(B, V, -1)
     f_L2R = _drop(_lin(f_L2R, sd, pre + '.fc'), p, tr)
@@ -307,8 +342,8 @@ def prepare_assets(assets):
     return out
 
 
-def decoder_forward(sd, A, gf, fmaps, p, tr):
-    """decoder.forward, models/decoder.py:128-174"""
+def decoder_forward(sd, A, gf, fmaps, p, tr, variant='intaghand'):
+    """decoder.forward, models/decoder.py:128-174; variant 'graph' = common/myhand/decoder_lijun_graph.py:279-320"""
     fmaps = fmaps[:-1]
     B = gf.shape[0]
     dc = sd['decoder.dense_coor'][None].repeat(B, 1, 1) * 2 - 1
@@ -323,11 +358,11 @@ def decoder_forward(sd, A, gf, fmaps, p, tr):
         pre = 'decoder.dual_gcn.layers.%d' % i
         emb = sd[pre + '.position_embeddings.weight'][None]
         Lf, Rf = Lf + emb, Rf + emb
-        Lf = graph_layer(Lf, sd, pre + '.graph_left', A['left']['L'][i], p, tr)
-        Rf = graph_layer(Rf, sd, pre + '.graph_right', A['right']['L'][i], p, tr)
+        Lf = graph_layer(Lf, sd, pre + '.graph_left', A['left']['L'][i], p, tr, variant=variant)
+        Rf = graph_layer(Rf, sd, pre + '.graph_right', A['right']['L'][i], p, tr, variant=variant)
         Lf = img_ex(fmaps[i], Lf, sd, pre + '.img_ex_left', p, tr)
         Rf = img_ex(fmaps[i], Rf, sd, pre + '.img_ex_right', p, tr)
-        Lf, Rf = inter_attn(Lf, Rf, sd, pre + '.attn', p, tr)
+        Lf, Rf = inter_attn(Lf, Rf, sd, pre + '.attn', p, tr, variant=variant)
         if i != 2:
             Lf, Rf = graph_upsample(Lf, 2), graph_upsample(Rf, 2)
     scale, trans2d, v3, v2 = {}, {}, {}, {}
@@ -342,7 +377,7 @@ def decoder_forward(sd, A, gf, fmaps, p, tr):
         result['verts3d'][side] = up
         result['verts2d'][side] = projection_batch(scale[side], trans2d[side], up)
     other = {'verts3d_MANO_list': {'left': [], 'right': []}, 'verts2d_MANO_list': {'left': [], 'right': []}}
-    for side in ('left', 'right'):
+    for side in (('left', 'right') if variant != 'graph' else ()):
         pr, va = A[side]['perm_rev'], A[side]['vNum_all']
         other['verts3d_MANO_list'][side].append(graph_upsample(v3[side], va // v3[side].shape[1])[:, pr])
         other['verts2d_MANO_list'][side].append(graph_upsample(v2[side], va // v2[side].shape[1])[:, pr])
@@ -352,6 +387,10 @@ def decoder_forward(sd, A, gf, fmaps, p, tr):
 def model_forward(sd, assets_prepared, img, training=False, dropout=0.0):
     """HandNET_GCN.forward, models/model.py:25-37.  `sd` maps reference state_dict keys to tensors (BN running
     statistics are updated in place when training=True, exactly like nn.BatchNorm2d)."""
+    if 'encoder.resnet.conv1.weight' in sd and 'encoder.hms_decoder.final_layer.weight' not in sd:
+        # the common/myhand "graph" model (lijun_model_graph.py:27-34): trunk -> mid -> decoder, no auxiliary maps
+        gf, fmaps = graph_mid_forward(sd, resnet_trunk(sd, img, training), training)
+        return decoder_forward(sd, assets_prepared, gf, fmaps, dropout, training, variant='graph')
     if 'encoder.hrnet.conv1.weight' in sd:      # ENCODER_TYPE: hrnet* (models/encoder.py:365-372)
         hms, mask, dp, img_f, _, _ = hrnet_encoder_forward(sd, img, training)
         gf, fmaps = hrnet_mid_forward(sd, img_f, training)

@@ -198,3 +198,138 @@ def build_reference_mano(side='right', asset_dir=None, **kw):
     asset_dir = asset_dir or extract_assets()
     path = os.path.join(asset_dir, 'mano', 'MANO_%s.pkl' % side.upper())
     return ns.mano.ManoLayer(path, **kw)
+
+
+# ----------------------------------------------------------------------------- common/myhand variants
+MISSING_PACKAGES = ('manopth', 'mmcv', 'pytorch3d', 'imgaug', 'timm', 'tensorboardX', 'matplotlib', 'skimage', 'trimesh', 'fvcore', 'sdf',
+                    'tkinter', 'chumpy')
+
+
+def _install_missing_package_stubs():
+    """Third-party packages the reference imports at module level along the constructor path but never calls on the model's forward /
+    backward path (SURVEY 8c lists them as absent from this container): any `import pkg.sub` / `from pkg.sub import name` resolves to an
+    inert stand-in.  Packages that ARE installed are left alone."""
+    import importlib.abc
+    import importlib.machinery
+    import importlib.util
+
+    class _Dummy:
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, *a, **k):
+            return _Dummy()
+
+        def __getattr__(self, name):
+            if name.startswith('__'):
+                raise AttributeError(name)
+            return _Dummy()
+
+    class _StubModule(types.ModuleType):
+        __path__ = []
+
+        def __getattr__(self, name):
+            if name.startswith('__'):
+                raise AttributeError(name)
+            return type(name, (_Dummy,), {})
+
+    class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        _rih_stub_finder = True
+
+        def __init__(self, roots):
+            self.roots = roots
+
+        def find_spec(self, fullname, path=None, target=None):
+            if fullname.split('.')[0] in self.roots:
+                return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+            return None
+
+        def create_module(self, spec):
+            return _StubModule(spec.name)
+
+        def exec_module(self, module):
+            pass
+
+    if any(getattr(f, '_rih_stub_finder', False) for f in sys.meta_path):
+        return
+    roots = set()
+    for name in MISSING_PACKAGES:
+        if name in sys.modules:
+            continue
+        try:
+            found = importlib.util.find_spec(name) is not None
+        except Exception:
+            found = False
+        if not found:
+            roots.add(name)
+    sys.meta_path.append(_Finder(roots))
+
+
+def build_reference_myhand_model(asset_dir, variant='graph', dropout=0.05, mano_flag=False):
+    """`common/myhand/lijun_model_graph.load_graph_model` (variant 'graph', what apps/train.py and apps/eval_interhand.py build by
+    default: core/lijun_trainer.py:102-113) on the CPU.  The reference hard-codes `.cuda()` in its decoder constructor
+    (decoder_lijun_graph.py:228-232), imports `manopth` and creates output folders at import (main/config.py:132-135); those three
+    environment dependencies are shimmed IN MEMORY for the duration of the call (identity `.cuda()`, empty `manopth` module,
+    no-op folder creation) -- no reference file is modified or copied, the code that runs is the reference's own.
+    MANO pickles are read from `<asset_dir>/mano` through a temporary working directory (main/config.py:123 uses a relative path)."""
+    import contextlib
+    import torch
+    ns = import_reference()
+
+    @contextlib.contextmanager
+    def shims():
+        saved = (torch.Tensor.cuda, torch.nn.Module.cuda, os.makedirs, os.getcwd())
+        tmp = os.path.join(asset_dir, '_cwd')
+        os.makedirs(os.path.join(tmp, 'misc'), exist_ok=True)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        orig_to = torch.Tensor.to
+
+        def is_cuda_dev(d):
+            return (isinstance(d, str) and d.startswith('cuda')) or (isinstance(d, torch.device) and d.type == 'cuda')
+
+        def to_cpu(self, *a, **k):        # `.to('cuda')` of common/utils/mano.py:34 (Jr) and friends
+            a = tuple('cpu' if is_cuda_dev(x) else x for x in a)
+            if is_cuda_dev(k.get('device')):
+                k['device'] = 'cpu'
+            return orig_to(self, *a, **k)
+        torch.Tensor.to = to_cpu
+        os.makedirs = lambda *a, **k: None
+        _install_missing_package_stubs()
+        link = os.path.join(tmp, 'misc', 'mano')
+        if not os.path.exists(link):
+            os.symlink(os.path.join(asset_dir, 'mano'), link)
+        os.chdir(tmp)
+        try:
+            yield
+        finally:
+            torch.Tensor.cuda, torch.nn.Module.cuda, os.makedirs = saved[:3]
+            torch.Tensor.to = orig_to
+            os.chdir(saved[3])
+
+    with shims():
+        import main.config as main_config
+        main_config.cfg.mano_flag = mano_flag
+        for k, v in (('render', False), ('normal', True), ('edge', True), ('vert2d', True), ('dice', False), ('sdf', False)):
+            if not hasattr(main_config.cfg, k):
+                setattr(main_config.cfg, k, v)
+        # common/utils/mano_to_vertex.py pulls in the dead common/nets harness, which instantiates a manopth layer at import
+        # (common/nets/mano_head.py:8); it is only needed by the unused CLIFF bbox decoder (bbox_decoder.py:22) -> inert stand-in
+        if 'common.utils.mano_to_vertex' not in sys.modules:
+            m = types.ModuleType('common.utils.mano_to_vertex')
+            m.mano_convert = None
+            sys.modules['common.utils.mano_to_vertex'] = m
+        paths = {'left': os.path.join(asset_dir, 'graph_left.pkl'), 'right': os.path.join(asset_dir, 'graph_right.pkl')}
+        if variant == 'graph':
+            import common.myhand.lijun_model_graph as mod
+            import common.myhand.decoder_lijun_graph as dec
+        else:
+            raise ValueError(variant)
+        dec.get_graph_dict_path = lambda: paths
+        dec.get_dense_color_path = lambda: os.path.join(asset_dir, 'v_color.pkl')
+        dec.get_upsample_path = lambda: os.path.join(asset_dir, 'upsample.pkl')
+        cfg = mod.load_cfg()
+        cfg.TRAIN.dropout = dropout
+        cfg.MODEL_PARAM.MODEL_PRETRAIN_PATH = '__none__'
+        model = mod.load_graph_model(cfg)
+    return model, cfg

@@ -109,7 +109,7 @@ class ResNetSimple_decoder(nn.Module):
 class ResNetSimple(nn.Module):
     """models/encoder.py:67-126 (torchvision trunk used as a parameter container only)"""
 
-    def __init__(self, model_type='resnet50', fmapDim=(128, 128, 128, 128), handNum=2, heatmapDim=21):
+    def __init__(self, model_type='resnet50', fmapDim=(128, 128, 128, 128), handNum=2, heatmapDim=21, aux_heads=True):
         super().__init__()
         import torchvision.models as tvm
         assert model_type in ('resnet50', 'resnet101', 'resnet152'), 'bottleneck ResNets only'
@@ -118,8 +118,10 @@ class ResNetSimple(nn.Module):
         for m in self.resnet.modules():
             if isinstance(m, nn.Conv2d):
                 _cl(m)
-        self.hms_decoder = ResNetSimple_decoder(self.expansion, fmapDim, ('flat', 'up', 'up', 'up'), heatmapDim * handNum)
-        self.dp_decoder = ResNetSimple_decoder(self.expansion, fmapDim, ('flat', 'up', 'up', 'up'), handNum + 3 * handNum)
+        self.aux_heads = aux_heads      # False: common/myhand/encoder_lijun.py:62-104 (trunk only, returns the 4 feature maps)
+        if aux_heads:
+            self.hms_decoder = ResNetSimple_decoder(self.expansion, fmapDim, ('flat', 'up', 'up', 'up'), heatmapDim * handNum)
+            self.dp_decoder = ResNetSimple_decoder(self.expansion, fmapDim, ('flat', 'up', 'up', 'up'), handNum + 3 * handNum)
         self.handNum = handNum
 
     def _stem(self, x, N, H, needs_input_grad):
@@ -165,6 +167,8 @@ class ResNetSimple(nn.Module):
             feats.append((x, H))
         x4, x3, x2, x1 = feats
         img_fmaps = [x1, x2, x3, x4]
+        if not self.aux_heads:
+            return img_fmaps
         hms, hms_fmaps, Hh = self.hms_decoder(x1[0], N, x1[1])
         out, dp_fmaps, _ = self.dp_decoder(x1[0], N, x1[1])
         hms = ops.nhwc_to_nchw(hms, N, Hh, Hh)
@@ -274,14 +278,40 @@ class GCN_ResBlock(nn.Module):
         return ops.layernorm(x1, self.norm3.weight, self.norm3.bias, b=x2, relu=relu_out)
 
 
+class MLP_GraphBlock(nn.Module):
+    """`GCN_ResBlock` of the common/myhand default variant (common/myhand/model_attn/DualGraph_lijun.py:28-58): same parameter names,
+    but no Laplacian -- relu(norm1(x)) -> fc1 -> relu(norm2) -> fc2 -> dropout, + shortcut(x), norm3."""
+
+    def __init__(self, in_dim, out_dim, mid_dim, graph, graph_k, drop_out):
+        super().__init__()
+        self.in_dim = in_dim
+        self.norm1 = nn.LayerNorm(in_dim, eps=1e-6)
+        self.fc1 = nn.Linear(in_dim, mid_dim)
+        self.norm2 = nn.LayerNorm(out_dim, eps=1e-6)
+        self.fc2 = nn.Linear(mid_dim, out_dim)
+        self.shortcut = nn.Linear(in_dim, out_dim)
+        self.norm3 = nn.LayerNorm(out_dim, eps=1e-6)
+        self.p = drop_out
+
+    def forward(self, x, B, V, relu_out):
+        p = self.p if self.training else 0.0
+        x1 = ops.layernorm(x, self.norm1.weight, self.norm1.bias, relu=True)
+        x1 = ops.linear(x1, self.fc1.weight, self.fc1.bias)
+        x1 = ops.layernorm(x1, self.norm2.weight, self.norm2.bias, relu=True)
+        x1 = ops.linear(x1, self.fc2.weight, self.fc2.bias, p_drop=p)
+        x2 = ops.linear(x, self.shortcut.weight, self.shortcut.bias)
+        return ops.layernorm(x1, self.norm3.weight, self.norm3.bias, b=x2, relu=relu_out)
+
+
 class GraphLayer(nn.Module):
     """models/model_attn/gcn.py:113-138"""
 
-    def __init__(self, in_dim, out_dim, graph, graph_k, graph_layer_num, drop_out):
+    def __init__(self, in_dim, out_dim, graph, graph_k, graph_layer_num, drop_out, block_cls=None):
         super().__init__()
-        self.GCN_blocks = nn.ModuleList([GCN_ResBlock(in_dim, out_dim, out_dim, graph, graph_k, drop_out)])
+        block_cls = block_cls or GCN_ResBlock
+        self.GCN_blocks = nn.ModuleList([block_cls(in_dim, out_dim, out_dim, graph, graph_k, drop_out)])
         for _ in range(graph_layer_num - 1):
-            self.GCN_blocks.append(GCN_ResBlock(out_dim, out_dim, out_dim, graph, graph_k, drop_out))
+            self.GCN_blocks.append(block_cls(out_dim, out_dim, out_dim, graph, graph_k, drop_out))
 
     def forward(self, x, B, V):
         n = len(self.GCN_blocks)
@@ -404,8 +434,12 @@ class img_ex(nn.Module):
 class inter_attn(nn.Module):
     """models/model_attn/inter_attn.py:36-123 (w_qs/w_ks/w_vs/fc are shared between the two hands)"""
 
-    def __init__(self, f_dim, n_heads=4, dropout=0.1):
+    def __init__(self, f_dim, n_heads=4, dropout=0.1, variant='cross'):
         super().__init__()
+        # 'cross': models/model_attn/inter_attn.py (each hand queries the OTHER hand's keys);
+        # 'lijun': common/myhand/model_attn/inter_attn_lijun.py:79-91 (LayerNorm of Lf + Rf, own keys, the other hand's values)
+        assert variant in ('cross', 'lijun')
+        self.variant = variant
         self.L_self_attn_layer = SelfAttn(f_dim, n_heads=n_heads, hid_dim=f_dim, dropout=dropout)
         self.R_self_attn_layer = SelfAttn(f_dim, n_heads=n_heads, hid_dim=f_dim, dropout=dropout)
         d = f_dim // n_heads
@@ -423,8 +457,9 @@ class inter_attn(nn.Module):
     def forward(self, Lf, Rf, B, V):
         p = self.p if self.training else 0.0
         Lf, Rf = run_hands(Lf.device, lambda: self.L_self_attn_layer(Lf, B, V), lambda: self.R_self_attn_layer(Rf, B, V))
-        L2 = ops.layernorm(Lf, self.layer_norm1.weight, self.layer_norm1.bias)
-        R2 = ops.layernorm(Rf, self.layer_norm2.weight, self.layer_norm2.bias)
+        lij = self.variant == 'lijun'
+        L2 = ops.layernorm(Lf, self.layer_norm1.weight, self.layer_norm1.bias, b=Rf if lij else None)
+        R2 = ops.layernorm(Rf, self.layer_norm2.weight, self.layer_norm2.bias, b=Lf if lij else None)
         Lq = ops.linear(L2, self.w_qs.weight, self.w_qs.bias)
         Lk = ops.linear(L2, self.w_ks.weight, self.w_ks.bias)
         Lv = ops.linear(L2, self.w_vs.weight, self.w_vs.bias)
@@ -433,8 +468,8 @@ class inter_attn(nn.Module):
         Rv = ops.linear(R2, self.w_vs.weight, self.w_vs.bias)
         H = self.n_heads
         # reference order of the two dropout1 draws: attn_R2L then attn_L2R (inter_attn.py:101-102)
-        feat_R2L = ops.attention(Lq, Rk, Rv, B, H, V, V, p_drop=p)
-        feat_L2R = ops.attention(Rq, Lk, Lv, B, H, V, V, p_drop=p)
+        feat_R2L = ops.attention(Lq, Lk if lij else Rk, Rv, B, H, V, V, p_drop=p)
+        feat_L2R = ops.attention(Rq, Rk if lij else Lk, Lv, B, H, V, V, p_drop=p)
         xR = ops.linear(feat_L2R, self.fc.weight, self.fc.bias, res=Rf, p_drop=p)
         xL = ops.linear(feat_R2L, self.fc.weight, self.fc.bias, res=Lf, p_drop=p)
         return run_hands(xL.device, lambda: self.ffL(xL), lambda: self.ffR(xR))
@@ -444,16 +479,16 @@ class DualGraphLayer(nn.Module):
     """models/model_attn/DualGraph.py:21-91 (the position-embedding add is fused into the caller's entry kernel)"""
 
     def __init__(self, verts_in_dim, verts_out_dim, graph_L, graph_R, graph_k, graph_layer_num, img_size, img_f_dim,
-                 grid_size, grid_f_dim, n_heads, dropout):
+                 grid_size, grid_f_dim, n_heads, dropout, block_cls=None, attn_variant='cross'):
         super().__init__()
         self.verts_num = graph_L.V
         self.verts_in_dim = verts_in_dim
         self.position_embeddings = nn.Embedding(self.verts_num, verts_in_dim)
-        self.graph_left = GraphLayer(verts_in_dim, verts_out_dim, graph_L, graph_k, graph_layer_num, dropout)
-        self.graph_right = GraphLayer(verts_in_dim, verts_out_dim, graph_R, graph_k, graph_layer_num, dropout)
+        self.graph_left = GraphLayer(verts_in_dim, verts_out_dim, graph_L, graph_k, graph_layer_num, dropout, block_cls)
+        self.graph_right = GraphLayer(verts_in_dim, verts_out_dim, graph_R, graph_k, graph_layer_num, dropout, block_cls)
         self.img_ex_left = img_ex(img_size, img_f_dim, grid_size, grid_f_dim, verts_out_dim, n_heads, dropout)
         self.img_ex_right = img_ex(img_size, img_f_dim, grid_size, grid_f_dim, verts_out_dim, n_heads, dropout)
-        self.attn = inter_attn(verts_out_dim, n_heads=n_heads, dropout=dropout)
+        self.attn = inter_attn(verts_out_dim, n_heads=n_heads, dropout=dropout, variant=attn_variant)
 
     def forward(self, Lf, Rf, img_f, B):
         """Lf/Rf already carry `+ position_embeddings` (added by the entry / upsample kernels)."""
@@ -467,13 +502,13 @@ class DualGraph(nn.Module):
     """models/model_attn/DualGraph.py:94-139"""
 
     def __init__(self, verts_in_dim, verts_out_dim, graphs_L, graphs_R, graph_k, graph_layer_num, img_size, img_f_dim,
-                 grid_size, grid_f_dim, n_heads, dropout):
+                 grid_size, grid_f_dim, n_heads, dropout, block_cls=None, attn_variant='cross'):
         super().__init__()
         self.layers = nn.ModuleList()
         for i in range(len(verts_in_dim)):
             self.layers.append(DualGraphLayer(verts_in_dim[i], verts_out_dim[i], graphs_L[i], graphs_R[i], graph_k[i],
                                               graph_layer_num[i], img_size[i], img_f_dim[i], grid_size[i], grid_f_dim[i],
-                                              n_heads, dropout))
+                                              n_heads, dropout, block_cls, attn_variant))
 
     def forward(self, Lf, Rf, img_f_list, B):
         for i, layer in enumerate(self.layers):
@@ -512,8 +547,9 @@ class decoder(nn.Module):
 
     def __init__(self, global_feature_dim, f_in_Dim, f_out_Dim, gcn_in_dim, gcn_out_dim, graph_k, graph_layer_num,
                  left_graph_dict, right_graph_dict, vertex_num=778, dense_coor=None, num_attn_heads=4,
-                 upsample_weight=None, dropout=0.05):
+                 upsample_weight=None, dropout=0.05, block_cls=None, attn_variant='cross', mano_lists=True):
         super().__init__()
+        self.mano_lists = mano_lists     # False: common/myhand/decoder_lijun_graph.py:316-320 returns empty MANO lists
         f_in_Dim = list(f_in_Dim)[:-1]
         gd = {'left': left_graph_dict, 'right': right_graph_dict}
         graph_L = {}
@@ -533,7 +569,7 @@ class decoder(nn.Module):
         graphs = {s: [GraphCSR(L) for L in graph_L[s][:3]] for s in ('left', 'right')}
         self.dual_gcn = DualGraph(self.gcn_in_dim, self.gcn_out_dim, graphs['left'], graphs['right'],
                                   [graph_k] * 3, [graph_layer_num] * 3, [8, 16, 32], f_in_Dim, [8, 8, 8], list(f_out_Dim),
-                                  num_attn_heads, dropout)
+                                  num_attn_heads, dropout, block_cls, attn_variant)
         self.gf_layer_left = nn.Sequential(nn.Linear(self.gf_dim, self.gcn_in_dim[0] - 3),
                                            nn.LayerNorm(self.gcn_in_dim[0] - 3, eps=1e-6))
         self.gf_layer_right = nn.Sequential(nn.Linear(self.gf_dim, self.gcn_in_dim[0] - 3),
@@ -600,7 +636,7 @@ class decoder(nn.Module):
         handDictList = [{'verts3d': verts3d, 'verts2d': verts2d}]
         otherInfo = {'verts3d_MANO_list': {'left': [], 'right': []}, 'verts2d_MANO_list': {'left': [], 'right': []}}
         div = self.vNum_all // self.vNum_out
-        for side in ('left', 'right'):
+        for side in (('left', 'right') if self.mano_lists else ()):
             idx = self._rev_idx(side, x.device)
             otherInfo['verts3d_MANO_list'][side].append(ops.gather_rows(verts3d[side], idx, div))
             otherInfo['verts2d_MANO_list'][side].append(ops.gather_rows(verts2d[side], idx, div))

@@ -18,8 +18,9 @@ def rel_err(a, b):
     return float(((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).detach())
 
 
-# (golden file, MODEL.ENCODER_TYPE, first BatchNorm of the trunk): ResNet-50 (BASELINE configs 2-4) and HRNet-w48 (config 5)
-CASES = {'resnet50': ('model_synth_b2.pt', 'encoder.resnet.bn1'), 'hrnet48': ('model_hrnet48_synth_b2.pt', 'encoder.hrnet.bn1')}
+# (golden file, first BatchNorm of the trunk) per model: ResNet-50 (BASELINE configs 2-4), HRNet-w48 (config 5), myhand graph variant
+CASES = {'resnet50': ('model_synth_b2.pt', 'encoder.resnet.bn1'), 'hrnet48': ('model_hrnet48_synth_b2.pt', 'encoder.hrnet.bn1'),
+         'graph': ('model_graph_synth_b2.pt', 'encoder.resnet.bn1')}      # 'graph' = common/myhand default variant
 
 
 # hrnet_mid's biased convolutions that feed a BatchNorm (models/encoder.py:304-326)
@@ -39,8 +40,12 @@ def setup(gold):
     from renderih_b200.model import load_model
     a = rih_assets.synthetic_assets(0)
     cfg = load_cfg(None)
-    cfg.MODEL.ENCODER_TYPE = gold['encoder_type']
-    tmpl = load_model(cfg, assets=a).state_dict()
+    if gold['encoder_type'] == 'graph':
+        from renderih_b200.myhand import load_graph_model
+        tmpl = load_graph_model(cfg, assets=a, mano_assets={s_: rih_assets.synthetic_mano(0, s_) for s_ in ('left', 'right')}).state_dict()
+    else:
+        cfg.MODEL.ENCODER_TYPE = gold['encoder_type']
+        tmpl = load_model(cfg, assets=a).state_dict()
     sd = fixtures.init_state_dict(tmpl)
     assert fixtures.checksum(sd) == gold['weights_sha256'], 'deterministic weight init drifted from the golden run'
     return a, sd
@@ -53,8 +58,9 @@ def flat(out):
         d['verts3d_' + side] = result['verts3d'][side]; d['verts2d_' + side] = result['verts2d'][side]
         d['scale_' + side] = params['scale'][side]; d['trans2d_' + side] = params['trans2d'][side]
         d['v3c_' + side] = hlist[0]['verts3d'][side]; d['v2c_' + side] = hlist[0]['verts2d'][side]
-        d['v3list_' + side] = other['verts3d_MANO_list'][side][0]; d['v2list_' + side] = other['verts2d_MANO_list'][side][0]
-    for k in ('hms', 'mask', 'dense'):
+        if other['verts3d_MANO_list'][side]:
+            d['v3list_' + side] = other['verts3d_MANO_list'][side][0]; d['v2list_' + side] = other['verts2d_MANO_list'][side][0]
+    for k in (('hms', 'mask', 'dense') if 'hms' in other else ()):
         t = other[k] if other[k].dim() == 4 else other[k][:, None]      # HRnet_encoder's mask is [B,64,64] (models/encoder.py:235)
         d[k + '_sub'] = t[:, :, ::8, ::8]; d[k + '_mean'] = t.mean(dim=(2, 3))
     return d
@@ -74,7 +80,7 @@ def test_oracle_train_forward_backward_matches_reference_golden(gold, setup):
     a, sd = setup
     sd = {k: v.clone() for k, v in sd.items()}
     for k, v in sd.items():
-        if v.is_floating_point() and 'running_' not in k and k not in ('decoder.dense_coor', 'decoder.unsample_layer.weight'):
+        if v.is_floating_point() and 'running_' not in k and '.mano_' not in k and k not in ('decoder.dense_coor', 'decoder.unsample_layer.weight'):
             v.requires_grad_(True)
     out = model_ref.model_forward(sd, model_ref.prepare_assets(a), fixtures.make_image(gold['batch']), training=True, dropout=0.0)
     fo = flat(out)
