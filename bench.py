@@ -21,7 +21,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # FlopCounterMode on the reference (algorithmic 2*MAC FLOPs per image, forward+backward / forward)
-FLOPS = {'resnet50': (50.450e9, 17.721e9), 'hrnet48': (168.090e9, 56.201e9)}
+FLOPS = {'resnet50': (50.450e9, 17.721e9), 'hrnet48': (168.090e9, 56.201e9),
+         'graph': (38.422e9, 13.268e9)}     # common/myhand graph variant (ResNet-50 trunk), FlopCounterMode on the reference built on CPU
 FLOPS_PER_IMG_FWD_BWD, FLOPS_PER_IMG_FWD = FLOPS['resnet50']
 
 
@@ -32,8 +33,9 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=None, help='images per GPU (default 64; 32 for --encoder hrnet48 = BASELINE.json configs[4])')
-    ap.add_argument('--encoder', default='resnet50', choices=['resnet50', 'hrnet48'],
-                    help='MODEL.ENCODER_TYPE: resnet50 = BASELINE.json configs[2] (the headline metric), hrnet48 = configs[4]')
+    ap.add_argument('--encoder', default='resnet50', choices=['resnet50', 'hrnet48', 'graph'],
+                    help='resnet50 = BASELINE.json configs[2] (the headline metric), hrnet48 = configs[4] (MODEL.ENCODER_TYPE), '
+                         'graph = the common/myhand default model variant (SURVEY 8 f1; ResNet-50 trunk, batch 64)')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--gemm-mode', default='ref', choices=['ref', 'refrn', 'simt', 'tf32', 'tf32rn', 'tf32c', 'tf32x3'],
                     help="arithmetic of the conv / Linear GEMMs; 'ref' = the reference's own GPU numerics class: TF32 convolutions (as "
@@ -132,8 +134,12 @@ def cpu_port_step_time(batch, steps=1, warmup=0, budget_s=1e9, encoder='resnet50
     from renderih_b200.model import load_model
     a = A.synthetic_assets(0)
     cfg = load_cfg()
-    cfg.MODEL.ENCODER_TYPE = encoder
-    sd = fixtures.init_state_dict(load_model(cfg, assets=a).state_dict())
+    if encoder == 'graph':
+        from renderih_b200.myhand import load_graph_model
+        sd = fixtures.init_state_dict(load_graph_model(cfg, assets=a, mano_assets={s: A.synthetic_mano(0, s) for s in ('left', 'right')}).state_dict())
+    else:
+        cfg.MODEL.ENCODER_TYPE = encoder
+        sd = fixtures.init_state_dict(load_model(cfg, assets=a).state_dict())
     avail = host_cores()
     cands, c = [], avail
     while c >= 16 and len(cands) < 4:
@@ -154,7 +160,7 @@ def cpu_port_step_time(batch, steps=1, warmup=0, budget_s=1e9, encoder='resnet50
         cores = cands[0]
     torch.set_num_threads(cores)
     for k, v in sd.items():
-        if v.is_floating_point() and 'running_' not in k and k not in ('decoder.dense_coor', 'decoder.unsample_layer.weight'):
+        if v.is_floating_point() and 'running_' not in k and '.mano_' not in k and k not in ('decoder.dense_coor', 'decoder.unsample_layer.weight'):
             v.requires_grad_(True)
     Ap = model_ref.prepare_assets(a)
     la = fixtures.make_loss_assets(a, A.synthetic_mano(0, 'left'), A.synthetic_mano(0, 'right'))
@@ -248,11 +254,15 @@ def run_ours(args):
     conv_mode, lin_mode = {'ref': ('tf32c', 'tf32x3'), 'refrn': ('tf32rn', 'tf32x3')}.get(args.gemm_mode, (args.gemm_mode, args.gemm_mode))
     _ops.set_gemm_mode(conv_mode, lin_mode)
     cfg = load_cfg()
-    cfg.MODEL.ENCODER_TYPE = args.encoder
     flops_fb = FLOPS[args.encoder][0]
     a = A.synthetic_assets(0)
     torch.manual_seed(cfg.SEED)
-    model = load_model(cfg, assets=a).cuda().train()          # train mode: batch-stat BN, dropout 0.05 (reference defaults)
+    if args.encoder == 'graph':
+        from renderih_b200.myhand import load_graph_model
+        model = load_graph_model(cfg, assets=a, mano_assets={s: A.synthetic_mano(0, s) for s in ('left', 'right')}).cuda().train()
+    else:
+        cfg.MODEL.ENCODER_TYPE = args.encoder
+        model = load_model(cfg, assets=a).cuda().train()          # train mode: batch-stat BN, dropout 0.05 (reference defaults)
     model.decoder.unsample_layer.weight.requires_grad_(False)   # MODEL.freeze_upsample
     B = args.batch
     g = torch.Generator().manual_seed(cfg.SEED + rank)
@@ -328,7 +338,7 @@ def run_ours(args):
                       'ref': 'f32 storage; tcgen05 TF32 convolutions (truncating + mean-compensated: the accuracy class of the reference\'s cuDNN-TF32 default, measured) + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate', 'tf32rn': 'tf32 (rn) conv+Linear, fp32 accumulate/storage',
                       'tf32x3': '3xTF32 (fp32-faithful) conv+Linear, fp32 accumulate/storage'}[args.gemm_mode], 'data': 'synthetic',
             'config': {'workload': 'BASELINE.json configs[%d]: HandNET_GCN %s cfg, batch %d/GPU, 256x256, train mode (batch-stat BN, dropout 0.05), '
-                                   'random-init weights, synthetic graph/MANO assets' % (4 if args.encoder == 'hrnet48' else 2, args.encoder, B),
+                                   'random-init weights, synthetic graph/MANO assets' % (4 if args.encoder == 'hrnet48' else 2, {'graph': 'common/myhand graph variant (ResNet50 trunk)'}.get(args.encoder, args.encoder), B),
                        'global_batch': total_imgs, 'parallelism': 'dp%d' % world, 'cuda_graph': not args.no_graph,
                        'l2': 'per-step working set (activations, several GB) >> 126 MB L2; no explicit flush needed',
                        'algorithmic_gflop_per_image': flops_fb / 1e9},

@@ -4,6 +4,7 @@
 // reference: SelfAttn.self_attn  models/model_attn/self_attn.py:63-76 ; inter_attn.inter_attn  inter_attn.py:73-123
 // Tensor addressing: element (b, row, h, dd) of T is  T + b*T_bs + row*ldT + h*d + dd.
 #include "common.cuh"
+#include "bgemm.cuh"
 using namespace rih;
 
 constexpr int ATT_WARPS = 8;
@@ -428,4 +429,135 @@ RIH_API int rih_attn_set_row_blocks(int rows_fwd, int rows_bwd) {
   RIH_REQUIRE((rows_fwd == 0 || rows_fwd == 4 || rows_fwd == 8) && (rows_bwd == 0 || rows_bwd == 2 || rows_bwd == 4), "attn_set_row_blocks: fwd in {0,4,8}, bwd in {0,2,4}");
   g_att_force_rf = rows_fwd; g_att_force_rb = rows_bwd;
   return 0;
+}
+
+// ================================================================================================ tensor-core attention core
+// The same operator with its four contractions on the tcgen05 tensor cores (TMA -> shared memory -> tcgen05.mma, 3xTF32 or TF32), as
+// batched per-head GEMMs over 4-D tensor maps (gemm_tc.cu: bgemm_tf32) around two warp-per-row softmax kernels:
+//   forward : S = scale * Q K^T  ->  P = softmax(S), P~ = dropout(P)  ->  O = P~ V
+//   backward: dP~ = dO V^T  ->  dS = P o (dP~ o M - rowsum(dP~ o M o P)), P~ = P o M  ->  dQ = scale dS K, dK = scale dS^T Q, dV = P~^T dO
+// The score matrices [B*H, Sq, Skp] (Skp = Sk rounded up to 4 floats so that rows are 16-byte aligned for TMA) live in HBM / L2
+// between the launches, like the reference's attn tensor (self_attn.py:69-72); P is kept for the backward pass.
+constexpr int SM_MAXT = 16;   // keys per lane (Sk <= 512)
+
+__global__ void __launch_bounds__(256)
+attn_softmax_fwd_kernel(float* __restrict__ P, float* __restrict__ Pd, long long rows, int Sq, int Sk, int Skp,
+                        const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
+  float* p = P + row * Skp;
+  float x[SM_MAXT];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < SM_MAXT; ++t) {
+    const int j = lane + 32 * t;
+    x[t] = (j < Sk) ? p[j] : -INFINITY;
+    mx = fmaxf(mx, x[t]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < SM_MAXT; ++t) {
+    const int j = lane + 32 * t;
+    x[t] = (j < Sk) ? expf(x[t] - mx) : 0.f;
+    sum += x[t];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  const size_t drop_base = (size_t)row * Sk;
+#pragma unroll
+  for (int t = 0; t < SM_MAXT; ++t) {
+    const int j = lane + 32 * t;
+    if (j < Sk) {
+      const float pr = x[t] * inv;
+      p[j] = pr;
+      if (thresh) Pd[row * Skp + j] = pr * dropout_scale(seed, drop_base + j, thresh, inv_keep);
+    }
+  }
+}
+
+// dS (in place over dP) and, with dropout, P~ = P o M (the operand of dV = P~^T dO)
+__global__ void __launch_bounds__(256)
+attn_softmax_bwd_kernel(const float* __restrict__ P, float* __restrict__ dP, float* __restrict__ Pd, long long rows, int Sq, int Sk, int Skp,
+                        const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
+  const float* p = P + row * Skp;
+  float* g = dP + row * Skp;
+  const size_t drop_base = (size_t)row * Sk;
+  float pr[SM_MAXT], gm[SM_MAXT];
+  float dl = 0.f;
+#pragma unroll
+  for (int t = 0; t < SM_MAXT; ++t) {
+    const int j = lane + 32 * t;
+    pr[t] = 0.f; gm[t] = 0.f;
+    if (j < Sk) {
+      pr[t] = p[j];
+      const float m = thresh ? dropout_scale(seed, drop_base + j, thresh, inv_keep) : 1.f;
+      gm[t] = g[j] * m;
+      if (thresh) Pd[row * Skp + j] = pr[t] * m;
+      dl = fmaf(gm[t], pr[t], dl);
+    }
+  }
+  dl = warp_sum(dl);
+#pragma unroll
+  for (int t = 0; t < SM_MAXT; ++t) {
+    const int j = lane + 32 * t;
+    if (j < Sk) g[j] = pr[t] * (gm[t] - dl);
+  }
+}
+
+static inline tc::BOperand tok(const float* p, int S, int d, int ld) { return tc::BOperand{p, 1, S, d, ld}; }
+static inline tc::BOperand scr(const float* p, int R, int C, int Cp) { return tc::BOperand{p, 0, R, C, Cp}; }
+static int attn_tc_check(const char* who, int Sq, int Sk, int d, int ldp) {
+  RIH_REQUIRE(Sk > 0 && Sk <= 32 * SM_MAXT, "%s: Sk=%d unsupported (max %d)", who, Sk, 32 * SM_MAXT);
+  RIH_REQUIRE(d >= 4 && d % 4 == 0, "%s: head dim %d must be a multiple of 4", who, d);
+  RIH_REQUIRE(ldp >= Sk && ldp % 4 == 0, "%s: score row stride %d must be >= Sk and a multiple of 4 floats", who, ldp);
+  return 0;
+}
+
+// Forward on the tensor cores.  q/k/v/o: token matrices [B*S, ld] (head h = columns [h*d, (h+1)*d)); P: [B*H, Sq, ldp] receives the
+// softmax probabilities (kept for backward); Pd: same shape, dropped / rescaled probabilities (only touched when dropout_p > 0).
+// nsplit: 1 = TF32, 3 = 3xTF32 (fp32-faithful).  reference: SelfAttn.self_attn models/model_attn/self_attn.py:63-76, inter_attn.py:90-105
+RIH_API int rih_attn_tc_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo, float* P, float* Pd, int ldp,
+                            int B, int H, int Sq, int Sk, int d, float scale, float dropout_p, const unsigned long long* seed_ptr, unsigned long long site,
+                            int nsplit, cudaStream_t s) {
+  if (int e = attn_tc_check("attn_tc_fwd", Sq, Sk, d, ldp)) return e;
+  RIH_REQUIRE(nsplit == 1 || nsplit == 3, "attn_tc_fwd: nsplit must be 1 (TF32) or 3 (3xTF32)");
+  if (B * H == 0 || Sq == 0) return 0;
+  tc::set_nsplit(nsplit); tc::set_acc_scale(1.f);
+  if (int e = tc::bgemm_tf32(tok(q, Sq, d, ldq), 0, tok(k, Sk, d, ldk), 0, scr(P, Sq, Sk, ldp), B, H, Sq, Sk, d, scale, s)) return e;
+  const uint32_t thresh = dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u;
+  const float ik = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  RIH_REQUIRE(!thresh || (Pd && seed_ptr), "attn_tc_fwd: dropout needs the Pd buffer and a device seed");
+  const long long rows = (long long)B * H * Sq;
+  attn_softmax_fwd_kernel<<<cdiv(rows, 8), 256, 0, s>>>(P, Pd, rows, Sq, Sk, ldp, seed_ptr, site, thresh, ik);
+  if (int e = check_launch("attn_softmax_fwd")) return e;
+  return tc::bgemm_tf32(scr(thresh ? Pd : P, Sq, Sk, ldp), 0, tok(v, Sk, d, ldv), 1, tok(o, Sq, d, ldo), B, H, Sq, d, Sk, 1.f, s);
+}
+
+// Backward on the tensor cores.  ws: [B*H, Sq, ldp] scratch (dP~ then dS); Pd: scratch for P~ (dropout only).
+RIH_API int rih_attn_tc_bwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* dout, int lddo, const float* P,
+                            float* ws, float* Pd, int ldp, float* dq, int lddq, float* dk, int lddk, float* dv, int lddv,
+                            int B, int H, int Sq, int Sk, int d, float scale, float dropout_p, const unsigned long long* seed_ptr, unsigned long long site,
+                            int nsplit, cudaStream_t s) {
+  if (int e = attn_tc_check("attn_tc_bwd", Sq, Sk, d, ldp)) return e;
+  RIH_REQUIRE(nsplit == 1 || nsplit == 3, "attn_tc_bwd: nsplit must be 1 (TF32) or 3 (3xTF32)");
+  if (B * H == 0 || Sq == 0) return 0;
+  tc::set_nsplit(nsplit); tc::set_acc_scale(1.f);
+  if (int e = tc::bgemm_tf32(tok(dout, Sq, d, lddo), 0, tok(v, Sk, d, ldv), 0, scr(ws, Sq, Sk, ldp), B, H, Sq, Sk, d, 1.f, s)) return e;
+  const uint32_t thresh = dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u;
+  const float ik = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  RIH_REQUIRE(!thresh || (Pd && seed_ptr), "attn_tc_bwd: dropout needs the Pd buffer and a device seed");
+  const long long rows = (long long)B * H * Sq;
+  attn_softmax_bwd_kernel<<<cdiv(rows, 8), 256, 0, s>>>(P, ws, Pd, rows, Sq, Sk, ldp, seed_ptr, site, thresh, ik);
+  if (int e = check_launch("attn_softmax_bwd")) return e;
+  const float* Pt = thresh ? Pd : P;
+  if (int e = tc::bgemm_tf32(scr(ws, Sq, Sk, ldp), 0, tok(k, Sk, d, ldk), 1, tok(dq, Sq, d, lddq), B, H, Sq, d, Sk, scale, s)) return e;     // dQ = scale dS K
+  if (int e = tc::bgemm_tf32(scr(ws, Sq, Sk, ldp), 1, tok(q, Sq, d, ldq), 1, tok(dk, Sk, d, lddk), B, H, Sk, d, Sq, scale, s)) return e;     // dK = scale dS^T Q
+  return tc::bgemm_tf32(scr(Pt, Sq, Sk, ldp), 1, tok(dout, Sq, d, lddo), 1, tok(dv, Sk, d, lddv), B, H, Sk, d, Sq, 1.f, s);                 // dV = P~^T dO
 }

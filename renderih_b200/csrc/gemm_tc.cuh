@@ -76,6 +76,10 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const 
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
@@ -148,7 +152,7 @@ template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() {
 template <int BN, bool A_MN, bool B_MN>
 struct DenseProducer {
   int kbeg;
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
     const int k0 = kb * BK;
     if constexpr (!A_MN) tma_load_2d(sa, ta, k0, m0, bar);
     else {
@@ -159,6 +163,35 @@ struct DenseProducer {
     else {
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, n0 + c * 32, k0, bar);
+    }
+  }
+};
+
+// Batched (per attention head) GEMM operands as 4-D tensors, tile batch index z = b * H + h:
+//   token matrix  T[B*S, ld], head slice of width d : dims {d, H, S, B}    -> coordinates (col, z % H, row, z / H)
+//   score matrix  P[B*H, R, C] (row stride padded)   : dims {C, R, B*H, 1}  -> coordinates (col, row, z, 0)
+// Rows / columns of a 128 x BN tile that stick out of ONE head's matrix are zero-filled by the TMA unit (they never alias the next
+// head, because head and batch are separate tensor dimensions), so Sq = 63 ... 316 and d = 16 need no padding copies.
+template <int BN, bool A_MN, bool B_MN>
+struct BatchedProducer {
+  int H;          // heads per batch image
+  int a_tok, b_tok;   // operand is a token matrix (1) or a score matrix (0)
+  // token matrix map dims {d, H, S, B} (strides ascending), score matrix map dims {C, R, B*H, 1}
+  __device__ __forceinline__ void ld4(void* dst, const CUtensorMap* m, int tok, int col, int row, int z, uint64_t* bar) const {
+    if (tok) tma_load_4d(dst, m, col, z % H, row, z / H, bar);
+    else tma_load_4d(dst, m, col, row, z, 0, bar);
+  }
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+    const int k0 = kb * BK;
+    if constexpr (!A_MN) ld4(sa, ta, a_tok, k0, m0, z, bar);
+    else {
+#pragma unroll
+      for (int c = 0; c < BM / 32; ++c) ld4(sa + c * (BK * 128), ta, a_tok, m0 + c * 32, k0, z, bar);
+    }
+    if constexpr (!B_MN) ld4(sb, tb, b_tok, k0, n0, z, bar);
+    else {
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) ld4(sb + c * (BK * 128), tb, b_tok, n0 + c * 32, k0, z, bar);
     }
   }
 };
@@ -181,7 +214,7 @@ __device__ __forceinline__ void s2_tap(int r, int pad, int& parity, int& shift) 
 template <int BN>
 struct ConvFwdProducer {
   ConvTcGeom g;
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
     // channel blocks per tap; when Cin % 32 != 0 the last block of a tap is partly out of bounds in the activation map (TMA zero
     // fill), which also cancels whatever the weight box picks up from the next tap's columns
     const int cpb = (g.Cin + BK - 1) / BK;
@@ -204,7 +237,7 @@ struct ConvFwdProducer {
 template <int BN>
 struct ConvDgradProducer {
   ConvTcGeom g;
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
     const int cpb = (g.Cout + BK - 1) / BK;
     const int tap = kb / cpb, co0 = (kb - tap * cpb) * BK;
     const int r = tap / g.S, s = tap - r * g.S;
@@ -219,7 +252,7 @@ struct ConvDgradProducer {
 template <int BN>
 struct ConvWgradProducer {
   ConvTcGeom g;
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
     const int p0 = kb * BK;
     const int P = g.Ho * g.Wo;
     const int n = p0 / P, rem = p0 - n * P;
@@ -291,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], AB_BYTES);
         uint8_t* sa = smem + s * STAGE_BYTES;
-        prod.load(&tmap_a, &tmap_b, kb_beg + kb, m0, n0, sa, sa + A_BYTES, &full[s]);
+        prod.load(&tmap_a, &tmap_b, kb_beg + kb, m0, n0, 0, sa, sa + A_BYTES, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -465,29 +498,31 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto tile_coords = [&](int t, int& m0, int& n0, int& kb_beg, int& nkb) {
+  // third tile coordinate z: split-K slice (kb_beg = z * kb_per_split), or -- batched GEMM (ep.batch_heads != 0) -- the batch index
+  const bool batched = ep.batch_heads != 0;
+  auto tile_coords = [&](int t, int& m0, int& n0, int& kb_beg, int& nkb, int& z) {
     const int ni = t % tiles_n;
     const int r = t / tiles_n;
     const int mi = r % tiles_m;
-    const int z = r / tiles_m;
+    z = r / tiles_m;
     m0 = mi * BM; n0 = ni * BN;
-    kb_beg = z * kb_per_split;
-    nkb = min(num_kb_total - kb_beg, kb_per_split);
+    kb_beg = batched ? 0 : z * kb_per_split;
+    nkb = batched ? num_kb_total : min(num_kb_total - kb_beg, kb_per_split);
   };
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int m0, n0, kb_beg, nkb;
-        tile_coords(t, m0, n0, kb_beg, nkb);
+        int m0, n0, kb_beg, nkb, z;
+        tile_coords(t, m0, n0, kb_beg, nkb, z);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], AB_BYTES);
           uint8_t* sa = smem + s * STAGE_BYTES;
-          prod.load(&tmap_a, &tmap_b, kb_beg + kb, m0, n0, sa, sa + A_BYTES, &full[s]);
+          prod.load(&tmap_a, &tmap_b, kb_beg + kb, m0, n0, z, sa, sa + A_BYTES, &full[s]);
         }
       }
     }
@@ -495,8 +530,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     if (lane == 0) {
       uint32_t it = 0, tc = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
-        int m0, n0, kb_beg, nkb;
-        tile_coords(t, m0, n0, kb_beg, nkb);
+        int m0, n0, kb_beg, nkb, z;
+        tile_coords(t, m0, n0, kb_beg, nkb, z);
         const uint32_t acc = tc & 1, aph = (tc >> 1) & 1;
         mbar_wait(&tmem_empty[acc], aph ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
@@ -529,8 +564,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     const int tsp = threadIdx.x - 64;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int m0, n0, kb_beg, nkb;
-      tile_coords(t, m0, n0, kb_beg, nkb);
+      int m0, n0, kb_beg, nkb, z;
+      tile_coords(t, m0, n0, kb_beg, nkb, z);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -560,8 +595,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     const unsigned long long dseed = ep.thresh ? (*ep.seed_ptr + ep.site * 0xD1B54A32D192ED03ull) : 0ull;
     uint32_t tc = 0, cc = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
-      int m0, n0, kb_beg, nkb;
-      tile_coords(t, m0, n0, kb_beg, nkb);
+      int m0, n0, kb_beg, nkb, z;
+      tile_coords(t, m0, n0, kb_beg, nkb, z);
       const uint32_t acc = tc & 1, aph = (tc >> 1) & 1;
       mbar_wait(&tmem_full[acc], aph);
       tc_fence_after();
@@ -580,6 +615,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           sc1 = nb / ep.nv_pad; sc0 = nb - sc1 * ep.nv_pad;
           if (sc0 >= ep.nv_real) continue;
         }
+        if (batched && nb >= ep.N) continue;   // e.g. head dim 16 in a 64-wide tile: nothing to store
         if (tma_epi) {
           if (ep.scale != 1.f) {
 #pragma unroll
@@ -608,7 +644,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           fence_proxy_async();
           epi_bar_sync();
           if (elected) {
-            if (ep.nv_pad) {
+            if (batched) {
+              const int hh = ep.batch_heads & 0x3FFFFFFF;
+              if (ep.batch_heads & (1 << 30)) tma_store_4d(&tmap_c, buf, nb, m0, z, 0);     // score matrix [B*H][M][N]
+              else tma_store_4d(&tmap_c, buf, nb, z % hh, m0, z / hh);                        // head slice of a token matrix
+            } else if (ep.nv_pad) {
               if (ep.mode == 0) tma_store_3d(&tmap_c, buf, sc0, sc1, m0);
               else tma_reduce_add_3d(&tmap_c, buf, sc0, sc1, m0);
             } else if (ep.mode == 0) tma_store_2d(&tmap_c, buf, nb, m0);

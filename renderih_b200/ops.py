@@ -15,6 +15,8 @@ call = _lib.call
 
 
 GEMM_MODES = {'simt': 0, 'tf32': 1, 'tf32x3': 2, 'tf32rn': 3, 'tf32c': 4}
+import os as _os
+_ATTN = {'nsplit': 0, 'force': _os.environ.get('RIH_ATTN_IMPL') or None}     # RIH_ATTN_IMPL=simt|tc overrides the mode-derived choice (A/B runs)
 
 
 def set_gemm_mode(conv='simt', linear='simt'):
@@ -24,6 +26,9 @@ def set_gemm_mode(conv='simt', linear='simt'):
     'tf32rn' = TF32 with the operands rounded to nearest in shared memory before the MMA (unbiased; the cuDNN convention),
     'tf32x3' = the same tensor-core kernels with an in-kernel hi/lo operand split and 3 MMAs per step (fp32-faithful)."""
     call('rih_set_gemm_mode', GEMM_MODES[conv], GEMM_MODES[linear])
+    # the attention contractions follow the nn.Linear arithmetic (the reference runs both as fp32 torch.matmul / addmm):
+    # 0 = fused SIMT kernel (exact fp32), 1 = tcgen05 TF32, 3 = tcgen05 3xTF32
+    _ATTN['nsplit'] = {'simt': 0, 'tf32x3': 3}.get(linear, 1)
 
 
 def _stream():
@@ -318,8 +323,58 @@ class AttnFn(Function):
         return dq, dk, dv, None, None, None, None, None, None
 
 
-def attention(q, k, v, B, H, Sq, Sk, p_drop=0.0):
+class AttnTcFn(Function):
+    """The same attention core with QK^T / PV (and the three backward contractions) on the tcgen05 tensor cores as batched per-head
+    GEMMs (rih_attn_tc_fwd / rih_attn_tc_bwd); the softmax probabilities [B*H, Sq, Sk] are kept for the backward pass."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, B, H, Sq, Sk, p_drop, site, nsplit):
+        q, k, v = _rows(q), _rows(k), _rows(v)
+        HD = q.shape[1]
+        d = HD // H
+        assert q.shape[0] == B * Sq and k.shape[0] == B * Sk and v.shape[0] == B * Sk
+        ldp = (Sk + 3) // 4 * 4
+        o = torch.empty((B * Sq, HD), device=q.device, dtype=torch.float32)
+        P = torch.empty((B * H, Sq, ldp), device=q.device, dtype=torch.float32)
+        Pd = torch.empty_like(P) if p_drop > 0 else None
+        scale = 1.0 / (d ** 0.5)
+        sp = seed_state.ptr(q.device) if p_drop > 0 else None
+        call('rih_attn_tc_fwd', _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(o), HD, _p(P), _p(Pd), ldp,
+             B, H, Sq, Sk, d, scale, float(p_drop), sp, site, nsplit, _stream())
+        ctx.save_for_backward(q, k, v, P)
+        ctx.meta = (B, H, Sq, Sk, d, scale, p_drop, site, nsplit, ldp)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, P = ctx.saved_tensors
+        B, H, Sq, Sk, d, scale, p_drop, site, nsplit, ldp = ctx.meta
+        do = _rows(do.contiguous() if do.stride(-1) != 1 else do)
+        HD = H * d
+        dq = torch.empty((B * Sq, HD), device=do.device, dtype=torch.float32)
+        dk = torch.empty((B * Sk, HD), device=do.device, dtype=torch.float32)
+        dv = torch.empty((B * Sk, HD), device=do.device, dtype=torch.float32)
+        ws = torch.empty_like(P)
+        Pd = torch.empty_like(P) if p_drop > 0 else None
+        sp = seed_state.ptr(do.device) if p_drop > 0 else None
+        call('rih_attn_tc_bwd', _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(do), _ld(do), _p(P), _p(ws), _p(Pd), ldp,
+             _p(dq), HD, _p(dk), HD, _p(dv), HD, B, H, Sq, Sk, d, scale, float(p_drop), sp, site, nsplit, _stream())
+        return dq, dk, dv, None, None, None, None, None, None, None
+
+
+def attention(q, k, v, B, H, Sq, Sk, p_drop=0.0, impl=None):
+    """impl: None = follow set_gemm_mode (SIMT fused kernel in 'simt' mode, tensor-core batched GEMMs otherwise), 'simt' | 'tc' to force."""
     site = seed_state.next_site() if p_drop > 0 else 0
+    nsplit = _ATTN['nsplit']
+    impl = impl or _ATTN.get('force')
+    if impl == 'simt':
+        nsplit = 0
+    elif impl == 'tc' and nsplit == 0:
+        nsplit = 3
+    d = q.shape[1] // H
+    aligned = all(t.data_ptr() % 16 == 0 and _ld(t) % 4 == 0 for t in (q, k, v)) and d % 4 == 0
+    if nsplit and aligned and B * H > 0 and Sq > 0 and Sk <= 512:
+        return AttnTcFn.apply(q, k, v, B, H, Sq, Sk, p_drop, site, nsplit)
     return AttnFn.apply(q, k, v, B, H, Sq, Sk, p_drop, site)
 
 

@@ -201,6 +201,60 @@ def test_attention(ops, B, H, Sq, Sk, d):
         check(u, r, 1e-4, 'attn d' + n)
 
 
+@pytest.mark.parametrize('B,H,Sq,Sk,d', [(3, 4, 63, 63, 64), (2, 4, 252, 316, 16), (2, 4, 126, 190, 32), (2, 4, 64, 64, 16), (5, 4, 63, 127, 64),
+                                          (1, 2, 5, 7, 8), (2, 3, 130, 70, 32)])
+@pytest.mark.parametrize('nsplit_mode', ['tf32x3', 'tf32'])
+def test_attention_tensor_core(ops, B, H, Sq, Sk, d, nsplit_mode):
+    """tcgen05 attention core (batched per-head GEMMs over 4-D TMA maps + warp-per-row softmax), forward and backward, against plain
+    torch fp32.  Stated tolerance: 3xTF32 5e-5 relative to each tensor's max (fp32-faithful), single-pass TF32 5e-3."""
+    tol = 5e-5 if nsplit_mode == 'tf32x3' else 5e-3
+    q, k, v = T(B * Sq, H * d, seed=1), T(B * Sk, H * d, seed=2), T(B * Sk, H * d, seed=3)
+    ops.set_gemm_mode('simt', nsplit_mode)
+    try:
+        o = ops.attention(q, k, v, B, H, Sq, Sk, impl='tc')
+        g_ours = grads(o, [q, k, v])
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+    qh, kh, vh = (t.view(B, -1, H, d).transpose(1, 2) for t in (q, k, v))
+    ref = torch.matmul(F.softmax(torch.matmul(qh, kh.transpose(-1, -2)) / d ** 0.5, -1), vh).transpose(1, 2).reshape(B * Sq, H * d)
+    check(o, ref, tol, 'attn tc fwd')
+    for a, r, n in zip(g_ours, grads(ref, [q, k, v]), 'qkv'):
+        check(a, r, tol, 'attn tc d' + n)
+
+
+def test_attention_tensor_core_dropout_matches_simt_statistics(ops):
+    """Dropout on the tensor-core path: forward / backward stay consistent (same regenerated mask), the kept fraction is 1 - p and the
+    expectation is preserved; with p = 0 the result equals the SIMT kernel's to fp32 round-off."""
+    B, H, S, d = 4, 4, 126, 32
+    q, k, v = T(B * S, H * d, seed=4), T(B * S, H * d, seed=5), T(B * S, H * d, seed=6)
+    ops.seed_state.manual_seed(1234, q.device)
+    ops.seed_state.begin_forward()
+    ops.set_gemm_mode('simt', 'tf32x3')
+    try:
+        o0 = ops.attention(q, k, v, B, H, S, S, p_drop=0.0, impl='tc')
+        o1 = ops.attention(q, k, v, B, H, S, S, p_drop=0.3, impl='tc')
+        gq, gk, gv = grads(o1, [q, k, v])
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+    os_ = ops.attention(q, k, v, B, H, S, S, p_drop=0.0, impl='simt')
+    check(o0, os_, 5e-5, 'tc vs simt (no dropout)')
+    assert torch.isfinite(o1).all() and torch.isfinite(gq).all() and torch.isfinite(gk).all() and torch.isfinite(gv).all()
+    assert rel(o1.mean(0), o0.mean(0)) < 0.5            # same expectation (loose: one draw)
+    # finite-difference check of the dropout path through V (linear in V, so exact up to round-off): <dO, dV-direction>
+    dvdir = torch.randn_like(v)
+    ops.seed_state.begin_forward()
+    ops.set_gemm_mode('simt', 'tf32x3')
+    try:
+        _ = ops.attention(q, k, v, B, H, S, S, p_drop=0.0, impl='tc')           # consume site 0 like above
+        o2 = ops.attention(q, k, (v + dvdir).detach(), B, H, S, S, p_drop=0.3, impl='tc')
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+    w = torch.randn(o1.shape, generator=torch.Generator(device='cpu').manual_seed(0)).to(o1.device)     # the cotangent grads() used
+    lhs = float(((o2 - o1) * w).sum())
+    rhs = float((gv * dvdir).sum())
+    assert abs(lhs - rhs) / (abs(rhs) + 1e-6) < 1e-3, (lhs, rhs)
+
+
 def test_attention_strided_qkv(ops):
     B, H, S, d = 2, 4, 63, 16
     qkv = T(B * S, 3 * H * d)

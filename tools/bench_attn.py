@@ -19,14 +19,17 @@ def main():
     ap.add_argument('--rows-bwd', type=int, default=0)
     ap.add_argument('--dropout', type=float, default=0.05)
     ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--impl', default='simt', choices=['simt', 'tc'])
+    ap.add_argument('--linear-mode', default='tf32x3')
     args = ap.parse_args()
     from renderih_b200 import ops
     from renderih_b200._lib import call
     call('rih_attn_set_row_blocks', args.rows_fwd, args.rows_bwd)
+    ops.set_gemm_mode('simt', args.linear_mode)
     B, H = args.batch, 4
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     tot_f = tot_b = 0.0
-    print('rows_fwd=%d rows_bwd=%d dropout=%.2f' % (args.rows_fwd, args.rows_bwd, args.dropout))
+    print('impl=%s mode=%s rows_fwd=%d rows_bwd=%d dropout=%.2f' % (args.impl, args.linear_mode, args.rows_fwd, args.rows_bwd, args.dropout))
     for Sq, Sk, d, calls in SHAPES:
         q = torch.randn(B * Sq, H * d, device='cuda', requires_grad=True)
         k = torch.randn(B * Sk, H * d, device='cuda', requires_grad=True)
@@ -38,7 +41,7 @@ def main():
             flush.zero_()
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-            o = ops.attention(q, k, v, B, H, Sq, Sk, p_drop=args.dropout)
+            o = ops.attention(q, k, v, B, H, Sq, Sk, p_drop=args.dropout, impl=args.impl)
             e1.record()
             o.backward(go)
             e2.record()
