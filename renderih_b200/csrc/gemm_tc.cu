@@ -154,7 +154,7 @@ static void plan_splitk(Epilogue& ep, int M, int N, int BN, int num_kb, int allo
   splits = 1;
   if (allow && tiles < 148 && num_kb >= 32) {
     splits = (int)((296 + tiles - 1) / tiles);
-    int maxs = num_kb / 16;
+    int maxs = num_kb / 4;      // >= 4 k-blocks (128 reduction rows) per slice: these GEMMs are latency bound, so many short slices win
     if (splits > maxs) splits = maxs;
     if (splits > 128) splits = 128;
     if (splits < 1) splits = 1;

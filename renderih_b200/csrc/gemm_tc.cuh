@@ -453,9 +453,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // tiles, the accumulator is double-buffered in TMEM (2 x BN columns) and the epilogue has its own four warps, so the
 // TMA stores of tile i overlap the loads / MMAs of tile i+1 and the per-CTA prologue (TMEM allocation, barrier init,
 // descriptor fetch) is paid once per SM instead of once per tile.
-//   warp 0 = TMA producer | warp 1 = MMA issuer + TMEM owner | warps 2..5 = hi/lo splitter (NSPLIT == 3 only) |
+//   warp 0 = TMA producer | warp 1 = MMA issuer + TMEM owner | warps 2..9 = hi/lo splitter (NSPLIT >= 2 only) |
 //   last 4 warps = epilogue (TMEM -> registers -> swizzled smem -> TMA store / reduce-add)
-template <int NSPLIT> __host__ __device__ constexpr int persistent_threads() { return NSPLIT >= 2 ? 320 : 192; }
+constexpr int SPLIT_WARPS = 8;   // hi/lo splitter warps of the persistent kernel (NSPLIT >= 2): the split pass (32-48 KB of shared memory per k-block) is what
+                                 // bounds the many small, latency-bound 3xTF32 GEMMs of the decoder -- 8 warps halve it against the original 4
+template <int NSPLIT> __host__ __device__ constexpr int persistent_threads() { return NSPLIT >= 2 ? (2 + SPLIT_WARPS + 4) * 32 : 192; }
 
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
 __global__ void __launch_bounds__(persistent_threads<NSPLIT>())
@@ -465,7 +467,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, AB_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGE_BYTES = stage_bytes<BN, NSPLIT>();
   constexpr uint32_t IDESC = make_idesc_tf32(BN, A_MN, B_MN);
-  constexpr int EPI_WARP0 = (NSPLIT >= 2) ? 6 : 2;
+  constexpr int EPI_WARP0 = (NSPLIT >= 2) ? 2 + SPLIT_WARPS : 2;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -485,7 +487,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (tma_epi) tma_prefetch_desc(&tmap_c);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 128); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], SPLIT_WARPS * 32); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
     fence_barrier_init();
   }
@@ -560,7 +562,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       }
     }
   } else if (NSPLIT >= 2 && warp < EPI_WARP0) {
-    // hi/lo splitter warps 2..5
+    // hi/lo splitter warps 2 .. 2 + SPLIT_WARPS - 1
     const int tsp = threadIdx.x - 64;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -573,7 +575,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         uint4* hi = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + AB_BYTES);
 #pragma unroll 4
-        for (int i = tsp; i < AB_BYTES / 16; i += 128) {
+        for (int i = tsp; i < AB_BYTES / 16; i += SPLIT_WARPS * 32) {
           uint4 v = hi[i];
           uint4 h = make_uint4((v.x + 0x1000u) & 0xFFFFE000u, (v.y + 0x1000u) & 0xFFFFE000u, (v.z + 0x1000u) & 0xFFFFE000u, (v.w + 0x1000u) & 0xFFFFE000u);
           uint4 l;

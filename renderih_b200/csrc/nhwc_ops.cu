@@ -170,6 +170,7 @@ RIH_API int rih_bn_apply(const float* x, int ldx, const float* mean, const float
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
                      const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
                      int M, int C, int rows_per_cta, int relu, double* __restrict__ ws) {
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const int c = blockIdx.x * 32 + tx * 4;
@@ -177,13 +178,19 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __rest
   double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
   if (c < C) {
     const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), be = ga;
+    if (relu && !y) { ga = *reinterpret_cast<const float4*>(gamma + c); be = *reinterpret_cast<const float4*>(beta + c); }
     for (int r = r0 + ty; r < r1; r += 32) {
       float4 g = *reinterpret_cast<const float4*>(dy + (size_t)r * lddy + c);
+      const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * ldx + c);
       if (relu) {
-        const float4 yy = *reinterpret_cast<const float4*>(y + (size_t)r * ldy + c);
+        // ReLU mask: from the saved output, or (no residual) recomputed from x with the forward's exact expression (bn_apply_kernel)
+        float4 yy;
+        if (y) yy = *reinterpret_cast<const float4*>(y + (size_t)r * ldy + c);
+        else { yy.x = (xv.x - mu.x) * rs.x * ga.x + be.x; yy.y = (xv.y - mu.y) * rs.y * ga.y + be.y;
+               yy.z = (xv.z - mu.z) * rs.z * ga.z + be.z; yy.w = (xv.w - mu.w) * rs.w * ga.w + be.w; }
         if (!(yy.x > 0.f)) g.x = 0.f; if (!(yy.y > 0.f)) g.y = 0.f; if (!(yy.z > 0.f)) g.z = 0.f; if (!(yy.w > 0.f)) g.w = 0.f;
       }
-      const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * ldx + c);
       s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
       sx[0] += (double)g.x * ((xv.x - mu.x) * rs.x); sx[1] += (double)g.y * ((xv.y - mu.y) * rs.y);
       sx[2] += (double)g.z * ((xv.z - mu.z) * rs.z); sx[3] += (double)g.w * ((xv.w - mu.w) * rs.w);
@@ -213,7 +220,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, int C, flo
 // backward pass 2: dx = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) [train] ; dres (+)= g ; optional mask by (x>0) for Conv->ReLU->BN
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
                                     const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
                                     float* __restrict__ dx, int lddx, float* __restrict__ dres, int lddr, int dres_acc,
                                     long long M, int C4, int relu, int training, int mask_input) {
   long long total = M * C4;
@@ -222,8 +229,16 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, cons
     long long r; int c; divmod(i, C4, total < (1ll << 32), r, c); c *= 4;
     float4 g4 = *reinterpret_cast<const float4*>(dy + r * lddy + c);
     float g[4] = {g4.x, g4.y, g4.z, g4.w};
+    const float4 x4 = *reinterpret_cast<const float4*>(x + r * ldx + c);
     if (relu) {
-      float4 y4 = *reinterpret_cast<const float4*>(y + r * ldy + c);
+      float4 y4;
+      if (y) y4 = *reinterpret_cast<const float4*>(y + r * ldy + c);
+      else {   // no residual: the forward output is a function of x alone -- same expression as bn_apply_kernel, so the mask is bit-identical
+        const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+        y4.x = (x4.x - mu.x) * rs.x * ga.x + be.x; y4.y = (x4.y - mu.y) * rs.y * ga.y + be.y;
+        y4.z = (x4.z - mu.z) * rs.z * ga.z + be.z; y4.w = (x4.w - mu.w) * rs.w * ga.w + be.w;
+      }
       if (!(y4.x > 0.f)) g[0] = 0.f; if (!(y4.y > 0.f)) g[1] = 0.f;
       if (!(y4.z > 0.f)) g[2] = 0.f; if (!(y4.w > 0.f)) g[3] = 0.f;
     }
@@ -232,7 +247,6 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, cons
       if (dres_acc) { float4 o = *reinterpret_cast<float4*>(q); o.x += g[0]; o.y += g[1]; o.z += g[2]; o.w += g[3]; *reinterpret_cast<float4*>(q) = o; }
       else *reinterpret_cast<float4*>(q) = make_float4(g[0], g[1], g[2], g[3]);
     }
-    float4 x4 = *reinterpret_cast<const float4*>(x + r * ldx + c);
     float xv[4] = {x4.x, x4.y, x4.z, x4.w};
     float o[4];
 #pragma unroll
@@ -252,26 +266,29 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, cons
   }
 }
 // ws: double[2C]; tmp: float[2C] (sum_g, sum_gx)
+// y (the forward output) is only needed for the ReLU mask of a residual block; pass NULL otherwise and the mask is recomputed from x
+// (needs beta) -- one tensor read less in each of the two passes
 RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const float* x, int ldx,
-                       const float* mean, const float* rstd, const float* gamma,
+                       const float* mean, const float* rstd, const float* gamma, const float* beta,
                        float* dx, int lddx, float* dres, int lddr, int dres_acc,
                        float* dgamma, float* dbeta, int param_acc,
                        long long M, int C, int relu, int training, int mask_input,
                        double* ws, float* tmp, cudaStream_t s) {
   RIH_REQUIRE(C % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0, "bn_bwd: needs C,ld %% 4 == 0");
   RIH_REQUIRE(M < (1ll << 31), "bn_bwd: too many rows");
+  RIH_REQUIRE(!relu || y || beta, "bn_bwd: the ReLU mask needs either the forward output or beta");
   RIH_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, s));
   int gx = cdiv(C, 32);
   int target = cdiv(148 * 8, gx);
   int rows_per_cta = max(64, cdiv(M, target));
   dim3 grid(gx, cdiv(M, rows_per_cta));
-  bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, (int)M, C, rows_per_cta, relu, ws);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, (int)M, C, rows_per_cta, relu, ws);
   if (int e = check_launch("bn_bwd_reduce")) return e;
   bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(ws, C, dgamma, dbeta, tmp, tmp + C, param_acc);
   if (int e = check_launch("bn_bwd_finalize")) return e;
   long long total = M * (C / 4);
   int g2 = (int)min((long long)148 * 16, (total + 255) / 256);
-  bn_bwd_apply_kernel<<<g2, 256, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, tmp, tmp + C, dx, lddx, dres, lddr, dres_acc,
+  bn_bwd_apply_kernel<<<g2, 256, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, tmp, tmp + C, dx, lddx, dres, lddr, dres_acc,
                                          M, C / 4, relu, training, mask_input);
   return check_launch("bn_bwd_apply");
 }

@@ -658,7 +658,8 @@ class BatchNormFn(Function):
             res = _rows(res)
         call('rih_bn_apply', _p(x), _ld(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(res), _ld(res) if res is not None else 0,
              _p(y), C, M, C, int(relu), s)
-        ctx.save_for_backward(x, gamma, mean, rstd, y if relu else None)
+        # the ReLU mask of a residual block needs the output; otherwise it is recomputed from x in the backward kernels (one read less)
+        ctx.save_for_backward(x, gamma, mean, rstd, y if (relu and res is not None) else None)
         ctx.meta = (training, relu, mask_input, res is not None)
         ctx.beta_ref = beta
         return y
@@ -678,7 +679,7 @@ class BatchNormFn(Function):
         dbeta = tb if direct else torch.empty((C,), device=dev)
         ws = torch.empty((2 * C,), device=dev, dtype=torch.float64)
         tmp = torch.empty((2 * C,), device=dev)
-        call('rih_bn_bwd', _p(dy), _ld(dy), _p(y), C, _p(x), _ld(x), _p(mean), _p(rstd), _p(gamma),
+        call('rih_bn_bwd', _p(dy), _ld(dy), _p(y), C, _p(x), _ld(x), _p(mean), _p(rstd), _p(gamma), _p(ctx.beta_ref),
              _p(dx), C, _p(dres), C, 0, _p(dgamma), _p(dbeta), int(direct), M, C, int(relu), int(training), int(mask_input),
              _p(ws), _p(tmp), _stream())
         if direct:
