@@ -106,6 +106,15 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def metric_name(batch, world):
+    return 'images/sec fwd+bwd @batch%d 256x256 (training step: fwd + calc_loss_GCN + bwd + AdamW%s)' % (batch, ' + NCCL grad all-reduce' if world > 1 else '')
+
+
+def workload_name(encoder, batch):
+    return 'BASELINE.json configs[%d]: HandNET_GCN %s cfg, batch %d/GPU, 256x256, train mode (batch-stat BN, dropout 0.05), random-init weights, ' \
+           'synthetic graph/MANO assets' % (4 if encoder == 'hrnet48' else 2, {'graph': 'common/myhand graph variant (ResNet50 trunk)'}.get(encoder, encoder), batch)
+
+
 def host_cores():
     """CPU threads this process can actually run on: the scheduler affinity mask, capped by the cgroup CPU quota (a container on
     a 128-thread host may own far fewer; oversubscribing torch's intra-op pool there makes the CPU baseline tens of times slower
@@ -165,6 +174,7 @@ def cpu_port_step_time(batch, steps=1, warmup=0, budget_s=1e9, encoder='resnet50
     Ap = model_ref.prepare_assets(a)
     la = fixtures.make_loss_assets(a, A.synthetic_mano(0, 'left'), A.synthetic_mano(0, 'right'))
     img, labels = fixtures.make_image(batch), fixtures.make_labels(batch)
+    opt = torch.optim.AdamW([v for v in sd.values() if v.requires_grad], lr=cfg.TRAIN.LR, weight_decay=cfg.TRAIN.weight_decay)
     times = []
     t_begin = time.perf_counter()
     for i in range(warmup + steps):
@@ -176,6 +186,7 @@ def cpu_port_step_time(batch, steps=1, warmup=0, budget_s=1e9, encoder='resnet50
         out = model_ref.model_forward(sd, Ap, img, training=True, dropout=0.05)
         loss = model_ref.calc_loss_GCN(out, labels, la)
         loss.backward()
+        opt.step()
         t1 = time.perf_counter()
         if i >= warmup:
             times.append(t1 - t0)
@@ -189,12 +200,14 @@ def run_reference(args):
     # bounded: the CPU port needs tens of seconds per step on a big host, so at most ~3 steps / ~150 s are timed
     t, cores, nsteps = cpu_port_step_time(args.cpu_batch, steps=max(1, min(args.steps, 3)), warmup=0, budget_s=150.0, encoder=args.encoder)
     v = args.cpu_batch / t
-    line = {'impl': 'reference', 'metric': 'images/sec fwd+bwd (calc_loss_GCN) @256x256', 'value': v, 'unit': 'images/s',
+    line = {'impl': 'reference', 'metric': metric_name(args.batch, 1), 'value': v, 'unit': 'images/s',
             'n_gpus': args.gpus, 'steps': nsteps, 'warmup': 0, 'ms_per_step': t * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'HandNET_GCN %s cfg, fwd+calc_loss_GCN+bwd, CPU sample batch %d of the batch-%d workload' % (args.encoder, args.cpu_batch, args.batch)},
+            'config': {'workload': workload_name(args.encoder, args.batch), 'global_batch': args.batch * args.gpus, 'parallelism': 'dp%d' % args.gpus,
+                       'reference_arm': 'the reference algorithm (oracle/model_ref.py port: same torch CPU ops as the reference graph) on the host cores, '
+                                        'each step a bounded sample of batch %d images of the batch-%d workload' % (args.cpu_batch, args.batch)},
             'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                             'sample': 'batch %d fwd+bwd, oracle/model_ref.py on torch CPU fp32, %d threads' % (args.cpu_batch, cores)},
+                             'sample': 'batch %d fwd+calc_loss_GCN+bwd+AdamW, oracle/model_ref.py on torch CPU fp32, %d of %d usable threads' % (args.cpu_batch, cores, host_cores())},
             'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
@@ -331,14 +344,13 @@ def run_ours(args):
     total_imgs = B * world
     value = total_imgs / (ms_dev * 1e-3)
     e2e = total_imgs / (ms_e2e * 1e-3)
-    line = {'metric': 'images/sec fwd+bwd @batch%d 256x256 (training step: fwd + calc_loss_GCN + bwd + AdamW%s)' % (B, ' + NCCL grad all-reduce' if world > 1 else ''),
+    line = {'metric': metric_name(B, world),
             'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_dev,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': {'simt': 'f32', 'refrn': 'f32 storage; tcgen05 TF32(rn) convolutions (cuDNN-default class of the reference) + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate',
                       'tf32': 'tf32 (truncating) conv+Linear, fp32 accumulate/storage', 'tf32c': 'tf32 (truncating, mean-compensated) conv+Linear, fp32 accumulate/storage',
                       'ref': 'f32 storage; tcgen05 TF32 convolutions (truncating + mean-compensated: the accuracy class of the reference\'s cuDNN-TF32 default, measured) + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate', 'tf32rn': 'tf32 (rn) conv+Linear, fp32 accumulate/storage',
                       'tf32x3': '3xTF32 (fp32-faithful) conv+Linear, fp32 accumulate/storage'}[args.gemm_mode], 'data': 'synthetic',
-            'config': {'workload': 'BASELINE.json configs[%d]: HandNET_GCN %s cfg, batch %d/GPU, 256x256, train mode (batch-stat BN, dropout 0.05), '
-                                   'random-init weights, synthetic graph/MANO assets' % (4 if args.encoder == 'hrnet48' else 2, {'graph': 'common/myhand graph variant (ResNet50 trunk)'}.get(args.encoder, args.encoder), B),
+            'config': {'workload': workload_name(args.encoder, B),
                        'global_batch': total_imgs, 'parallelism': 'dp%d' % world, 'cuda_graph': not args.no_graph,
                        'l2': 'per-step working set (activations, several GB) >> 126 MB L2; no explicit flush needed',
                        'algorithmic_gflop_per_image': flops_fb / 1e9},
@@ -349,7 +361,7 @@ def run_ours(args):
     if not args.skip_cpu_baseline and world == 1:
         t, cores, _ = cpu_port_step_time(args.cpu_batch, steps=1, warmup=0, encoder=args.encoder)
         line['cpu_baseline'] = {'value': args.cpu_batch / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                'sample': 'batch %d fwd+calc_loss_GCN+bwd once, oracle/model_ref.py (torch CPU fp32, %d of %d usable threads)' % (args.cpu_batch, cores, host_cores())}
+                                'sample': 'batch %d fwd+calc_loss_GCN+bwd+AdamW once, oracle/model_ref.py (torch CPU fp32, %d of %d usable threads)' % (args.cpu_batch, cores, host_cores())}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
