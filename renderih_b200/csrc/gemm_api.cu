@@ -42,7 +42,7 @@ static inline bool use_tc(int which) {
 extern "C" int rih_bn_colstats(const float* x, int ld, int M, int C, double* ws, cudaStream_t s);
 static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
                            int M, int N, int K, int relu, int accumulate, const float* res, int ldres,
-                           float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, double* stats, cudaStream_t stream);
+                           float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, double* stats, int as_conv, cudaStream_t stream);
 static inline bool tc_ok(const void* p, long long ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0); }
 
 static inline int is_vec_ok(const void* p, int ld) {
@@ -50,23 +50,24 @@ static inline int is_vec_ok(const void* p, int ld) {
 }
 
 // y[M,N] = x[M,K] @ w[N,K]^T (+bias) (+residual) (relu) ; reference: torch.nn.Linear (e.g. models/model_attn/gcn.py:92-96)
+// as_conv != 0: the GEMM is a convolution in disguise (the im2col'ed RGB stem): use the convolution arithmetic mode, not the Linear one
 RIH_API int rih_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
                            int M, int N, int K, int relu, int accumulate, const float* res, int ldres,
-                           float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, double* stats, cudaStream_t stream) {
+                           float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, double* stats, int as_conv, cudaStream_t stream) {
   RIH_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_fwd: bad shape M=%d N=%d K=%d", M, N, K);
   if (stats) {   // fused BatchNorm statistics of the output (see rih_conv2d_fwd)
     RIH_REQUIRE(!accumulate && !res, "linear_fwd: stats need a plain store epilogue");
     RIH_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N, stream));
   }
   tc::g_stats_fused = 0;
-  int rc = linear_fwd_impl(x, ldx, w, ldw, bias, y, ldy, M, N, K, relu, accumulate, res, ldres, dropout_p, seed_ptr, site, stats, stream);
+  int rc = linear_fwd_impl(x, ldx, w, ldw, bias, y, ldy, M, N, K, relu, accumulate, res, ldres, dropout_p, seed_ptr, site, stats, as_conv, stream);
   if (rc) return rc;
   if (stats && !tc::g_stats_fused) return rih_bn_colstats(y, ldy, M, N, stats, stream);
   return 0;
 }
 static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
                            int M, int N, int K, int relu, int accumulate, const float* res, int ldres,
-                           float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, double* stats, cudaStream_t stream) {
+                           float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, double* stats, int as_conv, cudaStream_t stream) {
   DenseK a{x, ldx, M, is_vec_ok(x, ldx) && (K % 4 == 0)};
   DenseK b{w, ldw, N, is_vec_ok(w, ldw) && (K % 4 == 0)};
   Epilogue ep = make_epilogue(y, ldy, M, N, bias, relu, accumulate ? 1 : 0);
@@ -75,31 +76,31 @@ static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, con
     RIH_REQUIRE(seed_ptr != nullptr && dropout_p < 1.f, "linear_fwd: dropout needs a device seed and p < 1");
     ep.seed_ptr = seed_ptr; ep.site = site; ep.thresh = dropout_thresh(dropout_p); ep.inv_keep = 1.f / (1.f - dropout_p);
   }
-  if (use_tc(1) && M >= 64 && tc_ok(x, ldx) && tc_ok(w, ldw))
+  if (use_tc(as_conv ? 0 : 1) && M >= 64 && tc_ok(x, ldx) && tc_ok(w, ldw))
     return tc::gemm_tf32(x, ldx, 0, w, ldw, 0, ep, M, N, K, 0, stream);
   return launch_gemm_simt(a, b, ep, M, N, K, 0, stream, "linear_fwd");
 }
 
 // dx[M,K] (+)= dy[M,N] @ w[N,K]
 RIH_API int rih_linear_dgrad(const float* dy, int lddy, const float* w, int ldw, float* dx, int lddx,
-                             int M, int N, int K, int accumulate, cudaStream_t stream) {
+                             int M, int N, int K, int accumulate, int as_conv, cudaStream_t stream) {
   RIH_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_dgrad: bad shape");
   DenseK a{dy, lddy, M, is_vec_ok(dy, lddy) && (N % 4 == 0)};
   DenseMN b{w, ldw, K, is_vec_ok(w, ldw)};
   Epilogue ep = make_epilogue(dx, lddx, M, K, nullptr, 0, accumulate ? 1 : 0);
-  if (use_tc(1) && M >= 64 && tc_ok(dy, lddy) && tc_ok(w, ldw))
+  if (use_tc(as_conv ? 0 : 1) && M >= 64 && tc_ok(dy, lddy) && tc_ok(w, ldw))
     return tc::gemm_tf32(dy, lddy, 0, w, ldw, 1, ep, M, K, N, 0, stream);
   return launch_gemm_simt(a, b, ep, M, K, N, 0, stream, "linear_dgrad");
 }
 
 // dw[N,K] (+)= dy[M,N]^T @ x[M,K]
 RIH_API int rih_linear_wgrad(const float* dy, int lddy, const float* x, int ldx, float* dw, int lddw,
-                             int M, int N, int K, int accumulate, cudaStream_t stream) {
+                             int M, int N, int K, int accumulate, int as_conv, cudaStream_t stream) {
   RIH_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_wgrad: bad shape");
   DenseMN a{dy, lddy, N, is_vec_ok(dy, lddy)};
   DenseMN b{x, ldx, K, is_vec_ok(x, ldx)};
   Epilogue ep = make_epilogue(dw, lddw, N, K, nullptr, 0, accumulate ? 1 : 0);
-  if (use_tc(1) && M >= 64 && N >= 16 && tc_ok(dy, lddy) && tc_ok(x, ldx))
+  if (use_tc(as_conv ? 0 : 1) && M >= 64 && N >= 16 && tc_ok(dy, lddy) && tc_ok(x, ldx))
     return tc::gemm_tf32(dy, lddy, 1, x, ldx, 1, ep, N, K, M, 1, stream);
   return launch_gemm_simt(a, b, ep, N, K, M, 1, stream, "linear_wgrad");
 }

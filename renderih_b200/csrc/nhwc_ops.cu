@@ -33,8 +33,22 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restri
     if (c < C && p < HW) y[((size_t)n * C + c) * HW + p] = tile[threadIdx.x][i];
   }
 }
+// few-channel images (the RGB input): one thread per pixel, plane reads coalesced across the warp, pixel writes contiguous
+__global__ void nchw_to_nhwc_small_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int Cp, int ldy, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW; const int p = (int)(i - n * HW);
+    float* q = y + i * ldy;
+    for (int c = 0; c < Cp; ++c) q[c] = c < C ? x[(n * C + c) * HW + p] : 0.f;
+  }
+}
 RIH_API int rih_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int Cp, int ldy, cudaStream_t s) {
   RIH_REQUIRE(Cp >= C && ldy >= Cp, "nchw_to_nhwc: bad channel padding");
+  if (Cp <= 8) {
+    const long long total = (long long)N * HW;
+    if (total == 0) return 0;
+    nchw_to_nhwc_small_kernel<<<(int)min((long long)148 * 16, (total + 255) / 256), 256, 0, s>>>(x, y, C, HW, Cp, ldy, total);
+    return check_launch("nchw_to_nhwc");
+  }
   dim3 grid(cdiv(HW, 32), cdiv(Cp, 32), N), block(32, 8);
   nchw_to_nhwc_kernel<<<grid, block, 0, s>>>(x, y, N, C, HW, Cp, ldy);
   return check_launch("nchw_to_nhwc");
@@ -345,18 +359,65 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned 
     dx[i] = acc;
   }
 }
+// float4 (4 channels per thread) variants: the 268 MB stem activation is streamed once at full width
+__global__ void maxpool4_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ idx,
+                                    int N, int H, int W, int C4, int Ho, int Wo) {
+  const long long total = (long long)N * Ho * Wo * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4); long long t = i / C4; int ow = (int)(t % Wo); t /= Wo; int oh = (int)(t % Ho); int n = (int)(t / Ho);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bi[4] = {-1, -1, -1, -1};
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r; if ((unsigned)ih >= (unsigned)H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 - 1 + s; if ((unsigned)iw >= (unsigned)W) continue;
+        const float4 v4 = *reinterpret_cast<const float4*>(x + (((size_t)(n * H + ih) * W + iw) * C4 + c) * 4);
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (bi[k] < 0 || v[k] > best[k] || isnan(v[k])) { best[k] = v[k]; bi[k] = r * 3 + s; }
+      }
+    }
+    *reinterpret_cast<float4*>(y + i * 4) = make_float4(best[0], best[1], best[2], best[3]);
+    *reinterpret_cast<uchar4*>(idx + i * 4) = make_uchar4((unsigned char)bi[0], (unsigned char)bi[1], (unsigned char)bi[2], (unsigned char)bi[3]);
+  }
+}
+__global__ void maxpool4_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ idx, float* __restrict__ dx,
+                                    int N, int H, int W, int C4, int Ho, int Wo) {
+  const long long total = (long long)N * H * W * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4); long long t = i / C4; int iw = (int)(t % W); t /= W; int ih = (int)(t % H); int n = (int)(t / H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < 3; ++r) {
+      const int a = ih + 1 - r; if (a < 0 || (a & 1)) continue; const int oh = a >> 1; if (oh >= Ho) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int b = iw + 1 - s; if (b < 0 || (b & 1)) continue; const int ow = b >> 1; if (ow >= Wo) continue;
+        const size_t o = (((size_t)(n * Ho + oh) * Wo + ow) * C4 + c) * 4;
+        const uchar4 id = *reinterpret_cast<const uchar4*>(idx + o);
+        const float4 g = *reinterpret_cast<const float4*>(dy + o);
+        const unsigned char tag = (unsigned char)(r * 3 + s);
+        if (id.x == tag) acc[0] += g.x; if (id.y == tag) acc[1] += g.y; if (id.z == tag) acc[2] += g.z; if (id.w == tag) acc[3] += g.w;
+      }
+    }
+    *reinterpret_cast<float4*>(dx + i * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
 RIH_API int rih_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int N, int H, int W, int C, cudaStream_t s) {
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  long long total = (long long)N * Ho * Wo * C;
+  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && (reinterpret_cast<uintptr_t>(idx) & 3) == 0;
+  long long total = (long long)N * Ho * Wo * (vec ? C / 4 : C);
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  maxpool_fwd_kernel<<<grid, 256, 0, s>>>(x, y, idx, N, H, W, C, Ho, Wo);
+  if (vec) maxpool4_fwd_kernel<<<grid, 256, 0, s>>>(x, y, idx, N, H, W, C / 4, Ho, Wo);
+  else maxpool_fwd_kernel<<<grid, 256, 0, s>>>(x, y, idx, N, H, W, C, Ho, Wo);
   return check_launch("maxpool_fwd");
 }
 RIH_API int rih_maxpool3x3s2_bwd(const float* dy, const unsigned char* idx, float* dx, int N, int H, int W, int C, cudaStream_t s) {
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  long long total = (long long)N * H * W * C;
+  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 && (reinterpret_cast<uintptr_t>(idx) & 3) == 0;
+  long long total = (long long)N * H * W * (vec ? C / 4 : C);
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  maxpool_bwd_kernel<<<grid, 256, 0, s>>>(dy, idx, dx, N, H, W, C, Ho, Wo);
+  if (vec) maxpool4_bwd_kernel<<<grid, 256, 0, s>>>(dy, idx, dx, N, H, W, C / 4, Ho, Wo);
+  else maxpool_bwd_kernel<<<grid, 256, 0, s>>>(dy, idx, dx, N, H, W, C, Ho, Wo);
   return check_launch("maxpool_bwd");
 }
 
@@ -400,7 +461,13 @@ __global__ void bilinear2x_bwd_kernel(const float* __restrict__ dy, int lddy, fl
     atomicAdd(b + ((size_t)h1 * W + w1) * lddx, lh * lw * g);
   }
 }
+RIH_API int rih_bilinear_up_fwd(const float* x, int ldx, float* y, int ldy, int N, int H, int W, int C, int f, cudaStream_t s);
+RIH_API int rih_bilinear_up_bwd(const float* dy, int lddy, float* dx, int lddx, int N, int H, int W, int C, int f, cudaStream_t s);
+static inline bool bil_vec_ok(const void* a, int lda, const void* b, int ldb, int C) {
+  return C % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
 RIH_API int rih_bilinear2x_fwd(const float* x, int ldx, float* y, int ldy, int N, int H, int W, int C, cudaStream_t s) {
+  if (bil_vec_ok(x, ldx, y, ldy, C)) return rih_bilinear_up_fwd(x, ldx, y, ldy, N, H, W, C, 2, s);      // float4 kernel
   long long total = (long long)N * 4 * H * W * C;
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
   bilinear2x_fwd_kernel<<<grid, 256, 0, s>>>(x, ldx, y, ldy, N, H, W, C);
@@ -408,6 +475,7 @@ RIH_API int rih_bilinear2x_fwd(const float* x, int ldx, float* y, int ldy, int N
 }
 // dx must be zero-initialised by the caller (scatter-add)
 RIH_API int rih_bilinear2x_bwd(const float* dy, int lddy, float* dx, int lddx, int N, int H, int W, int C, cudaStream_t s) {
+  if (bil_vec_ok(dy, lddy, dx, lddx, C)) return rih_bilinear_up_bwd(dy, lddy, dx, lddx, N, H, W, C, 2, s);   // gather form: overwrites dx, no atomics
   long long total = (long long)N * 4 * H * W * C;
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
   bilinear2x_bwd_kernel<<<grid, 256, 0, s>>>(dy, lddy, dx, lddx, N, H, W, C);
@@ -678,10 +746,43 @@ __global__ void im2col_kernel(const float* __restrict__ x, int ldx, float* __res
     A[i] = v;
   }
 }
+// float4 stores: one thread per 4 consecutive columns of a row of A.  Within a filter row r the S*C columns map to S*C CONTIGUOUS
+// floats of the NHWC input (pixels iw0 .. iw0+S-1, all channels), so neighbouring threads read neighbouring addresses.
+template <int TR, int TS, int TC>
+__global__ void im2col4_kernel(const float* __restrict__ x, int ldx, float* __restrict__ A, int N, int H, int W, int Ho, int Wo,
+                               int stride, int pad, int Kpad4) {
+  constexpr int K = TR * TS * TC, SC = TS * TC;
+  const long long total = (long long)N * Ho * Wo * Kpad4;
+  const bool small = total < (1ll << 32);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long m; int k4;
+    divmod(i, Kpad4, small, m, k4);
+    const int ow = (int)(m % Wo); const long long t = m / Wo; const int oh = (int)(t % Ho), n = (int)(t / Ho);
+    const int ih0 = oh * stride - pad, iw0 = ow * stride - pad;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k4 * 4 + e;
+      v[e] = 0.f;
+      if (k < K) {
+        const int r = k / SC, off = k - r * SC, s_ = off / TC, c = off - s_ * TC;
+        const int ih = ih0 + r, iw = iw0 + s_;
+        if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) v[e] = __ldg(x + ((size_t)(n * H + ih) * W + iw) * ldx + c);
+      }
+    }
+    reinterpret_cast<float4*>(A)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
 RIH_API int rih_im2col(const float* x, int ldx, float* A, int N, int H, int W, int C, int R, int S, int stride, int pad, int Kpad, cudaStream_t s) {
   RIH_REQUIRE(Kpad >= R * S * C && Kpad % 4 == 0, "im2col: Kpad must be a multiple of 4 and >= R*S*C");
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
   const long long total = (long long)N * Ho * Wo * Kpad;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) == 0 && C == 3 && R == S && (R == 7 || R == 3)) {
+    const int g4 = (int)min((long long)148 * 32, (total / 4 + 255) / 256);
+    if (R == 7) im2col4_kernel<7, 7, 3><<<g4, 256, 0, s>>>(x, ldx, A, N, H, W, Ho, Wo, stride, pad, Kpad / 4);
+    else im2col4_kernel<3, 3, 3><<<g4, 256, 0, s>>>(x, ldx, A, N, H, W, Ho, Wo, stride, pad, Kpad / 4);
+    return check_launch("im2col");
+  }
   int grid = (int)min((long long)148 * 32, (total + 255) / 256);
   if (R == 7 && S == 7 && C == 3) im2col_kernel<7, 7, 3><<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
   else if (R == 3 && S == 3 && C == 3) im2col_kernel<3, 3, 3><<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);   // HRNet stem

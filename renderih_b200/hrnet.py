@@ -73,7 +73,7 @@ def stem_conv_bn(x, conv, bn, N, H, training, image_needs_grad):
     A = ops.im2col(x, N, H, H, R, S, st, pd, Kpad)
     w2d = torch.nn.functional.pad(conv.weight.permute(0, 2, 3, 1).reshape(Cout, K), (0, Kpad - K))   # tiny
     stats = torch.empty(2 * Cout, device=x.device, dtype=torch.float64) if training else None
-    y = ops.linear(A, w2d, conv.bias, stats=stats)
+    y = ops.linear(A, w2d, conv.bias, stats=stats, as_conv=True)
     y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training=training, momentum=bn.momentum,
                       eps=bn.eps, relu=True, stats=stats)
     return y, (H + 2 * pd - R) // st + 1

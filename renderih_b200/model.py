@@ -136,7 +136,7 @@ class ResNetSimple(nn.Module):
         A = ops.im2col(x, N, H, H, R, S, conv.stride[0], conv.padding[0], Kpad)
         w2d = torch.nn.functional.pad(conv.weight.permute(0, 2, 3, 1).reshape(Cout, K), (0, Kpad - K))   # tiny (64 x 160)
         stats = torch.empty(2 * Cout, device=x.device, dtype=torch.float64)
-        y = ops.linear(A, w2d, None, stats=stats)
+        y = ops.linear(A, w2d, None, stats=stats, as_conv=True)
         y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training=True, momentum=bn.momentum, eps=bn.eps,
                           relu=True, stats=stats)
         return y, (H + 2 * conv.padding[0] - R) // conv.stride[0] + 1

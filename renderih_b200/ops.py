@@ -127,7 +127,7 @@ class LinearFn(Function):
     """y = dropout(relu(x @ w^T + b)) + res  -- torch.nn.Linear call sites of models/model_attn/*.py, models/decoder.py"""
 
     @staticmethod
-    def forward(ctx, x, w, b, relu, res, p_drop, site, stats=None):
+    def forward(ctx, x, w, b, relu, res, p_drop, site, stats=None, as_conv=False):
         x = _rows(x); _check(w, 'weight')
         M, K = x.shape
         N = w.shape[0]
@@ -138,9 +138,10 @@ class LinearFn(Function):
             res = _rows(res)
         sp = seed_state.ptr(x.device) if p_drop > 0 else None
         call('rih_linear_fwd', _p(x), _ld(x), _p(w), w.stride(0), _p(b), _p(y), N, M, N, K, int(relu), 0,
-             _p(res), _ld(res) if res is not None else 0, float(p_drop), sp, site, _p(stats), _stream())
+             _p(res), _ld(res) if res is not None else 0, float(p_drop), sp, site, _p(stats), int(as_conv), _stream())
         ctx.save_for_backward(x, w, y if (relu or p_drop > 0) else None)
         ctx.meta = (relu, p_drop, site, b is not None, res is not None)
+        ctx.as_conv = int(as_conv)
         ctx.bias_ref = b
         return y
 
@@ -160,14 +161,14 @@ class LinearFn(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), device=dy.device, dtype=torch.float32)
-            call('rih_linear_dgrad', _p(g), _ld(g), _p(w), w.stride(0), _p(dx), K, M, N, K, 0, s)
+            call('rih_linear_dgrad', _p(g), _ld(g), _p(w), w.stride(0), _p(dx), K, M, N, K, 0, ctx.as_conv, s)
         if ctx.needs_input_grad[1]:
             tgt = _gt(w)
             if tgt is not None:
-                call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(tgt), w.stride(0), M, N, K, 1, s)
+                call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(tgt), w.stride(0), M, N, K, 1, ctx.as_conv, s)
             else:
                 dw = torch.empty((N, K), device=dy.device, dtype=torch.float32)
-                call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(dw), K, M, N, K, 0, s)
+                call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(dw), K, M, N, K, 0, ctx.as_conv, s)
         if has_b and ctx.needs_input_grad[2]:
             tgt = _gt(ctx.bias_ref)
             if tgt is not None:
@@ -176,13 +177,14 @@ class LinearFn(Function):
                 db = torch.empty((N,), device=dy.device, dtype=torch.float32)
                 call('rih_colsum', _p(g), _ld(g), M, N, _p(db), 0, s)
         dres = dy if (has_res and ctx.needs_input_grad[4]) else None
-        return dx, dw, db, None, dres, None, None, None
+        return dx, dw, db, None, dres, None, None, None, None
 
 
-def linear(x, w, b=None, relu=False, res=None, p_drop=0.0, stats=None):
-    """stats: optional float64 [2*N] buffer receiving the output's column sums / sums of squares (fused BN statistics)."""
+def linear(x, w, b=None, relu=False, res=None, p_drop=0.0, stats=None, as_conv=False):
+    """stats: optional float64 [2*N] buffer receiving the output's column sums / sums of squares (fused BN statistics).
+    as_conv: this GEMM is a convolution (im2col'ed stem): it follows the convolution arithmetic mode of set_gemm_mode."""
     site = seed_state.next_site() if p_drop > 0 else 0
-    return LinearFn.apply(x, w, b, relu, res, p_drop, site, stats)
+    return LinearFn.apply(x, w, b, relu, res, p_drop, site, stats, as_conv)
 
 
 # ----------------------------------------------------------------------------- LayerNorm
