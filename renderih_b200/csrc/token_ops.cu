@@ -39,36 +39,44 @@ RIH_API int rih_layernorm_fwd(const float* a, int lda, const float* b, int ldb, 
 
 // dx = rstd * (g*gamma - mean_c(g*gamma) - xhat * mean_c(g*gamma*xhat)), g = dy * (y>0 if relu)
 // dgamma += sum_r g*xhat ; dbeta += sum_r g        (F <= 32*LN_MAXC)
-constexpr int LN_MAXC = 16;
-__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ a, int lda,
-                                     const float* __restrict__ b, int ldb, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     float* __restrict__ dx, int lddx, int dx_acc, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     int M, int F, int relu) {
+// MAXC = columns per lane (F <= 32 * MAXC), THREADS per CTA: narrow rows use 32 warps per CTA so that a warp walks only a few rows
+// (the per-row dependent chain load -> 2 warp reductions -> store is latency bound) while the per-CTA parameter-gradient atomics stay few.
+template <int MAXC, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ a, int lda,
+                     const float* __restrict__ b, int ldb, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     float* __restrict__ dx, int lddx, int dx_acc, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     int M, int F, int relu) {
+  constexpr int WARPS = THREADS / 32;
   int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int warp = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
-  int nwarps = gridDim.x * (blockDim.x >> 5);
-  float ag[LN_MAXC], ab[LN_MAXC];
+  int warp = blockIdx.x * WARPS + warp_in_cta;
+  int nwarps = gridDim.x * WARPS;
+  float ag[MAXC], ab[MAXC], gam[MAXC], bet[MAXC];
 #pragma unroll
-  for (int j = 0; j < LN_MAXC; ++j) { ag[j] = 0.f; ab[j] = 0.f; }
+  for (int j = 0; j < MAXC; ++j) {
+    const int c = lane + 32 * j;
+    ag[j] = 0.f; ab[j] = 0.f;
+    gam[j] = c < F ? gamma[c] : 0.f; bet[j] = (c < F && relu) ? beta[c] : 0.f;
+  }
   for (int r = warp; r < M; r += nwarps) {
     const float* pa = a + (size_t)r * lda;
     const float* pb = b ? b + (size_t)r * ldb : nullptr;
     const float* pg = dy + (size_t)r * lddy;
     float mu = mean[r], rs = rstd[r];
     float s1 = 0.f, s2 = 0.f;
-    float gg[LN_MAXC], xh[LN_MAXC];
+    float gg[MAXC], xh[MAXC];
 #pragma unroll
-    for (int j = 0; j < LN_MAXC; ++j) {
+    for (int j = 0; j < MAXC; ++j) {
       int c = lane + 32 * j;
       gg[j] = 0.f; xh[j] = 0.f;
       if (c < F) {
         float x = pa[c] + (pb ? pb[c] : 0.f);
         float h = (x - mu) * rs;
         float g = pg[c];
-        if (relu && !(h * gamma[c] + beta[c] > 0.f)) g = 0.f;
+        if (relu && !(h * gam[j] + bet[j] > 0.f)) g = 0.f;
         ag[j] += g * h; ab[j] += g;
-        float gw = g * gamma[c];
+        float gw = g * gam[j];
         gg[j] = gw; xh[j] = h;
         s1 += gw; s2 += gw * h;
       }
@@ -76,7 +84,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, con
     s1 = warp_sum(s1) / (float)F; s2 = warp_sum(s2) / (float)F;
     float* pd = dx + (size_t)r * lddx;
 #pragma unroll
-    for (int j = 0; j < LN_MAXC; ++j) {
+    for (int j = 0; j < MAXC; ++j) {
       int c = lane + 32 * j;
       if (c < F) {
         float v = rs * (gg[j] - s1 - xh[j] * s2);
@@ -85,14 +93,14 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, con
     }
   }
   // CTA reduction of the parameter gradients, then one atomicAdd per column per CTA
-  __shared__ float sg[8][32 * LN_MAXC + 1];
-  __shared__ float sb[8][32 * LN_MAXC + 1];
+  __shared__ float sg[WARPS][32 * MAXC + 1];
+  __shared__ float sb[WARPS][32 * MAXC + 1];
 #pragma unroll
-  for (int j = 0; j < LN_MAXC; ++j) { sg[warp_in_cta][lane + 32 * j] = ag[j]; sb[warp_in_cta][lane + 32 * j] = ab[j]; }
+  for (int j = 0; j < MAXC; ++j) { sg[warp_in_cta][lane + 32 * j] = ag[j]; sb[warp_in_cta][lane + 32 * j] = ab[j]; }
   __syncthreads();
-  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+  for (int c = threadIdx.x; c < F; c += THREADS) {
     float g = 0.f, bb = 0.f;
-    for (int w = 0; w < 8; ++w) { g += sg[w][c]; bb += sb[w][c]; }
+    for (int w = 0; w < WARPS; ++w) { g += sg[w][c]; bb += sb[w][c]; }
     if (dgamma) atomicAdd(dgamma + c, g);
     if (dbeta) atomicAdd(dbeta + c, bb);
   }
@@ -101,10 +109,16 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, con
 RIH_API int rih_layernorm_bwd(const float* dy, int lddy, const float* a, int lda, const float* b, int ldb,
                               const float* gamma, const float* beta, const float* mean, const float* rstd,
                               float* dx, int lddx, int dx_acc, float* dgamma, float* dbeta, int M, int F, int relu, cudaStream_t s) {
-  RIH_REQUIRE(F <= 32 * LN_MAXC, "layernorm_bwd: F=%d exceeds %d", F, 32 * LN_MAXC);
+  RIH_REQUIRE(F <= 512, "layernorm_bwd: F=%d exceeds 512", F);
   if (M == 0) return 0;
-  int grid = min(148 * 2, cdiv(M, 8));
-  layernorm_bwd_kernel<<<grid, 256, 0, s>>>(dy, lddy, a, lda, b, ldb, gamma, beta, mean, rstd, dx, lddx, dx_acc, dgamma, dbeta, M, F, relu);
+#define RIH_LN_BWD(MC, TH)                                                                                                        \
+  layernorm_bwd_kernel<MC, TH><<<min(148 * (1024 / TH), cdiv(M, TH / 32)), TH, 0, s>>>(dy, lddy, a, lda, b, ldb, gamma, beta, mean, rstd, dx, lddx, dx_acc, \
+                                                                                      dgamma, dbeta, M, F, relu)
+  if (F <= 64) RIH_LN_BWD(2, 1024);
+  else if (F <= 128) RIH_LN_BWD(4, 1024);
+  else if (F <= 256) RIH_LN_BWD(8, 512);
+  else RIH_LN_BWD(16, 256);
+#undef RIH_LN_BWD
   return check_launch("layernorm_bwd");
 }
 

@@ -625,10 +625,11 @@ class decoder(nn.Module):
 
         scale, trans2d, verts3d, verts2d = {}, {}, {}, {}
         result = {'verts3d': {}, 'verts2d': {}}
-        for side, f in (('left', Lf), ('right', Rf)):
-            s, t, v3c, v2c, v3, v2 = ops.decoder_tail(
-                f, self.avg_head.weight.view(-1), self.avg_head.bias, self.params_head.weight, self.params_head.bias,
-                self.coord_head.weight, self.coord_head.bias, self.unsample_layer.weight, B, self.vNum_out, float(IMG_SIZE))
+        def tail(f):
+            return ops.decoder_tail(f, self.avg_head.weight.view(-1), self.avg_head.bias, self.params_head.weight, self.params_head.bias,
+                                    self.coord_head.weight, self.coord_head.bias, self.unsample_layer.weight, B, self.vNum_out, float(IMG_SIZE))
+        tails = run_hands(Lf.device, lambda: tail(Lf), lambda: tail(Rf))
+        for side, (s, t, v3c, v2c, v3, v2) in zip(('left', 'right'), tails):
             scale[side], trans2d[side] = s, t
             verts3d[side], verts2d[side] = v3c, v2c
             result['verts3d'][side], result['verts2d'][side] = v3, v2
