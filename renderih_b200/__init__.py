@@ -3,6 +3,8 @@
 Public API mirrors the reference modules it replaces:
     load_model(cfg) / HandNET_GCN      <-  models/model.py:18-60
     ManoLayer, rodrigues_batch          <-  models/manolayer.py:32-48,100-322
+    load_graph_model(cfg)               <-  common/myhand/lijun_model_graph.py:37-70 (the trainers' default model)
+    preprocess_u8(frames, flip)         <-  core/loader.py:151-152,178-181 (host image ops of the loader, on the GPU)
 """
 from . import _build
 
@@ -19,6 +21,12 @@ def __getattr__(name):
     if name in ('ManoLayer', 'rodrigues_batch'):
         from . import manolayer
         return getattr(manolayer, name)
+    if name == 'load_graph_model':
+        from . import myhand
+        return myhand.load_graph_model
+    if name == 'preprocess_u8':
+        from . import input as _input
+        return _input.preprocess_u8
     if name in ('load_cfg', 'get_cfg_defaults'):
         from . import config
         return getattr(config, name)

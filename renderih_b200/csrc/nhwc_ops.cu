@@ -789,3 +789,33 @@ RIH_API int rih_im2col(const float* x, int ldx, float* A, int N, int H, int W, i
   else im2col_kernel<0, 0, 0><<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
   return check_launch("im2col");
 }
+
+// ============================================================== input pipeline on the GPU
+// uint8 HWC BGR frames (what cv.imread / the reference's datasets hold) -> normalised float32 NCHW RGB network input, with the optional
+// horizontal flip of the augmentation: the per-sample host work of core/loader.py:151-152 (cv.flip), :178-181 (cv.cvtColor BGR2RGB,
+// / 255, permute(2,0,1), transforms.Normalize(mean, std)).  Same operation order (divide by 255, subtract mean, divide by std) so the
+// result is bit-identical to the torch / torchvision ops; the host -> device copy shrinks 4x (uint8 instead of float32).
+__global__ void preprocess_u8_kernel(const unsigned char* __restrict__ src, const unsigned char* __restrict__ flip, float* __restrict__ dst,
+                                     int B, int H, int W, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const long long total = (long long)B * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W); const long long t = i / W; const int y = (int)(t % H); const int b = (int)(t / H);
+    const int sx = (flip && flip[b]) ? (W - 1 - x) : x;
+    const unsigned char* p = src + (((size_t)b * H + y) * W + sx) * 3;
+    const float bl = (float)p[0] / 255.f, gr = (float)p[1] / 255.f, rd = (float)p[2] / 255.f;
+    float* o = dst + (size_t)b * 3 * H * W + (size_t)y * W + x;
+    o[0] = (rd - m0) / s0;
+    o[(size_t)H * W] = (gr - m1) / s1;
+    o[2 * (size_t)H * W] = (bl - m2) / s2;
+  }
+}
+// src: [B,H,W,3] uint8 BGR; flip: [B] uint8 flags or NULL; dst: [B,3,H,W] float32 RGB, (x/255 - mean[c]) / std[c]
+RIH_API int rih_preprocess_u8(const unsigned char* src, const unsigned char* flip, float* dst, int B, int H, int W,
+                              const float* mean3_host, const float* std3_host, cudaStream_t s) {
+  RIH_REQUIRE(B >= 0 && H > 0 && W > 0, "preprocess_u8: bad shape");
+  const long long total = (long long)B * H * W;
+  if (total == 0) return 0;
+  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  preprocess_u8_kernel<<<grid, 256, 0, s>>>(src, flip, dst, B, H, W, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1], std3_host[2]);
+  return check_launch("preprocess_u8");
+}

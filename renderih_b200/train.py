@@ -15,6 +15,17 @@ from ._lib import call
 from . import ops
 
 
+def lr_at_epoch(epoch, base_lr, init_lr=None, warm_up_epoch=3, gamma=0.1, step_size=80, min_thres=0.05):
+    """Learning rate of the reference's `StepLR_withWarmUp` (utils/lr_sc.py:159-175) at `epoch` (= the scheduler's `last_epoch`):
+    linear warm-up from init_lr (the trainer passes 1e-2 * LR, core/lijun_trainer.py:147-153) over `warm_up_epoch` epochs, then
+    base_lr * max(gamma ** ((epoch - warm_up) // step_size), min_thres)."""
+    if init_lr is None:
+        init_lr = 1e-2 * base_lr
+    if epoch < warm_up_epoch:
+        return init_lr + (base_lr - init_lr) * (epoch / warm_up_epoch)
+    return base_lr * max(gamma ** ((epoch - warm_up_epoch) // step_size), min_thres)
+
+
 class FlatParams:
     """Re-home the given parameters (and their .grad) into flat contiguous buffers, preserving each tensor's strides
     (conv weights stay channels_last)."""
@@ -84,12 +95,22 @@ class TrainStep:
     def __init__(self, model, loss_fn, example_img, lr=3e-4, weight_decay=1e-2, use_graph=True, group=None):
         self.model, self.loss_fn, self.group = model, loss_fn, group
         self.lr, self.wd = lr, weight_decay
+        self.base_lr = lr
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.flatp = FlatParams(trainable_used_params(model, loss_fn, example_img))
         self.static_img = example_img.clone()
         self.graph = None
         self.loss = None
         self.use_graph = use_graph
+
+    def set_epoch(self, epoch, cfg=None, **kw):
+        """Learning-rate schedule of the reference trainer: the fused AdamW kernel takes the rate as a launch argument
+        (it runs outside the captured graph), so the schedule costs nothing per step."""
+        if cfg is not None:
+            kw = dict(warm_up_epoch=cfg.TRAIN.warm_up, gamma=cfg.TRAIN.lr_decay_gamma, step_size=cfg.TRAIN.lr_decay_step, **kw)
+            self.base_lr = cfg.TRAIN.LR
+        self.lr = lr_at_epoch(epoch, getattr(self, 'base_lr', self.lr), **kw)
+        return self.lr
 
     def _step_body(self):
         self.flatp.zero_grad()

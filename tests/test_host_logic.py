@@ -134,3 +134,15 @@ def test_flat_gradient_allreduce_two_ranks_gloo():
     l1, r1 = out[1]
     assert torch.allclose(r0, l0 + l1) and torch.allclose(r1, l0 + l1)
     assert not torch.allclose(l0, l1)
+
+
+def test_lr_schedule_matches_reference_scheduler():
+    """`lr_at_epoch` against the learning rates the reference's own StepLR_withWarmUp produced (tests/golden/lr_schedule.json, generated
+    by stepping the unmodified utils/lr_sc.py scheduler 300 times with the trainer's arguments, core/lijun_trainer.py:147-153)."""
+    import json
+    from renderih_b200.train import lr_at_epoch
+    g = json.load(open(os.path.join(GOLD, 'lr_schedule.json')))
+    for i, ref in enumerate(g['lrs']):
+        mine = lr_at_epoch(i + 1, g['base_lr'], init_lr=g['init_lr'], warm_up_epoch=g['warm_up_epoch'], gamma=g['gamma'],
+                           step_size=g['step_size'], min_thres=g['min_thres'])
+        assert abs(mine - ref) <= 1e-12 + 1e-9 * ref, (i + 1, mine, ref)

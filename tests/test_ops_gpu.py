@@ -552,3 +552,29 @@ def test_gemm_wide_tiles_match_narrow(nsplit):
     ref = F.relu(a.double() @ b.double().t() + bias.double())
     assert rel(outs[0], ref) < (3e-3 if nsplit == 1 else 2e-5)
     assert rel(outs[0], outs[1]) < 1e-6
+
+
+def test_preprocess_u8_matches_reference_loader_ops():
+    """GPU input kernel against the exact host ops of core/loader.py:151-152,178-181 (cv.flip, cv.cvtColor BGR2RGB, /255, permute,
+    torchvision Normalize): bit-identical."""
+    import numpy as np
+    import cv2 as cv
+    from torchvision import transforms
+    from renderih_b200.input import preprocess_u8
+    rng = np.random.RandomState(0)
+    imgs = rng.randint(0, 256, size=(5, 64, 48, 3), dtype=np.uint8)
+    flips = [False, True, False, True, True]
+    norm = transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+    ref = []
+    for img, f in zip(imgs, flips):
+        if f:
+            img = cv.flip(img, 1)
+        t = torch.tensor(cv.cvtColor(img, cv.COLOR_BGR2RGB), dtype=torch.float32) / 255
+        ref.append(norm(t.permute(2, 0, 1)))
+    ref = torch.stack(ref)
+    out = preprocess_u8(torch.from_numpy(imgs).cuda(), flip=torch.tensor(flips))
+    assert out.shape == ref.shape and torch.equal(out.cpu(), ref)
+    out2 = preprocess_u8(torch.from_numpy(imgs).cuda())
+    assert torch.equal(out2[0].cpu(), ref[0]) and not torch.equal(out2[1].cpu(), ref[1])
+    with pytest.raises(RuntimeError):
+        preprocess_u8(torch.from_numpy(imgs))
