@@ -263,13 +263,23 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, cons
     }
     float xv[4] = {x4.x, x4.y, x4.z, x4.w};
     float o[4];
+    const float4 rs4 = *reinterpret_cast<const float4*>(rstd + c), ga4 = *reinterpret_cast<const float4*>(gamma + c);
+    const float rsv[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, gav[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+    float muv[4] = {0.f, 0.f, 0.f, 0.f}, sgv[4] = {0.f, 0.f, 0.f, 0.f}, sxv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (training) {
+      const float4 mu4 = *reinterpret_cast<const float4*>(mean + c), sg4 = *reinterpret_cast<const float4*>(sum_g + c),
+                   sx4 = *reinterpret_cast<const float4*>(sum_gx + c);
+      muv[0] = mu4.x; muv[1] = mu4.y; muv[2] = mu4.z; muv[3] = mu4.w;
+      sgv[0] = sg4.x; sgv[1] = sg4.y; sgv[2] = sg4.z; sgv[3] = sg4.w;
+      sxv[0] = sx4.x; sxv[1] = sx4.y; sxv[2] = sx4.z; sxv[3] = sx4.w;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float rs = rstd[c + j], ga = gamma[c + j];
+      const float rs = rsv[j], ga = gav[j];
       float t;
       if (training) {
-        float xh = (xv[j] - mean[c + j]) * rs;
-        t = ga * rs * (g[j] - sum_g[c + j] * invM - xh * sum_gx[c + j] * invM);
+        float xh = (xv[j] - muv[j]) * rs;
+        t = ga * rs * (g[j] - sgv[j] * invM - xh * sxv[j] * invM);
       } else {
         t = ga * rs * g[j];
       }

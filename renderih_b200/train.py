@@ -98,6 +98,10 @@ class TrainStep:
         self.base_lr = lr
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.flatp = FlatParams(trainable_used_params(model, loss_fn, example_img))
+        try:      # the two decoder streams make some AccumulateGrad nodes run on a side stream; torch's advisory warning is expected here
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except Exception:
+            pass
         self.static_img = example_img.clone()
         self.graph = None
         self.loss = None
