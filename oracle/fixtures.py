@@ -84,3 +84,52 @@ def make_mano_loss_weights(batch, seed=SEED):
     """Fixed random cotangents for ManoLayer gradient checks: loss = <v, wv> + <j, wj>."""
     g = torch.Generator().manual_seed(seed + 3)
     return torch.randn(batch, 778, 3, generator=g), torch.randn(batch, 21, 3, generator=g)
+
+
+def add_mano_assets(prepared, mano_left, mano_right):
+    """MANO tables the 'newgraph' tail needs (oracle/model_ref.newgraph_tail): raw dicts with the left-hand shapedirs flip of
+    decoder_lijun_mano.py:171-173 applied, and the 21-joint regressor of common/utils/mano.py:48-79 (tips 745/317/445/556/673)."""
+    out = dict(prepared)
+    dicts = {'left': dict(mano_left), 'right': dict(mano_right)}
+    sl, sr = np.asarray(dicts['left']['shapedirs'], np.float32), np.asarray(dicts['right']['shapedirs'], np.float32)
+    if np.abs(sl[:, 0, :] - sr[:, 0, :]).sum() < 1:
+        sl = sl.copy(); sl[:, 0, :] *= -1
+        dicts['left']['shapedirs'] = sl
+    jr21 = {}
+    for side, m in dicts.items():
+        jr = m['J_regressor']
+        jr = np.asarray(jr.todense()) if hasattr(jr, 'todense') else np.asarray(jr)
+        tips = np.zeros((5, jr.shape[1]), np.float32)
+        for i, v in enumerate((745, 317, 445, 556, 673)):
+            tips[i, v] = 1.0
+        jr = np.concatenate((jr.astype(np.float32), tips))[[0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20]]
+        jr21[side] = torch.from_numpy(jr)
+    out['mano'], out['mano_jr21'] = dicts, jr21
+    return out
+
+
+def make_newgraph_cotangents(batch, seed=SEED):
+    """Fixed random cotangents for the 'newgraph' outputs: loss = sum_k <out_k, w_k> (the reference's mano_loss_GCN is not importable here)."""
+    g = torch.Generator().manual_seed(seed + 4)
+    r = lambda *s: torch.randn(*s, generator=g)
+    return {'verts3d_left': r(batch, 778, 3), 'verts3d_right': r(batch, 778, 3), 'verts2d_left': r(batch, 778, 2) * 0.01,
+            'verts2d_right': r(batch, 778, 2) * 0.01, 'mano_pose_left': r(batch, 48), 'mano_pose_right': r(batch, 48),
+            'mano_shape_left': r(batch, 10), 'mano_shape_right': r(batch, 10), 'joints3d_left': r(batch, 21, 3), 'joints3d_right': r(batch, 21, 3),
+            'root_rel': r(batch, 3), 'v3c_left': r(batch, 252, 3), 'v3c_right': r(batch, 252, 3)}
+
+
+def flat_newgraph(out):
+    result, params, hlist, other = out
+    d = {'root_rel': other['root_rel'], 'length': other['length'], 'v3d_left': result['v3d_left'], 'v3d_right': result['v3d_right']}
+    for side in ('left', 'right'):
+        d['verts3d_' + side] = result['verts3d'][side]; d['verts2d_' + side] = result['verts2d'][side]
+        d['scale_' + side] = params['scale'][side]; d['trans2d_' + side] = params['trans2d'][side]
+        d['scalelength_' + side] = params['scalelength_' + side]
+        d['v3c_' + side] = hlist[0]['verts3d'][side]; d['v2c_' + side] = hlist[0]['verts2d'][side]
+        for k in ('joints3d', 'mano_pose', 'mano_shape'):
+            d[k + '_' + side] = other['verts3d_MANO_list'][side][k]
+    return d
+
+
+def newgraph_loss(flat, cot):
+    return sum((flat[k] * w.to(flat[k].device, flat[k].dtype)).sum() for k, w in cot.items())

@@ -161,8 +161,41 @@ def mano_grad_golden(ns, tmp):
     print('mano gradient golden: %d cases' % len(out['cases']))
 
 
+def newgraph_golden(ns, tmp):
+    """'newgraph' variant (common/myhand/lijun_model_newgraph.load_new_model: graph decoder + ParamRegressor + MANO tail), eval forward and
+    train forward/backward under a fixed linear functional of the outputs (the reference's mano_loss_GCN is not importable here)."""
+    ref, _ = rb.build_reference_myhand_model(tmp, 'newgraph', dropout=0.0)
+    sd = fixtures.init_state_dict(ref.state_dict())
+    ref.load_state_dict(sd)
+    B = 2
+    img = fixtures.make_image(B)
+    with ref._rih_cpu_shims():
+        ref.eval()
+        with torch.no_grad():
+            out_eval = {k: v.detach().clone() for k, v in fixtures.flat_newgraph(ref(img)).items()}
+        ref.train()
+        for p in ref.parameters():
+            p.requires_grad_(True)
+        ref.decoder.unsample_layer.weight.requires_grad_(False)
+        fo = fixtures.flat_newgraph(ref(img))
+        loss = fixtures.newgraph_loss(fo, fixtures.make_newgraph_cotangents(B))
+        loss.backward()
+    grads = {}
+    for k, p in ref.named_parameters():
+        if p.grad is None:
+            continue
+        grads[k] = {'norm': float(p.grad.norm()), 'sum': float(p.grad.sum())}
+        if p.grad.numel() <= 4096:
+            grads[k]['full'] = p.grad.detach().clone()
+    gold = {'weights_sha256': fixtures.checksum(sd), 'batch': B, 'seed': fixtures.SEED, 'torch': torch.__version__, 'eval': out_eval,
+            'train': {'out': {k: v.detach().clone() for k, v in fo.items()}, 'loss': float(loss), 'grads': grads,
+                      'no_grad_keys': [k for k, p in ref.named_parameters() if p.grad is None]}}
+    torch.save(gold, os.path.join(GOLD, 'model_newgraph_synth_b2.pt'))
+    print('newgraph golden: loss %.6f, %d grads, %d keys' % (float(loss), len(grads), len(sd)))
+
+
 def main(which):
-    """which: any of 'resnet50', 'hrnet48', 'graph', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
+    """which: any of 'resnet50', 'hrnet48', 'graph', 'newgraph', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
     os.makedirs(GOLD, exist_ok=True)
     ns = rb.import_reference()
     with tempfile.TemporaryDirectory() as tmp:
@@ -173,6 +206,8 @@ def main(which):
             model_golden(ns, tmp, 'hrnet48', 'model_hrnet48_synth_b2.pt', 'hrnet')
         if 'graph' in which:       # common/myhand/lijun_model_graph.load_graph_model
             model_golden(ns, tmp, 'graph', 'model_graph_synth_b2.pt', 'resnet')
+        if 'newgraph' in which:    # SURVEY 8(f) row 1, MANO tail
+            newgraph_golden(ns, tmp)
         if 'mano' in which:
             mano_golden(ns, tmp)
         if 'mano_grad' in which:
@@ -180,4 +215,4 @@ def main(which):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'graph', 'mano', 'mano_grad'])
+    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'graph', 'newgraph', 'mano', 'mano_grad'])

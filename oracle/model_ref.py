@@ -384,13 +384,105 @@ def decoder_forward(sd, A, gf, fmaps, p, tr, variant='intaghand'):
     return result, {'scale': scale, 'trans2d': trans2d}, [{'verts3d': v3, 'verts2d': v2}], other
 
 
+# ---------------------------------------------------------------- 'newgraph' MANO tail: common/myhand/decoder_lijun_mano.py:26-58, 238-305
+def _mlp_hardswish(x, sd, pre, n_lin, act_final):
+    """make_linear_layers (decoder_lijun_mano.py:70-81): Linear (+ Hardswish except, optionally, after the last)"""
+    idx = 0
+    for i in range(n_lin):
+        x = _lin(x, sd, '%s.%d' % (pre, idx))
+        idx += 1
+        if i < n_lin - 1 or act_final:
+            x = F.hardswish(x)
+            idx += 1
+    return x
+
+
+def rot6d_to_rotmat(x):
+    """ParamRegressor.rot6d_to_rotmat, decoder_lijun_mano.py:36-43"""
+    x = x.view(-1, 3, 2)
+    a1, a2 = x[:, :, 0], x[:, :, 1]
+    b1 = F.normalize(a1)
+    b2 = F.normalize(a2 - torch.einsum('bi,bi->b', b1, a2).unsqueeze(-1) * b1)
+    return torch.stack((b1, b2, torch.linalg.cross(b1, b2, dim=-1)), dim=-1)
+
+
+def rotation_matrix_to_angle_axis(R):
+    """common/myhand/utils/comm.py:176-200 (3x3 input path) = rotation_matrix_to_quaternion (:250-324) then quaternion_to_angle_axis (:203-247)"""
+    rt = R.transpose(1, 2)
+    m22 = rt[:, 2, 2] < 1e-6
+    m01 = rt[:, 0, 0] > rt[:, 1, 1]
+    m0n1 = rt[:, 0, 0] < -rt[:, 1, 1]
+    t = [1 + rt[:, 0, 0] - rt[:, 1, 1] - rt[:, 2, 2], 1 - rt[:, 0, 0] + rt[:, 1, 1] - rt[:, 2, 2],
+         1 - rt[:, 0, 0] - rt[:, 1, 1] + rt[:, 2, 2], 1 + rt[:, 0, 0] + rt[:, 1, 1] + rt[:, 2, 2]]
+    q = [torch.stack([rt[:, 1, 2] - rt[:, 2, 1], t[0], rt[:, 0, 1] + rt[:, 1, 0], rt[:, 2, 0] + rt[:, 0, 2]], -1),
+         torch.stack([rt[:, 2, 0] - rt[:, 0, 2], rt[:, 0, 1] + rt[:, 1, 0], t[1], rt[:, 1, 2] + rt[:, 2, 1]], -1),
+         torch.stack([rt[:, 0, 1] - rt[:, 1, 0], rt[:, 2, 0] + rt[:, 0, 2], rt[:, 1, 2] + rt[:, 2, 1], t[2]], -1),
+         torch.stack([t[3], rt[:, 1, 2] - rt[:, 2, 1], rt[:, 2, 0] - rt[:, 0, 2], rt[:, 0, 1] - rt[:, 1, 0]], -1)]
+    masks = [m22 & m01, m22 & ~m01, ~m22 & m0n1, ~m22 & ~m0n1]
+    masks = [mk.view(-1, 1).type_as(q[0]) for mk in masks]
+    quat = sum(qi * mk for qi, mk in zip(q, masks))
+    quat = quat / torch.sqrt(sum(ti.view(-1, 1) * mk for ti, mk in zip(t, masks))) * 0.5
+    v = quat[:, 1:]
+    sin2 = (v * v).sum(-1)
+    sin_t, cos_t = torch.sqrt(sin2), quat[:, 0]
+    two_theta = 2.0 * torch.where(cos_t < 0.0, torch.atan2(-sin_t, -cos_t), torch.atan2(sin_t, cos_t))
+    k = torch.where(sin2 > 0.0, two_theta / sin_t, 2.0 * torch.ones_like(sin_t))
+    aa = v * k.unsqueeze(-1)
+    return torch.where(torch.isnan(aa), torch.zeros_like(aa), aa)
+
+
+def _rodrigues_t(axis):
+    """rodrigues_batch, common/utils/manolayer.py:32-48"""
+    angle = torch.norm(axis, p=2, dim=1, keepdim=True) + 1e-8
+    u = axis / angle
+    L = torch.zeros((axis.shape[0], 3, 3), dtype=axis.dtype)
+    L[:, 2, 1] = u[:, 0]; L[:, 1, 2] = -u[:, 0]
+    L[:, 0, 2] = u[:, 1]; L[:, 2, 0] = -u[:, 1]
+    L[:, 1, 0] = u[:, 2]; L[:, 0, 1] = -u[:, 2]
+    return torch.eye(3, dtype=axis.dtype)[None] + torch.sin(angle)[..., None] * L + (1 - torch.cos(angle))[..., None] * L.bmm(L)
+
+
+def newgraph_tail(sd, A, base_out, img_size=IMG_SIZE):
+    """decoder.forward of the 'newgraph' variant after the shared graph part, decoder_lijun_mano.py:238-305.  A['mano'][side]: MANO dict
+    (left shapedirs already flipped as in :171-173); A['mano_jr21'][side]: MANO.joint_regressor_torch (common/utils/mano.py:48-79)."""
+    from . import mano_ref
+    res0, params, hlist, _ = base_out
+    scale, trans2d = params['scale'], params['trans2d']
+    up = res0['verts3d']
+    result = {'verts3d': {}, 'verts2d': {}, 'v3d_left': up['left'], 'v3d_right': up['right']}
+    j3d = {s: torch.einsum('bik,ji->bjk', up[s], A['mano_jr21'][s]) for s in ('left', 'right')}
+    root_rel = j3d['right'][:, 0] - j3d['left'][:, 0]
+    pred, sl = {}, {}
+    for s in ('left', 'right'):
+        B = up[s].shape[0]
+        feat = _mlp_hardswish(up[s].reshape(B, -1), sd, 'decoder.param_regressor.fc', 2, True)
+        rotmat = rot6d_to_rotmat(_mlp_hardswish(feat, sd, 'decoder.param_regressor.fc_pose', 2, False))
+        pose = rotation_matrix_to_angle_axis(rotmat).reshape(B, -1)
+        shape = torch.tanh(_mlp_hardswish(feat, sd, 'decoder.param_regressor.fc_shape', 2, False)) * 3
+        v, j = mano_ref.mano_forward_torch(A['mano'][s], _rodrigues_t(pose[:, :3]), pose[:, 3:], shape, use_pca=True, center_idx=None)
+        v, j = v * 1000 / 1000, j * 1000 / 1000                                  # common/utils/manolayer.py:323-325 then :255-256
+        v = v - j[:, 0:1]
+        sl[s] = (0.095 / torch.linalg.norm(j[:, 9:10] - j[:, 0:1], dim=-1)).reshape(-1, 1, 1)
+        v = v * sl[s]
+        pred[s] = {'verts3d': v, 'joints3d': j, 'mano_pose': pose, 'mano_shape': shape}
+        result['verts2d'][s] = projection_batch(scale[s], trans2d[s], v, img_size)
+    result['verts3d']['left'] = pred['left']['verts3d']
+    result['verts3d']['right'] = pred['right']['verts3d'] + root_rel.reshape(-1, 1, 3)
+    other = {'length': (sl['left'] + sl['right']) / 2, 'root_rel': root_rel, 'verts3d_MANO_list': pred, 'verts2d_MANO_list': {'left': [], 'right': []}}
+    params = {'scale': scale, 'trans2d': trans2d, 'scalelength_left': sl['left'], 'scalelength_right': sl['right'], 'root_rel': root_rel}
+    return result, params, hlist, other
+
+
 def model_forward(sd, assets_prepared, img, training=False, dropout=0.0):
     """HandNET_GCN.forward, models/model.py:25-37.  `sd` maps reference state_dict keys to tensors (BN running
     statistics are updated in place when training=True, exactly like nn.BatchNorm2d)."""
     if 'encoder.resnet.conv1.weight' in sd and 'encoder.hms_decoder.final_layer.weight' not in sd:
         # the common/myhand "graph" model (lijun_model_graph.py:27-34): trunk -> mid -> decoder, no auxiliary maps
         gf, fmaps = graph_mid_forward(sd, resnet_trunk(sd, img, training), training)
-        return decoder_forward(sd, assets_prepared, gf, fmaps, dropout, training, variant='graph')
+        out = decoder_forward(sd, assets_prepared, gf, fmaps, dropout, training, variant='graph')
+        if 'decoder.param_regressor.fc.0.weight' in sd:      # 'newgraph': lijun_model_newgraph.py + decoder_lijun_mano.py
+            out = newgraph_tail(sd, assets_prepared, out)
+        return out
     if 'encoder.hrnet.conv1.weight' in sd:      # ENCODER_TYPE: hrnet* (models/encoder.py:365-372)
         hms, mask, dp, img_f, _, _ = hrnet_encoder_forward(sd, img, training)
         gf, fmaps = hrnet_mid_forward(sd, img_f, training)

@@ -323,6 +323,14 @@ def build_reference_myhand_model(asset_dir, variant='graph', dropout=0.05, mano_
         if variant == 'graph':
             import common.myhand.lijun_model_graph as mod
             import common.myhand.decoder_lijun_graph as dec
+            loader = 'load_graph_model'
+        elif variant == 'newgraph':      # lijun_model_newgraph.load_new_model + decoder_lijun_mano (MANO tail)
+            import common.myhand.lijun_model_newgraph as mod
+            import common.myhand.decoder_lijun_mano as dec
+            loader = 'load_new_model'
+            main_config.cfg.mano_flag = True
+            if not hasattr(main_config.cfg, 'reverse'):
+                main_config.cfg.reverse = False
         else:
             raise ValueError(variant)
         dec.get_graph_dict_path = lambda: paths
@@ -331,5 +339,6 @@ def build_reference_myhand_model(asset_dir, variant='graph', dropout=0.05, mano_
         cfg = mod.load_cfg()
         cfg.TRAIN.dropout = dropout
         cfg.MODEL_PARAM.MODEL_PRETRAIN_PATH = '__none__'
-        model = mod.load_graph_model(cfg)
+        model = getattr(mod, loader)(cfg)
+    model._rih_cpu_shims = shims          # the 'newgraph' forward calls .cuda() too (decoder_lijun_mano.py:51): run it under `with model._rih_cpu_shims():`
     return model, cfg

@@ -31,8 +31,10 @@ def rodrigues_batch(axis):
 
 
 class ManoLayer(Module):
-    def __init__(self, manoPath, center_idx=9, use_pca=True, new_skel=False, device=None):
+    def __init__(self, manoPath, center_idx=9, use_pca=True, new_skel=False, device=None, out_scale=None):
         super().__init__()
+        # out_scale = 1000: the `common/utils/manolayer.py` copy of this layer converts its outputs to millimetres (lines 323-325)
+        self.out_scale = out_scale
         self.center_idx = center_idx
         self.use_pca = use_pca
         self.new_skel = new_skel
@@ -150,6 +152,8 @@ class ManoLayer(Module):
             assert tuple(P.shape[1:]) == (15, 3, 3)
         assert S.shape == (bs, 10)
         v, j = _ManoFn.apply(self, R, P, S, T, C)
+        if self.out_scale is not None:
+            v, j = v * self.out_scale, j * self.out_scale
         if in_dev != dev:
             v, j = v.to(in_dev), j.to(in_dev)
         return v, j

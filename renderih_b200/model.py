@@ -225,6 +225,10 @@ class HandStreams:
         key = (device.type, device.index)
         if key not in cls._cache:
             cls._cache[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+            try:      # parameters shared by both hands accumulate gradients from two streams by design; silence torch's advisory
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            except Exception:
+                pass
         return cls._cache[key]
 
 

@@ -49,7 +49,7 @@ class MANO(nn.Module):
 
     def __init__(self, mano_dict):
         super().__init__()
-        self.layer = ManoLayer(mano_dict, center_idx=None)
+        self.layer = ManoLayer(mano_dict, center_idx=None, out_scale=1000.0)     # common/utils/manolayer.py: millimetres
         self.vertex_num, self.joint_num = 778, 21
         self.face = self.layer.faces
         jr = self.layer.J_regressor.numpy()
@@ -72,7 +72,11 @@ class decoder(_decoder_base):
         self.cfg = cfg
         self.mano = bool(getattr(cfg, 'mano_flag', False))
         if self.mano:
-            raise NotImplementedError('mano_flag=True (ParamRegressor tail of decoder_lijun_graph.py:226) is not built yet; see DESIGN.md "next"')
+            raise NotImplementedError('decoder_lijun_graph with mano_flag=True only adds an unused ParamRegressor (decoder_lijun_graph.py:226); '
+                                      'use load_new_model for the MANO tail')
+        self._init_mano(mano_left, mano_right)
+
+    def _init_mano(self, mano_left, mano_right):
         self.mano_left = MANO(mano_left)
         self.mano_left_layer = self.mano_left.layer
         self.mano_right = MANO(mano_right)
@@ -82,6 +86,122 @@ class decoder(_decoder_base):
         # decoder_lijun_graph.py:234-236: the released MANO_LEFT has a mirrored first shape direction
         if torch.sum(torch.abs(self.mano_left_layer.shapedirs[:, 0, :] - self.mano_right_layer.shapedirs[:, 0, :])) < 1:
             self.mano_left_layer.shapedirs[:, 0, :] *= -1
+
+
+def rot6d_to_rotmat(x):
+    """6-D rotation representation -> rotation matrices (Gram-Schmidt on the two 3-vectors interleaved in x), the construction used by
+    `ParamRegressor.rot6d_to_rotmat` (common/myhand/decoder_lijun_mano.py:36-43).  x: [N, 6] -> [N, 3, 3] with columns b1, b2, b3."""
+    x = x.reshape(-1, 3, 2)
+    a1, a2 = x[:, :, 0], x[:, :, 1]
+    b1 = torch.nn.functional.normalize(a1, dim=1)
+    b2 = torch.nn.functional.normalize(a2 - (b1 * a2).sum(dim=1, keepdim=True) * b1, dim=1)
+    b3 = torch.linalg.cross(b1, b2, dim=1)
+    return torch.stack((b1, b2, b3), dim=-1)
+
+
+def rotmat_to_axis_angle(R):
+    """Rotation matrices [N,3,3] -> axis-angle [N,3] through a unit quaternion, with the branch structure of the conversion the
+    reference calls (common/myhand/utils/comm.py:176-200 -> :250-324 matrix -> quaternion, :203-247 quaternion -> axis-angle):
+    the quaternion component with the largest magnitude is chosen by the signs / order of the diagonal, the angle is taken with atan2
+    on the half-angle sine / cosine (folded to the cos >= 0 half), NaNs (zero rotation) become 0."""
+    m = R.transpose(1, 2)               # the reference works on the transpose
+    d0, d1, d2 = m[:, 0, 0], m[:, 1, 1], m[:, 2, 2]
+    low = d2 < 1e-6
+    c0 = low & (d0 > d1)
+    c1 = low & ~(d0 > d1)
+    c2 = ~low & (d0 < -d1)
+    t = torch.where(c0, 1 + d0 - d1 - d2, torch.where(c1, 1 - d0 + d1 - d2, torch.where(c2, 1 - d0 - d1 + d2, 1 + d0 + d1 + d2)))
+    s01, s02, s12 = m[:, 0, 1] + m[:, 1, 0], m[:, 2, 0] + m[:, 0, 2], m[:, 1, 2] + m[:, 2, 1]
+    a01, a20, a12 = m[:, 0, 1] - m[:, 1, 0], m[:, 2, 0] - m[:, 0, 2], m[:, 1, 2] - m[:, 2, 1]
+    qa = torch.stack([a12, t, s01, s02], -1)       # x largest
+    qb = torch.stack([a20, s01, t, s12], -1)       # y largest
+    qc = torch.stack([a01, s02, s12, t], -1)       # z largest
+    qd = torch.stack([t, a12, a20, a01], -1)       # w largest
+    sel = lambda c: c[:, None]
+    q = torch.where(sel(c0), qa, torch.where(sel(c1), qb, torch.where(sel(c2), qc, qd)))
+    q = q / torch.sqrt(t)[:, None] * 0.5
+    w, v = q[:, 0], q[:, 1:]
+    sin2 = (v * v).sum(-1)
+    sin_h = torch.sqrt(sin2)
+    two_theta = 2.0 * torch.where(w < 0.0, torch.atan2(-sin_h, -w), torch.atan2(sin_h, w))
+    k = torch.where(sin2 > 0.0, two_theta / sin_h, torch.full_like(sin_h, 2.0))
+    aa = v * k[:, None]
+    return torch.where(torch.isnan(aa), torch.zeros_like(aa), aa)
+
+
+class ParamRegressor(nn.Module):
+    """common/myhand/decoder_lijun_mano.py:26-58: 2334 -> 1024 -> 512 trunk, two 512 -> 128 -> {96, 10} heads (Hardswish), 6-D rotations
+    of the 16 joints -> axis-angle.  The Linear layers run on the GEMM kernels; the activations and the rotation conversions are a few
+    torch elementwise ops on [B, <= 1024] tensors."""
+
+    def __init__(self, joint_num=778):
+        super().__init__()
+        self.joint_num = joint_num
+
+        def mlp(dims, act_final):
+            layers = []
+            for i in range(len(dims) - 1):
+                layers.append(nn.Linear(dims[i], dims[i + 1]))
+                if i < len(dims) - 2 or act_final:
+                    layers.append(nn.Hardswish(inplace=True))
+            return nn.Sequential(*layers)
+        self.fc = mlp([joint_num * 3, 1024, 512], True)
+        self.fc_pose = mlp([512, 128, 16 * 6], False)
+        self.fc_shape = mlp([512, 128, 10], False)
+
+    @staticmethod
+    def _run(seq, x):
+        for m in seq:
+            x = ops.linear(x, m.weight, m.bias) if isinstance(m, nn.Linear) else torch.nn.functional.hardswish(x)
+        return x
+
+    def forward(self, verts):
+        B = verts.shape[0]
+        feat = self._run(self.fc, verts.reshape(B, self.joint_num * 3))
+        rotmat = rot6d_to_rotmat(self._run(self.fc_pose, feat))
+        pose = rotmat_to_axis_angle(rotmat).reshape(B, -1)
+        return pose, self._run(self.fc_shape, feat), rotmat
+
+
+class decoder_mano(decoder):
+    """common/myhand/decoder_lijun_mano.py:81-305 ('newgraph'): the graph decoder followed by the MANO tail -- ParamRegressor on the
+    up-sampled 778-vertex mesh -> (pose, shape) -> ManoLayer (one fused kernel each way) -> root-centred, bone-length-normalised mesh."""
+
+    def __init__(self, cfg, mano_left, mano_right, **kw):
+        nn.Module.__init__(self)
+        _decoder_base.__init__(self, block_cls=MLP_GraphBlock, attn_variant='lijun', mano_lists=False, **kw)
+        self.cfg = cfg
+        self.mano = True
+        self.param_regressor = ParamRegressor(joint_num=778)
+        self._init_mano(mano_left, mano_right)
+
+    def forward(self, x, fmaps):
+        from .manolayer import rodrigues_batch
+        from .model import IMG_SIZE
+        res, paramsDict, handDictList, _ = _decoder_base.forward(self, x, fmaps)
+        scale, trans2d = paramsDict['scale'], paramsDict['trans2d']
+        up = {s: res['verts3d'][s] for s in ('left', 'right')}          # unsample_layer output (decoder_lijun_mano.py:243)
+        result = {'verts3d': {}, 'verts2d': {}, 'v3d_left': up['left'], 'v3d_right': up['right']}
+        j0 = {s: torch.einsum('bik,i->bk', up[s], getattr(self, 'mano_' + s).joint_regressor_torch[0]) for s in ('left', 'right')}
+        root_rel = j0['right'] - j0['left']                              # joint 0 of get_3d_joints (:244-246)
+        pred, sl = {}, {}
+        for s in ('left', 'right'):
+            pose, shape, _ = self.param_regressor(up[s])
+            shape = torch.tanh(shape) * 3
+            v, j = getattr(self, 'mano_%s_layer' % s)(rodrigues_batch(pose[:, :3]), pose[:, 3:], shape)     # millimetres
+            v, j = v / 1000, j / 1000
+            v = v - j[:, 0:1]
+            sl[s] = (0.095 / torch.linalg.norm(j[:, 9:10] - j[:, 0:1], dim=-1)).reshape(-1, 1, 1)           # bone-length rescale (:265-268)
+            v = v * sl[s]
+            pred[s] = {'verts3d': v, 'joints3d': j, 'mano_pose': pose, 'mano_shape': shape}
+            sc = (scale[s] * IMG_SIZE)[:, None, None]
+            result['verts2d'][s] = sc * v[..., :2] + (trans2d[s] * IMG_SIZE / 2 + IMG_SIZE / 2)[:, None]      # projection_batch
+        result['verts3d']['left'] = pred['left']['verts3d']
+        result['verts3d']['right'] = pred['right']['verts3d'] + root_rel.reshape(-1, 1, 3)
+        otherInfo = {'length': (sl['left'] + sl['right']) / 2, 'root_rel': root_rel,
+                     'verts3d_MANO_list': {'left': pred['left'], 'right': pred['right']}, 'verts2d_MANO_list': {'left': [], 'right': []}}
+        paramsDict = {'scale': scale, 'trans2d': trans2d, 'scalelength_left': sl['left'], 'scalelength_right': sl['right'], 'root_rel': root_rel}
+        return result, paramsDict, handDictList, otherInfo
 
 
 class HandNET_GCN(nn.Module):
@@ -108,7 +228,12 @@ class HandNET_GCN(nn.Module):
         return self.decoder(global_feature, fmaps)
 
 
-def load_graph_model(cfg=None, cliff=False, assets=None, mano_assets=None, asset_root=None):
+def load_new_model(cfg=None, cliff=False, assets=None, mano_assets=None, asset_root=None):
+    """`load_new_model(cfg)` of common/myhand/lijun_model_newgraph.py:34-71: the graph model with the MANO tail (decoder_lijun_mano)."""
+    return load_graph_model(cfg, cliff, assets, mano_assets, asset_root, decoder_cls=decoder_mano)
+
+
+def load_graph_model(cfg=None, cliff=False, assets=None, mano_assets=None, asset_root=None, decoder_cls=None):
     """`load_graph_model(cfg)` of common/myhand/lijun_model_graph.py:37-70.  cfg: path | CfgNode-like | None (defaults).
     assets / mano_assets: pre-loaded graph / MANO dictionaries (tests use synthetic ones); default = the reference's misc/ files."""
     if cfg is None or isinstance(cfg, str):
@@ -123,7 +248,7 @@ def load_graph_model(cfg=None, cliff=False, assets=None, mano_assets=None, asset
         root = asset_root or default_asset_root()
         mano_assets = {s: load_mano_dict(os.path.join(root, 'mano', 'MANO_%s.pkl' % s.upper())) for s in ('left', 'right')}
     info = mid.get_info()
-    dec = decoder(cfg, mano_assets['left'], mano_assets['right'],
+    dec = (decoder_cls or decoder)(cfg, mano_assets['left'], mano_assets['right'],
                   global_feature_dim=info['global_feature_dim'], f_in_Dim=info['fmaps_dim'], f_out_Dim=cfg.MODEL.IMG_DIMS,
                   gcn_in_dim=cfg.MODEL.GCN_IN_DIM, gcn_out_dim=cfg.MODEL.GCN_OUT_DIM, graph_k=cfg.MODEL.graph_k,
                   graph_layer_num=cfg.MODEL.graph_layer_num, vertex_num=778, dense_coor=a['dense_coor'],

@@ -132,3 +132,88 @@ def test_graph_variant_forward_backward_train(gold, setup):
             cos = float(F.cosine_similarity(mine.detach().cpu().flatten().double(), g['full'].flatten().double(), dim=0))
             assert cos > 0.995, (k, cos)
     print('graph variant train: worst grad-norm rel err vs fp64 %.2e at %s (reference fp32 median %.2e)' % (worst + (med,)))
+
+
+# ----------------------------------------------------------------------------- 'newgraph': graph decoder + ParamRegressor + MANO tail
+@pytest.fixture(scope='module')
+def ng():
+    from renderih_b200.myhand import load_new_model
+    gold = torch.load(os.path.join(GOLD, 'model_newgraph_synth_b2.pt'), weights_only=False)
+    a = rih_assets.synthetic_assets(0)
+    manos = {s: rih_assets.synthetic_mano(0, s) for s in ('left', 'right')}
+    model = load_new_model(None, assets=a, mano_assets=manos)
+    sd = fixtures.init_state_dict(model.state_dict())
+    assert fixtures.checksum(sd) == gold['weights_sha256']
+    model.load_state_dict(sd)
+    A = fixtures.add_mano_assets(model_ref.prepare_assets(a), manos['left'], manos['right'])
+    return gold, sd, model.cuda(), A
+
+
+def test_newgraph_forward_eval(ng):
+    """common/myhand/lijun_model_newgraph (decoder_lijun_mano.py): MANO pose / shape regression + fused ManoLayer kernel + bone-length
+    rescale.  Eval forward vs the reference golden: 5e-5 relative (the tail takes atan2 / normalisations of fp32 intermediates)."""
+    from renderih_b200 import ops
+    gold, sd, model, A = ng
+    model.eval()
+    with torch.no_grad():
+        out = fixtures.flat_newgraph(model(fixtures.make_image(2).cuda()))
+    errs = {k: rel_err(out[k], v) for k, v in gold['eval'].items()}
+    print('newgraph eval fwd rel errs vs reference golden:', {k: '%.2e' % e for k, e in errs.items()})
+    for k, e in errs.items():
+        assert out[k].shape == gold['eval'][k].shape and e < 5e-5, (k, e)
+    ops.set_gemm_mode('tf32c', 'tf32x3')
+    try:
+        with torch.no_grad():
+            out = fixtures.flat_newgraph(model(fixtures.make_image(2).cuda()))
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+    for k, v in gold['eval'].items():
+        assert rel_err(out[k], v) < 2e-2, ('tf32c/tf32x3', k, rel_err(out[k], v))
+
+
+def test_newgraph_forward_backward_train(ng):
+    """Gradients flow from the MANO outputs through the fused ManoLayer backward kernel, the rotation conversions and the ParamRegressor into
+    the graph decoder and the encoder.  Forward 5e-3 vs the reference golden; gradient norms vs the fp64 oracle, as close as the reference's
+    own fp32 run (3x its error + 2e-2), cf. tests/test_hrnet_gpu.py."""
+    gold, sd, model, A = ng
+    model.load_state_dict(sd)
+    model.train()
+    for m in model.modules():
+        if hasattr(m, 'p'):
+            m.p = 0.0
+    model.decoder.unsample_layer.weight.requires_grad_(False)
+    model.zero_grad()
+    cot = fixtures.make_newgraph_cotangents(2)
+    fo = fixtures.flat_newgraph(model(fixtures.make_image(2).cuda()))
+    loss = fixtures.newgraph_loss(fo, cot)
+    loss.backward()
+    for k, v in gold['train']['out'].items():
+        assert rel_err(fo[k], v) < TRAIN_FWD_TOL, ('train fwd', k, rel_err(fo[k], v))
+    params = dict(model.named_parameters())
+    for k in gold['train']['no_grad_keys']:
+        g = params[k].grad
+        assert g is None or float(g.abs().max()) == 0.0, k
+    # fp64 truth from the oracle
+    sd64 = {k: (v.clone().double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    for k, v in sd64.items():
+        if v.is_floating_point() and 'running_' not in k and '.mano_' not in k and k not in ('decoder.dense_coor', 'decoder.unsample_layer.weight'):
+            v.requires_grad_(True)
+    A64 = dict(A)
+    for side in ('left', 'right'):
+        A64[side] = dict(A[side]); A64[side]['L'] = [l.double() for l in A[side]['L']]
+    A64['mano_jr21'] = {s: t.double() for s, t in A['mano_jr21'].items()}
+    f64 = fixtures.flat_newgraph(model_ref.model_forward(sd64, A64, fixtures.make_image(2).double(), training=True, dropout=0.0))
+    fixtures.newgraph_loss(f64, cot).backward()
+    ref_err = {k: abs(g['norm'] - float(sd64[k].grad.norm())) / max(float(sd64[k].grad.norm()), 1e-9) for k, g in gold['train']['grads'].items()}
+    med = sorted(ref_err.values())[len(ref_err) // 2]
+    worst = (0.0, None)
+    for k, g in gold['train']['grads'].items():
+        mine = params[k].grad
+        assert mine is not None, k
+        if k.endswith('w_ks.bias'):
+            continue
+        n64 = float(sd64[k].grad.norm())
+        e = abs(float(mine.norm()) - n64) / max(n64, 1e-9)
+        worst = max(worst, (e, k))
+        assert e < 3 * max(ref_err[k], med) + GRAD_TOL, (k, e, ref_err[k])
+    print('newgraph train: worst grad-norm rel err vs fp64 %.2e at %s (reference fp32 median %.2e)' % (worst + (med,)))

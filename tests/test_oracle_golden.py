@@ -168,3 +168,45 @@ def test_mano_torch_oracle_gradients_match_reference_golden():
                 assert case[name] is None
                 continue
             assert rel_err(t.grad, case[name]) < 2e-5, (case['side'], c, name, rel_err(t.grad, case[name]))
+
+
+# ----------------------------------------------------------------------------- 'newgraph' variant (graph decoder + ParamRegressor + MANO tail)
+@pytest.fixture(scope='module')
+def newgraph_setup():
+    from renderih_b200.myhand import load_new_model
+    gold = torch.load(os.path.join(GOLD, 'model_newgraph_synth_b2.pt'), weights_only=False)
+    a = rih_assets.synthetic_assets(0)
+    manos = {s_: rih_assets.synthetic_mano(0, s_) for s_ in ('left', 'right')}
+    tmpl = load_new_model(None, assets=a, mano_assets=manos).state_dict()
+    sd = fixtures.init_state_dict(tmpl)
+    assert len(sd) == 1063 and fixtures.checksum(sd) == gold['weights_sha256'], 'state_dict keys / order / deterministic init drifted from the reference'
+    A = fixtures.add_mano_assets(model_ref.prepare_assets(a), manos['left'], manos['right'])
+    return gold, sd, A
+
+
+def test_newgraph_oracle_matches_reference_golden(newgraph_setup):
+    """oracle/model_ref.newgraph_tail (+ the differentiable MANO restatement) against the unmodified reference's load_new_model outputs
+    and gradients (built on the CPU through oracle/ref_bridge shims): forward 2e-5, loss 1e-5, gradient norms 2e-3."""
+    gold, sd0, A = newgraph_setup
+    with torch.no_grad():
+        out = fixtures.flat_newgraph(model_ref.model_forward({k: v.clone() for k, v in sd0.items()}, A, fixtures.make_image(2), training=False))
+    for k, v in gold['eval'].items():
+        assert out[k].shape == v.shape and rel_err(out[k], v) < RTOL, (k, rel_err(out[k], v))
+    sd = {k: v.clone() for k, v in sd0.items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and 'running_' not in k and '.mano_' not in k and k not in ('decoder.dense_coor', 'decoder.unsample_layer.weight'):
+            v.requires_grad_(True)
+    fo = fixtures.flat_newgraph(model_ref.model_forward(sd, A, fixtures.make_image(2), training=True, dropout=0.0))
+    for k, v in gold['train']['out'].items():
+        assert rel_err(fo[k], v) < RTOL, (k, rel_err(fo[k], v))
+    loss = fixtures.newgraph_loss(fo, fixtures.make_newgraph_cotangents(2))
+    assert abs(float(loss) - gold['train']['loss']) < 1e-5 * max(1.0, abs(gold['train']['loss'])) + 2e-3
+    loss.backward()
+    for k in gold['train']['no_grad_keys']:
+        assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+    for k, g in gold['train']['grads'].items():
+        mine = sd[k].grad
+        assert mine is not None, k
+        if k.endswith('w_ks.bias'):
+            continue
+        assert abs(float(mine.norm()) - g['norm']) / max(g['norm'], 1e-6) < 2e-3, (k, float(mine.norm()), g['norm'])
