@@ -90,6 +90,46 @@ def _gt(t):
     return grad
 
 
+# ----------------------------------------------------------------------------- weight gradients on a side stream
+# A weight-gradient GEMM (and the bias-gradient column sum) has no consumer until the optimizer: when it accumulates straight into the
+# flat gradient buffer it is issued on a side stream that forks off the stream running backward, so the (latency-bound) chain
+# dgrad -> previous layer's backward does not wait for it.  All side streams are joined into the caller's stream by an autograd-engine
+# final callback when the backward pass ends (under CUDA-graph capture the fork / join become parallel graph branches).
+# RIH_WGRAD_STREAM=0 disables it.
+_WG = {'streams': {}, 'armed': False, 'enabled': _os.environ.get('RIH_WGRAD_STREAM', '1') != '0'}
+
+
+def _wgrad_fork(*tensors):
+    """-> side stream handle (int) to launch on, or None when disabled.  `tensors` are the operands the side-stream kernels read:
+    they are registered with the caching allocator as in use on the side stream."""
+    if not _WG['enabled']:
+        return None
+    cur = torch.cuda.current_stream()
+    key = (cur.device.index, cur.cuda_stream)
+    st = _WG['streams'].get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=cur.device)
+        _WG['streams'][key] = st
+    st.wait_stream(cur)
+    _WG.setdefault('dirty', set()).add(key)
+    for t in tensors:
+        if t is not None:
+            t.record_stream(st)
+    if not _WG['armed']:
+        _WG['armed'] = True
+        torch.autograd.Variable._execution_engine.queue_callback(_wgrad_join)
+    return st.cuda_stream
+
+
+def _wgrad_join():
+    """Join only the side streams that forked during THIS backward pass (a stream that belongs to no running capture must not be waited
+    on from a capturing stream)."""
+    _WG['armed'] = False
+    dirty, _WG['dirty'] = _WG.get('dirty', set()), set()
+    for key in dirty:
+        torch.cuda.current_stream(key[0]).wait_stream(_WG['streams'][key])
+
+
 # ----------------------------------------------------------------------------- dropout seed (device resident)
 class _SeedState:
     """Device-resident base seed advanced once per step (so CUDA-graph replays draw fresh masks)."""
@@ -113,6 +153,8 @@ class _SeedState:
 
     def begin_forward(self):
         self.site = 0
+        _WG['armed'] = False      # a backward pass that raised may have left the join callback un-run
+        _WG['dirty'] = set()
 
     def next_site(self):
         self.site += 1
@@ -162,17 +204,21 @@ class LinearFn(Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), device=dy.device, dtype=torch.float32)
             call('rih_linear_dgrad', _p(g), _ld(g), _p(w), w.stride(0), _p(dx), K, M, N, K, 0, ctx.as_conv, s)
+        side = None
         if ctx.needs_input_grad[1]:
             tgt = _gt(w)
             if tgt is not None:
-                call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(tgt), w.stride(0), M, N, K, 1, ctx.as_conv, s)
+                side = _wgrad_fork(g, x)
+                call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(tgt), w.stride(0), M, N, K, 1, ctx.as_conv, side or s)
             else:
                 dw = torch.empty((N, K), device=dy.device, dtype=torch.float32)
                 call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(dw), K, M, N, K, 0, ctx.as_conv, s)
         if has_b and ctx.needs_input_grad[2]:
             tgt = _gt(ctx.bias_ref)
             if tgt is not None:
-                call('rih_colsum', _p(g), _ld(g), M, N, _p(tgt), 1, s)
+                if side is None:
+                    side = _wgrad_fork(g)
+                call('rih_colsum', _p(g), _ld(g), M, N, _p(tgt), 1, side or s)
             else:
                 db = torch.empty((N,), device=dy.device, dtype=torch.float32)
                 call('rih_colsum', _p(g), _ld(g), M, N, _p(db), 0, s)
@@ -571,7 +617,9 @@ class Conv2dFn(Function):
             g2, _, _ = _geom(N, H, W, Cin, Cout, R, S, stride, pad, _ld(x), _ld(dy))
             tgt = _gt(w)
             if tgt is not None:
-                call('rih_conv2d_wgrad', _p(dy), _p(x), _p(tgt), g2, 1, _p(_conv_ws(g2, 2, dy.device)), s)
+                wsb = _conv_ws(g2, 2, dy.device)
+                side = _wgrad_fork(dy, x, wsb)
+                call('rih_conv2d_wgrad', _p(dy), _p(x), _p(tgt), g2, 1, _p(wsb), side or s)
             else:
                 dw = torch.empty_like(w)
                 call('rih_conv2d_wgrad', _p(dy), _p(x), _p(dw), g2, 0, _p(_conv_ws(g2, 2, dy.device)), s)
