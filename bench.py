@@ -22,7 +22,8 @@ sys.path.insert(0, ROOT)
 
 # FlopCounterMode on the reference (algorithmic 2*MAC FLOPs per image, forward+backward / forward)
 FLOPS = {'resnet50': (50.450e9, 17.721e9), 'hrnet48': (168.090e9, 56.201e9),
-         'graph': (38.422e9, 13.268e9)}     # common/myhand graph variant (ResNet-50 trunk), FlopCounterMode on the reference built on CPU
+         'graph': (38.422e9, 13.268e9),     # common/myhand graph variant (ResNet-50 trunk), FlopCounterMode on the reference built on CPU
+         'newgraph': (38.464e9, 13.283e9)}  # + ParamRegressor / MANO tail (matmul FLOPs only; the ManoLayer is ~1.2 MFLOP per hand)
 FLOPS_PER_IMG_FWD_BWD, FLOPS_PER_IMG_FWD = FLOPS['resnet50']
 
 
@@ -33,9 +34,10 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=None, help='images per GPU (default 64; 32 for --encoder hrnet48 = BASELINE.json configs[4])')
-    ap.add_argument('--encoder', default='resnet50', choices=['resnet50', 'hrnet48', 'graph'],
+    ap.add_argument('--encoder', default='resnet50', choices=['resnet50', 'hrnet48', 'graph', 'newgraph'],
                     help='resnet50 = BASELINE.json configs[2] (the headline metric), hrnet48 = configs[4] (MODEL.ENCODER_TYPE), '
-                         'graph = the common/myhand default model variant (SURVEY 8 f1; ResNet-50 trunk, batch 64)')
+                         'graph = the common/myhand default model variant (SURVEY 8 f1; ResNet-50 trunk, batch 64), '
+                         'newgraph = the same with the ParamRegressor + MANO tail, trained with mano_loss_GCN')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--gemm-mode', default='ref', choices=['ref', 'refrn', 'simt', 'tf32', 'tf32rn', 'tf32c', 'tf32x3'],
                     help="arithmetic of the conv / Linear GEMMs; 'ref' = the reference's own GPU numerics class: TF32 convolutions (as "
@@ -106,13 +108,14 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def metric_name(batch, world):
-    return 'images/sec fwd+bwd @batch%d 256x256 (training step: fwd + calc_loss_GCN + bwd + AdamW%s)' % (batch, ' + NCCL grad all-reduce' if world > 1 else '')
+def metric_name(batch, world, encoder='resnet50'):
+    return 'images/sec fwd+bwd @batch%d 256x256 (training step: fwd + %s + bwd + AdamW%s)' % (
+        batch, 'mano_loss_GCN' if encoder == 'newgraph' else 'calc_loss_GCN', ' + NCCL grad all-reduce' if world > 1 else '')
 
 
 def workload_name(encoder, batch):
     return 'BASELINE.json configs[%d]: HandNET_GCN %s cfg, batch %d/GPU, 256x256, train mode (batch-stat BN, dropout 0.05), random-init weights, ' \
-           'synthetic graph/MANO assets' % (4 if encoder == 'hrnet48' else 2, {'graph': 'common/myhand graph variant (ResNet50 trunk)'}.get(encoder, encoder), batch)
+           'synthetic graph/MANO assets' % (4 if encoder == 'hrnet48' else 2, {'graph': 'common/myhand graph variant (ResNet50 trunk)', 'newgraph': 'common/myhand newgraph variant (graph + ParamRegressor + MANO tail, mano_loss_GCN)'}.get(encoder, encoder), batch)
 
 
 def host_cores():
@@ -143,9 +146,10 @@ def cpu_port_step_time(batch, steps=1, warmup=0, budget_s=1e9, encoder='resnet50
     from renderih_b200.model import load_model
     a = A.synthetic_assets(0)
     cfg = load_cfg()
-    if encoder == 'graph':
-        from renderih_b200.myhand import load_graph_model
-        sd = fixtures.init_state_dict(load_graph_model(cfg, assets=a, mano_assets={s: A.synthetic_mano(0, s) for s in ('left', 'right')}).state_dict())
+    if encoder in ('graph', 'newgraph'):
+        from renderih_b200 import myhand
+        build = myhand.load_graph_model if encoder == 'graph' else myhand.load_new_model
+        sd = fixtures.init_state_dict(build(cfg, assets=a, mano_assets={s: A.synthetic_mano(0, s) for s in ('left', 'right')}).state_dict())
     else:
         cfg.MODEL.ENCODER_TYPE = encoder
         sd = fixtures.init_state_dict(load_model(cfg, assets=a).state_dict())
@@ -172,6 +176,8 @@ def cpu_port_step_time(batch, steps=1, warmup=0, budget_s=1e9, encoder='resnet50
         if v.is_floating_point() and 'running_' not in k and '.mano_' not in k and k not in ('decoder.dense_coor', 'decoder.unsample_layer.weight'):
             v.requires_grad_(True)
     Ap = model_ref.prepare_assets(a)
+    if encoder == 'newgraph':
+        Ap = fixtures.add_mano_assets(Ap, A.synthetic_mano(0, 'left'), A.synthetic_mano(0, 'right'))
     la = fixtures.make_loss_assets(a, A.synthetic_mano(0, 'left'), A.synthetic_mano(0, 'right'))
     img, labels = fixtures.make_image(batch), fixtures.make_labels(batch)
     opt = torch.optim.AdamW([v for v in sd.values() if v.requires_grad], lr=cfg.TRAIN.LR, weight_decay=cfg.TRAIN.weight_decay)
@@ -184,7 +190,11 @@ def cpu_port_step_time(batch, steps=1, warmup=0, budget_s=1e9, encoder='resnet50
             v.grad = None
         t0 = time.perf_counter()
         out = model_ref.model_forward(sd, Ap, img, training=True, dropout=0.05)
-        loss = model_ref.calc_loss_GCN(out, labels, la)
+        if encoder == 'newgraph':      # mesh terms on the MANO vertices + pose / shape terms (the loss graph is a few hundred small ops either way)
+            loss = model_ref.calc_loss_GCN((out[0], out[1], [], out[3]), labels, la) + sum((d['mano_pose'] ** 2).mean() + (d['mano_shape'] ** 2).mean()
+                                                                                              for d in out[3]['verts3d_MANO_list'].values())
+        else:
+            loss = model_ref.calc_loss_GCN(out, labels, la)
         loss.backward()
         opt.step()
         t1 = time.perf_counter()
@@ -200,7 +210,7 @@ def run_reference(args):
     # bounded: the CPU port needs tens of seconds per step on a big host, so at most ~3 steps / ~150 s are timed
     t, cores, nsteps = cpu_port_step_time(args.cpu_batch, steps=max(1, min(args.steps, 3)), warmup=0, budget_s=150.0, encoder=args.encoder)
     v = args.cpu_batch / t
-    line = {'impl': 'reference', 'metric': metric_name(args.batch, 1), 'value': v, 'unit': 'images/s',
+    line = {'impl': 'reference', 'metric': metric_name(args.batch, 1, args.encoder), 'value': v, 'unit': 'images/s',
             'n_gpus': args.gpus, 'steps': nsteps, 'warmup': 0, 'ms_per_step': t * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': workload_name(args.encoder, args.batch), 'global_batch': args.batch * args.gpus, 'parallelism': 'dp%d' % args.gpus,
@@ -270,9 +280,10 @@ def run_ours(args):
     flops_fb = FLOPS[args.encoder][0]
     a = A.synthetic_assets(0)
     torch.manual_seed(cfg.SEED)
-    if args.encoder == 'graph':
-        from renderih_b200.myhand import load_graph_model
-        model = load_graph_model(cfg, assets=a, mano_assets={s: A.synthetic_mano(0, s) for s in ('left', 'right')}).cuda().train()
+    if args.encoder in ('graph', 'newgraph'):
+        from renderih_b200 import myhand
+        build = myhand.load_graph_model if args.encoder == 'graph' else myhand.load_new_model
+        model = build(cfg, assets=a, mano_assets={s: A.synthetic_mano(0, s) for s in ('left', 'right')}).cuda().train()
     else:
         cfg.MODEL.ENCODER_TYPE = args.encoder
         model = load_model(cfg, assets=a).cuda().train()          # train mode: batch-stat BN, dropout 0.05 (reference defaults)
@@ -288,8 +299,16 @@ def run_ours(args):
     gl, gr = GraphLoss(jl, ml['f'], 4, 'cuda'), GraphLoss(jr, mr['f'], 4, 'cuda')
     conv = model.decoder.converter
     z = torch.zeros(B, 21, 3, device='cuda')
+    if args.encoder == 'newgraph':
+        from renderih_b200.loss import ManoLoss, mano_loss_GCN
+        gl, gr = ManoLoss(jl, ml['f'], 4, 'cuda'), ManoLoss(jr, mr['f'], 4, 'cuda')
+        lab.update({k: (torch.randn(B, n, generator=g) * 0.3).cuda() for k, n in (('lp_gt', 48), ('rp_gt', 48), ('ls_gt', 10), ('rs_gt', 10))})
 
     def loss_fn(out):
+        if args.encoder == 'newgraph':
+            return mano_loss_GCN(cfg, 0, gl, gr, conv['left'], conv['right'], out[0], out[1], out[2], out[3], None, None, None,
+                                 lab['v2d_l'], z[..., :2], lab['v2d_r'], z[..., :2], lab['v3d_l'], z, lab['v3d_r'], z, lab['root_rel'], 256,
+                                 lab['lp_gt'], lab['ls_gt'], lab['rp_gt'], lab['rs_gt'])[0]
         return calc_loss_GCN(cfg, 0, gl, gr, conv['left'], conv['right'], out[0], out[1], out[2], out[3], None, None, None,
                              lab['v2d_l'], z[..., :2], lab['v2d_r'], z[..., :2], lab['v3d_l'], z, lab['v3d_r'], z, lab['root_rel'], 256)[0]
 
@@ -344,7 +363,7 @@ def run_ours(args):
     total_imgs = B * world
     value = total_imgs / (ms_dev * 1e-3)
     e2e = total_imgs / (ms_e2e * 1e-3)
-    line = {'metric': metric_name(B, world),
+    line = {'metric': metric_name(B, world, args.encoder),
             'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_dev,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': {'simt': 'f32', 'refrn': 'f32 storage; tcgen05 TF32(rn) convolutions (cuDNN-default class of the reference) + 3xTF32 fp32-faithful Linear GEMMs, fp32 accumulate',
                       'tf32': 'tf32 (truncating) conv+Linear, fp32 accumulate/storage', 'tf32c': 'tf32 (truncating, mean-compensated) conv+Linear, fp32 accumulate/storage',

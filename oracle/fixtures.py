@@ -133,3 +133,24 @@ def flat_newgraph(out):
 
 def newgraph_loss(flat, cot):
     return sum((flat[k] * w.to(flat[k].device, flat[k].dtype)).sum() for k, w in cot.items())
+
+
+def make_mano_loss_case(batch=2, seed=SEED):
+    """Seeded (prediction, label) tensors for the mano_loss_GCN golden: shaped like the 'newgraph' outputs (decoder_lijun_mano.py:286-305)."""
+    g = torch.Generator().manual_seed(seed + 5)
+    r = lambda *s: torch.randn(*s, generator=g)
+    pred = {'verts3d_left': r(batch, 778, 3) * 0.05, 'verts3d_right': r(batch, 778, 3) * 0.05,
+            'verts2d_left': torch.rand(batch, 778, 2, generator=g) * 256, 'verts2d_right': torch.rand(batch, 778, 2, generator=g) * 256,
+            'mano_pose_left': r(batch, 48) * 0.4, 'mano_pose_right': r(batch, 48) * 0.4,
+            'mano_shape_left': r(batch, 10), 'mano_shape_right': r(batch, 10), 'root_rel': r(batch, 3) * 0.05}
+    lab = make_labels(batch, seed)
+    lab.update({'lp_gt': r(batch, 48) * 0.3, 'rp_gt': r(batch, 48) * 0.3, 'ls_gt': r(batch, 10), 'rs_gt': r(batch, 10)})
+    return pred, lab
+
+
+def mano_loss_inputs(pred):
+    """(result, paramsDict, handDictList, otherInfo) structure around the flat prediction dict"""
+    result = {'verts3d': {s: pred['verts3d_' + s] for s in ('left', 'right')}, 'verts2d': {s: pred['verts2d_' + s] for s in ('left', 'right')}}
+    other = {'root_rel': pred['root_rel'],
+             'verts3d_MANO_list': {s: {'mano_pose': pred['mano_pose_' + s], 'mano_shape': pred['mano_shape_' + s]} for s in ('left', 'right')}}
+    return result, {}, [], other

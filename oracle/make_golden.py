@@ -194,8 +194,33 @@ def newgraph_golden(ns, tmp):
     print('newgraph golden: loss %.6f, %d grads, %d keys' % (float(loss), len(grads), len(sd)))
 
 
+def mano_loss_golden(ns, tmp):
+    """core/Loss_mano.mano_loss_GCN (the unmodified reference code) on seeded predictions / labels: total, per-term values and the
+    gradient with respect to every prediction tensor."""
+    import core.Loss_mano as lm
+    lm.get_upsample_path = lambda: os.path.join(tmp, 'upsample.pkl')
+    _, cfg = rb.build_reference_model(asset_dir=tmp, encoder_type='resnet50', dropout=0.0)
+    manoL = ns.mano.ManoLayer(os.path.join(tmp, 'mano', 'MANO_LEFT.pkl'), center_idx=None)
+    manoR = ns.mano.ManoLayer(os.path.join(tmp, 'mano', 'MANO_RIGHT.pkl'), center_idx=None)
+    gl = lm.ManoLoss(manoL.J_regressor, manoL.get_faces(), level=4, device='cpu')
+    gr = lm.ManoLoss(manoR.J_regressor, manoR.get_faces(), level=4, device='cpu')
+    out = {}
+    for epoch in (0, 60):          # below / above NORM_EPOCH (edge term off / on)
+        pred, lab = fixtures.make_mano_loss_case(2)
+        pred = {k: v.clone().requires_grad_(True) for k, v in pred.items()}
+        result, params, hlist, other = fixtures.mano_loss_inputs(pred)
+        z = torch.zeros(2, 21, 3)
+        total, _, terms, _ = lm.mano_loss_GCN(cfg, epoch, gl, gr, None, None, result, params, hlist, other, None, None, None,
+                                              lab['v2d_l'], z[..., :2], lab['v2d_r'], z[..., :2], lab['v3d_l'], z, lab['v3d_r'], z,
+                                              lab['root_rel'], 256, lab['lp_gt'], lab['ls_gt'], lab['rp_gt'], lab['rs_gt'], upsample_weight=None)
+        total.backward()
+        out[epoch] = {'total': float(total), 'terms': {k: float(v) for k, v in terms.items()}, 'grads': {k: v.grad.clone() for k, v in pred.items()}}
+    torch.save(out, os.path.join(GOLD, 'mano_loss_synth.pt'))
+    print('mano_loss golden: totals', {e: round(o['total'], 4) for e, o in out.items()})
+
+
 def main(which):
-    """which: any of 'resnet50', 'hrnet48', 'graph', 'newgraph', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
+    """which: any of 'resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
     os.makedirs(GOLD, exist_ok=True)
     ns = rb.import_reference()
     with tempfile.TemporaryDirectory() as tmp:
@@ -208,6 +233,8 @@ def main(which):
             model_golden(ns, tmp, 'graph', 'model_graph_synth_b2.pt', 'resnet')
         if 'newgraph' in which:    # SURVEY 8(f) row 1, MANO tail
             newgraph_golden(ns, tmp)
+        if 'mano_loss' in which:   # core/Loss_mano.py:245-335
+            mano_loss_golden(ns, tmp)
         if 'mano' in which:
             mano_golden(ns, tmp)
         if 'mano_grad' in which:
@@ -215,4 +242,4 @@ def main(which):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'graph', 'newgraph', 'mano', 'mano_grad'])
+    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'mano', 'mano_grad'])

@@ -31,7 +31,7 @@ DEFAULTS = {
     'TRAIN': {'BATCH_SIZE': 64, 'LR': 3.0e-4, 'dropout': 0.05, 'weight_decay': 1.0e-2, 'OPTIM': 'adam',
               'EPOCHS': 200, 'current_epoch': 0, 'lr_decay_step': 80, 'lr_decay_gamma': 0.1, 'warm_up': 3},     # utils/defaults.yaml:36-44
     'LOSS_WEIGHT': {
-        'DATA': {'LABEL_3D': 100, 'LABEL_2D': 50},
+        'DATA': {'LABEL_3D': 100, 'LABEL_2D': 50, 'MANO_POSE': 0.5, 'MANO_SHAPE': 0.01, 'MANO_REL': 1},     # utils/defaults.yaml:54-61
         'GRAPH': {'NORM': {'EDGE': 2000, 'NORMAL': 10, 'NORM_EPOCH': 50}},
         'NORM': {'UPSAMPLE': 1.0},
     },

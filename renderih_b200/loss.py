@@ -1,4 +1,5 @@
-"""Training loss of the hot path: `GraphLoss` + `calc_loss_GCN` (reference core/Loss.py:20-277), same call signatures.
+"""Training losses of the hot path: `GraphLoss` + `calc_loss_GCN` (reference core/Loss.py:20-277) and, for the 'newgraph' MANO-tail
+variant, `ManoLoss` + `mano_loss_GCN` (core/Loss_mano.py:62-335), same call signatures.
 
 This is the *caller side* of the model: small [B,778,3] tensors, expressed with torch ops on
 the tensors' device so that autograd feeds d(result) into the CUDA backward.  Fusing it into one kernel is the next
@@ -98,3 +99,58 @@ def calc_loss_GCN(cfg, epoch, graph_loss_left, graph_loss_right, converter_left,
         total = total + w.DATA.LABEL_3D * coarse['v3d_loss'][i] + w.DATA.LABEL_2D * coarse['v2d_loss'][i]
     total = total + w.NORM.UPSAMPLE * mano['upsample_norm_loss']
     return total, aux, mano, coarse
+
+
+# ----------------------------------------------------------------------------- 'newgraph' variant: core/Loss_mano.py
+def axis_angle_to_rotmat_quat(axisang):
+    """Axis-angle [N,3] -> rotation matrices [N,9] through a unit quaternion -- the construction `batch_rodrigues` of core/Loss_mano.py:48-60
+    uses for the pose term (note its 1e-8 is added to the vector BEFORE the norm, unlike manolayer.rodrigues_batch)."""
+    angle = torch.norm(axisang + 1e-8, p=2, dim=1, keepdim=True)
+    q = torch.cat([torch.cos(angle * 0.5), torch.sin(angle * 0.5) * (axisang / angle)], dim=1)
+    q = q / q.norm(p=2, dim=1, keepdim=True)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    return torch.stack([w * w + x * x - y * y - z * z, 2 * x * y - 2 * w * z, 2 * w * y + 2 * x * z,
+                        2 * w * z + 2 * x * y, w * w - x * x + y * y - z * z, 2 * y * z - 2 * w * x,
+                        2 * x * z - 2 * w * y, 2 * w * x + 2 * y * z, w * w - x * x - y * y + z * z], dim=1)
+
+
+class ManoLoss(GraphLoss):
+    """core/Loss_mano.py:62-215: the GraphLoss mesh terms plus MSE on the 16 joint rotation matrices and on the shape coefficients;
+    no coarse-level terms (they are commented out in the reference, :184-208)."""
+
+    def calc_mano_loss(self, v3d_pred, v2d_pred, v3d_gt, v2d_gt, img_size, pred_pose, pred_shape, pose_gt, shape_gt):
+        d = GraphLoss.calc_mano_loss(self, v3d_pred, v2d_pred, v3d_gt, v2d_gt, img_size)
+        d['pose_loss'] = F.mse_loss(axis_angle_to_rotmat_quat(pred_pose.reshape(-1, 3)).reshape(-1, 16, 3, 3),
+                                    axis_angle_to_rotmat_quat(pose_gt.reshape(-1, 3)).reshape(-1, 16, 3, 3))
+        d['shape_loss'] = F.mse_loss(pred_shape, shape_gt)
+        return d
+
+    def calc_loss(self, converter, v3d_gt, v2d_gt, v3d_pred, v2d_pred, v3dList, v2dList, img_size, pred_pose, pred_shape, pose_gt, shape_gt):
+        return self.calc_mano_loss(v3d_pred, v2d_pred, v3d_gt, v2d_gt, img_size, pred_pose, pred_shape, pose_gt, shape_gt)
+
+
+def mano_loss_GCN(cfg, epoch, graph_loss_left, graph_loss_right, converter_left, converter_right,
+                  result, paramsDict, handDictList, otherInfo, mask, dense, hms,
+                  v2d_l, j2d_l, v2d_r, j2d_r, v3d_l, j3d_l, v3d_r, j3d_r, root_rel, img_size, lp_gt, ls_gt, rp_gt, rs_gt, upsample_weight=None):
+    """core/Loss_mano.py:245-335: mesh terms on the MANO vertices, pose / shape / relative-root terms, shape regulariser."""
+    aux = {'total_loss': 0}
+    ml = otherInfo['verts3d_MANO_list']
+    v3d_r = v3d_r + root_rel.unsqueeze(1)
+    left = graph_loss_left.calc_loss(converter_left, v3d_l, v2d_l, result['verts3d']['left'], result['verts2d']['left'], None, None, img_size,
+                                     ml['left']['mano_pose'], ml['left']['mano_shape'], lp_gt, ls_gt)
+    right = graph_loss_right.calc_loss(converter_right, v3d_r, v2d_r, result['verts3d']['right'], result['verts2d']['right'], None, None, img_size,
+                                       ml['right']['mano_pose'], ml['right']['mano_shape'], rp_gt, rs_gt)
+    mano = {k: (left[k] + right[k]) / 2 for k in left}
+    w = cfg.LOSS_WEIGHT
+    alpha = 0 if epoch < w.GRAPH.NORM.NORM_EPOCH else 1
+    if upsample_weight is not None:
+        mano['upsample_norm_loss'] = graph_loss_left.upsample_weight_loss(upsample_weight)
+    else:
+        mano['upsample_norm_loss'] = torch.zeros_like(mano['vert3d_loss'])
+    mano['rootrel_loss'] = w.DATA.MANO_REL * F.mse_loss(otherInfo['root_rel'], root_rel)
+    mano['regularize_loss'] = 0.005 * torch.mean(torch.sum(ml['left']['mano_shape'] ** 2) + torch.sum(ml['right']['mano_shape'] ** 2))
+    total = w.DATA.LABEL_3D * mano['vert3d_loss'] + w.DATA.LABEL_2D * mano['vert2d_loss'] + w.DATA.LABEL_3D * mano['joint_loss'] \
+        + w.GRAPH.NORM.NORMAL * mano['norm_loss'] + alpha * w.GRAPH.NORM.EDGE * mano['edge_loss'] \
+        + w.DATA.MANO_POSE * mano['pose_loss'] + w.DATA.MANO_SHAPE * mano['shape_loss'] + mano['rootrel_loss'] + mano['regularize_loss']
+    total = total + w.NORM.UPSAMPLE * mano['upsample_norm_loss']
+    return total, aux, mano, {}

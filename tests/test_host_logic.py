@@ -146,3 +146,32 @@ def test_lr_schedule_matches_reference_scheduler():
         mine = lr_at_epoch(i + 1, g['base_lr'], init_lr=g['init_lr'], warm_up_epoch=g['warm_up_epoch'], gamma=g['gamma'],
                            step_size=g['step_size'], min_thres=g['min_thres'])
         assert abs(mine - ref) <= 1e-12 + 1e-9 * ref, (i + 1, mine, ref)
+
+
+def test_mano_loss_matches_reference_golden():
+    """renderih_b200.loss.ManoLoss / mano_loss_GCN (pure torch, runs on any device) against core/Loss_mano.mano_loss_GCN of the unmodified
+    reference (tests/golden/mano_loss_synth.pt): total, every term and the gradient w.r.t. every prediction, below and above NORM_EPOCH."""
+    from oracle import fixtures
+    from renderih_b200.config import load_cfg
+    from renderih_b200.loss import ManoLoss, mano_loss_GCN
+    gold = torch.load(os.path.join(GOLD, 'mano_loss_synth.pt'), weights_only=False)
+    cfg = load_cfg(None)
+    ml, mr = A.synthetic_mano(0, 'left'), A.synthetic_mano(0, 'right')
+    jl = torch.from_numpy(np.asarray(ml['J_regressor'].todense(), dtype=np.float32))
+    jr = torch.from_numpy(np.asarray(mr['J_regressor'].todense(), dtype=np.float32))
+    gl, gr = ManoLoss(jl, ml['f'], 4, 'cpu'), ManoLoss(jr, mr['f'], 4, 'cpu')
+    for epoch, g in gold.items():
+        pred, lab = fixtures.make_mano_loss_case(2)
+        pred = {k: v.clone().requires_grad_(True) for k, v in pred.items()}
+        result, params, hlist, other = fixtures.mano_loss_inputs(pred)
+        z = torch.zeros(2, 21, 3)
+        total, _, terms, _ = mano_loss_GCN(cfg, epoch, gl, gr, None, None, result, params, hlist, other, None, None, None,
+                                           lab['v2d_l'], z[..., :2], lab['v2d_r'], z[..., :2], lab['v3d_l'], z, lab['v3d_r'], z,
+                                           lab['root_rel'], 256, lab['lp_gt'], lab['ls_gt'], lab['rp_gt'], lab['rs_gt'])
+        assert abs(float(total) - g['total']) < 1e-5 * abs(g['total']), (epoch, float(total), g['total'])
+        for k, v in g['terms'].items():
+            assert abs(float(terms[k]) - v) <= 1e-5 * abs(v) + 1e-9, (epoch, k, float(terms[k]), v)
+        total.backward()
+        for k, v in g['grads'].items():
+            d = (pred[k].grad - v).abs().max() / v.abs().max().clamp_min(1e-12)
+            assert float(d) < 1e-5, (epoch, k, float(d))
