@@ -210,7 +210,7 @@ def run_reference(args):
     # bounded: the CPU port needs tens of seconds per step on a big host, so at most ~3 steps / ~150 s are timed
     t, cores, nsteps = cpu_port_step_time(args.cpu_batch, steps=max(1, min(args.steps, 3)), warmup=0, budget_s=150.0, encoder=args.encoder)
     v = args.cpu_batch / t
-    line = {'impl': 'reference', 'metric': metric_name(args.batch, 1, args.encoder), 'value': v, 'unit': 'images/s',
+    line = {'impl': 'reference', 'metric': metric_name(args.batch, args.gpus, args.encoder), 'value': v, 'unit': 'images/s',
             'n_gpus': args.gpus, 'steps': nsteps, 'warmup': 0, 'ms_per_step': t * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': workload_name(args.encoder, args.batch), 'global_batch': args.batch * args.gpus, 'parallelism': 'dp%d' % args.gpus,
