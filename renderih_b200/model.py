@@ -52,15 +52,18 @@ def _cl(conv):
 
 
 # ============================================================================ encoder (models/encoder.py:21-173)
-def _conv_bn(x, conv, bn, N, H, W, training, relu=True, res=None):
-    """torchvision order Conv -> BN -> (+res) -> ReLU"""
+def _conv_bn(x, conv, bn, N, H, W, training, relu=True, res=None, alias_input=False):
+    """torchvision order Conv -> BN -> (+res) -> ReLU.  alias_input: returns (y, Ho, x_alias) -- see ops.conv2d."""
     k = conv.kernel_size[0]
     stats = torch.empty(2 * conv.out_channels, device=x.device, dtype=torch.float64) if training else None
-    y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], stats=stats)
+    y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], stats=stats, alias_input=alias_input)
+    xa = None
+    if alias_input:
+        y, xa = y
     Ho = (H + 2 * conv.padding[0] - k) // conv.stride[0] + 1
     y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, res=res, training=training,
                       momentum=bn.momentum, eps=bn.eps, relu=relu, stats=stats)
-    return y, Ho
+    return (y, Ho, xa) if alias_input else (y, Ho)
 
 
 def _conv_relu_bn(x, conv, bn, N, H, W, training):
@@ -143,12 +146,18 @@ class ResNetSimple(nn.Module):
 
     def _bottleneck(self, blk, x, N, H):
         tr = self.training
-        out, _ = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr)
+        # the block input feeds conv1 AND the residual path: the residual path hangs off conv1's alias output, so its gradient is
+        # accumulated by conv1's dgrad kernel instead of a separate add over the largest activations of the network
+        fuse = tr and x.requires_grad
+        if fuse:
+            out, _, xa = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr, alias_input=True)
+        else:
+            (out, _), xa = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr), x
         out, Ho = _conv_bn(out, blk.conv2, blk.bn2, N, H, H, tr)
         if blk.downsample is not None:
-            identity, _ = _conv_bn(x, blk.downsample[0], blk.downsample[1], N, H, H, tr, relu=False)
+            identity, _ = _conv_bn(xa, blk.downsample[0], blk.downsample[1], N, H, H, tr, relu=False)
         else:
-            identity = x
+            identity = xa
         out, _ = _conv_bn(out, blk.conv3, blk.bn3, N, Ho, Ho, tr, relu=True, res=identity)
         return out, Ho
 

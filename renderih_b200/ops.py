@@ -584,8 +584,9 @@ class Conv2dFn(Function):
     """NHWC conv (+bias)(+relu) -- nn.Conv2d sites of models/encoder.py, torchvision resnet, img_attn.py:48"""
 
     @staticmethod
-    def forward(ctx, x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer, stats):
+    def forward(ctx, x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer, stats, alias_input=False):
         x = _rows(x); _w_phys(_check(w, 'weight'))
+        ctx.alias_input = alias_input
         Cout, Cin, R, S = w.shape
         assert x.shape == (N * H * W, Cin), (x.shape, N, H, W, Cin)
         g, Ho, Wo = _geom(N, H, W, Cin, Cout, R, S, stride, pad, _ld(x), Cout)
@@ -595,10 +596,12 @@ class Conv2dFn(Function):
         ctx.save_for_backward(x, w, y if need_y else None)
         ctx.meta = (N, H, W, stride, pad, need_y, b is not None)
         ctx.bias_ref = b
+        if alias_input:      # second output = the input itself: a later consumer of x (the residual add, the downsample conv) hangs off it,
+            return y, x      # so its gradient arrives HERE and the dgrad kernel accumulates onto it instead of autograd adding two tensors
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, d_alias=None):
         x, w, y = ctx.saved_tensors
         N, H, W, stride, pad, need_y, has_b = ctx.meta
         Cout, Cin, R, S = w.shape
@@ -611,8 +614,16 @@ class Conv2dFn(Function):
         g, Ho, Wo = _geom(N, H, W, Cin, Cout, R, S, stride, pad, Cin, _ld(dy))
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty((N * H * W, Cin), device=dy.device, dtype=torch.float32)
-            call('rih_conv2d_dgrad', _p(dy), _p(w), _p(dx), g, 0, _p(_conv_ws(g, 1, dy.device)), s)
+            acc = 0
+            if d_alias is not None and d_alias.is_contiguous() and d_alias.shape == (N * H * W, Cin):
+                dx, acc = d_alias, 1      # accumulate onto the gradient that came in through the alias output (epilogue: TMA reduce-add)
+            else:
+                dx = torch.empty((N * H * W, Cin), device=dy.device, dtype=torch.float32)
+            call('rih_conv2d_dgrad', _p(dy), _p(w), _p(dx), g, acc, _p(_conv_ws(g, 1, dy.device)), s)
+            if d_alias is not None and acc == 0:
+                dx = dx + d_alias
+        elif d_alias is not None:
+            dx = d_alias
         if ctx.needs_input_grad[1]:
             g2, _, _ = _geom(N, H, W, Cin, Cout, R, S, stride, pad, _ld(x), _ld(dy))
             tgt = _gt(w)
@@ -630,12 +641,14 @@ class Conv2dFn(Function):
             else:
                 db = torch.empty((Cout,), device=dy.device, dtype=torch.float32)
                 call('rih_colsum', _p(dy), _ld(dy), dy.shape[0], Cout, _p(db), 0, s)
-        return dx, dw, db, None, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None, None
 
 
-def conv2d(x, w, b, N, H, W, stride=1, pad=0, relu=False, relu_masked_by_consumer=False, stats=None):
-    """stats: optional float64 [2*Cout] buffer that receives the output's per-channel sum / sum of squares (fused BN statistics)."""
-    return Conv2dFn.apply(x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer, stats)
+def conv2d(x, w, b, N, H, W, stride=1, pad=0, relu=False, relu_masked_by_consumer=False, stats=None, alias_input=False):
+    """stats: optional float64 [2*Cout] buffer that receives the output's per-channel sum / sum of squares (fused BN statistics).
+    alias_input: also return x as a second output; route every OTHER use of x through it and their gradients are accumulated by this
+    convolution's dgrad kernel (no separate add pass over the activation gradient)."""
+    return Conv2dFn.apply(x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer, stats, alias_input)
 
 
 class PatchifyFn(Function):
