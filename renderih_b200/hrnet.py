@@ -49,15 +49,28 @@ def _cbr_seq(cin, cout, k, stride=1, relu=True, bias=False):
 
 
 # ----------------------------------------------------------------------------- kernel-side helpers
-def conv_bn(x, conv, bn, N, H, training, relu=True, res=None):
-    """Conv2d(+bias) -> BatchNorm2d -> (+res) -> (ReLU) on a square NHWC map; returns (y, Ho).
+def conv_bn(x, conv, bn, N, H, training, relu=True, res=None, alias_input=False):
+    """Conv2d(+bias) -> BatchNorm2d -> (+res) -> (ReLU) on a square NHWC map; returns (y, Ho) -- or (y, Ho, x_alias) with alias_input:
+    route the residual use of x through x_alias and its gradient is accumulated by this convolution's dgrad kernel (ops.conv2d).
     Training-mode batch statistics come out of the convolution's epilogue when it runs on the tensor-core path."""
     k, st, pd = conv.kernel_size[0], conv.stride[0], conv.padding[0]
     stats = torch.empty(2 * conv.out_channels, device=x.device, dtype=torch.float64) if training else None
-    y = ops.conv2d(x, conv.weight, conv.bias, N, H, H, stride=st, pad=pd, stats=stats)
+    y = ops.conv2d(x, conv.weight, conv.bias, N, H, H, stride=st, pad=pd, stats=stats, alias_input=alias_input)
+    xa = None
+    if alias_input:
+        y, xa = y
     y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, res=res, training=training,
                       momentum=bn.momentum, eps=bn.eps, relu=relu, stats=stats)
-    return y, (H + 2 * pd - k) // st + 1
+    Ho = (H + 2 * pd - k) // st + 1
+    return (y, Ho, xa) if alias_input else (y, Ho)
+
+
+def _first_conv_with_alias(x, conv, bn, N, H, training):
+    """(out, x_for_the_residual_path): the alias form when gradients will flow (training), the plain form otherwise"""
+    if training and x.requires_grad:
+        out, _, xa = conv_bn(x, conv, bn, N, H, training, alias_input=True)
+        return out, xa
+    return conv_bn(x, conv, bn, N, H, training)[0], x
 
 
 def stem_conv_bn(x, conv, bn, N, H, training, image_needs_grad):
@@ -92,8 +105,8 @@ class BasicBlock(nn.Module):
 
     def forward(self, x, N, H):
         tr = self.training
-        out, _ = conv_bn(x, self.conv1, self.bn1, N, H, tr)
-        out, _ = conv_bn(out, self.conv2, self.bn2, N, H, tr, relu=True, res=x)
+        out, xa = _first_conv_with_alias(x, self.conv1, self.bn1, N, H, tr)
+        out, _ = conv_bn(out, self.conv2, self.bn2, N, H, tr, relu=True, res=xa)
         return out
 
 
@@ -115,11 +128,11 @@ class Bottleneck(nn.Module):
 
     def forward(self, x, N, H):
         tr = self.training
-        out, _ = conv_bn(x, self.conv1, self.bn1, N, H, tr)
+        out, xa = _first_conv_with_alias(x, self.conv1, self.bn1, N, H, tr)
         out, _ = conv_bn(out, self.conv2, self.bn2, N, H, tr)
-        idt = x
+        idt = xa
         if self.downsample is not None:
-            idt, _ = conv_bn(x, self.downsample[0], self.downsample[1], N, H, tr, relu=False)
+            idt, _ = conv_bn(xa, self.downsample[0], self.downsample[1], N, H, tr, relu=False)
         out, _ = conv_bn(out, self.conv3, self.bn3, N, H, tr, relu=True, res=idt)
         return out
 
