@@ -74,10 +74,100 @@ class GraphLoss:
         return mano, coarse
 
 
+class _FusedGraphLossFn(torch.autograd.Function):
+    """rih_graph_loss_fwd / _bwd (csrc/loss.cu): both hands' GraphLoss.calc_loss + the calc_loss_GCN weighting as one forward and one
+    backward kernel (the torch formulation above costs ~400 small launches, 2 ms of a 36 ms step)."""
+
+    @staticmethod
+    def forward(ctx, tables, weights, img, v3p_l, v2p_l, v3c_l, v2c_l, v3p_r, v2p_r, v3c_r, v2c_r, v3g_l, v2g_l, v3g_r, v2g_r, root_rel):
+        import ctypes
+        from ._lib import call
+        from .ops import _stream
+        preds = [t.contiguous().float() for t in (v3p_l, v2p_l, v3c_l, v2c_l, v3p_r, v2p_r, v3c_r, v2c_r)]
+        labels = [t.contiguous().float() for t in (v3g_l, v2g_l, v3g_r, v2g_r, root_rel)]
+        dev = preds[0].device
+        B, Vc = preds[0].shape[0], preds[2].shape[1]
+        F_ = tables['faces'][0].shape[0]
+        pool = tables['perm'][0].numel() // Vc
+        fp = (ctypes.c_void_p * 16)(preds[0].data_ptr(), preds[1].data_ptr(), labels[0].data_ptr(), labels[1].data_ptr(), None,
+                                    preds[2].data_ptr(), preds[3].data_ptr(), tables['J21'][0].data_ptr(),
+                                    preds[4].data_ptr(), preds[5].data_ptr(), labels[2].data_ptr(), labels[3].data_ptr(), labels[4].data_ptr(),
+                                    preds[6].data_ptr(), preds[7].data_ptr(), tables['J21'][1].data_ptr())
+        ip = (ctypes.c_void_p * 4)(tables['faces'][0].data_ptr(), tables['perm'][0].data_ptr(), tables['faces'][1].data_ptr(), tables['perm'][1].data_ptr())
+        partial = torch.empty((2, B, 7), device=dev)
+        out = torch.empty(15, device=dev)
+        coef = torch.empty(7, device=dev)
+        w = (ctypes.c_float * 7)(*weights)
+        call('rih_graph_loss_fwd', fp, ip, B, F_, Vc, pool, float(img), w, partial.data_ptr(), out.data_ptr(), coef.data_ptr(), _stream())
+        ctx.save_for_backward(coef, *preds, *labels)
+        ctx.meta = (tables, B, F_, Vc, pool, float(img))
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, d_total, _d_out):
+        import ctypes
+        from ._lib import call
+        from .ops import _stream
+        coef, *rest = ctx.saved_tensors
+        preds, labels = rest[:8], rest[8:]
+        tables, B, F_, Vc, pool, img = ctx.meta
+        fp = (ctypes.c_void_p * 16)(preds[0].data_ptr(), preds[1].data_ptr(), labels[0].data_ptr(), labels[1].data_ptr(), None,
+                                    preds[2].data_ptr(), preds[3].data_ptr(), tables['J21'][0].data_ptr(),
+                                    preds[4].data_ptr(), preds[5].data_ptr(), labels[2].data_ptr(), labels[3].data_ptr(), labels[4].data_ptr(),
+                                    preds[6].data_ptr(), preds[7].data_ptr(), tables['J21'][1].data_ptr())
+        ip = (ctypes.c_void_p * 4)(tables['faces'][0].data_ptr(), tables['perm'][0].data_ptr(), tables['faces'][1].data_ptr(), tables['perm'][1].data_ptr())
+        grads = [torch.empty_like(t) for t in preds]
+        gp = (ctypes.c_void_p * 8)(*[g.data_ptr() for g in grads])
+        up = d_total.contiguous().float().reshape(1)
+        scratch = torch.empty(7, device=up.device)
+        call('rih_graph_loss_bwd', fp, ip, gp, B, F_, Vc, pool, img, coef.data_ptr(), up.data_ptr(), scratch.data_ptr(), _stream())
+        return (None, None, None) + tuple(grads) + (None, None, None, None, None)
+
+
+def _fused_tables(gl_left, gl_right, conv_left, conv_right, device):
+    """int32 face / permutation tables and the 21-joint regressors on the device (cached on the GraphLoss objects)."""
+    key = str(device)
+    cache = gl_left.__dict__.setdefault('_fused_tables', {})
+    if key not in cache:
+        t = {'faces': [], 'perm': [], 'J21': []}
+        for gl, conv in ((gl_left, conv_left), (gl_right, conv_right)):
+            t['faces'].append(gl.faces.to(device=device, dtype=torch.int32).contiguous())
+            perm = np.asarray(conv.graph_perm, dtype=np.int32)
+            if perm.min() < 0 or perm.max() >= 778 or int(gl.faces.max()) >= 778:
+                raise ValueError('fused GraphLoss: graph_perm / faces index outside the 778 MANO vertices')
+            t['perm'].append(torch.as_tensor(perm).to(device))
+            t['J21'].append(gl.J_regressor.to(device=device, dtype=torch.float32).contiguous())
+        cache[key] = t
+    return cache[key]
+
+
 def calc_loss_GCN(cfg, epoch, graph_loss_left, graph_loss_right, converter_left, converter_right,
                   result, paramsDict, handDictList, otherInfo, mask, dense, hms,
                   v2d_l, j2d_l, v2d_r, j2d_r, v3d_l, j3d_l, v3d_r, j3d_r, root_rel, img_size, upsample_weight=None):
-    """core/Loss.py:201-277 (the auxiliary mask/dense/heat-map loss is disabled in the reference at line 213)."""
+    """core/Loss.py:201-277 (the auxiliary mask/dense/heat-map loss is disabled in the reference at line 213).
+    CUDA inputs with one coarse level (the models of this package) take the fused kernel; anything else the torch formulation below."""
+    import os
+    v3p = result['verts3d']['left']
+    if (v3p.is_cuda and len(handDictList) == 1 and type(graph_loss_left) is GraphLoss and os.environ.get('RIH_FUSED_LOSS', '1') != '0'
+            and handDictList[0]['verts3d']['left'].shape[1] * 4 == len(converter_left.graph_perm)):
+        w = cfg.LOSS_WEIGHT
+        alpha = 0 if epoch < w.GRAPH.NORM.NORM_EPOCH else 1
+        weights = (w.DATA.LABEL_3D, w.DATA.LABEL_2D, w.DATA.LABEL_3D, w.GRAPH.NORM.NORMAL, alpha * w.GRAPH.NORM.EDGE, w.DATA.LABEL_3D, w.DATA.LABEL_2D)
+        tables = _fused_tables(graph_loss_left, graph_loss_right, converter_left, converter_right, v3p.device)
+        hd = handDictList[0]
+        total, out = _FusedGraphLossFn.apply(tables, weights, img_size, result['verts3d']['left'], result['verts2d']['left'],
+                                             hd['verts3d']['left'], hd['verts2d']['left'], result['verts3d']['right'], result['verts2d']['right'],
+                                             hd['verts3d']['right'], hd['verts2d']['right'], v3d_l, v2d_l, v3d_r, v2d_r, root_rel)
+        names = ('vert3d_loss', 'vert2d_loss', 'joint_loss', 'norm_loss', 'edge_loss')
+        mano = {n: (out[1 + i] + out[8 + i]) / 2 for i, n in enumerate(names)}
+        coarse = {'v3d_loss': [(out[6] + out[13]) / 2], 'v2d_loss': [(out[7] + out[14]) / 2]}
+        if upsample_weight is not None:
+            mano['upsample_norm_loss'] = graph_loss_left.upsample_weight_loss(upsample_weight)
+            total = total + w.NORM.UPSAMPLE * mano['upsample_norm_loss']
+        else:
+            mano['upsample_norm_loss'] = torch.zeros_like(total)
+        return total, {'total_loss': 0}, mano, coarse
     aux = {'total_loss': 0}
     v3d_r = v3d_r + root_rel.unsqueeze(1)
     outs = {}

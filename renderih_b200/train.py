@@ -145,9 +145,30 @@ class TrainStep:
         self.flatp.step_count += 0
         return self
 
+    def prefetch(self, img_host):
+        """Start the host -> device copy of the NEXT step's batch (pinned host tensor) on a copy stream, overlapping the current step; the
+        next `__call__()` (without an argument) moves it into the graph's static input with one device-to-device copy.  This is the
+        input double-buffering a DataLoader with `pin_memory` + `non_blocking` gives the reference trainer (core/lijun_trainer.py:255-262)."""
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.static_img.device)
+            self._stage = torch.empty_like(self.static_img)
+            self._stage_free = None
+        if self._stage_free is not None:
+            self._copy_stream.wait_event(self._stage_free)      # the previous stage -> static copy must have consumed the buffer
+        with torch.cuda.stream(self._copy_stream):
+            self._stage.copy_(img_host, non_blocking=True)
+        self._staged = True
+
     def __call__(self, img=None):
         if img is not None:
             self.static_img.copy_(img, non_blocking=True)
+        elif getattr(self, '_staged', False):
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self._copy_stream)
+            self.static_img.copy_(self._stage, non_blocking=True)
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(cur)
+            self._staged = False
         if self.graph is None:
             return self._eager()
         self.graph.replay()
