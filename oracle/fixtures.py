@@ -154,3 +154,30 @@ def mano_loss_inputs(pred):
     other = {'root_rel': pred['root_rel'],
              'verts3d_MANO_list': {s: {'mano_pose': pred['mano_pose_' + s], 'mano_shape': pred['mano_shape_' + s]} for s in ('left', 'right')}}
     return result, {}, [], other
+
+
+def make_eval_case(batch=6, seed=SEED):
+    """Seeded (prediction, ground truth) meshes for the evaluation-metric golden (apps/eval_interhand.py loop body): [B,778,3] metres.
+    Predictions are a similarity transform of the ground truth plus 4 mm noise (so the Procrustes numbers differ from the plain ones);
+    the left ground truth touches the right one on about a third of the vertices (contact-deviation term); the last sample has the
+    hands 1 m apart (no contact -> NaN)."""
+    g = torch.Generator().manual_seed(seed + 9)
+    r = lambda *s: torch.randn(*s, generator=g)
+    gt_r = r(batch, 778, 3) * 0.04 + r(batch, 1, 3) * 0.1
+    perm = torch.stack([torch.randperm(778, generator=g) for _ in range(batch)])
+    gt_l = torch.gather(gt_r, 1, perm[:, :, None].repeat(1, 1, 3)) + r(batch, 778, 3) * 0.0012
+    far = torch.rand(batch, 778, 1, generator=g) > 0.35
+    gt_l = gt_l + far * (r(batch, 778, 3) * 0.03 + 0.02)
+    gt_l[-1] += 1.0
+
+    def perturb(v):
+        a = r(batch, 3) * 0.25
+        th = a.norm(dim=-1, keepdim=True)[..., None]
+        k = a / a.norm(dim=-1, keepdim=True)
+        K = torch.zeros(batch, 3, 3)
+        K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
+        R = torch.eye(3) + torch.sin(th) * K + (1 - torch.cos(th)) * K.bmm(K)
+        s = 1 + r(batch, 1, 1) * 0.08
+        c = v.mean(1, keepdim=True)
+        return s * (v - c).bmm(R.transpose(1, 2)) + c + r(batch, 1, 3) * 0.02 + r(batch, 778, 3) * 0.004
+    return {'pred_left': perturb(gt_l), 'pred_right': perturb(gt_r), 'gt_left': gt_l, 'gt_right': gt_r}

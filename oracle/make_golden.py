@@ -219,8 +219,93 @@ def mano_loss_golden(ns, tmp):
     print('mano_loss golden: totals', {e: round(o['total'], 4) for e, o in out.items()})
 
 
+def eval_metrics_golden(ns, tmp):
+    """Evaluation metrics of apps/eval_interhand.py, produced by EXECUTING the reference's own source: the definitions of
+    batch_compute_similarity_transform_torch / compute_similarity_transform(_batch) / get_alignMesh / Jr, the accumulator set-up
+    (:268-298), the body of the evaluation loop (:300-438, minus the data loading / network call / timing statements) on two seeded
+    batches, and the reductions after it (:441-552) -- all compiled from the file under /root/reference at generation time.
+    `pytorch3d.ops.knn_points` (used by utils/eval_metrics.compute_cdev) is absent from this container; a brute-force K=1 stand-in with
+    the same return convention (squared distances, indices) is injected, and that is stated in the golden's meta."""
+    import ast
+    import contextlib
+    import io
+    import types
+    path = os.path.join(rb.REF_ROOT, 'apps', 'eval_interhand.py')
+    tree = ast.parse(open(path).read())
+    wanted = {'batch_compute_similarity_transform_torch', 'compute_similarity_transform', 'compute_similarity_transform_batch', 'get_alignMesh', 'Jr'}
+    defs = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in wanted]
+    assert len(defs) == len(wanted)
+    env = {'torch': torch, 'np': np}
+    exec(compile(ast.Module(body=defs, type_ignores=[]), path, 'exec'), env)
+
+    def knn_points(p1, p2, lengths1=None, lengths2=None, K=1, return_nn=False):
+        d2 = ((p1[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)
+        dist, idx = d2.min(dim=2)
+        return dist[:, :, None], idx[:, :, None], None
+    p3d, p3d_ops = types.ModuleType('pytorch3d'), types.ModuleType('pytorch3d.ops')
+    p3d_ops.knn_points = knn_points
+    p3d.ops = p3d_ops
+    sys.modules['pytorch3d'], sys.modules['pytorch3d.ops'] = p3d, p3d_ops
+    sys.modules.pop('utils.eval_metrics', None)
+
+    main_if = [n for n in tree.body if isinstance(n, ast.If)][0]
+    with_node = [n for n in main_if.body if isinstance(n, ast.With)][0]
+    loop = with_node.body[0]
+    assert isinstance(loop, ast.For)
+    setup = [n for n in main_if.body if 268 <= n.lineno <= 298]
+    tail = [n for n in main_if.body if n.lineno > with_node.lineno]
+
+    def keep(stmt):                      # drop data loading (.cuda() of the loader tuple), the network call and the wall-clock statements
+        text = ast.unparse(stmt)
+        return not (('data[' in text and '.cuda()' in text) or 'network(' in text or 'time.time()' in text or text.startswith('total_time'))
+    body = [n for n in loop.body if keep(n)]
+    dropped = [ast.unparse(n) for n in loop.body if not keep(n)]
+    assert len(dropped) == 9, dropped
+
+    def run(stmts):
+        for st in stmts:
+            exec(compile(ast.Module(body=[st], type_ignores=[]), path, 'exec'), env)
+            if isinstance(st, ast.Assign) and ast.unparse(st.targets[0]) == 'error_mpjpe':
+                env.setdefault('_error_mpjpe', []).append(float(env['error_mpjpe']))
+
+    manoL = ns.mano.ManoLayer(os.path.join(tmp, 'mano', 'MANO_LEFT.pkl'), center_idx=None)
+    manoR = ns.mano.ManoLayer(os.path.join(tmp, 'mano', 'MANO_RIGHT.pkl'), center_idx=None)
+    env['J_regressor'] = {'left': env['Jr'](manoL.J_regressor, device='cpu'), 'right': env['Jr'](manoR.J_regressor, device='cpu')}
+    case = fixtures.make_eval_case(6)
+    n = case['gt_left'].shape[0]
+    env.update({'iou033': np.arange(n) % 3 == 0, 'iou067': np.arange(n) % 3 == 1, 'iou1': np.arange(n) % 3 == 2})
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink), torch.no_grad():
+        run(setup)
+        for lo, hi in ((0, 4), (4, 6)):          # two batches of different size: the reference concatenates them after the loop
+            env.update({'verts_left_gt': case['gt_left'][lo:hi].clone(), 'verts_right_gt': case['gt_right'][lo:hi].clone(),
+                        'result': {'verts3d': {'left': case['pred_left'][lo:hi].clone(), 'right': case['pred_right'][lo:hi].clone()}}})
+            run(body)
+        run(tail)
+    t = lambda a: torch.as_tensor(np.asarray(a))
+    out = {'meta': {'source': 'apps/eval_interhand.py executed in place (defs + loop body :300-438 + reductions :441-552)',
+                    'knn_points': 'brute-force stand-in for pytorch3d.ops.knn_points (absent here)', 'torch': torch.__version__,
+                    'batches': [4, 2], 'dropped_loop_statements': dropped},
+           'per_element': {side: {k: t(env[k][side]) for k in ('orijoint_loss', 'orivert_loss', 'joints_loss', 'verts_loss', 'pajoints_loss', 'paverts_loss')}
+                           for side in ('left', 'right')},
+           'mrrpe': t(env['mrrpe']), 'cdev': env['error'].clone(),
+           'summary_mm': {'ori_mpjpe_left': float(env['orijoint_left']), 'ori_mpjpe_right': float(env['orijoint_right']),
+                          'ori_mpvpe_left': float(env['orivert_left']), 'ori_mpvpe_right': float(env['orivert_right']),
+                          'mpjpe_left': float(env['joints_loss']['left'].mean() * 1000), 'mpjpe_right': float(env['joints_loss']['right'].mean() * 1000),
+                          'mpvpe_left': float(env['verts_loss']['left'].mean() * 1000), 'mpvpe_right': float(env['verts_loss']['right'].mean() * 1000),
+                          'pa_mpjpe_left': float(env['joints_mean_loss_left']), 'pa_mpjpe_right': float(env['joints_mean_loss_right']),
+                          'pa_mpvpe_left': float(env['verts_mean_loss_left']), 'pa_mpvpe_right': float(env['verts_mean_loss_right']),
+                          'double_pa_mpjpe': float(1000 * np.mean(env['pa_joint_error'])), 'double_pa_mpvpe': float(1000 * np.mean(env['pa_mesh_error'])),
+                          'double_mpjpe': 1000 * env['_error_mpjpe'][0], 'double_mpvpe': 1000 * env['_error_mpjpe'][1]},
+           'double_per_sample': {'pa_joint': t(env['get_alignMesh'](env['pred_3djoint'], env['gt_3djoint'], reduction=None)[0]),
+                                 'pa_mesh': t(env['get_alignMesh'](env['pred_mesh'], env['gt_mesh'], reduction=None)[0])},
+           'printed': sink.getvalue()}
+    torch.save(out, os.path.join(GOLD, 'eval_metrics_synth.pt'))
+    print('eval_metrics golden:', {k: round(v, 4) for k, v in out['summary_mm'].items()})
+
+
 def main(which):
-    """which: any of 'resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
+    """which: any of 'resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'eval_metrics', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
     os.makedirs(GOLD, exist_ok=True)
     ns = rb.import_reference()
     with tempfile.TemporaryDirectory() as tmp:
@@ -235,6 +320,8 @@ def main(which):
             newgraph_golden(ns, tmp)
         if 'mano_loss' in which:   # core/Loss_mano.py:245-335
             mano_loss_golden(ns, tmp)
+        if 'eval_metrics' in which:   # apps/eval_interhand.py metric loop
+            eval_metrics_golden(ns, tmp)
         if 'mano' in which:
             mano_golden(ns, tmp)
         if 'mano_grad' in which:
@@ -242,4 +329,4 @@ def main(which):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'mano', 'mano_grad'])
+    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'eval_metrics', 'mano', 'mano_grad'])

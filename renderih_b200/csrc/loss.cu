@@ -203,11 +203,11 @@ __global__ void graph_loss_finalize_kernel(const float* __restrict__ partial, in
       for (int hnd = 0; hnd < 2; ++hnd) {
         float s = 0.f;
         for (int b = 0; b < B; ++b) s += partial[((size_t)hnd * B + b) * GL_TERMS + t];
-        m[hnd] = s / cnt[t];
+        m[hnd] = cnt[t] > 0.f ? s / cnt[t] : 0.f;          // Vc == 0: no coarse level (ManoLoss, core/Loss_mano.py:184-208)
         out[1 + hnd * GL_TERMS + t] = m[hnd];
       }
       total += w[t] * (m[0] + m[1]) * 0.5f;
-      coef[t] = w[t] * 0.5f / cnt[t];
+      coef[t] = cnt[t] > 0.f ? w[t] * 0.5f / cnt[t] : 0.f;
     }
     out[0] = total;
   }
@@ -217,7 +217,7 @@ __global__ void graph_loss_scale_coef_kernel(const float* __restrict__ coef, con
 }
 
 static int fill_args(GraphLossArgs& a, const float* const* ptrs, const int* const* iptrs, float* const* gptrs, int B, int F, int Vc, int pool, float img) {
-  RIH_REQUIRE(B > 0 && F > 0 && Vc > 0 && Vc <= 1024 && pool >= 1, "graph_loss: bad sizes B=%d F=%d Vc=%d pool=%d", B, F, Vc, pool);
+  RIH_REQUIRE(B > 0 && F > 0 && Vc >= 0 && Vc <= 1024 && pool >= 1, "graph_loss: bad sizes B=%d F=%d Vc=%d pool=%d", B, F, Vc, pool);
   for (int hnd = 0; hnd < 2; ++hnd) {
     GraphLossHand& h = a.h[hnd];
     const float* const* p = ptrs + hnd * 8;
@@ -232,6 +232,7 @@ static int fill_args(GraphLossArgs& a, const float* const* ptrs, const int* cons
 
 // Forward.  ptrs: 2 x 8 float pointers {v3d_pred, v2d_pred, v3d_gt, v2d_gt, root_rel | NULL, v3d_coarse, v2d_coarse, J21}; iptrs: 2 x 2 int
 // pointers {faces [F,3], graph_perm [pool*Vc]}; weights[7]; partial: scratch [2,B,7]; out: [15] (total, 7 means per hand); coef: [7].
+// Vc == 0 (coarse pointers / perm may be NULL) drops the coarse terms: the mesh part of ManoLoss.calc_mano_loss (core/Loss_mano.py:157-182).
 // reference: GraphLoss.calc_loss + calc_loss_GCN, core/Loss.py:103-162, 201-277
 RIH_API int rih_graph_loss_fwd(const float* const* ptrs, const int* const* iptrs, int B, int F, int Vc, int pool, float img, const float* weights_host,
                                float* partial, float* out, float* coef, cudaStream_t s) {

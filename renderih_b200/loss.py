@@ -1,9 +1,12 @@
 """Training losses of the hot path: `GraphLoss` + `calc_loss_GCN` (reference core/Loss.py:20-277) and, for the 'newgraph' MANO-tail
 variant, `ManoLoss` + `mano_loss_GCN` (core/Loss_mano.py:62-335), same call signatures.
 
-This is the *caller side* of the model: small [B,778,3] tensors, expressed with torch ops on
-the tensors' device so that autograd feeds d(result) into the CUDA backward.  Fusing it into one kernel is the next
-scope row; it contains no GEMM-class work.
+This is the *caller side* of the model.  On CUDA tensors the mesh terms of both hands (vertex, 2-D, joint,
+face-normal, edge-length, coarse-level) run in the fused kernels of csrc/loss.cu (`rih_graph_loss_fwd/_bwd`: one forward and one backward
+launch instead of ~400 small torch kernels); the handful of [B,48] / [B,10] pose and shape terms of `mano_loss_GCN` are torch ops on the
+device.  The torch formulation in `GraphLoss` / `ManoLoss` is the readable statement of the same arithmetic: the host-side tests pin it to
+the reference's loss code on CPU tensors, the GPU tests pin the fused kernels to it and to the fp64 oracle (`RIH_FUSED_LOSS=0` selects it
+on the GPU for such A/B checks).
 """
 import numpy as np
 import torch
@@ -83,12 +86,15 @@ class _FusedGraphLossFn(torch.autograd.Function):
         import ctypes
         from ._lib import call
         from .ops import _stream
+        dev = v3p_l.device
+        if v3c_l is None:           # no coarse level (ManoLoss): zero-sized stand-ins keep the argument layout
+            v3c_l = v3c_r = torch.empty(v3p_l.shape[0], 0, 3, device=dev)
+            v2c_l = v2c_r = torch.empty(v3p_l.shape[0], 0, 2, device=dev)
         preds = [t.contiguous().float() for t in (v3p_l, v2p_l, v3c_l, v2c_l, v3p_r, v2p_r, v3c_r, v2c_r)]
         labels = [t.contiguous().float() for t in (v3g_l, v2g_l, v3g_r, v2g_r, root_rel)]
-        dev = preds[0].device
         B, Vc = preds[0].shape[0], preds[2].shape[1]
         F_ = tables['faces'][0].shape[0]
-        pool = tables['perm'][0].numel() // Vc
+        pool = tables['perm'][0].numel() // Vc if Vc else 1
         fp = (ctypes.c_void_p * 16)(preds[0].data_ptr(), preds[1].data_ptr(), labels[0].data_ptr(), labels[1].data_ptr(), None,
                                     preds[2].data_ptr(), preds[3].data_ptr(), tables['J21'][0].data_ptr(),
                                     preds[4].data_ptr(), preds[5].data_ptr(), labels[2].data_ptr(), labels[3].data_ptr(), labels[4].data_ptr(),
@@ -122,6 +128,7 @@ class _FusedGraphLossFn(torch.autograd.Function):
         up = d_total.contiguous().float().reshape(1)
         scratch = torch.empty(7, device=up.device)
         call('rih_graph_loss_bwd', fp, ip, gp, B, F_, Vc, pool, img, coef.data_ptr(), up.data_ptr(), scratch.data_ptr(), _stream())
+        grads = [g if g.numel() else None for g in grads]
         return (None, None, None) + tuple(grads) + (None, None, None, None, None)
 
 
@@ -133,7 +140,7 @@ def _fused_tables(gl_left, gl_right, conv_left, conv_right, device):
         t = {'faces': [], 'perm': [], 'J21': []}
         for gl, conv in ((gl_left, conv_left), (gl_right, conv_right)):
             t['faces'].append(gl.faces.to(device=device, dtype=torch.int32).contiguous())
-            perm = np.asarray(conv.graph_perm, dtype=np.int32)
+            perm = np.asarray(conv.graph_perm if conv is not None else [0], dtype=np.int32)      # ManoLoss: no coarse level, no permutation
             if perm.min() < 0 or perm.max() >= 778 or int(gl.faces.max()) >= 778:
                 raise ValueError('fused GraphLoss: graph_perm / faces index outside the 778 MANO vertices')
             t['perm'].append(torch.as_tensor(perm).to(device))
@@ -223,8 +230,30 @@ def mano_loss_GCN(cfg, epoch, graph_loss_left, graph_loss_right, converter_left,
                   result, paramsDict, handDictList, otherInfo, mask, dense, hms,
                   v2d_l, j2d_l, v2d_r, j2d_r, v3d_l, j3d_l, v3d_r, j3d_r, root_rel, img_size, lp_gt, ls_gt, rp_gt, rs_gt, upsample_weight=None):
     """core/Loss_mano.py:245-335: mesh terms on the MANO vertices, pose / shape / relative-root terms, shape regulariser."""
+    import os
     aux = {'total_loss': 0}
     ml = otherInfo['verts3d_MANO_list']
+    if result['verts3d']['left'].is_cuda and type(graph_loss_left) is ManoLoss and os.environ.get('RIH_FUSED_LOSS', '1') != '0':
+        # mesh terms of both hands (vert3d, vert2d, joint, normal, edge) from the fused kernel; the small pose / shape / root terms stay torch ops
+        w = cfg.LOSS_WEIGHT
+        alpha = 0 if epoch < w.GRAPH.NORM.NORM_EPOCH else 1
+        weights = (w.DATA.LABEL_3D, w.DATA.LABEL_2D, w.DATA.LABEL_3D, w.GRAPH.NORM.NORMAL, alpha * w.GRAPH.NORM.EDGE, 0.0, 0.0)
+        tables = _fused_tables(graph_loss_left, graph_loss_right, None, None, result['verts3d']['left'].device)
+        total, out = _FusedGraphLossFn.apply(tables, weights, img_size, result['verts3d']['left'], result['verts2d']['left'], None, None,
+                                             result['verts3d']['right'], result['verts2d']['right'], None, None, v3d_l, v2d_l, v3d_r, v2d_r, root_rel)
+        mano = {n: (out[1 + i] + out[8 + i]) / 2 for i, n in enumerate(('vert3d_loss', 'vert2d_loss', 'joint_loss', 'norm_loss', 'edge_loss'))}
+        rot = lambda p: axis_angle_to_rotmat_quat(p.reshape(-1, 3)).reshape(-1, 16, 3, 3)
+        mano['pose_loss'] = (F.mse_loss(rot(ml['left']['mano_pose']), rot(lp_gt)) + F.mse_loss(rot(ml['right']['mano_pose']), rot(rp_gt))) / 2
+        mano['shape_loss'] = (F.mse_loss(ml['left']['mano_shape'], ls_gt) + F.mse_loss(ml['right']['mano_shape'], rs_gt)) / 2
+        if upsample_weight is not None:
+            mano['upsample_norm_loss'] = graph_loss_left.upsample_weight_loss(upsample_weight)
+        else:
+            mano['upsample_norm_loss'] = torch.zeros_like(total)
+        mano['rootrel_loss'] = w.DATA.MANO_REL * F.mse_loss(otherInfo['root_rel'], root_rel)
+        mano['regularize_loss'] = 0.005 * torch.mean(torch.sum(ml['left']['mano_shape'] ** 2) + torch.sum(ml['right']['mano_shape'] ** 2))
+        total = total + w.DATA.MANO_POSE * mano['pose_loss'] + w.DATA.MANO_SHAPE * mano['shape_loss'] + mano['rootrel_loss'] + mano['regularize_loss'] \
+            + w.NORM.UPSAMPLE * mano['upsample_norm_loss']
+        return total, aux, mano, {}
     v3d_r = v3d_r + root_rel.unsqueeze(1)
     left = graph_loss_left.calc_loss(converter_left, v3d_l, v2d_l, result['verts3d']['left'], result['verts2d']['left'], None, None, img_size,
                                      ml['left']['mano_pose'], ml['left']['mano_shape'], lp_gt, ls_gt)

@@ -119,4 +119,43 @@ def test_fused_graph_loss_in_cuda_graph():
     t_graph, g_graph = t_static.clone(), g_static.clone()
     t_eager, g_eager = run()
     assert torch.allclose(t_graph, t_eager, rtol=1e-6)
-    assert torch.allclose(g_graph, g_eager, rtol=1e-5, atol=1e-9)
+    # the face-gradient scatter uses shared-memory atomics: summation order (hence the last bits) varies from launch to launch
+    assert float((g_graph - g_eager).abs().max()) <= 1e-5 * float(g_eager.abs().max())
+
+
+@pytest.mark.parametrize('epoch', [0, 60])
+def test_fused_mano_loss_matches_reference_golden(epoch):
+    """mano_loss_GCN with the fused mesh terms against the golden produced by the unmodified core/Loss_mano.mano_loss_GCN
+    (tests/golden/mano_loss_synth.pt: total, per-term values, gradients of every prediction tensor) and against the torch formulation."""
+    from oracle import fixtures
+    from renderih_b200 import assets as A
+    from renderih_b200.config import load_cfg
+    from renderih_b200.loss import ManoLoss, mano_loss_GCN
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'mano_loss_synth.pt'), weights_only=False)[epoch]
+    cfg = load_cfg()
+    ml, mr = A.synthetic_mano(0, 'left'), A.synthetic_mano(0, 'right')
+    J = {s: torch.from_numpy(np.asarray(m['J_regressor'].todense(), dtype='float32')) for s, m in (('left', ml), ('right', mr))}
+    gl, gr = ManoLoss(J['left'], ml['f'], 4, 'cuda'), ManoLoss(J['right'], mr['f'], 4, 'cuda')
+    res = {}
+    for fused in (True, False):
+        os.environ['RIH_FUSED_LOSS'] = '1' if fused else '0'
+        try:
+            pred, lab = fixtures.make_mano_loss_case(2)
+            pred = {k: v.cuda().requires_grad_(True) for k, v in pred.items()}
+            lab = {k: v.cuda() for k, v in lab.items()}
+            result, params, hlist, other = fixtures.mano_loss_inputs(pred)
+            z = torch.zeros(2, 21, 3, device='cuda')
+            total, _, terms, _ = mano_loss_GCN(cfg, epoch, gl, gr, None, None, result, params, hlist, other, None, None, None,
+                                               lab['v2d_l'], z[..., :2], lab['v2d_r'], z[..., :2], lab['v3d_l'], z, lab['v3d_r'], z,
+                                               lab['root_rel'], 256, lab['lp_gt'], lab['ls_gt'], lab['rp_gt'], lab['rs_gt'])
+            total.backward()
+            res[fused] = (float(total.detach()), {k: float(v.detach()) for k, v in terms.items()}, {k: v.grad.cpu() for k, v in pred.items()})
+        finally:
+            os.environ.pop('RIH_FUSED_LOSS', None)
+    for fused in (True, False):
+        total, terms, grads = res[fused]
+        assert abs(total - gold['total']) <= 2e-5 * abs(gold['total']), (fused, total, gold['total'])
+        for k, v in gold['terms'].items():
+            assert abs(terms[k] - v) <= 2e-5 * abs(v) + 1e-9, (fused, k)
+        for k, g in gold['grads'].items():
+            assert float((grads[k] - g).norm()) <= 2e-5 * float(g.norm()) + 1e-12, (fused, k)

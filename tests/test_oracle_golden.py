@@ -210,3 +210,39 @@ def test_newgraph_oracle_matches_reference_golden(newgraph_setup):
         if k.endswith('w_ks.bias'):
             continue
         assert abs(float(mine.norm()) - g['norm']) / max(g['norm'], 1e-6) < 2e-3, (k, float(mine.norm()), g['norm'])
+
+
+def test_eval_metrics_oracle_matches_reference_golden():
+    """oracle/metrics_ref.py against the numbers produced by executing apps/eval_interhand.py's own loop body and reductions
+    (tests/golden/eval_metrics_synth.pt, two batches of 4 and 2 samples; the 2-sample batch exercises the reference's layout quirk)."""
+    import numpy as np
+    from oracle import metrics_ref
+    from renderih_b200 import assets as A
+    gold = torch.load(os.path.join(GOLD, 'eval_metrics_synth.pt'), weights_only=False)
+    case = fixtures.make_eval_case(6)
+    J = {s: metrics_ref.joint_regressor21(torch.from_numpy(np.asarray(A.synthetic_mano(0, s)['J_regressor'].todense(), dtype='float32'))) for s in ('left', 'right')}
+    outs = [metrics_ref.eval_batch(J['left'], J['right'], *[case[k][lo:hi] for k in ('pred_left', 'pred_right', 'gt_left', 'gt_right')])
+            for lo, hi in ((0, 4), (4, 6))]
+    for side in ('left', 'right'):
+        for k, v in gold['per_element'][side].items():
+            o = torch.cat([b[side][k] for b in outs])
+            assert o.shape == v.shape
+            assert float((o - v).abs().max()) <= 1e-6 * float(v.abs().max()), (side, k)
+    assert torch.equal(torch.cat([b['mrrpe'] for b in outs]), gold['mrrpe'])
+    cd = torch.cat([b['cdev'] for b in outs])
+    assert torch.isnan(cd[-1]) and torch.isnan(gold['cdev'][-1])
+    assert torch.allclose(cd[:-1], gold['cdev'][:-1], rtol=1e-6)
+    for k, name in (('double_pa_joint', 'pa_joint'), ('double_pa_mesh', 'pa_mesh')):
+        assert np.allclose(np.concatenate([b[k] for b in outs]), gold['double_per_sample'][name].numpy(), rtol=1e-6)
+    s = metrics_ref.summarize(outs)
+    g = gold['summary_mm']
+    for side in ('left', 'right'):
+        for k in ('ori_mpjpe', 'ori_mpvpe', 'mpjpe', 'mpvpe', 'pa_mpjpe', 'pa_mpvpe'):
+            assert abs(s[side][k] - g['%s_%s' % (k, side)]) <= 1e-6 * g['%s_%s' % (k, side)], (side, k)
+    for k, gk in (('double_pa_joint', 'double_pa_mpjpe'), ('double_pa_mesh', 'double_pa_mpvpe'), ('double_joint', 'double_mpjpe'), ('double_mesh', 'double_mpvpe')):
+        assert abs(s[k] - g[gk]) <= 1e-6 * g[gk], k
+    # without the reference's batch-size quirk the 4-sample batch is unchanged and the 2-sample one differs (documented deviation of the kernel)
+    plain = metrics_ref.eval_batch(J['left'], J['right'], *[case[k][4:6] for k in ('pred_left', 'pred_right', 'gt_left', 'gt_right')], batch_quirk=False)
+    assert float((plain['left']['pajoints_loss'] - outs[1]['left']['pajoints_loss']).abs().max()) > 1e-4
+    plain4 = metrics_ref.eval_batch(J['left'], J['right'], *[case[k][0:4] for k in ('pred_left', 'pred_right', 'gt_left', 'gt_right')], batch_quirk=False)
+    assert torch.equal(plain4['left']['pajoints_loss'], outs[0]['left']['pajoints_loss'])
