@@ -1,7 +1,7 @@
 """Reference-equivalent eager PyTorch on the GPU (the op sequence of the reference model via oracle/model_ref.py run on
 CUDA tensors with autograd): images/s of forward + calc_loss_GCN + backward at batch 64.  This is the 'reference PyTorch-GPU'
 number north_star compares against (cuDNN TF32 convolutions by default, exactly like the reference); it is NOT the bench's
-reference arm (that one is the CPU path).   usage: python tools/torch_gpu_baseline.py [--batch 64] [--no-tf32]"""
+reference arm (that one is the CPU path).   usage: python tests/baselines/torch_gpu_baseline.py [--batch 64] [--no-tf32]"""
 import argparse
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import fixtures, model_ref  # noqa: E402
 from renderih_b200 import assets as A   # noqa: E402
