@@ -181,3 +181,24 @@ def make_eval_case(batch=6, seed=SEED):
         c = v.mean(1, keepdim=True)
         return s * (v - c).bmm(R.transpose(1, 2)) + c + r(batch, 1, 3) * 0.02 + r(batch, 778, 3) * 0.004
     return {'pred_left': perturb(gt_l), 'pred_right': perturb(gt_r), 'gt_left': gt_l, 'gt_right': gt_r}
+
+
+def make_augment_case(n=3, size=256, seed=SEED):
+    """Seeded loader inputs for the augmentation golden: smooth random uint8 BGR frames and a hand_dict shaped like the datasets' (core/loader.py:105-113)."""
+    rng = np.random.RandomState(seed + 11)
+    frames, dicts = [], []
+    for i in range(n):
+        f = rng.randint(0, 256, (size // 8, size // 8, 3)).astype(np.float32)
+        f = np.kron(f, np.ones((8, 8, 1), np.float32))
+        k = np.ones(5, np.float32) / 5                         # separable box blur: smooth gradients exercise the interpolation weights
+        for ax in (0, 1):
+            f = np.apply_along_axis(lambda m: np.convolve(m, k, mode='same'), ax, f)
+        f = f + rng.randint(0, 40, f.shape)
+        frames.append(np.clip(f, 0, 255).astype(np.uint8))
+        hd = {}
+        for side in ('left', 'right'):
+            j3 = rng.randn(21, 3).astype(np.float32) * 0.04
+            hd[side] = {'verts2d': (rng.rand(778, 2) * size).astype(np.float32), 'joints2d': (rng.rand(21, 2) * size).astype(np.float32),
+                        'verts3d': rng.randn(778, 3).astype(np.float32) * 0.04, 'joints3d': j3}
+        dicts.append(hd)
+    return frames, dicts

@@ -304,8 +304,65 @@ def eval_metrics_golden(ns, tmp):
     print('eval_metrics golden:', {k: round(v, 4) for k, v in out['summary_mm'].items()})
 
 
+def augment_golden(ns, tmp):
+    """Training-time loader path, produced by EXECUTING the reference's own `handDataset.augm_params` / `handDataset.process_data`
+    (core/loader.py:96-220, compiled from the file under /root/reference -- the module itself cannot be imported here: imgaug, dataset
+    classes) with the reference's `imgUtils` (utils/manoutils.py) and this container's cv2 / torchvision.  The random draws of each
+    sample are recorded (augm_params outputs; the `a`, `b` of imgUtils.add_noise replayed from the saved generator states)."""
+    import ast
+    import random
+    import types
+    import cv2 as cv
+    import torchvision.transforms as transforms
+    from utils.manoutils import imgUtils
+    from dataset.dataset_utils import BONE_LENGTH
+    path = os.path.join(rb.REF_ROOT, 'core', 'loader.py')
+    tree = ast.parse(open(path).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'handDataset'][0]
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ('augm_params', 'process_data')]
+    assert len(fns) == 2
+    env = {'imgUtils': imgUtils, 'cv': cv, 'np': np, 'torch': torch, 'random': random}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), path, 'exec'), env)
+    me = types.SimpleNamespace(train=True, seq=None, noise=0.0, flip=True, theta=[-90, 90], scale=[0.75, 1.25], uv=[-10, 10], bone_length=BONE_LENGTH,
+                               normalize_img=transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225]))
+    draws = {}
+    orig_noise = imgUtils.add_noise
+
+    def recording_noise(img, noise=0.0, scale=255.0, alpha=0.3, beta=0.05):
+        st_np, st_py = np.random.get_state(), random.getstate()
+        draws['a'] = np.random.uniform(1 - alpha, 1 + alpha, 3)
+        draws['b'] = scale * beta * (2 * random.random() - 1)
+        np.random.set_state(st_np); random.setstate(st_py)
+        return orig_noise(img, noise=noise, scale=scale, alpha=alpha, beta=beta)
+
+    def recording_params():
+        out = env['augm_params'](me)
+        draws['params'] = out
+        return out
+    me.augm_params = recording_params
+    imgUtils.add_noise = staticmethod(recording_noise)
+    frames, dicts = fixtures.make_augment_case(3)
+    samples = []
+    try:
+        for i, (f, hd) in enumerate(zip(frames, dicts)):
+            random.seed(100 + i); np.random.seed(100 + i)
+            out = env['process_data'](me, f.copy(), {s: {k: v.copy() for k, v in d.items()} for s, d in hd.items()})
+            theta, scale, u, v, flip = draws['params']
+            names = ('ori_img', 'imgTensor', 'v2d_l', 'j2d_l', 'v2d_r', 'j2d_r', 'v3d_l', 'j3d_l', 'v3d_r', 'j3d_r', 'root_rel')
+            rec = dict(zip(names, out))
+            u8 = (rec.pop('ori_img') * 255).round().to(torch.uint8).permute(1, 2, 0).contiguous()        # exact: ori_img = uint8 / 255
+            samples.append({'theta': theta, 'scale': scale, 'u': u, 'v': v, 'flip': bool(flip), 'a': draws['a'].copy(), 'b': float(draws['b']),
+                            'final_u8_bgr': u8, 'imgTensor': rec.pop('imgTensor') if i == 0 else (rec.pop('imgTensor'), None)[1], 'labels': rec})
+    finally:
+        imgUtils.add_noise = staticmethod(orig_noise)
+    torch.save({'meta': {'source': 'core/loader.py handDataset.augm_params / process_data executed in place; utils/manoutils.imgUtils',
+                         'cv2': cv.__version__, 'torch': torch.__version__, 'bone_length': BONE_LENGTH}, 'samples': samples},
+               os.path.join(GOLD, 'augment_synth.pt'))
+    print('augment golden:', [(round(s['theta'], 2), round(s['scale'], 3), s['flip']) for s in samples])
+
+
 def main(which):
-    """which: any of 'resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'eval_metrics', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
+    """which: any of 'resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'eval_metrics', 'augment', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
     os.makedirs(GOLD, exist_ok=True)
     ns = rb.import_reference()
     with tempfile.TemporaryDirectory() as tmp:
@@ -320,6 +377,8 @@ def main(which):
             newgraph_golden(ns, tmp)
         if 'mano_loss' in which:   # core/Loss_mano.py:245-335
             mano_loss_golden(ns, tmp)
+        if 'augment' in which:        # core/loader.py augmentation + normalisation
+            augment_golden(ns, tmp)
         if 'eval_metrics' in which:   # apps/eval_interhand.py metric loop
             eval_metrics_golden(ns, tmp)
         if 'mano' in which:
@@ -329,4 +388,4 @@ def main(which):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'eval_metrics', 'mano', 'mano_grad'])
+    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'eval_metrics', 'augment', 'mano', 'mano_grad'])

@@ -246,3 +246,33 @@ def test_eval_metrics_oracle_matches_reference_golden():
     assert float((plain['left']['pajoints_loss'] - outs[1]['left']['pajoints_loss']).abs().max()) > 1e-4
     plain4 = metrics_ref.eval_batch(J['left'], J['right'], *[case[k][0:4] for k in ('pred_left', 'pred_right', 'gt_left', 'gt_right')], batch_quirk=False)
     assert torch.equal(plain4['left']['pajoints_loss'], outs[0]['left']['pajoints_loss'])
+
+
+def test_augment_oracle_matches_reference_golden_and_cv2():
+    """oracle/augment_ref.py (fixed-point restatement of cv2.warpAffine + the loader's noise / flip / normalise / label steps) against
+    tests/golden/augment_synth.pt = outputs of the reference's own handDataset.process_data, bit-exact for the images; and, when cv2 is
+    importable, against cv2.warpAffine directly over a sweep of the loader's augmentation ranges and some extreme maps."""
+    import numpy as np
+    from oracle import augment_ref as ar
+    gold = torch.load(os.path.join(GOLD, 'augment_synth.pt'), weights_only=False)
+    frames, dicts = fixtures.make_augment_case(3)
+    for i, s in enumerate(gold['samples']):
+        img, ori, net, M = ar.process_image(frames[i], s['theta'], s['scale'], s['u'], s['v'], s['a'], s['b'], s['flip'])
+        final = img[:, ::-1] if s['flip'] else img
+        assert np.array_equal(final, s['final_u8_bgr'].numpy()), i
+        if s['imgTensor'] is not None:
+            assert np.array_equal(net, s['imgTensor'].numpy())
+        lab = ar.process_labels(dicts[i], s['theta'], M, s['flip'], bone_length=gold['meta']['bone_length'])
+        for k, v in s['labels'].items():
+            assert np.array_equal(lab[k], v.numpy()), (i, k)
+    try:
+        import cv2
+    except ImportError:
+        return
+    rng = np.random.RandomState(5)
+    cases = [(0, 1, 0, 0), (90, 1, 0, 0), (-90, 0.5, 100, -100), (45, 3.0, 0, 0), (180, 1, 0.5, 0.5), (0, 1, 300, 0)]
+    cases += [(rng.uniform(-90, 90), rng.uniform(0.75, 1.25), rng.uniform(-10, 10), rng.uniform(-10, 10)) for _ in range(12)]
+    for j, (theta, sc, u, v) in enumerate(cases):
+        img = frames[j % 3] if j % 2 else rng.randint(0, 256, (256, 256, 3)).astype(np.uint8)
+        M = ar.get_affine_mat(theta, sc, u, v, 256, 256)
+        assert np.array_equal(cv2.warpAffine(src=img, M=M[0:2, :], dsize=(256, 256)), ar.warp_affine_u8(img, M[0:2, :])), (theta, sc, u, v)
