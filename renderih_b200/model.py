@@ -94,19 +94,26 @@ class ResNetSimple_decoder(nn.Module):
             self.models.append(nn.Sequential(*layers))
         self.final_layer = _cl(nn.Conv2d(fDim[-1], out_dim, kernel_size=1, stride=1, padding=0))
 
+    def stage(self, i, x, N, H):
+        """Stage i of the reference's Sequential list (encoder.py:33-47): [bilinear x2] -> conv -> ReLU -> BN.  -> (x, H)"""
+        seq = self.models[i]
+        if self.direction[i] == 'up':
+            x = ops.bilinear2x(x, N, H, H)
+            H = 2 * H
+            conv, bn = seq[1], seq[3]
+        else:
+            conv, bn = seq[0], seq[2]
+        return _conv_relu_bn(x, conv, bn, N, H, H, self.training), H
+
+    def head(self, x, N, H):
+        return ops.conv2d(x, self.final_layer.weight, self.final_layer.bias, N, H, H)
+
     def forward(self, x, N, H):
         fmaps = []
-        for i, seq in enumerate(self.models):
-            if self.direction[i] == 'up':
-                x = ops.bilinear2x(x, N, H, H)
-                H = 2 * H
-                conv, bn = seq[1], seq[3]
-            else:
-                conv, bn = seq[0], seq[2]
-            x = _conv_relu_bn(x, conv, bn, N, H, H, self.training)
+        for i in range(len(self.models)):
+            x, H = self.stage(i, x, N, H)
             fmaps.append((x, H))
-        out = ops.conv2d(x, self.final_layer.weight, self.final_layer.bias, N, H, H)
-        return out, fmaps, H
+        return self.head(x, N, H), fmaps, H
 
 
 class ResNetSimple(nn.Module):
@@ -161,7 +168,8 @@ class ResNetSimple(nn.Module):
         out, _ = _conv_bn(out, blk.conv3, blk.bn3, N, Ho, Ho, tr, relu=True, res=identity)
         return out, Ho
 
-    def forward(self, img):
+    def trunk(self, img):
+        """stem + layer1..4 (encoder.py:107-118) -> [x1 (8x8), x2, x3, x4 (64x64)] as (NHWC rows, H) pairs."""
         N, C, H, W = img.shape
         assert H == W
         r = self.resnet
@@ -175,14 +183,22 @@ class ResNetSimple(nn.Module):
                 x, H = self._bottleneck(blk, x, N, H)
             feats.append((x, H))
         x4, x3, x2, x1 = feats
-        img_fmaps = [x1, x2, x3, x4]
+        return [x1, x2, x3, x4]
+
+    def aux_outputs(self, hms, out, N, Hh):
+        """NHWC head outputs -> the NCHW hms / mask / dense maps of encoder.py:121-125."""
+        return (ops.nhwc_to_nchw(hms, N, Hh, Hh), ops.nhwc_to_nchw(out, N, Hh, Hh, 0, self.handNum),
+                ops.nhwc_to_nchw(out, N, Hh, Hh, self.handNum, out.shape[1] - self.handNum))
+
+    def forward(self, img):
+        N = img.shape[0]
+        img_fmaps = self.trunk(img)
         if not self.aux_heads:
             return img_fmaps
+        x1 = img_fmaps[0]
         hms, hms_fmaps, Hh = self.hms_decoder(x1[0], N, x1[1])
         out, dp_fmaps, _ = self.dp_decoder(x1[0], N, x1[1])
-        hms = ops.nhwc_to_nchw(hms, N, Hh, Hh)
-        mask = ops.nhwc_to_nchw(out, N, Hh, Hh, 0, self.handNum)
-        dp = ops.nhwc_to_nchw(out, N, Hh, Hh, self.handNum, out.shape[1] - self.handNum)
+        hms, mask, dp = self.aux_outputs(hms, out, N, Hh)
         return hms, mask, dp, img_fmaps, hms_fmaps, dp_fmaps
 
 
@@ -204,18 +220,20 @@ class resnet_mid(nn.Module):
     def get_info(self):
         return {'global_feature_dim': self.global_feature_dim, 'fmaps_dim': self.fmaps_dim}
 
+    def level(self, i, img_fmaps, hms_fmap, dp_fmap, N):
+        """Level i of encoder.py:168-172: cat(hms fmap, dp fmap[, trunk feature]) -> conv1x1 -> ReLU -> BN.  -> (x, H)"""
+        seq = self.convs[i]
+        parts = [hms_fmap[0], dp_fmap[0]]
+        if i > 0:
+            parts.append(img_fmaps[i][0])
+        H = hms_fmap[1]
+        x = ops.concat_channels(parts)
+        return _conv_relu_bn(x, seq[0], seq[2], N, H, H, self.training), H
+
     def forward(self, img_fmaps, hms_fmaps, dp_fmaps, N):
         x1, H1 = img_fmaps[0]
         global_feature = ops.global_avgpool(x1, N, H1 * H1)
-        fmaps = []
-        for i, seq in enumerate(self.convs):
-            parts = [hms_fmaps[i][0], dp_fmaps[i][0]]
-            if i > 0:
-                parts.append(img_fmaps[i][0])
-            H = hms_fmaps[i][1]
-            x = ops.concat_channels(parts)
-            fmaps.append((_conv_relu_bn(x, seq[0], seq[2], N, H, H, self.training), H))
-        return global_feature, fmaps
+        return global_feature, [self.level(i, img_fmaps, hms_fmaps[i], dp_fmaps[i], N) for i in range(len(self.convs))]
 
 
 # ============================================================================ two-hand concurrency
@@ -674,9 +692,13 @@ class HandNET_GCN(nn.Module):
         if self.training:
             ops.seed_state.advance(img.device)
         N = img.shape[0]
-        hms, mask, dp, img_fmaps, hms_fmaps, dp_fmaps = self.encoder(img)
-        global_feature, fmaps = self.mid_model(img_fmaps, hms_fmaps, dp_fmaps, N)
-        result, paramsDict, handDictList, otherInfo = self.decoder(global_feature, fmaps)
+        aux = AuxStream.get(img.device) if (type(self.encoder) is ResNetSimple and self.encoder.aux_heads and type(self.mid_model) is resnet_mid) else None
+        if aux is not None:
+            result, paramsDict, handDictList, otherInfo, hms, mask, dp = self._forward_pipelined(img, N, aux)
+        else:
+            hms, mask, dp, img_fmaps, hms_fmaps, dp_fmaps = self.encoder(img)
+            global_feature, fmaps = self.mid_model(img_fmaps, hms_fmaps, dp_fmaps, N)
+            result, paramsDict, handDictList, otherInfo = self.decoder(global_feature, fmaps)
         if hms is not None:
             otherInfo['hms'] = hms
         if mask is not None:
@@ -684,6 +706,67 @@ class HandNET_GCN(nn.Module):
         if dp is not None:
             otherInfo['dense'] = dp
         return result, paramsDict, handDictList, otherInfo
+
+
+    def _forward_pipelined(self, img, N, aux):
+        """Same arithmetic as encoder -> mid_model -> decoder, issued as two concurrent pipelines: everything behind the trunk on the
+        convolution side (heat-map / dense-pose decoder stages at 8, 16, 32, 64 px, the mid 1x1 convs, the aux heads) runs on the aux stream
+        and publishes each mid level with an event; the token decoder (main + hand streams) waits for level i only when DualGraph layer i
+        starts.  DualGraph layer 1 overlaps the 16 px stage, layer 2 the 32 px stage, layer 3 the 64 px stage + heads, which nothing in the
+        decoder reads.  autograd replays every node on its forward stream, so the backward pass is pipelined the same way."""
+        enc, mid = self.encoder, self.mid_model
+        dev = img.device
+        img_fmaps = enc.trunk(img)
+        x1, H1 = img_fmaps[0]
+        global_feature = ops.global_avgpool(x1, N, H1 * H1)
+        main = torch.cuda.current_stream(dev)
+        aux.wait_stream(main)
+        fmaps, events = [], []
+        with torch.cuda.stream(aux):
+            xh, xd, H = x1, x1, H1
+            for i in range(len(mid.convs)):
+                xh, Hn = enc.hms_decoder.stage(i, xh, N, H)
+                xd, _ = enc.dp_decoder.stage(i, xd, N, H)
+                H = Hn
+                fmaps.append(mid.level(i, img_fmaps, (xh, H), (xd, H), N))
+                ev = torch.cuda.Event()
+                ev.record(aux)
+                events.append(ev)
+            hms, mask, dp = enc.aux_outputs(enc.hms_decoder.head(xh, N, H), enc.dp_decoder.head(xd, N, H), N, H)
+        out = self.decoder(global_feature, _StreamedFmaps(fmaps, events))
+        main.wait_stream(aux)
+        for t in (hms, mask, dp) + tuple(f[0] for f in fmaps):
+            t.record_stream(main)
+        return out + (hms, mask, dp)
+
+
+class AuxStream:
+    """Side stream of HandNET_GCN._forward_pipelined; `RIH_AUX_STREAM=0` (or `RIH_HAND_STREAMS=0`) selects the sequential forward."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, device):
+        import os
+        if os.environ.get('RIH_AUX_STREAM', '0') == '0' or HandStreams.get(device) is None:
+            return None
+        key = (device.type, device.index)
+        if key not in cls._cache:
+            cls._cache[key] = torch.cuda.Stream(device=device)
+        return cls._cache[key]
+
+
+class _StreamedFmaps(list):
+    """List of (feature map, H) pairs produced on another stream: the consuming stream waits for a level's event when that level is read."""
+
+    def __init__(self, fmaps, events):
+        super().__init__(fmaps)
+        self.events = list(events)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return _StreamedFmaps(list.__getitem__(self, i), self.events[i])
+        torch.cuda.current_stream().wait_event(self.events[i])
+        return list.__getitem__(self, i)
 
 
 def load_encoder(cfg):
