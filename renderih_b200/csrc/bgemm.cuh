@@ -15,6 +15,7 @@ int bgemm_tf32(const BOperand& a, int a_mn, const BOperand& b, int b_mn, const B
                cudaStream_t s);
 void set_nsplit(int n);
 void set_acc_scale(float s);
+int set_stream_cta_limit(cudaStream_t s, int ctas);   // cap the persistent grid of GEMMs launched on stream s (0 = no cap)
 
 }  // namespace tc
 }  // namespace rih

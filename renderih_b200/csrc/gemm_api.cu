@@ -11,6 +11,7 @@ int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long
               int allow_splitk, cudaStream_t s);
 bool conv_tc_supported(const ConvGeom& g, int which);
 void set_nsplit(int n);
+int set_stream_cta_limit(cudaStream_t s, int ctas);
 void set_acc_scale(float s);
 extern int g_stats_fused;
 long long conv_tc_workspace(const ConvGeom& g, int which);
@@ -31,6 +32,14 @@ static int g_mode[2] = {0, 0};
 RIH_API int rih_set_gemm_mode(int conv_mode, int linear_mode) {
   RIH_REQUIRE(conv_mode >= 0 && conv_mode <= 4 && linear_mode >= 0 && linear_mode <= 4, "set_gemm_mode: modes must be 0 (simt), 1 (tf32), 2 (tf32x3), 3 (tf32rn) or 4 (tf32c)");
   g_mode[0] = conv_mode; g_mode[1] = linear_mode;
+  return 0;
+}
+// Cap the persistent grid (CTAs = SMs used) of every tensor-core GEMM / convolution launched on `stream`; 0 removes the cap.  Used for the
+// convolution-side pipeline of HandNET_GCN._forward_pipelined so the concurrently running token decoder keeps some SMs.  (No reference
+// counterpart: scheduling only, results are unchanged.)
+RIH_API int rih_set_stream_cta_limit(cudaStream_t stream, int ctas) {
+  RIH_REQUIRE(ctas >= 0, "set_stream_cta_limit: ctas must be >= 0");
+  RIH_REQUIRE(tc::set_stream_cta_limit(stream, ctas) == 0, "set_stream_cta_limit: more than 4 capped streams");
   return 0;
 }
 static inline bool use_tc(int which) {

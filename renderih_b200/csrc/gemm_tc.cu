@@ -84,6 +84,18 @@ static int g_persistent = 1;     // 0 = one CTA per tile (non-persistent kernel;
 void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
 void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
+// Optional cap on the persistent grid of GEMMs launched on a given stream (rih_set_stream_cta_limit): a convolution pipeline that runs
+// concurrently with the latency-bound token decoder leaves the remaining SMs to it instead of occupying all 148 for every tile loop.
+static cudaStream_t g_cap_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+static int g_cap_ctas[4] = {0, 0, 0, 0};
+int set_stream_cta_limit(cudaStream_t s, int ctas) {
+  for (int i = 0; i < 4; ++i) if (g_cap_stream[i] == s || g_cap_ctas[i] == 0) { g_cap_stream[i] = s; g_cap_ctas[i] = ctas > 0 ? ctas : 0; return 0; }
+  return 1;
+}
+static inline int stream_cta_limit(cudaStream_t s, int num_sms) {
+  for (int i = 0; i < 4; ++i) if (g_cap_ctas[i] > 0 && g_cap_stream[i] == s) return g_cap_ctas[i] < num_sms ? g_cap_ctas[i] : num_sms;
+  return num_sms;
+}
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep, const Producer& prod, int M, int N, int num_kb, int splits,
                       int kb_per_split, cudaStream_t s, const CUtensorMap* c_map = nullptr) {
@@ -124,7 +136,8 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep,
     if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
     const int tiles_n = cdiv(N, BN), tiles_m = cdiv(M, BM);
     const long long total = (long long)tiles_n * tiles_m * splits;
-    const int ctas = (int)(total < num_sms ? total : num_sms);
+    const int cap = stream_cta_limit(s, num_sms);
+    const int ctas = (int)(total < cap ? total : cap);
     if (ep.stats && !(tma_epi && splits == 1)) ep.stats = nullptr;
     g_stats_fused = ep.stats != nullptr;
     pk<<<ctas, persistent_threads<NSPLIT>(), smem_bytes<BN, NSPLIT>(), s>>>(ta, tb, tc_, ep, prod, num_kb, kb_per_split, tiles_m, tiles_n, splits, tma_epi);
