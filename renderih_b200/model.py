@@ -251,7 +251,8 @@ class HandStreams:
             return None
         key = (device.type, device.index)
         if key not in cls._cache:
-            cls._cache[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+            prio = int(os.environ.get('RIH_HAND_PRIORITY', '-1'))      # -1: the (latency-bound) hand branches are scheduled ahead of concurrent convolution work
+            cls._cache[key] = (torch.cuda.Stream(device=device, priority=prio), torch.cuda.Stream(device=device, priority=prio))
             try:      # parameters shared by both hands accumulate gradients from two streams by design; silence torch's advisory
                 torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
             except Exception:
@@ -733,7 +734,16 @@ class HandNET_GCN(nn.Module):
                 ev.record(aux)
                 events.append(ev)
             hms, mask, dp = enc.aux_outputs(enc.hms_decoder.head(xh, N, H), enc.dp_decoder.head(xd, N, H), N, H)
-        out = self.decoder(global_feature, _StreamedFmaps(fmaps, events))
+        dec = AuxStream.decoder_stream(dev)
+        if dec is None:
+            out = self.decoder(global_feature, _StreamedFmaps(fmaps, events))
+        else:       # the token decoder's joint (two-hand) parts on a high-priority stream as well, like its hand branches
+            dec.wait_stream(main)
+            with torch.cuda.stream(dec):
+                out = self.decoder(global_feature, _StreamedFmaps(fmaps, events))
+            main.wait_stream(dec)
+            _record_stream_tree(out, main)
+            global_feature.record_stream(dec)
         main.wait_stream(aux)
         for t in (hms, mask, dp) + tuple(f[0] for f in fmaps):
             t.record_stream(main)
@@ -758,6 +768,31 @@ class AuxStream:
                 from ._lib import call
                 call('rih_set_stream_cta_limit', cls._cache[key].cuda_stream, ctas)
         return cls._cache[key]
+
+    _dec = {}
+
+    @classmethod
+    def decoder_stream(cls, device):
+        import os
+        prio = int(os.environ.get('RIH_DEC_PRIORITY', '0'))
+        if prio == 0:
+            return None
+        key = (device.type, device.index)
+        if key not in cls._dec:
+            cls._dec[key] = torch.cuda.Stream(device=device, priority=prio)
+        return cls._dec[key]
+
+
+def _record_stream_tree(obj, stream):
+    if torch.is_tensor(obj):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream_tree(v, stream)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_stream_tree(v, stream)
 
 
 class _StreamedFmaps(list):
