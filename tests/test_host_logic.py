@@ -175,3 +175,43 @@ def test_mano_loss_matches_reference_golden():
         for k, v in g['grads'].items():
             d = (pred[k].grad - v).abs().max() / v.abs().max().clamp_min(1e-12)
             assert float(d) < 1e-5, (epoch, k, float(d))
+
+
+def test_input_host_helpers_match_reference_golden():
+    """Host-side mirrors of the loader code (renderih_b200/input.py): get_affine_mat == imgUtils.get_affine_mat bit for bit (through the
+    oracle, which is pinned to the reference's process_data golden), the cv::warpAffine matrix inversion, and prepare_labels against the
+    labels the reference's handDataset.process_data produced (tests/golden/augment_synth.pt)."""
+    import numpy as np
+    import torch
+    from oracle import augment_ref, fixtures
+    from renderih_b200 import input as I
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'augment_synth.pt'), weights_only=False)
+    S = gold['samples']
+    rng = np.random.RandomState(0)
+    for _ in range(20):
+        th, sc, u, v = rng.uniform(-90, 90), rng.uniform(0.5, 1.5), rng.uniform(-20, 20), rng.uniform(-20, 20)
+        M = I.get_affine_mat(th, sc, u, v, 256, 256)
+        assert M.dtype == np.float32 and np.array_equal(M, augment_ref.get_affine_mat(th, sc, u, v, 256, 256))
+        assert np.array_equal(I._invert_affine(M[0:2]), augment_ref.invert_affine(M[0:2]))
+    _, dicts = fixtures.make_augment_case(3)
+    hd = {s: {k: torch.from_numpy(np.stack([d[s][k] for d in dicts])) for k in dicts[0][s]} for s in ('left', 'right')}
+    A = np.stack([I.get_affine_mat(s['theta'], s['scale'], s['u'], s['v'], 256, 256) for s in S])
+    lab = I.prepare_labels(hd, [s['theta'] for s in S], A, [s['flip'] for s in S], bone_length=gold['meta']['bone_length'])
+    assert list(lab.keys()) == ['root_rel', 'v2d_l', 'v2d_r', 'v3d_l', 'v3d_r', 'j2d_l', 'j2d_r', 'j3d_l', 'j3d_r']
+    for k in lab:
+        ref = torch.stack([s['labels'][k] for s in S])
+        assert float((lab[k] - ref).abs().max()) <= 2e-6 * float(ref.abs().max()), k
+
+
+def test_metrics_jr_matches_oracle():
+    import numpy as np
+    import torch
+    from oracle import metrics_ref
+    from renderih_b200 import assets as A
+    from renderih_b200.metrics import Jr, SAMPLE_FIELDS
+    J16 = torch.from_numpy(np.asarray(A.synthetic_mano(0, 'left')['J_regressor'].todense(), dtype='float32'))
+    jr = Jr(J16, device='cpu')
+    assert torch.equal(jr.J_regressor, metrics_ref.joint_regressor21(J16))
+    v = torch.randn(3, 778, 3)
+    assert torch.allclose(jr(v), torch.matmul(metrics_ref.joint_regressor21(J16), v))
+    assert len(SAMPLE_FIELDS) == 8
