@@ -228,7 +228,7 @@ class HandNET_GCN(nn.Module):
             ops.seed_state.advance(img.device)
         N = img.shape[0]
         img_fmaps = self.encoder(img)
-        aux = AuxStream.get(img.device) if (type(self.mid_model) is resnet_mid and os.environ.get('RIH_AUX_STREAM_GRAPH', '0') != '0') else None
+        aux = AuxStream.get(img.device) if (type(self.mid_model) is resnet_mid and os.environ.get('RIH_AUX_STREAM_GRAPH', '1') != '0') else None
         if aux is None:
             global_feature, fmaps = self.mid_model(img_fmaps, N)
             return self.decoder(global_feature, fmaps)
