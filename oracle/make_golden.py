@@ -58,7 +58,7 @@ def flat(out):
     return {k: v.detach().clone() for k, v in d.items()}
 
 
-def model_golden(ns, tmp, encoder_type, fname, bn_probe):
+def model_golden(ns, tmp, encoder_type, fname, bn_probe, B=2):
     """Eval forward + train-mode forward/backward (dropout 0) of the unmodified reference model with `encoder_type`
     ('graph' = the common/myhand default variant, built through oracle/ref_bridge.build_reference_myhand_model)."""
     if encoder_type == 'graph':
@@ -68,7 +68,6 @@ def model_golden(ns, tmp, encoder_type, fname, bn_probe):
         ref, cfg = rb.build_reference_model(asset_dir=tmp, encoder_type=encoder_type, dropout=0.0)
     sd = fixtures.init_state_dict(ref.state_dict())
     ref.load_state_dict(sd)
-    B = 2
     img = fixtures.make_image(B)
     ref.eval()
     with torch.no_grad():
@@ -167,7 +166,6 @@ def newgraph_golden(ns, tmp):
     ref, _ = rb.build_reference_myhand_model(tmp, 'newgraph', dropout=0.0)
     sd = fixtures.init_state_dict(ref.state_dict())
     ref.load_state_dict(sd)
-    B = 2
     img = fixtures.make_image(B)
     with ref._rih_cpu_shims():
         ref.eval()
@@ -361,14 +359,40 @@ def augment_golden(ns, tmp):
     print('augment golden:', [(round(s['theta'], 2), round(s['scale'], 3), s['flip']) for s in samples])
 
 
+def mano_helpers_golden(ns, tmp):
+    """The pose-representation helpers around the ManoLayer (models/manolayer.py:20-98, 163-248): rodrigues_batch, vec2mat,
+    build_mano_frame, the pca/axis/Rmat conversions, get_local_frame, buildSE3_batch / SE3_apply -- outputs of the unmodified reference
+    on seeded inputs (synthetic MANO tables).  Batch sizes avoid 3: the reference's `torch.cross` calls carry no `dim`, so a batch of
+    exactly 3 frames would be crossed along the batch axis (a reference quirk this package does not reproduce)."""
+    g = torch.Generator().manual_seed(fixtures.SEED + 7)
+    layer = ns.mano.ManoLayer(os.path.join(tmp, 'mano', 'MANO_RIGHT.pkl'), center_idx=9, use_pca=True)
+    ax = torch.randn(40, 3, generator=g) * 1.5
+    ax[0] = 0
+    inp = {'axis': ax, 'vec6': torch.randn(16, 6, generator=g), 'skel': torch.randn(4, 21, 3, generator=g),
+           'rot_axis': torch.randn(30, 3, generator=g) * 2.5, 'pca': torch.randn(4, 30, generator=g), 'axis45': torch.randn(4, 45, generator=g) * 0.5,
+           'shape': torch.randn(5, 10, generator=g), 't': torch.randn(5, 3, 1, generator=g), 'v': torch.randn(5, 3, generator=g)}
+    Rm = ns.mano.rodrigues_batch(inp['rot_axis'])
+    R5 = ns.mano.rodrigues_batch(inp['rot_axis'][:5])
+    se3 = layer.buildSE3_batch(R5, inp['t'])
+    out = {'rodrigues': ns.mano.rodrigues_batch(ax), 'vec2mat': ns.mano.vec2mat(inp['vec6']), 'frame': ns.mano.build_mano_frame(inp['skel']),
+           'Rmat2axis': layer.Rmat2axis(Rm), 'pca2axis': layer.pca2axis(inp['pca']), 'pca2Rmat': layer.pca2Rmat(inp['pca']),
+           'axis2pca': layer.axis2pca(inp['axis45']), 'Rmat2pca': layer.Rmat2pca(layer.axis2Rmat(inp['axis45'])),
+           'local_frame': layer.get_local_frame(inp['shape']), 'se3': se3, 'se3_apply': layer.SE3_apply(se3, inp['v'])}
+    torch.save({'inputs': inp, 'outputs': {k: v.detach().clone() for k, v in out.items()}, 'torch': torch.__version__},
+               os.path.join(GOLD, 'mano_helpers_synth.pt'))
+    print('mano helpers golden:', {k: tuple(v.shape) for k, v in out.items()})
+
+
 def main(which):
-    """which: any of 'resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'eval_metrics', 'augment', 'mano', 'mano_grad' (default: all).  Each golden file is written independently."""
+    """which: any of 'resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'eval_metrics', 'augment', 'mano', 'mano_grad', 'mano_helpers' (default: all).  Each golden file is written independently."""
     os.makedirs(GOLD, exist_ok=True)
     ns = rb.import_reference()
     with tempfile.TemporaryDirectory() as tmp:
         write_synthetic_asset_dir(tmp, 0)
         if 'resnet50' in which:
             model_golden(ns, tmp, 'resnet50', 'model_synth_b2.pt', 'resnet')
+        if 'resnet50_b16' in which:   # same model at batch 16: BatchNorm statistics over >= 1024 samples, so train-mode parity can be held much tighter
+            model_golden(ns, tmp, 'resnet50', 'model_synth_b16.pt', 'resnet', B=16)
         if 'hrnet48' in which:     # BASELINE config 5 (models/encoder.py:176-352, model_zoo/hrnet.py)
             model_golden(ns, tmp, 'hrnet48', 'model_hrnet48_synth_b2.pt', 'hrnet')
         if 'graph' in which:       # SURVEY 8(f) row 1: common/myhand/lijun_model_graph.load_graph_model
@@ -385,7 +409,9 @@ def main(which):
             mano_golden(ns, tmp)
         if 'mano_grad' in which:
             mano_grad_golden(ns, tmp)
+        if 'mano_helpers' in which:
+            mano_helpers_golden(ns, tmp)
 
 
 if __name__ == '__main__':
-    main(sys.argv[1:] or ['resnet50', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'eval_metrics', 'augment', 'mano', 'mano_grad'])
+    main(sys.argv[1:] or ['resnet50', 'resnet50_b16', 'hrnet48', 'graph', 'newgraph', 'mano_loss', 'eval_metrics', 'augment', 'mano', 'mano_grad', 'mano_helpers'])

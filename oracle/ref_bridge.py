@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE -- never imported by the product package `renderih_b200`.
 
 This module imports the reference's own Python modules *in place* from /root/reference
-(read-only, present only in the authoring container; it does not exist on the GPU box),
+(read-only, present only in the authoring container) or, where that does not exist (the GPU box),
+from the byte-for-byte staged copy `oracle/_ref/src` made by `oracle/build_ref.py`,
 after installing two tiny import shims for packages the container lacks:
 
   * `yacs.config.CfgNode`   (needed by  utils/config.py:1)
@@ -21,9 +22,21 @@ import pickle
 
 import numpy as np
 
-REF_ROOT = os.environ.get('RIH_REFERENCE_ROOT', '/root/reference')
 HERE = os.path.dirname(os.path.abspath(__file__))
 ASSET_DIR = os.path.join(HERE, '_ref', 'misc')
+STAGED_ROOT = os.path.join(HERE, '_ref', 'src')       # byte-for-byte copy made by oracle/build_ref.py (git-ignored; travels to the GPU box)
+
+
+def _pick_root():
+    env = os.environ.get('RIH_REFERENCE_ROOT')
+    if env:
+        return env
+    if os.path.isdir('/root/reference/models'):
+        return '/root/reference'
+    return STAGED_ROOT
+
+
+REF_ROOT = _pick_root()
 
 
 def reference_available():

@@ -41,10 +41,28 @@ def needs_build():
         return f.read().strip() != _digest()
 
 
+def have_nvcc():
+    return os.path.exists(shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc')
+
+
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library.  Returns the library path."""
+    """Compile every .cu under csrc/ into one shared library.  Returns the library path.
+    Concurrent callers (the ranks of a torchrun launch) serialise on a file lock; the library is moved into place with an atomic rename."""
     if not force and not needs_build():
         return LIB_PATH
+    import fcntl
+    os.makedirs(os.path.join(HERE, 'csrc', 'build'), exist_ok=True)
+    with open(os.path.join(HERE, 'csrc', 'build', '.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():      # another rank built it while we waited
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     if not os.path.exists(nvcc):
         raise RuntimeError('nvcc not found: cannot build renderih_b200 CUDA library')
@@ -65,10 +83,12 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError('nvcc failed on %s:\n%s' % (src, out.decode()))
-    cmd = [nvcc] + ARCH_FLAGS + ['-shared', '-o', LIB_PATH] + objs + ['-lcuda']
+    tmp = LIB_PATH + '.tmp.%d' % os.getpid()
+    cmd = [nvcc] + ARCH_FLAGS + ['-shared', '-o', tmp] + objs + ['-lcuda']
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s' % r.stdout.decode())
+    os.replace(tmp, LIB_PATH)
     with open(STAMP_PATH, 'w') as f:
         f.write(_digest())
     return LIB_PATH

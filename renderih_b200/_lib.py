@@ -38,9 +38,13 @@ def parse_header(path=HEADER):
         ret, name, params = m.group(1).strip(), m.group(2), m.group(3)
         args = [_ctype(p) for p in params.split(',')]
         protos[name] = (ret, [a for a in args if a is not None])
+        if params.split(',')[-1].strip().startswith('cudaStream_t'):
+            STREAM_LAST.add(name)
     return protos
 
 
+STREAM_LAST = set()   # entry points whose last parameter is the CUDA stream to launch on (every kernel-launching one)
+TRACE = None          # measurement hook (bench.py): when set to a list, every launching call is bracketed by CUDA events recorded on ITS stream
 _lib = None
 CALLS = [0]   # number of C-ABI kernel-launching calls issued by this process (bench.py reports it as gpu_launches)
 
@@ -56,15 +60,17 @@ def load():
         return _lib
     path = _build.LIB_PATH
     if _build.needs_build():
-        try:
-            _build.build()
-        except Exception as e:  # no nvcc on this box: accept a prebuilt library if one exists
-            if not os.path.exists(path):
-                raise RuntimeError('renderih_b200: CUDA library is not built and cannot be built here: %s' % e)
+        if _build.have_nvcc():
+            _build.build()          # compile / link errors propagate: never run a stale library against a newer header
+        elif not os.path.exists(path):
+            raise RuntimeError('renderih_b200: CUDA library is not built and nvcc is not available here')
+        # no nvcc (e.g. a deployment box): a prebuilt library is accepted only if its embedded source digest matches, checked below
     if not os.path.exists(path):
         raise RuntimeError('renderih_b200: %s missing -- run `python -m renderih_b200._build`' % path)
     lib = ctypes.CDLL(path)
     for name, (ret, args) in parse_header().items():
+        if not hasattr(lib, name):
+            raise RuntimeError('renderih_b200: %s does not export %s (stale library? rebuild with `python -m renderih_b200._build --force`)' % (path, name))
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
         fn.restype = ctypes.c_char_p if 'char' in ret else ctypes.c_int
         fn.argtypes = args
@@ -76,6 +82,15 @@ def call(name, *args):
     """Invoke a C-ABI entry point; raise RuntimeError(rih_last_error()) on a non-zero status."""
     lib = _lib if _lib is not None else load()
     CALLS[0] += 1
-    rc = getattr(lib, name)(*args)
+    if TRACE is not None and name in STREAM_LAST:
+        import torch
+        st = torch.cuda.ExternalStream(args[-1]) if args[-1] else torch.cuda.default_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        rc = getattr(lib, name)(*args)
+        e1.record(st)
+        TRACE.append((name, args, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError('%s failed (status %d): %s' % (name, rc, lib.rih_last_error().decode()))

@@ -97,30 +97,25 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int 
     atomicAdd(ws + c, s); atomicAdd(ws + C + c, ss);
   }
 }
-// mean / rstd and running-stat update (torch.nn.BatchNorm2d training semantics: momentum, unbiased running var)
-__global__ void bn_finalize_kernel(const double* __restrict__ ws, int M, int C, float eps, float momentum,
-                                   float* __restrict__ mean, float* __restrict__ rstd,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double m = ws[c] / M;
-  double var = ws[C + c] / M - m * m;
-  if (var < 0) var = 0;
-  mean[c] = (float)m;
-  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) {
-    double unbiased = M > 1 ? var * M / (M - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-  }
+// Thread -> (channel quad, first row) mapping shared by the element-wise BatchNorm passes: the launch has a multiple of C/4 threads, so
+// a thread keeps ONE channel quad for its whole grid-stride loop and the per-channel terms are computed once per thread.
+struct BnMap { int q; long long r0, rstride; };
+__device__ __forceinline__ BnMap bn_map(int C4) {
+  const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long T = (long long)gridDim.x * blockDim.x;
+  BnMap m; m.q = (int)(gid % C4); m.r0 = gid / C4; m.rstride = T / C4;
+  return m;
 }
-__global__ void bn_eval_prep_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, float eps,
-                                    float* __restrict__ mean, float* __restrict__ rstd) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  mean[c] = rm[c];
-  rstd[c] = 1.f / sqrtf(rv[c] + eps);
+static inline int bn_grid(long long M, int C4, int threads) {
+  int g = 1, a = C4, b = threads;                 // grid must be a multiple of C4 / gcd(C4, threads)
+  while (b) { int t = a % b; a = b; b = t; }
+  g = C4 / a;
+  long long want = (M * C4 + threads - 1) / threads;
+  if (want > 148 * 16) want = 148 * 16;
+  if (want < 1) want = 1;
+  return (int)((want + g - 1) / g * g);
 }
+
 // column sums / sums of squares of x into ws[0:C], ws[C:2C] (fp64; ws is zeroed here)
 RIH_API int rih_bn_colstats(const float* x, int ld, int M, int C, double* ws, cudaStream_t s) {
   RIH_REQUIRE(M > 0 && C > 0, "bn_colstats: empty");
@@ -132,51 +127,67 @@ RIH_API int rih_bn_colstats(const float* x, int ld, int M, int C, double* ws, cu
   bn_stats_kernel<<<grid, block, 0, s>>>(x, ld, M, C, rows_per_cta, ws);
   return check_launch("bn_stats");
 }
-// mean / rstd (+ running statistics update) from column sums produced by rih_bn_colstats or by a convolution's fused epilogue
-RIH_API int rih_bn_finalize(const double* ws, int M, int C, float eps, float momentum, float* mean, float* rstd,
-                            float* running_mean, float* running_var, cudaStream_t s) {
-  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(ws, M, C, eps, momentum, mean, rstd, running_mean, running_var);
-  return check_launch("bn_finalize");
-}
-RIH_API int rih_bn_stats(const float* x, int ld, int M, int C, float eps, float momentum, double* ws,
-                         float* mean, float* rstd, float* running_mean, float* running_var, cudaStream_t s) {
-  if (int e = rih_bn_colstats(x, ld, M, C, ws, s)) return e;
-  return rih_bn_finalize(ws, M, C, eps, momentum, mean, rstd, running_mean, running_var, s);
-}
-RIH_API int rih_bn_eval_prep(const float* rm, const float* rv, int C, float eps, float* mean, float* rstd, cudaStream_t s) {
-  bn_eval_prep_kernel<<<cdiv(C, 128), 128, 0, s>>>(rm, rv, C, eps, mean, rstd);
-  return check_launch("bn_eval_prep");
-}
 
-// y = (x-mean)*rstd*gamma+beta (+res) (relu).   C % 4 == 0, all row strides % 4 == 0
-__global__ void bn_apply_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ res, int ldr, float* __restrict__ y, int ldy,
-                                long long M, int C4, int relu) {
-  long long total = M * C4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long r; int c; divmod(i, C4, total < (1ll << 32), r, c); c *= 4;
-    float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
-    float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
-    float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+// BatchNorm forward in ONE pass over the activation: the per-channel mean / rstd are derived by every thread for its own channel quad
+//   training (stats != NULL): from the fp64 column sums (a convolution's fused epilogue or rih_bn_colstats), torch.nn.BatchNorm2d
+//                             semantics: biased variance for the normalisation, momentum update of the running statistics with the
+//                             unbiased variance, num_batches_tracked += 1 -- written once, by the threads that own row 0
+//   eval     (stats == NULL): from the running statistics
+// then y = (x - mean) * rstd * gamma + beta (+res) (relu).  mean / rstd are also stored for the backward pass.  C % 4 == 0, ld % 4 == 0.
+__global__ void __launch_bounds__(256)
+bn_forward_kernel(const float* __restrict__ x, int ldx, const double* __restrict__ stats, long long M, int C4, float eps, float momentum,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ res, int ldr,
+                  float* __restrict__ y, int ldy, int relu, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                  float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ tracked) {
+  const BnMap mp = bn_map(C4);
+  const int c = mp.q * 4, C = C4 * 4;
+  float mu[4], rs[4];
+  if (stats) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double m = stats[c + j] / (double)M;
+      double var = stats[C + c + j] / (double)M - m * m;
+      if (var < 0) var = 0;
+      mu[j] = (float)m;
+      rs[j] = (float)(1.0 / sqrt(var + (double)eps));
+      if (mp.r0 == 0 && running_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_mean[c + j] = (1.f - momentum) * running_mean[c + j] + momentum * (float)m;
+        running_var[c + j] = (1.f - momentum) * running_var[c + j] + momentum * (float)unbiased;
+      }
+    }
+    if (mp.r0 == 0 && mp.q == 0 && tracked) *tracked += 1;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mu[j] = running_mean[c + j]; rs[j] = 1.f / sqrtf(running_var[c + j] + eps); }
+  }
+  if (mp.r0 == 0) {
+    *reinterpret_cast<float4*>(mean_out + c) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+    *reinterpret_cast<float4*>(rstd_out + c) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+  }
+  const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+  for (long long r = mp.r0; r < M; r += mp.rstride) {
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
     float4 o;
-    o.x = (v.x - mu.x) * rs.x * g.x + b.x; o.y = (v.y - mu.y) * rs.y * g.y + b.y;
-    o.z = (v.z - mu.z) * rs.z * g.z + b.z; o.w = (v.w - mu.w) * rs.w * g.w + b.w;
+    o.x = (v.x - mu[0]) * rs[0] * g.x + b.x; o.y = (v.y - mu[1]) * rs[1] * g.y + b.y;
+    o.z = (v.z - mu[2]) * rs[2] * g.z + b.z; o.w = (v.w - mu[3]) * rs[3] * g.w + b.w;
     if (res) {
-      float4 q = *reinterpret_cast<const float4*>(res + r * ldr + c);
+      const float4 q = *reinterpret_cast<const float4*>(res + r * ldr + c);
       o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
     }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     *reinterpret_cast<float4*>(y + r * ldy + c) = o;
   }
 }
-RIH_API int rih_bn_apply(const float* x, int ldx, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                         const float* res, int ldr, float* y, int ldy, long long M, int C, int relu, cudaStream_t s) {
-  RIH_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (!res || ldr % 4 == 0), "bn_apply: needs C,ld %% 4 == 0");
-  long long total = M * (C / 4);
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  bn_apply_kernel<<<grid, 256, 0, s>>>(x, ldx, mean, rstd, gamma, beta, res, ldr, y, ldy, M, C / 4, relu);
-  return check_launch("bn_apply");
+// reference: torch.nn.BatchNorm2d forward (torchvision ResNet blocks; models/encoder.py:54; models/model_zoo/__init__.py:57,66)
+RIH_API int rih_bn_forward(const float* x, int ldx, const double* stats, long long M, int C, float eps, float momentum,
+                           const float* gamma, const float* beta, const float* res, int ldr, float* y, int ldy, int relu,
+                           float* mean_out, float* rstd_out, float* running_mean, float* running_var, long long* tracked, cudaStream_t s) {
+  RIH_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (!res || ldr % 4 == 0), "bn_forward: needs C,ld %% 4 == 0");
+  RIH_REQUIRE(M > 0 && (stats || (running_mean && running_var)), "bn_forward: eval mode needs the running statistics");
+  bn_forward_kernel<<<bn_grid(M, C / 4, 256), 256, 0, s>>>(x, ldx, stats, M, C / 4, eps, momentum, gamma, beta, res, ldr, y, ldy, relu,
+                                                          mean_out, rstd_out, running_mean, running_var, tracked);
+  return check_launch("bn_forward");
 }
 
 // backward pass 1: g = dy * (y > 0 if relu);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat
@@ -222,66 +233,63 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __rest
     if (cc < C) atomicAdd(ws + which * C + cc, acc);
   }
 }
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, int C, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ sum_g, float* __restrict__ sum_gx, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = (float)ws[c], sx = (float)ws[C + c];
-  sum_g[c] = s; sum_gx[c] = sx;
-  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + sx : sx;
-  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + s : s;
-}
-// backward pass 2: dx = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) [train] ; dres (+)= g ; optional mask by (x>0) for Conv->ReLU->BN
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
-                                    const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
-                                    float* __restrict__ dx, int lddx, float* __restrict__ dres, int lddr, int dres_acc,
-                                    long long M, int C4, int relu, int training, int mask_input) {
-  long long total = M * C4;
-  float invM = 1.f / (float)M;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long r; int c; divmod(i, C4, total < (1ll << 32), r, c); c *= 4;
-    float4 g4 = *reinterpret_cast<const float4*>(dy + r * lddy + c);
+// backward pass 2 (the per-channel finalisation folded in): dx = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) [train] ; dres (+)= g ;
+// optional mask by (x>0) for Conv->ReLU->BN; the threads that own row 0 write dgamma / dbeta.  Same thread mapping as bn_forward_kernel.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+                    const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ ws,
+                    float* __restrict__ dx, int lddx, float* __restrict__ dres, int lddr, int dres_acc,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, int param_acc,
+                    long long M, int C4, int relu, int training, int mask_input) {
+  const BnMap mp = bn_map(C4);
+  const int c = mp.q * 4, C = C4 * 4;
+  const float invM = 1.f / (float)M;
+  const float4 mu4 = *reinterpret_cast<const float4*>(mean + c), rs4 = *reinterpret_cast<const float4*>(rstd + c);
+  const float4 ga4 = *reinterpret_cast<const float4*>(gamma + c);
+  float4 be4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (relu && !y) be4 = *reinterpret_cast<const float4*>(beta + c);
+  const float muv[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rsv[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, gav[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+  const float bev[4] = {be4.x, be4.y, be4.z, be4.w};
+  float sgv[4], sxv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sgv[j] = (float)ws[c + j]; sxv[j] = (float)ws[C + c + j]; }
+  if (mp.r0 == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (dgamma) dgamma[c + j] = param_acc ? dgamma[c + j] + sxv[j] : sxv[j];
+      if (dbeta) dbeta[c + j] = param_acc ? dbeta[c + j] + sgv[j] : sgv[j];
+    }
+  }
+  for (long long r = mp.r0; r < M; r += mp.rstride) {
+    const float4 g4 = *reinterpret_cast<const float4*>(dy + r * lddy + c);
     float g[4] = {g4.x, g4.y, g4.z, g4.w};
     const float4 x4 = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
     if (relu) {
-      float4 y4;
-      if (y) y4 = *reinterpret_cast<const float4*>(y + r * ldy + c);
-      else {   // no residual: the forward output is a function of x alone -- same expression as bn_apply_kernel, so the mask is bit-identical
-        const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
-        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
-        y4.x = (x4.x - mu.x) * rs.x * ga.x + be.x; y4.y = (x4.y - mu.y) * rs.y * ga.y + be.y;
-        y4.z = (x4.z - mu.z) * rs.z * ga.z + be.z; y4.w = (x4.w - mu.w) * rs.w * ga.w + be.w;
+      float yv[4];
+      if (y) { const float4 y4 = *reinterpret_cast<const float4*>(y + r * ldy + c); yv[0] = y4.x; yv[1] = y4.y; yv[2] = y4.z; yv[3] = y4.w; }
+      else {   // no residual: the forward output is a function of x alone -- same expression as bn_forward_kernel, so the mask is bit-identical
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yv[j] = (xv[j] - muv[j]) * rsv[j] * gav[j] + bev[j];
       }
-      if (!(y4.x > 0.f)) g[0] = 0.f; if (!(y4.y > 0.f)) g[1] = 0.f;
-      if (!(y4.z > 0.f)) g[2] = 0.f; if (!(y4.w > 0.f)) g[3] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (!(yv[j] > 0.f)) g[j] = 0.f;
     }
     if (dres) {
       float* q = dres + r * lddr + c;
       if (dres_acc) { float4 o = *reinterpret_cast<float4*>(q); o.x += g[0]; o.y += g[1]; o.z += g[2]; o.w += g[3]; *reinterpret_cast<float4*>(q) = o; }
       else *reinterpret_cast<float4*>(q) = make_float4(g[0], g[1], g[2], g[3]);
     }
-    float xv[4] = {x4.x, x4.y, x4.z, x4.w};
     float o[4];
-    const float4 rs4 = *reinterpret_cast<const float4*>(rstd + c), ga4 = *reinterpret_cast<const float4*>(gamma + c);
-    const float rsv[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, gav[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
-    float muv[4] = {0.f, 0.f, 0.f, 0.f}, sgv[4] = {0.f, 0.f, 0.f, 0.f}, sxv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (training) {
-      const float4 mu4 = *reinterpret_cast<const float4*>(mean + c), sg4 = *reinterpret_cast<const float4*>(sum_g + c),
-                   sx4 = *reinterpret_cast<const float4*>(sum_gx + c);
-      muv[0] = mu4.x; muv[1] = mu4.y; muv[2] = mu4.z; muv[3] = mu4.w;
-      sgv[0] = sg4.x; sgv[1] = sg4.y; sgv[2] = sg4.z; sgv[3] = sg4.w;
-      sxv[0] = sx4.x; sxv[1] = sx4.y; sxv[2] = sx4.z; sxv[3] = sx4.w;
-    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float rs = rsv[j], ga = gav[j];
       float t;
       if (training) {
-        float xh = (xv[j] - muv[j]) * rs;
-        t = ga * rs * (g[j] - sgv[j] * invM - xh * sxv[j] * invM);
+        const float xh = (xv[j] - muv[j]) * rsv[j];
+        t = gav[j] * rsv[j] * (g[j] - sgv[j] * invM - xh * sxv[j] * invM);
       } else {
-        t = ga * rs * g[j];
+        t = gav[j] * rsv[j] * g[j];
       }
       if (mask_input && !(xv[j] > 0.f)) t = 0.f;
       o[j] = t;
@@ -289,7 +297,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, cons
     *reinterpret_cast<float4*>(dx + r * lddx + c) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
-// ws: double[2C]; tmp: float[2C] (sum_g, sum_gx)
+// ws: double[2C] (sum g, sum g*xhat; zeroed here)
 // y (the forward output) is only needed for the ReLU mask of a residual block; pass NULL otherwise and the mask is recomputed from x
 // (needs beta) -- one tensor read less in each of the two passes
 RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const float* x, int ldx,
@@ -297,7 +305,7 @@ RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const
                        float* dx, int lddx, float* dres, int lddr, int dres_acc,
                        float* dgamma, float* dbeta, int param_acc,
                        long long M, int C, int relu, int training, int mask_input,
-                       double* ws, float* tmp, cudaStream_t s) {
+                       double* ws, cudaStream_t s) {
   RIH_REQUIRE(C % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0, "bn_bwd: needs C,ld %% 4 == 0");
   RIH_REQUIRE(M < (1ll << 31), "bn_bwd: too many rows");
   RIH_REQUIRE(!relu || y || beta, "bn_bwd: the ReLU mask needs either the forward output or beta");
@@ -308,12 +316,8 @@ RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const
   dim3 grid(gx, cdiv(M, rows_per_cta));
   bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, (int)M, C, rows_per_cta, relu, ws);
   if (int e = check_launch("bn_bwd_reduce")) return e;
-  bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(ws, C, dgamma, dbeta, tmp, tmp + C, param_acc);
-  if (int e = check_launch("bn_bwd_finalize")) return e;
-  long long total = M * (C / 4);
-  int g2 = (int)min((long long)148 * 16, (total + 255) / 256);
-  bn_bwd_apply_kernel<<<g2, 256, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, tmp, tmp + C, dx, lddx, dres, lddr, dres_acc,
-                                         M, C / 4, relu, training, mask_input);
+  bn_bwd_apply_kernel<<<bn_grid(M, C / 4, 256), 256, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx, dres, lddr, dres_acc,
+                                                            dgamma, dbeta, param_acc, M, C / 4, relu, training, mask_input);
   return check_launch("bn_bwd_apply");
 }
 

@@ -401,9 +401,11 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 }
 RIH_API int rih_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                            float eps, float weight_decay, int step, float grad_scale, cudaStream_t s) {
+  RIH_REQUIRE(n >= 0 && step >= 1, "adamw_step: n must be >= 0 and step >= 1 (got n=%lld step=%d)", n, step);
   if (n == 0) return 0;
-  float bc1 = 1.f - powf(beta1, (float)step);
-  float bc2 = 1.f - powf(beta2, (float)step);
+  // bias corrections in double like torch.optim.AdamW's Python scalars (1 - 0.999f in float is already 5e-5 off at step 1)
+  float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
   int grid = (int)min((long long)148 * 16, (n + 255) / 256);
   adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
   return check_launch("adamw");

@@ -59,7 +59,7 @@ def conv_bn(x, conv, bn, N, H, training, relu=True, res=None, alias_input=False)
     xa = None
     if alias_input:
         y, xa = y
-    y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, res=res, training=training,
+    y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, tracked=bn.num_batches_tracked, res=res, training=training,
                       momentum=bn.momentum, eps=bn.eps, relu=relu, stats=stats)
     Ho = (H + 2 * pd - k) // st + 1
     return (y, Ho, xa) if alias_input else (y, Ho)
@@ -87,7 +87,7 @@ def stem_conv_bn(x, conv, bn, N, H, training, image_needs_grad):
     w2d = torch.nn.functional.pad(conv.weight.permute(0, 2, 3, 1).reshape(Cout, K), (0, Kpad - K))   # tiny
     stats = torch.empty(2 * Cout, device=x.device, dtype=torch.float64) if training else None
     y = ops.linear(A, w2d, conv.bias, stats=stats, as_conv=True)
-    y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training=training, momentum=bn.momentum,
+    y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, tracked=bn.num_batches_tracked, training=training, momentum=bn.momentum,
                       eps=bn.eps, relu=True, stats=stats)
     return y, (H + 2 * pd - R) // st + 1
 

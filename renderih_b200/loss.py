@@ -90,6 +90,21 @@ class _FusedGraphLossFn(torch.autograd.Function):
         if v3c_l is None:           # no coarse level (ManoLoss): zero-sized stand-ins keep the argument layout
             v3c_l = v3c_r = torch.empty(v3p_l.shape[0], 0, 3, device=dev)
             v2c_l = v2c_r = torch.empty(v3p_l.shape[0], 0, 2, device=dev)
+        # the kernel hard-codes the MANO mesh (778 vertices) and a [B, V, 3|2] layout and reads raw pointers: check everything it will touch
+        B0 = v3p_l.shape[0]
+        Vc0 = v3c_l.shape[1]
+        want = {'v3p_l': (B0, 778, 3), 'v2p_l': (B0, 778, 2), 'v3c_l': (B0, Vc0, 3), 'v2c_l': (B0, Vc0, 2),
+                'v3p_r': (B0, 778, 3), 'v2p_r': (B0, 778, 2), 'v3c_r': (B0, Vc0, 3), 'v2c_r': (B0, Vc0, 2),
+                'v3g_l': (B0, 778, 3), 'v2g_l': (B0, 778, 2), 'v3g_r': (B0, 778, 3), 'v2g_r': (B0, 778, 2), 'root_rel': (B0, 3)}
+        got = dict(v3p_l=v3p_l, v2p_l=v2p_l, v3c_l=v3c_l, v2c_l=v2c_l, v3p_r=v3p_r, v2p_r=v2p_r, v3c_r=v3c_r, v2c_r=v2c_r,
+                   v3g_l=v3g_l, v2g_l=v2g_l, v3g_r=v3g_r, v2g_r=v2g_r, root_rel=root_rel)
+        for name, shape in want.items():
+            t = got[name]
+            if not (torch.is_tensor(t) and t.is_cuda and t.device == dev):
+                raise RuntimeError('renderih_b200 fused loss: %s must be a CUDA tensor on %s (got %s); there is no CPU fallback'
+                                   % (name, dev, getattr(t, 'device', type(t))))
+            if tuple(t.shape) != shape:
+                raise RuntimeError('renderih_b200 fused loss: %s has shape %s, expected %s' % (name, tuple(t.shape), shape))
         preds = [t.contiguous().float() for t in (v3p_l, v2p_l, v3c_l, v2c_l, v3p_r, v2p_r, v3c_r, v2c_r)]
         labels = [t.contiguous().float() for t in (v3g_l, v2g_l, v3g_r, v2g_r, root_rel)]
         B, Vc = preds[0].shape[0], preds[2].shape[1]

@@ -13,21 +13,7 @@ from torch.nn import Module
 from . import ops
 from .assets import load_mano_dict
 from ._lib import call
-
-
-def rodrigues_batch(axis):
-    """models/manolayer.py:32-48 (helper used by callers to build root rotations)."""
-    bs = axis.shape[0]
-    Imat = torch.eye(3, dtype=axis.dtype, device=axis.device).repeat(bs, 1, 1)
-    angle = torch.norm(axis, p=2, dim=1, keepdim=True) + 1e-8
-    axes = axis / angle
-    sin = torch.sin(angle).unsqueeze(2)
-    cos = torch.cos(angle).unsqueeze(2)
-    L = torch.zeros((bs, 3, 3), dtype=axis.dtype, device=axis.device)
-    L[:, 2, 1] = axes[:, 0]; L[:, 1, 2] = -axes[:, 0]
-    L[:, 0, 2] = axes[:, 1]; L[:, 2, 0] = -axes[:, 1]
-    L[:, 1, 0] = axes[:, 2]; L[:, 0, 1] = -axes[:, 2]
-    return Imat + sin * L + (1 - cos) * L.bmm(L)
+from .rotations import build_mano_frame, rodrigues_batch, rotmat_to_axis, se3_apply, se3_from, vec2mat   # noqa: F401  (re-exported API surface)
 
 
 class ManoLayer(Module):
@@ -67,58 +53,37 @@ class ManoLayer(Module):
     def eval(self):
         self.train(False)
 
-    # ---- parameter conversions (manolayer.py:163-215); light host-side helpers, not on the hot path
+    # ---- parameter conversions between the PCA / axis-angle / rotation-matrix pose representations (API of models/manolayer.py:163-248;
+    #      formulations in renderih_b200/rotations.py).  Light host-side helpers, not on the hot path.
     def pca2axis(self, pca):
-        return pca.mm(self.hands_components[:pca.shape[1]]) + self.hands_mean
+        """[bs, n<=45] PCA coefficients -> [bs,45] axis-angle (first n principal components + mean pose)."""
+        return torch.addmm(self.hands_mean, pca, self.hands_components[:pca.shape[1]])
+
+    def axis2pca(self, axis):
+        return torch.mm(axis - self.hands_mean, self.hands_components_inv)
+
+    def axis2Rmat(self, axis):
+        return rodrigues_batch(axis.reshape(-1, 3)).reshape(-1, 15, 3, 3)
+
+    def Rmat2axis(self, R):
+        return rotmat_to_axis(R).reshape(-1, 45)
 
     def pca2Rmat(self, pca):
         return self.axis2Rmat(self.pca2axis(pca))
 
-    def axis2Rmat(self, axis):
-        return rodrigues_batch(axis.view(-1, 3)).view(-1, 15, 3, 3)
-
-    def axis2pca(self, axis):
-        return (axis - self.hands_mean).mm(self.hands_components_inv)
-
     def Rmat2pca(self, R):
         return self.axis2pca(self.Rmat2axis(R))
 
-    def Rmat2axis(self, R):
-        """manolayer.py:186-215 (rotation matrix -> axis-angle with the reference's clamping / quadrant fix-ups)"""
-        R = R.view(-1, 3, 3)
-        temp = (R - R.permute(0, 2, 1)) / 2
-        L = temp[:, [2, 0, 1], [1, 2, 0]]
-        sin = torch.norm(L, dim=1, keepdim=False)
-        L = L / (sin.unsqueeze(-1) + 1e-8)
-        temp = (R + R.permute(0, 2, 1)) / 2
-        temp = temp - torch.eye(3, dtype=R.dtype, device=R.device)
-        temp2 = torch.matmul(L.unsqueeze(-1), L.unsqueeze(1))
-        temp2 = temp2 - torch.eye(3, dtype=R.dtype, device=R.device)
-        temp = temp[:, 0, 0] + temp[:, 1, 1] + temp[:, 2, 2]
-        temp2 = temp2[:, 0, 0] + temp2[:, 1, 1] + temp2[:, 2, 2]
-        cos = 1 - temp / (temp2 + 1e-8)
-        sin = torch.clamp(sin, min=-1 + 1e-7, max=1 - 1e-7)
-        theta = torch.asin(sin)
-        theta2 = theta.clone()
-        idx1 = (cos < 0) & (sin > 0)
-        idx2 = (cos < 0) & (sin < 0)
-        theta2[idx1] = 3.14159 - theta[idx1]
-        theta2[idx2] = -3.14159 - theta[idx2]
-        return (theta2.unsqueeze(-1) * L).view(-1, 45)
+    def get_local_frame(self, shape):
+        """Zero-pose local joint frames [bs,15,3,3] for shape coefficients [bs,10] (models/manolayer.py:217-227).  The finger tips of this
+        helper are vertices 744/320/444/555/672 -- NOT the 745/317/444/556/673 of forward() -- exactly as in the reference."""
+        with torch.no_grad():
+            v = self.v_template + torch.einsum('vck,bk->bvc', self.shapedirs, shape)
+            j21 = torch.cat([torch.einsum('jv,bvc->bjc', self.J_regressor, v), v[:, [744, 320, 444, 555, 672]]], dim=1)
+            return build_mano_frame(j21[:, self.new_order])
 
-    @staticmethod
-    def buildSE3_batch(R, t):
-        """manolayer.py:229-238"""
-        bs = R.shape[0]
-        pad = torch.zeros((bs, 1, 4), dtype=R.dtype, device=R.device)
-        pad[:, 0, 3] = 1.0
-        return torch.cat([torch.cat([R, t], 2), pad], 1)
-
-    @staticmethod
-    def SE3_apply(SE3, v):
-        """manolayer.py:240-248"""
-        pad = torch.ones((v.shape[0], 1), dtype=v.dtype, device=v.device)
-        return SE3.bmm(torch.cat([v, pad], 1).unsqueeze(2))[:, :3, 0]
+    buildSE3_batch = staticmethod(se3_from)
+    SE3_apply = staticmethod(se3_apply)
 
     # ---- device-side constant tables (transposed for coalesced reads); rebuilt if a buffer is mutated in place
     def _tables(self, device):

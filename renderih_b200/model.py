@@ -61,7 +61,7 @@ def _conv_bn(x, conv, bn, N, H, W, training, relu=True, res=None, alias_input=Fa
     if alias_input:
         y, xa = y
     Ho = (H + 2 * conv.padding[0] - k) // conv.stride[0] + 1
-    y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, res=res, training=training,
+    y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, tracked=bn.num_batches_tracked, res=res, training=training,
                       momentum=bn.momentum, eps=bn.eps, relu=relu, stats=stats)
     return (y, Ho, xa) if alias_input else (y, Ho)
 
@@ -71,7 +71,7 @@ def _conv_relu_bn(x, conv, bn, N, H, W, training):
     stats = torch.empty(2 * conv.out_channels, device=x.device, dtype=torch.float64) if training else None
     y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], relu=True,
                    relu_masked_by_consumer=True, stats=stats)
-    return ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training=training,
+    return ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, tracked=bn.num_batches_tracked, training=training,
                          momentum=bn.momentum, eps=bn.eps, relu=False, mask_input=True, stats=stats)
 
 
@@ -122,9 +122,9 @@ class ResNetSimple(nn.Module):
     def __init__(self, model_type='resnet50', fmapDim=(128, 128, 128, 128), handNum=2, heatmapDim=21, aux_heads=True):
         super().__init__()
         import torchvision.models as tvm
-        assert model_type in ('resnet50', 'resnet101', 'resnet152'), 'bottleneck ResNets only'
+        assert model_type in ('resnet18', 'resnet34', 'resnet50', 'resnet101', 'resnet152')       # models/encoder.py:74
         self.resnet = getattr(tvm, model_type)(weights=None)
-        self.expansion = 4
+        self.expansion = 1 if model_type in ('resnet18', 'resnet34') else 4                         # basic blocks vs bottlenecks
         for m in self.resnet.modules():
             if isinstance(m, nn.Conv2d):
                 _cl(m)
@@ -147,7 +147,7 @@ class ResNetSimple(nn.Module):
         w2d = torch.nn.functional.pad(conv.weight.permute(0, 2, 3, 1).reshape(Cout, K), (0, Kpad - K))   # tiny (64 x 160)
         stats = torch.empty(2 * Cout, device=x.device, dtype=torch.float64)
         y = ops.linear(A, w2d, None, stats=stats, as_conv=True)
-        y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training=True, momentum=bn.momentum, eps=bn.eps,
+        y = ops.batchnorm(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, tracked=bn.num_batches_tracked, training=True, momentum=bn.momentum, eps=bn.eps,
                           relu=True, stats=stats)
         return y, (H + 2 * conv.padding[0] - R) // conv.stride[0] + 1
 
@@ -168,6 +168,22 @@ class ResNetSimple(nn.Module):
         out, _ = _conv_bn(out, blk.conv3, blk.bn3, N, Ho, Ho, tr, relu=True, res=identity)
         return out, Ho
 
+    def _basic(self, blk, x, N, H):
+        """torchvision BasicBlock (resnet18 / resnet34, models/encoder.py:75-80): conv3x3 -> BN -> ReLU -> conv3x3 -> BN, + identity
+        (1x1 stride-2 conv + BN when the block down-samples), ReLU.  Same residual-gradient routing as the bottleneck."""
+        tr = self.training
+        fuse = tr and x.requires_grad
+        if fuse:
+            out, Ho, xa = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr, alias_input=True)
+        else:
+            (out, Ho), xa = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr), x
+        if blk.downsample is not None:
+            identity, _ = _conv_bn(xa, blk.downsample[0], blk.downsample[1], N, H, H, tr, relu=False)
+        else:
+            identity = xa
+        out, _ = _conv_bn(out, blk.conv2, blk.bn2, N, Ho, Ho, tr, relu=True, res=identity)
+        return out, Ho
+
     def trunk(self, img):
         """stem + layer1..4 (encoder.py:107-118) -> [x1 (8x8), x2, x3, x4 (64x64)] as (NHWC rows, H) pairs."""
         N, C, H, W = img.shape
@@ -180,7 +196,7 @@ class ResNetSimple(nn.Module):
         feats = []
         for layer in (r.layer1, r.layer2, r.layer3, r.layer4):
             for blk in layer:
-                x, H = self._bottleneck(blk, x, N, H)
+                x, H = self._bottleneck(blk, x, N, H) if self.expansion == 4 else self._basic(blk, x, N, H)
             feats.append((x, H))
         x4, x3, x2, x1 = feats
         return [x1, x2, x3, x4]
@@ -207,14 +223,14 @@ class resnet_mid(nn.Module):
 
     def __init__(self, model_type='resnet50', in_fmapDim=(128, 128, 128, 128), out_fmapDim=(256, 256, 256, 256)):
         super().__init__()
-        self.expansion = 4
-        self.img_fmaps_dim = [512 * 4, 256 * 4, 128 * 4, 64 * 4]
+        self.expansion = 1 if model_type in ('resnet18', 'resnet34') else 4                         # models/encoder.py:135-138
+        self.img_fmaps_dim = [512 * self.expansion, 256 * self.expansion, 128 * self.expansion, 64 * self.expansion]
         self.convs = nn.ModuleList()
         for i in range(len(out_fmapDim)):
             inDim = 2 * in_fmapDim[i] + (self.img_fmaps_dim[i] if i > 0 else 0)
             self.convs.append(nn.Sequential(_cl(nn.Conv2d(inDim, out_fmapDim[i], kernel_size=1, bias=False)),
                                             nn.ReLU(inplace=True), nn.BatchNorm2d(out_fmapDim[i])))
-        self.global_feature_dim = 512 * 4
+        self.global_feature_dim = 512 * self.expansion
         self.fmaps_dim = list(out_fmapDim)
 
     def get_info(self):
@@ -820,7 +836,7 @@ def load_encoder(cfg):
         enc = HRnet_encoder(model_type=et, pretrained=getattr(cfg.MODEL, 'ENCODER_PRETRAIN_PATH', ''), handNum=2, heatmapDim=21)
         mid = hrnet_mid(model_type=et, in_fmapDim=enc.fmaps_dim, out_fmapDim=cfg.MODEL.DECONV_DIMS)
         return enc, mid
-    raise NotImplementedError('encoder %r: only resnet50/101/152 and hrnet* encoders exist in the reference (models/encoder.py:355-374)' % et)
+    raise NotImplementedError('encoder %r: only resnet18/34/50/101/152 and hrnet* encoders exist in the reference (models/encoder.py:355-374)' % et)
 
 
 def load_decoder(cfg, encoder_info, assets=None, asset_root=None):

@@ -14,6 +14,7 @@ from . import _lib
 call = _lib.call
 
 
+GROUP_FLOPS = {}      # entry point -> f(args) = algorithmic flops of one call (measurement metadata for bench.py's class roofline)
 GEMM_MODES = {'simt': 0, 'tf32': 1, 'tf32x3': 2, 'tf32rn': 3, 'tf32c': 4}
 import os as _os
 _ATTN = {'nsplit': 0, 'force': _os.environ.get('RIH_ATTN_IMPL') or None}     # RIH_ATTN_IMPL=simt|tc overrides the mode-derived choice (A/B runs)
@@ -205,10 +206,13 @@ class LinearFn(Function):
             dx = torch.empty((M, K), device=dy.device, dtype=torch.float32)
             call('rih_linear_dgrad', _p(g), _ld(g), _p(w), w.stride(0), _p(dx), K, M, N, K, 0, ctx.as_conv, s)
         side = None
+        # When g IS dy and dy is also handed back as the residual gradient, autograd may accumulate the other branch's gradient into it
+        # in place on the main stream while a side stream still reads it (record_stream only guards the free): keep such launches in order.
+        may_fork = not (has_res and g is dy)
         if ctx.needs_input_grad[1]:
             tgt = _gt(w)
             if tgt is not None:
-                side = _wgrad_fork(g, x)
+                side = _wgrad_fork(g, x) if may_fork else None
                 call('rih_linear_wgrad', _p(g), _ld(g), _p(x), _ld(x), _p(tgt), w.stride(0), M, N, K, 1, ctx.as_conv, side or s)
             else:
                 dw = torch.empty((N, K), device=dy.device, dtype=torch.float32)
@@ -216,7 +220,7 @@ class LinearFn(Function):
         if has_b and ctx.needs_input_grad[2]:
             tgt = _gt(ctx.bias_ref)
             if tgt is not None:
-                if side is None:
+                if side is None and may_fork:
                     side = _wgrad_fork(g)
                 call('rih_colsum', _p(g), _ld(g), M, N, _p(tgt), 1, side or s)
             else:
@@ -703,24 +707,23 @@ class BatchNormFn(Function):
     """BatchNorm2d over NHWC rows (+residual)(+relu); training uses per-rank batch statistics (no SyncBN)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, rmean, rvar, res, training, momentum, eps, relu, mask_input, stats):
+    def forward(ctx, x, gamma, beta, rmean, rvar, res, training, momentum, eps, relu, mask_input, stats, tracked):
         x = _rows(x)
         M, C = x.shape
         dev = x.device
         mean = torch.empty((C,), device=dev); rstd = torch.empty((C,), device=dev)
         s = _stream()
-        if training and stats is not None:    # column sums already produced by the convolution's epilogue
-            call('rih_bn_finalize', _p(stats), M, C, float(eps), float(momentum), _p(mean), _p(rstd), _p(rmean), _p(rvar), s)
-        elif training:
-            ws = torch.empty((2 * C,), device=dev, dtype=torch.float64)
-            call('rih_bn_stats', _p(x), _ld(x), M, C, float(eps), float(momentum), _p(ws), _p(mean), _p(rstd), _p(rmean), _p(rvar), s)
-        else:
-            call('rih_bn_eval_prep', _p(rmean), _p(rvar), C, float(eps), _p(mean), _p(rstd), s)
+        if training and stats is None:        # column sums not produced by the convolution's epilogue: one reduction pass
+            stats = torch.empty((2 * C,), device=dev, dtype=torch.float64)
+            call('rih_bn_colstats', _p(x), _ld(x), M, C, _p(stats), s)
         y = torch.empty((M, C), device=dev, dtype=torch.float32)
         if res is not None:
             res = _rows(res)
-        call('rih_bn_apply', _p(x), _ld(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(res), _ld(res) if res is not None else 0,
-             _p(y), C, M, C, int(relu), s)
+        # ONE launch: mean / rstd from the column sums (or the running statistics in eval mode), running-stat + num_batches_tracked
+        # update, normalise (+res)(+relu)
+        call('rih_bn_forward', _p(x), _ld(x), _p(stats) if training else None, M, C, float(eps), float(momentum), _p(gamma), _p(beta),
+             _p(res), _ld(res) if res is not None else 0, _p(y), C, int(relu), _p(mean), _p(rstd), _p(rmean), _p(rvar),
+             _p(tracked) if training else None, s)
         # the ReLU mask of a residual block needs the output; otherwise it is recomputed from x in the backward kernels (one read less)
         ctx.save_for_backward(x, gamma, mean, rstd, y if (relu and res is not None) else None)
         ctx.meta = (training, relu, mask_input, res is not None)
@@ -741,17 +744,21 @@ class BatchNormFn(Function):
         dgamma = tg if direct else torch.empty((C,), device=dev)
         dbeta = tb if direct else torch.empty((C,), device=dev)
         ws = torch.empty((2 * C,), device=dev, dtype=torch.float64)
-        tmp = torch.empty((2 * C,), device=dev)
         call('rih_bn_bwd', _p(dy), _ld(dy), _p(y), C, _p(x), _ld(x), _p(mean), _p(rstd), _p(gamma), _p(ctx.beta_ref),
              _p(dx), C, _p(dres), C, 0, _p(dgamma), _p(dbeta), int(direct), M, C, int(relu), int(training), int(mask_input),
-             _p(ws), _p(tmp), _stream())
+             _p(ws), _stream())
         if direct:
             dgamma = dbeta = None
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None, None
 
 
-def batchnorm(x, gamma, beta, rmean, rvar, res=None, training=True, momentum=0.1, eps=1e-5, relu=False, mask_input=False, stats=None):
-    return BatchNormFn.apply(x, gamma, beta, rmean, rvar, res, training, momentum, eps, relu, mask_input, stats)
+def batchnorm(x, gamma, beta, rmean, rvar, res=None, training=True, momentum=0.1, eps=1e-5, relu=False, mask_input=False, stats=None,
+              tracked=None):
+    """tracked: the module's `num_batches_tracked` buffer (int64, on the device): incremented by the kernel in training mode, like
+    torch.nn.BatchNorm2d does, so saved checkpoints carry the same buffer values as the reference's."""
+    if tracked is not None and not (tracked.is_cuda and tracked.dtype == torch.int64):
+        raise RuntimeError('renderih_b200: num_batches_tracked must be an int64 CUDA tensor')
+    return BatchNormFn.apply(x, gamma, beta, rmean, rvar, res, training, momentum, eps, relu, mask_input, stats, tracked)
 
 
 class MaxPoolFn(Function):

@@ -41,6 +41,7 @@ class FlatParams:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4        # keep every tensor 16-byte aligned
         self.numel = total
+        self.offsets = offs
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -66,6 +67,40 @@ class FlatParams:
             return dist.get_world_size(group)
         return 1
 
+    # -- optimizer state in torch.optim.AdamW's own layout, so the reference's optimizer resume (MODEL_PARAM.OPTIM_PATH,
+    #    core/lijun_trainer.py:131-144) round-trips: state[i] = {'step', 'exp_avg', 'exp_avg_sq'} per parameter in `self.params` order
+    def _views(self, flat):
+        return [torch.as_strided(flat, p.shape, p.stride(), off) for p, off in zip(self.params, self.offsets)]
+
+    def state_dict(self, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        state = {}
+        for i, (m, v) in enumerate(zip(self._views(self.exp_avg), self._views(self.exp_avg_sq))):
+            state[i] = {'step': torch.tensor(float(self.step_count)), 'exp_avg': m.detach().clone(), 'exp_avg_sq': v.detach().clone()}
+        group = {'lr': lr, 'betas': tuple(betas), 'eps': eps, 'weight_decay': weight_decay, 'amsgrad': False, 'maximize': False,
+                 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None, 'params': list(range(len(self.params)))}
+        return {'state': state, 'param_groups': [group]}
+
+    def load_state_dict(self, sd):
+        state = sd['state']
+        assert len(state) in (0, len(self.params)), 'optimizer state holds %d tensors, the flat buffer %d' % (len(state), len(self.params))
+        steps = set()
+        for i, (m, v) in enumerate(zip(self._views(self.exp_avg), self._views(self.exp_avg_sq))):
+            st = state.get(i, state.get(str(i)))
+            if st is None:
+                continue
+            m.copy_(st['exp_avg']); v.copy_(st['exp_avg_sq'])
+            steps.add(int(float(st['step'])))
+        assert len(steps) <= 1, 'per-parameter step counts differ (%s): the fused AdamW kernel keeps one' % sorted(steps)
+        self.step_count = steps.pop() if steps else 0
+
+    def snapshot(self):
+        """Copy of everything an optimizer step mutates (used to undo the warm-up / dry-run steps of TrainStep)."""
+        return (self.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_count)
+
+    def restore(self, snap):
+        self.flat.copy_(snap[0]); self.exp_avg.copy_(snap[1]); self.exp_avg_sq.copy_(snap[2]); self.step_count = snap[3]
+        self.grad.zero_()
+
     def adamw_step(self, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0, step=None):
         """torch.optim.AdamW semantics (decoupled weight decay) as one kernel over the flat buffer."""
         if step is None:
@@ -76,13 +111,49 @@ class FlatParams:
              torch.cuda.current_stream().cuda_stream)
 
 
+def _mutable_state(model, device):
+    """Everything besides parameters that a training-mode forward mutates: module buffers (BatchNorm running statistics,
+    num_batches_tracked) and the device-resident dropout seed."""
+    bufs = [b for b in model.buffers()]
+    ops.seed_state.ptr(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    return bufs, ops.seed_state.tensors[key]
+
+
+class _Preserve:
+    """Context manager: snapshot the model's buffers + the dropout seed (+ optionally the flat optimizer state) on entry, restore on exit,
+    so dry runs / warm-up steps leave a loaded checkpoint bit-identical."""
+
+    def __init__(self, model, device, flatp=None):
+        self.bufs, self.seed = _mutable_state(model, device)
+        self.flatp = flatp
+
+    def __enter__(self):
+        self.saved = [b.detach().clone() for b in self.bufs]
+        self.saved_seed = self.seed.clone()
+        self.snap = self.flatp.snapshot() if self.flatp is not None else None
+        return self
+
+    def __exit__(self, *exc):
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for b, s in zip(self.bufs, self.saved):
+                b.copy_(s)
+            self.seed.copy_(self.saved_seed)
+        if self.snap is not None:
+            self.flatp.restore(self.snap)
+        return False
+
+
 def trainable_used_params(model, loss_fn, img):
     """Parameters that actually receive a gradient (the reference needs find_unused_parameters=True because 63 tensors
-    never do): found with one dry-run backward."""
+    never do): found with one dry-run backward.  The dry run leaves no trace: BatchNorm running statistics and the
+    dropout seed are restored afterwards."""
     for p in model.parameters():
         p.grad = None
-    out = model(img)
-    loss_fn(out).backward()
+    with _Preserve(model, img.device):
+        out = model(img)
+        loss_fn(out).backward()
     used = [p for p in model.parameters() if p.requires_grad and p.grad is not None]
     for p in model.parameters():
         p.grad = None
@@ -92,12 +163,22 @@ def trainable_used_params(model, loss_fn, img):
 class TrainStep:
     """One data-parallel training step: forward -> loss -> backward -> (all-reduce) -> AdamW, optionally CUDA-graphed."""
 
-    def __init__(self, model, loss_fn, example_img, lr=3e-4, weight_decay=1e-2, use_graph=True, group=None):
+    def __init__(self, model, loss_fn, example_img, lr=3e-4, weight_decay=1e-2, use_graph=True, group=None, labels=None):
+        """labels: optional dict of DEVICE tensors that `loss_fn` reads (the batch's ground truth).  They are the step's static label
+        buffers: `__call__(img, labels)` / `prefetch(img, labels)` copy each new batch's labels into them, like the image."""
         self.model, self.loss_fn, self.group = model, loss_fn, group
+        self.labels = labels or {}
         self.lr, self.wd = lr, weight_decay
         self.base_lr = lr
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.flatp = FlatParams(trainable_used_params(model, loss_fn, example_img))
+        if self.world > 1:
+            # DDP broadcasts rank 0's parameters and buffers at construction (core/lijun_trainer.py:122-127); without it any per-rank
+            # difference at init (seed, a checkpoint loaded on one rank) would persist under identical averaged gradients
+            dist.broadcast(self.flatp.flat, 0, group=group)
+            for t in list(model.buffers()) + [p.data for p in model.parameters() if not any(p is q for q in self.flatp.params)]:
+                if t.is_cuda and t.numel() > 0:
+                    dist.broadcast(t, 0, group=group)
         try:      # the two decoder streams make some AccumulateGrad nodes run on a side stream; torch's advisory warning is expected here
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         except Exception:
@@ -123,6 +204,10 @@ class TrainStep:
         loss.backward()
         return loss.detach()
 
+    def _eager_no_opt(self):
+        """Forward + loss + backward, eager, no collective and no optimizer step (measurement passes: parameters stay where they are)."""
+        return self._step_body()
+
     def _eager(self):
         loss = self._step_body()
         self.flatp.all_reduce(self.group)
@@ -130,48 +215,60 @@ class TrainStep:
         return loss
 
     def capture(self, warmup=3):
-        """Warm up on a side stream, then capture fwd+bwd (graph 1) and the optimizer (graph 2); the NCCL all-reduce
-        runs between the two replays on the same stream (single-GPU: nothing in between)."""
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(warmup):
-                self._eager()
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._step_body()
-        self.flatp.step_count += 0
+        """Warm up forward+backward on a side stream, then capture them into one CUDA graph; the NCCL all-reduce and the fused AdamW
+        kernel run after each replay on the same stream.  Neither the warm-up passes nor the capture pass (which executes nothing, but
+        the warm-up does) leave a trace: parameters, Adam moments, step count, BatchNorm running statistics and the dropout seed are
+        snapshotted before and restored after, so resuming from a checkpoint through TrainStep does not perturb the loaded model."""
+        with _Preserve(self.model, self.static_img.device, self.flatp):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(warmup):
+                    self._step_body()          # forward + backward only: no optimizer step, no collective
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._step_body()
         return self
 
-    def prefetch(self, img_host):
-        """Start the host -> device copy of the NEXT step's batch (pinned host tensor) on a copy stream, overlapping the current step; the
-        next `__call__()` (without an argument) moves it into the graph's static input with one device-to-device copy.  This is the
-        input double-buffering a DataLoader with `pin_memory` + `non_blocking` gives the reference trainer (core/lijun_trainer.py:255-262)."""
+    def prefetch(self, img_host, labels_host=None):
+        """Start the host -> device copy of the NEXT step's batch (pinned host tensors: the image and, optionally, its labels) on a copy
+        stream, overlapping the current step; the next `__call__()` (without arguments) moves it into the graph's static inputs with
+        device-to-device copies.  This is the input double-buffering a DataLoader with `pin_memory` + `non_blocking` gives the reference
+        trainer (core/lijun_trainer.py:246-262: imgTensors and every label tensor go `.to(rank)` each iteration)."""
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.static_img.device)
             self._stage = torch.empty_like(self.static_img)
+            self._stage_labels = {k: torch.empty_like(v) for k, v in self.labels.items()}
             self._stage_free = None
         if self._stage_free is not None:
-            self._copy_stream.wait_event(self._stage_free)      # the previous stage -> static copy must have consumed the buffer
+            self._copy_stream.wait_event(self._stage_free)      # the previous stage -> static copy must have consumed the buffers
         with torch.cuda.stream(self._copy_stream):
             self._stage.copy_(img_host, non_blocking=True)
+            for k, v in (labels_host or {}).items():
+                self._stage_labels[k].copy_(v, non_blocking=True)
         self._staged = True
+        self._staged_keys = tuple((labels_host or {}).keys())
 
-    def __call__(self, img=None):
+    def __call__(self, img=None, labels=None):
         if img is not None:
             self.static_img.copy_(img, non_blocking=True)
+            for k, v in (labels or {}).items():
+                self.labels[k].copy_(v, non_blocking=True)
         elif getattr(self, '_staged', False):
             cur = torch.cuda.current_stream()
             cur.wait_stream(self._copy_stream)
             self.static_img.copy_(self._stage, non_blocking=True)
+            for k in self._staged_keys:
+                self.labels[k].copy_(self._stage_labels[k], non_blocking=True)
             self._stage_free = torch.cuda.Event()
             self._stage_free.record(cur)
             self._staged = False
         if self.graph is None:
             return self._eager()
         self.graph.replay()
-        self.flatp.all_reduce(self.group)
+        if not getattr(self, 'skip_all_reduce', False):      # measurement switch (bench.py: exposed communication = step time with - without)
+            self.flatp.all_reduce(self.group)
         self.flatp.adamw_step(self.lr, weight_decay=self.wd, grad_scale=1.0 / self.world)
         return self.loss

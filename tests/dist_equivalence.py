@@ -1,0 +1,111 @@
+"""2-rank NCCL equivalence of the data-parallel training step (launched by tests/test_train_gpu.py under torchrun, or by hand:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 tests/dist_equivalence.py
+
+SURVEY 4: "N-GPU step == 1-GPU step on the concatenated batch, modulo BatchNorm-statistic locality" (the reference's DDP,
+core/lijun_trainer.py:122-127, averages gradients over ranks; its BatchNorm statistics stay per rank).  Here:
+  * every rank builds the product model with the same seeded weights in eval mode (BatchNorm on running statistics, dropout off; gradients flow as usual);
+  * rank r runs TrainStep on images [r*B, (r+1)*B) of a 2B batch: forward, fused loss, backward, ONE all-reduce of the flat gradient, AdamW
+    with the 1/world mean folded in;
+  * rank 0 additionally runs the 1-rank step on the whole 2B batch from the same initial state;
+  * the loss is a mean over the batch, so the averaged 2-rank gradient must equal the 1-rank gradient and the updated parameters must agree.
+Also checks that TrainStep broadcasts rank 0's parameters at construction (rank 1 starts from perturbed weights on purpose).
+Stated tolerance: gradient 2e-4 of its max magnitude (exact-fp32 kernels; different batch tiling changes summation order only); AdamW updates
+of the elements whose gradient is not round-off within 2 % of lr (the first Adam step is lr * sign(g), ill-conditioned only where g ~ 0).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+B = 4
+
+
+def build(batch, img, labels, perturb=False):
+    from oracle import fixtures
+    from renderih_b200 import assets as A, ops
+    from renderih_b200.config import load_cfg
+    from renderih_b200.loss import GraphLoss, calc_loss_GCN
+    from renderih_b200.model import load_model
+    from renderih_b200.train import TrainStep
+    ops.clear_grad_targets()
+    a = A.synthetic_assets(0)
+    cfg = load_cfg()
+    model = load_model(cfg, assets=a)
+    model.load_state_dict(fixtures.init_state_dict(model.state_dict()))
+    if perturb:
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(0.01)
+    model = model.cuda().eval()           # BatchNorm on its running statistics (no cross-sample coupling: the shards are independent), dropout off
+    model.decoder.unsample_layer.weight.requires_grad_(False)
+    ml, mr = A.synthetic_mano(0, 'left'), A.synthetic_mano(0, 'right')
+    J = {s: torch.from_numpy(np.asarray(m['J_regressor'].todense(), dtype='float32')) for s, m in (('left', ml), ('right', mr))}
+    gl, gr = GraphLoss(J['left'], ml['f'], 4, 'cuda'), GraphLoss(J['right'], mr['f'], 4, 'cuda')
+    lab = {k: v.cuda() for k, v in labels.items()}
+    z = torch.zeros(batch, 21, 3, device='cuda')
+    conv = model.decoder.converter
+
+    def loss_fn(out):
+        return calc_loss_GCN(cfg, 0, gl, gr, conv['left'], conv['right'], out[0], out[1], out[2], out[3], None, None, None,
+                             lab['v2d_l'], z[..., :2], lab['v2d_r'], z[..., :2], lab['v3d_l'], z, lab['v3d_r'], z, lab['root_rel'], 256)[0]
+    return model, loss_fn, TrainStep, img.cuda()
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from oracle import fixtures
+    img_all, lab_all = fixtures.make_image(world * B), fixtures.make_labels(world * B)
+    sl = slice(rank * B, (rank + 1) * B)
+    model, loss_fn, TrainStep, img = build(B, img_all[sl], {k: v[sl] for k, v in lab_all.items()}, perturb=(rank == 1))
+    step = TrainStep(model, loss_fn, img, lr=3e-4, weight_decay=1e-2, use_graph=True)
+    assert step.world == world
+    step.capture(warmup=1)
+    loss = step(img)
+    torch.cuda.synchronize()
+    grad_dp = step.flatp.grad.clone() / world          # the kernel folds the mean into AdamW; the buffer holds the SUM over ranks
+    flat_dp = step.flatp.flat.clone()
+    gathered = [torch.empty_like(flat_dp) for _ in range(world)]
+    dist.all_gather(gathered, flat_dp)
+    for g in gathered[1:]:
+        assert torch.equal(g, gathered[0]), 'ranks diverged after one step (parameters not broadcast / gradients not identical)'
+    losses = [torch.zeros((), device='cuda') for _ in range(world)]
+    dist.all_gather(losses, loss.reshape(()))
+    dist.barrier()
+    ok = True
+    if rank == 0:
+        model1, loss_fn1, TrainStep1, img1 = build(world * B, img_all, lab_all)
+        init_flat = None
+        # a 1-rank TrainStep inside an initialised process group: construct it with world forced to 1
+        import renderih_b200.train as T
+        saved = T.dist.is_initialized
+        T.dist.is_initialized = lambda: False
+        try:
+            solo = TrainStep1(model1, loss_fn1, img1, lr=3e-4, weight_decay=1e-2, use_graph=False)
+            init_flat = solo.flatp.flat.clone()
+            loss1 = solo(img1)
+        finally:
+            T.dist.is_initialized = saved
+        torch.cuda.synchronize()
+        g1 = solo.flatp.grad
+        eg = float((grad_dp - g1).abs().max() / g1.abs().max())
+        # one AdamW step from zero moments moves an element by -lr * (g / (|g| + eps) + wd * p): compare the updates where g is not round-off
+        sig = g1.abs() > 1e-3 * g1.abs().max()
+        ep = float(((flat_dp - init_flat) - (solo.flatp.flat - init_flat)).abs()[sig].max() / 3e-4)
+        lm = float(sum(losses) / world)
+        print('2-rank mean loss %.6f vs 1-rank loss on the concatenated batch %.6f' % (lm, float(loss1)))
+        print('averaged 2-rank gradient vs 1-rank gradient: %.2e of max |g| ; AdamW updates on significant elements differ by %.2e of lr' % (eg, ep))
+        ok = eg < 2e-4 and ep < 2e-2 and abs(lm - float(loss1)) < 1e-4 * abs(float(loss1))
+        print('DIST_EQUIVALENCE_OK' if ok else 'DIST_EQUIVALENCE_FAILED')
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == '__main__':
+    main()

@@ -215,3 +215,24 @@ def test_metrics_jr_matches_oracle():
     v = torch.randn(3, 778, 3)
     assert torch.allclose(jr(v), torch.matmul(metrics_ref.joint_regressor21(J16), v))
     assert len(SAMPLE_FIELDS) == 8
+
+
+def test_mano_pose_helpers_match_reference_golden():
+    """rotations.py / ManoLayer conversion helpers vs values the unmodified reference produced (oracle/make_golden.py mano_helpers):
+    models/manolayer.py:20-98 (vec2mat, rodrigues_batch, build_mano_frame), 163-248 (pca/axis/Rmat conversions, get_local_frame, SE3)."""
+    from renderih_b200 import rotations as R
+    from renderih_b200.manolayer import ManoLayer
+    gold = torch.load(os.path.join(GOLD, 'mano_helpers_synth.pt'), weights_only=False)
+    i, o = gold['inputs'], gold['outputs']
+    layer = ManoLayer(A.synthetic_mano(0, 'right'), center_idx=9, use_pca=True)
+    Rm = R.rodrigues_batch(i['rot_axis'])
+    se3 = layer.buildSE3_batch(R.rodrigues_batch(i['rot_axis'][:5]), i['t'])
+    got = {'rodrigues': R.rodrigues_batch(i['axis']), 'vec2mat': R.vec2mat(i['vec6']), 'frame': R.build_mano_frame(i['skel']),
+           'Rmat2axis': layer.Rmat2axis(Rm), 'pca2axis': layer.pca2axis(i['pca']), 'pca2Rmat': layer.pca2Rmat(i['pca']),
+           'axis2pca': layer.axis2pca(i['axis45']), 'Rmat2pca': layer.Rmat2pca(layer.axis2Rmat(i['axis45'])),
+           'local_frame': layer.get_local_frame(i['shape']), 'se3': se3, 'se3_apply': layer.SE3_apply(se3, i['v'])}
+    for k, ref in o.items():
+        assert got[k].shape == ref.shape, k
+        err = float((got[k] - ref).abs().max())
+        assert err < 2e-6, (k, err)       # fp32 round-off of two equivalent closed forms (measured <= 2.4e-7)
+    assert torch.allclose(R.rodrigues_batch(torch.zeros(2, 3)), torch.eye(3).expand(2, 3, 3))     # zero pose -> identity

@@ -20,7 +20,8 @@ def rel_err(a, b):
 
 # (golden file, first BatchNorm of the trunk) per model: ResNet-50 (BASELINE configs 2-4), HRNet-w48 (config 5), myhand graph variant
 CASES = {'resnet50': ('model_synth_b2.pt', 'encoder.resnet.bn1'), 'hrnet48': ('model_hrnet48_synth_b2.pt', 'encoder.hrnet.bn1'),
-         'graph': ('model_graph_synth_b2.pt', 'encoder.resnet.bn1')}      # 'graph' = common/myhand default variant
+         'graph': ('model_graph_synth_b2.pt', 'encoder.resnet.bn1'),      # 'graph' = common/myhand default variant
+         'resnet50_b16': ('model_synth_b16.pt', 'encoder.resnet.bn1')}    # batch 16: well-conditioned train-mode BatchNorm (>= 1024 samples per channel)
 
 
 # hrnet_mid's biased convolutions that feed a BatchNorm (models/encoder.py:304-326)
@@ -30,7 +31,8 @@ BN_SHADOWED_BIAS = {'mid_model.downsamp_modules.%d.0.bias' % i for i in range(3)
 @pytest.fixture(scope='module', params=sorted(CASES))
 def gold(request):
     g = torch.load(os.path.join(GOLD, CASES[request.param][0]), weights_only=False)
-    g['encoder_type'] = request.param
+    g['encoder_type'] = request.param.split('_')[0]
+    g['case'] = request.param
     return g
 
 
@@ -90,7 +92,7 @@ def test_oracle_train_forward_backward_matches_reference_golden(gold, setup):
     loss = model_ref.calc_loss_GCN(out, fixtures.make_labels(gold['batch']), la)
     assert abs(float(loss) - gold['train']['loss']) / gold['train']['loss'] < 1e-5
     loss.backward()
-    bn1 = CASES[gold['encoder_type']][1]
+    bn1 = CASES[gold['case']][1]
     assert rel_err(sd[bn1 + '.running_mean'], gold['train']['bn1_running_mean']) < RTOL
     assert rel_err(sd[bn1 + '.running_var'], gold['train']['bn1_running_var']) < RTOL
     for k in gold['train']['no_grad_keys']:
