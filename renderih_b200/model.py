@@ -296,6 +296,47 @@ def run_hands(device, fn_left, fn_right):
     return outs[0], outs[1]
 
 
+class GridStreams:
+    """Two more side streams for work that depends only on the image feature maps (`RIH_GRID_STREAMS=0` disables them)."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, device):
+        import os
+        if os.environ.get('RIH_GRID_STREAMS', '1') == '0' or HandStreams.get(device) is None:
+            return None
+        key = (device.type, device.index)
+        if key not in cls._cache:
+            cls._cache[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+        return cls._cache[key]
+
+
+def start_side(device, which, fn):
+    """Launch fn() on grid stream `which`, forked off the current stream, WITHOUT joining.  -> handle for `join_side` (the value itself when the
+    side streams are disabled: then fn is deferred to the join point, i.e. the sequential order)."""
+    st = GridStreams.get(device)
+    if st is None:
+        return ('deferred', fn)
+    s = st[which]
+    s.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(s):
+        out = fn()
+        ev = torch.cuda.Event()
+        ev.record(s)
+    return ('started', out, ev)
+
+
+def join_side(handle):
+    """Make the CURRENT stream wait for a `start_side` branch and hand over its result."""
+    if handle[0] == 'deferred':
+        return handle[1]()
+    _, out, ev = handle
+    cur = torch.cuda.current_stream()
+    cur.wait_event(ev)
+    _record_stream_tree(out, cur)
+    return out
+
+
 # ============================================================================ decoder blocks (models/model_attn/*.py)
 class GCN_ResBlock(nn.Module):
     """models/model_attn/gcn.py:72-110 -- note norm1 is computed-and-discarded by the reference (103-104): it is a
@@ -317,7 +358,10 @@ class GCN_ResBlock(nn.Module):
     def forward(self, x, B, V, relu_out):
         g = self.graph.to(x.device)
         p = self.p if self.training else 0.0
-        c = ops.cheb(x, g, B, V)
+        if x.requires_grad and ops.FUSED['alias']:        # x feeds the graph convolution AND the shortcut: the shortcut hangs off the alias output (no autograd add)
+            c, x = ops.cheb(x, g, B, V, alias_input=True)
+        else:
+            c = ops.cheb(x, g, B, V)
         x1 = ops.linear(c, self.fc1.weight, self.fc1.bias)
         x1 = ops.layernorm(x1, self.norm2.weight, self.norm2.bias, relu=True)
         c = ops.cheb(x1, g, B, V)
@@ -343,7 +387,10 @@ class MLP_GraphBlock(nn.Module):
 
     def forward(self, x, B, V, relu_out):
         p = self.p if self.training else 0.0
-        x1 = ops.layernorm(x, self.norm1.weight, self.norm1.bias, relu=True)
+        if x.requires_grad and ops.FUSED['alias']:
+            x1, x = ops.layernorm(x, self.norm1.weight, self.norm1.bias, relu=True, alias_input=True)
+        else:
+            x1 = ops.layernorm(x, self.norm1.weight, self.norm1.bias, relu=True)
         x1 = ops.linear(x1, self.fc1.weight, self.fc1.bias)
         x1 = ops.layernorm(x1, self.norm2.weight, self.norm2.bias, relu=True)
         x1 = ops.linear(x1, self.fc2.weight, self.fc2.bias, p_drop=p)
@@ -368,6 +415,14 @@ class GraphLayer(nn.Module):
         return x
 
 
+def _ln_res(x, ln):
+    """(LayerNorm(x), x') for a pre-LN residual block: x' is x routed through the LayerNorm node's alias output when gradients flow, so the
+    residual branch's gradient is summed by the LN-backward kernel."""
+    if x.requires_grad and ops.FUSED['alias']:
+        return ops.layernorm(x, ln.weight, ln.bias, alias_input=True)
+    return ops.layernorm(x, ln.weight, ln.bias), x
+
+
 class MLP_res_block(nn.Module):
     """models/model_attn/self_attn.py:17-33"""
 
@@ -380,7 +435,7 @@ class MLP_res_block(nn.Module):
 
     def forward(self, x):
         p = self.p if self.training else 0.0
-        h = ops.layernorm(x, self.layer_norm.weight, self.layer_norm.bias)
+        h, x = _ln_res(x, self.layer_norm)
         h = ops.linear(h, self.fc1.weight, self.fc1.bias, relu=True, p_drop=p)
         return ops.linear(h, self.fc2.weight, self.fc2.bias, res=x, p_drop=p)
 
@@ -401,13 +456,14 @@ class SelfAttn(nn.Module):
         self.ff = MLP_res_block(f_dim, hid_dim, dropout)
         self.p = dropout
 
+    def fused_param_groups(self):
+        """Parameters the fused projections read as one stacked matrix / vector (train.FlatParams keeps them back to back)."""
+        return [(self.w_qs.weight, self.w_ks.weight, self.w_vs.weight), (self.w_qs.bias, self.w_ks.bias, self.w_vs.bias)]
+
     def forward(self, x, B, S):
         p = self.p if self.training else 0.0
-        xn = ops.layernorm(x, self.layer_norm.weight, self.layer_norm.bias)
-        q = ops.linear(xn, self.w_qs.weight, self.w_qs.bias)
-        k = ops.linear(xn, self.w_ks.weight, self.w_ks.bias)
-        v = ops.linear(xn, self.w_vs.weight, self.w_vs.bias)
-        o = ops.attention(q, k, v, B, self.n_heads, S, S, p_drop=p)
+        xn, x = _ln_res(x, self.layer_norm)
+        o = ops.attention_proj(xn, None, self.w_qs, self.w_ks, self.w_vs, B, self.n_heads, S, S, p_drop=p)     # ONE GEMM for q | k | v
         x = ops.linear(o, self.fc.weight, self.fc.bias, res=x, p_drop=p)
         return self.ff(x)
 
@@ -415,13 +471,10 @@ class SelfAttn(nn.Module):
         """SelfAttn over cat([verts (V), extra (E)]) keeping only the V vertex rows (img_attn.py:86-90):
         rows >= V are only ever used as keys/values, so Q / fc / MLP run on the vertex rows alone -- exact."""
         p = self.p if self.training else 0.0
-        vn = ops.layernorm(verts_f, self.layer_norm.weight, self.layer_norm.bias)
+        vn, verts_f = _ln_res(verts_f, self.layer_norm)
         en = ops.layernorm(extra_f, self.layer_norm.weight, self.layer_norm.bias)
         xn = ops.concat_rows(vn, en, B, V, E)
-        q = ops.linear(vn, self.w_qs.weight, self.w_qs.bias)
-        k = ops.linear(xn, self.w_ks.weight, self.w_ks.bias)
-        v = ops.linear(xn, self.w_vs.weight, self.w_vs.bias)
-        o = ops.attention(q, k, v, B, self.n_heads, V, V + E, p_drop=p)
+        o = ops.attention_proj(vn, xn, self.w_qs, self.w_ks, self.w_vs, B, self.n_heads, V, V + E, p_drop=p)   # q from the vertex rows, [k | v] as one GEMM
         x = ops.linear(o, self.fc.weight, self.fc.bias, res=verts_f, p_drop=p)
         return self.ff(x)
 
@@ -474,8 +527,10 @@ class img_ex(nn.Module):
         self.attn = img_attn(verts_f_dim, grid_f_dim, n_heads, dropout)
         self.G = grid_size * grid_size
 
-    def forward(self, img, verts_f, B, V):
-        grid = self.encoder(img, B)
+    def forward(self, img, verts_f, B, V, grid=None):
+        """grid: the image-grid tokens when they were already produced on another stream (`start_grid`)."""
+        if grid is None:
+            grid = self.encoder(img, B)
         return self.attn(verts_f, grid, B, V, self.G)
 
 
@@ -502,10 +557,24 @@ class inter_attn(nn.Module):
         self.ffR = MLP_res_block(f_dim, f_dim, dropout)
         self.p = dropout
 
+    def fused_param_groups(self):
+        return [(self.w_ks.weight, self.w_vs.weight), (self.w_ks.bias, self.w_vs.bias)]
+
     def forward(self, Lf, Rf, B, V):
         p = self.p if self.training else 0.0
         Lf, Rf = run_hands(Lf.device, lambda: self.L_self_attn_layer(Lf, B, V), lambda: self.R_self_attn_layer(Rf, B, V))
         lij = self.variant == 'lijun'
+        H = self.n_heads
+        if not lij:
+            L2, Lf = _ln_res(Lf, self.layer_norm1)
+            R2, Rf = _ln_res(Rf, self.layer_norm2)
+            # each hand's queries against the OTHER hand's keys / values (shared weights): q and [k | v] projections as one GEMM each;
+            # reference order of the two dropout1 draws: attn_R2L then attn_L2R (inter_attn.py:101-102)
+            feat_R2L = ops.attention_proj(L2, R2, self.w_qs, self.w_ks, self.w_vs, B, H, V, V, p_drop=p)
+            feat_L2R = ops.attention_proj(R2, L2, self.w_qs, self.w_ks, self.w_vs, B, H, V, V, p_drop=p)
+            xR = ops.linear(feat_L2R, self.fc.weight, self.fc.bias, res=Rf, p_drop=p)
+            xL = ops.linear(feat_R2L, self.fc.weight, self.fc.bias, res=Lf, p_drop=p)
+            return run_hands(xL.device, lambda: self.ffL(xL), lambda: self.ffR(xR))
         L2 = ops.layernorm(Lf, self.layer_norm1.weight, self.layer_norm1.bias, b=Rf if lij else None)
         R2 = ops.layernorm(Rf, self.layer_norm2.weight, self.layer_norm2.bias, b=Lf if lij else None)
         Lq = ops.linear(L2, self.w_qs.weight, self.w_qs.bias)
@@ -514,7 +583,6 @@ class inter_attn(nn.Module):
         Rq = ops.linear(R2, self.w_qs.weight, self.w_qs.bias)
         Rk = ops.linear(R2, self.w_ks.weight, self.w_ks.bias)
         Rv = ops.linear(R2, self.w_vs.weight, self.w_vs.bias)
-        H = self.n_heads
         # reference order of the two dropout1 draws: attn_R2L then attn_L2R (inter_attn.py:101-102)
         feat_R2L = ops.attention(Lq, Lk if lij else Rk, Rv, B, H, V, V, p_drop=p)
         feat_L2R = ops.attention(Rq, Rk if lij else Lk, Lv, B, H, V, V, p_drop=p)
@@ -541,8 +609,12 @@ class DualGraphLayer(nn.Module):
     def forward(self, Lf, Rf, img_f, B):
         """Lf/Rf already carry `+ position_embeddings` (added by the entry / upsample kernels)."""
         V = self.verts_num
-        Lf, Rf = run_hands(Lf.device, lambda: self.img_ex_left(img_f, self.graph_left(Lf, B, V), B, V),
-                           lambda: self.img_ex_right(img_f, self.graph_right(Rf, B, V), B, V))
+        # the image-grid tokens (patch GEMM + position embedding + a 64-token SelfAttn, ~14 launches per hand) depend only on the feature map:
+        # they start on their own streams now and run beside the 28-launch graph-convolution chains of the two hands
+        gl = start_side(Lf.device, 0, lambda: self.img_ex_left.encoder(img_f, B))
+        gr = start_side(Lf.device, 1, lambda: self.img_ex_right.encoder(img_f, B))
+        Lf, Rf = run_hands(Lf.device, lambda: self.img_ex_left(img_f, self.graph_left(Lf, B, V), B, V, grid=join_side(gl)),
+                           lambda: self.img_ex_right(img_f, self.graph_right(Rf, B, V), B, V, grid=join_side(gr)))
         return self.attn(Lf, Rf, B, V)
 
 

@@ -242,7 +242,7 @@ class LayerNormFn(Function):
     """y = LN(a (+ b)) (relu)  -- nn.LayerNorm(eps=1e-6) sites, e.g. models/model_attn/gcn.py:105,110"""
 
     @staticmethod
-    def forward(ctx, a, b, gamma, beta, eps, relu):
+    def forward(ctx, a, b, gamma, beta, eps, relu, alias_input=False):
         a = _rows(a)
         if b is not None:
             b = _rows(b)
@@ -254,27 +254,40 @@ class LayerNormFn(Function):
              _p(mean), _p(rstd), M, F, float(eps), int(relu), _stream())
         ctx.save_for_backward(a, b, gamma, beta, mean, rstd)
         ctx.relu = relu
+        if alias_input:       # second output = the input itself: the residual branch of a pre-LN block hangs off it, so its gradient arrives
+            assert b is None  # in backward as `d_alias` and the LN-backward kernel adds onto it (no autograd add pass)
+            return y, a
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, d_alias=None):
         a, b, gamma, beta, mean, rstd = ctx.saved_tensors
-        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
         M, F = a.shape
-        dx = torch.empty((M, F), device=dy.device, dtype=torch.float32)
+        if dy is None:        # only the alias branch contributed (cannot happen in the models of this package; kept for completeness)
+            return d_alias, None, None, None, None, None, None
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        acc = 0
+        if d_alias is not None and d_alias.is_contiguous() and d_alias.shape == (M, F):
+            dx, acc = d_alias, 1
+        else:
+            dx = torch.empty((M, F), device=dy.device, dtype=torch.float32)
         tg, tb = _gt(gamma), _gt(beta)
         direct = tg is not None and tb is not None
         dgamma = tg if direct else torch.zeros((F,), device=dy.device, dtype=torch.float32)
         dbeta = tb if direct else torch.zeros((F,), device=dy.device, dtype=torch.float32)
         call('rih_layernorm_bwd', _p(dy), _ld(dy), _p(a), _ld(a), _p(b), _ld(b) if b is not None else 0, _p(gamma), _p(beta),
-             _p(mean), _p(rstd), _p(dx), F, 0, _p(dgamma), _p(dbeta), M, F, int(ctx.relu), _stream())
+             _p(mean), _p(rstd), _p(dx), F, acc, _p(dgamma), _p(dbeta), M, F, int(ctx.relu), _stream())
+        if d_alias is not None and acc == 0:
+            dx = dx + d_alias
         if direct:
             dgamma = dbeta = None
-        return dx, (dx if b is not None else None), dgamma, dbeta, None, None
+        return dx, (dx if b is not None else None), dgamma, dbeta, None, None, None
 
 
-def layernorm(a, gamma, beta, b=None, eps=1e-6, relu=False):
-    return LayerNormFn.apply(a, b, gamma, beta, eps, relu)
+def layernorm(a, gamma, beta, b=None, eps=1e-6, relu=False, alias_input=False):
+    """alias_input: also return `a` as a second output; route the block's residual use of `a` through it and the gradient of that branch
+    is accumulated by the LayerNorm-backward kernel instead of a separate autograd add (pre-LN residual blocks, self_attn.py:24-33,66-85)."""
+    return LayerNormFn.apply(a, b, gamma, beta, eps, relu, alias_input)
 
 
 # ----------------------------------------------------------------------------- Chebyshev basis (K=2)
@@ -282,27 +295,37 @@ class ChebFn(Function):
     """[x, Lx] interleaved along features -- graph_conv_cheby, models/model_attn/gcn.py:34-69"""
 
     @staticmethod
-    def forward(ctx, x, graph, B, V):
+    def forward(ctx, x, graph, B, V, alias_input=False):
         x = _rows(x)
         F = x.shape[1]
         assert x.shape[0] == B * V
         out = torch.empty((B * V, 2 * F), device=x.device, dtype=torch.float32)
         call('rih_cheb_fwd', _p(x), _ld(x), _p(graph.rowptr), _p(graph.col), _p(graph.val), _p(out), B, V, F, _stream())
         ctx.graph, ctx.dims = graph, (B, V, F)
+        if alias_input:
+            return out, x
         return out
 
     @staticmethod
-    def backward(ctx, d):
+    def backward(ctx, d, d_alias=None):
         B, V, F = ctx.dims
         g = ctx.graph
         d = d.contiguous()
-        dx = torch.empty((B * V, F), device=d.device, dtype=torch.float32)
-        call('rih_cheb_bwd', _p(d), _p(g.rowptr_t), _p(g.col_t), _p(g.val_t), _p(dx), F, 0, B, V, F, _stream())
-        return dx, None, None, None
+        acc = 0
+        if d_alias is not None and d_alias.is_contiguous() and d_alias.shape == (B * V, F):
+            dx, acc = d_alias, 1         # the shortcut branch's gradient: the SpMM-transpose kernel adds onto it
+        else:
+            dx = torch.empty((B * V, F), device=d.device, dtype=torch.float32)
+        call('rih_cheb_bwd', _p(d), _p(g.rowptr_t), _p(g.col_t), _p(g.val_t), _p(dx), F, acc, B, V, F, _stream())
+        if d_alias is not None and acc == 0:
+            dx = dx + d_alias
+        return dx, None, None, None, None
 
 
-def cheb(x, graph, B, V):
-    return ChebFn.apply(x, graph, B, V)
+def cheb(x, graph, B, V, alias_input=False):
+    """alias_input: also return x as a second output for the block's shortcut branch (gcn.py:99-110): its gradient is accumulated by the
+    backward SpMM kernel instead of an autograd add."""
+    return ChebFn.apply(x, graph, B, V, alias_input)
 
 
 # ----------------------------------------------------------------------------- position embedding (+ nearest vertex upsample)
@@ -428,6 +451,221 @@ def attention(q, k, v, B, H, Sq, Sk, p_drop=0.0, impl=None):
     if nsplit and aligned and B * H > 0 and Sq > 0 and Sk <= 512:
         return AttnTcFn.apply(q, k, v, B, H, Sq, Sk, p_drop, site, nsplit)
     return AttnFn.apply(q, k, v, B, H, Sq, Sk, p_drop, site)
+
+
+# ----------------------------------------------------------------------------- fused projections + attention core
+def adjacent(ts):
+    """True when the tensors lie back to back in memory (each one dense): then [t0; t1; ...] is ONE row-major matrix / vector."""
+    if any(t is None for t in ts):
+        return False
+    for a, b in zip(ts[:-1], ts[1:]):
+        if not a.is_contiguous() or a.data_ptr() + a.numel() * a.element_size() != b.data_ptr():
+            return False
+    return ts[-1].is_contiguous()
+
+
+def fuse_storage(params):
+    """Make the given parameters adjacent in memory (one backing buffer, each `.data` a view of it) unless they already are, so that GEMMs can
+    treat them as one stacked matrix.  Parameters that train.FlatParams has re-homed keep their place (FlatParams lays tagged groups out
+    adjacently itself); returns True when the group is adjacent afterwards."""
+    if adjacent([p.data for p in params]):
+        return True
+    if any(p.data_ptr() in GRAD_TARGETS for p in params) or torch.cuda.is_current_stream_capturing():
+        return False
+    with torch.no_grad():
+        buf = torch.empty(sum(p.numel() for p in params), device=params[0].device, dtype=params[0].dtype)
+        off = 0
+        for p in params:
+            v = buf[off:off + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            off += p.numel()
+    return True
+
+
+class AttnProjFn(Function):
+    """Q / K / V projections + the attention core as ONE autograd node:
+         q = xq Wq^T + bq ; [k | v] = xkv [Wk; Wv]^T + [bk; bv] ; o = softmax(q k^T / sqrt(d)) v  (probability dropout)
+       -- self_attn.py:66-76, inter_attn.py:82-105.  With xq is xkv (plain self-attention) the three projections are ONE GEMM with N = 3 HD
+       (the weights are adjacent in memory: fuse_storage / FlatParams groups); otherwise one GEMM for q and one for [k | v].  q, k, v live as
+       column slices of one [rows, 3 HD] / [rows, 2 HD] buffer (the kernels take row strides), and in backward the attention kernels write
+       dq / dk / dv into the slices of one gradient buffer, so the input gradient is ONE dgrad GEMM (K = 3 HD) and the weight gradient ONE
+       wgrad GEMM -- instead of 3 + 3 + 3 launches and two autograd adds."""
+
+    @staticmethod
+    def forward(ctx, xq, xkv, wq, wk, wv, bq, bk, bv, B, H, Sq, Sk, p_drop, site, nsplit):
+        same = xkv is None
+        xq = _rows(xq)
+        xkv = xq if same else _rows(xkv)
+        HD, K = wq.shape
+        d = HD // H
+        assert xq.shape == (B * Sq, K) and xkv.shape == (B * Sk, K)
+        Mq, Mk = xq.shape[0], xkv.shape[0]
+        dev = xq.device
+        s = _stream()
+        w_adj = adjacent([wq, wk, wv]) and adjacent([bq, bk, bv])
+        if same:
+            qkv = torch.empty((Mq, 3 * HD), device=dev, dtype=torch.float32)
+            if w_adj:
+                call('rih_linear_fwd', _p(xq), _ld(xq), _p(wq), K, _p(bq), _p(qkv), 3 * HD, Mq, 3 * HD, K, 0, 0, None, 0, 0.0, None, 0, None, 0, s)
+            else:
+                for i, (w, b) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
+                    call('rih_linear_fwd', _p(xq), _ld(xq), _p(w), K, _p(b), qkv.data_ptr() + 4 * i * HD, 3 * HD, Mq, HD, K, 0, 0, None, 0, 0.0, None, 0, None, 0, s)
+            q, k, v = qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:]
+            kvbuf = None
+        else:
+            qkv = torch.empty((Mq, HD), device=dev, dtype=torch.float32)
+            kvbuf = torch.empty((Mk, 2 * HD), device=dev, dtype=torch.float32)
+            call('rih_linear_fwd', _p(xq), _ld(xq), _p(wq), K, _p(bq), _p(qkv), HD, Mq, HD, K, 0, 0, None, 0, 0.0, None, 0, None, 0, s)
+            if adjacent([wk, wv]) and adjacent([bk, bv]):
+                call('rih_linear_fwd', _p(xkv), _ld(xkv), _p(wk), K, _p(bk), _p(kvbuf), 2 * HD, Mk, 2 * HD, K, 0, 0, None, 0, 0.0, None, 0, None, 0, s)
+            else:
+                for i, (w, b) in enumerate(((wk, bk), (wv, bv))):
+                    call('rih_linear_fwd', _p(xkv), _ld(xkv), _p(w), K, _p(b), kvbuf.data_ptr() + 4 * i * HD, 2 * HD, Mk, HD, K, 0, 0, None, 0, 0.0, None, 0, None, 0, s)
+            q, k, v = qkv, kvbuf[:, :HD], kvbuf[:, HD:]
+        o = torch.empty((Mq, HD), device=dev, dtype=torch.float32)
+        scale = 1.0 / (d ** 0.5)
+        sp = seed_state.ptr(dev) if p_drop > 0 else None
+        P = Pd = lse = None
+        ldp = (Sk + 3) // 4 * 4
+        if nsplit:
+            P = torch.empty((B * H, Sq, ldp), device=dev, dtype=torch.float32)
+            Pd = torch.empty_like(P) if p_drop > 0 else None
+            call('rih_attn_tc_fwd', _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(o), HD, _p(P), _p(Pd), ldp,
+                 B, H, Sq, Sk, d, scale, float(p_drop), sp, site, nsplit, s)
+        else:
+            lse = torch.empty((B * H * Sq,), device=dev, dtype=torch.float32)
+            call('rih_attn_fwd', _p(q), Sq * _ld(q), _ld(q), _p(k), Sk * _ld(k), _ld(k), _p(v), Sk * _ld(v), _ld(v),
+                 _p(o), Sq * HD, HD, _p(lse), B, H, Sq, Sk, d, scale, float(p_drop), sp, site, s)
+        ctx.save_for_backward(xq, None if same else xkv, wq, wk, wv, qkv, kvbuf, o, P, lse)
+        ctx.meta = (same, B, H, Sq, Sk, d, scale, p_drop, site, nsplit, ldp)
+        ctx.refs = (bq, bk, bv)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        xq, xkv, wq, wk, wv, qkv, kvbuf, o, P, lse = ctx.saved_tensors
+        same, B, H, Sq, Sk, d, scale, p_drop, site, nsplit, ldp = ctx.meta
+        bq, bk, bv = ctx.refs
+        if same:
+            xkv = xq
+        do = _rows(do.contiguous() if do.stride(-1) != 1 else do)
+        HD, K = wq.shape
+        Mq, Mk = xq.shape[0], xkv.shape[0]
+        dev = do.device
+        s = _stream()
+        if same:
+            q, k, v = qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:]
+            dqkv = torch.empty((Mq, 3 * HD), device=dev, dtype=torch.float32)
+            dq, dk, dv = dqkv[:, :HD], dqkv[:, HD:2 * HD], dqkv[:, 2 * HD:]
+            dkv = None
+        else:
+            q, k, v = qkv, kvbuf[:, :HD], kvbuf[:, HD:]
+            dqkv = torch.empty((Mq, HD), device=dev, dtype=torch.float32)
+            dkv = torch.empty((Mk, 2 * HD), device=dev, dtype=torch.float32)
+            dq, dk, dv = dqkv, dkv[:, :HD], dkv[:, HD:]
+        sp = seed_state.ptr(dev) if p_drop > 0 else None
+        if nsplit:
+            ws = torch.empty_like(P)
+            Pd = torch.empty_like(P) if p_drop > 0 else None
+            call('rih_attn_tc_bwd', _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(do), _ld(do), _p(P), _p(ws), _p(Pd), ldp,
+                 _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv), B, H, Sq, Sk, d, scale, float(p_drop), sp, site, nsplit, s)
+        else:
+            call('rih_attn_bwd', _p(q), Sq * _ld(q), _ld(q), _p(k), Sk * _ld(k), _ld(k), _p(v), Sk * _ld(v), _ld(v),
+                 _p(o), Sq * HD, HD, _p(do), Sq * _ld(do), _ld(do), _p(lse),
+                 _p(dq), Sq * _ld(dq), _ld(dq), _p(dk), Sk * _ld(dk), _ld(dk), _p(dv), Sk * _ld(dv), _ld(dv),
+                 B, H, Sq, Sk, d, scale, float(p_drop), sp, site, s)
+        ni = ctx.needs_input_grad
+        dxq = dxkv = None
+        w3 = adjacent([wq, wk, wv])
+        w2 = adjacent([wk, wv])
+        # ---- input gradients
+        if same and ni[0]:
+            dxq = torch.empty((Mq, K), device=dev, dtype=torch.float32)
+            if w3:
+                call('rih_linear_dgrad', _p(dqkv), 3 * HD, _p(wq), K, _p(dxq), K, Mq, 3 * HD, K, 0, 0, s)
+            else:
+                for i, w in enumerate((wq, wk, wv)):
+                    call('rih_linear_dgrad', dqkv.data_ptr() + 4 * i * HD, 3 * HD, _p(w), K, _p(dxq), K, Mq, HD, K, int(i > 0), 0, s)
+        elif not same:
+            if ni[0]:
+                dxq = torch.empty((Mq, K), device=dev, dtype=torch.float32)
+                call('rih_linear_dgrad', _p(dqkv), HD, _p(wq), K, _p(dxq), K, Mq, HD, K, 0, 0, s)
+            if ni[1]:
+                dxkv = torch.empty((Mk, K), device=dev, dtype=torch.float32)
+                if w2:
+                    call('rih_linear_dgrad', _p(dkv), 2 * HD, _p(wk), K, _p(dxkv), K, Mk, 2 * HD, K, 0, 0, s)
+                else:
+                    for i, w in enumerate((wk, wv)):
+                        call('rih_linear_dgrad', dkv.data_ptr() + 4 * i * HD, 2 * HD, _p(w), K, _p(dxkv), K, Mk, HD, K, int(i > 0), 0, s)
+        # ---- parameter gradients: straight into the flat gradient buffer when registered (side stream), else returned to autograd
+        tw = [_gt(w) for w in (wq, wk, wv)]
+        tb = [_gt(b) for b in (bq, bk, bv)]
+        direct = all(t is not None for t in tw + tb)
+        if direct:
+            side = _wgrad_fork(dqkv, dkv, xq, xkv) or s
+            gw, gb = tw, tb
+            acc = 1
+        else:
+            side = s
+            gw = [torch.empty((HD, K), device=dev, dtype=torch.float32) for _ in range(3)] if not (same and w3) else None
+            gb = [torch.empty((HD,), device=dev, dtype=torch.float32) for _ in range(3)]
+            acc = 0
+        if same and w3 and (not direct or (adjacent(tw) and adjacent(tb))):
+            if direct:
+                call('rih_linear_wgrad', _p(dqkv), 3 * HD, _p(xq), _ld(xq), _p(gw[0]), K, Mq, 3 * HD, K, 1, 0, side)
+                call('rih_colsum', _p(dqkv), 3 * HD, Mq, 3 * HD, _p(gb[0]), 1, side)
+            else:
+                big = torch.empty((3 * HD, K), device=dev, dtype=torch.float32)
+                bigb = torch.empty((3 * HD,), device=dev, dtype=torch.float32)
+                call('rih_linear_wgrad', _p(dqkv), 3 * HD, _p(xq), _ld(xq), _p(big), K, Mq, 3 * HD, K, 0, 0, side)
+                call('rih_colsum', _p(dqkv), 3 * HD, Mq, 3 * HD, _p(bigb), 0, side)
+                gw = [big[i * HD:(i + 1) * HD] for i in range(3)]
+                gb = [bigb[i * HD:(i + 1) * HD] for i in range(3)]
+        else:
+            if gw is None:
+                gw = [torch.empty((HD, K), device=dev, dtype=torch.float32) for _ in range(3)]
+            srcs = ((dqkv, 0, 3 * HD, xq, Mq), (dqkv, HD, 3 * HD, xq, Mq), (dqkv, 2 * HD, 3 * HD, xq, Mq)) if same else \
+                   ((dqkv, 0, HD, xq, Mq), (dkv, 0, 2 * HD, xkv, Mk), (dkv, HD, 2 * HD, xkv, Mk))
+            for i, (g, off, ld, x, M) in enumerate(srcs):
+                call('rih_linear_wgrad', g.data_ptr() + 4 * off, ld, _p(x), _ld(x), _p(gw[i]), K, M, HD, K, acc, 0, side)
+                call('rih_colsum', g.data_ptr() + 4 * off, ld, M, HD, _p(gb[i]), acc, side)
+        if direct:
+            gw = gb = [None, None, None]
+        return (dxq, dxkv, gw[0], gw[1], gw[2], gb[0], gb[1], gb[2]) + (None,) * 7
+
+
+FUSED = {'qkv': _os.environ.get('RIH_FUSED_QKV', '1') != '0',        # A/B switches: 0 = separate projection GEMMs + attention node
+         'alias': _os.environ.get('RIH_RES_ALIAS', '1') != '0'}       #               0 = residual-branch gradients summed by autograd adds
+
+
+def attention_proj(xq, xkv, lin_q, lin_k, lin_v, B, H, Sq, Sk, p_drop=0.0):
+    """o = Attention(xq Wq, xkv Wk, xkv Wv) -- see AttnProjFn.  lin_*: the nn.Linear parameter holders (self_attn.py:54-56); pass xkv=None
+    for plain self-attention (queries, keys and values all from xq)."""
+    if not FUSED['qkv']:
+        xk = xq if xkv is None else xkv
+        q = linear(xq, lin_q.weight, lin_q.bias)
+        k = linear(xk, lin_k.weight, lin_k.bias)
+        v = linear(xk, lin_v.weight, lin_v.bias)
+        return attention(q, k, v, B, H, Sq, Sk, p_drop=p_drop)
+    site = seed_state.next_site() if p_drop > 0 else 0
+    nsplit = _ATTN['nsplit']
+    impl = _ATTN.get('force')
+    if impl == 'simt':
+        nsplit = 0
+    elif impl == 'tc' and nsplit == 0:
+        nsplit = 3
+    HD = lin_q.weight.shape[0]
+    d = HD // H
+    if not (nsplit and d % 4 == 0 and B * H > 0 and Sq > 0 and Sk <= 512):
+        nsplit = 0
+    if xkv is None:
+        fuse_storage([lin_q.weight, lin_k.weight, lin_v.weight])
+        fuse_storage([lin_q.bias, lin_k.bias, lin_v.bias])
+    else:
+        fuse_storage([lin_k.weight, lin_v.weight])
+        fuse_storage([lin_k.bias, lin_v.bias])
+    return AttnProjFn.apply(xq, xkv, lin_q.weight, lin_k.weight, lin_v.weight, lin_q.bias, lin_k.bias, lin_v.bias, B, H, Sq, Sk, p_drop, site, nsplit)
 
 
 # ----------------------------------------------------------------------------- dropout (stand-alone)

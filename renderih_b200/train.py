@@ -30,9 +30,24 @@ class FlatParams:
     """Re-home the given parameters (and their .grad) into flat contiguous buffers, preserving each tensor's strides
     (conv weights stay channels_last)."""
 
-    def __init__(self, params):
+    def __init__(self, params, groups=()):
+        """groups: tuples of parameters that must lie back to back in the flat buffers (same for their gradients), in the given order --
+        e.g. (w_qs.weight, w_ks.weight, w_vs.weight), which the fused Q/K/V projection reads as ONE [3d, d] matrix (ops.AttnProjFn)."""
         params = [p for p in params if p.requires_grad]
         assert params, 'no trainable parameters'
+        present = {id(p) for p in params}
+        member = {}
+        for g in groups:
+            if all(id(p) in present for p in g) and all(p.numel() % 4 == 0 for p in g):
+                for p in g:
+                    member[id(p)] = g
+        ordered, placed = [], set()
+        for p in params:
+            if id(p) in placed:
+                continue
+            for q in member.get(id(p), (p,)):
+                ordered.append(q); placed.add(id(q))
+        params = ordered
         dev = params[0].device
         self.params = params
         total = 0
@@ -72,19 +87,26 @@ class FlatParams:
     def _views(self, flat):
         return [torch.as_strided(flat, p.shape, p.stride(), off) for p, off in zip(self.params, self.offsets)]
 
-    def state_dict(self, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    def state_dict(self, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, index=None, n_params=None):
+        """index: {id(parameter): position in the optimizer's parameter list} (default: position in this buffer).  TrainStep passes the
+        position among the model's trainable parameters, i.e. the numbering `torch.optim.AdamW(network.parameters())` uses in the
+        reference trainer; parameters that never receive a gradient have no state there either."""
+        index = index or {id(p): i for i, p in enumerate(self.params)}
         state = {}
-        for i, (m, v) in enumerate(zip(self._views(self.exp_avg), self._views(self.exp_avg_sq))):
-            state[i] = {'step': torch.tensor(float(self.step_count)), 'exp_avg': m.detach().clone(), 'exp_avg_sq': v.detach().clone()}
+        for p, m, v in zip(self.params, self._views(self.exp_avg), self._views(self.exp_avg_sq)):
+            state[index[id(p)]] = {'step': torch.tensor(float(self.step_count)), 'exp_avg': m.detach().clone().contiguous(),
+                                   'exp_avg_sq': v.detach().clone().contiguous()}
         group = {'lr': lr, 'betas': tuple(betas), 'eps': eps, 'weight_decay': weight_decay, 'amsgrad': False, 'maximize': False,
-                 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None, 'params': list(range(len(self.params)))}
+                 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None,
+                 'params': list(range(n_params if n_params is not None else len(self.params)))}
         return {'state': state, 'param_groups': [group]}
 
-    def load_state_dict(self, sd):
+    def load_state_dict(self, sd, index=None):
         state = sd['state']
-        assert len(state) in (0, len(self.params)), 'optimizer state holds %d tensors, the flat buffer %d' % (len(state), len(self.params))
+        index = index or {id(p): i for i, p in enumerate(self.params)}
         steps = set()
-        for i, (m, v) in enumerate(zip(self._views(self.exp_avg), self._views(self.exp_avg_sq))):
+        for p, m, v in zip(self.params, self._views(self.exp_avg), self._views(self.exp_avg_sq)):
+            i = index[id(p)]
             st = state.get(i, state.get(str(i)))
             if st is None:
                 continue
@@ -171,7 +193,8 @@ class TrainStep:
         self.lr, self.wd = lr, weight_decay
         self.base_lr = lr
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.flatp = FlatParams(trainable_used_params(model, loss_fn, example_img))
+        groups = [g for m in model.modules() if hasattr(m, 'fused_param_groups') for g in m.fused_param_groups()]
+        self.flatp = FlatParams(trainable_used_params(model, loss_fn, example_img), groups=groups)
         if self.world > 1:
             # DDP broadcasts rank 0's parameters and buffers at construction (core/lijun_trainer.py:122-127); without it any per-rank
             # difference at init (seed, a checkpoint loaded on one rank) would persist under identical averaged gradients
@@ -187,6 +210,19 @@ class TrainStep:
         self.graph = None
         self.loss = None
         self.use_graph = use_graph
+
+    def _optim_index(self):
+        train = [p for p in self.model.parameters() if p.requires_grad]
+        return {id(p): i for i, p in enumerate(train)}, len(train)
+
+    def optimizer_state_dict(self):
+        """AdamW state in torch.optim.AdamW's layout, numbered like `torch.optim.AdamW(network.parameters())` numbers the model's trainable
+        parameters (the reference trainer's optimizer, core/lijun_trainer.py:131-144), so MODEL_PARAM.OPTIM_PATH checkpoints round-trip."""
+        index, n = self._optim_index()
+        return self.flatp.state_dict(lr=self.lr, weight_decay=self.wd, index=index, n_params=n)
+
+    def load_optimizer_state_dict(self, sd):
+        self.flatp.load_state_dict(sd, index=self._optim_index()[0])
 
     def set_epoch(self, epoch, cfg=None, **kw):
         """Learning-rate schedule of the reference trainer: the fused AdamW kernel takes the rate as a launch argument
