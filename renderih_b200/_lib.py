@@ -43,6 +43,7 @@ def parse_header(path=HEADER):
     return protos
 
 
+PDL_DEFAULT = '0'     # flipped to '1' once validated on hardware (A/B in bench.py)
 STREAM_LAST = set()   # entry points whose last parameter is the CUDA stream to launch on (every kernel-launching one)
 TRACE = None          # measurement hook (bench.py): when set to a list, every launching call is bracketed by CUDA events recorded on ITS stream
 _lib = None
@@ -75,6 +76,8 @@ def load():
         fn.restype = ctypes.c_char_p if 'char' in ret else ctypes.c_int
         fn.argtypes = args
     _lib = lib
+    # programmatic dependent launch for every kernel (csrc/common.cuh); RIH_PDL=0 selects plain stream-ordered launches
+    lib.rih_set_pdl(1 if os.environ.get('RIH_PDL', PDL_DEFAULT) != '0' else 0)
     return lib
 
 

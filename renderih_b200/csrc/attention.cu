@@ -73,6 +73,7 @@ attn_fwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const floa
                 const float* __restrict__ v, long long v_bs, int ldv, float* __restrict__ o, long long o_bs, int ldo,
                 float* __restrict__ lse, int H, int Sq, int Sk, int d, float scale, int rows_per_cta,
                 const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
+  pdl_sync();
   const unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
   extern __shared__ __align__(16) float smem[];
   const AttGeo g = make_geo(d, Sk);
@@ -194,7 +195,7 @@ RIH_API int rih_attn_fwd(const float* q, long long q_bs, int ldq, const float* k
   {                                                                                                                                    \
     static bool attr = false;                                                                                                          \
     if (!attr) { RIH_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<MJ, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; } \
-    attn_fwd_kernel<MJ, RR><<<grid, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, lse, H, Sq, Sk, d, scale, \
+    launch_k(attn_fwd_kernel<MJ, RR>, grid, ATT_WARPS * 32, smem, s, q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, lse, H, Sq, Sk, d, scale, \
                                                                 rows_per_cta, seed_ptr, site, thresh, ik);                             \
   }
   if (Skr <= 128) { if (RF == 8) RIH_ATT_FWD(4, 8) else RIH_ATT_FWD(4, 4) }
@@ -215,6 +216,7 @@ attn_bwd_kernel(const float* __restrict__ q, long long q_bs, int ldq, const floa
                 float* __restrict__ dq, long long dq_bs, int lddq, float* __restrict__ dk, long long dk_bs, int lddk,
                 float* __restrict__ dv, long long dv_bs, int lddv,
                 int H, int Sq, int Sk, int d, float scale, const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
+  pdl_sync();
   const unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
   extern __shared__ __align__(16) float smem[];
   const AttGeo gk = make_geo(d, Sk);   // splits over keys (phase A accumulations)
@@ -414,7 +416,7 @@ RIH_API int rih_attn_bwd(const float* q, long long q_bs, int ldq, const float* k
   {                                                                                                                                    \
     static bool attr = false;                                                                                                          \
     if (!attr) { RIH_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<MJ, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; } \
-    attn_bwd_kernel<MJ, RR><<<B * H, ATT_WARPS * 32, smem, s>>>(q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, dout, do_bs, lddo, lse, \
+    launch_k(attn_bwd_kernel<MJ, RR>, B * H, ATT_WARPS * 32, smem, s, q, q_bs, ldq, k, k_bs, ldk, v, v_bs, ldv, o, o_bs, ldo, dout, do_bs, lddo, lse, \
                                                                  dq, dq_bs, lddq, dk, dk_bs, lddk, dv, dv_bs, lddv, H, Sq, Sk, d, scale, seed_ptr, site, thresh, ik); \
   }
   if (Smax <= 128) { if (RB == 4) RIH_ATT_BWD(4, 4) else RIH_ATT_BWD(4, 2) }
@@ -443,6 +445,7 @@ constexpr int SM_MAXT = 16;   // keys per lane (Sk <= 512)
 __global__ void __launch_bounds__(256)
 attn_softmax_fwd_kernel(float* __restrict__ P, float* __restrict__ Pd, long long rows, int Sq, int Sk, int Skp,
                         const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
+  pdl_sync();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -482,6 +485,7 @@ attn_softmax_fwd_kernel(float* __restrict__ P, float* __restrict__ Pd, long long
 __global__ void __launch_bounds__(256)
 attn_softmax_bwd_kernel(const float* __restrict__ P, float* __restrict__ dP, float* __restrict__ Pd, long long rows, int Sq, int Sk, int Skp,
                         const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
+  pdl_sync();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -535,7 +539,7 @@ RIH_API int rih_attn_tc_fwd(const float* q, int ldq, const float* k, int ldk, co
   const float ik = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
   RIH_REQUIRE(!thresh || (Pd && seed_ptr), "attn_tc_fwd: dropout needs the Pd buffer and a device seed");
   const long long rows = (long long)B * H * Sq;
-  attn_softmax_fwd_kernel<<<cdiv(rows, 8), 256, 0, s>>>(P, Pd, rows, Sq, Sk, ldp, seed_ptr, site, thresh, ik);
+  launch_k(attn_softmax_fwd_kernel, cdiv(rows, 8), 256, 0, s, P, Pd, rows, Sq, Sk, ldp, seed_ptr, site, thresh, ik);
   if (int e = check_launch("attn_softmax_fwd")) return e;
   return tc::bgemm_tf32(scr(thresh ? Pd : P, Sq, Sk, ldp), 0, tok(v, Sk, d, ldv), 1, tok(o, Sq, d, ldo), B, H, Sq, d, Sk, 1.f, s);
 }
@@ -554,7 +558,7 @@ RIH_API int rih_attn_tc_bwd(const float* q, int ldq, const float* k, int ldk, co
   const float ik = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
   RIH_REQUIRE(!thresh || (Pd && seed_ptr), "attn_tc_bwd: dropout needs the Pd buffer and a device seed");
   const long long rows = (long long)B * H * Sq;
-  attn_softmax_bwd_kernel<<<cdiv(rows, 8), 256, 0, s>>>(P, ws, Pd, rows, Sq, Sk, ldp, seed_ptr, site, thresh, ik);
+  launch_k(attn_softmax_bwd_kernel, cdiv(rows, 8), 256, 0, s, P, ws, Pd, rows, Sq, Sk, ldp, seed_ptr, site, thresh, ik);
   if (int e = check_launch("attn_softmax_bwd")) return e;
   const float* Pt = thresh ? Pd : P;
   if (int e = tc::bgemm_tf32(scr(ws, Sq, Sk, ldp), 0, tok(k, Sk, d, ldk), 1, tok(dq, Sq, d, lddq), B, H, Sq, d, Sk, scale, s)) return e;     // dQ = scale dS K

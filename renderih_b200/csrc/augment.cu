@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256)
 augment_u8_kernel(const unsigned char* __restrict__ src, const double* __restrict__ minv, const double* __restrict__ gain_offset,
                   const unsigned char* __restrict__ flip, float* __restrict__ dst, float* __restrict__ ori, unsigned char* __restrict__ out_u8,
                   int B, int H, int W, float m0, float m1, float m2, float s0, float s1, float s2) {
+  pdl_sync();
   const long long total = (long long)B * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % W); const long long t = i / W; const int y = (int)(t % H); const int b = (int)(t / H);
@@ -66,7 +67,7 @@ RIH_API int rih_augment_u8(const unsigned char* src, const double* minv, const d
   const long long total = (long long)B * H * W;
   if (total == 0) return 0;
   const int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  augment_u8_kernel<<<grid, 256, 0, s>>>(src, minv, gain_offset, flip, dst, ori, out_u8, B, H, W, mean3_host[0], mean3_host[1], mean3_host[2],
+  launch_k(augment_u8_kernel, grid, 256, 0, s, src, minv, gain_offset, flip, dst, ori, out_u8, B, H, W, mean3_host[0], mean3_host[1], mean3_host[2],
                                          std3_host[0], std3_host[1], std3_host[2]);
   return check_launch("augment_u8");
 }

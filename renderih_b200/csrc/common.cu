@@ -3,6 +3,7 @@
 
 namespace rih {
 static thread_local char g_err[1024] = "";
+int g_pdl = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -22,7 +23,11 @@ int check_launch(const char* what) {
 }  // namespace rih
 
 RIH_API const char* rih_last_error(void) { return rih::g_err; }
-RIH_API int rih_version(void) { return 100; }
+RIH_API int rih_version(void) { return 200; }
+
+// Programmatic dependent launch for every kernel of the library (see common.cuh): 1 = on, 0 = plain stream-ordered launches.  Scheduling only:
+// results are unchanged (no reference counterpart).
+RIH_API int rih_set_pdl(int on) { rih::g_pdl = on ? 1 : 0; return 0; }
 
 // Device properties probe (used by the host side to fail loudly on a non-sm_100 device).
 RIH_API int rih_device_info(int device, int* cc_major, int* cc_minor, int* sm_count, size_t* smem_optin) {

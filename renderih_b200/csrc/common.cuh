@@ -32,6 +32,30 @@ int check_launch(const char* what);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of this library is launched through launch_k() and starts with pdl_sync() (or its two halves).  With g_pdl != 0 the launch
+// carries cudaLaunchAttributeProgrammaticStreamSerialization: the kernel may be scheduled as soon as every CTA of its stream predecessor has
+// executed griddepcontrol.launch_dependents (first instruction of all our kernels) -- its CTAs become resident on free SMs, run their
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) and then block in griddepcontrol.wait until the predecessor has COMPLETED and
+// its memory operations are visible.  That takes the launch latency and the prologue off the dependent chains of the decoder (hundreds of
+// 5-15 us kernels).  Nothing before pdl_wait() may touch global memory a predecessor writes.  Under CUDA-graph capture the edges become
+// programmatic dependencies of the graph.  g_pdl == 0: plain launches; griddepcontrol.* are no-ops then.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_launch_dependents(); pdl_wait(); }
+
+template <class... KArgs, class... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through check_launch() (cudaGetLastError)
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -197,6 +197,7 @@ static inline Epilogue make_epilogue(float* c, int ldc, int M, int N, const floa
 template <int BM, int BN, int TM, int TN, class AL, class BL>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_simt_kernel(AL al, BL bl, Epilogue ep, int K, int k_per_split) {
+  pdl_sync();
   static_assert((BM / TM) * (BN / TN) == GEMM_THREADS, "tile/thread mismatch");
   static_assert(TM == 4 || TM == 8, "TM");
   static_assert(TN == 4 || TN == 8, "TN");
@@ -346,9 +347,9 @@ int launch_gemm_simt(const AL& al, const BL& bl, Epilogue ep, int M, int N, int 
   dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
   if (grid.y > 65535) { set_error("%s: M too large for grid.y", what); return 1; }
   if (big)
-    gemm_simt_kernel<128, 128, 8, 8, AL, BL><<<grid, GEMM_THREADS, 0, stream>>>(al, bl, ep, K, kps);
+    launch_k(gemm_simt_kernel<128, 128, 8, 8, AL, BL>, grid, GEMM_THREADS, 0, stream, al, bl, ep, K, kps);
   else
-    gemm_simt_kernel<64, 64, 4, 4, AL, BL><<<grid, GEMM_THREADS, 0, stream>>>(al, bl, ep, K, kps);
+    launch_k(gemm_simt_kernel<64, 64, 4, 4, AL, BL>, grid, GEMM_THREADS, 0, stream, al, bl, ep, K, kps);
   return check_launch(what);
 }
 

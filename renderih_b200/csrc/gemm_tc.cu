@@ -140,11 +140,11 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep,
     const int ctas = (int)(total < cap ? total : cap);
     if (ep.stats && !(tma_epi && splits == 1)) ep.stats = nullptr;
     g_stats_fused = ep.stats != nullptr;
-    pk<<<ctas, persistent_threads<NSPLIT>(), smem_bytes<BN, NSPLIT>(), s>>>(ta, tb, tc_, ep, prod, num_kb, kb_per_split, tiles_m, tiles_n, splits, tma_epi);
+    launch_k(pk, dim3(ctas), dim3(persistent_threads<NSPLIT>()), (size_t)smem_bytes<BN, NSPLIT>(), s, ta, tb, tc_, ep, prod, num_kb, kb_per_split, tiles_m, tiles_n, splits, tma_epi);
     return check_launch("gemm_tc_persistent");
   }
   g_stats_fused = 0;
-  kern<<<grid, THREADS, smem_bytes<BN, NSPLIT>(), s>>>(ta, tb, tc_, ep, prod, num_kb, kb_per_split, tma_epi);
+  launch_k(kern, grid, dim3(THREADS), (size_t)smem_bytes<BN, NSPLIT>(), s, ta, tb, tc_, ep, prod, num_kb, kb_per_split, tma_epi);
   return check_launch("gemm_tc");
 }
 static int g_nsplit = 1;   // set per call by the dispatchers below (1 = TF32, 2 = TF32 rn, 3 = 3xTF32)

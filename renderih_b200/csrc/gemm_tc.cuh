@@ -294,6 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_full = bars + 3 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
 
+  pdl_launch_dependents();     // the stream successor may start its own prologue now; it blocks in its pdl_wait() until this grid is done
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kb_beg = blockIdx.z * kb_per_split;
@@ -315,6 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // prologue done (barriers, TMEM, descriptors): from here on the kernel reads what its stream predecessor wrote
 
   if (warp == 0) {
     if (lane == 0) {
@@ -480,6 +482,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   uint64_t* tmem_empty = bars + 3 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
+  pdl_launch_dependents();     // the stream successor may start its own prologue now; it blocks in its pdl_wait() until this grid is done
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = tiles_m * tiles_n * splits;
 
@@ -499,6 +502,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // prologue done (barriers, TMEM, descriptors): from here on the kernel reads what its stream predecessor wrote
 
   // third tile coordinate z: split-K slice (kb_beg = z * kb_per_split), or -- batched GEMM (ep.batch_heads != 0) -- the batch index
   const bool batched = ep.batch_heads != 0;

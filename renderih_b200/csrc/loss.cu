@@ -50,6 +50,7 @@ __device__ __forceinline__ void block_reduce_terms(float (&acc)[GL_TERMS], float
 template <bool BWD>
 __global__ void __launch_bounds__(GL_THREADS)
 graph_loss_kernel(GraphLossArgs a, float* __restrict__ partial, const float* __restrict__ coef) {
+  pdl_sync();
   __shared__ float s_vp[GL_V * 3], s_vg[GL_V * 3];
   __shared__ float s_gv[BWD ? GL_V * 3 : 1];
   __shared__ float s_jd[GL_J * 3];
@@ -194,6 +195,7 @@ graph_loss_kernel(GraphLossArgs a, float* __restrict__ partial, const float* __r
 // LABEL_3D, LABEL_2D); coef[7] (for backward) = d total / d (term sum) = w[t] / (2 * count[t]) * upstream.
 __global__ void graph_loss_finalize_kernel(const float* __restrict__ partial, int B, int F, int Vc, float w0, float w1, float w2, float w3, float w4,
                                            float w5, float w6, float* __restrict__ out, float* __restrict__ coef) {
+  pdl_sync();
   const float w[GL_TERMS] = {w0, w1, w2, w3, w4, w5, w6};
   const float cnt[GL_TERMS] = {(float)B * GL_V * 3, (float)B * GL_V * 2, (float)B * GL_J * 3, (float)B * F * 3, (float)B * F * 3, (float)B * Vc * 3, (float)B * Vc * 2};
   if (threadIdx.x == 0) {
@@ -213,6 +215,7 @@ __global__ void graph_loss_finalize_kernel(const float* __restrict__ partial, in
   }
 }
 __global__ void graph_loss_scale_coef_kernel(const float* __restrict__ coef, const float* __restrict__ upstream, float* __restrict__ out) {
+  pdl_sync();
   if (threadIdx.x < GL_TERMS) out[threadIdx.x] = coef[threadIdx.x] * upstream[0];
 }
 
@@ -238,10 +241,10 @@ RIH_API int rih_graph_loss_fwd(const float* const* ptrs, const int* const* iptrs
                                float* partial, float* out, float* coef, cudaStream_t s) {
   GraphLossArgs a;
   if (int e = fill_args(a, ptrs, iptrs, nullptr, B, F, Vc, pool, img)) return e;
-  graph_loss_kernel<false><<<dim3(B, 2), GL_THREADS, 0, s>>>(a, partial, nullptr);
+  launch_k(graph_loss_kernel<false>, dim3(B, 2), GL_THREADS, 0, s, a, partial, nullptr);
   if (int e = check_launch("graph_loss_fwd")) return e;
   const float* w = weights_host;
-  graph_loss_finalize_kernel<<<1, 32, 0, s>>>(partial, B, F, Vc, w[0], w[1], w[2], w[3], w[4], w[5], w[6], out, coef);
+  launch_k(graph_loss_finalize_kernel, 1, 32, 0, s, partial, B, F, Vc, w[0], w[1], w[2], w[3], w[4], w[5], w[6], out, coef);
   return check_launch("graph_loss_finalize");
 }
 
@@ -251,8 +254,8 @@ RIH_API int rih_graph_loss_bwd(const float* const* ptrs, const int* const* iptrs
                                const float* coef, const float* upstream, float* coef_scaled, cudaStream_t s) {
   GraphLossArgs a;
   if (int e = fill_args(a, ptrs, iptrs, gptrs, B, F, Vc, pool, img)) return e;
-  graph_loss_scale_coef_kernel<<<1, 32, 0, s>>>(coef, upstream, coef_scaled);
+  launch_k(graph_loss_scale_coef_kernel, 1, 32, 0, s, coef, upstream, coef_scaled);
   if (int e = check_launch("graph_loss_scale_coef")) return e;
-  graph_loss_kernel<true><<<dim3(B, 2), GL_THREADS, 0, s>>>(a, nullptr, coef_scaled);
+  launch_k(graph_loss_kernel<true>, dim3(B, 2), GL_THREADS, 0, s, a, nullptr, coef_scaled);
   return check_launch("graph_loss_bwd");
 }

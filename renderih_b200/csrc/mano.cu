@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(MANO_THREADS)
 mano_fwd_kernel(ManoConsts mc, const float* __restrict__ root_rot, const float* __restrict__ pose, int use_pca, int ncomps,
                 const float* __restrict__ shape, const float* __restrict__ trans, const float* __restrict__ scale,
                 int center_idx, int new_skel, float* __restrict__ v_out, float* __restrict__ j_out) {
+  pdl_sync();
   __shared__ float s_v[MANO_V3];        // v_shaped -> v_tpose -> v_output
   __shared__ float s_axis[48];
   __shared__ float s_R[16][9];          // [0] = root, [1..15] = pose rotations
@@ -238,6 +239,7 @@ mano_bwd_kernel(ManoConsts mc, const float* __restrict__ root_rot, const float* 
                 int center_idx, int new_skel, const float* __restrict__ g_v, const float* __restrict__ g_j,
                 float* __restrict__ d_root, float* __restrict__ d_pose, float* __restrict__ d_shape,
                 float* __restrict__ d_trans, float* __restrict__ d_scale) {
+  pdl_sync();
   __shared__ float s_vt[MANO_V3];       // v_shaped -> v_tpose
   __shared__ float s_vl[MANO_V3];       // skinned vertices (before centre / scale / trans)
   __shared__ float s_g[MANO_V3];        // gradient buffer: g(v_out) -> g(v_lbs) -> g(v_tpose) -> g(v_shaped)
@@ -583,7 +585,7 @@ RIH_API int rih_mano_bwd(const float* const* const_ptrs, const int* parent, cons
   if (B == 0) return 0;
   ManoConsts mc;
   if (int e = fill_consts(mc, const_ptrs, parent, "mano_bwd")) return e;
-  mano_bwd_kernel<<<B, MANO_THREADS, 0, s>>>(mc, root_rot, pose, use_pca, ncomps, shape, trans, scale, center_idx, new_skel, g_v, g_j,
+  launch_k(mano_bwd_kernel, B, MANO_THREADS, 0, s, mc, root_rot, pose, use_pca, ncomps, shape, trans, scale, center_idx, new_skel, g_v, g_j,
                                              d_root, d_pose, d_shape, d_trans, d_scale);
   return check_launch("mano_bwd");
 }
@@ -598,6 +600,6 @@ RIH_API int rih_mano_fwd(const float* const* const_ptrs, const int* parent, cons
   if (B == 0) return 0;
   ManoConsts mc;
   if (int e = fill_consts(mc, const_ptrs, parent, "mano_fwd")) return e;
-  mano_fwd_kernel<<<B, MANO_THREADS, 0, s>>>(mc, root_rot, pose, use_pca, ncomps, shape, trans, scale, center_idx, new_skel, v_out, j_out);
+  launch_k(mano_fwd_kernel, B, MANO_THREADS, 0, s, mc, root_rot, pose, use_pca, ncomps, shape, trans, scale, center_idx, new_skel, v_out, j_out);
   return check_launch("mano_fwd");
 }

@@ -95,6 +95,7 @@ __device__ __forceinline__ float aligned_err(const float* T, const float* x1, co
 }
 
 __global__ void __launch_bounds__(EM_THREADS) eval_metrics_kernel(EvalArgs a) {
+  pdl_sync();
   __shared__ float s_vp[EM_V * 3], s_vg[EM_V * 3];         // absolute on load, root-relative after step 2
   __shared__ float s_jp[EM_J * 3], s_jg[EM_J * 3];
   __shared__ float s_red[EM_WARPS * 20];
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(EM_THREADS) eval_metrics_kernel(EvalArgs a) {
 __global__ void __launch_bounds__(EM_THREADS)
 eval_pair_kernel(const float* __restrict__ pl, const float* __restrict__ pr, const float* __restrict__ gl, const float* __restrict__ gr,
                  const float* __restrict__ roots, int B, float contact, float* __restrict__ mrrpe, float* __restrict__ cdev) {
+  pdl_sync();
   __shared__ float s_gl[EM_V * 3];
   __shared__ float s_red[EM_WARPS * 2];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -276,9 +278,9 @@ RIH_API int rih_eval_metrics(const float* const* ptrs, int B, float contact_dist
     RIH_REQUIRE(a.h[hnd].vp && a.h[hnd].vg && a.h[hnd].J21, "eval_metrics: null input pointer (hand %d)", hnd);
   }
   a.B = B; a.sample = sample; a.per_joint = per_joint; a.per_vert = per_vert; a.roots = roots;
-  eval_metrics_kernel<<<dim3(B, 2), EM_THREADS, 0, s>>>(a);
+  launch_k(eval_metrics_kernel, dim3(B, 2), EM_THREADS, 0, s, a);
   RIH_CUDA(cudaGetLastError());
-  eval_pair_kernel<<<B, EM_THREADS, 0, s>>>(a.h[0].vp, a.h[1].vp, a.h[0].vg, a.h[1].vg, roots, B, contact_dist, mrrpe, cdev);
+  launch_k(eval_pair_kernel, B, EM_THREADS, 0, s, a.h[0].vp, a.h[1].vp, a.h[0].vg, a.h[1].vg, roots, B, contact_dist, mrrpe, cdev);
   RIH_CUDA(cudaGetLastError());
   return 0;
 }

@@ -6,6 +6,7 @@ using namespace rih;
 // ============================================================== layout conversion
 // NCHW [N,C,H,W] -> NHWC [N,H,W,Cp] (channels >= C zero-filled). reference input layout: models/model.py:25
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int C, int HW, int Cp, int ldy) {
+  pdl_sync();
   __shared__ float tile[32][33];
   int n = blockIdx.z;
   int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -20,6 +21,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restri
   }
 }
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int C, int HW, int ldx, int c_off) {
+  pdl_sync();
   __shared__ float tile[32][33];
   int n = blockIdx.z;
   int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -35,6 +37,7 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restri
 }
 // few-channel images (the RGB input): one thread per pixel, plane reads coalesced across the warp, pixel writes contiguous
 __global__ void nchw_to_nhwc_small_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int Cp, int ldy, long long total) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / HW; const int p = (int)(i - n * HW);
     float* q = y + i * ldy;
@@ -46,22 +49,23 @@ RIH_API int rih_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int
   if (Cp <= 8) {
     const long long total = (long long)N * HW;
     if (total == 0) return 0;
-    nchw_to_nhwc_small_kernel<<<(int)min((long long)148 * 16, (total + 255) / 256), 256, 0, s>>>(x, y, C, HW, Cp, ldy, total);
+    launch_k(nchw_to_nhwc_small_kernel, (int)min((long long)148 * 16, (total + 255) / 256), 256, 0, s, x, y, C, HW, Cp, ldy, total);
     return check_launch("nchw_to_nhwc");
   }
   dim3 grid(cdiv(HW, 32), cdiv(Cp, 32), N), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, s>>>(x, y, N, C, HW, Cp, ldy);
+  launch_k(nchw_to_nhwc_kernel, grid, block, 0, s, x, y, N, C, HW, Cp, ldy);
   return check_launch("nchw_to_nhwc");
 }
 // y NCHW [N,C,HW] <- channels [c_off, c_off+C) of x NHWC
 RIH_API int rih_nhwc_to_nchw(const float* x, float* y, int N, int C, int HW, int ldx, int c_off, cudaStream_t s) {
   dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
-  nhwc_to_nchw_kernel<<<grid, block, 0, s>>>(x, y, N, C, HW, ldx, c_off);
+  launch_k(nhwc_to_nchw_kernel, grid, block, 0, s, x, y, N, C, HW, ldx, c_off);
   return check_launch("nhwc_to_nchw");
 }
 
 // generic strided 2-D copy / add:  y[r, 0:C] (+)= x[r, 0:C]
 __global__ void copy2d_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, long long rows, int C, int acc) {
+  pdl_sync();
   long long total = rows * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long r; int c; divmod(i, C, total < (1ll << 32), r, c);
@@ -73,13 +77,14 @@ __global__ void copy2d_kernel(const float* __restrict__ x, int ldx, float* __res
 RIH_API int rih_copy2d(const float* x, int ldx, float* y, int ldy, long long rows, int C, int accumulate, cudaStream_t s) {
   if (rows * C == 0) return 0;
   int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
-  copy2d_kernel<<<grid, 256, 0, s>>>(x, ldx, y, ldy, rows, C, accumulate);
+  launch_k(copy2d_kernel, grid, 256, 0, s, x, ldx, y, ldy, rows, C, accumulate);
   return check_launch("copy2d");
 }
 
 // ============================================================== BatchNorm
 // column statistics over M rows: partial sums in double, atomically merged.  ws = double[2*C] (zeroed here)
 __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int C, int rows_per_cta, double* __restrict__ ws) {
+  pdl_sync();
   int c = blockIdx.x * 32 + threadIdx.x;
   int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
   double s = 0.0, ss = 0.0;
@@ -124,7 +129,7 @@ RIH_API int rih_bn_colstats(const float* x, int ld, int M, int C, double* ws, cu
   int target = cdiv(148 * 8, gx);
   int rows_per_cta = max(64, cdiv(M, target));
   dim3 grid(gx, cdiv(M, rows_per_cta)), block(32, 8);
-  bn_stats_kernel<<<grid, block, 0, s>>>(x, ld, M, C, rows_per_cta, ws);
+  launch_k(bn_stats_kernel, grid, block, 0, s, x, ld, M, C, rows_per_cta, ws);
   return check_launch("bn_stats");
 }
 
@@ -139,6 +144,7 @@ bn_forward_kernel(const float* __restrict__ x, int ldx, const double* __restrict
                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ res, int ldr,
                   float* __restrict__ y, int ldy, int relu, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                   float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ tracked) {
+  pdl_sync();
   const BnMap mp = bn_map(C4);
   const int c = mp.q * 4, C = C4 * 4;
   float mu[4], rs[4];
@@ -185,7 +191,7 @@ RIH_API int rih_bn_forward(const float* x, int ldx, const double* stats, long lo
                            float* mean_out, float* rstd_out, float* running_mean, float* running_var, long long* tracked, cudaStream_t s) {
   RIH_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (!res || ldr % 4 == 0), "bn_forward: needs C,ld %% 4 == 0");
   RIH_REQUIRE(M > 0 && (stats || (running_mean && running_var)), "bn_forward: eval mode needs the running statistics");
-  bn_forward_kernel<<<bn_grid(M, C / 4, 256), 256, 0, s>>>(x, ldx, stats, M, C / 4, eps, momentum, gamma, beta, res, ldr, y, ldy, relu,
+  launch_k(bn_forward_kernel, bn_grid(M, C / 4, 256), 256, 0, s, x, ldx, stats, M, C / 4, eps, momentum, gamma, beta, res, ldr, y, ldy, relu,
                                                           mean_out, rstd_out, running_mean, running_var, tracked);
   return check_launch("bn_forward");
 }
@@ -197,6 +203,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __rest
                      const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      int M, int C, int rows_per_cta, int relu, double* __restrict__ ws) {
+  pdl_sync();
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const int c = blockIdx.x * 32 + tx * 4;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
@@ -242,6 +249,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restr
                     float* __restrict__ dx, int lddx, float* __restrict__ dres, int lddr, int dres_acc,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, int param_acc,
                     long long M, int C4, int relu, int training, int mask_input) {
+  pdl_sync();
   const BnMap mp = bn_map(C4);
   const int c = mp.q * 4, C = C4 * 4;
   const float invM = 1.f / (float)M;
@@ -314,9 +322,9 @@ RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const
   int target = cdiv(148 * 8, gx);
   int rows_per_cta = max(64, cdiv(M, target));
   dim3 grid(gx, cdiv(M, rows_per_cta));
-  bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, (int)M, C, rows_per_cta, relu, ws);
+  launch_k(bn_bwd_reduce_kernel, grid, 256, 0, s, dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, (int)M, C, rows_per_cta, relu, ws);
   if (int e = check_launch("bn_bwd_reduce")) return e;
-  bn_bwd_apply_kernel<<<bn_grid(M, C / 4, 256), 256, 0, s>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx, dres, lddr, dres_acc,
+  launch_k(bn_bwd_apply_kernel, bn_grid(M, C / 4, 256), 256, 0, s, dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx, dres, lddr, dres_acc,
                                                             dgamma, dbeta, param_acc, M, C / 4, relu, training, mask_input);
   return check_launch("bn_bwd_apply");
 }
@@ -324,6 +332,7 @@ RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const
 // relu backward in place/out of place for Conv->ReLU fused epilogues: dx = dy * (y > 0)
 __global__ void relu_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, float* __restrict__ dx, int lddx,
                                 long long rows, int C) {
+  pdl_sync();
   long long total = rows * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long r; int c; divmod(i, C, total < (1ll << 32), r, c);
@@ -333,7 +342,7 @@ __global__ void relu_bwd_kernel(const float* __restrict__ dy, int lddy, const fl
 RIH_API int rih_relu_bwd(const float* dy, int lddy, const float* y, int ldy, float* dx, int lddx, long long rows, int C, cudaStream_t s) {
   if (rows * C == 0) return 0;
   int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
-  relu_bwd_kernel<<<grid, 256, 0, s>>>(dy, lddy, y, ldy, dx, lddx, rows, C);
+  launch_k(relu_bwd_kernel, grid, 256, 0, s, dy, lddy, y, ldy, dx, lddx, rows, C);
   return check_launch("relu_bwd");
 }
 
@@ -341,6 +350,7 @@ RIH_API int rih_relu_bwd(const float* dy, int lddy, const float* y, int ldy, flo
 // first-max-wins in (r,s) scan order, matching ATen max_pool2d; idx stores r*3+s (uint8)
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ idx,
                                    int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_sync();
   long long total = (long long)N * Ho * Wo * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C); long long t = i / C; int ow = (int)(t % Wo); t /= Wo; int oh = (int)(t % Ho); int n = (int)(t / Ho);
@@ -358,6 +368,7 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restric
 }
 __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ idx, float* __restrict__ dx,
                                    int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_sync();
   long long total = (long long)N * H * W * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C); long long t = i / C; int iw = (int)(t % W); t /= W; int ih = (int)(t % H); int n = (int)(t / H);
@@ -376,6 +387,7 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned 
 // float4 (4 channels per thread) variants: the 268 MB stem activation is streamed once at full width
 __global__ void maxpool4_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ idx,
                                     int N, int H, int W, int C4, int Ho, int Wo) {
+  pdl_sync();
   const long long total = (long long)N * Ho * Wo * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C4); long long t = i / C4; int ow = (int)(t % Wo); t /= Wo; int oh = (int)(t % Ho); int n = (int)(t / Ho);
@@ -398,6 +410,7 @@ __global__ void maxpool4_fwd_kernel(const float* __restrict__ x, float* __restri
 }
 __global__ void maxpool4_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ idx, float* __restrict__ dx,
                                     int N, int H, int W, int C4, int Ho, int Wo) {
+  pdl_sync();
   const long long total = (long long)N * H * W * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C4); long long t = i / C4; int iw = (int)(t % W); t /= W; int ih = (int)(t % H); int n = (int)(t / H);
@@ -421,8 +434,8 @@ RIH_API int rih_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, i
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && (reinterpret_cast<uintptr_t>(idx) & 3) == 0;
   long long total = (long long)N * Ho * Wo * (vec ? C / 4 : C);
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  if (vec) maxpool4_fwd_kernel<<<grid, 256, 0, s>>>(x, y, idx, N, H, W, C / 4, Ho, Wo);
-  else maxpool_fwd_kernel<<<grid, 256, 0, s>>>(x, y, idx, N, H, W, C, Ho, Wo);
+  if (vec) launch_k(maxpool4_fwd_kernel, grid, 256, 0, s, x, y, idx, N, H, W, C / 4, Ho, Wo);
+  else launch_k(maxpool_fwd_kernel, grid, 256, 0, s, x, y, idx, N, H, W, C, Ho, Wo);
   return check_launch("maxpool_fwd");
 }
 RIH_API int rih_maxpool3x3s2_bwd(const float* dy, const unsigned char* idx, float* dx, int N, int H, int W, int C, cudaStream_t s) {
@@ -430,8 +443,8 @@ RIH_API int rih_maxpool3x3s2_bwd(const float* dy, const unsigned char* idx, floa
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 && (reinterpret_cast<uintptr_t>(idx) & 3) == 0;
   long long total = (long long)N * H * W * (vec ? C / 4 : C);
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  if (vec) maxpool4_bwd_kernel<<<grid, 256, 0, s>>>(dy, idx, dx, N, H, W, C / 4, Ho, Wo);
-  else maxpool_bwd_kernel<<<grid, 256, 0, s>>>(dy, idx, dx, N, H, W, C, Ho, Wo);
+  if (vec) launch_k(maxpool4_bwd_kernel, grid, 256, 0, s, dy, idx, dx, N, H, W, C / 4, Ho, Wo);
+  else launch_k(maxpool_bwd_kernel, grid, 256, 0, s, dy, idx, dx, N, H, W, C, Ho, Wo);
   return check_launch("maxpool_bwd");
 }
 
@@ -444,6 +457,7 @@ __device__ __forceinline__ void bil_coord(int o, float scale, int in, int& i0, i
   l1 = src - (float)i0;
 }
 __global__ void bilinear2x_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int N, int H, int W, int C) {
+  pdl_sync();
   int Ho = 2 * H, Wo = 2 * W;
   float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
   long long total = (long long)N * Ho * Wo * C;
@@ -459,6 +473,7 @@ __global__ void bilinear2x_fwd_kernel(const float* __restrict__ x, int ldx, floa
   }
 }
 __global__ void bilinear2x_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx, int N, int H, int W, int C) {
+  pdl_sync();
   int Ho = 2 * H, Wo = 2 * W;
   float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
   long long total = (long long)N * Ho * Wo * C;
@@ -484,7 +499,7 @@ RIH_API int rih_bilinear2x_fwd(const float* x, int ldx, float* y, int ldy, int N
   if (bil_vec_ok(x, ldx, y, ldy, C)) return rih_bilinear_up_fwd(x, ldx, y, ldy, N, H, W, C, 2, s);      // float4 kernel
   long long total = (long long)N * 4 * H * W * C;
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  bilinear2x_fwd_kernel<<<grid, 256, 0, s>>>(x, ldx, y, ldy, N, H, W, C);
+  launch_k(bilinear2x_fwd_kernel, grid, 256, 0, s, x, ldx, y, ldy, N, H, W, C);
   return check_launch("bilinear2x_fwd");
 }
 // dx must be zero-initialised by the caller (scatter-add)
@@ -492,7 +507,7 @@ RIH_API int rih_bilinear2x_bwd(const float* dy, int lddy, float* dx, int lddx, i
   if (bil_vec_ok(dy, lddy, dx, lddx, C)) return rih_bilinear_up_bwd(dy, lddy, dx, lddx, N, H, W, C, 2, s);   // gather form: overwrites dx, no atomics
   long long total = (long long)N * 4 * H * W * C;
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  bilinear2x_bwd_kernel<<<grid, 256, 0, s>>>(dy, lddy, dx, lddx, N, H, W, C);
+  launch_k(bilinear2x_bwd_kernel, grid, 256, 0, s, dy, lddy, dx, lddx, N, H, W, C);
   return check_launch("bilinear2x_bwd");
 }
 
@@ -501,6 +516,7 @@ RIH_API int rih_bilinear2x_bwd(const float* dy, int lddy, float* dx, int lddx, i
 // three coarse HRNet branches are up-sampled x2 / x4 / x8 and written straight into their channel slice of the 720-wide concat
 // buffer (y points at the slice, ldy is the full row stride), so torch.cat (encoder.py:231) costs no extra pass.
 __global__ void bilinear_up4_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int N, int H, int W, int C4, int f) {
+  pdl_sync();
   const int Ho = f * H, Wo = f * W;
   const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
   const long long total = (long long)N * Ho * Wo * C4;
@@ -523,6 +539,7 @@ __global__ void bilinear_up4_fwd_kernel(const float* __restrict__ x, int ldx, fl
 // backward as a gather: every input pixel (h, w) sums the contributions of the output pixels whose interpolation window
 // touches it (rows oh with src(oh) in (h-1, h+1)), no atomics, deterministic.
 __global__ void bilinear_up4_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx, int N, int H, int W, int C4, int f) {
+  pdl_sync();
   const int Ho = f * H, Wo = f * W;
   const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
   const long long total = (long long)N * H * W * C4;
@@ -560,7 +577,7 @@ RIH_API int rih_bilinear_up_fwd(const float* x, int ldx, float* y, int ldy, int 
   long long total = (long long)N * f * H * f * W * (C / 4);
   if (total == 0) return 0;
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  bilinear_up4_fwd_kernel<<<grid, 256, 0, s>>>(x, ldx, y, ldy, N, H, W, C / 4, f);
+  launch_k(bilinear_up4_fwd_kernel, grid, 256, 0, s, x, ldx, y, ldy, N, H, W, C / 4, f);
   return check_launch("bilinear_up_fwd");
 }
 // dx[N*H*W, C] = adjoint of rih_bilinear_up_fwd applied to dy[N*fH*fW, C] (row stride lddy); overwrites dx
@@ -570,7 +587,7 @@ RIH_API int rih_bilinear_up_bwd(const float* dy, int lddy, float* dx, int lddx, 
   long long total = (long long)N * H * W * (C / 4);
   if (total == 0) return 0;
   int grid = (int)min((long long)148 * 16, (total + 127) / 128);
-  bilinear_up4_bwd_kernel<<<grid, 128, 0, s>>>(dy, lddy, dx, lddx, N, H, W, C / 4, f);
+  launch_k(bilinear_up4_bwd_kernel, grid, 128, 0, s, dy, lddy, dx, lddx, N, H, W, C / 4, f);
   return check_launch("bilinear_up_bwd");
 }
 
@@ -580,6 +597,7 @@ RIH_API int rih_bilinear_up_bwd(const float* dy, int lddy, float* dx, int lddx, 
 // Terms are added in list order (the reference's left-to-right association).
 struct FuseTerms { const float* p[4]; int ld[4]; int f[4]; int n; };
 __global__ void fuse_sum_kernel(FuseTerms a, float* __restrict__ y, int ldy, int N, int H, int W, int C4, int relu) {
+  pdl_sync();
   const long long total = (long long)N * H * W * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C4); long long t = i / C4; int w = (int)(t % W); t /= W; int h = (int)(t % H); int n = (int)(t / H);
@@ -610,12 +628,13 @@ RIH_API int rih_fuse_sum(const float* const* terms, const int* lds, const int* f
   long long total = (long long)N * H * W * (C / 4);
   if (total == 0) return 0;
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  fuse_sum_kernel<<<grid, 256, 0, s>>>(a, y, ldy, N, H, W, C / 4, relu);
+  launch_k(fuse_sum_kernel, grid, 256, 0, s, a, y, ldy, N, H, W, C / 4, relu);
   return check_launch("fuse_sum");
 }
 // adjoint of a nearest x f up-sample: dx[n,h,w,:] = sum_{a,b<f} (y > 0 ? dy : 0)[n, f*h+a, f*w+b, :]   (y == nullptr: no mask)
 __global__ void pool_sum_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, float* __restrict__ dx, int lddx,
                                 int N, int H, int W, int C4, int f) {
+  pdl_sync();
   const long long total = (long long)N * H * W * C4;
   const int Hf = H * f, Wf = W * f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -640,12 +659,13 @@ RIH_API int rih_pool_sum(const float* dy, int lddy, const float* y, int ldy, flo
   long long total = (long long)N * H * W * (C / 4);
   if (total == 0) return 0;
   int grid = (int)min((long long)148 * 16, (total + 127) / 128);
-  pool_sum_kernel<<<grid, 128, 0, s>>>(dy, lddy, y, ldy, dx, lddx, N, H, W, C / 4, f);
+  launch_k(pool_sum_kernel, grid, 128, 0, s, dy, lddy, y, ldy, dx, lddx, N, H, W, C / 4, f);
   return check_launch("pool_sum");
 }
 
 // ============================================================== global average pool [N, HW, C] -> [N, C]
 __global__ void gap_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int N, int HW, int C) {
+  pdl_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   int n = i / C, c = i - n * C;
@@ -654,6 +674,7 @@ __global__ void gap_fwd_kernel(const float* __restrict__ x, int ldx, float* __re
   y[i] = s / (float)HW;
 }
 __global__ void gap_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int lddx, int N, int HW, int C, int acc) {
+  pdl_sync();
   long long total = (long long)N * HW * C;
   float inv = 1.f / (float)HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -664,19 +685,20 @@ __global__ void gap_bwd_kernel(const float* __restrict__ dy, float* __restrict__
   }
 }
 RIH_API int rih_gap_fwd(const float* x, int ldx, float* y, int N, int HW, int C, cudaStream_t s) {
-  gap_fwd_kernel<<<cdiv((long long)N * C, 256), 256, 0, s>>>(x, ldx, y, N, HW, C);
+  launch_k(gap_fwd_kernel, cdiv((long long)N * C, 256), 256, 0, s, x, ldx, y, N, HW, C);
   return check_launch("gap_fwd");
 }
 RIH_API int rih_gap_bwd(const float* dy, float* dx, int lddx, int N, int HW, int C, int accumulate, cudaStream_t s) {
   long long total = (long long)N * HW * C;
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  gap_bwd_kernel<<<grid, 256, 0, s>>>(dy, dx, lddx, N, HW, C, accumulate);
+  launch_k(gap_bwd_kernel, grid, 256, 0, s, dy, dx, lddx, N, HW, C, accumulate);
   return check_launch("gap_bwd");
 }
 
 // ============================================================== stride-2 helpers for the tensor-core convolution path
 // parity stack: xp[(ph*2+pw)*N + n, i, j, :] = x[n, 2i+ph, 2j+pw, :]   (space-to-depth by pixel parity, H and W even)
 __global__ void parity_stack_kernel(const float* __restrict__ x, int ldx, float* __restrict__ xp, int N, int H, int W, int C4) {
+  pdl_sync();
   const int H2 = H / 2, W2 = W / 2;
   long long total = (long long)N * H * W * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -690,11 +712,12 @@ RIH_API int rih_parity_stack(const float* x, int ldx, float* xp, int N, int H, i
   RIH_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0 && ldx % 4 == 0, "parity_stack: H, W must be even and C, ld multiples of 4");
   long long total = (long long)N * H * W * (C / 4);
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  parity_stack_kernel<<<grid, 256, 0, s>>>(x, ldx, xp, N, H, W, C / 4);
+  launch_k(parity_stack_kernel, grid, 256, 0, s, x, ldx, xp, N, H, W, C / 4);
   return check_launch("parity_stack");
 }
 // zero insertion: yd[n, 2i, 2j, :] = y[n, i, j, :], 0 elsewhere (yd is [N, 2Ho, 2Wo, C] contiguous)
 __global__ void dilate2x_kernel(const float* __restrict__ y, int ldy, float* __restrict__ yd, int N, int Ho, int Wo, int C4) {
+  pdl_sync();
   const int H = 2 * Ho, W = 2 * Wo;
   long long total = (long long)N * H * W * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -708,13 +731,14 @@ RIH_API int rih_dilate2x(const float* y, int ldy, float* yd, int N, int Ho, int 
   RIH_REQUIRE(C % 4 == 0 && ldy % 4 == 0, "dilate2x: C, ld must be multiples of 4");
   long long total = (long long)N * 4 * Ho * Wo * (C / 4);
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  dilate2x_kernel<<<grid, 256, 0, s>>>(y, ldy, yd, N, Ho, Wo, C / 4);
+  launch_k(dilate2x_kernel, grid, 256, 0, s, y, ldy, yd, N, Ho, Wo, C / 4);
   return check_launch("dilate2x");
 }
 
 // ============================================================== non-overlapping patches (kernel == stride): im2col without blow-up
 // P[(n,gh,gw), (r,s,c)] = x[n, p*gh+r, p*gw+s, c]   -- img_feat_to_grid.proj, models/model_attn/img_attn.py:48,60
 __global__ void patchify_kernel(const float* __restrict__ x, int ldx, float* __restrict__ P, int N, int H, int W, int C4, int p, int scatter) {
+  pdl_sync();
   const int gh_n = H / p, gw_n = W / p;
   long long total = (long long)N * H * W * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -731,7 +755,7 @@ RIH_API int rih_patchify(float* x, int ldx, float* P, int N, int H, int W, int C
   RIH_REQUIRE(p >= 1 && H % p == 0 && W % p == 0 && C % 4 == 0 && ldx % 4 == 0, "patchify: bad geometry");
   long long total = (long long)N * H * W * (C / 4);
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  patchify_kernel<<<grid, 256, 0, s>>>(x, ldx, P, N, H, W, C / 4, p, scatter);
+  launch_k(patchify_kernel, grid, 256, 0, s, x, ldx, P, N, H, W, C / 4, p, scatter);
   return check_launch("patchify");
 }
 
@@ -743,6 +767,7 @@ RIH_API int rih_patchify(float* x, int ldx, float* P, int N, int H, int W, int C
 template <int TR, int TS, int TC>
 __global__ void im2col_kernel(const float* __restrict__ x, int ldx, float* __restrict__ A, int N, int H, int W, int C_, int Ho, int Wo,
                               int R_, int S_, int stride, int pad, int Kpad) {
+  pdl_sync();
   const int R = TR > 0 ? TR : R_, S = TS > 0 ? TS : S_, C = TC > 0 ? TC : C_;
   const long long total = (long long)N * Ho * Wo * Kpad;
   const bool small = total < (1ll << 32);
@@ -765,6 +790,7 @@ __global__ void im2col_kernel(const float* __restrict__ x, int ldx, float* __res
 template <int TR, int TS, int TC>
 __global__ void im2col4_kernel(const float* __restrict__ x, int ldx, float* __restrict__ A, int N, int H, int W, int Ho, int Wo,
                                int stride, int pad, int Kpad4) {
+  pdl_sync();
   constexpr int K = TR * TS * TC, SC = TS * TC;
   const long long total = (long long)N * Ho * Wo * Kpad4;
   const bool small = total < (1ll << 32);
@@ -793,14 +819,14 @@ RIH_API int rih_im2col(const float* x, int ldx, float* A, int N, int H, int W, i
   const long long total = (long long)N * Ho * Wo * Kpad;
   if ((reinterpret_cast<uintptr_t>(A) & 15) == 0 && C == 3 && R == S && (R == 7 || R == 3)) {
     const int g4 = (int)min((long long)148 * 32, (total / 4 + 255) / 256);
-    if (R == 7) im2col4_kernel<7, 7, 3><<<g4, 256, 0, s>>>(x, ldx, A, N, H, W, Ho, Wo, stride, pad, Kpad / 4);
-    else im2col4_kernel<3, 3, 3><<<g4, 256, 0, s>>>(x, ldx, A, N, H, W, Ho, Wo, stride, pad, Kpad / 4);
+    if (R == 7) launch_k(im2col4_kernel<7, 7, 3>, g4, 256, 0, s, x, ldx, A, N, H, W, Ho, Wo, stride, pad, Kpad / 4);
+    else launch_k(im2col4_kernel<3, 3, 3>, g4, 256, 0, s, x, ldx, A, N, H, W, Ho, Wo, stride, pad, Kpad / 4);
     return check_launch("im2col");
   }
   int grid = (int)min((long long)148 * 32, (total + 255) / 256);
-  if (R == 7 && S == 7 && C == 3) im2col_kernel<7, 7, 3><<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
-  else if (R == 3 && S == 3 && C == 3) im2col_kernel<3, 3, 3><<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);   // HRNet stem
-  else im2col_kernel<0, 0, 0><<<grid, 256, 0, s>>>(x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
+  if (R == 7 && S == 7 && C == 3) launch_k(im2col_kernel<7, 7, 3>, grid, 256, 0, s, x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
+  else if (R == 3 && S == 3 && C == 3) launch_k(im2col_kernel<3, 3, 3>, grid, 256, 0, s, x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);   // HRNet stem
+  else launch_k(im2col_kernel<0, 0, 0>, grid, 256, 0, s, x, ldx, A, N, H, W, C, Ho, Wo, R, S, stride, pad, Kpad);
   return check_launch("im2col");
 }
 
@@ -811,6 +837,7 @@ RIH_API int rih_im2col(const float* x, int ldx, float* A, int N, int H, int W, i
 // result is bit-identical to the torch / torchvision ops; the host -> device copy shrinks 4x (uint8 instead of float32).
 __global__ void preprocess_u8_kernel(const unsigned char* __restrict__ src, const unsigned char* __restrict__ flip, float* __restrict__ dst,
                                      int B, int H, int W, float m0, float m1, float m2, float s0, float s1, float s2) {
+  pdl_sync();
   const long long total = (long long)B * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % W); const long long t = i / W; const int y = (int)(t % H); const int b = (int)(t / H);
@@ -830,6 +857,6 @@ RIH_API int rih_preprocess_u8(const unsigned char* src, const unsigned char* fli
   const long long total = (long long)B * H * W;
   if (total == 0) return 0;
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  preprocess_u8_kernel<<<grid, 256, 0, s>>>(src, flip, dst, B, H, W, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1], std3_host[2]);
+  launch_k(preprocess_u8_kernel, grid, 256, 0, s, src, flip, dst, B, H, W, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1], std3_host[2]);
   return check_launch("preprocess_u8");
 }

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(TAIL_THREADS)
 tail_fwd_kernel(TailParams P, const float* __restrict__ Lf, int ldl, int V, int F, int Nv, float img,
                 float* __restrict__ prm_out /*[B,3] raw scale,tx,ty*/, float* __restrict__ temp_out /*[B,F]*/,
                 float* __restrict__ v3c, float* __restrict__ v2c, float* __restrict__ v3, float* __restrict__ v2) {
+  pdl_sync();
   __shared__ float s_temp[TAIL_MAXF];
   __shared__ float s_prm[3];
   __shared__ float s_v3[TAIL_MAXV][3];
@@ -73,7 +74,7 @@ RIH_API int rih_tail_fwd(const float* const* params /*7 ptrs: TailParams order*/
   RIH_REQUIRE(V <= TAIL_MAXV && F <= TAIL_MAXF && Nv <= TAIL_MAXN, "tail_fwd: shape V=%d F=%d Nv=%d exceeds limits", V, F, Nv);
   if (B == 0) return 0;
   TailParams P{params[0], params[1], params[2], params[3], params[4], params[5], params[6]};
-  tail_fwd_kernel<<<B, TAIL_THREADS, 0, s>>>(P, Lf, ldl, V, F, Nv, img, prm, temp, v3c, v2c, v3, v2);
+  launch_k(tail_fwd_kernel, B, TAIL_THREADS, 0, s, P, Lf, ldl, V, F, Nv, img, prm, temp, v3c, v2c, v3, v2);
   return check_launch("tail_fwd");
 }
 
@@ -86,6 +87,7 @@ tail_bwd_kernel(TailParams P, TailGrads G, const float* __restrict__ Lf, int ldl
                 const float* __restrict__ prm, const float* __restrict__ temp, const float* __restrict__ v3c, const float* __restrict__ v3,
                 const float* __restrict__ d_scale, const float* __restrict__ d_trans, const float* __restrict__ d_v3c, const float* __restrict__ d_v2c,
                 const float* __restrict__ d_v3, const float* __restrict__ d_v2, float* __restrict__ dLf, int lddl) {
+  pdl_sync();
   __shared__ float s_gup[TAIL_MAXN][3];
   __shared__ float s_gc[TAIL_MAXV][3];
   __shared__ float s_dtemp[TAIL_MAXF];
@@ -188,13 +190,14 @@ RIH_API int rih_tail_bwd(const float* const* params, float* const* grads /*7 ptr
   if (B == 0) return 0;
   TailParams P{params[0], params[1], params[2], params[3], params[4], params[5], params[6]};
   TailGrads G{grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6]};
-  tail_bwd_kernel<<<B, TAIL_THREADS, 0, s>>>(P, G, Lf, ldl, V, F, Nv, img, prm, temp, v3c, v3, d_scale, d_trans, d_v3c, d_v2c, d_v3, d_v2, dLf, lddl);
+  launch_k(tail_bwd_kernel, B, TAIL_THREADS, 0, s, P, G, Lf, ldl, V, F, Nv, img, prm, temp, v3c, v3, d_scale, d_trans, d_v3c, d_v2c, d_v3, d_v2, dLf, lddl);
   return check_launch("tail_bwd");
 }
 
 // ============================================================== row gather: y[b, i, :] = x[b, idx[i], :]   (GCN_to_vert / vert_to_GCN, graph_upsample p)
 // reference: GCN_vert_convert models/model_zoo/__init__.py:85-96 ; decoder.py:165-172 (graph_upsample(p=4) then GCN_to_vert)
 __global__ void gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ idx, float* __restrict__ y, int B, int Vin, int Vout, int C, int div) {
+  pdl_sync();
   long long total = (long long)B * Vout * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C); long long t = i / C; int v = (int)(t % Vout); int b = (int)(t / Vout);
@@ -202,6 +205,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, const int* __res
   }
 }
 __global__ void scatter_rows_add_kernel(const float* __restrict__ dy, const int* __restrict__ idx, float* __restrict__ dx, int B, int Vin, int Vout, int C, int div) {
+  pdl_sync();
   long long total = (long long)B * Vout * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C); long long t = i / C; int v = (int)(t % Vout); int b = (int)(t / Vout);
@@ -212,7 +216,7 @@ RIH_API int rih_gather_rows(const float* x, const int* idx, float* y, int B, int
   long long total = (long long)B * Vout * C;
   if (total == 0) return 0;
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  gather_rows_kernel<<<grid, 256, 0, s>>>(x, idx, y, B, Vin, Vout, C, div);
+  launch_k(gather_rows_kernel, grid, 256, 0, s, x, idx, y, B, Vin, Vout, C, div);
   return check_launch("gather_rows");
 }
 // dx must be zero-initialised (or hold a gradient to accumulate into)
@@ -220,6 +224,6 @@ RIH_API int rih_scatter_rows_add(const float* dy, const int* idx, float* dx, int
   long long total = (long long)B * Vout * C;
   if (total == 0) return 0;
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  scatter_rows_add_kernel<<<grid, 256, 0, s>>>(dy, idx, dx, B, Vin, Vout, C, div);
+  launch_k(scatter_rows_add_kernel, grid, 256, 0, s, dy, idx, dx, B, Vin, Vout, C, div);
   return check_launch("scatter_rows_add");
 }

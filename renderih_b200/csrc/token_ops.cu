@@ -10,6 +10,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ a, int lda, const
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float* __restrict__ y, int ldy, float* __restrict__ mean, float* __restrict__ rstd,
                                      int M, int F, float eps, int relu) {
+  pdl_sync();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int r = warp; r < M; r += nwarps) {
@@ -33,7 +34,7 @@ RIH_API int rih_layernorm_fwd(const float* a, int lda, const float* b, int ldb, 
                               float* y, int ldy, float* mean, float* rstd, int M, int F, float eps, int relu, cudaStream_t s) {
   if (M == 0) return 0;
   int grid = min(148 * 8, cdiv(M, 8));
-  layernorm_fwd_kernel<<<grid, 256, 0, s>>>(a, lda, b, ldb, gamma, beta, y, ldy, mean, rstd, M, F, eps, relu);
+  launch_k(layernorm_fwd_kernel, grid, 256, 0, s, a, lda, b, ldb, gamma, beta, y, ldy, mean, rstd, M, F, eps, relu);
   return check_launch("layernorm_fwd");
 }
 
@@ -48,6 +49,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __rest
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      float* __restrict__ dx, int lddx, int dx_acc, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      int M, int F, int relu) {
+  pdl_sync();
   constexpr int WARPS = THREADS / 32;
   int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int warp = blockIdx.x * WARPS + warp_in_cta;
@@ -112,7 +114,7 @@ RIH_API int rih_layernorm_bwd(const float* dy, int lddy, const float* a, int lda
   RIH_REQUIRE(F <= 512, "layernorm_bwd: F=%d exceeds 512", F);
   if (M == 0) return 0;
 #define RIH_LN_BWD(MC, TH)                                                                                                        \
-  layernorm_bwd_kernel<MC, TH><<<min(148 * (1024 / TH), cdiv(M, TH / 32)), TH, 0, s>>>(dy, lddy, a, lda, b, ldb, gamma, beta, mean, rstd, dx, lddx, dx_acc, \
+  launch_k(layernorm_bwd_kernel<MC, TH>, min(148 * (1024 / TH), cdiv(M, TH / 32)), TH, 0, s, dy, lddy, a, lda, b, ldb, gamma, beta, mean, rstd, dx, lddx, dx_acc, \
                                                                                       dgamma, dbeta, M, F, relu)
   if (F <= 64) RIH_LN_BWD(2, 1024);
   else if (F <= 128) RIH_LN_BWD(4, 1024);
@@ -126,6 +128,7 @@ RIH_API int rih_layernorm_bwd(const float* dy, int lddy, const float* a, int lda
 // reference: graph_conv_cheby, models/model_attn/gcn.py:34-69 (dense torch.mm(L, x0) at :54 and the Fin x K interleave at :61-63)
 __global__ void cheb_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ rowptr, const int* __restrict__ col,
                                 const float* __restrict__ val, float* __restrict__ out, int B, int V, int F) {
+  pdl_sync();
   long long total = (long long)B * V * F;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F); long long t = i / F; int v = (int)(t % V); int b = (int)(t / V);
@@ -138,6 +141,7 @@ __global__ void cheb_fwd_kernel(const float* __restrict__ x, int ldx, const int*
 // dx[b,v,f] (+)= d[b,v,f,0] + sum_u L[u,v] d[b,u,f,1]   (CSR of L^T passed in)
 __global__ void cheb_bwd_kernel(const float* __restrict__ d, const int* __restrict__ rowptr, const int* __restrict__ col,
                                 const float* __restrict__ val, float* __restrict__ dx, int lddx, int acc_flag, int B, int V, int F) {
+  pdl_sync();
   long long total = (long long)B * V * F;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F); long long t = i / F; int v = (int)(t % V); int b = (int)(t / V);
@@ -151,6 +155,7 @@ __global__ void cheb_bwd_kernel(const float* __restrict__ d, const int* __restri
 // float4 variants (F % 4 == 0): 4 features per thread, 16-byte gathers of the <= 11 neighbours of a vertex
 __global__ void cheb4_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ rowptr, const int* __restrict__ col,
                                  const float* __restrict__ val, float* __restrict__ out, int B, int V, int F4) {
+  pdl_sync();
   const long long total = (long long)B * V * F4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F4); long long t = i / F4; int v = (int)(t % V); int b = (int)(t / V);
@@ -169,6 +174,7 @@ __global__ void cheb4_fwd_kernel(const float* __restrict__ x, int ldx, const int
 }
 __global__ void cheb4_bwd_kernel(const float* __restrict__ d, const int* __restrict__ rowptr, const int* __restrict__ col,
                                  const float* __restrict__ val, float* __restrict__ dx, int lddx, int acc_flag, int B, int V, int F4) {
+  pdl_sync();
   const long long total = (long long)B * V * F4;
   const int F = F4 * 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -193,11 +199,11 @@ RIH_API int rih_cheb_fwd(const float* x, int ldx, const int* rowptr, const int* 
   if (total == 0) return 0;
   if (F % 4 == 0 && ldx % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     int grid = (int)min((long long)148 * 16, (total / 4 + 255) / 256);
-    cheb4_fwd_kernel<<<grid, 256, 0, s>>>(x, ldx, rowptr, col, val, out, B, V, F / 4);
+    launch_k(cheb4_fwd_kernel, grid, 256, 0, s, x, ldx, rowptr, col, val, out, B, V, F / 4);
     return check_launch("cheb_fwd");
   }
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  cheb_fwd_kernel<<<grid, 256, 0, s>>>(x, ldx, rowptr, col, val, out, B, V, F);
+  launch_k(cheb_fwd_kernel, grid, 256, 0, s, x, ldx, rowptr, col, val, out, B, V, F);
   return check_launch("cheb_fwd");
 }
 RIH_API int rih_cheb_bwd(const float* d, const int* rowptrT, const int* colT, const float* valT, float* dx, int lddx, int accumulate,
@@ -206,11 +212,11 @@ RIH_API int rih_cheb_bwd(const float* d, const int* rowptrT, const int* colT, co
   if (total == 0) return 0;
   if (F % 4 == 0 && lddx % 4 == 0 && ((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
     int grid = (int)min((long long)148 * 16, (total / 4 + 255) / 256);
-    cheb4_bwd_kernel<<<grid, 256, 0, s>>>(d, rowptrT, colT, valT, dx, lddx, accumulate, B, V, F / 4);
+    launch_k(cheb4_bwd_kernel, grid, 256, 0, s, d, rowptrT, colT, valT, dx, lddx, accumulate, B, V, F / 4);
     return check_launch("cheb_bwd");
   }
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  cheb_bwd_kernel<<<grid, 256, 0, s>>>(d, rowptrT, colT, valT, dx, lddx, accumulate, B, V, F);
+  launch_k(cheb_bwd_kernel, grid, 256, 0, s, d, rowptrT, colT, valT, dx, lddx, accumulate, B, V, F);
   return check_launch("cheb_bwd");
 }
 
@@ -219,6 +225,7 @@ RIH_API int rih_cheb_bwd(const float* d, const int* rowptrT, const int* colT, co
 //            grid position embeddings, img_attn.py:57-63
 __global__ void posemb_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ emb, float* __restrict__ y, int ldy,
                                   int B, int U, int F, int p) {
+  pdl_sync();
   long long total = (long long)B * U * F;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F); long long t = i / F; int u = (int)(t % U); int b = (int)(t / U);
@@ -227,6 +234,7 @@ __global__ void posemb_fwd_kernel(const float* __restrict__ x, int ldx, const fl
 }
 // dx[b,v,:] = sum_{i<p} dy[b,p*v+i,:]
 __global__ void posemb_bwd_x_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx, int B, int U, int F, int p) {
+  pdl_sync();
   int V = U / p;
   long long total = (long long)B * V * F;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -238,6 +246,7 @@ __global__ void posemb_bwd_x_kernel(const float* __restrict__ dy, int lddy, floa
 }
 // demb[u,:] += sum_b dy[b,u,:]
 __global__ void posemb_bwd_emb_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ demb, int B, int U, int F) {
+  pdl_sync();
   long long total = (long long)U * F;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int f = (int)(i % F); int u = (int)(i / F);
@@ -251,7 +260,7 @@ RIH_API int rih_posemb_fwd(const float* x, int ldx, const float* emb, float* y, 
   long long total = (long long)B * U * F;
   if (total == 0) return 0;
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  posemb_fwd_kernel<<<grid, 256, 0, s>>>(x, ldx, emb, y, ldy, B, U, F, p);
+  launch_k(posemb_fwd_kernel, grid, 256, 0, s, x, ldx, emb, y, ldy, B, U, F, p);
   return check_launch("posemb_fwd");
 }
 RIH_API int rih_posemb_bwd(const float* dy, int lddy, float* dx, int lddx, float* demb, int B, int U, int F, int p, cudaStream_t s) {
@@ -259,13 +268,13 @@ RIH_API int rih_posemb_bwd(const float* dy, int lddy, float* dx, int lddx, float
   if (dx) {
     long long total = (long long)B * (U / p) * F;
     int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-    posemb_bwd_x_kernel<<<grid, 256, 0, s>>>(dy, lddy, dx, lddx, B, U, F, p);
+    launch_k(posemb_bwd_x_kernel, grid, 256, 0, s, dy, lddy, dx, lddx, B, U, F, p);
     if (int e = check_launch("posemb_bwd_x")) return e;
   }
   if (demb) {
     long long total = (long long)U * F;
     int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-    posemb_bwd_emb_kernel<<<grid, 256, 0, s>>>(dy, lddy, demb, B, U, F);
+    launch_k(posemb_bwd_emb_kernel, grid, 256, 0, s, dy, lddy, demb, B, U, F);
     if (int e = check_launch("posemb_bwd_emb")) return e;
   }
   return 0;
@@ -273,6 +282,7 @@ RIH_API int rih_posemb_bwd(const float* dy, int lddy, float* dx, int lddx, float
 
 // ============================================================== column sum: out[n] (+)= sum_m x[m,n]   (bias gradients)
 __global__ void colsum_kernel(const float* __restrict__ x, int ld, int M, int N, int rows_per_cta, float* __restrict__ out) {
+  pdl_sync();
   int c = blockIdx.x * 32 + threadIdx.x;
   int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
   float s = 0.f;
@@ -292,7 +302,7 @@ RIH_API int rih_colsum(const float* x, int ld, int M, int N, float* out, int acc
   int target = cdiv(148 * 4, gx);
   int rows_per_cta = max(32, cdiv(M, target));
   dim3 grid(gx, cdiv(M, rows_per_cta)), block(32, 8);
-  colsum_kernel<<<grid, block, 0, s>>>(x, ld, M, N, rows_per_cta, out);
+  launch_k(colsum_kernel, grid, block, 0, s, x, ld, M, N, rows_per_cta, out);
   return check_launch("colsum");
 }
 
@@ -300,6 +310,7 @@ RIH_API int rih_colsum(const float* x, int ld, int M, int N, float* out, int acc
 // mask index = row*C + col over the logical [rows, C] tensor; seed = *seed_ptr + site*const  (same map as the GEMM epilogue)
 __global__ void dropout_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, long long rows, int C,
                                const unsigned long long* __restrict__ seed_ptr, unsigned long long site, uint32_t thresh, float inv_keep) {
+  pdl_sync();
   long long total = rows * C;
   unsigned long long seed = *seed_ptr + site * 0xD1B54A32D192ED03ull;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -313,7 +324,7 @@ RIH_API int rih_dropout(const float* x, int ldx, float* y, int ldy, long long ro
   if (rows * C == 0) return 0;
   RIH_REQUIRE(p > 0.f && p < 1.f && seed_ptr, "dropout: p out of range or missing seed");
   int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
-  dropout_kernel<<<grid, 256, 0, s>>>(x, ldx, y, ldy, rows, C, seed_ptr, site, dropout_thresh(p), 1.f / (1.f - p));
+  launch_k(dropout_kernel, grid, 256, 0, s, x, ldx, y, ldy, rows, C, seed_ptr, site, dropout_thresh(p), 1.f / (1.f - p));
   return check_launch("dropout");
 }
 // backward pre-pass of a fused GEMM epilogue  y = dropout(relu(z)) (+res):  g = dy * keep_scale * (y_pre_res > 0 if relu)
@@ -321,6 +332,7 @@ RIH_API int rih_dropout(const float* x, int ldx, float* y, int ldy, long long ro
 __global__ void epilogue_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, float* __restrict__ g, int ldg,
                                     long long rows, int C, int relu, const unsigned long long* __restrict__ seed_ptr, unsigned long long site,
                                     uint32_t thresh, float inv_keep) {
+  pdl_sync();
   long long total = rows * C;
   unsigned long long seed = thresh ? (*seed_ptr + site * 0xD1B54A32D192ED03ull) : 0ull;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -336,13 +348,14 @@ RIH_API int rih_epilogue_bwd(const float* dy, int lddy, const float* y, int ldy,
   if (rows * C == 0) return 0;
   RIH_REQUIRE(dropout_p == 0.f || (seed_ptr && dropout_p < 1.f), "epilogue_bwd: dropout needs a device seed");
   int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
-  epilogue_bwd_kernel<<<grid, 256, 0, s>>>(dy, lddy, y, ldy, g, ldg, rows, C, relu, seed_ptr, site,
+  launch_k(epilogue_bwd_kernel, grid, 256, 0, s, dy, lddy, y, ldy, g, ldg, rows, C, relu, seed_ptr, site,
                                            dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u, dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f);
   return check_launch("epilogue_bwd");
 }
-__global__ void seed_advance_kernel(unsigned long long* seed) { *seed = *seed * 6364136223846793005ull + 1442695040888963407ull; }
+__global__ void seed_advance_kernel(unsigned long long* seed) {
+  pdl_sync(); *seed = *seed * 6364136223846793005ull + 1442695040888963407ull; }
 RIH_API int rih_seed_advance(unsigned long long* seed_ptr, cudaStream_t s) {
-  seed_advance_kernel<<<1, 1, 0, s>>>(seed_ptr);
+  launch_k(seed_advance_kernel, 1, 1, 0, s, seed_ptr);
   return check_launch("seed_advance");
 }
 
@@ -350,6 +363,7 @@ RIH_API int rih_seed_advance(unsigned long long* seed_ptr, cudaStream_t s) {
 // reference: models/decoder.py:132-135 (repeat + cat) fused with the level-0 position-embedding add (DualGraph.py:76-80)
 __global__ void gf_broadcast_fwd_kernel(const float* __restrict__ g, const float* __restrict__ pe, const float* __restrict__ emb,
                                         float* __restrict__ y, int B, int V, int G) {
+  pdl_sync();
   int F = G + 3;
   long long total = (long long)B * V * F;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -360,6 +374,7 @@ __global__ void gf_broadcast_fwd_kernel(const float* __restrict__ g, const float
 }
 // dg[b,f] = sum_v dy[b,v,f] (f<G) ; demb[v,f] += sum_b dy[b,v,f]
 __global__ void gf_broadcast_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dg, int B, int V, int G) {
+  pdl_sync();
   int F = G + 3;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * G) return;
@@ -371,16 +386,16 @@ __global__ void gf_broadcast_bwd_kernel(const float* __restrict__ dy, float* __r
 RIH_API int rih_gf_broadcast_fwd(const float* g, const float* pe, const float* emb, float* y, int B, int V, int G, cudaStream_t s) {
   long long total = (long long)B * V * (G + 3);
   int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-  gf_broadcast_fwd_kernel<<<grid, 256, 0, s>>>(g, pe, emb, y, B, V, G);
+  launch_k(gf_broadcast_fwd_kernel, grid, 256, 0, s, g, pe, emb, y, B, V, G);
   return check_launch("gf_broadcast_fwd");
 }
 RIH_API int rih_gf_broadcast_bwd(const float* dy, float* dg, float* demb, int B, int V, int G, cudaStream_t s) {
-  gf_broadcast_bwd_kernel<<<cdiv((long long)B * G, 256), 256, 0, s>>>(dy, dg, B, V, G);
+  launch_k(gf_broadcast_bwd_kernel, cdiv((long long)B * G, 256), 256, 0, s, dy, dg, B, V, G);
   if (int e = check_launch("gf_broadcast_bwd")) return e;
   if (demb) {
     long long total = (long long)V * (G + 3);
     int grid = (int)min((long long)148 * 16, (total + 255) / 256);
-    posemb_bwd_emb_kernel<<<grid, 256, 0, s>>>(dy, G + 3, demb, B, V, G + 3);
+    launch_k(posemb_bwd_emb_kernel, grid, 256, 0, s, dy, G + 3, demb, B, V, G + 3);
     if (int e = check_launch("gf_broadcast_bwd_emb")) return e;
   }
   return 0;
@@ -389,6 +404,7 @@ RIH_API int rih_gf_broadcast_bwd(const float* dy, float* dg, float* demb, int B,
 // ============================================================== fused AdamW over a flat fp32 buffer (torch.optim.AdamW semantics)
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float gi = g[i] * gscale;
     float pi = p[i] * (1.f - lr * wd);
@@ -407,6 +423,6 @@ RIH_API int rih_adamw_step(float* p, const float* g, float* m, float* v, long lo
   float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
   int grid = (int)min((long long)148 * 16, (n + 255) / 256);
-  adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  launch_k(adamw_kernel, grid, 256, 0, s, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
   return check_launch("adamw");
 }
