@@ -83,7 +83,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int wg = 0) { asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory"); }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -141,9 +141,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // hi = value rounded to TF32 and lo = value - hi (exact in fp32), and D += hi*hi + lo*hi + hi*lo  (fp32-faithful).
 template <int BN, int NSPLIT> __host__ __device__ constexpr int stage_bytes() { return (BM * 128 + BN * 128) * (NSPLIT == 3 ? 2 : 1); }
 template <int BN, int NSPLIT> __host__ __device__ constexpr int num_stages() { return (BN >= 256 && NSPLIT == 3) ? 2 : (BN >= 128 ? 3 : 4); }
-constexpr int EPI_STAGING_BYTES = 2 * BM * 128;   // two [128 x 32 fp32] staging tiles for the TMA-store epilogue
+constexpr int EPI_STAGING_BYTES = 2 * BM * 128;   // two [128 x 32 fp32] staging tiles for the TMA-store epilogue (per epilogue warpgroup)
+// Epilogue warpgroups of the persistent kernel.  The single-pass TF32 kernels (NSPLIT = 1) have no splitter warps and room in shared memory, so
+// they run TWO epilogue warpgroups that take alternate 32-column chunks of the accumulator (each with its own pair of staging tiles, its own
+// named barrier and its own TMA-store bulk groups): the store-bound 1x1 convolutions (K = 64 ... 256, 128 KB of output per 128 x 256 tile)
+// were limited by the serial tcgen05.ld -> st.shared -> barrier -> TMA-store chain of one warpgroup (3.6 TB/s of 6.5).
+template <int NSPLIT> __host__ __device__ constexpr int epi_wgs() { return NSPLIT == 1 ? 2 : 1; }
 template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() {
-  return num_stages<BN, NSPLIT>() * stage_bytes<BN, NSPLIT>() + EPI_STAGING_BYTES + 1024 + 256;
+  return num_stages<BN, NSPLIT>() * stage_bytes<BN, NSPLIT>() + EPI_STAGING_BYTES * epi_wgs<NSPLIT>() + 1024 + 256;
 }
 
 // ---------------------------------------------------------------- producers (TMA issue logic, one elected lane)
@@ -459,7 +464,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 //   last 4 warps = epilogue (TMEM -> registers -> swizzled smem -> TMA store / reduce-add)
 constexpr int SPLIT_WARPS = 8;   // hi/lo splitter warps of the persistent kernel (NSPLIT >= 2): the split pass (32-48 KB of shared memory per k-block) is what
                                  // bounds the many small, latency-bound 3xTF32 GEMMs of the decoder -- 8 warps halve it against the original 4
-template <int NSPLIT> __host__ __device__ constexpr int persistent_threads() { return NSPLIT >= 2 ? (2 + SPLIT_WARPS + 4) * 32 : 192; }
+template <int NSPLIT> __host__ __device__ constexpr int persistent_threads() { return NSPLIT >= 2 ? (2 + SPLIT_WARPS + 4) * 32 : (2 + 4 * epi_wgs<NSPLIT>()) * 32; }
 
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
 __global__ void __launch_bounds__(persistent_threads<NSPLIT>())
@@ -470,11 +475,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   constexpr int STAGE_BYTES = stage_bytes<BN, NSPLIT>();
   constexpr uint32_t IDESC = make_idesc_tf32(BN, A_MN, B_MN);
   constexpr int EPI_WARP0 = (NSPLIT >= 2) ? 2 + SPLIT_WARPS : 2;
+  constexpr int EPI_WG = epi_wgs<NSPLIT>();
   constexpr uint32_t TMEM_COLS = 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_STAGING_BYTES * EPI_WG);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* ready = bars + 2 * STAGES;
@@ -491,7 +497,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     tma_prefetch_desc(&tmap_b);
     if (tma_epi) tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], SPLIT_WARPS * 32); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128 * EPI_WG); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -595,10 +601,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       }
     }
   } else if (warp >= EPI_WARP0) {
-    const int q = warp & 3;
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read (warp index modulo 4)
+    const int wg = (warp - EPI_WARP0) >> 2;         // epilogue warpgroup: takes the chunks c with c % EPI_WG == wg
     const int rr = q * 32 + lane;
-    const bool elected = (threadIdx.x == EPI_WARP0 * 32);
+    const bool elected = (threadIdx.x == (EPI_WARP0 + 4 * wg) * 32);
+    uint8_t* const wg_staging = staging + wg * EPI_STAGING_BYTES;
     const unsigned long long dseed = ep.thresh ? (*ep.seed_ptr + ep.site * 0xD1B54A32D192ED03ull) : 0ull;
+    constexpr int NCHUNK = BN / 32;
+    const int last_c = ((NCHUNK - 1 - wg) / EPI_WG) * EPI_WG + wg;    // last chunk of this warpgroup
     uint32_t tc = 0, cc = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
       int m0, n0, kb_beg, nkb, z;
@@ -608,10 +618,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       tc_fence_after();
       const int m = m0 + rr;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = wg; c < NCHUNK; c += EPI_WG) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-        if (c == BN / 32 - 1) {        // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+        if (c == last_c) {             // all TMEM reads of this accumulator by this thread are done: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&tmem_empty[acc]);
         }
@@ -641,14 +651,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           }
           if (cc >= 2) {
             if (elected) tma_store_wait_read<1>();
-            epi_bar_sync();
+            epi_bar_sync(wg);
           }
-          uint8_t* buf = staging + (cc & 1) * (BM * 128);
+          uint8_t* buf = wg_staging + (cc & 1) * (BM * 128);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(buf + rr * 128 + ((j ^ (rr & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           fence_proxy_async();
-          epi_bar_sync();
+          epi_bar_sync(wg);
           if (elected) {
             if (batched) {
               const int hh = ep.batch_heads & 0x3FFFFFFF;

@@ -197,6 +197,9 @@ class ResNetSimple(nn.Module):
         for layer in (r.layer1, r.layer2, r.layer3, r.layer4):
             for blk in layer:
                 x, H = self._bottleneck(blk, x, N, H) if self.expansion == 4 else self._basic(blk, x, N, H)
+            # this layer's output gradient is complete exactly when every later layer / head has been back-propagated (train.TrainStep
+            # starts the gradient all-reduce of those parameters then)
+            ops.backward_marker(x, 'encoder.resnet.layer%d' % (len(feats) + 1))
             feats.append((x, H))
         x4, x3, x2, x1 = feats
         return [x1, x2, x3, x4]
@@ -286,6 +289,7 @@ def run_hands(device, fn_left, fn_right):
     outs = []
     for s, fn in zip(st, (fn_left, fn_right)):
         s.wait_stream(main)
+        ops.note_stream(s)
         with torch.cuda.stream(s):
             outs.append(fn())
     for s, o in zip(st, outs):
@@ -319,6 +323,7 @@ def start_side(device, which, fn):
         return ('deferred', fn)
     s = st[which]
     s.wait_stream(torch.cuda.current_stream(device))
+    ops.note_stream(s)
     with torch.cuda.stream(s):
         out = fn()
         ev = torch.cuda.Event()
@@ -810,6 +815,7 @@ class HandNET_GCN(nn.Module):
         global_feature = ops.global_avgpool(x1, N, H1 * H1)
         main = torch.cuda.current_stream(dev)
         aux.wait_stream(main)
+        ops.note_stream(aux)
         fmaps, events = [], []
         with torch.cuda.stream(aux):
             xh, xd, H = x1, x1, H1

@@ -112,6 +112,7 @@ def _wgrad_fork(*tensors):
         st = torch.cuda.Stream(device=cur.device)
         _WG['streams'][key] = st
     st.wait_stream(cur)
+    note_stream(st)
     _WG.setdefault('dirty', set()).add(key)
     for t in tensors:
         if t is not None:
@@ -129,6 +130,29 @@ def _wgrad_join():
     dirty, _WG['dirty'] = _WG.get('dirty', set()), set()
     for key in dirty:
         torch.cuda.current_stream(key[0]).wait_stream(_WG['streams'][key])
+
+
+# ----------------------------------------------------------------------------- backward-progress markers / streams of the current step
+# The model marks tensors whose gradient completes a backward segment (e.g. a ResNet layer's output: its gradient is ready exactly when
+# everything downstream has been back-propagated).  train.TrainStep installs a callback and starts the gradient all-reduce of the finished
+# segment's parameters on a communication stream while the rest of backward runs.
+MARKER_CALLBACK = [None]
+STEP_STREAMS = {}          # cuda_stream handle -> torch stream: every side stream the current step has forked work onto
+
+
+def note_stream(st):
+    STEP_STREAMS[st.cuda_stream] = st
+
+
+def backward_marker(t, name):
+    if t.requires_grad and MARKER_CALLBACK[0] is not None:
+        def hook(grad, name=name):
+            cb = MARKER_CALLBACK[0]
+            if cb is not None:
+                cb(name)
+            return None
+        t.register_hook(hook)
+    return t
 
 
 # ----------------------------------------------------------------------------- dropout seed (device resident)
@@ -154,6 +178,7 @@ class _SeedState:
 
     def begin_forward(self):
         self.site = 0
+        STEP_STREAMS.clear()
         _WG['armed'] = False      # a backward pass that raised may have left the join callback un-run
         _WG['dirty'] = set()
 

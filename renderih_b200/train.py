@@ -206,10 +206,70 @@ class TrainStep:
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         except Exception:
             pass
+        self._setup_overlap()
         self.static_img = example_img.clone()
         self.graph = None
         self.loss = None
         self.use_graph = use_graph
+
+    # ---- gradient all-reduce overlapped with backward (DDP's bucketed reducer does this in the reference, core/lijun_trainer.py:122-127)
+    def _setup_overlap(self):
+        """Split the flat gradient into segments that finish one after the other during backward and all-reduce each on a communication
+        stream as soon as it is complete, instead of one exposed 155 MB all-reduce after backward.  Segments follow the model's backward
+        markers (ops.backward_marker): [everything after the ResNet trunk: aux decoders, mid, token decoder] -> layer4 -> layer3 -> the rest.
+        Models without markers (HRNet, ...) fall back to one all-reduce at the end of backward (still inside the captured step).
+        `RIH_OVERLAP_ALLREDUCE=0` restores the single all-reduce issued after the graph replay."""
+        import os
+        self.overlap = self.world > 1 and os.environ.get('RIH_OVERLAP_ALLREDUCE', '1') != '0'
+        self._segments, self._comm = {}, None
+        if not self.overlap:
+            return
+        self._comm = torch.cuda.Stream(device=self.flatp.flat.device)
+        names = {id(p): k for k, p in self.model.named_parameters()}
+        first = {}                      # prefix -> first offset of a parameter with that prefix in the flat buffer
+        for p, off in zip(self.flatp.params, self.flatp.offsets):
+            k = names.get(id(p), '')
+            for pre in ('encoder.resnet.layer3.', 'encoder.resnet.layer4.'):
+                if k.startswith(pre):
+                    first[pre] = min(first.get(pre, off), off)
+            if not k.startswith('encoder.resnet.'):
+                first['rest'] = min(first.get('rest', off), off)
+        n = self.flatp.numel
+        if all(k in first for k in ('encoder.resnet.layer3.', 'encoder.resnet.layer4.', 'rest')) and \
+                first['encoder.resnet.layer3.'] < first['encoder.resnet.layer4.'] < first['rest']:
+            l3, l4, rest = first['encoder.resnet.layer3.'], first['encoder.resnet.layer4.'], first['rest']
+            # marker name -> (lo, hi): the gradient of layer k's OUTPUT is complete when everything after layer k has been back-propagated
+            self._segments = {'encoder.resnet.layer4': (rest, n), 'encoder.resnet.layer3': (l4, rest), 'encoder.resnet.layer2': (l3, l4)}
+        self._pending = None
+
+    def _reduce_range(self, lo, hi):
+        """All-reduce grad[lo:hi] on the communication stream, ordered after every stream of the step that may still be writing into it."""
+        if hi <= lo:
+            return
+        dev = self.flatp.flat.device
+        self._comm.wait_stream(torch.cuda.current_stream(dev))
+        for st in list(ops.STEP_STREAMS.values()):
+            self._comm.wait_stream(st)
+        with torch.cuda.stream(self._comm):
+            dist.all_reduce(self.flatp.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+
+    def _on_marker(self, name):
+        seg = self._segments.get(name)
+        if seg is None or self._pending is None or name in self._pending['done']:
+            return
+        self._pending['done'].add(name)
+        self._pending['ranges'].append(seg)
+        self._reduce_range(*seg)
+
+    def _finish_reduce(self):
+        """After backward: all-reduce whatever no marker covered (layer1-2 + stem, or everything), then join the communication stream."""
+        done = sorted(self._pending['ranges'])
+        lo = 0
+        for a, b in done + [(self.flatp.numel, self.flatp.numel)]:
+            self._reduce_range(lo, a)
+            lo = max(lo, b)
+        torch.cuda.current_stream(self.flatp.flat.device).wait_stream(self._comm)
+        self._pending = None
 
     def _optim_index(self):
         train = [p for p in self.model.parameters() if p.requires_grad]
@@ -233,24 +293,34 @@ class TrainStep:
         self.lr = lr_at_epoch(epoch, getattr(self, 'base_lr', self.lr), **kw)
         return self.lr
 
-    def _step_body(self):
+    def _step_body(self, reduce=True):
         self.flatp.zero_grad()
-        out = self.model(self.static_img)
-        loss = self.loss_fn(out)
-        loss.backward()
+        do_overlap = self.overlap and reduce and not getattr(self, 'skip_all_reduce', False)
+        if do_overlap:
+            self._pending = {'done': set(), 'ranges': []}
+            ops.MARKER_CALLBACK[0] = self._on_marker
+        try:
+            out = self.model(self.static_img)
+            loss = self.loss_fn(out)
+            loss.backward()
+            if do_overlap:
+                self._finish_reduce()
+        finally:
+            ops.MARKER_CALLBACK[0] = None
         return loss.detach()
 
     def _eager_no_opt(self):
         """Forward + loss + backward, eager, no collective and no optimizer step (measurement passes: parameters stay where they are)."""
-        return self._step_body()
+        return self._step_body(reduce=False)
 
     def _eager(self):
         loss = self._step_body()
-        self.flatp.all_reduce(self.group)
+        if not self.overlap:
+            self.flatp.all_reduce(self.group)
         self.flatp.adamw_step(self.lr, weight_decay=self.wd, grad_scale=1.0 / self.world)
         return loss
 
-    def capture(self, warmup=3):
+    def capture(self, warmup=3, reduce=True):
         """Warm up forward+backward on a side stream, then capture them into one CUDA graph; the NCCL all-reduce and the fused AdamW
         kernel run after each replay on the same stream.  Neither the warm-up passes nor the capture pass (which executes nothing, but
         the warm-up does) leave a trace: parameters, Adam moments, step count, BatchNorm running statistics and the dropout seed are
@@ -260,12 +330,12 @@ class TrainStep:
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(warmup):
-                    self._step_body()          # forward + backward only: no optimizer step, no collective
+                    self._step_body(reduce)    # forward + backward (+ the overlapped gradient all-reduce when world > 1): no optimizer step
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.loss = self._step_body()
+                self.loss = self._step_body(reduce)
         return self
 
     def prefetch(self, img_host, labels_host=None):
@@ -304,7 +374,7 @@ class TrainStep:
         if self.graph is None:
             return self._eager()
         self.graph.replay()
-        if not getattr(self, 'skip_all_reduce', False):      # measurement switch (bench.py: exposed communication = step time with - without)
+        if not self.overlap and not getattr(self, 'skip_all_reduce', False):   # overlapped mode: the all-reduce segments are inside the captured step
             self.flatp.all_reduce(self.group)
         self.flatp.adamw_step(self.lr, weight_decay=self.wd, grad_scale=1.0 / self.world)
         return self.loss
