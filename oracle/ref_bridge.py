@@ -170,6 +170,7 @@ def import_reference():
 
         def make(orig):
             def f(pretrained=False, **kw):
+                kw.pop('weights', None)         # the product's own containers call resnetXX(weights=None) through the same (patched) symbol
                 return orig(weights=None, **kw)
             f._rih_patched = True
             return f

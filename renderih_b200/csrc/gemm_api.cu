@@ -11,6 +11,7 @@ int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long
               int allow_splitk, cudaStream_t s);
 bool conv_tc_supported(const ConvGeom& g, int which);
 void set_nsplit(int n);
+void set_narrow_small(int on);
 int set_stream_cta_limit(cudaStream_t s, int ctas);
 void set_acc_scale(float s);
 extern int g_stats_fused;
@@ -42,6 +43,9 @@ RIH_API int rih_set_stream_cta_limit(cudaStream_t stream, int ctas) {
   RIH_REQUIRE(tc::set_stream_cta_limit(stream, ctas) == 0, "set_stream_cta_limit: more than 4 capped streams");
   return 0;
 }
+// 1 (default) = GEMMs whose 128-wide tiling would occupy at most half of the SMs use 64-wide N tiles (twice the CTAs, half the serial work
+// per CTA); 0 = always the widest tile.  Scheduling only: results are unchanged.
+RIH_API int rih_set_narrow_tiles(int on) { tc::set_narrow_small(on); return 0; }
 static inline bool use_tc(int which) {
   if (g_mode[which] == 0) return false;
   tc::set_nsplit(g_mode[which] == 2 ? 3 : (g_mode[which] == 3 ? 2 : 1));

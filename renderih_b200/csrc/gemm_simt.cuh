@@ -167,6 +167,8 @@ struct Epilogue {
   double* stats;                               // optional [2*N] column sum / sum of squares of the stored values (fused BatchNorm statistics)
   int batch_heads;                             // > 0: batched (attention) GEMM on the tensor-core path -- tile batch z addresses the operands / output as
                                                // 4-D tensors; token matrices use (head, batch) = (z % batch_heads, z / batch_heads), score matrices (z, 0); bit 30 set = output is a score matrix
+  int reverse;                                 // tensor-core persistent kernel: walk the output tiles from the last to the first (see rih_set_traversal)
+  unsigned long long a_policy;                 // tensor-core path: L2 eviction-priority policy for the A-operand TMA loads (0 = none)
   int nv_pad, nv_real;                         // tensor-core wgrad with Cin % BN != 0: column n of the (virtual) tile grid is (tap = n / nv_pad, c = n % nv_pad), stored iff c < nv_real
   __device__ __forceinline__ void store4(int m, int n, float4 v) const {
     if (m >= M || n >= N) return;
@@ -189,7 +191,7 @@ struct Epilogue {
 };
 static inline Epilogue make_epilogue(float* c, int ldc, int M, int N, const float* bias, int relu, int mode) {
   Epilogue e; e.c = c; e.ldc = ldc; e.M = M; e.N = N; e.bias = bias; e.relu = relu; e.mode = mode;
-  e.res = nullptr; e.ldres = 0; e.seed_ptr = nullptr; e.site = 0; e.thresh = 0; e.inv_keep = 1.f; e.stats = nullptr; e.scale = 1.f; e.nv_pad = 0; e.nv_real = 0; e.batch_heads = 0;
+  e.res = nullptr; e.ldres = 0; e.seed_ptr = nullptr; e.site = 0; e.thresh = 0; e.inv_keep = 1.f; e.stats = nullptr; e.scale = 1.f; e.nv_pad = 0; e.nv_real = 0; e.batch_heads = 0; e.reverse = 0; e.a_policy = 0ull;
   return e;
 }
 

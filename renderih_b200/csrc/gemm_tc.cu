@@ -80,6 +80,8 @@ int make_tmap_wgrad_out(CUtensorMap* map, const float* base, int Cout, int taps,
 int g_stats_fused = 0;            // set by the launcher when the epilogue accumulated ep.stats (fused BatchNorm statistics)
 static int g_wide_tiles = 1;     // 128 x 256 output tiles when N % 256 == 0
 void set_wide_tiles(int on) { g_wide_tiles = on ? 1 : 0; }
+static int g_narrow_small = 1;   // 64-wide N tiles for GEMMs whose 128-wide tiling would leave half of the SMs idle (RIH_NARROW_TILES=0 to compare)
+void set_narrow_small(int on) { g_narrow_small = on ? 1 : 0; }
 static int g_persistent = 1;     // 0 = one CTA per tile (non-persistent kernel; debug / comparison)
 void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
@@ -154,6 +156,8 @@ template <int BN, bool A_MN, bool B_MN, class Producer>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep, const Producer& prod, int M, int N, int num_kb, int splits,
                       int kb_per_split, cudaStream_t s, const CUtensorMap* c_map = nullptr) {
   ep.scale = g_scale;
+  ep.reverse = g_reverse;
+  ep.a_policy = g_l2_hints ? 1ull : 0ull;
   if (g_nsplit == 3) return launch_one<BN, A_MN, B_MN, Producer, 3>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s, c_map);
   if (g_nsplit == 2 && g_persistent) return launch_one<BN, A_MN, B_MN, Producer, 2>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s, c_map);
   return launch_one<BN, A_MN, B_MN, Producer, 1>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s, c_map);
@@ -191,13 +195,17 @@ int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long
   int BN = (N > 64) ? 128 : 64;
   // 128 x 256 tiles (full 512 TMEM columns with double buffering) when N allows: each A tile is fetched once per 256 columns
   if (g_persistent && g_wide_tiles && N % 256 == 0 && (long long)cdiv(M, BM) * (N / 256) >= 120) BN = 256;
+  // Latency-bound GEMMs of the token decoder (a few dozen 128-row tiles, K <= 512): when 128-wide tiles would occupy at most half of the SMs,
+  // 64-wide tiles put twice as many CTAs to work -- each splits / multiplies half the B tile and drains half the accumulator, which is what a
+  // single-tile-per-CTA dependent chain (TMA -> split -> MMA -> epilogue) is made of.
+  if (BN == 128 && g_persistent && g_narrow_small && (long long)cdiv(M, BM) * cdiv(N, 128) <= 74) BN = 64;
   if (a_mn ? make_tmap_2d(&ta, a, K, M, lda, 32, true) : make_tmap_2d(&ta, a, M, K, lda, BM)) return 1;
   if (b_mn ? make_tmap_2d(&tb, b, K, N, ldb, 32, true) : make_tmap_2d(&tb, b, N, K, ldb, BN)) return 1;
   int num_kb = cdiv(K, BK), splits, kps;
   plan_splitk(ep, M, N, BN, num_kb, allow_splitk, splits, kps, s);
 #define RIH_TC_CASE(bn, am, bm)                                                              \
   if (BN == bn && a_mn == am && b_mn == bm) {                                                \
-    DenseProducer<bn, am != 0, bm != 0> prod{0};                                             \
+    DenseProducer<bn, am != 0, bm != 0> prod{0, 0ull};                                             \
     return launch_cfg<bn, am != 0, bm != 0>(ta, tb, ep, prod, M, N, num_kb, splits, kps, s); \
   }
   RIH_TC_CASE(256, 0, 0) RIH_TC_CASE(256, 0, 1) RIH_TC_CASE(256, 1, 1)
@@ -307,9 +315,9 @@ int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g
   if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, BN)) return 1;
   ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, g.stride == 2 ? g.N : 0, g.Cin};
   const int num_kb = g.R * g.S * cdiv(g.Cin, BK);
-  if (BN == 256) { ConvFwdProducer<256> p{cg}; return launch_cfg<256, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
-  if (BN == 128) { ConvFwdProducer<128> p{cg}; return launch_cfg<128, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
-  ConvFwdProducer<64> p{cg};
+  if (BN == 256) { ConvFwdProducer<256> p{cg, 0ull}; return launch_cfg<256, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
+  if (BN == 128) { ConvFwdProducer<128> p{cg, 0ull}; return launch_cfg<128, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
+  ConvFwdProducer<64> p{cg, 0ull};
   return launch_cfg<64, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s);
 }
 

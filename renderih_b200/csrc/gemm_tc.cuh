@@ -52,6 +52,25 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// L2 eviction-priority hints for streamed operands: an activation tile a GEMM reads once should not push the output of the previous
+// kernel (which the next kernel is about to read) out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_hint(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -140,13 +159,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // rounded to nearest in shared memory first (unbiased, what cuDNN/cuBLAS TF32 do).  NSPLIT = 3: error-compensated "3xTF32": every operand tile is split in shared memory into
 // hi = value rounded to TF32 and lo = value - hi (exact in fp32), and D += hi*hi + lo*hi + hi*lo  (fp32-faithful).
 template <int BN, int NSPLIT> __host__ __device__ constexpr int stage_bytes() { return (BM * 128 + BN * 128) * (NSPLIT == 3 ? 2 : 1); }
-template <int BN, int NSPLIT> __host__ __device__ constexpr int num_stages() { return (BN >= 256 && NSPLIT == 3) ? 2 : (BN >= 128 ? 3 : 4); }
+// Build-time tuning knobs (A/B variants of the library are built by renderih_b200/_build.build_variant):
+//   RIH_EPI_WGS   epilogue warpgroups of the single-pass TF32 persistent kernels (default 2)
+//   RIH_DEEP      1 = as many shared-memory stages as fit next to the staging tiles for the single-pass TF32 kernels
+#ifndef RIH_EPI_WGS
+#define RIH_EPI_WGS 2
+#endif
+#ifndef RIH_DEEP
+#define RIH_DEEP 0
+#endif
+template <int BN, int NSPLIT> __host__ __device__ constexpr int num_stages() {
+  if (NSPLIT == 1 && RIH_DEEP) {
+    // 227 KB per CTA - staging (32 KB per epilogue warpgroup) - barriers, in units of one stage (24 / 32 / 48 KB for BN = 64 / 128 / 256)
+    return (227 * 1024 - 32 * 1024 * RIH_EPI_WGS - 2048) / ((BM + BN) * 128);
+  }
+  return (BN >= 256 && NSPLIT == 3) ? 2 : (BN >= 128 ? 3 : 4);
+}
 constexpr int EPI_STAGING_BYTES = 2 * BM * 128;   // two [128 x 32 fp32] staging tiles for the TMA-store epilogue (per epilogue warpgroup)
 // Epilogue warpgroups of the persistent kernel.  The single-pass TF32 kernels (NSPLIT = 1) have no splitter warps and room in shared memory, so
 // they run TWO epilogue warpgroups that take alternate 32-column chunks of the accumulator (each with its own pair of staging tiles, its own
 // named barrier and its own TMA-store bulk groups): the store-bound 1x1 convolutions (K = 64 ... 256, 128 KB of output per 128 x 256 tile)
 // were limited by the serial tcgen05.ld -> st.shared -> barrier -> TMA-store chain of one warpgroup (3.6 TB/s of 6.5).
-template <int NSPLIT> __host__ __device__ constexpr int epi_wgs() { return NSPLIT == 1 ? 2 : 1; }
+template <int NSPLIT> __host__ __device__ constexpr int epi_wgs() { return NSPLIT == 1 ? RIH_EPI_WGS : 1; }
 template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() {
   return num_stages<BN, NSPLIT>() * stage_bytes<BN, NSPLIT>() + EPI_STAGING_BYTES * epi_wgs<NSPLIT>() + 1024 + 256;
 }
@@ -157,9 +191,11 @@ template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() {
 template <int BN, bool A_MN, bool B_MN>
 struct DenseProducer {
   int kbeg;
+  unsigned long long a_policy;   // 0 = no hint
+  __device__ __forceinline__ void set_policy(unsigned long long p) { a_policy = p; }
   __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
     const int k0 = kb * BK;
-    if constexpr (!A_MN) tma_load_2d(sa, ta, k0, m0, bar);
+    if constexpr (!A_MN) { if (a_policy) tma_load_2d_hint(sa, ta, k0, m0, bar, a_policy); else tma_load_2d(sa, ta, k0, m0, bar); }
     else {
 #pragma unroll
       for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, k0, bar);
@@ -179,6 +215,7 @@ struct DenseProducer {
 // head, because head and batch are separate tensor dimensions), so Sq = 63 ... 316 and d = 16 need no padding copies.
 template <int BN, bool A_MN, bool B_MN>
 struct BatchedProducer {
+  __device__ __forceinline__ void set_policy(unsigned long long) {}
   int H;          // heads per batch image
   int a_tok, b_tok;   // operand is a token matrix (1) or a score matrix (0)
   // token matrix map dims {d, H, S, B} (strides ascending), score matrix map dims {C, R, B*H, 1}
@@ -219,6 +256,8 @@ __device__ __forceinline__ void s2_tap(int r, int pad, int& parity, int& shift) 
 template <int BN>
 struct ConvFwdProducer {
   ConvTcGeom g;
+  unsigned long long a_policy;
+  __device__ __forceinline__ void set_policy(unsigned long long p) { a_policy = p; }
   __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
     // channel blocks per tap; when Cin % 32 != 0 the last block of a tap is partly out of bounds in the activation map (TMA zero
     // fill), which also cancels whatever the weight box picks up from the next tap's columns
@@ -232,6 +271,8 @@ struct ConvFwdProducer {
       s2_tap(r, g.pad, ph, dh);
       s2_tap(s, g.pad, pw, dw_);
       tma_load_4d(sa, ta, c0, dw_, oh0 + dh, (ph * 2 + pw) * g.s2_images + n, bar);
+    } else if (a_policy && g.R == 1) {
+      tma_load_4d_hint(sa, ta, c0, s - g.pad, oh0 + r - g.pad, n, bar, a_policy);    // single-tap only: a 3x3 re-reads every input tile nine times
     } else {
       tma_load_4d(sa, ta, c0, s - g.pad, oh0 + r - g.pad, n, bar);
     }
@@ -242,6 +283,7 @@ struct ConvFwdProducer {
 template <int BN>
 struct ConvDgradProducer {
   ConvTcGeom g;
+  __device__ __forceinline__ void set_policy(unsigned long long) {}
   __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
     const int cpb = (g.Cout + BK - 1) / BK;
     const int tap = kb / cpb, co0 = (kb - tap * cpb) * BK;
@@ -257,6 +299,7 @@ struct ConvDgradProducer {
 template <int BN>
 struct ConvWgradProducer {
   ConvTcGeom g;
+  __device__ __forceinline__ void set_policy(unsigned long long) {}
   __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
     const int p0 = kb * BK;
     const int P = g.Ho * g.Wo;
@@ -513,6 +556,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   // third tile coordinate z: split-K slice (kb_beg = z * kb_per_split), or -- batched GEMM (ep.batch_heads != 0) -- the batch index
   const bool batched = ep.batch_heads != 0;
   auto tile_coords = [&](int t, int& m0, int& n0, int& kb_beg, int& nkb, int& z) {
+    if (ep.reverse) t = total_tiles - 1 - t;          // serpentine traversal across consecutive kernels (rih_set_traversal)
     const int ni = t % tiles_n;
     const int r = t / tiles_n;
     const int mi = r % tiles_m;
@@ -525,6 +569,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
+      Producer pr = prod;
+      pr.set_policy(ep.a_policy ? l2_policy_evict_first() : 0ull);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int m0, n0, kb_beg, nkb, z;
         tile_coords(t, m0, n0, kb_beg, nkb, z);
@@ -534,7 +580,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], AB_BYTES);
           uint8_t* sa = smem + s * STAGE_BYTES;
-          prod.load(&tmap_a, &tmap_b, kb_beg + kb, m0, n0, z, sa, sa + A_BYTES, &full[s]);
+          pr.load(&tmap_a, &tmap_b, kb_beg + kb, m0, n0, z, sa, sa + A_BYTES, &full[s]);
         }
       }
     }
@@ -672,18 +718,28 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             tma_store_commit();
           }
           if (ep.stats) {
-            // fused BatchNorm statistics: this warp sums column `lane` of the chunk over its 32 rows straight from the staging
-            // tile (one 128-byte row per LDS wavefront: conflict-free), then one fp64 atomic pair per column per warp
-            const int col = nb + lane;
-            float sm = 0.f, sq = 0.f;
+            // fused BatchNorm statistics: column sums / sums of squares of the chunk over this warp's 32 rows.  Each lane holds one ROW
+            // (32 columns) in registers: a halving butterfly over the lanes (16 + 8 + 4 + 2 + 1 = 31 exchanges per quantity) leaves lane l with
+            // the totals of column l -- no shared-memory pass (the serial 32-row LDS loop this replaces cost ~0.5 us per chunk, a third of
+            // the epilogue of the store-bound 1x1 convolutions).  Then one fp64 atomic pair per column per warp.
             const int rows_valid = min(32, ep.M - (m0 + q * 32));
-            const int jc = lane >> 2, wi = lane & 3;
-            for (int r = 0; r < rows_valid; ++r) {
-              const int row = q * 32 + r;
-              const float x = *reinterpret_cast<const float*>(buf + row * 128 + ((jc ^ (row & 7)) << 4) + wi * 4);
-              sm += x; sq = fmaf(x, x, sq);
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float x = (lane < rows_valid) ? v[j] : 0.f; s1[j] = x; s2[j] = x * x; }
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) {
+              const bool up = (lane & w) != 0;
+#pragma unroll
+              for (int j = 0; j < w; ++j) {
+                // keep the half of the columns whose bit `w` equals this lane's bit `w`, hand the other half to the partner lane
+                const float keep1 = up ? s1[j + w] : s1[j], give1 = up ? s1[j] : s1[j + w];
+                const float keep2 = up ? s2[j + w] : s2[j], give2 = up ? s2[j] : s2[j + w];
+                s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, give1, w);
+                s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, give2, w);
+              }
             }
-            if (col < ep.N && rows_valid > 0) { atomicAdd(ep.stats + col, (double)sm); atomicAdd(ep.stats + ep.N + col, (double)sq); }
+            const int col = nb + lane;      // after the butterfly lane l holds column l (bit w of the column index = bit w of the lane)
+            if (col < ep.N && rows_valid > 0) { atomicAdd(ep.stats + col, (double)s1[0]); atomicAdd(ep.stats + ep.N + col, (double)s2[0]); }
           }
           ++cc;
         } else {

@@ -105,6 +105,10 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int 
 // Thread -> (channel quad, first row) mapping shared by the element-wise BatchNorm passes: the launch has a multiple of C/4 threads, so
 // a thread keeps ONE channel quad for its whole grid-stride loop and the per-channel terms are computed once per thread.
 struct BnMap { int q; long long r0, rstride; };
+// flags of the element-wise BatchNorm passes: bit 0 = walk the rows from the last to the first (rih_set_traversal), bit 1 = streamed inputs are
+// loaded with the evict-first priority (rih_set_l2_hints)
+__device__ __forceinline__ float4 ld4(const float* p, int hint) { return hint ? __ldcs(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p); }
+static inline int bn_flags() { return (g_reverse ? 1 : 0) | (g_l2_hints ? 2 : 0); }
 __device__ __forceinline__ BnMap bn_map(int C4) {
   const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long T = (long long)gridDim.x * blockDim.x;
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(256)
 bn_forward_kernel(const float* __restrict__ x, int ldx, const double* __restrict__ stats, long long M, int C4, float eps, float momentum,
                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ res, int ldr,
                   float* __restrict__ y, int ldy, int relu, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                  float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ tracked) {
+                  float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ tracked, int flags) {
   pdl_sync();
   const BnMap mp = bn_map(C4);
   const int c = mp.q * 4, C = C4 * 4;
@@ -172,13 +176,15 @@ bn_forward_kernel(const float* __restrict__ x, int ldx, const double* __restrict
     *reinterpret_cast<float4*>(rstd_out + c) = make_float4(rs[0], rs[1], rs[2], rs[3]);
   }
   const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
-  for (long long r = mp.r0; r < M; r += mp.rstride) {
-    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+  const int hint = flags & 2;
+  for (long long rr = mp.r0; rr < M; rr += mp.rstride) {
+    const long long r = (flags & 1) ? M - 1 - rr : rr;
+    const float4 v = ld4(x + r * ldx + c, hint);
     float4 o;
     o.x = (v.x - mu[0]) * rs[0] * g.x + b.x; o.y = (v.y - mu[1]) * rs[1] * g.y + b.y;
     o.z = (v.z - mu[2]) * rs[2] * g.z + b.z; o.w = (v.w - mu[3]) * rs[3] * g.w + b.w;
     if (res) {
-      const float4 q = *reinterpret_cast<const float4*>(res + r * ldr + c);
+      const float4 q = ld4(res + r * ldr + c, hint);
       o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
     }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
@@ -192,7 +198,7 @@ RIH_API int rih_bn_forward(const float* x, int ldx, const double* stats, long lo
   RIH_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (!res || ldr % 4 == 0), "bn_forward: needs C,ld %% 4 == 0");
   RIH_REQUIRE(M > 0 && (stats || (running_mean && running_var)), "bn_forward: eval mode needs the running statistics");
   launch_k(bn_forward_kernel, bn_grid(M, C / 4, 256), 256, 0, s, x, ldx, stats, M, C / 4, eps, momentum, gamma, beta, res, ldr, y, ldy, relu,
-                                                          mean_out, rstd_out, running_mean, running_var, tracked);
+                                                          mean_out, rstd_out, running_mean, running_var, tracked, bn_flags());
   return check_launch("bn_forward");
 }
 
@@ -248,7 +254,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restr
                     const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ ws,
                     float* __restrict__ dx, int lddx, float* __restrict__ dres, int lddr, int dres_acc,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, int param_acc,
-                    long long M, int C4, int relu, int training, int mask_input) {
+                    long long M, int C4, int relu, int training, int mask_input, int flags) {
   pdl_sync();
   const BnMap mp = bn_map(C4);
   const int c = mp.q * 4, C = C4 * 4;
@@ -269,10 +275,12 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restr
       if (dbeta) dbeta[c + j] = param_acc ? dbeta[c + j] + sgv[j] : sgv[j];
     }
   }
-  for (long long r = mp.r0; r < M; r += mp.rstride) {
-    const float4 g4 = *reinterpret_cast<const float4*>(dy + r * lddy + c);
+  const int hint = flags & 2;
+  for (long long rr = mp.r0; rr < M; rr += mp.rstride) {
+    const long long r = (flags & 1) ? M - 1 - rr : rr;
+    const float4 g4 = ld4(dy + r * lddy + c, hint);
     float g[4] = {g4.x, g4.y, g4.z, g4.w};
-    const float4 x4 = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float4 x4 = ld4(x + r * ldx + c, hint);
     const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
     if (relu) {
       float yv[4];
@@ -325,7 +333,7 @@ RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const
   launch_k(bn_bwd_reduce_kernel, grid, 256, 0, s, dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, (int)M, C, rows_per_cta, relu, ws);
   if (int e = check_launch("bn_bwd_reduce")) return e;
   launch_k(bn_bwd_apply_kernel, bn_grid(M, C / 4, 256), 256, 0, s, dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx, dres, lddr, dres_acc,
-                                                            dgamma, dbeta, param_acc, M, C / 4, relu, training, mask_input);
+                                                            dgamma, dbeta, param_acc, M, C / 4, relu, training, mask_input, bn_flags());
   return check_launch("bn_bwd_apply");
 }
 

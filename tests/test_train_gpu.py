@@ -2,7 +2,7 @@
 ONE step of the reference trainer -- the UNMODIFIED reference model + core.Loss.calc_loss_GCN + torch.optim.AdamW
 (core/lijun_trainer.py:131-144, 262-313) driven by oracle/ref_driver.py on the CPU -- on the same seeded weights / batch, dropout 0.
 
-Stated tolerances (batch 8; measured values are printed):
+Stated tolerances (batch 16; measured values are printed):
   exact-fp32 kernels ('simt'):  loss 2e-4 relative, every gradient tensor |norm ratio - 1| < 1e-2 and cosine > 0.9995,
                                  AdamW update direction: sign agreement on every element whose reference gradient is not round-off
   bench arithmetic ('ref' = tf32c convolutions + 3xTF32 Linears):  loss 5e-3, gradient norms 6e-2, cosine > 0.99
@@ -22,7 +22,7 @@ from renderih_b200 import assets as rih_assets
 pytestmark = pytest.mark.gpu
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
-B = 8
+B = 16      # BatchNorm statistics over >= 1024 samples per channel: well conditioned (batch 2 is not)
 
 
 def _product_step(mode, batch=B, use_graph=True, lr=3e-4, wd=1e-2):
@@ -119,7 +119,7 @@ def _compare_step(mode, ref, loss_tol, norm_tol, cos_tol):
               % ((mode,) + worst_n + worst_c + (flips,)))
         assert step.flatp.step_count == 1
         assert int(model.encoder.resnet.bn1.num_batches_tracked) == ref['bn1_tracked'] == 1        # BatchNorm2d.num_batches_tracked parity
-        assert float((model.encoder.resnet.bn1.running_mean.cpu() - ref['bn1_mean']).abs().max()) < 1e-5
+        assert float((model.encoder.resnet.bn1.running_mean.cpu() - ref['bn1_mean']).abs().max()) < (1e-5 if mode == 'simt' else 1e-3)
     finally:
         ops.set_gemm_mode('simt', 'simt')
         ops.clear_grad_targets()
@@ -162,7 +162,7 @@ def test_fused_adamw_kernel_matches_torch_optim_adamw():
     st_ref = opt.state_dict()['state']
     for i in range(len(shapes)):
         assert float(sd['state'][i]['step']) == float(st_ref[i]['step']) == 3.0
-        assert float((sd['state'][i]['exp_avg'].cpu() - st_ref[i]['exp_avg'].cpu()).abs().max()) < 1e-7
+        assert float((sd['state'][i]['exp_avg'].cpu() - st_ref[i]['exp_avg'].cpu()).abs().max() / st_ref[i]['exp_avg'].abs().max().cpu()) < 2e-6
     fp2 = FlatParams([torch.nn.Parameter(p.detach().clone()) for p in mine])
     fp2.load_state_dict(opt.state_dict())
     assert fp2.step_count == 3 and float((fp2.exp_avg_sq - fp.exp_avg_sq).abs().max()) < 1e-9
