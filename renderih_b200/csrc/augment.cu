@@ -66,7 +66,7 @@ RIH_API int rih_augment_u8(const unsigned char* src, const double* minv, const d
   RIH_REQUIRE(B >= 0 && H > 0 && W > 0 && H <= 32767 && W <= 32767 && src && minv && dst, "augment_u8: bad arguments");
   const long long total = (long long)B * H * W;
   if (total == 0) return 0;
-  const int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  const int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(augment_u8_kernel, grid, 256, 0, s, src, minv, gain_offset, flip, dst, ori, out_u8, B, H, W, mean3_host[0], mean3_host[1], mean3_host[2],
                                          std3_host[0], std3_host[1], std3_host[2]);
   return check_launch("augment_u8");

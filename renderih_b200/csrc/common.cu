@@ -14,6 +14,26 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Optional cap on the SMs that work launched on a given stream may occupy (rih_set_stream_cta_limit): a convolution pipeline that runs
+// concurrently with the latency-bound token decoder leaves the remaining SMs / thread slots to it.  Persistent GEMM grids are capped to `ctas`
+// CTAs; element-wise kernels on such a stream launch a quarter of their usual CTAs per SM (ew_ctas), so that a 448-thread GEMM CTA of the
+// decoder always finds thread slots next to them instead of waiting for a wave of 8 x 256-thread CTAs per SM to drain.
+static cudaStream_t g_cap_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+static int g_cap_ctas[4] = {0, 0, 0, 0};
+int set_stream_cta_limit(cudaStream_t s, int ctas) {
+  for (int i = 0; i < 4; ++i) if (g_cap_stream[i] == s || g_cap_ctas[i] == 0) { g_cap_stream[i] = s; g_cap_ctas[i] = ctas > 0 ? ctas : 0; return 0; }
+  return 1;
+}
+int stream_cta_limit(cudaStream_t s, int num_sms) {
+  for (int i = 0; i < 4; ++i) if (g_cap_ctas[i] > 0 && g_cap_stream[i] == s) return g_cap_ctas[i] < num_sms ? g_cap_ctas[i] : num_sms;
+  return num_sms;
+}
+int g_ew_cap = 1;
+long long ew_ctas(cudaStream_t s) {
+  if (g_ew_cap) for (int i = 0; i < 4; ++i) if (g_cap_ctas[i] > 0 && g_cap_stream[i] == s) return 148 * 4;
+  return 148 * 16;
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -39,6 +59,9 @@ RIH_API int rih_set_traversal(int reverse) { rih::g_reverse = reverse ? 1 : 0; r
 
 // 1 = activations that a GEMM / 1x1 convolution / BatchNorm pass streams through once are loaded with the L2 evict-first priority, so that they do
 // not displace the previous kernel's output (which the next kernel is about to read) from the L2.  Scheduling only.
+// 1 (default) = element-wise kernels launched on a CTA-capped stream (rih_set_stream_cta_limit) use a quarter of their usual grid.  Scheduling only.
+RIH_API int rih_set_ew_cap(int on) { rih::g_ew_cap = on ? 1 : 0; return 0; }
+
 RIH_API int rih_set_l2_hints(int on) { rih::g_l2_hints = on ? 1 : 0; return 0; }
 
 // Device properties probe (used by the host side to fail loudly on a non-sm_100 device).

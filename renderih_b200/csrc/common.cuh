@@ -12,6 +12,9 @@ namespace rih {
 // ---- error convention: 0 = ok, non-zero + rih_last_error() ----
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+int set_stream_cta_limit(cudaStream_t s, int ctas);
+int stream_cta_limit(cudaStream_t s, int num_sms);
+long long ew_ctas(cudaStream_t s);      // grid cap of element-wise kernels on stream s (148 * 16, or 148 * 4 on a CTA-capped stream)
 
 #define RIH_REQUIRE(cond, ...)                        \
   do {                                                \

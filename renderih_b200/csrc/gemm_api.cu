@@ -12,13 +12,15 @@ int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long
 bool conv_tc_supported(const ConvGeom& g, int which);
 void set_nsplit(int n);
 void set_narrow_small(int on);
-int set_stream_cta_limit(cudaStream_t s, int ctas);
+void set_wgrad_wide(int on);
 void set_acc_scale(float s);
 extern int g_stats_fused;
 long long conv_tc_workspace(const ConvGeom& g, int which);
 int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s);
 int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s);
 int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s);
+int stem_fwd_tf32(const float* xp, const float* w224, Epilogue ep, int N, int H, int W, cudaStream_t s);
+int stem_wgrad_tf32(const float* dy, int lddy, const float* xp, Epilogue ep, int N, int H, int W, cudaStream_t s);
 } }
 
 // Arithmetic mode of the GEMM-class ops: 0 = SIMT fp32 (exact), 1 = tcgen05 TF32 multiplicands / fp32 accumulate,
@@ -40,12 +42,15 @@ RIH_API int rih_set_gemm_mode(int conv_mode, int linear_mode) {
 // counterpart: scheduling only, results are unchanged.)
 RIH_API int rih_set_stream_cta_limit(cudaStream_t stream, int ctas) {
   RIH_REQUIRE(ctas >= 0, "set_stream_cta_limit: ctas must be >= 0");
-  RIH_REQUIRE(tc::set_stream_cta_limit(stream, ctas) == 0, "set_stream_cta_limit: more than 4 capped streams");
+  RIH_REQUIRE(set_stream_cta_limit(stream, ctas) == 0, "set_stream_cta_limit: more than 4 capped streams");
   return 0;
 }
 // 1 (default) = GEMMs whose 128-wide tiling would occupy at most half of the SMs use 64-wide N tiles (twice the CTAs, half the serial work
 // per CTA); 0 = always the widest tile.  Scheduling only: results are unchanged.
 RIH_API int rih_set_narrow_tiles(int on) { tc::set_narrow_small(on); return 0; }
+// 1 (default) = convolution weight gradients with Cin % 32 == 0 use 256-wide N tiles that span several filter taps; 0 = one tap per tile.
+// Scheduling / tiling only: results agree up to the summation order of the split-K reduction.
+RIH_API int rih_set_wgrad_wide(int on) { tc::set_wgrad_wide(on); return 0; }
 static inline bool use_tc(int which) {
   if (g_mode[which] == 0) return false;
   tc::set_nsplit(g_mode[which] == 2 ? 3 : (g_mode[which] == 3 ? 2 : 1));
@@ -223,4 +228,29 @@ RIH_API int rih_conv2d_wgrad(const float* dy, const float* x, float* dw, const i
   if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(x, g.ldx) && tc::conv_tc_supported(g, 2) && (g.stride == 1 || ws)) return tc::conv_wgrad_tf32(dy, x, ep, g, ws, stream);
   ConvWgradB b{x, g, Kn, is_vec_ok(x, g.ldx) && (g.Cin % 4 == 0)};
   return launch_gemm_simt(a, b, ep, g.Cout, Kn, (int)P, 1, stream, "conv2d_wgrad");
+}
+
+// RGB stem conv1 (7x7 / stride 2 / pad 3, 3 -> 64; torchvision resnet.conv1 as used by models/encoder.py:108) as a tcgen05 implicit GEMM
+// over the zero-bordered NHWC4 image xp[N][H+6][W+8][4] written by rih_nchw_to_nhwc4_pad; w224 = the filter repacked as [64][7][8][4]
+// (8th column and 4th channel zero).  Tensor-core convolution modes only (rih_set_gemm_mode); `stats` as in rih_conv2d_fwd.
+RIH_API int rih_stem_conv_fwd(const float* xp, const float* w224, float* y, int N, int H, int W, double* stats, cudaStream_t stream) {
+  RIH_REQUIRE(N > 0 && H > 0 && W > 0, "stem_conv_fwd: bad shape");
+  RIH_REQUIRE(use_tc(0), "stem_conv_fwd: needs a tensor-core convolution mode (rih_set_gemm_mode)");
+  RIH_REQUIRE(tc_ok(xp, 4) && tc_ok(w224, 224) && tc_ok(y, 64), "stem_conv_fwd: pointers must be 16-byte aligned");
+  if (stats) RIH_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * 64, stream));
+  tc::g_stats_fused = 0;
+  const int M = N * (H / 2) * (W / 2);
+  Epilogue ep = make_epilogue(y, 64, M, 64, nullptr, 0, 0);
+  ep.stats = stats;
+  if (int e = tc::stem_fwd_tf32(xp, w224, ep, N, H, W, stream)) return e;
+  if (stats && !tc::g_stats_fused) return rih_bn_colstats(y, 64, M, 64, stats, stream);
+  return 0;
+}
+// dw224[64][224] (+)= weight gradient of the stem convolution (dy: [N*Ho*Wo, 64] rows with stride lddy)
+RIH_API int rih_stem_conv_wgrad(const float* dy, int lddy, const float* xp, float* dw224, int N, int H, int W, int accumulate, cudaStream_t stream) {
+  RIH_REQUIRE(N > 0 && H > 0 && W > 0, "stem_conv_wgrad: bad shape");
+  RIH_REQUIRE(use_tc(0), "stem_conv_wgrad: needs a tensor-core convolution mode (rih_set_gemm_mode)");
+  RIH_REQUIRE(tc_ok(xp, 4) && tc_ok(dy, lddy) && tc_ok(dw224, 224), "stem_conv_wgrad: pointers must be 16-byte aligned");
+  Epilogue ep = make_epilogue(dw224, 224, 64, 224, nullptr, 0, accumulate ? 1 : 0);
+  return tc::stem_wgrad_tf32(dy, lddy, xp, ep, N, H, W, stream);
 }

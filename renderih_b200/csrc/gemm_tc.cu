@@ -57,6 +57,25 @@ int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int
   return 0;
 }
 
+int make_tmap_stem(CUtensorMap* map, const float* base, int N, int Hp, int Wp, int Wo, int box_ow, bool atom32) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 1; }
+  if (reinterpret_cast<uintptr_t>(base) & 15) { set_error("tensor map (stem): base not 16-byte aligned"); return 1; }
+  cuuint64_t dims[4] = {32u, (cuuint64_t)Wo, (cuuint64_t)Hp, (cuuint64_t)N};
+  cuuint64_t strides[3] = {32u, (cuuint64_t)Wp * 16u, (cuuint64_t)Hp * Wp * 16u};     // bytes: 2 padded pixels, one padded row, one padded image
+  cuuint32_t box[4] = {32u, (cuuint32_t)box_ow, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    cudaFree(0);
+  }
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(stem, overlapping strides) failed (%d) N=%d Hp=%d Wp=%d Wo=%d", (int)r, N, Hp, Wp, Wo); return 1; }
+  return 0;
+}
+
 // wgrad output dW[Cout][taps][Cin] as a 3-D map, box {32 channels, 1 tap, 128 filters}: a channel chunk is clipped at its own tap
 int make_tmap_wgrad_out(CUtensorMap* map, const float* base, int Cout, int taps, int Cin) {
   EncodeTiledFn fn = get_encode_fn();
@@ -80,24 +99,14 @@ int make_tmap_wgrad_out(CUtensorMap* map, const float* base, int Cout, int taps,
 int g_stats_fused = 0;            // set by the launcher when the epilogue accumulated ep.stats (fused BatchNorm statistics)
 static int g_wide_tiles = 1;     // 128 x 256 output tiles when N % 256 == 0
 void set_wide_tiles(int on) { g_wide_tiles = on ? 1 : 0; }
+static int g_wgrad_wide = 1;     // 256-wide multi-tap N tiles for the convolution weight gradients (rih_set_wgrad_wide)
+void set_wgrad_wide(int on) { g_wgrad_wide = on ? 1 : 0; }
 static int g_narrow_small = 1;   // 64-wide N tiles for GEMMs whose 128-wide tiling would leave half of the SMs idle (RIH_NARROW_TILES=0 to compare)
 void set_narrow_small(int on) { g_narrow_small = on ? 1 : 0; }
 static int g_persistent = 1;     // 0 = one CTA per tile (non-persistent kernel; debug / comparison)
 void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
 void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
-// Optional cap on the persistent grid of GEMMs launched on a given stream (rih_set_stream_cta_limit): a convolution pipeline that runs
-// concurrently with the latency-bound token decoder leaves the remaining SMs to it instead of occupying all 148 for every tile loop.
-static cudaStream_t g_cap_stream[4] = {nullptr, nullptr, nullptr, nullptr};
-static int g_cap_ctas[4] = {0, 0, 0, 0};
-int set_stream_cta_limit(cudaStream_t s, int ctas) {
-  for (int i = 0; i < 4; ++i) if (g_cap_stream[i] == s || g_cap_ctas[i] == 0) { g_cap_stream[i] = s; g_cap_ctas[i] = ctas > 0 ? ctas : 0; return 0; }
-  return 1;
-}
-static inline int stream_cta_limit(cudaStream_t s, int num_sms) {
-  for (int i = 0; i < 4; ++i) if (g_cap_ctas[i] > 0 && g_cap_stream[i] == s) return g_cap_ctas[i] < num_sms ? g_cap_ctas[i] : num_sms;
-  return num_sms;
-}
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep, const Producer& prod, int M, int N, int num_kb, int splits,
                       int kb_per_split, cudaStream_t s, const CUtensorMap* c_map = nullptr) {
@@ -344,11 +353,38 @@ int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom
   return launch_cfg<64, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s);
 }
 
+// RGB stem as an implicit GEMM over the zero-bordered NHWC4 image xp[N][H+6][W+8][4] (see StemFwdProducer): y[N*Ho*Wo, 64] = X'[., 224] . w224^T
+int stem_fwd_tf32(const float* xp, const float* w224, Epilogue ep, int N, int H, int W, cudaStream_t s) {
+  const int Ho = H / 2, Wo = W / 2, M = N * Ho * Wo;
+  if (Wo != BM || (H & 1) || (W & 1)) { set_error("stem_fwd_tf32: needs an even image with W / 2 == 128 (got %d x %d)", H, W); return 1; }
+  CUtensorMap ta, tb;
+  if (make_tmap_stem(&ta, xp, N, H + 6, W + 8, Wo, BM, false)) return 1;
+  if (make_tmap_2d(&tb, w224, 64, 224, 224, 64)) return 1;
+  StemFwdProducer<64> p{Ho, Wo};
+  return launch_cfg<64, false, false>(ta, tb, ep, p, M, 64, 7, 1, 7, s);
+}
+// dw224[64, 224] (+)= dY[N*Ho*Wo, 64]^T . X'
+int stem_wgrad_tf32(const float* dy, int lddy, const float* xp, Epilogue ep, int N, int H, int W, cudaStream_t s) {
+  const int Ho = H / 2, Wo = W / 2, P = N * Ho * Wo;
+  if (Wo % 32 || (H & 1) || (W & 1)) { set_error("stem_wgrad_tf32: needs an even image with W / 2 a multiple of 32"); return 1; }
+  CUtensorMap ta, tb;
+  if (make_tmap_2d(&ta, dy, P, 64, lddy, 32, true)) return 1;
+  if (make_tmap_stem(&tb, xp, N, H + 6, W + 8, Wo, 32, true)) return 1;
+  int num_kb = P / BK, splits, kps;
+  plan_splitk(ep, 64, 224, 256, num_kb, 1, splits, kps, s);
+  StemWgradProducer<256> p{Ho, Wo};
+  return launch_cfg<256, true, true>(ta, tb, ep, p, 64, 224, num_kb, splits, kps, s);
+}
+
 int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom& g, float* ws, cudaStream_t s) {
-  const int P = g.N * g.Ho * g.Wo, taps = g.R * g.S, Nn = taps * g.Cin, BN = (g.Cin % 128 == 0) ? 128 : 64;
+  const int P = g.N * g.Ho * g.Wo, taps = g.R * g.S, Nn = taps * g.Cin;
+  // Cin a multiple of 32: the 32-column chunks of an N tile never straddle a tap, so 256-wide tiles may span several taps (the dY operand is
+  // re-read once per N tile: 3 times instead of 9 for Cin = 64, 9 instead of 18 for Cin = 256) -- RIH_WGRAD_WIDE=0 keeps one tap per tile
+  const bool wide = g_wgrad_wide && g_persistent && g.Cin % 32 == 0 && Nn >= 256;
+  const int BN = wide ? 256 : ((g.Cin % 128 == 0) ? 128 : 64);
   // N tiles never straddle a tap: each tap owns ceil(Cin / BN) tiles; when BN does not divide Cin (48, 96, ...) the tile grid is
   // "virtual" (cin_pad columns per tap) and the epilogue stores through a 3-D map [Cout][taps][Cin] that clips at the tap's edge
-  const int cin_pad = cdiv(g.Cin, BN) * BN, Ngrid = taps * cin_pad;
+  const int cin_pad = wide ? g.Cin : cdiv(g.Cin, BN) * BN, Ngrid = taps * cin_pad;
   const int bw = g.Wo < 32 ? g.Wo : 32, bh = 32 / bw;
   CUtensorMap ta, tb, tcm;
   if (make_tmap_2d(&ta, dy, P, g.Cout, g.ldy, 32, true)) return 1;
@@ -368,6 +404,7 @@ int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom
     if (make_tmap_wgrad_out(&tcm, ep.c, g.Cout, taps, g.Cin)) return 1;
     cmap = &tcm; ep.nv_pad = cin_pad; ep.nv_real = g.Cin;
   }
+  if (BN == 256) { ConvWgradProducer<256> p{cg}; return launch_cfg<256, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap); }
   if (BN == 128) { ConvWgradProducer<128> p{cg}; return launch_cfg<128, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap); }
   ConvWgradProducer<64> p{cg};
   return launch_cfg<64, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap);

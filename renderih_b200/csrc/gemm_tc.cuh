@@ -166,7 +166,7 @@ template <int BN, int NSPLIT> __host__ __device__ constexpr int stage_bytes() { 
 #define RIH_EPI_WGS 2
 #endif
 #ifndef RIH_DEEP
-#define RIH_DEEP 0
+#define RIH_DEEP 1      // measured on the ResNet-50 trunk (tools/trunk_bench.py): 20.85 -> 20.53 ms fwd+bwd
 #endif
 template <int BN, int NSPLIT> __host__ __device__ constexpr int num_stages() {
   if (NSPLIT == 1 && RIH_DEEP) {
@@ -295,7 +295,9 @@ struct ConvDgradProducer {
     for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, tap * g.Cin + n0 + c * 32, co0, bar);
   }
 };
-// wgrad: A = dY as MN-major chunks {32 co, 32 pixels}, B = shifted input boxes of 32 pixels as MN-major chunks {32 c, 32 pixels}
+// wgrad: A = dY as MN-major chunks {32 co, 32 pixels}, B = shifted input boxes of 32 pixels as MN-major chunks {32 c, 32 pixels}.
+// The N axis enumerates (tap, channel) in cin_pad-wide groups; every 32-column chunk of the N tile finds its OWN tap, so a tile may span
+// several taps (Cin = 64: a 256-wide tile covers 4 taps and the dY tile is fetched 3 times instead of 9).
 template <int BN>
 struct ConvWgradProducer {
   ConvTcGeom g;
@@ -305,19 +307,63 @@ struct ConvWgradProducer {
     const int P = g.Ho * g.Wo;
     const int n = p0 / P, rem = p0 - n * P;
     const int oh = rem / g.Wo, ow = rem - oh * g.Wo;
-    const int tap = n0 / g.cin_pad, cbase = n0 - tap * g.cin_pad;
-    const int r = tap / g.S, s = tap - r * g.S;
+    const int taps = g.R * g.S;
 #pragma unroll
     for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
-    int cw = ow + s - g.pad, ch = oh + r - g.pad, cn = n;
-    if (g.s2_images > 0) {
-      int ph, dh, pw, dw_;
-      s2_tap(r, g.pad, ph, dh);
-      s2_tap(s, g.pad, pw, dw_);
-      cw = ow + dw_; ch = oh + dh; cn = (ph * 2 + pw) * g.s2_images + n;
-    }
 #pragma unroll
-    for (int c = 0; c < BN / 32; ++c) tma_load_4d(sb + c * (BK * 128), tb, cbase + c * 32, cw, ch, cn, bar);
+    for (int c = 0; c < BN / 32; ++c) {
+      const int col = n0 + c * 32;
+      int tap = col / g.cin_pad, cbase = col - tap * g.cin_pad;
+      if (tap >= taps) { tap = 0; cbase = g.cin_pad + 64; }      // beyond the last tap: a channel coordinate outside the tensor -> the TMA unit zero-fills
+      const int r = tap / g.S, s = tap - r * g.S;
+      int cw = ow + s - g.pad, ch = oh + r - g.pad, cn = n;
+      if (g.s2_images > 0) {
+        int ph, dh, pw, dw_;
+        s2_tap(r, g.pad, ph, dh);
+        s2_tap(s, g.pad, pw, dw_);
+        cw = ow + dw_; ch = oh + dh; cn = (ph * 2 + pw) * g.s2_images + n;
+      }
+      tma_load_4d(sb + c * (BK * 128), tb, cbase, cw, ch, cn, bar);
+    }
+  }
+};
+
+// ---- RGB stem (conv1 7x7 / stride 2 / pad 3, 3 -> 64; torchvision ResNet, models/encoder.py:108) as an implicit GEMM without an im2col buffer.
+// The image is stored once as zero-bordered NHWC4 P[n][H+6][W+8][4] (3 rows / columns of padding in front, RGB + one zero channel).  The 8
+// horizontally adjacent padded pixels that filter row r sees for output pixel (oh, ow) -- columns 2 ow .. 2 ow + 7 of padded row 2 oh + r, i.e.
+// taps s = 0 .. 6 plus one extra column that meets a zero weight -- are 32 CONTIGUOUS floats.  A 4-D tensor map with the (overlapping) strides
+// {4 B, 32 B (= 2 pixels), row pitch, image pitch} and dims {32, Wo, H + 6, N} therefore presents them as a "virtual" NHWC tensor with 32
+// channels per (row, ow), and the convolution becomes a 7-tap (R = 7, S = 1) implicit GEMM with K = 7 x 32 = 224 against weights repacked
+// as [64][7][8][4]: one TMA box {32, 128 ow, 1, 1} per k-block, 128-byte rows, SWIZZLE_128B -- the same machinery as every other
+// convolution.  An output tile is one output row (Wo = 128).
+template <int BN>
+struct StemFwdProducer {
+  int Ho, Wo;
+  __device__ __forceinline__ void set_policy(unsigned long long) {}
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+    const int P = Ho * Wo;
+    const int n = m0 / P, oh = (m0 - n * P) / Wo;
+    tma_load_4d(sa, ta, 0, 0, 2 * oh + kb, n, bar);       // filter row r = kb
+    tma_load_2d(sb, tb, kb * 32, n0, bar);
+  }
+};
+// weight gradient of the stem: dW[64][7 x 32] = sum over pixels dY^T . X', k-block = 32 consecutive output pixels of one output row
+template <int BN>
+struct StemWgradProducer {
+  int Ho, Wo;
+  __device__ __forceinline__ void set_policy(unsigned long long) {}
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+    const int p0 = kb * BK;
+    const int P = Ho * Wo;
+    const int n = p0 / P, rem = p0 - n * P;
+    const int oh = rem / Wo, ow = rem - oh * Wo;
+#pragma unroll
+    for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      const int r = (n0 >> 5) + c;                         // filter row of this 32-column chunk; rows >= 7 do not exist -> out-of-range row coordinate, zero fill
+      tma_load_4d(sb + c * (BK * 128), tb, 0, ow, r < 7 ? 2 * oh + r : (1 << 20), n, bar);
+    }
   }
 };
 
@@ -768,6 +814,8 @@ EncodeTiledFn get_encode_fn();
 int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows, bool atom32 = false);
 // 4-D fp32 tensor map over an NHWC tensor [N,H,W,C] with pixel stride ld; box = {32 channels, bw, bh, bn}.
 int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int C, long long ld, int bw, int bh, int bn, bool atom32);
+// overlapping-stride view of the zero-bordered NHWC4 stem input (see StemFwdProducer); box = {32, box_ow, 1, 1}
+int make_tmap_stem(CUtensorMap* map, const float* base, int N, int Hp, int Wp, int Wo, int box_ow, bool atom32);
 
 }  // namespace tc
 }  // namespace rih

@@ -49,7 +49,7 @@ RIH_API int rih_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int
   if (Cp <= 8) {
     const long long total = (long long)N * HW;
     if (total == 0) return 0;
-    launch_k(nchw_to_nhwc_small_kernel, (int)min((long long)148 * 16, (total + 255) / 256), 256, 0, s, x, y, C, HW, Cp, ldy, total);
+    launch_k(nchw_to_nhwc_small_kernel, (int)min(ew_ctas(s), (total + 255) / 256), 256, 0, s, x, y, C, HW, Cp, ldy, total);
     return check_launch("nchw_to_nhwc");
   }
   dim3 grid(cdiv(HW, 32), cdiv(Cp, 32), N), block(32, 8);
@@ -61,6 +61,30 @@ RIH_API int rih_nhwc_to_nchw(const float* x, float* y, int N, int C, int HW, int
   dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
   launch_k(nhwc_to_nchw_kernel, grid, block, 0, s, x, y, N, C, HW, ldx, c_off);
   return check_launch("nhwc_to_nchw");
+}
+
+// NCHW RGB image -> zero-bordered NHWC4 [N][H+6][W+8][4] (3 rows / columns of zeros in front, RGB + one zero channel): the layout the
+// implicit-GEMM stem reads (rih_stem_conv_fwd).  One thread per padded pixel, coalesced plane reads, one float4 store.
+__global__ void nchw_to_nhwc4_pad_kernel(const float* __restrict__ x, float4* __restrict__ y, int N, int H, int W) {
+  pdl_sync();
+  const int Hp = H + 6, Wp = W + 8;
+  const long long total = (long long)N * Hp * Wp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int wp = (int)(i % Wp); long long t = i / Wp; const int hp = (int)(t % Hp); const int n = (int)(t / Hp);
+    const int h = hp - 3, w = wp - 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) {
+      const float* p = x + ((size_t)n * 3 * H + h) * W + w;
+      v.x = p[0]; v.y = p[(size_t)H * W]; v.z = p[2 * (size_t)H * W];
+    }
+    y[i] = v;
+  }
+}
+RIH_API int rih_nchw_to_nhwc4_pad(const float* x, float* y, int N, int H, int W, cudaStream_t s) {
+  RIH_REQUIRE(N > 0 && H > 0 && W > 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "nchw_to_nhwc4_pad: bad arguments");
+  const long long total = (long long)N * (H + 6) * (W + 8);
+  launch_k(nchw_to_nhwc4_pad_kernel, (int)min(ew_ctas(s), (total + 255) / 256), 256, 0, s, x, reinterpret_cast<float4*>(y), N, H, W);
+  return check_launch("nchw_to_nhwc4_pad");
 }
 
 // generic strided 2-D copy / add:  y[r, 0:C] (+)= x[r, 0:C]
@@ -76,7 +100,7 @@ __global__ void copy2d_kernel(const float* __restrict__ x, int ldx, float* __res
 }
 RIH_API int rih_copy2d(const float* x, int ldx, float* y, int ldy, long long rows, int C, int accumulate, cudaStream_t s) {
   if (rows * C == 0) return 0;
-  int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (rows * C + 255) / 256);
   launch_k(copy2d_kernel, grid, 256, 0, s, x, ldx, y, ldy, rows, C, accumulate);
   return check_launch("copy2d");
 }
@@ -115,12 +139,12 @@ __device__ __forceinline__ BnMap bn_map(int C4) {
   BnMap m; m.q = (int)(gid % C4); m.r0 = gid / C4; m.rstride = T / C4;
   return m;
 }
-static inline int bn_grid(long long M, int C4, int threads) {
+static inline int bn_grid(long long M, int C4, int threads, long long cap = 148 * 16) {
   int g = 1, a = C4, b = threads;                 // grid must be a multiple of C4 / gcd(C4, threads)
   while (b) { int t = a % b; a = b; b = t; }
   g = C4 / a;
   long long want = (M * C4 + threads - 1) / threads;
-  if (want > 148 * 16) want = 148 * 16;
+  if (want > cap) want = cap;
   if (want < 1) want = 1;
   return (int)((want + g - 1) / g * g);
 }
@@ -197,7 +221,7 @@ RIH_API int rih_bn_forward(const float* x, int ldx, const double* stats, long lo
                            float* mean_out, float* rstd_out, float* running_mean, float* running_var, long long* tracked, cudaStream_t s) {
   RIH_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (!res || ldr % 4 == 0), "bn_forward: needs C,ld %% 4 == 0");
   RIH_REQUIRE(M > 0 && (stats || (running_mean && running_var)), "bn_forward: eval mode needs the running statistics");
-  launch_k(bn_forward_kernel, bn_grid(M, C / 4, 256), 256, 0, s, x, ldx, stats, M, C / 4, eps, momentum, gamma, beta, res, ldr, y, ldy, relu,
+  launch_k(bn_forward_kernel, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, x, ldx, stats, M, C / 4, eps, momentum, gamma, beta, res, ldr, y, ldy, relu,
                                                           mean_out, rstd_out, running_mean, running_var, tracked, bn_flags());
   return check_launch("bn_forward");
 }
@@ -332,7 +356,7 @@ RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const
   dim3 grid(gx, cdiv(M, rows_per_cta));
   launch_k(bn_bwd_reduce_kernel, grid, 256, 0, s, dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, (int)M, C, rows_per_cta, relu, ws);
   if (int e = check_launch("bn_bwd_reduce")) return e;
-  launch_k(bn_bwd_apply_kernel, bn_grid(M, C / 4, 256), 256, 0, s, dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx, dres, lddr, dres_acc,
+  launch_k(bn_bwd_apply_kernel, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx, dres, lddr, dres_acc,
                                                             dgamma, dbeta, param_acc, M, C / 4, relu, training, mask_input, bn_flags());
   return check_launch("bn_bwd_apply");
 }
@@ -349,7 +373,7 @@ __global__ void relu_bwd_kernel(const float* __restrict__ dy, int lddy, const fl
 }
 RIH_API int rih_relu_bwd(const float* dy, int lddy, const float* y, int ldy, float* dx, int lddx, long long rows, int C, cudaStream_t s) {
   if (rows * C == 0) return 0;
-  int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (rows * C + 255) / 256);
   launch_k(relu_bwd_kernel, grid, 256, 0, s, dy, lddy, y, ldy, dx, lddx, rows, C);
   return check_launch("relu_bwd");
 }
@@ -441,7 +465,7 @@ RIH_API int rih_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, i
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && (reinterpret_cast<uintptr_t>(idx) & 3) == 0;
   long long total = (long long)N * Ho * Wo * (vec ? C / 4 : C);
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   if (vec) launch_k(maxpool4_fwd_kernel, grid, 256, 0, s, x, y, idx, N, H, W, C / 4, Ho, Wo);
   else launch_k(maxpool_fwd_kernel, grid, 256, 0, s, x, y, idx, N, H, W, C, Ho, Wo);
   return check_launch("maxpool_fwd");
@@ -450,7 +474,7 @@ RIH_API int rih_maxpool3x3s2_bwd(const float* dy, const unsigned char* idx, floa
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 && (reinterpret_cast<uintptr_t>(idx) & 3) == 0;
   long long total = (long long)N * H * W * (vec ? C / 4 : C);
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   if (vec) launch_k(maxpool4_bwd_kernel, grid, 256, 0, s, dy, idx, dx, N, H, W, C / 4, Ho, Wo);
   else launch_k(maxpool_bwd_kernel, grid, 256, 0, s, dy, idx, dx, N, H, W, C, Ho, Wo);
   return check_launch("maxpool_bwd");
@@ -506,7 +530,7 @@ static inline bool bil_vec_ok(const void* a, int lda, const void* b, int ldb, in
 RIH_API int rih_bilinear2x_fwd(const float* x, int ldx, float* y, int ldy, int N, int H, int W, int C, cudaStream_t s) {
   if (bil_vec_ok(x, ldx, y, ldy, C)) return rih_bilinear_up_fwd(x, ldx, y, ldy, N, H, W, C, 2, s);      // float4 kernel
   long long total = (long long)N * 4 * H * W * C;
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(bilinear2x_fwd_kernel, grid, 256, 0, s, x, ldx, y, ldy, N, H, W, C);
   return check_launch("bilinear2x_fwd");
 }
@@ -514,7 +538,7 @@ RIH_API int rih_bilinear2x_fwd(const float* x, int ldx, float* y, int ldy, int N
 RIH_API int rih_bilinear2x_bwd(const float* dy, int lddy, float* dx, int lddx, int N, int H, int W, int C, cudaStream_t s) {
   if (bil_vec_ok(dy, lddy, dx, lddx, C)) return rih_bilinear_up_bwd(dy, lddy, dx, lddx, N, H, W, C, 2, s);   // gather form: overwrites dx, no atomics
   long long total = (long long)N * 4 * H * W * C;
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(bilinear2x_bwd_kernel, grid, 256, 0, s, dy, lddy, dx, lddx, N, H, W, C);
   return check_launch("bilinear2x_bwd");
 }
@@ -584,7 +608,7 @@ RIH_API int rih_bilinear_up_fwd(const float* x, int ldx, float* y, int ldy, int 
               "bilinear_up_fwd: needs C, strides multiples of 4 floats and 16-byte aligned pointers (C=%d ldx=%d ldy=%d)", C, ldx, ldy);
   long long total = (long long)N * f * H * f * W * (C / 4);
   if (total == 0) return 0;
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(bilinear_up4_fwd_kernel, grid, 256, 0, s, x, ldx, y, ldy, N, H, W, C / 4, f);
   return check_launch("bilinear_up_fwd");
 }
@@ -594,7 +618,7 @@ RIH_API int rih_bilinear_up_bwd(const float* dy, int lddy, float* dx, int lddx, 
               "bilinear_up_bwd: needs C, strides multiples of 4 floats and 16-byte aligned pointers");
   long long total = (long long)N * H * W * (C / 4);
   if (total == 0) return 0;
-  int grid = (int)min((long long)148 * 16, (total + 127) / 128);
+  int grid = (int)min(ew_ctas(s), (total + 127) / 128);
   launch_k(bilinear_up4_bwd_kernel, grid, 128, 0, s, dy, lddy, dx, lddx, N, H, W, C / 4, f);
   return check_launch("bilinear_up_bwd");
 }
@@ -635,7 +659,7 @@ RIH_API int rih_fuse_sum(const float* const* terms, const int* lds, const int* f
   }
   long long total = (long long)N * H * W * (C / 4);
   if (total == 0) return 0;
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(fuse_sum_kernel, grid, 256, 0, s, a, y, ldy, N, H, W, C / 4, relu);
   return check_launch("fuse_sum");
 }
@@ -666,7 +690,7 @@ RIH_API int rih_pool_sum(const float* dy, int lddy, const float* y, int ldy, flo
   RIH_REQUIRE(f >= 1 && C % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && (!y || ldy % 4 == 0), "pool_sum: channels / strides must be multiples of 4");
   long long total = (long long)N * H * W * (C / 4);
   if (total == 0) return 0;
-  int grid = (int)min((long long)148 * 16, (total + 127) / 128);
+  int grid = (int)min(ew_ctas(s), (total + 127) / 128);
   launch_k(pool_sum_kernel, grid, 128, 0, s, dy, lddy, y, ldy, dx, lddx, N, H, W, C / 4, f);
   return check_launch("pool_sum");
 }
@@ -698,7 +722,7 @@ RIH_API int rih_gap_fwd(const float* x, int ldx, float* y, int N, int HW, int C,
 }
 RIH_API int rih_gap_bwd(const float* dy, float* dx, int lddx, int N, int HW, int C, int accumulate, cudaStream_t s) {
   long long total = (long long)N * HW * C;
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(gap_bwd_kernel, grid, 256, 0, s, dy, dx, lddx, N, HW, C, accumulate);
   return check_launch("gap_bwd");
 }
@@ -719,7 +743,7 @@ __global__ void parity_stack_kernel(const float* __restrict__ x, int ldx, float*
 RIH_API int rih_parity_stack(const float* x, int ldx, float* xp, int N, int H, int W, int C, cudaStream_t s) {
   RIH_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0 && ldx % 4 == 0, "parity_stack: H, W must be even and C, ld multiples of 4");
   long long total = (long long)N * H * W * (C / 4);
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(parity_stack_kernel, grid, 256, 0, s, x, ldx, xp, N, H, W, C / 4);
   return check_launch("parity_stack");
 }
@@ -738,7 +762,7 @@ __global__ void dilate2x_kernel(const float* __restrict__ y, int ldy, float* __r
 RIH_API int rih_dilate2x(const float* y, int ldy, float* yd, int N, int Ho, int Wo, int C, cudaStream_t s) {
   RIH_REQUIRE(C % 4 == 0 && ldy % 4 == 0, "dilate2x: C, ld must be multiples of 4");
   long long total = (long long)N * 4 * Ho * Wo * (C / 4);
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(dilate2x_kernel, grid, 256, 0, s, y, ldy, yd, N, Ho, Wo, C / 4);
   return check_launch("dilate2x");
 }
@@ -762,7 +786,7 @@ __global__ void patchify_kernel(const float* __restrict__ x, int ldx, float* __r
 RIH_API int rih_patchify(float* x, int ldx, float* P, int N, int H, int W, int C, int p, int scatter, cudaStream_t s) {
   RIH_REQUIRE(p >= 1 && H % p == 0 && W % p == 0 && C % 4 == 0 && ldx % 4 == 0, "patchify: bad geometry");
   long long total = (long long)N * H * W * (C / 4);
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(patchify_kernel, grid, 256, 0, s, x, ldx, P, N, H, W, C / 4, p, scatter);
   return check_launch("patchify");
 }
@@ -864,7 +888,7 @@ RIH_API int rih_preprocess_u8(const unsigned char* src, const unsigned char* fli
   RIH_REQUIRE(B >= 0 && H > 0 && W > 0, "preprocess_u8: bad shape");
   const long long total = (long long)B * H * W;
   if (total == 0) return 0;
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(preprocess_u8_kernel, grid, 256, 0, s, src, flip, dst, B, H, W, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1], std3_host[2]);
   return check_launch("preprocess_u8");
 }

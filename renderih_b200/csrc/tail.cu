@@ -215,7 +215,7 @@ __global__ void scatter_rows_add_kernel(const float* __restrict__ dy, const int*
 RIH_API int rih_gather_rows(const float* x, const int* idx, float* y, int B, int Vin, int Vout, int C, int div, cudaStream_t s) {
   long long total = (long long)B * Vout * C;
   if (total == 0) return 0;
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(gather_rows_kernel, grid, 256, 0, s, x, idx, y, B, Vin, Vout, C, div);
   return check_launch("gather_rows");
 }
@@ -223,7 +223,7 @@ RIH_API int rih_gather_rows(const float* x, const int* idx, float* y, int B, int
 RIH_API int rih_scatter_rows_add(const float* dy, const int* idx, float* dx, int B, int Vin, int Vout, int C, int div, cudaStream_t s) {
   long long total = (long long)B * Vout * C;
   if (total == 0) return 0;
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(scatter_rows_add_kernel, grid, 256, 0, s, dy, idx, dx, B, Vin, Vout, C, div);
   return check_launch("scatter_rows_add");
 }

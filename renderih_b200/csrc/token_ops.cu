@@ -198,11 +198,11 @@ RIH_API int rih_cheb_fwd(const float* x, int ldx, const int* rowptr, const int* 
   long long total = (long long)B * V * F;
   if (total == 0) return 0;
   if (F % 4 == 0 && ldx % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
-    int grid = (int)min((long long)148 * 16, (total / 4 + 255) / 256);
+    int grid = (int)min(ew_ctas(s), (total / 4 + 255) / 256);
     launch_k(cheb4_fwd_kernel, grid, 256, 0, s, x, ldx, rowptr, col, val, out, B, V, F / 4);
     return check_launch("cheb_fwd");
   }
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(cheb_fwd_kernel, grid, 256, 0, s, x, ldx, rowptr, col, val, out, B, V, F);
   return check_launch("cheb_fwd");
 }
@@ -211,11 +211,11 @@ RIH_API int rih_cheb_bwd(const float* d, const int* rowptrT, const int* colT, co
   long long total = (long long)B * V * F;
   if (total == 0) return 0;
   if (F % 4 == 0 && lddx % 4 == 0 && ((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
-    int grid = (int)min((long long)148 * 16, (total / 4 + 255) / 256);
+    int grid = (int)min(ew_ctas(s), (total / 4 + 255) / 256);
     launch_k(cheb4_bwd_kernel, grid, 256, 0, s, d, rowptrT, colT, valT, dx, lddx, accumulate, B, V, F / 4);
     return check_launch("cheb_bwd");
   }
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(cheb_bwd_kernel, grid, 256, 0, s, d, rowptrT, colT, valT, dx, lddx, accumulate, B, V, F);
   return check_launch("cheb_bwd");
 }
@@ -259,7 +259,7 @@ RIH_API int rih_posemb_fwd(const float* x, int ldx, const float* emb, float* y, 
   RIH_REQUIRE(p >= 1 && U % p == 0, "posemb_fwd: U %% p != 0");
   long long total = (long long)B * U * F;
   if (total == 0) return 0;
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(posemb_fwd_kernel, grid, 256, 0, s, x, ldx, emb, y, ldy, B, U, F, p);
   return check_launch("posemb_fwd");
 }
@@ -267,13 +267,13 @@ RIH_API int rih_posemb_bwd(const float* dy, int lddy, float* dx, int lddx, float
   RIH_REQUIRE(p >= 1 && U % p == 0, "posemb_bwd: U %% p != 0");
   if (dx) {
     long long total = (long long)B * (U / p) * F;
-    int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+    int grid = (int)min(ew_ctas(s), (total + 255) / 256);
     launch_k(posemb_bwd_x_kernel, grid, 256, 0, s, dy, lddy, dx, lddx, B, U, F, p);
     if (int e = check_launch("posemb_bwd_x")) return e;
   }
   if (demb) {
     long long total = (long long)U * F;
-    int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+    int grid = (int)min(ew_ctas(s), (total + 255) / 256);
     launch_k(posemb_bwd_emb_kernel, grid, 256, 0, s, dy, lddy, demb, B, U, F);
     if (int e = check_launch("posemb_bwd_emb")) return e;
   }
@@ -323,7 +323,7 @@ RIH_API int rih_dropout(const float* x, int ldx, float* y, int ldy, long long ro
                         const unsigned long long* seed_ptr, unsigned long long site, cudaStream_t s) {
   if (rows * C == 0) return 0;
   RIH_REQUIRE(p > 0.f && p < 1.f && seed_ptr, "dropout: p out of range or missing seed");
-  int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (rows * C + 255) / 256);
   launch_k(dropout_kernel, grid, 256, 0, s, x, ldx, y, ldy, rows, C, seed_ptr, site, dropout_thresh(p), 1.f / (1.f - p));
   return check_launch("dropout");
 }
@@ -347,7 +347,7 @@ RIH_API int rih_epilogue_bwd(const float* dy, int lddy, const float* y, int ldy,
                              float dropout_p, const unsigned long long* seed_ptr, unsigned long long site, cudaStream_t s) {
   if (rows * C == 0) return 0;
   RIH_REQUIRE(dropout_p == 0.f || (seed_ptr && dropout_p < 1.f), "epilogue_bwd: dropout needs a device seed");
-  int grid = (int)min((long long)148 * 16, (rows * C + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (rows * C + 255) / 256);
   launch_k(epilogue_bwd_kernel, grid, 256, 0, s, dy, lddy, y, ldy, g, ldg, rows, C, relu, seed_ptr, site,
                                            dropout_p > 0.f ? dropout_thresh(dropout_p) : 0u, dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f);
   return check_launch("epilogue_bwd");
@@ -385,7 +385,7 @@ __global__ void gf_broadcast_bwd_kernel(const float* __restrict__ dy, float* __r
 }
 RIH_API int rih_gf_broadcast_fwd(const float* g, const float* pe, const float* emb, float* y, int B, int V, int G, cudaStream_t s) {
   long long total = (long long)B * V * (G + 3);
-  int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+  int grid = (int)min(ew_ctas(s), (total + 255) / 256);
   launch_k(gf_broadcast_fwd_kernel, grid, 256, 0, s, g, pe, emb, y, B, V, G);
   return check_launch("gf_broadcast_fwd");
 }
@@ -394,7 +394,7 @@ RIH_API int rih_gf_broadcast_bwd(const float* dy, float* dg, float* demb, int B,
   if (int e = check_launch("gf_broadcast_bwd")) return e;
   if (demb) {
     long long total = (long long)V * (G + 3);
-    int grid = (int)min((long long)148 * 16, (total + 255) / 256);
+    int grid = (int)min(ew_ctas(s), (total + 255) / 256);
     launch_k(posemb_bwd_emb_kernel, grid, 256, 0, s, dy, G + 3, demb, B, V, G + 3);
     if (int e = check_launch("gf_broadcast_bwd_emb")) return e;
   }
@@ -403,26 +403,29 @@ RIH_API int rih_gf_broadcast_bwd(const float* dy, float* dg, float* demb, int B,
 
 // ============================================================== fused AdamW over a flat fp32 buffer (torch.optim.AdamW semantics)
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+                             long long n, float decay, float b1, float omb1, float b2, float omb2, float eps, float step_size, float bc2_sqrt, float gscale) {
   pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float gi = g[i] * gscale;
-    float pi = p[i] * (1.f - lr * wd);
-    float mi = b1 * m[i] + (1.f - b1) * gi;
-    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    float pi = p[i] * decay;                       // decoupled weight decay: p *= 1 - lr * wd
+    float mi = b1 * m[i] + omb1 * gi;              // exp_avg.lerp_(grad, 1 - beta1)
+    float vi = b2 * v[i] + omb2 * gi * gi;         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
     m[i] = mi; v[i] = vi;
     float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - (lr / bc1) * (mi / denom);
+    p[i] = pi - step_size * (mi / denom);          // step_size = lr / (1 - beta1^t)
   }
 }
-RIH_API int rih_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                           float eps, float weight_decay, int step, float grad_scale, cudaStream_t s) {
+// torch.optim.AdamW.step (single-tensor path of torch/optim/adamw.py): every scalar (1 - beta, the bias corrections, lr / bc1, 1 - lr * wd) is
+// formed in DOUBLE on the host exactly like torch forms them as Python floats, then rounded to float once -- the kernel then matches
+// torch.optim.AdamW on identical gradients to fp32 round-off (tests/test_train_gpu.py).  grad_scale folds the data-parallel mean (1 / world).
+RIH_API int rih_adamw_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
+                           double eps, double weight_decay, int step, double grad_scale, cudaStream_t s) {
   RIH_REQUIRE(n >= 0 && step >= 1, "adamw_step: n must be >= 0 and step >= 1 (got n=%lld step=%d)", n, step);
   if (n == 0) return 0;
-  // bias corrections in double like torch.optim.AdamW's Python scalars (1 - 0.999f in float is already 5e-5 off at step 1)
-  float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
-  float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
-  int grid = (int)min((long long)148 * 16, (n + 255) / 256);
-  launch_k(adamw_kernel, grid, 256, 0, s, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  int grid = (int)min(ew_ctas(s), (n + 255) / 256);
+  launch_k(adamw_kernel, grid, 256, 0, s, p, g, m, v, n, (float)(1.0 - lr * weight_decay), (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+           (float)eps, (float)(lr / bc1), (float)sqrt(bc2), (float)grad_scale);
   return check_launch("adamw");
 }

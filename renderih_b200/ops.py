@@ -20,6 +20,9 @@ import os as _os
 _ATTN = {'nsplit': 0, 'force': _os.environ.get('RIH_ATTN_IMPL') or None}     # RIH_ATTN_IMPL=simt|tc overrides the mode-derived choice (A/B runs)
 
 
+MODE = {'conv': 'simt', 'linear': 'simt'}
+
+
 def set_gemm_mode(conv='simt', linear='simt'):
     """Arithmetic of the GEMM-class kernels: 'simt' = exact fp32 CUDA-core path, 'tf32' = tcgen05 tensor cores with TF32
     multiplicands and fp32 accumulation (what the reference's cuDNN convolutions use by default on this GPU),
@@ -27,6 +30,7 @@ def set_gemm_mode(conv='simt', linear='simt'):
     'tf32rn' = TF32 with the operands rounded to nearest in shared memory before the MMA (unbiased; the cuDNN convention),
     'tf32x3' = the same tensor-core kernels with an in-kernel hi/lo operand split and 3 MMAs per step (fp32-faithful)."""
     call('rih_set_gemm_mode', GEMM_MODES[conv], GEMM_MODES[linear])
+    MODE['conv'], MODE['linear'] = conv, linear
     # the attention contractions follow the nn.Linear arithmetic (the reference runs both as fp32 torch.matmul / addmm):
     # 0 = fused SIMT kernel (exact fp32), 1 = tcgen05 TF32, 3 = tcgen05 3xTF32
     _ATTN['nsplit'] = {'simt': 0, 'tf32x3': 3}.get(linear, 1)
@@ -964,6 +968,46 @@ class Im2colFn(Function):
 def im2col(x, N, H, W, R, S, stride, pad, Kpad):
     assert not x.requires_grad
     return Im2colFn.apply(x, N, H, W, R, S, stride, pad, Kpad)
+
+
+class StemConvFn(Function):
+    """torchvision resnet.conv1 (7x7 / stride 2 / pad 3, 3 -> 64; models/encoder.py:108) as a tcgen05 implicit GEMM over the zero-bordered NHWC4
+    image (csrc/gemm_tc.cuh StemFwdProducer): no im2col buffer (the old path wrote and re-read 671 MB at batch 64).  w224 = the filter
+    repacked [64][7][8][4].  The image receives no gradient."""
+
+    @staticmethod
+    def forward(ctx, xp, w224, N, H, W, stats):
+        y = torch.empty((N * (H // 2) * (W // 2), 64), device=xp.device, dtype=torch.float32)
+        call('rih_stem_conv_fwd', _p(xp), _p(w224), _p(y), N, H, W, _p(stats), _stream())
+        ctx.save_for_backward(xp)
+        ctx.dims = (N, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xp,) = ctx.saved_tensors
+        N, H, W = ctx.dims
+        dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
+        dw = torch.empty((64, 224), device=dy.device, dtype=torch.float32)
+        call('rih_stem_conv_wgrad', _p(dy), _ld(dy), _p(xp), _p(dw), N, H, W, 0, _stream())
+        return None, dw, None, None, None, None
+
+
+def stem_supported(H, W):
+    """The implicit-GEMM stem needs a tensor-core convolution mode and 256 x 256 images (one output row = one 128-pixel tile)."""
+    return MODE['conv'] != 'simt' and H == W == 256 and _os.environ.get('RIH_STEM_IGEMM', '1') != '0'
+
+
+def stem_conv(img, weight, stats=None):
+    """img: [N,3,H,W] (no gradient), weight: conv1.weight [64,3,7,7] channels_last.  -> NHWC rows [N*(H/2)*(W/2), 64]."""
+    img = _check(img).contiguous()
+    N, C, H, W = img.shape
+    assert C == 3 and tuple(weight.shape) == (64, 3, 7, 7) and not img.requires_grad
+    xp = torch.empty((N, H + 6, W + 8, 4), device=img.device, dtype=torch.float32)
+    call('rih_nchw_to_nhwc4_pad', _p(img), _p(xp), N, H, W, _stream())
+    # [64,3,7,7] (memory [64][7][7][3]) -> [64][7][8][4]: one zero column (the 8th pixel of every 128-byte row) and one zero channel
+    w224 = torch.nn.functional.pad(weight.permute(0, 2, 3, 1), (0, 1, 0, 1)).reshape(64, 224)
+    return StemConvFn.apply(xp, w224, N, H, W, stats)
 
 
 class BatchNormFn(Function):
