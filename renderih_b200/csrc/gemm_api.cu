@@ -13,6 +13,8 @@ bool conv_tc_supported(const ConvGeom& g, int which);
 void set_nsplit(int n);
 void set_narrow_small(int on);
 void set_wgrad_wide(int on);
+void set_s2_direct(int on);
+int s2_direct();
 void set_acc_scale(float s);
 extern int g_stats_fused;
 long long conv_tc_workspace(const ConvGeom& g, int which);
@@ -50,6 +52,10 @@ RIH_API int rih_set_stream_cta_limit(cudaStream_t stream, int ctas) {
 RIH_API int rih_set_narrow_tiles(int on) { tc::set_narrow_small(on); return 0; }
 // 1 (default) = convolution weight gradients with Cin % 32 == 0 use 256-wide N tiles that span several filter taps; 0 = one tap per tile.
 // Scheduling / tiling only: results agree up to the summation order of the split-K reduction.
+// 1 (default) = stride-2 convolutions (forward, weight gradient, input gradient) address the full-resolution tensors in place through tensor
+// maps with element strides {1, 2, 2, 1}; the input gradient runs as four dense parity-class GEMMs.  0 = the copy-based formulation
+// (parity-stacked input for forward / wgrad, zero-inserted dY for dgrad; needs the rih_conv2d_workspace buffers).
+RIH_API int rih_set_s2_direct(int on) { tc::set_s2_direct(on); return 0; }
 RIH_API int rih_set_wgrad_wide(int on) { tc::set_wgrad_wide(on); return 0; }
 static inline bool use_tc(int which) {
   if (g_mode[which] == 0) return false;
@@ -182,7 +188,7 @@ static int conv2d_fwd_impl(const float* x, const float* w, const float* bias, fl
       return tc::gemm_tf32(x, g.ldx, 0, w, K, 0, ep, (int)M, g.Cout, K, 0, stream);
     return launch_gemm_simt(a, b, ep, (int)M, g.Cout, K, 0, stream, "conv1x1_fwd");
   }
-  if (use_tc(0) && tc_ok(x, g.ldx) && tc_ok(w, K) && tc::conv_tc_supported(g, 0) && (g.stride == 1 || ws)) return tc::conv_fwd_tf32(x, w, ep, g, ws, stream);
+  if (use_tc(0) && tc_ok(x, g.ldx) && tc_ok(w, K) && tc::conv_tc_supported(g, 0) && (g.stride == 1 || ws || tc::s2_direct())) return tc::conv_fwd_tf32(x, w, ep, g, ws, stream);
   ConvFwdA a{x, g, (int)M, is_vec_ok(x, g.ldx) && (g.Cin % 4 == 0)};
   return launch_gemm_simt(a, b, ep, (int)M, g.Cout, K, 0, stream, "conv2d_fwd");
 }
@@ -203,7 +209,7 @@ RIH_API int rih_conv2d_dgrad(const float* dy, const float* w, float* dx, const i
       return tc::gemm_tf32(dy, g.ldy, 0, w, g.Cin, 1, ep, (int)M, g.Cin, g.Cout, 0, stream);
     return launch_gemm_simt(a, b, ep, (int)M, g.Cin, g.Cout, 0, stream, "conv1x1_dgrad");
   }
-  if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(w, g.Cin) && tc::conv_tc_supported(g, 1) && (g.stride == 1 || ws)) return tc::conv_dgrad_tf32(dy, w, ep, g, ws, stream);
+  if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(w, g.Cin) && tc::conv_tc_supported(g, 1) && (g.stride == 1 || ws || tc::s2_direct())) return tc::conv_dgrad_tf32(dy, w, ep, g, ws, stream);
   ConvDgradA a{dy, g, (int)M, is_vec_ok(dy, g.ldy) && (g.Cout % 4 == 0)};
   ConvDgradB b{w, g, g.Cin, is_vec_ok(w, g.Cin)};
   return launch_gemm_simt(a, b, ep, (int)M, g.Cin, K, 0, stream, "conv2d_dgrad");
@@ -225,7 +231,7 @@ RIH_API int rih_conv2d_wgrad(const float* dy, const float* x, float* dw, const i
       return tc::gemm_tf32(dy, g.ldy, 1, x, g.ldx, 1, ep, g.Cout, Kn, (int)P, 1, stream);
     return launch_gemm_simt(a, b, ep, g.Cout, Kn, (int)P, 1, stream, "conv1x1_wgrad");
   }
-  if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(x, g.ldx) && tc::conv_tc_supported(g, 2) && (g.stride == 1 || ws)) return tc::conv_wgrad_tf32(dy, x, ep, g, ws, stream);
+  if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(x, g.ldx) && tc::conv_tc_supported(g, 2) && (g.stride == 1 || ws || tc::s2_direct())) return tc::conv_wgrad_tf32(dy, x, ep, g, ws, stream);
   ConvWgradB b{x, g, Kn, is_vec_ok(x, g.ldx) && (g.Cin % 4 == 0)};
   return launch_gemm_simt(a, b, ep, g.Cout, Kn, (int)P, 1, stream, "conv2d_wgrad");
 }

@@ -37,14 +37,16 @@ int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, long long 
   return 0;
 }
 
-int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int C, long long ld, int bw, int bh, int bn, bool atom32) {
+int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int C, long long ld, int bw, int bh, int bn, bool atom32, int estride) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 1; }
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4)) { set_error("tensor map: base/ld not 16-byte aligned"); return 1; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4};
-  cuuint32_t box[4] = {32u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  // with a traversal stride e the box extent is given in traversed elements: bw * e positions yield bw fetched pixels
+  cuuint32_t box[4] = {32u, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1u, (cuuint32_t)estride, (cuuint32_t)estride, 1u};
+  if (box[1] > 256u || box[2] > 256u) { set_error("tensor map (nhwc, element stride %d): box %u x %u exceeds 256", estride, box[1], box[2]); return 1; }
   CUresult r = CUDA_SUCCESS;
   for (int attempt = 0; attempt < 2; ++attempt) {
     r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
@@ -282,6 +284,9 @@ int bgemm_tf32(const BOperand& a, int a_mn, const BOperand& b, int b_mn, const B
   return rc;
 }
 
+static int g_s2_direct = 1;      // stride-2 convolutions through element-strided tensor maps (no parity-stacked / zero-inserted copies); rih_set_s2_direct
+void set_s2_direct(int on) { g_s2_direct = on ? 1 : 0; }
+int s2_direct() { return g_s2_direct; }
 static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // Can the stride-1 convolution run on the tcgen05 implicit-GEMM path?
@@ -295,12 +300,14 @@ bool conv_tc_supported(const ConvGeom& g, int which /*0 fwd, 1 dgrad, 2 wgrad*/)
   if (g.Cin % 16 || g.Cout % 16 || g.Cin < 32 || g.Cout < 32) return false;
   if (g.ldx % 4 || g.ldy % 4) return false;
   if (which == 0) return pow2(g.Wo) && pow2(g.Ho) && g.Wo <= 128 && ((long long)g.N * g.Ho * g.Wo) % BM == 0 && (g.Wo * g.Ho >= BM || BM % (g.Wo * g.Ho) == 0);
+  if (which == 1 && g.stride == 2 && g_s2_direct)     // four parity-class GEMMs over the half-resolution (= output) grid
+    return pow2(g.Wo) && pow2(g.Ho) && g.Wo <= 128 && ((long long)g.N * g.Ho * g.Wo) % BM == 0 && (g.Wo * g.Ho >= BM || BM % (g.Wo * g.Ho) == 0);
   if (which == 1) return pow2(g.W) && pow2(g.H) && g.W <= 128 && ((long long)g.N * g.H * g.W) % BM == 0 && (g.W * g.H >= BM || BM % (g.W * g.H) == 0);
   return pow2(g.Wo) && pow2(g.Ho) && (g.Ho * g.Wo) % 32 == 0 && (g.Cin % 64 == 0 || g_persistent);
 }
 
 long long conv_tc_workspace(const ConvGeom& g, int which) {
-  if (g.stride != 2) return 0;
+  if (g.stride != 2 || g_s2_direct) return 0;
   if (which == 1) return (long long)g.N * g.H * g.W * g.Cout;   // zero-inserted dY
   return (long long)g.N * g.H * g.W * g.Cin;                    // parity-stacked x
 }
@@ -314,7 +321,9 @@ int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g
   const int tile_h = (BM / g.Wo) < g.Ho ? (BM / g.Wo) : g.Ho;
   const int tile_n = BM / (g.Wo * tile_h);
   CUtensorMap ta, tb;
-  if (g.stride == 2) {
+  if (g.stride == 2 && g_s2_direct) {
+    if (make_tmap_nhwc(&ta, x, g.N, g.H, g.W, g.Cin, g.ldx, g.Wo, tile_h, tile_n, false, 2)) return 1;
+  } else if (g.stride == 2) {
     if (!ws) { set_error("conv_fwd_tf32: stride-2 path needs workspace"); return 1; }
     if (int e = rih_parity_stack(x, g.ldx, ws, g.N, g.H, g.W, g.Cin, s)) return e;
     if (make_tmap_nhwc(&ta, ws, 4 * g.N, g.H / 2, g.W / 2, g.Cin, g.Cin, g.Wo, tile_h, tile_n, false)) return 1;
@@ -322,7 +331,7 @@ int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g
     if (make_tmap_nhwc(&ta, x, g.N, g.H, g.W, g.Cin, g.ldx, g.Wo, tile_h, tile_n, false)) return 1;
   }
   if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, BN)) return 1;
-  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, g.stride == 2 ? g.N : 0, g.Cin};
+  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, g.stride == 2 ? (g_s2_direct ? -1 : g.N) : 0, g.Cin};
   const int num_kb = g.R * g.S * cdiv(g.Cin, BK);
   if (BN == 256) { ConvFwdProducer<256> p{cg, 0ull}; return launch_cfg<256, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
   if (BN == 128) { ConvFwdProducer<128> p{cg, 0ull}; return launch_cfg<128, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s); }
@@ -330,8 +339,60 @@ int conv_fwd_tf32(const float* x, const float* w, Epilogue ep, const ConvGeom& g
   return launch_cfg<64, false, false>(ta, tb, ep, p, M, g.Cout, num_kb, 1, num_kb, s);
 }
 
+// stride-2 dgrad as four dense parity-class GEMMs over the half-resolution grid (ConvDgradS2Producer), stored / accumulated in place through an
+// element-strided map of dx.  Classes without a contributing tap (1x1 convolutions: three of four) are zero-filled unless the caller accumulates.
+static int conv_dgrad_s2_direct(const float* dy, const float* w, Epilogue ep, const ConvGeom& g, cudaStream_t s) {
+  const int H2 = g.Ho, W2 = g.Wo;                       // class grid == output grid (even H, W)
+  const int M = g.N * H2 * W2;
+  int BN = (g.Cin > 64) ? 128 : 64;
+  if (g_persistent && g_wide_tiles && g.Cin % 256 == 0 && (long long)(M / BM) * (g.Cin / 256) >= 120) BN = 256;
+  const int tile_h = (BM / W2) < H2 ? (BM / W2) : H2;
+  const int tile_n = BM / (W2 * tile_h);
+  CUtensorMap ta, tb, tcm;
+  if (make_tmap_nhwc(&ta, dy, g.N, g.Ho, g.Wo, g.Cout, g.ldy, W2, tile_h, tile_n, false)) return 1;
+  if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, 32, true)) return 1;
+  if (make_tmap_nhwc(&tcm, ep.c, g.N, g.H, g.W, g.Cin, ep.ldc, W2, tile_h, tile_n, false, 2)) return 1;
+  const int accumulate = ep.mode != 0;
+  bool zeroed = false;
+  for (int ph = 0; ph < 2; ++ph) for (int pw = 0; pw < 2; ++pw) {
+    int rs[2], nr = 0, ss[2], ns = 0;
+    for (int r = 0; r < g.R; ++r) if (((ph + g.pad - r) & 1) == 0) rs[nr++] = r;
+    for (int q = 0; q < g.S; ++q) if (((pw + g.pad - q) & 1) == 0) ss[ns++] = q;
+    if (nr * ns == 0) {
+      if (!accumulate && !zeroed) {      // this class receives no gradient: zero the whole tensor once, the other classes overwrite their pixels
+        if (ep.ldc == g.Cin) cudaMemsetAsync(ep.c, 0, (size_t)g.N * g.H * g.W * g.Cin * sizeof(float), s);
+        else cudaMemset2DAsync(ep.c, (size_t)ep.ldc * sizeof(float), 0, (size_t)g.Cin * sizeof(float), (size_t)g.N * g.H * g.W, s);
+        zeroed = true;
+      }
+      continue;
+    }
+  }
+  for (int ph = 0; ph < 2; ++ph) for (int pw = 0; pw < 2; ++pw) {
+    ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, H2, W2, g.Ho, g.Wo, tile_h, 0, g.Cin};
+    int nt = 0, tap[4], dr[4], ds[4];
+    for (int r = 0; r < g.R; ++r) if (((ph + g.pad - r) & 1) == 0)
+      for (int q = 0; q < g.S; ++q) if (((pw + g.pad - q) & 1) == 0) {
+        if (nt >= 4) { set_error("conv_dgrad_s2: more than 4 taps per parity class (kernel %dx%d)", g.R, g.S); return 1; }
+        tap[nt] = r * g.S + q; dr[nt] = (ph + g.pad - r) / 2; ds[nt] = (pw + g.pad - q) / 2; ++nt;
+      }
+    if (nt == 0) continue;
+    Epilogue e2 = ep;
+    e2.M = M; e2.s2_w2 = W2; e2.s2_h2 = H2; e2.s2_ph = ph; e2.s2_pw = pw;
+    const int num_kb = nt * cdiv(g.Cout, BK);
+    int rc;
+#define RIH_S2_CASE(bn)                                                                                                        \
+    { ConvDgradS2Producer<bn> p{cg, nt, {tap[0], tap[1], tap[2], tap[3]}, {dr[0], dr[1], dr[2], dr[3]}, {ds[0], ds[1], ds[2], ds[3]}}; \
+      rc = launch_cfg<bn, false, true>(ta, tb, e2, p, M, g.Cin, num_kb, 1, num_kb, s, &tcm); }
+    if (BN == 256) RIH_S2_CASE(256) else if (BN == 128) RIH_S2_CASE(128) else RIH_S2_CASE(64)
+#undef RIH_S2_CASE
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom& g0, float* ws, cudaStream_t s) {
   ConvGeom g = g0;
+  if (g0.stride == 2 && g_s2_direct) return conv_dgrad_s2_direct(dy, w, ep, g0, s);
   if (g0.stride == 2) {   // zero-insert dY, then it is a stride-1 dgrad over an H x W "output"
     if (!ws) { set_error("conv_dgrad_tf32: stride-2 path needs workspace"); return 1; }
     if (int e = rih_dilate2x(dy, g0.ldy, ws, g0.N, g0.Ho, g0.Wo, g0.Cout, s)) return e;
@@ -388,14 +449,16 @@ int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom
   const int bw = g.Wo < 32 ? g.Wo : 32, bh = 32 / bw;
   CUtensorMap ta, tb, tcm;
   if (make_tmap_2d(&ta, dy, P, g.Cout, g.ldy, 32, true)) return 1;
-  if (g.stride == 2) {
+  if (g.stride == 2 && g_s2_direct) {
+    if (make_tmap_nhwc(&tb, x, g.N, g.H, g.W, g.Cin, g.ldx, bw, bh, 1, true, 2)) return 1;
+  } else if (g.stride == 2) {
     if (!ws) { set_error("conv_wgrad_tf32: stride-2 path needs workspace"); return 1; }
     if (int e = rih_parity_stack(x, g.ldx, ws, g.N, g.H, g.W, g.Cin, s)) return e;
     if (make_tmap_nhwc(&tb, ws, 4 * g.N, g.H / 2, g.W / 2, g.Cin, g.Cin, bw, bh, 1, true)) return 1;
   } else {
     if (make_tmap_nhwc(&tb, x, g.N, g.H, g.W, g.Cin, g.ldx, bw, bh, 1, true)) return 1;
   }
-  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, 0, g.stride == 2 ? g.N : 0, cin_pad};
+  ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, 0, g.stride == 2 ? (g_s2_direct ? -1 : g.N) : 0, cin_pad};
   int num_kb = P / BK, splits, kps;
   plan_splitk(ep, g.Cout, Nn, BN, num_kb, 1, splits, kps, s, Ngrid);
   const CUtensorMap* cmap = nullptr;

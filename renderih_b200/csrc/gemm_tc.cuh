@@ -99,6 +99,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
@@ -243,6 +247,8 @@ struct ConvTcGeom {
   int H, W, Ho, Wo;        // input / output spatial size (stride 1 only)
   int tile_h;              // fwd/dgrad: rows of the 128-pixel tile (tile_w == full width); tile images = 128/(tile_w*tile_h)
   int s2_images;           // > 0: stride-2 convolution reading the parity-stacked input [4*N, H/2, W/2, C]; value = N
+                           // -1 : stride-2 convolution reading the input IN PLACE through a tensor map with element strides {1, 2, 2, 1}
+                           //      (the TMA unit fetches every second pixel of a box): coordinates are plain input pixels, no copy of the input
   int cin_pad;             // wgrad: columns per tap in the (virtual) N tile grid = ceil(Cin / BN) * BN (== Cin when BN divides Cin)
 };
 // stride 2: input row 2*o + r - pad = 2*(o + shift) + parity
@@ -266,7 +272,9 @@ struct ConvFwdProducer {
     const int r = tap / g.S, s = tap - r * g.S;
     const int P = g.Ho * g.Wo;
     const int n = m0 / P, oh0 = (m0 - n * P) / g.Wo;
-    if (g.s2_images > 0) {
+    if (g.s2_images < 0) {
+      tma_load_4d(sa, ta, c0, s - g.pad, 2 * oh0 + r - g.pad, n, bar);
+    } else if (g.s2_images > 0) {
       int ph, dh, pw, dw_;
       s2_tap(r, g.pad, ph, dh);
       s2_tap(s, g.pad, pw, dw_);
@@ -295,6 +303,26 @@ struct ConvDgradProducer {
     for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, tap * g.Cin + n0 + c * 32, co0, bar);
   }
 };
+// dgrad of a stride-2 convolution, one PARITY CLASS of input pixels (ih, iw) = (2 i + ph, 2 j + pw): only the taps r = ph + pad (mod 2),
+// s = pw + pad (mod 2) reach those pixels, from output pixel (i + dr, j + ds) with dr = (ph + pad - r) / 2.  Each class is a dense
+// stride-1 problem over the half-resolution grid: A = dY boxes shifted by (dr, ds), B = that tap's weights (MN-major chunks), K = ntaps * Cout;
+// the four classes together do a quarter of the multiply-adds of "zero-insert dY, then a stride-1 dgrad" and need no dilated copy.
+template <int BN>
+struct ConvDgradS2Producer {
+  ConvTcGeom g;            // H, W = half-resolution grid of the class (= Ho, Wo of the convolution); tile_h as usual
+  int ntaps;
+  int tap[4], dr[4], ds[4];
+  __device__ __forceinline__ void set_policy(unsigned long long) {}
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+    const int cpb = (g.Cout + BK - 1) / BK;
+    const int ti = kb / cpb, co0 = (kb - ti * cpb) * BK;
+    const int P = g.H * g.W;
+    const int n = m0 / P, i0 = (m0 - n * P) / g.W;
+    tma_load_4d(sa, ta, co0, ds[ti], i0 + dr[ti], n, bar);
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, tap[ti] * g.Cin + n0 + c * 32, co0, bar);
+  }
+};
 // wgrad: A = dY as MN-major chunks {32 co, 32 pixels}, B = shifted input boxes of 32 pixels as MN-major chunks {32 c, 32 pixels}.
 // The N axis enumerates (tap, channel) in cin_pad-wide groups; every 32-column chunk of the N tile finds its OWN tap, so a tile may span
 // several taps (Cin = 64: a 256-wide tile covers 4 taps and the dY tile is fetched 3 times instead of 9).
@@ -317,7 +345,8 @@ struct ConvWgradProducer {
       if (tap >= taps) { tap = 0; cbase = g.cin_pad + 64; }      // beyond the last tap: a channel coordinate outside the tensor -> the TMA unit zero-fills
       const int r = tap / g.S, s = tap - r * g.S;
       int cw = ow + s - g.pad, ch = oh + r - g.pad, cn = n;
-      if (g.s2_images > 0) {
+      if (g.s2_images < 0) { cw = 2 * ow + s - g.pad; ch = 2 * oh + r - g.pad; }
+      else if (g.s2_images > 0) {
         int ph, dh, pw, dw_;
         s2_tap(r, g.pad, ph, dh);
         s2_tap(s, g.pad, pw, dw_);
@@ -756,6 +785,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
               const int hh = ep.batch_heads & 0x3FFFFFFF;
               if (ep.batch_heads & (1 << 30)) tma_store_4d(&tmap_c, buf, nb, m0, z, 0);     // score matrix [B*H][M][N]
               else tma_store_4d(&tmap_c, buf, nb, z % hh, m0, z / hh);                        // head slice of a token matrix
+            } else if (ep.s2_w2) {           // stride-2 dgrad parity class: rows (n, i, j) -> input pixels (2 i + ph, 2 j + pw), element-strided 4-D map
+              const int P2 = ep.s2_h2 * ep.s2_w2;
+              const int n_ = m0 / P2, i0 = (m0 - n_ * P2) / ep.s2_w2;
+              if (ep.mode == 0) tma_store_4d(&tmap_c, buf, nb, ep.s2_pw, 2 * i0 + ep.s2_ph, n_);
+              else tma_reduce_add_4d(&tmap_c, buf, nb, ep.s2_pw, 2 * i0 + ep.s2_ph, n_);
             } else if (ep.nv_pad) {
               if (ep.mode == 0) tma_store_3d(&tmap_c, buf, sc0, sc1, m0);
               else tma_reduce_add_3d(&tmap_c, buf, sc0, sc1, m0);
@@ -813,7 +847,9 @@ EncodeTiledFn get_encode_fn();
 // 2-D fp32 tensor map over a row-major [rows, cols] matrix with row stride ld (elements); box = {32 cols, box_rows}.
 int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows, bool atom32 = false);
 // 4-D fp32 tensor map over an NHWC tensor [N,H,W,C] with pixel stride ld; box = {32 channels, bw, bh, bn}.
-int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int C, long long ld, int bw, int bh, int bn, bool atom32);
+// estride = 2: the box visits every second pixel in W and H (stride-2 convolutions read / write the full-resolution tensor in place);
+// bw / bh stay the numbers of pixels FETCHED
+int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int C, long long ld, int bw, int bh, int bn, bool atom32, int estride = 1);
 // overlapping-stride view of the zero-bordered NHWC4 stem input (see StemFwdProducer); box = {32, box_ow, 1, 1}
 int make_tmap_stem(CUtensorMap* map, const float* base, int N, int Hp, int Wp, int Wo, int box_ow, bool atom32);
 

@@ -170,7 +170,7 @@ RIH_API int rih_bn_colstats(const float* x, int ld, int M, int C, double* ws, cu
 __global__ void __launch_bounds__(256)
 bn_forward_kernel(const float* __restrict__ x, int ldx, const double* __restrict__ stats, long long M, int C4, float eps, float momentum,
                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ res, int ldr,
-                  float* __restrict__ y, int ldy, int relu, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                  float* __restrict__ y, int ldy, int relu, unsigned char* __restrict__ relu_mask, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                   float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ tracked, int flags) {
   pdl_sync();
   const BnMap mp = bn_map(C4);
@@ -211,17 +211,22 @@ bn_forward_kernel(const float* __restrict__ x, int ldx, const double* __restrict
       const float4 q = ld4(res + r * ldr + c, hint);
       o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
     }
-    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (relu) {
+      // one byte per channel quad records which of the four outputs passed the ReLU: the backward passes of a residual block read it
+      // (1/16 of the bytes) instead of the whole forward output
+      if (relu_mask) relu_mask[r * C4 + mp.q] = (unsigned char)((o.x > 0.f ? 1 : 0) | (o.y > 0.f ? 2 : 0) | (o.z > 0.f ? 4 : 0) | (o.w > 0.f ? 8 : 0));
+      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
     *reinterpret_cast<float4*>(y + r * ldy + c) = o;
   }
 }
 // reference: torch.nn.BatchNorm2d forward (torchvision ResNet blocks; models/encoder.py:54; models/model_zoo/__init__.py:57,66)
 RIH_API int rih_bn_forward(const float* x, int ldx, const double* stats, long long M, int C, float eps, float momentum,
-                           const float* gamma, const float* beta, const float* res, int ldr, float* y, int ldy, int relu,
+                           const float* gamma, const float* beta, const float* res, int ldr, float* y, int ldy, int relu, unsigned char* relu_mask,
                            float* mean_out, float* rstd_out, float* running_mean, float* running_var, long long* tracked, cudaStream_t s) {
   RIH_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (!res || ldr % 4 == 0), "bn_forward: needs C,ld %% 4 == 0");
   RIH_REQUIRE(M > 0 && (stats || (running_mean && running_var)), "bn_forward: eval mode needs the running statistics");
-  launch_k(bn_forward_kernel, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, x, ldx, stats, M, C / 4, eps, momentum, gamma, beta, res, ldr, y, ldy, relu,
+  launch_k(bn_forward_kernel, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, x, ldx, stats, M, C / 4, eps, momentum, gamma, beta, res, ldr, y, ldy, relu, relu_mask,
                                                           mean_out, rstd_out, running_mean, running_var, tracked, bn_flags());
   return check_launch("bn_forward");
 }
@@ -229,7 +234,7 @@ RIH_API int rih_bn_forward(const float* x, int ldx, const double* stats, long lo
 // backward pass 1: g = dy * (y > 0 if relu);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat
 // block = 8 channel quads (32 channels, float4 loads) x 32 row lanes; fp64 accumulation, one fp64 atomic pair per channel per CTA
 __global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, const unsigned char* __restrict__ relu_mask,
                      const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      int M, int C, int rows_per_cta, int relu, double* __restrict__ ws) {
@@ -245,8 +250,11 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __rest
     for (int r = r0 + ty; r < r1; r += 32) {
       float4 g = *reinterpret_cast<const float4*>(dy + (size_t)r * lddy + c);
       const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * ldx + c);
-      if (relu) {
-        // ReLU mask: from the saved output, or (no residual) recomputed from x with the forward's exact expression (bn_apply_kernel)
+      if (relu && relu_mask) {
+        const unsigned m4 = relu_mask[(size_t)r * (C >> 2) + (c >> 2)];
+        if (!(m4 & 1)) g.x = 0.f; if (!(m4 & 2)) g.y = 0.f; if (!(m4 & 4)) g.z = 0.f; if (!(m4 & 8)) g.w = 0.f;
+      } else if (relu) {
+        // ReLU mask: from the saved output, or (no residual) recomputed from x with the forward's exact expression (bn_forward_kernel)
         float4 yy;
         if (y) yy = *reinterpret_cast<const float4*>(y + (size_t)r * ldy + c);
         else { yy.x = (xv.x - mu.x) * rs.x * ga.x + be.x; yy.y = (xv.y - mu.y) * rs.y * ga.y + be.y;
@@ -273,7 +281,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __rest
 // backward pass 2 (the per-channel finalisation folded in): dx = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) [train] ; dres (+)= g ;
 // optional mask by (x>0) for Conv->ReLU->BN; the threads that own row 0 write dgamma / dbeta.  Same thread mapping as bn_forward_kernel.
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, const unsigned char* __restrict__ relu_mask,
                     const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ ws,
                     float* __restrict__ dx, int lddx, float* __restrict__ dres, int lddr, int dres_acc,
@@ -306,7 +314,11 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restr
     float g[4] = {g4.x, g4.y, g4.z, g4.w};
     const float4 x4 = ld4(x + r * ldx + c, hint);
     const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-    if (relu) {
+    if (relu && relu_mask) {
+      const unsigned m4 = relu_mask[r * C4 + mp.q];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (!(m4 & (1u << j))) g[j] = 0.f;
+    } else if (relu) {
       float yv[4];
       if (y) { const float4 y4 = *reinterpret_cast<const float4*>(y + r * ldy + c); yv[0] = y4.x; yv[1] = y4.y; yv[2] = y4.z; yv[3] = y4.w; }
       else {   // no residual: the forward output is a function of x alone -- same expression as bn_forward_kernel, so the mask is bit-identical
@@ -338,9 +350,9 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restr
   }
 }
 // ws: double[2C] (sum g, sum g*xhat; zeroed here)
-// y (the forward output) is only needed for the ReLU mask of a residual block; pass NULL otherwise and the mask is recomputed from x
-// (needs beta) -- one tensor read less in each of the two passes
-RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const float* x, int ldx,
+// ReLU mask of a residual block: relu_mask (one byte per channel quad, written by rih_bn_forward) or, without it, y (the forward output);
+// pass both NULL for non-residual blocks and the mask is recomputed from x (needs beta) -- one tensor read less in each of the two passes
+RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const unsigned char* relu_mask, const float* x, int ldx,
                        const float* mean, const float* rstd, const float* gamma, const float* beta,
                        float* dx, int lddx, float* dres, int lddr, int dres_acc,
                        float* dgamma, float* dbeta, int param_acc,
@@ -348,15 +360,15 @@ RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const
                        double* ws, cudaStream_t s) {
   RIH_REQUIRE(C % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0, "bn_bwd: needs C,ld %% 4 == 0");
   RIH_REQUIRE(M < (1ll << 31), "bn_bwd: too many rows");
-  RIH_REQUIRE(!relu || y || beta, "bn_bwd: the ReLU mask needs either the forward output or beta");
+  RIH_REQUIRE(!relu || y || relu_mask || beta, "bn_bwd: the ReLU mask needs the mask bytes, the forward output or beta");
   RIH_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, s));
   int gx = cdiv(C, 32);
   int target = cdiv(148 * 8, gx);
   int rows_per_cta = max(64, cdiv(M, target));
   dim3 grid(gx, cdiv(M, rows_per_cta));
-  launch_k(bn_bwd_reduce_kernel, grid, 256, 0, s, dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, (int)M, C, rows_per_cta, relu, ws);
+  launch_k(bn_bwd_reduce_kernel, grid, 256, 0, s, dy, lddy, y, ldy, relu_mask, x, ldx, mean, rstd, gamma, beta, (int)M, C, rows_per_cta, relu, ws);
   if (int e = check_launch("bn_bwd_reduce")) return e;
-  launch_k(bn_bwd_apply_kernel, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, dy, lddy, y, ldy, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx, dres, lddr, dres_acc,
+  launch_k(bn_bwd_apply_kernel, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, dy, lddy, y, ldy, relu_mask, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx, dres, lddr, dres_acc,
                                                             dgamma, dbeta, param_acc, M, C / 4, relu, training, mask_input, bn_flags());
   return check_launch("bn_bwd_apply");
 }

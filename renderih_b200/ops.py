@@ -1028,18 +1028,21 @@ class BatchNormFn(Function):
             res = _rows(res)
         # ONE launch: mean / rstd from the column sums (or the running statistics in eval mode), running-stat + num_batches_tracked
         # update, normalise (+res)(+relu)
+        # the ReLU mask of a residual block cannot be recomputed from x alone: the forward kernel records it as one byte per channel quad
+        # (1/16 of the output's bytes), which the two backward passes read instead of the output; otherwise it is recomputed from x
+        mask = torch.empty((M, C // 4), device=dev, dtype=torch.uint8) if (relu and res is not None and ctx.needs_input_grad[0]) else None
         call('rih_bn_forward', _p(x), _ld(x), _p(stats) if training else None, M, C, float(eps), float(momentum), _p(gamma), _p(beta),
-             _p(res), _ld(res) if res is not None else 0, _p(y), C, int(relu), _p(mean), _p(rstd), _p(rmean), _p(rvar),
+             _p(res), _ld(res) if res is not None else 0, _p(y), C, int(relu), _p(mask), _p(mean), _p(rstd), _p(rmean), _p(rvar),
              _p(tracked) if training else None, s)
-        # the ReLU mask of a residual block needs the output; otherwise it is recomputed from x in the backward kernels (one read less)
-        ctx.save_for_backward(x, gamma, mean, rstd, y if (relu and res is not None) else None)
+        ctx.save_for_backward(x, gamma, mean, rstd, mask)
         ctx.meta = (training, relu, mask_input, res is not None)
         ctx.beta_ref = beta
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, gamma, mean, rstd, y = ctx.saved_tensors
+        x, gamma, mean, rstd, mask = ctx.saved_tensors
+        y = None
         training, relu, mask_input, has_res = ctx.meta
         dy = _rows(dy.contiguous() if dy.stride(-1) != 1 else dy)
         M, C = x.shape
@@ -1051,7 +1054,7 @@ class BatchNormFn(Function):
         dgamma = tg if direct else torch.empty((C,), device=dev)
         dbeta = tb if direct else torch.empty((C,), device=dev)
         ws = torch.empty((2 * C,), device=dev, dtype=torch.float64)
-        call('rih_bn_bwd', _p(dy), _ld(dy), _p(y), C, _p(x), _ld(x), _p(mean), _p(rstd), _p(gamma), _p(ctx.beta_ref),
+        call('rih_bn_bwd', _p(dy), _ld(dy), _p(y), C, _p(mask), _p(x), _ld(x), _p(mean), _p(rstd), _p(gamma), _p(ctx.beta_ref),
              _p(dx), C, _p(dres), C, 0, _p(dgamma), _p(dbeta), int(direct), M, C, int(relu), int(training), int(mask_input),
              _p(ws), _stream())
         if direct:

@@ -426,8 +426,13 @@ def test_conv2d_tensor_core_tf32(ops, N, H, Cin, Cout, k):
 
 @pytest.mark.parametrize('N,H,Cin,Cout,k', [(4, 64, 128, 128, 3), (4, 32, 256, 256, 3), (8, 16, 512, 512, 3), (4, 64, 256, 512, 1), (4, 16, 1024, 2048, 1)])
 @pytest.mark.parametrize('mode', ['tf32', 'tf32x3'])
-def test_conv2d_stride2_tensor_core(ops, N, H, Cin, Cout, k, mode):
-    """stride-2 convolutions on the tcgen05 path (parity-stacked input for fwd/wgrad, zero-inserted dY for dgrad)."""
+@pytest.mark.parametrize('direct', [1, 0])
+def test_conv2d_stride2_tensor_core(ops, N, H, Cin, Cout, k, mode, direct):
+    """stride-2 convolutions on the tcgen05 path.  direct = 1: the tensors are addressed in place through element-strided tensor maps (forward,
+    weight gradient) and the input gradient runs as four parity-class GEMMs; direct = 0: parity-stacked input for fwd/wgrad, zero-inserted dY
+    for dgrad (the copy-based formulation kept for comparison)."""
+    from renderih_b200._lib import call
+    call('rih_set_s2_direct', direct)
     x = T(N, Cin, H, H)
     w = (torch.randn(Cout, Cin, k, k) * (Cin * k * k) ** -0.5).to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     xr = x.permute(0, 2, 3, 1).contiguous().reshape(N * H * H, Cin)
@@ -437,6 +442,7 @@ def test_conv2d_stride2_tensor_core(ops, N, H, Cin, Cout, k, mode):
         g_ours = grads(y, [x, w])
     finally:
         ops.set_gemm_mode('simt', 'simt')
+        call('rih_set_s2_direct', 1)
     yr = F.conv2d(x, w, None, stride=2, padding=k // 2).permute(0, 2, 3, 1).reshape(-1, Cout)
     tol = 3e-3 if mode == "tf32" else 1e-4
     assert rel(y, yr) < tol, rel(y, yr)
@@ -578,3 +584,29 @@ def test_preprocess_u8_matches_reference_loader_ops():
     assert torch.equal(out2[0].cpu(), ref[0]) and not torch.equal(out2[1].cpu(), ref[1])
     with pytest.raises(RuntimeError):
         preprocess_u8(torch.from_numpy(imgs))
+
+
+@pytest.mark.parametrize('mode', ['tf32', 'tf32x3'])
+def test_stem_conv_implicit_gemm(ops, mode):
+    """torchvision conv1 (7x7 / stride 2 / pad 3, 3 -> 64) as the tcgen05 implicit GEMM over the zero-bordered NHWC4 image (overlapping-stride
+    tensor map, no im2col buffer): forward, fused BatchNorm column statistics and the weight gradient against F.conv2d."""
+    N, H = 2, 256
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(N, 3, H, H, generator=g).to(DEV)
+    w = (torch.randn(64, 3, 7, 7, generator=g) * 147 ** -0.5).to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    ops.set_gemm_mode(mode, mode)
+    try:
+        assert ops.stem_supported(H, H)
+        stats = torch.empty(128, device=DEV, dtype=torch.float64)
+        y = ops.stem_conv(img, w, stats)
+        gw = grads(y, [w])[0]
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+    wr = w.detach().clone().requires_grad_(True)
+    yr = F.conv2d(img, wr, None, stride=2, padding=3).permute(0, 2, 3, 1).reshape(-1, 64)
+    tol = 3e-3 if mode == 'tf32' else 1e-4
+    assert y.shape == yr.shape
+    assert rel(y, yr) < tol, rel(y, yr)
+    assert rel(gw, grads(yr, [wr])[0]) < tol, rel(gw, grads(yr, [wr])[0])
+    ref_s = torch.cat([y.double().sum(0), (y.double() ** 2).sum(0)])
+    assert rel(stats, ref_s) < 1e-6, rel(stats, ref_s)
