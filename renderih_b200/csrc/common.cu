@@ -6,6 +6,7 @@ static thread_local char g_err[1024] = "";
 int g_pdl = 0;
 int g_reverse = 0;
 int g_l2_hints = 0;
+int g_kb_rotate = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -60,6 +61,10 @@ RIH_API int rih_set_traversal(int reverse) { rih::g_reverse = reverse ? 1 : 0; r
 // 1 = activations that a GEMM / 1x1 convolution / BatchNorm pass streams through once are loaded with the L2 evict-first priority, so that they do
 // not displace the previous kernel's output (which the next kernel is about to read) from the L2.  Scheduling only.
 // 1 (default) = element-wise kernels launched on a CTA-capped stream (rih_set_stream_cta_limit) use a quarter of their usual grid.  Scheduling only.
+// 1 = every output tile of the tensor-core GEMM / convolution kernels starts its k loop at a tile-dependent k-block and wraps around, so
+// that concurrently running CTAs do not all fetch the same 128-byte slice of their rows at the same time.  Results agree up to fp32
+// summation order inside the tensor core accumulation.
+RIH_API int rih_set_k_rotation(int on) { rih::g_kb_rotate = on ? 1 : 0; return 0; }
 RIH_API int rih_set_ew_cap(int on) { rih::g_ew_cap = on ? 1 : 0; return 0; }
 
 RIH_API int rih_set_l2_hints(int on) { rih::g_l2_hints = on ? 1 : 0; return 0; }

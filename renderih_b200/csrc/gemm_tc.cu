@@ -168,6 +168,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep,
                       int kb_per_split, cudaStream_t s, const CUtensorMap* c_map = nullptr) {
   ep.scale = g_scale;
   ep.reverse = g_reverse;
+  ep.kb_rotate = g_kb_rotate;
   ep.a_policy = g_l2_hints ? 1ull : 0ull;
   if (g_nsplit == 3) return launch_one<BN, A_MN, B_MN, Producer, 3>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s, c_map);
   if (g_nsplit == 2 && g_persistent) return launch_one<BN, A_MN, B_MN, Producer, 2>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s, c_map);
