@@ -19,19 +19,20 @@ void set_error(const char* fmt, ...) {
 // concurrently with the latency-bound token decoder leaves the remaining SMs / thread slots to it.  Persistent GEMM grids are capped to `ctas`
 // CTAs; element-wise kernels on such a stream launch a quarter of their usual CTAs per SM (ew_ctas), so that a 448-thread GEMM CTA of the
 // decoder always finds thread slots next to them instead of waiting for a wave of 8 x 256-thread CTAs per SM to drain.
-static cudaStream_t g_cap_stream[4] = {nullptr, nullptr, nullptr, nullptr};
-static int g_cap_ctas[4] = {0, 0, 0, 0};
+constexpr int CAP_SLOTS = 16;
+static cudaStream_t g_cap_stream[CAP_SLOTS] = {};
+static int g_cap_ctas[CAP_SLOTS] = {};
 int set_stream_cta_limit(cudaStream_t s, int ctas) {
-  for (int i = 0; i < 4; ++i) if (g_cap_stream[i] == s || g_cap_ctas[i] == 0) { g_cap_stream[i] = s; g_cap_ctas[i] = ctas > 0 ? ctas : 0; return 0; }
+  for (int i = 0; i < CAP_SLOTS; ++i) if (g_cap_stream[i] == s || g_cap_ctas[i] == 0) { g_cap_stream[i] = s; g_cap_ctas[i] = ctas > 0 ? ctas : 0; return 0; }
   return 1;
 }
 int stream_cta_limit(cudaStream_t s, int num_sms) {
-  for (int i = 0; i < 4; ++i) if (g_cap_ctas[i] > 0 && g_cap_stream[i] == s) return g_cap_ctas[i] < num_sms ? g_cap_ctas[i] : num_sms;
+  for (int i = 0; i < CAP_SLOTS; ++i) if (g_cap_ctas[i] > 0 && g_cap_stream[i] == s) return g_cap_ctas[i] < num_sms ? g_cap_ctas[i] : num_sms;
   return num_sms;
 }
 int g_ew_cap = 1;
 long long ew_ctas(cudaStream_t s) {
-  if (g_ew_cap) for (int i = 0; i < 4; ++i) if (g_cap_ctas[i] > 0 && g_cap_stream[i] == s) return 148 * 4;
+  if (g_ew_cap) for (int i = 0; i < CAP_SLOTS; ++i) if (g_cap_ctas[i] > 0 && g_cap_stream[i] == s && g_cap_ctas[i] < 96) return 148 * 4;
   return 148 * 16;
 }
 

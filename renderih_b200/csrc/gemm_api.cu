@@ -44,7 +44,7 @@ RIH_API int rih_set_gemm_mode(int conv_mode, int linear_mode) {
 // counterpart: scheduling only, results are unchanged.)
 RIH_API int rih_set_stream_cta_limit(cudaStream_t stream, int ctas) {
   RIH_REQUIRE(ctas >= 0, "set_stream_cta_limit: ctas must be >= 0");
-  RIH_REQUIRE(set_stream_cta_limit(stream, ctas) == 0, "set_stream_cta_limit: more than 4 capped streams");
+  RIH_REQUIRE(set_stream_cta_limit(stream, ctas) == 0, "set_stream_cta_limit: more than 16 capped streams");
   return 0;
 }
 // 1 (default) = GEMMs whose 128-wide tiling would occupy at most half of the SMs use 64-wide N tiles (twice the CTAs, half the serial work

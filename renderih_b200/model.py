@@ -52,11 +52,11 @@ def _cl(conv):
 
 
 # ============================================================================ encoder (models/encoder.py:21-173)
-def _conv_bn(x, conv, bn, N, H, W, training, relu=True, res=None, alias_input=False):
+def _conv_bn(x, conv, bn, N, H, W, training, relu=True, res=None, alias_input=False, link=None):
     """torchvision order Conv -> BN -> (+res) -> ReLU.  alias_input: returns (y, Ho, x_alias) -- see ops.conv2d."""
     k = conv.kernel_size[0]
     stats = torch.empty(2 * conv.out_channels, device=x.device, dtype=torch.float64) if training else None
-    y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], stats=stats, alias_input=alias_input)
+    y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], stats=stats, alias_input=alias_input, link=link)
     xa = None
     if alias_input:
         y, xa = y
@@ -156,13 +156,14 @@ class ResNetSimple(nn.Module):
         # the block input feeds conv1 AND the residual path: the residual path hangs off conv1's alias output, so its gradient is
         # accumulated by conv1's dgrad kernel instead of a separate add over the largest activations of the network
         fuse = tr and x.requires_grad
+        link = {} if (fuse and blk.downsample is not None) else None      # shortcut conv -> conv1: deferred stride-2 input gradient (ops.Conv2dFn)
         if fuse:
-            out, _, xa = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr, alias_input=True)
+            out, _, xa = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr, alias_input=True, link=link)
         else:
             (out, _), xa = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr), x
         out, Ho = _conv_bn(out, blk.conv2, blk.bn2, N, H, H, tr)
         if blk.downsample is not None:
-            identity, _ = _conv_bn(xa, blk.downsample[0], blk.downsample[1], N, H, H, tr, relu=False)
+            identity, _ = _conv_bn(xa, blk.downsample[0], blk.downsample[1], N, H, H, tr, relu=False, link=link)
         else:
             identity = xa
         out, _ = _conv_bn(out, blk.conv3, blk.bn3, N, Ho, Ho, tr, relu=True, res=identity)
@@ -281,6 +282,11 @@ class HandStreams:
         if key not in cls._cache:
             prio = int(os.environ.get('RIH_HAND_PRIORITY', '-1'))      # -1: the (latency-bound) hand branches are scheduled ahead of concurrent convolution work
             cls._cache[key] = (torch.cuda.Stream(device=device, priority=prio), torch.cuda.Stream(device=device, priority=prio))
+            ctas = int(os.environ.get('RIH_HAND_CTAS', '0'))             # > 0: cap the persistent GEMM grids of each hand branch (several tiles per CTA amortise the
+            if ctas > 0:                                               # per-CTA prologue and leave SMs to the other branches); 0 = uncapped
+                from ._lib import call
+                for st in cls._cache[key]:
+                    call('rih_set_stream_cta_limit', st.cuda_stream, ctas)
             try:      # parameters shared by both hands accumulate gradients from two streams by design; silence torch's advisory
                 torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
             except Exception:
@@ -329,7 +335,7 @@ def start_side(device, which, fn):
     side streams are disabled: then fn is deferred to the join point, i.e. the sequential order)."""
     st = GridStreams.get(device)
     if st is None:
-        return ('deferred', fn)
+        return ['deferred', fn]
     s = st[which]
     s.wait_stream(torch.cuda.current_stream(device))
     ops.note_stream(s)
@@ -343,7 +349,9 @@ def start_side(device, which, fn):
 def join_side(handle):
     """Make the CURRENT stream wait for a `start_side` branch and hand over its result."""
     if handle[0] == 'deferred':
-        return handle[1]()
+        if len(handle) == 2:                 # evaluate once, hand the same result to every joiner
+            handle += (handle[1](),)
+        return handle[2]
     _, out, ev = handle
     cur = torch.cuda.current_stream()
     cur.wait_event(ev)
@@ -504,7 +512,16 @@ class img_feat_to_grid(nn.Module):
         self.proj = _cl(nn.Conv2d(img_f_dim, grid_f_dim, kernel_size=patch, stride=patch))
         self.self_attn = SelfAttn(grid_f_dim, n_heads=n_heads, hid_dim=grid_f_dim, dropout=dropout)
 
-    def forward(self, img, B):
+    def patches(self, img, B):
+        """The patch matrix both hands' grid encoders of a level read (kernel == stride: patches are disjoint, im2col is a pure re-ordering),
+        or None when the convolution path is taken."""
+        x, H = img
+        p = self.proj.stride[0]
+        if p > 1 and x.shape[1] % 4 == 0:
+            return ops.patchify(x, B, H, H, p)
+        return None
+
+    def forward(self, img, B, patches=None):
         x, H = img
         assert H == self.img_size
         G = self.grid_size * self.grid_size
@@ -512,7 +529,8 @@ class img_feat_to_grid(nn.Module):
         if p > 1 and x.shape[1] % 4 == 0:
             # kernel == stride: patches are disjoint, so im2col is a pure re-ordering and the conv is ONE dense GEMM
             w2d = self.proj.weight.permute(0, 2, 3, 1).reshape(self.proj.weight.shape[0], -1)   # view of the channels_last weight
-            g = ops.linear(ops.patchify(x, B, H, H, p), w2d, self.proj.bias, relu=True)
+            P = patches if patches is not None else ops.patchify(x, B, H, H, p)
+            g = ops.linear(P, w2d, self.proj.bias, relu=True)
         else:
             g = ops.conv2d(x, self.proj.weight, self.proj.bias, B, H, H, stride=p, pad=0, relu=True)
         g = ops.posemb(g, self.position_embeddings.weight, B, G, 1)
@@ -625,8 +643,9 @@ class DualGraphLayer(nn.Module):
         V = self.verts_num
         # the image-grid tokens (patch GEMM + position embedding + a 64-token SelfAttn, ~14 launches per hand) depend only on the feature map:
         # they start on their own streams now and run beside the 28-launch graph-convolution chains of the two hands
-        gl = start_side(Lf.device, 0, lambda: self.img_ex_left.encoder(img_f, B))
-        gr = start_side(Lf.device, 1, lambda: self.img_ex_right.encoder(img_f, B))
+        gp = start_side(Lf.device, 0, lambda: self.img_ex_left.encoder.patches(img_f, B))      # one patch matrix per level, shared by both hands
+        gl = start_side(Lf.device, 0, lambda: self.img_ex_left.encoder(img_f, B, patches=join_side(gp)))
+        gr = start_side(Lf.device, 1, lambda: self.img_ex_right.encoder(img_f, B, patches=join_side(gp)))
         Lf, Rf = run_hands(Lf.device, lambda: self.img_ex_left(img_f, self.graph_left(Lf, B, V), B, V, grid=join_side(gl)),
                            lambda: self.img_ex_right(img_f, self.graph_right(Rf, B, V), B, V, grid=join_side(gr)))
         return self.attn(Lf, Rf, B, V)

@@ -610,3 +610,38 @@ def test_stem_conv_implicit_gemm(ops, mode):
     assert rel(gw, grads(yr, [wr])[0]) < tol, rel(gw, grads(yr, [wr])[0])
     ref_s = torch.cat([y.double().sum(0), (y.double() ** 2).sum(0)])
     assert rel(stats, ref_s) < 1e-6, rel(stats, ref_s)
+
+
+def test_bottleneck_with_stride2_shortcut_tensor_core_matches_exact(ops):
+    """A ResNet bottleneck whose shortcut is a 1x1 / stride-2 convolution (layer2[0]), train mode: the tensor-core path (3xTF32; direct stride-2
+    convolutions, the shortcut's input gradient deferred into conv1's backward and reduce-added through an element-strided store, ReLU bitmask
+    of the residual BatchNorm, multi-tap wgrad tiles) against the exact-fp32 kernels -- output, input gradient and every parameter gradient."""
+    from renderih_b200.model import ResNetSimple
+    torch.manual_seed(0)
+    enc = ResNetSimple('resnet50', aux_heads=False).to(DEV).train()
+    blk = enc.resnet.layer2[0]
+    N, H = 4, 64
+    x0 = (torch.randn(N * H * H, 256, device=DEV) * 0.5)
+    res = {}
+    for mode in ('simt', 'tf32x3'):
+        for p in blk.parameters():
+            p.grad = None
+        for m in blk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.reset_running_stats()
+        x = x0.clone().requires_grad_(True)
+        ops.set_gemm_mode(mode, mode)
+        try:
+            y, Ho = enc._bottleneck(blk, x, N, H)
+            g = torch.Generator(device='cpu').manual_seed(1)
+            wgt = torch.randn(y.shape, generator=g).to(DEV)
+            (y * wgt).sum().backward()
+        finally:
+            ops.set_gemm_mode('simt', 'simt')
+        res[mode] = (y.detach().clone(), x.grad.clone(), {k: p.grad.clone() for k, p in blk.named_parameters()})
+    assert Ho == 32
+    assert rel(res['tf32x3'][0], res['simt'][0]) < 2e-4, rel(res['tf32x3'][0], res['simt'][0])
+    assert rel(res['tf32x3'][1], res['simt'][1]) < 5e-4, rel(res['tf32x3'][1], res['simt'][1])
+    for k, gref in res['simt'][2].items():
+        e = rel(res['tf32x3'][2][k], gref)
+        assert e < 1e-3, (k, e)
