@@ -232,51 +232,50 @@ RIH_API int rih_bn_forward(const float* x, int ldx, const double* stats, long lo
 }
 
 // backward pass 1: g = dy * (y > 0 if relu);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat
-// block = 8 channel quads (32 channels, float4 loads) x 32 row lanes; fp64 accumulation, one fp64 atomic pair per channel per CTA
+// Same thread mapping as the element-wise passes (a thread keeps one channel quad, consecutive threads read consecutive quads: whole rows are
+// read contiguously -- the previous 32-channel-column blocking fetched 128 bytes out of every 1 KB row per CTA and ran at 4.2 TB/s).  Per-thread
+// fp64 accumulators, merged per CTA through shared-memory fp64 atomics (2 C doubles of dynamic shared memory), then one global fp64 atomic
+// per channel and CTA.
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, const unsigned char* __restrict__ relu_mask,
                      const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                     int M, int C, int rows_per_cta, int relu, double* __restrict__ ws) {
+                     long long M, int C4, int relu, double* __restrict__ ws, int flags) {
   pdl_sync();
-  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  const int c = blockIdx.x * 32 + tx * 4;
-  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
-  double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
-  if (c < C) {
-    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
-    float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), be = ga;
-    if (relu && !y) { ga = *reinterpret_cast<const float4*>(gamma + c); be = *reinterpret_cast<const float4*>(beta + c); }
-    for (int r = r0 + ty; r < r1; r += 32) {
-      float4 g = *reinterpret_cast<const float4*>(dy + (size_t)r * lddy + c);
-      const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * ldx + c);
-      if (relu && relu_mask) {
-        const unsigned m4 = relu_mask[(size_t)r * (C >> 2) + (c >> 2)];
-        if (!(m4 & 1)) g.x = 0.f; if (!(m4 & 2)) g.y = 0.f; if (!(m4 & 4)) g.z = 0.f; if (!(m4 & 8)) g.w = 0.f;
-      } else if (relu) {
-        // ReLU mask: from the saved output, or (no residual) recomputed from x with the forward's exact expression (bn_forward_kernel)
-        float4 yy;
-        if (y) yy = *reinterpret_cast<const float4*>(y + (size_t)r * ldy + c);
-        else { yy.x = (xv.x - mu.x) * rs.x * ga.x + be.x; yy.y = (xv.y - mu.y) * rs.y * ga.y + be.y;
-               yy.z = (xv.z - mu.z) * rs.z * ga.z + be.z; yy.w = (xv.w - mu.w) * rs.w * ga.w + be.w; }
-        if (!(yy.x > 0.f)) g.x = 0.f; if (!(yy.y > 0.f)) g.y = 0.f; if (!(yy.z > 0.f)) g.z = 0.f; if (!(yy.w > 0.f)) g.w = 0.f;
-      }
-      s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
-      sx[0] += (double)g.x * ((xv.x - mu.x) * rs.x); sx[1] += (double)g.y * ((xv.y - mu.y) * rs.y);
-      sx[2] += (double)g.z * ((xv.z - mu.z) * rs.z); sx[3] += (double)g.w * ((xv.w - mu.w) * rs.w);
-    }
-  }
-  __shared__ double sh[2][32][33];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { sh[0][ty][tx * 4 + i] = s[i]; sh[1][ty][tx * 4 + i] = sx[i]; }
+  extern __shared__ double bn_sh[];          // [2 * C]
+  const int C = C4 * 4;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) bn_sh[i] = 0.0;
   __syncthreads();
-  if (threadIdx.x < 64) {
-    const int which = threadIdx.x >> 5, col = threadIdx.x & 31;
-    double acc = 0.0;
-    for (int i = 0; i < 32; ++i) acc += sh[which][i][col];
-    const int cc = blockIdx.x * 32 + col;
-    if (cc < C) atomicAdd(ws + which * C + cc, acc);
+  const BnMap mp = bn_map(C4);
+  const int c = mp.q * 4;
+  const int hint = flags & 2;
+  double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+  float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), be = ga;
+  if (relu && !y && !relu_mask) { ga = *reinterpret_cast<const float4*>(gamma + c); be = *reinterpret_cast<const float4*>(beta + c); }
+  for (long long rr = mp.r0; rr < M; rr += mp.rstride) {
+    const long long r = (flags & 1) ? M - 1 - rr : rr;
+    float4 g = ld4(dy + r * lddy + c, hint);
+    const float4 xv = ld4(x + r * ldx + c, 0);          // x is read again by the apply pass right after: keep it in the L2
+    if (relu && relu_mask) {
+      const unsigned m4 = relu_mask[r * C4 + mp.q];
+      if (!(m4 & 1)) g.x = 0.f; if (!(m4 & 2)) g.y = 0.f; if (!(m4 & 4)) g.z = 0.f; if (!(m4 & 8)) g.w = 0.f;
+    } else if (relu) {
+      // ReLU mask: from the saved output, or (no residual) recomputed from x with the forward's exact expression (bn_forward_kernel)
+      float4 yy;
+      if (y) yy = *reinterpret_cast<const float4*>(y + r * ldy + c);
+      else { yy.x = (xv.x - mu.x) * rs.x * ga.x + be.x; yy.y = (xv.y - mu.y) * rs.y * ga.y + be.y;
+             yy.z = (xv.z - mu.z) * rs.z * ga.z + be.z; yy.w = (xv.w - mu.w) * rs.w * ga.w + be.w; }
+      if (!(yy.x > 0.f)) g.x = 0.f; if (!(yy.y > 0.f)) g.y = 0.f; if (!(yy.z > 0.f)) g.z = 0.f; if (!(yy.w > 0.f)) g.w = 0.f;
+    }
+    s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
+    sx[0] += (double)g.x * ((xv.x - mu.x) * rs.x); sx[1] += (double)g.y * ((xv.y - mu.y) * rs.y);
+    sx[2] += (double)g.z * ((xv.z - mu.z) * rs.z); sx[3] += (double)g.w * ((xv.w - mu.w) * rs.w);
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { atomicAdd(&bn_sh[c + i], s[i]); atomicAdd(&bn_sh[C + c + i], sx[i]); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) { const double v = bn_sh[i]; if (v != 0.0) atomicAdd(ws + i, v); }
 }
 // backward pass 2 (the per-channel finalisation folded in): dx = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) [train] ; dres (+)= g ;
 // optional mask by (x>0) for Conv->ReLU->BN; the threads that own row 0 write dgamma / dbeta.  Same thread mapping as bn_forward_kernel.
@@ -362,11 +361,9 @@ RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const
   RIH_REQUIRE(M < (1ll << 31), "bn_bwd: too many rows");
   RIH_REQUIRE(!relu || y || relu_mask || beta, "bn_bwd: the ReLU mask needs the mask bytes, the forward output or beta");
   RIH_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, s));
-  int gx = cdiv(C, 32);
-  int target = cdiv(148 * 8, gx);
-  int rows_per_cta = max(64, cdiv(M, target));
-  dim3 grid(gx, cdiv(M, rows_per_cta));
-  launch_k(bn_bwd_reduce_kernel, grid, 256, 0, s, dy, lddy, y, ldy, relu_mask, x, ldx, mean, rstd, gamma, beta, (int)M, C, rows_per_cta, relu, ws);
+  RIH_REQUIRE(2 * C * (int)sizeof(double) <= 48 * 1024, "bn_bwd: C = %d too wide for the shared-memory reduction", C);
+  launch_k(bn_bwd_reduce_kernel, bn_grid(M, C / 4, 256, 148 * 8), 256, 2 * C * sizeof(double), s, dy, lddy, y, ldy, relu_mask, x, ldx, mean, rstd, gamma, beta,
+           M, C / 4, relu, ws, bn_flags());
   if (int e = check_launch("bn_bwd_reduce")) return e;
   launch_k(bn_bwd_apply_kernel, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, dy, lddy, y, ldy, relu_mask, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx, dres, lddr, dres_acc,
                                                             dgamma, dbeta, param_acc, M, C / 4, relu, training, mask_input, bn_flags());
