@@ -209,7 +209,14 @@ RIH_API int rih_conv2d_dgrad(const float* dy, const float* w, float* dx, const i
       return tc::gemm_tf32(dy, g.ldy, 0, w, g.Cin, 1, ep, (int)M, g.Cin, g.Cout, 0, stream);
     return launch_gemm_simt(a, b, ep, (int)M, g.Cin, g.Cout, 0, stream, "conv1x1_dgrad");
   }
-  if (use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(w, g.Cin) && tc::conv_tc_supported(g, 1) && (g.stride == 1 || ws || tc::s2_direct())) return tc::conv_dgrad_tf32(dy, w, ep, g, ws, stream);
+  // Stride 2 + accumulate: the direct formulation would have to reduce-add through an element-strided tensor map, which did not reproduce the
+  // exact-fp32 result on hardware (9e-2 off in the bottleneck test of round 2) -- stores through such maps are verified, reductions are not used.
+  // No model of this package accumulates into a stride-2 input gradient; the call is served by the copy-based path (needs ws) or the SIMT kernel.
+  const bool s2_acc = g.stride == 2 && accumulate && tc::s2_direct() && !ws;
+  if (!s2_acc && use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(w, g.Cin) && tc::conv_tc_supported(g, 1) && (g.stride == 1 || ws || tc::s2_direct())) {
+    if (g.stride == 2 && accumulate && ws) { tc::set_s2_direct(0); int rc = tc::conv_dgrad_tf32(dy, w, ep, g, ws, stream); tc::set_s2_direct(1); return rc; }
+    return tc::conv_dgrad_tf32(dy, w, ep, g, ws, stream);
+  }
   ConvDgradA a{dy, g, (int)M, is_vec_ok(dy, g.ldy) && (g.Cout % 4 == 0)};
   ConvDgradB b{w, g, g.Cin, is_vec_ok(w, g.Cin)};
   return launch_gemm_simt(a, b, ep, (int)M, g.Cin, K, 0, stream, "conv2d_dgrad");

@@ -354,6 +354,7 @@ static int conv_dgrad_s2_direct(const float* dy, const float* w, Epilogue ep, co
   if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, 32, true)) return 1;
   if (make_tmap_nhwc(&tcm, ep.c, g.N, g.H, g.W, g.Cin, ep.ldc, W2, tile_h, tile_n, false, 2)) return 1;
   const int accumulate = ep.mode != 0;
+  if (accumulate) { set_error("conv_dgrad_s2_direct: accumulation through an element-strided map is not supported (use the copy-based path)"); return 1; }
   bool zeroed = false;
   for (int ph = 0; ph < 2; ++ph) for (int pw = 0; pw < 2; ++pw) {
     int rs[2], nr = 0, ss[2], ns = 0;

@@ -129,10 +129,13 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int 
 // Thread -> (channel quad, first row) mapping shared by the element-wise BatchNorm passes: the launch has a multiple of C/4 threads, so
 // a thread keeps ONE channel quad for its whole grid-stride loop and the per-channel terms are computed once per thread.
 struct BnMap { int q; long long r0, rstride; };
-// flags of the element-wise BatchNorm passes: bit 0 = walk the rows from the last to the first (rih_set_traversal), bit 1 = streamed inputs are
-// loaded with the evict-first priority (rih_set_l2_hints)
-__device__ __forceinline__ float4 ld4(const float* p, int hint) { return hint ? __ldcs(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p); }
-static inline int bn_flags() { return (g_reverse ? 1 : 0) | (g_l2_hints ? 2 : 0); }
+// HINT: streamed inputs of the element-wise BatchNorm passes are loaded with the evict-first priority (rih_set_l2_hints)
+// (compile-time switch: a run-time branch around every load kept the compiler from batching the loads of the unrolled row loop -- the
+// residual BatchNorm pass dropped from 5.8 to 4.6 TB/s)
+template <bool HINT> __device__ __forceinline__ float4 ld4(const float* p) {
+  if constexpr (HINT) return __ldcs(reinterpret_cast<const float4*>(p));
+  else return *reinterpret_cast<const float4*>(p);
+}
 __device__ __forceinline__ BnMap bn_map(int C4) {
   const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long T = (long long)gridDim.x * blockDim.x;
@@ -167,11 +170,12 @@ RIH_API int rih_bn_colstats(const float* x, int ld, int M, int C, double* ws, cu
 //                             unbiased variance, num_batches_tracked += 1 -- written once, by the threads that own row 0
 //   eval     (stats == NULL): from the running statistics
 // then y = (x - mean) * rstd * gamma + beta (+res) (relu).  mean / rstd are also stored for the backward pass.  C % 4 == 0, ld % 4 == 0.
+template <bool HINT>
 __global__ void __launch_bounds__(256)
 bn_forward_kernel(const float* __restrict__ x, int ldx, const double* __restrict__ stats, long long M, int C4, float eps, float momentum,
                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ res, int ldr,
                   float* __restrict__ y, int ldy, int relu, unsigned char* __restrict__ relu_mask, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                  float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ tracked, int flags) {
+                  float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ tracked) {
   pdl_sync();
   const BnMap mp = bn_map(C4);
   const int c = mp.q * 4, C = C4 * 4;
@@ -200,15 +204,13 @@ bn_forward_kernel(const float* __restrict__ x, int ldx, const double* __restrict
     *reinterpret_cast<float4*>(rstd_out + c) = make_float4(rs[0], rs[1], rs[2], rs[3]);
   }
   const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
-  const int hint = flags & 2;
-  for (long long rr = mp.r0; rr < M; rr += mp.rstride) {
-    const long long r = (flags & 1) ? M - 1 - rr : rr;
-    const float4 v = ld4(x + r * ldx + c, hint);
+  for (long long r = mp.r0; r < M; r += mp.rstride) {
+    const float4 v = ld4<HINT>(x + r * ldx + c);
     float4 o;
     o.x = (v.x - mu[0]) * rs[0] * g.x + b.x; o.y = (v.y - mu[1]) * rs[1] * g.y + b.y;
     o.z = (v.z - mu[2]) * rs[2] * g.z + b.z; o.w = (v.w - mu[3]) * rs[3] * g.w + b.w;
     if (res) {
-      const float4 q = ld4(res + r * ldr + c, hint);
+      const float4 q = ld4<HINT>(res + r * ldr + c);
       o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
     }
     if (relu) {
@@ -226,66 +228,70 @@ RIH_API int rih_bn_forward(const float* x, int ldx, const double* stats, long lo
                            float* mean_out, float* rstd_out, float* running_mean, float* running_var, long long* tracked, cudaStream_t s) {
   RIH_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (!res || ldr % 4 == 0), "bn_forward: needs C,ld %% 4 == 0");
   RIH_REQUIRE(M > 0 && (stats || (running_mean && running_var)), "bn_forward: eval mode needs the running statistics");
-  launch_k(bn_forward_kernel, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, x, ldx, stats, M, C / 4, eps, momentum, gamma, beta, res, ldr, y, ldy, relu, relu_mask,
-                                                          mean_out, rstd_out, running_mean, running_var, tracked, bn_flags());
+  if (g_l2_hints) launch_k(bn_forward_kernel<true>, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, x, ldx, stats, M, C / 4, eps, momentum, gamma, beta, res, ldr, y, ldy, relu,
+                           relu_mask, mean_out, rstd_out, running_mean, running_var, tracked);
+  else launch_k(bn_forward_kernel<false>, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, x, ldx, stats, M, C / 4, eps, momentum, gamma, beta, res, ldr, y, ldy, relu,
+                relu_mask, mean_out, rstd_out, running_mean, running_var, tracked);
   return check_launch("bn_forward");
 }
 
 // backward pass 1: g = dy * (y > 0 if relu);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat
-// Same thread mapping as the element-wise passes (a thread keeps one channel quad, consecutive threads read consecutive quads: whole rows are
-// read contiguously -- the previous 32-channel-column blocking fetched 128 bytes out of every 1 KB row per CTA and ran at 4.2 TB/s).  Per-thread
-// fp64 accumulators, merged per CTA through shared-memory fp64 atomics (2 C doubles of dynamic shared memory), then one global fp64 atomic
-// per channel and CTA.
+// block = 8 channel quads (32 channels, float4 loads) x 32 row lanes; fp64 accumulation, one fp64 atomic pair per channel per CTA
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, const unsigned char* __restrict__ relu_mask,
                      const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                     long long M, int C4, int relu, double* __restrict__ ws, int flags) {
+                     int M, int C, int rows_per_cta, int relu, double* __restrict__ ws) {
   pdl_sync();
-  extern __shared__ double bn_sh[];          // [2 * C]
-  const int C = C4 * 4;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) bn_sh[i] = 0.0;
-  __syncthreads();
-  const BnMap mp = bn_map(C4);
-  const int c = mp.q * 4;
-  const int hint = flags & 2;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int c = blockIdx.x * 32 + tx * 4;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
   double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
-  const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
-  float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), be = ga;
-  if (relu && !y && !relu_mask) { ga = *reinterpret_cast<const float4*>(gamma + c); be = *reinterpret_cast<const float4*>(beta + c); }
-  for (long long rr = mp.r0; rr < M; rr += mp.rstride) {
-    const long long r = (flags & 1) ? M - 1 - rr : rr;
-    float4 g = ld4(dy + r * lddy + c, hint);
-    const float4 xv = ld4(x + r * ldx + c, 0);          // x is read again by the apply pass right after: keep it in the L2
-    if (relu && relu_mask) {
-      const unsigned m4 = relu_mask[r * C4 + mp.q];
-      if (!(m4 & 1)) g.x = 0.f; if (!(m4 & 2)) g.y = 0.f; if (!(m4 & 4)) g.z = 0.f; if (!(m4 & 8)) g.w = 0.f;
-    } else if (relu) {
-      // ReLU mask: from the saved output, or (no residual) recomputed from x with the forward's exact expression (bn_forward_kernel)
-      float4 yy;
-      if (y) yy = *reinterpret_cast<const float4*>(y + r * ldy + c);
-      else { yy.x = (xv.x - mu.x) * rs.x * ga.x + be.x; yy.y = (xv.y - mu.y) * rs.y * ga.y + be.y;
-             yy.z = (xv.z - mu.z) * rs.z * ga.z + be.z; yy.w = (xv.w - mu.w) * rs.w * ga.w + be.w; }
-      if (!(yy.x > 0.f)) g.x = 0.f; if (!(yy.y > 0.f)) g.y = 0.f; if (!(yy.z > 0.f)) g.z = 0.f; if (!(yy.w > 0.f)) g.w = 0.f;
+  if (c < C) {
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), be = ga;
+    if (relu && !y) { ga = *reinterpret_cast<const float4*>(gamma + c); be = *reinterpret_cast<const float4*>(beta + c); }
+    for (int r = r0 + ty; r < r1; r += 32) {
+      float4 g = *reinterpret_cast<const float4*>(dy + (size_t)r * lddy + c);
+      const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * ldx + c);
+      if (relu && relu_mask) {
+        const unsigned m4 = relu_mask[(size_t)r * (C >> 2) + (c >> 2)];
+        if (!(m4 & 1)) g.x = 0.f; if (!(m4 & 2)) g.y = 0.f; if (!(m4 & 4)) g.z = 0.f; if (!(m4 & 8)) g.w = 0.f;
+      } else if (relu) {
+        // ReLU mask: from the saved output, or (no residual) recomputed from x with the forward's exact expression (bn_forward_kernel)
+        float4 yy;
+        if (y) yy = *reinterpret_cast<const float4*>(y + (size_t)r * ldy + c);
+        else { yy.x = (xv.x - mu.x) * rs.x * ga.x + be.x; yy.y = (xv.y - mu.y) * rs.y * ga.y + be.y;
+               yy.z = (xv.z - mu.z) * rs.z * ga.z + be.z; yy.w = (xv.w - mu.w) * rs.w * ga.w + be.w; }
+        if (!(yy.x > 0.f)) g.x = 0.f; if (!(yy.y > 0.f)) g.y = 0.f; if (!(yy.z > 0.f)) g.z = 0.f; if (!(yy.w > 0.f)) g.w = 0.f;
+      }
+      s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
+      sx[0] += (double)g.x * ((xv.x - mu.x) * rs.x); sx[1] += (double)g.y * ((xv.y - mu.y) * rs.y);
+      sx[2] += (double)g.z * ((xv.z - mu.z) * rs.z); sx[3] += (double)g.w * ((xv.w - mu.w) * rs.w);
     }
-    s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
-    sx[0] += (double)g.x * ((xv.x - mu.x) * rs.x); sx[1] += (double)g.y * ((xv.y - mu.y) * rs.y);
-    sx[2] += (double)g.z * ((xv.z - mu.z) * rs.z); sx[3] += (double)g.w * ((xv.w - mu.w) * rs.w);
   }
+  __shared__ double sh[2][32][33];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { atomicAdd(&bn_sh[c + i], s[i]); atomicAdd(&bn_sh[C + c + i], sx[i]); }
+  for (int i = 0; i < 4; ++i) { sh[0][ty][tx * 4 + i] = s[i]; sh[1][ty][tx * 4 + i] = sx[i]; }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) { const double v = bn_sh[i]; if (v != 0.0) atomicAdd(ws + i, v); }
+  if (threadIdx.x < 64) {
+    const int which = threadIdx.x >> 5, col = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int i = 0; i < 32; ++i) acc += sh[which][i][col];
+    const int cc = blockIdx.x * 32 + col;
+    if (cc < C) atomicAdd(ws + which * C + cc, acc);
+  }
 }
 // backward pass 2 (the per-channel finalisation folded in): dx = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) [train] ; dres (+)= g ;
 // optional mask by (x>0) for Conv->ReLU->BN; the threads that own row 0 write dgamma / dbeta.  Same thread mapping as bn_forward_kernel.
+template <bool HINT>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, const unsigned char* __restrict__ relu_mask,
                     const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ ws,
                     float* __restrict__ dx, int lddx, float* __restrict__ dres, int lddr, int dres_acc,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, int param_acc,
-                    long long M, int C4, int relu, int training, int mask_input, int flags) {
+                    long long M, int C4, int relu, int training, int mask_input) {
   pdl_sync();
   const BnMap mp = bn_map(C4);
   const int c = mp.q * 4, C = C4 * 4;
@@ -306,12 +312,10 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restr
       if (dbeta) dbeta[c + j] = param_acc ? dbeta[c + j] + sgv[j] : sgv[j];
     }
   }
-  const int hint = flags & 2;
-  for (long long rr = mp.r0; rr < M; rr += mp.rstride) {
-    const long long r = (flags & 1) ? M - 1 - rr : rr;
-    const float4 g4 = ld4(dy + r * lddy + c, hint);
+  for (long long r = mp.r0; r < M; r += mp.rstride) {
+    const float4 g4 = ld4<HINT>(dy + r * lddy + c);
     float g[4] = {g4.x, g4.y, g4.z, g4.w};
-    const float4 x4 = ld4(x + r * ldx + c, hint);
+    const float4 x4 = ld4<HINT>(x + r * ldx + c);
     const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
     if (relu && relu_mask) {
       const unsigned m4 = relu_mask[r * C4 + mp.q];
@@ -361,12 +365,16 @@ RIH_API int rih_bn_bwd(const float* dy, int lddy, const float* y, int ldy, const
   RIH_REQUIRE(M < (1ll << 31), "bn_bwd: too many rows");
   RIH_REQUIRE(!relu || y || relu_mask || beta, "bn_bwd: the ReLU mask needs the mask bytes, the forward output or beta");
   RIH_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, s));
-  RIH_REQUIRE(2 * C * (int)sizeof(double) <= 48 * 1024, "bn_bwd: C = %d too wide for the shared-memory reduction", C);
-  launch_k(bn_bwd_reduce_kernel, bn_grid(M, C / 4, 256, 148 * 8), 256, 2 * C * sizeof(double), s, dy, lddy, y, ldy, relu_mask, x, ldx, mean, rstd, gamma, beta,
-           M, C / 4, relu, ws, bn_flags());
+  int gx = cdiv(C, 32);
+  int target = cdiv(148 * 8, gx);
+  int rows_per_cta = max(64, cdiv(M, target));
+  dim3 grid(gx, cdiv(M, rows_per_cta));
+  launch_k(bn_bwd_reduce_kernel, grid, 256, 0, s, dy, lddy, y, ldy, relu_mask, x, ldx, mean, rstd, gamma, beta, (int)M, C, rows_per_cta, relu, ws);
   if (int e = check_launch("bn_bwd_reduce")) return e;
-  launch_k(bn_bwd_apply_kernel, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, dy, lddy, y, ldy, relu_mask, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx, dres, lddr, dres_acc,
-                                                            dgamma, dbeta, param_acc, M, C / 4, relu, training, mask_input, bn_flags());
+  if (g_l2_hints) launch_k(bn_bwd_apply_kernel<true>, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, dy, lddy, y, ldy, relu_mask, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx,
+                           dres, lddr, dres_acc, dgamma, dbeta, param_acc, M, C / 4, relu, training, mask_input);
+  else launch_k(bn_bwd_apply_kernel<false>, bn_grid(M, C / 4, 256, ew_ctas(s)), 256, 0, s, dy, lddy, y, ldy, relu_mask, x, ldx, mean, rstd, gamma, beta, ws, dx, lddx,
+                dres, lddr, dres_acc, dgamma, dbeta, param_acc, M, C / 4, relu, training, mask_input);
   return check_launch("bn_bwd_apply");
 }
 

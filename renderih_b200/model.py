@@ -52,11 +52,11 @@ def _cl(conv):
 
 
 # ============================================================================ encoder (models/encoder.py:21-173)
-def _conv_bn(x, conv, bn, N, H, W, training, relu=True, res=None, alias_input=False, link=None):
+def _conv_bn(x, conv, bn, N, H, W, training, relu=True, res=None, alias_input=False):
     """torchvision order Conv -> BN -> (+res) -> ReLU.  alias_input: returns (y, Ho, x_alias) -- see ops.conv2d."""
     k = conv.kernel_size[0]
     stats = torch.empty(2 * conv.out_channels, device=x.device, dtype=torch.float64) if training else None
-    y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], stats=stats, alias_input=alias_input, link=link)
+    y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], stats=stats, alias_input=alias_input)
     xa = None
     if alias_input:
         y, xa = y
@@ -156,14 +156,13 @@ class ResNetSimple(nn.Module):
         # the block input feeds conv1 AND the residual path: the residual path hangs off conv1's alias output, so its gradient is
         # accumulated by conv1's dgrad kernel instead of a separate add over the largest activations of the network
         fuse = tr and x.requires_grad
-        link = {} if (fuse and blk.downsample is not None) else None      # shortcut conv -> conv1: deferred stride-2 input gradient (ops.Conv2dFn)
         if fuse:
-            out, _, xa = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr, alias_input=True, link=link)
+            out, _, xa = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr, alias_input=True)
         else:
             (out, _), xa = _conv_bn(x, blk.conv1, blk.bn1, N, H, H, tr), x
         out, Ho = _conv_bn(out, blk.conv2, blk.bn2, N, H, H, tr)
         if blk.downsample is not None:
-            identity, _ = _conv_bn(xa, blk.downsample[0], blk.downsample[1], N, H, H, tr, relu=False, link=link)
+            identity, _ = _conv_bn(xa, blk.downsample[0], blk.downsample[1], N, H, H, tr, relu=False)
         else:
             identity = xa
         out, _ = _conv_bn(out, blk.conv3, blk.bn3, N, Ho, Ho, tr, relu=True, res=identity)

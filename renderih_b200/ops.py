@@ -855,10 +855,9 @@ class Conv2dFn(Function):
     """NHWC conv (+bias)(+relu) -- nn.Conv2d sites of models/encoder.py, torchvision resnet, img_attn.py:48"""
 
     @staticmethod
-    def forward(ctx, x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer, stats, alias_input=False, link=None):
+    def forward(ctx, x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer, stats, alias_input=False):
         x = _rows(x); _w_phys(_check(w, 'weight'))
         ctx.alias_input = alias_input
-        ctx.link = link       # shared dict of a residual block: the stride-2 1x1 shortcut convolution hands its input gradient to conv1's backward
         Cout, Cin, R, S = w.shape
         assert x.shape == (N * H * W, Cin), (x.shape, N, H, W, Cin)
         g, Ho, Wo = _geom(N, H, W, Cin, Cout, R, S, stride, pad, _ld(x), Cout)
@@ -885,15 +884,7 @@ class Conv2dFn(Function):
             dy = g_
         g, Ho, Wo = _geom(N, H, W, Cin, Cout, R, S, stride, pad, Cin, _ld(dy))
         dx = dw = db = None
-        link = ctx.link
-        defer = (link is not None and not ctx.alias_input and stride == 2 and R == 1 and S == 1 and ctx.needs_input_grad[0]
-                 and MODE['conv'] != 'simt' and _os.environ.get('RIH_S2_DIRECT', '1') != '0')
-        if defer:
-            # 1x1 / stride-2 shortcut: only every second pixel of every second row receives a gradient.  Instead of materialising a
-            # mostly-zero dx (which conv1's dgrad would then read back and accumulate onto), hand (dy, w, geometry) to conv1's backward:
-            # it writes its own dgrad first and this one is reduce-added onto the (2i, 2j) pixels through an element-strided store.
-            link['pending'] = (dy, w, g)
-        elif ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0]:
             acc = 0
             if d_alias is not None and d_alias.is_contiguous() and d_alias.shape == (N * H * W, Cin):
                 dx, acc = d_alias, 1      # accumulate onto the gradient that came in through the alias output (epilogue: TMA reduce-add)
@@ -902,9 +893,6 @@ class Conv2dFn(Function):
             call('rih_conv2d_dgrad', _p(dy), _p(w), _p(dx), g, acc, _p(_conv_ws(g, 1, dy.device)), s)
             if d_alias is not None and acc == 0:
                 dx = dx + d_alias
-            if link is not None and ctx.alias_input and 'pending' in link:
-                pdy, pw, pg = link.pop('pending')
-                call('rih_conv2d_dgrad', _p(pdy), _p(pw), _p(dx), pg, 1, None, s)
         elif d_alias is not None:
             dx = d_alias
         if ctx.needs_input_grad[1]:
@@ -924,14 +912,14 @@ class Conv2dFn(Function):
             else:
                 db = torch.empty((Cout,), device=dy.device, dtype=torch.float32)
                 call('rih_colsum', _p(dy), _ld(dy), dy.shape[0], Cout, _p(db), 0, s)
-        return dx, dw, db, None, None, None, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None, None
 
 
-def conv2d(x, w, b, N, H, W, stride=1, pad=0, relu=False, relu_masked_by_consumer=False, stats=None, alias_input=False, link=None):
+def conv2d(x, w, b, N, H, W, stride=1, pad=0, relu=False, relu_masked_by_consumer=False, stats=None, alias_input=False):
     """stats: optional float64 [2*Cout] buffer that receives the output's per-channel sum / sum of squares (fused BN statistics).
     alias_input: also return x as a second output; route every OTHER use of x through it and their gradients are accumulated by this
     convolution's dgrad kernel (no separate add pass over the activation gradient)."""
-    return Conv2dFn.apply(x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer, stats, alias_input, link)
+    return Conv2dFn.apply(x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer, stats, alias_input)
 
 
 class PatchifyFn(Function):
