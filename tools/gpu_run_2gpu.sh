@@ -3,6 +3,8 @@
 set +e
 O=gpurun_out
 mkdir -p $O
+python tools/debug_bottleneck.py > $O/r2_dbg_bneck2.log 2>&1
+python -m pytest tests/test_ops_gpu.py -m gpu -q -k bottleneck -p no:cacheprovider > $O/r2_pytest_bneck.log 2>&1; tail -3 $O/r2_pytest_bneck.log
 python -m pytest tests/test_train_gpu.py -m gpu -q -s -k two_rank -p no:cacheprovider > $O/r2_pytest_2gpu.log 2>&1
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29581 bench.py --gpus 2 --steps 10 --warmup 3 > $O/r2_bench_2gpu.json 2> $O/r2_bench_2gpu.err
 RIH_OVERLAP_ALLREDUCE=0 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29582 bench.py --gpus 2 --steps 10 --warmup 3 > $O/r2_bench_2gpu_single.json 2> $O/r2_bench_2gpu_single.err
