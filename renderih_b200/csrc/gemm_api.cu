@@ -14,6 +14,7 @@ void set_nsplit(int n);
 void set_narrow_small(int on);
 void set_wgrad_wide(int on);
 void set_s2_direct(int on);
+void set_tma_res(int on);
 int s2_direct();
 void set_acc_scale(float s);
 extern int g_stats_fused;
@@ -55,6 +56,7 @@ RIH_API int rih_set_narrow_tiles(int on) { tc::set_narrow_small(on); return 0; }
 // 1 (default) = stride-2 convolutions (forward, weight gradient, input gradient) address the full-resolution tensors in place through tensor
 // maps with element strides {1, 2, 2, 1}; the input gradient runs as four dense parity-class GEMMs.  0 = the copy-based formulation
 // (parity-stacked input for forward / wgrad, zero-inserted dY for dgrad; needs the rih_conv2d_workspace buffers).
+RIH_API int rih_set_tma_res(int on) { tc::set_tma_res(on); return 0; }
 RIH_API int rih_set_s2_direct(int on) { tc::set_s2_direct(on); return 0; }
 RIH_API int rih_set_wgrad_wide(int on) { tc::set_wgrad_wide(on); return 0; }
 static inline bool use_tc(int which) {
@@ -159,8 +161,10 @@ RIH_API int rih_conv2d_tc_supported(const int* geom, int which, int* supported) 
   return 0;
 }
 
+// eval-mode BatchNorm (+ residual + final ReLU) folded into the convolution's epilogue, see rih_conv2d_bn_eval_fwd
+struct ConvFold { const float* col_scale; const float* col_shift; int affine_post; const float* res; int ldres; int relu_post; };
 static int conv2d_fwd_impl(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, int relu, float* ws, double* stats,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const ConvFold* fold = nullptr);
 
 // `stats` (optional, double[2*Cout]): receives the per-channel sum and sum of squares of the stored output (the following
 // BatchNorm's batch statistics) -- accumulated inside the GEMM epilogue on the tensor-core path, by a separate pass otherwise.
@@ -174,14 +178,34 @@ RIH_API int rih_conv2d_fwd(const float* x, const float* w, const float* bias, fl
   if (stats && !tc::g_stats_fused) return rih_bn_colstats(y, g.ldy, g.N * g.Ho * g.Wo, g.Cout, stats, stream);
   return 0;
 }
+// Convolution with an eval-mode BatchNorm folded into its epilogue (inference only: no statistics, nothing saved for a backward pass).
+//   col_scale[c] = gamma[c] / sqrt(running_var[c] + eps),  col_shift[c] = beta[c] - running_mean[c] * col_scale[c]   (rih_bn_fold)
+//   order 0 (torchvision blocks, Conv -> BN -> (+res) -> ReLU):  y = act(conv(x) * col_scale + col_shift + res),  act = ReLU when relu != 0
+//   order 1 (repo order Conv -> ReLU -> BN, models/encoder.py:52-54):  y = relu(conv(x)) * col_scale + col_shift   (res must be null)
+// reference: torch.nn.BatchNorm2d in eval mode after nn.Conv2d (torchvision Bottleneck / BasicBlock.forward; models/encoder.py:52-54)
+RIH_API int rih_conv2d_bn_eval_fwd(const float* x, const float* w, float* y, const int* geom, const float* col_scale, const float* col_shift,
+                                   int order, int relu, const float* res, int ldres, float* ws, cudaStream_t stream) {
+  ConvGeom g;
+  RIH_REQUIRE(parse_geom(geom, g) == 0, "conv2d_bn_eval_fwd: inconsistent geometry");
+  RIH_REQUIRE(col_scale && col_shift, "conv2d_bn_eval_fwd: needs the folded scale / shift vectors");
+  RIH_REQUIRE(order == 0 || order == 1, "conv2d_bn_eval_fwd: order must be 0 (Conv-BN-ReLU) or 1 (Conv-ReLU-BN)");
+  RIH_REQUIRE(!(order == 1 && res), "conv2d_bn_eval_fwd: a residual is only defined for order 0");
+  RIH_REQUIRE(!res || ldres >= g.Cout, "conv2d_bn_eval_fwd: residual row stride %d < Cout %d", ldres, g.Cout);
+  ConvFold f{col_scale, col_shift, order, res, ldres, (order == 0 && relu) ? 1 : 0};
+  return conv2d_fwd_impl(x, w, nullptr, y, g, (order == 1 && relu) ? 1 : 0, ws, nullptr, stream, &f);
+}
 static int conv2d_fwd_impl(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, int relu, float* ws, double* stats,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const ConvFold* fold) {
   long long M = (long long)g.N * g.Ho * g.Wo;
   int K = g.R * g.S * g.Cin;
   RIH_REQUIRE(M < (1ll << 31), "conv2d_fwd: too many output pixels");
   DenseK b{w, K, g.Cout, is_vec_ok(w, K)};
   Epilogue ep = make_epilogue(y, g.ldy, (int)M, g.Cout, bias, relu, 0);
   ep.stats = stats;
+  if (fold) {
+    ep.col_scale = fold->col_scale; ep.col_shift = fold->col_shift; ep.affine_post = fold->affine_post;
+    ep.res = fold->res; ep.ldres = fold->ldres; ep.relu_post = fold->relu_post;
+  }
   if (g.R == 1 && g.S == 1 && g.stride == 1 && g.pad == 0) {
     DenseK a{x, g.ldx, (int)M, is_vec_ok(x, g.ldx) && (K % 4 == 0)};
     if (use_tc(0) && tc_ok(x, g.ldx) && tc_ok(w, K))
@@ -209,9 +233,9 @@ RIH_API int rih_conv2d_dgrad(const float* dy, const float* w, float* dx, const i
       return tc::gemm_tf32(dy, g.ldy, 0, w, g.Cin, 1, ep, (int)M, g.Cin, g.Cout, 0, stream);
     return launch_gemm_simt(a, b, ep, (int)M, g.Cin, g.Cout, 0, stream, "conv1x1_dgrad");
   }
-  // Stride 2 + accumulate: the direct formulation would have to reduce-add through an element-strided tensor map, which did not reproduce the
-  // exact-fp32 result on hardware (9e-2 off in the bottleneck test of round 2) -- stores through such maps are verified, reductions are not used.
-  // No model of this package accumulates into a stride-2 input gradient; the call is served by the copy-based path (needs ws) or the SIMT kernel.
+  // Stride 2 + accumulate: the direct formulation would have to reduce-add through an element-strided tensor map; stores through such maps are
+  // verified on hardware, reductions are not (and no model of this package accumulates into a stride-2 input gradient), so the call is served
+  // by the copy-based path (needs ws) or the SIMT kernel.
   const bool s2_acc = g.stride == 2 && accumulate && tc::s2_direct() && !ws;
   if (!s2_acc && use_tc(0) && tc_ok(dy, g.ldy) && tc_ok(w, g.Cin) && tc::conv_tc_supported(g, 1) && (g.stride == 1 || ws || tc::s2_direct())) {
     if (g.stride == 2 && accumulate && ws) { tc::set_s2_direct(0); int rc = tc::conv_dgrad_tf32(dy, w, ep, g, ws, stream); tc::set_s2_direct(1); return rc; }

@@ -173,6 +173,10 @@ struct Epilogue {
   int reverse;                                 // tensor-core persistent kernel: walk the output tiles from the last to the first (see rih_set_traversal)
   unsigned long long a_policy;                 // tensor-core path: L2 eviction-priority policy for the A-operand TMA loads (0 = none)
   int nv_pad, nv_real;                         // tensor-core wgrad with Cin % BN != 0: column n of the (virtual) tile grid is (tap = n / nv_pad, c = n % nv_pad), stored iff c < nv_real
+  const float* col_scale; const float* col_shift;   // optional per-column affine (an eval-mode BatchNorm folded into the producing convolution):
+  int affine_post;                             //   0: applied to the accumulator BEFORE bias / ReLU (torchvision order Conv -> BN -> (+res) -> ReLU)
+                                               //   1: applied AFTER the ReLU (repo order Conv -> ReLU -> BN)
+  int relu_post;                               // ReLU after the residual add (the block's final activation)
   __device__ __forceinline__ void store4(int m, int n, float4 v) const {
     if (m >= M || n >= N) return;
     float* q = c + (size_t)m * ldc + n;
@@ -182,10 +186,13 @@ struct Epilogue {
     for (int i = 0; i < 4; ++i) {
       if (n + i >= N) break;
       float t = r[i] * scale;
+      if (col_scale && !affine_post) t = fmaf(t, __ldg(col_scale + n + i), __ldg(col_shift + n + i));
       if (bias) t += __ldg(bias + n + i);
       if (relu) t = fmaxf(t, 0.f);
+      if (col_scale && affine_post) t = fmaf(t, __ldg(col_scale + n + i), __ldg(col_shift + n + i));
       if (thresh) t *= dropout_scale(seed, (uint64_t)m * N + n + i, thresh, inv_keep);
       if (res) t += __ldg(res + (size_t)m * ldres + n + i);
+      if (relu_post) t = fmaxf(t, 0.f);
       if (mode == 0) q[i] = t;
       else if (mode == 1) q[i] += t;
       else atomicAdd(q + i, t);
@@ -195,6 +202,7 @@ struct Epilogue {
 static inline Epilogue make_epilogue(float* c, int ldc, int M, int N, const float* bias, int relu, int mode) {
   Epilogue e; e.c = c; e.ldc = ldc; e.M = M; e.N = N; e.bias = bias; e.relu = relu; e.mode = mode;
   e.res = nullptr; e.ldres = 0; e.seed_ptr = nullptr; e.site = 0; e.thresh = 0; e.inv_keep = 1.f; e.stats = nullptr; e.scale = 1.f; e.nv_pad = 0; e.nv_real = 0; e.batch_heads = 0; e.s2_w2 = 0; e.s2_h2 = 0; e.s2_ph = 0; e.s2_pw = 0; e.kb_rotate = 0; e.reverse = 0; e.a_policy = 0ull;
+  e.col_scale = nullptr; e.col_shift = nullptr; e.affine_post = 0; e.relu_post = 0;
   return e;
 }
 

@@ -109,6 +109,8 @@ static int g_persistent = 1;     // 0 = one CTA per tile (non-persistent kernel;
 void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
 void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
+static int g_tma_res = 1;        // residual rows read by the TMA-store epilogue (0: GEMMs with a residual use per-thread global stores, as before)
+void set_tma_res(int on) { g_tma_res = on ? 1 : 0; }
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep, const Producer& prod, int M, int N, int num_kb, int splits,
                       int kb_per_split, cudaStream_t s, const CUtensorMap* c_map = nullptr) {
@@ -122,14 +124,15 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep,
     attr = true;
   }
   dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
-  // TMA-store epilogue whenever the output is a 16-byte aligned matrix and no residual has to be read back
+  // TMA-store epilogue whenever the output is a 16-byte aligned matrix (a residual is read back row-wise by the epilogue threads when it is aligned too)
   CUtensorMap tc_;
   int tma_epi = 0;
   if (c_map) {       // caller-built output map (3-D wgrad view); only the persistent TMA-store epilogue understands it
     if (!g_persistent) { set_error("gemm_tc: output-map override needs the persistent kernel"); return 1; }
     tc_ = *c_map;
     tma_epi = 1;
-  } else if (!ep.res && ((reinterpret_cast<uintptr_t>(ep.c) & 15) == 0) && (ep.ldc % 4 == 0) && g_tma_epilogue) {
+  } else if ((!ep.res || (g_tma_res && splits == 1 && ((reinterpret_cast<uintptr_t>(ep.res) & 15) == 0) && ep.ldres % 4 == 0 && N % 4 == 0)) &&
+             ((reinterpret_cast<uintptr_t>(ep.c) & 15) == 0) && (ep.ldc % 4 == 0) && g_tma_epilogue) {
     if (make_tmap_2d(&tc_, ep.c, M, N, ep.ldc, BM)) return 1;
     tma_epi = 1;
   } else {

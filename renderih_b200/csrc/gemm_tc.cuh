@@ -396,6 +396,47 @@ struct StemWgradProducer {
   }
 };
 
+// Epilogue arithmetic of one 32-column chunk held in registers (row m, columns nb .. nb+31): the same sequence as Epilogue::store4.
+__device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep, int m, int nb, unsigned long long dseed) {
+  if (ep.scale != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= ep.scale;
+  }
+  if (ep.col_scale && !ep.affine_post) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] = fmaf(v[j], __ldg(ep.col_scale + nb + j), __ldg(ep.col_shift + nb + j));
+  }
+  if (ep.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] += __ldg(ep.bias + nb + j);
+  }
+  if (ep.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (ep.col_scale && ep.affine_post) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] = fmaf(v[j], __ldg(ep.col_scale + nb + j), __ldg(ep.col_shift + nb + j));
+  }
+  if (ep.thresh) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= dropout_scale(dseed, (uint64_t)m * ep.N + nb + j, ep.thresh, ep.inv_keep);
+  }
+  if (ep.res && m < ep.M) {        // residual row: 128 contiguous bytes per thread (host checked 16-byte alignment and N % 4 == 0)
+    const float4* r4 = reinterpret_cast<const float4*>(ep.res + (size_t)m * ep.ldres + nb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (nb + 4 * j < ep.N) {
+      const float4 q = __ldg(r4 + j);
+      v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+    }
+  }
+  if (ep.relu_post) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+}
+
+
 // ---------------------------------------------------------------- the kernel
 // tma_epi != 0: the epilogue stages 32-column chunks in 128B-swizzled shared memory and writes them with TMA stores
 // (cp.reduce.async.bulk ... .add for accumulate / split-K), fully coalesced and clipped at the tensor edge by the hardware.
@@ -522,22 +563,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
         const int nb = n0 + c * 32;
-        if (ep.scale != 1.f) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= ep.scale;
-        }
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] += __ldg(ep.bias + nb + j);
-        }
-        if (ep.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (ep.thresh) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= dropout_scale(dseed, (uint64_t)m * ep.N + nb + j, ep.thresh, ep.inv_keep);
-        }
+        epilogue_math(v, ep, m, nb, dseed);
         if (c >= 2) {                    // staging buffer (c & 1) must have been read out by its previous TMA store
           if (elected) tma_store_wait_read<1>();
           epi_bar_sync();
@@ -779,22 +805,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         }
         if (batched && nb >= ep.N) continue;   // e.g. head dim 16 in a 64-wide tile: nothing to store
         if (tma_epi) {
-          if (ep.scale != 1.f) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= ep.scale;
-          }
-          if (ep.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] += __ldg(ep.bias + nb + j);
-          }
-          if (ep.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (ep.thresh) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= dropout_scale(dseed, (uint64_t)m * ep.N + nb + j, ep.thresh, ep.inv_keep);
-          }
+          epilogue_math(v, ep, m, nb, dseed);
           if (cc >= 2) {
             if (elected) tma_store_wait_read<1>();
             epi_bar_sync(wg);

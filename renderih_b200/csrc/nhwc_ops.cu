@@ -909,3 +909,30 @@ RIH_API int rih_preprocess_u8(const unsigned char* src, const unsigned char* fli
   launch_k(preprocess_u8_kernel, grid, 256, 0, s, src, flip, dst, B, H, W, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1], std3_host[2]);
   return check_launch("preprocess_u8");
 }
+
+// ---------------------------------------------------------------- eval-mode BatchNorm folding
+// One launch folds EVERY BatchNorm of a network into per-channel (scale, shift) vectors for rih_conv2d_bn_eval_fwd:
+//   table[4 b .. 4 b + 3] = device addresses of (gamma, beta, running_mean, running_var) of BatchNorm b,  chan_bn[i] = the BatchNorm that owns
+//   flat channel i,  bn_off[b] = its first flat channel.  Reads the live parameter / buffer storage, so a CUDA graph that replays this launch
+//   always sees the current running statistics.
+__global__ void bn_fold_kernel(const unsigned long long* __restrict__ table, const int* __restrict__ chan_bn, const int* __restrict__ bn_off,
+                               const float* __restrict__ eps, float* __restrict__ scale, float* __restrict__ shift, int total) {
+  pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = chan_bn[i], c = i - bn_off[b];
+  const float* gamma = reinterpret_cast<const float*>(table[4 * b]);
+  const float* beta = reinterpret_cast<const float*>(table[4 * b + 1]);
+  const float* mean = reinterpret_cast<const float*>(table[4 * b + 2]);
+  const float* var = reinterpret_cast<const float*>(table[4 * b + 3]);
+  const float sc = gamma[c] * (1.0f / sqrtf(var[c] + eps[b]));
+  scale[i] = sc;
+  shift[i] = beta[c] - mean[c] * sc;
+}
+
+RIH_API int rih_bn_fold(const unsigned long long* table, const int* chan_bn, const int* bn_off, const float* eps, float* scale, float* shift,
+                        int total, cudaStream_t s) {
+  RIH_REQUIRE(table && chan_bn && bn_off && eps && scale && shift && total > 0, "bn_fold: null argument / empty table");
+  launch_k(bn_fold_kernel, dim3((total + 255) / 256), dim3(256), 0, s, table, chan_bn, bn_off, eps, scale, shift, total);
+  return check_launch("bn_fold");
+}

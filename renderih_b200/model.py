@@ -55,6 +55,10 @@ def _cl(conv):
 def _conv_bn(x, conv, bn, N, H, W, training, relu=True, res=None, alias_input=False):
     """torchvision order Conv -> BN -> (+res) -> ReLU.  alias_input: returns (y, Ho, x_alias) -- see ops.conv2d."""
     k = conv.kernel_size[0]
+    fold = None if (training or alias_input or torch.is_grad_enabled() or conv.bias is not None) else bn.__dict__.get('_rih_fold')
+    if fold is not None and ops.BN_FOLD:     # inference: the BatchNorm (+ residual + ReLU) rides in the convolution's epilogue
+        y = ops.conv2d_bn_eval(x, conv.weight, N, H, W, conv.stride[0], conv.padding[0], fold, order=0, relu=relu, res=res)
+        return y, (H + 2 * conv.padding[0] - k) // conv.stride[0] + 1
     stats = torch.empty(2 * conv.out_channels, device=x.device, dtype=torch.float64) if training else None
     y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], stats=stats, alias_input=alias_input)
     xa = None
@@ -68,6 +72,9 @@ def _conv_bn(x, conv, bn, N, H, W, training, relu=True, res=None, alias_input=Fa
 
 def _conv_relu_bn(x, conv, bn, N, H, W, training):
     """repo order Conv -> ReLU -> BN (models/model_zoo/__init__.py:56-82, models/encoder.py:52-54)"""
+    fold = None if (training or torch.is_grad_enabled() or conv.bias is not None) else bn.__dict__.get('_rih_fold')
+    if fold is not None and ops.BN_FOLD:
+        return ops.conv2d_bn_eval(x, conv.weight, N, H, W, conv.stride[0], conv.padding[0], fold, order=1, relu=True)
     stats = torch.empty(2 * conv.out_channels, device=x.device, dtype=torch.float64) if training else None
     y = ops.conv2d(x, conv.weight, None, N, H, W, stride=conv.stride[0], pad=conv.padding[0], relu=True,
                    relu_masked_by_consumer=True, stats=stats)
@@ -184,11 +191,13 @@ class ResNetSimple(nn.Module):
         out, _ = _conv_bn(out, blk.conv2, blk.bn2, N, Ho, Ho, tr, relu=True, res=identity)
         return out, Ho
 
-    def trunk(self, img):
+    def trunk(self, img, fold_done=False):
         """stem + layer1..4 (encoder.py:107-118) -> [x1 (8x8), x2, x3, x4 (64x64)] as (NHWC rows, H) pairs."""
         N, C, H, W = img.shape
         assert H == W
         r = self.resnet
+        if not self.training and not fold_done:
+            ops.bn_fold_refresh(self)        # inference: one launch folds every BatchNorm of the encoder for the conv epilogues
         if not img.requires_grad and ops.stem_supported(H, W):
             # conv1 straight from the NCHW image: zero-bordered NHWC4 copy + tcgen05 implicit GEMM (no im2col buffer), train and eval mode
             conv, bn = r.conv1, r.bn1
@@ -258,7 +267,9 @@ class resnet_mid(nn.Module):
         x = ops.concat_channels(parts)
         return _conv_relu_bn(x, seq[0], seq[2], N, H, H, self.training), H
 
-    def forward(self, img_fmaps, hms_fmaps, dp_fmaps, N):
+    def forward(self, img_fmaps, hms_fmaps, dp_fmaps, N, fold_done=False):
+        if not self.training and not fold_done:
+            ops.bn_fold_refresh(self)
         x1, H1 = img_fmaps[0]
         global_feature = ops.global_avgpool(x1, N, H1 * H1)
         return global_feature, [self.level(i, img_fmaps, hms_fmaps[i], dp_fmaps[i], N) for i in range(len(self.convs))]
@@ -813,9 +824,11 @@ class HandNET_GCN(nn.Module):
         if self.training:
             ops.seed_state.advance(img.device)
         N = img.shape[0]
+        # inference: ONE launch folds every BatchNorm of the network into (scale, shift) vectors for the convolution epilogues
+        fold_done = (not (self.encoder.training and self.mid_model.training)) and ops.bn_fold_refresh(self)
         aux = AuxStream.get(img.device) if (type(self.encoder) is ResNetSimple and self.encoder.aux_heads and type(self.mid_model) is resnet_mid) else None
         if aux is not None:
-            result, paramsDict, handDictList, otherInfo, hms, mask, dp = self._forward_pipelined(img, N, aux)
+            result, paramsDict, handDictList, otherInfo, hms, mask, dp = self._forward_pipelined(img, N, aux, fold_done)
         else:
             hms, mask, dp, img_fmaps, hms_fmaps, dp_fmaps = self.encoder(img)
             global_feature, fmaps = self.mid_model(img_fmaps, hms_fmaps, dp_fmaps, N)
@@ -829,7 +842,7 @@ class HandNET_GCN(nn.Module):
         return result, paramsDict, handDictList, otherInfo
 
 
-    def _forward_pipelined(self, img, N, aux):
+    def _forward_pipelined(self, img, N, aux, fold_done=False):
         """Same arithmetic as encoder -> mid_model -> decoder, issued as two concurrent pipelines: everything behind the trunk on the
         convolution side (heat-map / dense-pose decoder stages at 8, 16, 32, 64 px, the mid 1x1 convs, the aux heads) runs on the aux stream
         and publishes each mid level with an event; the token decoder (main + hand streams) waits for level i only when DualGraph layer i
@@ -837,7 +850,7 @@ class HandNET_GCN(nn.Module):
         decoder reads.  autograd replays every node on its forward stream, so the backward pass is pipelined the same way."""
         enc, mid = self.encoder, self.mid_model
         dev = img.device
-        img_fmaps = enc.trunk(img)
+        img_fmaps = enc.trunk(img, fold_done)
         x1, H1 = img_fmaps[0]
         global_feature = ops.global_avgpool(x1, N, H1 * H1)
         main = torch.cuda.current_stream(dev)

@@ -922,6 +922,90 @@ def conv2d(x, w, b, N, H, W, stride=1, pad=0, relu=False, relu_masked_by_consume
     return Conv2dFn.apply(x, w, b, N, H, W, stride, pad, relu, relu_masked_by_consumer, stats, alias_input)
 
 
+# ----------------------------------------------------------------------------- eval-mode BatchNorm folded into the convolution
+BN_FOLD = _os.environ.get('RIH_BN_FOLD', '1') != '0'
+
+
+class BnFold:
+    """Per-channel (scale, shift) vectors of every eval-mode BatchNorm2d under `root`, recomputed by ONE kernel launch per forward pass from
+    the live parameters / running statistics (`refresh`), so CUDA-graph replays and interleaved training always see current values.
+    `bn._rih_fold = (scale, shift)` are views into the flat buffers; conv2d_bn_eval consumes them.  Inference only (no autograd)."""
+
+    def __init__(self, root):
+        self.bns = [m for m in root.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+        self.device = None
+        self._key = None
+
+    def _build(self):
+        dev = self.bns[0].weight.device
+        sizes = [m.num_features for m in self.bns]
+        offs = [0]
+        for c in sizes:
+            offs.append(offs[-1] + c)
+        total = offs[-1]
+        for m in self.bns:
+            for t in (m.weight, m.bias, m.running_mean, m.running_var):
+                if t is None or not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                    raise RuntimeError('renderih_b200: BatchNorm folding needs affine fp32 CUDA BatchNorm2d modules with running statistics')
+        self.table = torch.tensor([[t.data_ptr() for t in (m.weight, m.bias, m.running_mean, m.running_var)] for m in self.bns],
+                                  dtype=torch.int64).to(dev)
+        self.chan_bn = torch.repeat_interleave(torch.arange(len(sizes), dtype=torch.int32), torch.tensor(sizes)).to(dev)
+        self.bn_off = torch.tensor(offs[:-1], dtype=torch.int32).to(dev)
+        self.eps = torch.tensor([m.eps for m in self.bns], dtype=torch.float32).to(dev)
+        self.scale = torch.empty(total, device=dev)
+        self.shift = torch.empty(total, device=dev)
+        self.total = total
+        for m, o, c in zip(self.bns, offs, sizes):
+            m._rih_fold = (self.scale[o:o + c], self.shift[o:o + c])
+        self.device = dev
+
+    def refresh(self):
+        if not self.bns:
+            return
+        key = tuple(t.data_ptr() for m in self.bns for t in (m.weight, m.bias, m.running_mean, m.running_var))
+        if key != self._key:           # first use, or a parameter / buffer was re-allocated (.to(), load with assign=True ...)
+            if torch.cuda.is_current_stream_capturing():
+                if self._key is None:
+                    raise RuntimeError('renderih_b200: run one eval-mode forward before capturing it into a CUDA graph (BatchNorm fold table)')
+                raise RuntimeError('renderih_b200: BatchNorm storage moved since the fold table was built; cannot rebuild it during capture')
+            self._build()
+            self._key = key
+        call('rih_bn_fold', self.table.data_ptr(), self.chan_bn.data_ptr(), self.bn_off.data_ptr(), _p(self.eps), _p(self.scale), _p(self.shift),
+             self.total, _stream())
+
+
+def bn_fold_refresh(root):
+    """Recompute the folded BatchNorm vectors of `root` (cached BnFold) when the folded inference path applies; returns True when it does."""
+    if not BN_FOLD or torch.is_grad_enabled():
+        return False
+    f = root.__dict__.get('_rih_bn_fold')
+    if f is None:
+        f = BnFold(root)
+        root.__dict__['_rih_bn_fold'] = f
+    f.refresh()
+    return True
+
+
+def conv2d_bn_eval(x, w, N, H, W, stride, pad, fold, order=0, relu=True, res=None):
+    """Convolution + eval-mode BatchNorm (+ residual)(+ ReLU) in one kernel (rih_conv2d_bn_eval_fwd); fold = (scale, shift) from BnFold.
+    order 0: Conv -> BN -> (+res) -> ReLU (torchvision blocks); order 1: Conv -> ReLU -> BN (models/encoder.py:52-54).  No autograd."""
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+        raise RuntimeError('renderih_b200: conv2d_bn_eval is an inference kernel (call it under torch.no_grad())')
+    x = _rows(x); _w_phys(_check(w, 'weight'))
+    Cout, Cin, R, S = w.shape
+    assert x.shape == (N * H * W, Cin), (x.shape, N, H, W, Cin)
+    g, Ho, Wo = _geom(N, H, W, Cin, Cout, R, S, stride, pad, _ld(x), Cout)
+    scale, shift = fold
+    assert scale.numel() == Cout and shift.numel() == Cout
+    if res is not None:
+        res = _rows(res)
+        assert res.shape == (N * Ho * Wo, Cout), (res.shape, N, Ho, Wo, Cout)
+    y = torch.empty((N * Ho * Wo, Cout), device=x.device, dtype=torch.float32)
+    call('rih_conv2d_bn_eval_fwd', _p(x), _p(w), _p(y), g, _p(scale), _p(shift), int(order), int(relu), _p(res), _ld(res) if res is not None else 0,
+         _p(_conv_ws(g, 0, x.device)), _stream())
+    return y
+
+
 class PatchifyFn(Function):
     """Non-overlapping p x p patches as rows: [N*H*W, C] -> [N*(H/p)*(W/p), p*p*C]  (kernel == stride convolutions of
     img_feat_to_grid, models/model_attn/img_attn.py:46-48,60, become one dense GEMM)."""

@@ -658,3 +658,59 @@ def test_bottleneck_with_stride2_shortcut_tensor_core_matches_exact(ops):
     for k, gref in res['simt'][2].items():
         e = l2(res['tf32x3'][2][k], gref)
         assert e < 5e-3, (k, e)
+
+
+@pytest.mark.parametrize('N,H,Cin,Cout,k,stride', [(4, 32, 256, 64, 1, 1), (4, 32, 64, 64, 3, 1), (4, 32, 64, 256, 1, 1), (2, 32, 128, 128, 3, 2),
+                                                    (2, 32, 256, 512, 1, 2), (2, 16, 48, 96, 3, 1)])
+@pytest.mark.parametrize('mode', ['simt', 'tf32x3'])
+@pytest.mark.parametrize('order,with_res', [(0, False), (0, True), (1, False)])
+def test_conv2d_with_folded_eval_batchnorm(ops, N, H, Cin, Cout, k, stride, mode, order, with_res):
+    """rih_conv2d_bn_eval_fwd (eval-mode BatchNorm, residual and final ReLU in the convolution's epilogue; scale / shift from rih_bn_fold) against
+    torch: order 0 = Conv -> BN -> (+res) -> ReLU (torchvision Bottleneck.forward), order 1 = Conv -> ReLU -> BN (models/encoder.py:52-54)."""
+    torch.manual_seed(Cin + Cout + k)
+    conv = torch.nn.Conv2d(Cin, Cout, k, stride, k // 2, bias=False).to(DEV)
+    conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)
+    bn = torch.nn.BatchNorm2d(Cout).to(DEV).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0)
+    holder = torch.nn.Sequential(conv, bn)
+    x = T(N, Cin, H, H, grad=False)
+    Ho = (H + 2 * (k // 2) - k) // stride + 1
+    res = T(N, Cout, Ho, Ho, seed=3, grad=False) if with_res else None
+    rows = lambda t: t.permute(0, 2, 3, 1).contiguous().reshape(-1, t.shape[1])
+    with torch.no_grad():
+        assert ops.bn_fold_refresh(holder)
+        ops.set_gemm_mode(mode, mode)
+        try:
+            y = ops.conv2d_bn_eval(rows(x), conv.weight, N, H, H, stride, k // 2, bn._rih_fold, order=order, relu=True,
+                                   res=rows(res) if with_res else None)
+        finally:
+            ops.set_gemm_mode('simt', 'simt')
+        c = F.conv2d(x.double(), conv.weight.double(), None, stride, k // 2)
+        bnd = lambda t: F.batch_norm(t, bn.running_mean.double(), bn.running_var.double(), bn.weight.double(), bn.bias.double(), False, 0.0, bn.eps)
+        if order == 0:
+            r = bnd(c)
+            if with_res:
+                r = r + res.double()
+            r = F.relu(r)
+        else:
+            r = bnd(F.relu(c))
+    assert rel(y, rows(r).float()) < 2e-5, rel(y, rows(r).float())
+
+
+def test_bn_fold_tracks_live_running_statistics(ops):
+    """The fold table reads the BatchNorm storage at every refresh: changing the running statistics in place (what training does between two
+    evaluations) changes the folded vectors without rebuilding anything."""
+    bn = torch.nn.BatchNorm2d(64).to(DEV).eval()
+    root = torch.nn.Sequential(bn, torch.nn.BatchNorm2d(48).to(DEV).eval())
+    with torch.no_grad():
+        assert ops.bn_fold_refresh(root)
+        s0 = bn._rih_fold[0].clone()
+        bn.running_var.mul_(4.0)
+        root[1].bias.add_(1.0)
+        assert ops.bn_fold_refresh(root)
+        assert rel(bn._rih_fold[0], s0 * ((bn.running_var / 4 + bn.eps) / (bn.running_var + bn.eps)).sqrt()) < 1e-6
+        b1 = root[1]
+        ref_shift = b1.bias - b1.running_mean * b1.weight / (b1.running_var + b1.eps).sqrt()
+        assert rel(b1._rih_fold[1], ref_shift) < 1e-6
+    assert not ops.bn_fold_refresh(root)          # gradients enabled: the folded inference path is off
