@@ -234,7 +234,7 @@ def test_two_rank_nccl_step_equals_one_rank_step_on_concatenated_batch():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1', '--master-port', '29571',
            os.path.join(root, 'tests', 'dist_equivalence.py')]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=root)
     print(r.stdout[-3000:])
     print(r.stderr[-3000:])
     assert r.returncode == 0
