@@ -372,6 +372,15 @@ def class_roofline(torch, step, pk, flops_step, ms_step):
     ach = cfl / (cms * 1e-3) / 1e12 if cms > 0 else 0.0
     peak = pk['tflops_sustained']
     top = sorted(per.items(), key=lambda kv: -kv[1][1])[:12]
+
+    def small_ints(a):       # the shape / flag arguments of a call (pointers and stream handles are large)
+        out = []
+        for v in a:
+            v = getattr(v, 'value', v)
+            if isinstance(v, int) and 0 <= v < (1 << 24):
+                out.append(v)
+        return out
+    slow = sorted(((e0.elapsed_time(e1), name, a) for name, a, e0, e1 in trace), key=lambda t: -t[0])[:16]
     return {'bound': 'tensor', 'kernel': 'class: every tcgen05 GEMM / implicit-GEMM launch of the step (gemm_tc_persistent_kernel<...>: Conv2d, nn.Linear and attention '
                                          'contractions, fwd + dgrad + wgrad), %d launches' % n,
             'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'frac_of_tf32_peak': ach / (0.5 * peak), 'traffic': None,
@@ -380,6 +389,7 @@ def class_roofline(torch, step, pk, flops_step, ms_step):
             'how': 'one eager step, CUDA events around every C-ABI launch on its own stream (cold launch gaps included); ncu launch list of the same step: profiles/',
             'peak_source': pk['src'] + ' bf16 dense SUSTAINED (kernels timed inside a long step); operands are TF32, whose tensor peak is half of it',
             'by_entry_point_ms': {k: round(v[1], 3) for k, v in top},
+            'slowest_calls': [{'ms': round(ms, 3), 'entry': name, 'int_args': small_ints(a)} for ms, name, a in slow],
             'step': {'achieved': flops_step / (ms_step * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
                      'frac': flops_step / (ms_step * 1e-3) / 1e12 / peak, 'frac_of_tf32_peak': flops_step / (ms_step * 1e-3) / 1e12 / (0.5 * peak),
                      'what': 'whole-step algorithmic flops (SURVEY 8d) / device-timed step'}}

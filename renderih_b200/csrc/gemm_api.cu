@@ -283,6 +283,18 @@ RIH_API int rih_stem_conv_fwd(const float* xp, const float* w224, float* y, int 
   if (stats && !tc::g_stats_fused) return rih_bn_colstats(y, 64, M, 64, stats, stream);
   return 0;
 }
+// Inference form of the stem: y = relu(conv(x) * col_scale + col_shift) -- eval-mode bn1 + ReLU in the epilogue (see rih_conv2d_bn_eval_fwd)
+RIH_API int rih_stem_conv_bn_eval_fwd(const float* xp, const float* w224, float* y, int N, int H, int W, const float* col_scale, const float* col_shift,
+                                      int relu, cudaStream_t stream) {
+  RIH_REQUIRE(N > 0 && H > 0 && W > 0, "stem_conv_bn_eval_fwd: bad shape");
+  RIH_REQUIRE(use_tc(0), "stem_conv_bn_eval_fwd: needs a tensor-core convolution mode (rih_set_gemm_mode)");
+  RIH_REQUIRE(tc_ok(xp, 4) && tc_ok(w224, 224) && tc_ok(y, 64), "stem_conv_bn_eval_fwd: pointers must be 16-byte aligned");
+  RIH_REQUIRE(col_scale && col_shift, "stem_conv_bn_eval_fwd: needs the folded scale / shift vectors");
+  const int M = N * (H / 2) * (W / 2);
+  Epilogue ep = make_epilogue(y, 64, M, 64, nullptr, 0, 0);
+  ep.col_scale = col_scale; ep.col_shift = col_shift; ep.affine_post = 0; ep.relu_post = relu ? 1 : 0;
+  return tc::stem_fwd_tf32(xp, w224, ep, N, H, W, stream);
+}
 // dw224[64][224] (+)= weight gradient of the stem convolution (dy: [N*Ho*Wo, 64] rows with stride lddy)
 RIH_API int rih_stem_conv_wgrad(const float* dy, int lddy, const float* xp, float* dw224, int N, int H, int W, int accumulate, cudaStream_t stream) {
   RIH_REQUIRE(N > 0 && H > 0 && W > 0, "stem_conv_wgrad: bad shape");

@@ -201,10 +201,12 @@ class ResNetSimple(nn.Module):
         if not img.requires_grad and ops.stem_supported(H, W):
             # conv1 straight from the NCHW image: zero-bordered NHWC4 copy + tcgen05 implicit GEMM (no im2col buffer), train and eval mode
             conv, bn = r.conv1, r.bn1
+            fold = None if (self.training or torch.is_grad_enabled() or not ops.BN_FOLD) else bn.__dict__.get('_rih_fold')
             stats = torch.empty(2 * 64, device=img.device, dtype=torch.float64) if self.training else None
-            x = ops.stem_conv(img, conv.weight, stats)
-            x = ops.batchnorm(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, tracked=bn.num_batches_tracked, training=self.training,
-                              momentum=bn.momentum, eps=bn.eps, relu=True, stats=stats)
+            x = ops.stem_conv(img, conv.weight, stats, fold)
+            if fold is None:
+                x = ops.batchnorm(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, tracked=bn.num_batches_tracked, training=self.training,
+                                  momentum=bn.momentum, eps=bn.eps, relu=True, stats=stats)
             H = H // 2
         else:
             x = ops.nchw_to_nhwc(img)

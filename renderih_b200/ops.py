@@ -1082,7 +1082,7 @@ def stem_supported(H, W):
     return MODE['conv'] != 'simt' and H == W == 256 and _os.environ.get('RIH_STEM_IGEMM', '1') != '0'
 
 
-def stem_conv(img, weight, stats=None):
+def stem_conv(img, weight, stats=None, fold=None):
     """img: [N,3,H,W] (no gradient), weight: conv1.weight [64,3,7,7] channels_last.  -> NHWC rows [N*(H/2)*(W/2), 64]."""
     img = _check(img).contiguous()
     N, C, H, W = img.shape
@@ -1091,6 +1091,12 @@ def stem_conv(img, weight, stats=None):
     call('rih_nchw_to_nhwc4_pad', _p(img), _p(xp), N, H, W, _stream())
     # [64,3,7,7] (memory [64][7][7][3]) -> [64][7][8][4]: one zero column (the 8th pixel of every 128-byte row) and one zero channel
     w224 = torch.nn.functional.pad(weight.permute(0, 2, 3, 1), (0, 1, 0, 1)).reshape(64, 224)
+    if fold is not None:         # inference: eval-mode bn1 + ReLU in the epilogue
+        if torch.is_grad_enabled() and weight.requires_grad:
+            raise RuntimeError('renderih_b200: the folded stem is an inference kernel (call it under torch.no_grad())')
+        y = torch.empty((N * (H // 2) * (W // 2), 64), device=img.device, dtype=torch.float32)
+        call('rih_stem_conv_bn_eval_fwd', _p(xp), _p(w224), _p(y), N, H, W, _p(fold[0]), _p(fold[1]), 1, _stream())
+        return y
     return StemConvFn.apply(xp, w224, N, H, W, stats)
 
 
