@@ -54,6 +54,9 @@ def conv_bn(x, conv, bn, N, H, training, relu=True, res=None, alias_input=False)
     route the residual use of x through x_alias and its gradient is accumulated by this convolution's dgrad kernel (ops.conv2d).
     Training-mode batch statistics come out of the convolution's epilogue when it runs on the tensor-core path."""
     k, st, pd = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+    fold = None if (training or alias_input or torch.is_grad_enabled() or conv.bias is not None or not ops.BN_FOLD) else bn.__dict__.get('_rih_fold')
+    if fold is not None:       # inference: BatchNorm (+ residual + ReLU) in the convolution's epilogue (ops.conv2d_bn_eval)
+        return ops.conv2d_bn_eval(x, conv.weight, N, H, H, st, pd, fold, order=0, relu=relu, res=res), (H + 2 * pd - k) // st + 1
     stats = torch.empty(2 * conv.out_channels, device=x.device, dtype=torch.float64) if training else None
     y = ops.conv2d(x, conv.weight, conv.bias, N, H, H, stride=st, pad=pd, stats=stats, alias_input=alias_input)
     xa = None
@@ -280,6 +283,8 @@ class HRnet_encoder(nn.Module):
     def forward(self, img):
         N, C, H, W = img.shape
         assert H == W
+        if not self.training:
+            ops.bn_fold_refresh(self)       # inference: fold every BatchNorm of the encoder for the convolution epilogues (one launch)
         x = ops.nchw_to_nhwc(img)
         ys = self.hrnet(x, N, H, img.requires_grad)
         H0 = ys[0][1]
@@ -318,6 +323,8 @@ class hrnet_mid(nn.Module):
     def forward(self, img_fmaps, hms_fmaps=None, dp_fmaps=None, N=None):
         tr = self.training
         from .model import _conv_relu_bn
+        if not tr:
+            ops.bn_fold_refresh(self)
         fmaps = [(_conv_relu_bn(x, seq[0], seq[2], N, H, H, tr), H) for (x, H), seq in zip(img_fmaps, self.convs)]
         rev = img_fmaps[::-1]
         y = self.incre_modules[0][0](rev[0][0], N, rev[0][1])

@@ -62,6 +62,38 @@ def build_step(encoder, batch, gemm_mode='ref'):
     return step
 
 
+def build_forward(encoder, batch, gemm_mode='ref'):
+    """Eval-mode forward under torch.no_grad(), captured into a CUDA graph (what `bench.py --config forward` times)."""
+    import torch
+    from renderih_b200 import _lib, assets as A, ops
+    from renderih_b200.config import load_cfg
+    from renderih_b200.model import load_model
+    _lib.load()
+    conv_mode, lin_mode = {'ref': ('tf32c', 'tf32x3')}.get(gemm_mode, (gemm_mode, gemm_mode))
+    ops.set_gemm_mode(conv_mode, lin_mode)
+    cfg = load_cfg()
+    cfg.MODEL.ENCODER_TYPE = encoder
+    torch.manual_seed(cfg.SEED)
+    model = load_model(cfg, assets=A.synthetic_assets(0)).cuda().eval()
+    img = torch.randn(batch, 3, 256, 256, generator=torch.Generator().manual_seed(cfg.SEED)).cuda()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s), torch.no_grad():
+        for _ in range(2):
+            model(img)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph), torch.no_grad():
+        out = model(img)
+    keep = (model, img, out)
+
+    def step():
+        keep  # noqa: B018  (static tensors of the graph stay alive)
+        graph.replay()
+    return step
+
+
 def klass(name):
     n = re.sub(r'^void ', '', name)
     n = re.sub(r'rih::|tc::|at::native::|<unnamed>::', '', n)
@@ -78,10 +110,11 @@ def main():
     ap.add_argument('--encoder', default='resnet50')
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'timeline.csv'))
+    ap.add_argument('--forward', action='store_true', help='eval-mode forward (bench.py --config forward) instead of the training step')
     args = ap.parse_args()
     import torch
     from torch.profiler import ProfilerActivity, profile
-    step = build_step(args.encoder, args.batch)
+    step = build_forward(args.encoder, args.batch) if args.forward else build_step(args.encoder, args.batch)
     for _ in range(3):
         step()
     torch.cuda.synchronize()
