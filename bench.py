@@ -348,11 +348,15 @@ def class_roofline(torch, step, pk, flops_step, ms_step):
     under-states the class a little; the share of the step is computed against the sum over ALL traced launches (serialised time)."""
     from renderih_b200 import _lib
     from renderih_b200.ops import GROUP_FLOPS
+    import ctypes
     _lib.TRACE = []
+    counts = (ctypes.c_longlong * 3)()
     try:
+        _lib.call('rih_gemm_launch_counts', None, 1)
         step._eager_no_opt()
         torch.cuda.synchronize()
         trace = _lib.TRACE
+        _lib.call('rih_gemm_launch_counts', counts, 0)
     finally:
         _lib.TRACE = None
     per = {}
@@ -389,6 +393,7 @@ def class_roofline(torch, step, pk, flops_step, ms_step):
             'how': 'one eager step, CUDA events around every C-ABI launch on its own stream (cold launch gaps included); ncu launch list of the same step: profiles/',
             'peak_source': pk['src'] + ' bf16 dense SUSTAINED (kernels timed inside a long step); operands are TF32, whose tensor peak is half of it',
             'by_entry_point_ms': {k: round(v[1], 3) for k, v in top},
+            'gemm_launches_by_path': {'tcgen05_tma_store_epilogue': counts[0], 'tcgen05_thread_store_epilogue': counts[1], 'exact_fp32_simt': counts[2]},
             'slowest_calls': [{'ms': round(ms, 3), 'entry': name, 'int_args': small_ints(a)} for ms, name, a in slow],
             'step': {'achieved': flops_step / (ms_step * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
                      'frac': flops_step / (ms_step * 1e-3) / 1e12 / peak, 'frac_of_tf32_peak': flops_step / (ms_step * 1e-3) / 1e12 / (0.5 * peak),

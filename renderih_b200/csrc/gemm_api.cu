@@ -15,6 +15,7 @@ void set_narrow_small(int on);
 void set_wgrad_wide(int on);
 void set_s2_direct(int on);
 void set_tma_res(int on);
+void set_epilogue_opt(int v);
 int s2_direct();
 void set_acc_scale(float s);
 extern int g_stats_fused;
@@ -56,6 +57,13 @@ RIH_API int rih_set_narrow_tiles(int on) { tc::set_narrow_small(on); return 0; }
 // 1 (default) = stride-2 convolutions (forward, weight gradient, input gradient) address the full-resolution tensors in place through tensor
 // maps with element strides {1, 2, 2, 1}; the input gradient runs as four dense parity-class GEMMs.  0 = the copy-based formulation
 // (parity-stacked input for forward / wgrad, zero-inserted dY for dgrad; needs the rih_conv2d_workspace buffers).
+// out[0..2] = tensor-core GEMM launches with the TMA-store epilogue, with per-thread stores, exact-fp32 SIMT GEMM launches since the last reset
+RIH_API int rih_gemm_launch_counts(long long* out, int reset) {
+  if (out) for (int i = 0; i < 3; ++i) out[i] = tc::g_launch_counts[i];
+  if (reset) for (int i = 0; i < 3; ++i) tc::g_launch_counts[i] = 0;
+  return 0;
+}
+RIH_API int rih_set_epilogue_opt(int bits) { tc::set_epilogue_opt(bits); return 0; }
 RIH_API int rih_set_tma_res(int on) { tc::set_tma_res(on); return 0; }
 RIH_API int rih_set_s2_direct(int on) { tc::set_s2_direct(on); return 0; }
 RIH_API int rih_set_wgrad_wide(int on) { tc::set_wgrad_wide(on); return 0; }

@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 namespace rih {
+namespace tc { extern long long g_launch_counts[3]; }   // launch bookkeeping shared with the tensor-core path (gemm_tc.cu)
 
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_THREADS = 256;
@@ -177,6 +178,7 @@ struct Epilogue {
   int affine_post;                             //   0: applied to the accumulator BEFORE bias / ReLU (torchvision order Conv -> BN -> (+res) -> ReLU)
                                                //   1: applied AFTER the ReLU (repo order Conv -> ReLU -> BN)
   int relu_post;                               // ReLU after the residual add (the block's final activation)
+  int opt;                                     // tensor-core persistent epilogue: bit 0 = residual rows prefetched a chunk ahead, bit 1 = column vectors cached in shared memory (rih_set_epilogue_opt)
   __device__ __forceinline__ void store4(int m, int n, float4 v) const {
     if (m >= M || n >= N) return;
     float* q = c + (size_t)m * ldc + n;
@@ -202,7 +204,7 @@ struct Epilogue {
 static inline Epilogue make_epilogue(float* c, int ldc, int M, int N, const float* bias, int relu, int mode) {
   Epilogue e; e.c = c; e.ldc = ldc; e.M = M; e.N = N; e.bias = bias; e.relu = relu; e.mode = mode;
   e.res = nullptr; e.ldres = 0; e.seed_ptr = nullptr; e.site = 0; e.thresh = 0; e.inv_keep = 1.f; e.stats = nullptr; e.scale = 1.f; e.nv_pad = 0; e.nv_real = 0; e.batch_heads = 0; e.s2_w2 = 0; e.s2_h2 = 0; e.s2_ph = 0; e.s2_pw = 0; e.kb_rotate = 0; e.reverse = 0; e.a_policy = 0ull;
-  e.col_scale = nullptr; e.col_shift = nullptr; e.affine_post = 0; e.relu_post = 0;
+  e.col_scale = nullptr; e.col_shift = nullptr; e.affine_post = 0; e.relu_post = 0; e.opt = 3;
   return e;
 }
 
@@ -331,6 +333,7 @@ template <class AL, class BL>
 int launch_gemm_simt(const AL& al, const BL& bl, Epilogue ep, int M, int N, int K, int allow_splitk,
                      cudaStream_t stream, const char* what) {
   if (M <= 0 || N <= 0) return 0;
+  tc::g_launch_counts[2]++;
   long long tiles_big = (long long)cdiv(M, 128) * cdiv(N, 128);
   bool big = (tiles_big >= 120) && N >= 96;
   int BM = big ? 128 : 64, BN = big ? 128 : 64;

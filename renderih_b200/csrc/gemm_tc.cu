@@ -109,6 +109,9 @@ static int g_persistent = 1;     // 0 = one CTA per tile (non-persistent kernel;
 void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
 void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
+long long g_launch_counts[3] = {0, 0, 0};   // tensor-core launches with the TMA-store epilogue / with per-thread stores / SIMT GEMM launches (rih_gemm_launch_counts)
+static int g_epi_opt = 3;        // Epilogue::opt of every launch (rih_set_epilogue_opt)
+void set_epilogue_opt(int v) { g_epi_opt = v & 3; }
 static int g_tma_res = 1;        // residual rows read by the TMA-store epilogue (0: GEMMs with a residual use per-thread global stores, as before)
 void set_tma_res(int on) { g_tma_res = on ? 1 : 0; }
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>
@@ -138,6 +141,8 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep,
   } else {
     tc_ = ta;
   }
+  if (ep.col_scale && ep.bias) { set_error("gemm_tc: a folded per-column affine and a bias cannot be combined (fold the bias into the shift)"); return 1; }
+  g_launch_counts[tma_epi ? 0 : 1]++;
   if (g_persistent) {
     auto pk = gemm_tc_persistent_kernel<BN, A_MN, B_MN, Producer, NSPLIT>;
     static bool pattr = false;
@@ -173,6 +178,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, Epilogue ep,
   ep.reverse = g_reverse;
   ep.kb_rotate = g_kb_rotate;
   ep.a_policy = g_l2_hints ? 1ull : 0ull;
+  ep.opt = g_epi_opt;
   if (g_nsplit == 3) return launch_one<BN, A_MN, B_MN, Producer, 3>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s, c_map);
   if (g_nsplit == 2 && g_persistent) return launch_one<BN, A_MN, B_MN, Producer, 2>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s, c_map);
   return launch_one<BN, A_MN, B_MN, Producer, 1>(ta, tb, ep, prod, M, N, num_kb, splits, kb_per_split, s, c_map);

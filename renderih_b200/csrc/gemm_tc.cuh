@@ -185,9 +185,16 @@ constexpr int EPI_STAGING_BYTES = 2 * BM * 128;   // two [128 x 32 fp32] staging
 // named barrier and its own TMA-store bulk groups): the store-bound 1x1 convolutions (K = 64 ... 256, 128 KB of output per 128 x 256 tile)
 // were limited by the serial tcgen05.ld -> st.shared -> barrier -> TMA-store chain of one warpgroup (3.6 TB/s of 6.5).
 template <int NSPLIT> __host__ __device__ constexpr int epi_wgs() { return NSPLIT == 1 ? RIH_EPI_WGS : 1; }
-template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() {
+template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_base_bytes() {
   return num_stages<BN, NSPLIT>() * stage_bytes<BN, NSPLIT>() + EPI_STAGING_BYTES * epi_wgs<NSPLIT>() + 1024 + 256;
 }
+// Per-column epilogue vectors of the tile's BN columns cached in shared memory (persistent kernel): [0] = multiplicative (folded BatchNorm scale),
+// [1] = additive (bias or folded BatchNorm shift).  Every epilogue thread needs all 32 values of a chunk: 16 broadcast LDS.128 instead of 64
+// broadcast LDG.32 per chunk.  Only when it fits next to the stage ring (it does not for 3xTF32 128 x 256 tiles: global loads there).
+template <int BN, int NSPLIT> __host__ __device__ constexpr int colvec_bytes() {
+  return (smem_base_bytes<BN, NSPLIT>() + 2 * BN * 4 <= 227 * 1024) ? 2 * BN * 4 : 0;
+}
+template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() { return smem_base_bytes<BN, NSPLIT>() + colvec_bytes<BN, NSPLIT>(); }
 
 // ---------------------------------------------------------------- producers (TMA issue logic, one elected lane)
 // Each producer loads, for k-block `kb`, the A tile (BM x 32) to `sa` and the B tile (BN x 32) to `sb`.
@@ -397,32 +404,65 @@ struct StemWgradProducer {
 };
 
 // Epilogue arithmetic of one 32-column chunk held in registers (row m, columns nb .. nb+31): the same sequence as Epilogue::store4.
-__device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep, int m, int nb, unsigned long long dseed) {
+//   pre  : the residual row chunk already in registers (prefetched by the caller) or nullptr = load it here
+//   cmul / cadd : this chunk's 32 multiplicative / additive column values in shared memory (see colvec_bytes) or nullptr = global loads
+__device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep, int m, int nb, unsigned long long dseed,
+                                              const float4* pre = nullptr, const float* cmul = nullptr, const float* cadd = nullptr) {
   if (ep.scale != 1.f) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= ep.scale;
   }
-  if (ep.col_scale && !ep.affine_post) {
+  const bool affine = ep.col_scale != nullptr;
+  if (cadd) {                       // cached column vectors: columns beyond N hold 1 / 0
+    if (affine && !ep.affine_post) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] = fmaf(v[j], __ldg(ep.col_scale + nb + j), __ldg(ep.col_shift + nb + j));
-  }
-  if (ep.bias) {
+      for (int j = 0; j < 8; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(cmul + 4 * j), b = *reinterpret_cast<const float4*>(cadd + 4 * j);
+        v[4 * j] = fmaf(v[4 * j], a.x, b.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, b.y);
+        v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, b.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, b.w);
+      }
+    } else if (ep.bias) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] += __ldg(ep.bias + nb + j);
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = *reinterpret_cast<const float4*>(cadd + 4 * j);
+        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    }
+  } else {
+    if (affine && !ep.affine_post) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] = fmaf(v[j], __ldg(ep.col_scale + nb + j), __ldg(ep.col_shift + nb + j));
+    }
+    if (ep.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] += __ldg(ep.bias + nb + j);
+    }
   }
   if (ep.relu) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
-  if (ep.col_scale && ep.affine_post) {
+  if (affine && ep.affine_post) {
+    if (cadd) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] = fmaf(v[j], __ldg(ep.col_scale + nb + j), __ldg(ep.col_shift + nb + j));
+      for (int j = 0; j < 8; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(cmul + 4 * j), b = *reinterpret_cast<const float4*>(cadd + 4 * j);
+        v[4 * j] = fmaf(v[4 * j], a.x, b.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, b.y);
+        v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, b.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, b.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (nb + j < ep.N) v[j] = fmaf(v[j], __ldg(ep.col_scale + nb + j), __ldg(ep.col_shift + nb + j));
+    }
   }
   if (ep.thresh) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= dropout_scale(dseed, (uint64_t)m * ep.N + nb + j, ep.thresh, ep.inv_keep);
   }
-  if (ep.res && m < ep.M) {        // residual row: 128 contiguous bytes per thread (host checked 16-byte alignment and N % 4 == 0)
+  if (pre) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[4 * j] += pre[j].x; v[4 * j + 1] += pre[j].y; v[4 * j + 2] += pre[j].z; v[4 * j + 3] += pre[j].w; }
+  } else if (ep.res && m < ep.M) {        // residual row: 128 contiguous bytes per thread (host checked 16-byte alignment and N % 4 == 0)
     const float4* r4 = reinterpret_cast<const float4*>(ep.res + (size_t)m * ep.ldres + nb);
 #pragma unroll
     for (int j = 0; j < 8; ++j) if (nb + 4 * j < ep.N) {
@@ -433,6 +473,17 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep
   if (ep.relu_post) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+}
+// residual row chunk (row m, columns nb .. nb+31) into registers; zeros outside the matrix
+__device__ __forceinline__ void load_res_chunk(float4 (&r)[8], const Epilogue& ep, int m, int nb) {
+  if (m < ep.M) {
+    const float4* p = reinterpret_cast<const float4*>(ep.res + (size_t)m * ep.ldres + nb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = (nb + 4 * j < ep.N) ? __ldg(p + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -631,6 +682,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   uint64_t* tmem_full = bars + 3 * STAGES;       // [2]
   uint64_t* tmem_empty = bars + 3 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  constexpr bool COLVEC = colvec_bytes<BN, NSPLIT>() > 0;
+  float* const colvec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);      // [2][BN] when COLVEC
 
   pdl_launch_dependents();     // the stream successor may start its own prologue now; it blocks in its pdl_wait() until this grid is done
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -781,16 +834,49 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       }
     };
     uint32_t tc = 0, cc = 0;
+    // residual rows are prefetched one chunk ahead into registers (the first chunk of a tile before the wait for its accumulator): a load issued
+    // inside the chunk's own arithmetic exposed one DRAM latency per chunk (conv3 + identity of a bottleneck: 230 us for 603 MB)
+    const bool use_res = tma_epi && ep.res != nullptr && !batched && !ep.nv_pad && (ep.opt & 1);
+    const bool use_cv = COLVEC && tma_epi && !batched && !ep.nv_pad && (ep.bias != nullptr || ep.col_scale != nullptr) && (ep.opt & 2);
+    // single-pass TF32 kernels (320 threads, 204 registers each) double-buffer the prefetch: chunk c + 1 is requested before chunk c's accumulator
+    // is read; the operand-splitting kernels (448 threads, 128 registers) re-use one buffer and request the next chunk at the end of the current one
+    constexpr bool RES_DB = (NSPLIT == 1);
+    float4 rcur[8], rnext[RES_DB ? 8 : 1];
+    int cv_n0 = -1;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
       int m0, n0, kb_beg, nkb, z;
       tile_coords(t, m0, n0, kb_beg, nkb, z);
       const uint32_t acc = tc & 1, aph = (tc >> 1) & 1;
+      const int m = m0 + rr;
+      if (use_res) load_res_chunk(rcur, ep, m, n0 + wg * 32);
+      if (use_cv && n0 != cv_n0) {       // this warpgroup's chunks of the tile's column vectors -> shared memory (all its threads are past the last read)
+        const int tw = threadIdx.x - (EPI_WARP0 + 4 * wg) * 32;      // 0..127 inside the warpgroup
+        for (int i = tw; i < NCH_WG * 32; i += 128) {
+          const int col = n0 + ((i >> 5) * EPI_WG + wg) * 32 + (i & 31);
+          const bool in = col < ep.N;
+          float mul = 1.f, add = 0.f;
+          if (ep.col_scale) { if (in) { mul = __ldg(ep.col_scale + col); add = __ldg(ep.col_shift + col); } }
+          else if (in) add = __ldg(ep.bias + col);
+          colvec[wg * NCH_WG * 32 + i] = mul;
+          colvec[BN + wg * NCH_WG * 32 + i] = add;
+        }
+        cv_n0 = n0;
+        epi_bar_sync(wg);
+      }
       mbar_wait(&tmem_full[acc], aph);
       tc_fence_after();
-      const int m = m0 + rr;
       if (ep.stats && n0 != acc_n0) { flush_stats(); acc_n0 = n0; }
 #pragma unroll 1
       for (int c = wg; c < NCHUNK; c += EPI_WG) {
+        if constexpr (RES_DB) {
+          if (use_res) {
+            if (c != wg) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
+            }
+            if (c + EPI_WG < NCHUNK) load_res_chunk(rnext, ep, m, n0 + (c + EPI_WG) * 32);
+          }
+        }
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
         if (c == last_c) {             // all TMEM reads of this accumulator by this thread are done: hand it back to the MMA warp
@@ -805,7 +891,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         }
         if (batched && nb >= ep.N) continue;   // e.g. head dim 16 in a 64-wide tile: nothing to store
         if (tma_epi) {
-          epilogue_math(v, ep, m, nb, dseed);
+          const float* cmul = use_cv ? colvec + (wg * NCH_WG + (c - wg) / EPI_WG) * 32 : nullptr;
+          epilogue_math(v, ep, m, nb, dseed, use_res ? rcur : nullptr, cmul, use_cv ? cmul + BN : nullptr);
           if (cc >= 2) {
             if (elected) tma_store_wait_read<1>();
             epi_bar_sync(wg);
@@ -860,6 +947,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             for (int k = 0; k < NCH_WG; ++k) if (k == ci) { racc1[k] += (double)s1[0]; racc2[k] += (double)s2[0]; }
           }
           ++cc;
+          if constexpr (!RES_DB) {
+            if (use_res && c + EPI_WG < NCHUNK) load_res_chunk(rcur, ep, m, n0 + (c + EPI_WG) * 32);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
