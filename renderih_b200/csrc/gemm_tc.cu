@@ -102,7 +102,7 @@ int g_stats_fused = 0;            // set by the launcher when the epilogue accum
 static int g_wide_tiles = 1;     // 128 x 256 output tiles when N % 256 == 0
 void set_wide_tiles(int on) { g_wide_tiles = on ? 1 : 0; }
 static int g_wgrad_wide = 1;     // 256-wide multi-tap N tiles for the convolution weight gradients (rih_set_wgrad_wide)
-void set_wgrad_wide(int on) { g_wgrad_wide = on ? 1 : 0; }
+void set_wgrad_wide(int on) { g_wgrad_wide = on & 3; }     // bit 0: multi-tap 256-wide tiles, bit 1: also for channel counts that are not multiples of 32
 static int g_narrow_small = 1;   // 64-wide N tiles for GEMMs whose 128-wide tiling would leave half of the SMs idle (RIH_NARROW_TILES=0 to compare)
 void set_narrow_small(int on) { g_narrow_small = on ? 1 : 0; }
 static int g_persistent = 1;     // 0 = one CTA per tile (non-persistent kernel; debug / comparison)
@@ -452,11 +452,16 @@ int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom
   const int P = g.N * g.Ho * g.Wo, taps = g.R * g.S, Nn = taps * g.Cin;
   // Cin a multiple of 32: the 32-column chunks of an N tile never straddle a tap, so 256-wide tiles may span several taps (the dY operand is
   // re-read once per N tile: 3 times instead of 9 for Cin = 64, 9 instead of 18 for Cin = 256) -- RIH_WGRAD_WIDE=0 keeps one tap per tile
-  const bool wide = g_wgrad_wide && g_persistent && g.Cin % 32 == 0 && Nn >= 256;
+  // Channel counts that are not multiples of 32 (HRNet's 48, 80, 208 ...) take the wide tiles too, on a "virtual" grid of cin32 = ceil32(Cin)
+  // columns per tap (rih_set_wgrad_wide bit 1): 48-channel convolutions ran nine 64-wide tiles (dY re-read 9 times, 240 us vs 53 us for the
+  // 96-channel convolutions of equal flops in the HRNet-w48 step); three 256-wide tiles over 9 x 64 virtual columns instead.
+  const int cin32 = cdiv(g.Cin, 32) * 32;
+  const bool wide_pad = (g_wgrad_wide & 2) && g.Cin % 32 != 0 && g.Cin % 4 == 0 && taps * cin32 >= 256;
+  const bool wide = g_wgrad_wide && g_persistent && (g.Cin % 32 == 0 || wide_pad) && Nn >= 256;
   const int BN = wide ? 256 : ((g.Cin % 128 == 0) ? 128 : 64);
   // N tiles never straddle a tap: each tap owns ceil(Cin / BN) tiles; when BN does not divide Cin (48, 96, ...) the tile grid is
   // "virtual" (cin_pad columns per tap) and the epilogue stores through a 3-D map [Cout][taps][Cin] that clips at the tap's edge
-  const int cin_pad = wide ? g.Cin : cdiv(g.Cin, BN) * BN, Ngrid = taps * cin_pad;
+  const int cin_pad = wide ? cin32 : cdiv(g.Cin, BN) * BN, Ngrid = taps * cin_pad;
   const int bw = g.Wo < 32 ? g.Wo : 32, bh = 32 / bw;
   CUtensorMap ta, tb, tcm;
   if (make_tmap_2d(&ta, dy, P, g.Cout, g.ldy, 32, true)) return 1;

@@ -887,7 +887,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         int sc0 = nb, sc1 = 0;
         if (ep.nv_pad) {               // virtual wgrad column -> (channel, tap); chunks wholly beyond Cin are skipped (warp-uniform)
           sc1 = nb / ep.nv_pad; sc0 = nb - sc1 * ep.nv_pad;
-          if (sc0 >= ep.nv_real) continue;
+          if (sc0 >= ep.nv_real || sc1 * ep.nv_real >= ep.N) continue;      // beyond the tap's channels / beyond the last tap (wide tiles over a padded grid)
         }
         if (batched && nb >= ep.N) continue;   // e.g. head dim 16 in a 64-wide tile: nothing to store
         if (tma_epi) {

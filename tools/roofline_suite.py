@@ -38,10 +38,24 @@ run(lambda: ops.conv2d(x, w, None, B, 64, 64, stride=1, pad=1))
 x1 = torch.randn(B * 64 * 64, 64, device='cuda')
 w1 = (torch.randn(256, 64, 1, 1, device='cuda') * 0.1).contiguous(memory_format=torch.channels_last)
 run(lambda: ops.conv2d(x1, w1, None, B, 64, 64))
+# ---- round 2: inference convolutions with the eval-mode BatchNorm folded into the epilogue (layer1 of the ResNet-50 trunk)
+holder = torch.nn.Sequential(torch.nn.BatchNorm2d(256), torch.nn.BatchNorm2d(64)).cuda().eval()
+resid = torch.randn(B * 64 * 64, 256, device='cuda')
+x2 = torch.randn(B * 64 * 64, 64, device='cuda')
+w2 = (torch.randn(64, 64, 3, 3, device='cuda') * 0.04).contiguous(memory_format=torch.channels_last)
+with torch.no_grad():
+    ops.bn_fold_refresh(holder)
+    f256, f64 = holder[0]._rih_fold, holder[1]._rih_fold
+    run(lambda: ops.conv2d_bn_eval(x1, w1, B, 64, 64, 1, 0, f256, order=0, relu=True, res=resid))      # conv3 + bn3 + identity + ReLU
+    run(lambda: ops.conv2d_bn_eval(x1, w1, B, 64, 64, 1, 0, f256, order=0, relu=False))                # downsample conv + BN
+    run(lambda: ops.conv2d_bn_eval(x2, w2, B, 64, 64, 1, 1, f64, order=0, relu=True))                  # conv2 3x3 64 -> 64 + bn2 + ReLU
 # ---- token Linear (3xTF32)
 t = torch.randn(B * 252, 128, device='cuda')
 wl, bl = torch.randn(64, 128, device='cuda') * 0.1, torch.zeros(64, device='cuda')
 run(lambda: ops.linear(t, wl, bl))
+t2 = torch.randn(B * 252, 256, device='cuda')
+wl2, bl3 = torch.randn(256, 256, device='cuda') * 0.06, torch.zeros(256, device='cuda')
+run(lambda: ops.linear(t2, wl2, bl3, res=t2))          # 256 -> 256 with bias + residual (TMA-store epilogue reading the residual rows)
 # ---- attention core on tcgen05 (forward + backward kernels)
 q = torch.randn(B * 252, 64, device='cuda', requires_grad=True)
 k = torch.randn(B * 316, 64, device='cuda', requires_grad=True)
