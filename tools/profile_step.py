@@ -50,7 +50,8 @@ def main():
         return calc_loss_GCN(cfg, 0, gl, gr, conv['left'], conv['right'], out[0], out[1], out[2], out[3], None, None, None,
                              lab['v2d_l'], z[..., :2], lab['v2d_r'], z[..., :2], lab['v3d_l'], z, lab['v3d_r'], z, lab['root_rel'], 256)[0]
 
-    fp = FlatParams(trainable_used_params(model, loss_fn, img))
+    groups = [g for m in model.modules() if hasattr(m, 'fused_param_groups') for g in m.fused_param_groups()]      # as train.TrainStep does
+    fp = FlatParams(trainable_used_params(model, loss_fn, img), groups=groups)
 
     def step():
         if args.fwd_only:
