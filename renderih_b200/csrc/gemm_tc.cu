@@ -101,7 +101,7 @@ int make_tmap_wgrad_out(CUtensorMap* map, const float* base, int Cout, int taps,
 int g_stats_fused = 0;            // set by the launcher when the epilogue accumulated ep.stats (fused BatchNorm statistics)
 static int g_wide_tiles = 1;     // 128 x 256 output tiles when N % 256 == 0
 void set_wide_tiles(int on) { g_wide_tiles = on ? 1 : 0; }
-static int g_wgrad_wide = 1;     // 256-wide multi-tap N tiles for the convolution weight gradients (rih_set_wgrad_wide)
+static int g_wgrad_wide = 3;     // 256-wide multi-tap N tiles for the convolution weight gradients, also over padded channel counts (rih_set_wgrad_wide)
 void set_wgrad_wide(int on) { g_wgrad_wide = on & 3; }     // bit 0: multi-tap 256-wide tiles, bit 1: also for channel counts that are not multiples of 32
 static int g_narrow_small = 1;   // 64-wide N tiles for GEMMs whose 128-wide tiling would leave half of the SMs idle (RIH_NARROW_TILES=0 to compare)
 void set_narrow_small(int on) { g_narrow_small = on ? 1 : 0; }
