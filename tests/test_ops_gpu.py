@@ -712,3 +712,50 @@ def test_bn_fold_tracks_live_running_statistics(ops):
         ref_shift = b1.bias - b1.running_mean * b1.weight / (b1.running_var + b1.eps).sqrt()
         assert rel(b1._rih_fold[1], ref_shift) < 1e-6
     assert not ops.bn_fold_refresh(root)          # gradients enabled: the folded inference path is off
+
+
+@pytest.mark.parametrize('opt', [0, 1, 2, 3, 7])
+@pytest.mark.parametrize('M,N,K,mode', [(8064, 256, 256, 'tf32x3'), (4032, 128, 256, 'tf32x3'), (1000, 64, 64, 'tf32x3'), (16384, 256, 64, 'tf32')])
+def test_epilogue_options_linear_with_bias_and_residual(ops, opt, M, N, K, mode):
+    """rih_set_epilogue_opt: residual prefetch (bit 0), column vectors in shared memory (bit 1), coalesced residual through the staging tile
+    (bit 2) are pure re-schedulings of the same arithmetic: y = relu(x W^T + b) + res must not depend on them (ragged M: 1000 rows)."""
+    from renderih_b200._lib import call
+    x, w, b, res = T(M, K, grad=False), T(N, K, scale=K ** -0.5, seed=1, grad=False), T(N, seed=2, grad=False), T(M, N, seed=3, grad=False)
+    call('rih_set_epilogue_opt', opt)
+    ops.set_gemm_mode(mode, mode)
+    try:
+        with torch.no_grad():
+            y = ops.linear(x, w, b, relu=True, res=res)
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+        call('rih_set_epilogue_opt', 3)
+    ref = (torch.relu(x.double() @ w.double().t() + b.double()) + res.double()).float()
+    tol = 2e-5 if mode == 'tf32x3' else 3e-3
+    assert rel(y, ref) < tol, rel(y, ref)
+
+
+@pytest.mark.parametrize('opt', [0, 7])
+def test_epilogue_options_folded_conv_with_residual(ops, opt):
+    """conv3 + bn3 + identity + ReLU of a layer1 bottleneck (1x1, 64 -> 256) with every epilogue option off / on."""
+    from renderih_b200._lib import call
+    N, H, Cin, Cout = 2, 64, 64, 256
+    conv = torch.nn.Conv2d(Cin, Cout, 1, bias=False).to(DEV)
+    conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)
+    bn = torch.nn.BatchNorm2d(Cout).to(DEV).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0)
+    x, res = T(N, Cin, H, H, grad=False), T(N, Cout, H, H, seed=5, grad=False)
+    rows = lambda t: t.permute(0, 2, 3, 1).contiguous().reshape(-1, t.shape[1])
+    call('rih_set_epilogue_opt', opt)
+    ops.set_gemm_mode('tf32x3', 'tf32x3')
+    try:
+        with torch.no_grad():
+            assert ops.bn_fold_refresh(torch.nn.Sequential(bn))
+            y = ops.conv2d_bn_eval(rows(x), conv.weight, N, H, H, 1, 0, bn._rih_fold, order=0, relu=True, res=rows(res))
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+        call('rih_set_epilogue_opt', 3)
+    with torch.no_grad():
+        r = F.relu(F.batch_norm(F.conv2d(x.double(), conv.weight.double()), bn.running_mean.double(), bn.running_var.double(), bn.weight.double(),
+                                bn.bias.double(), False, 0.0, bn.eps) + res.double())
+    assert rel(y, rows(r).float()) < 2e-5, rel(y, rows(r).float())
