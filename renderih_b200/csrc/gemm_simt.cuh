@@ -178,7 +178,7 @@ struct Epilogue {
   int affine_post;                             //   0: applied to the accumulator BEFORE bias / ReLU (torchvision order Conv -> BN -> (+res) -> ReLU)
                                                //   1: applied AFTER the ReLU (repo order Conv -> ReLU -> BN)
   int relu_post;                               // ReLU after the residual add (the block's final activation)
-  int opt;                                     // tensor-core persistent epilogue: bit 0 = residual rows prefetched a chunk ahead, bit 1 = column vectors cached in shared memory, bit 2 = residual read coalesced and redistributed through the staging tile (rih_set_epilogue_opt)
+  int opt;                                     // tensor-core persistent epilogue: bit 0 = residual rows prefetched a chunk ahead, bit 1 = column vectors cached in shared memory (rih_set_epilogue_opt)
   __device__ __forceinline__ void store4(int m, int n, float4 v) const {
     if (m >= M || n >= N) return;
     float* q = c + (size_t)m * ldc + n;

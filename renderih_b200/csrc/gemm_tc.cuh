@@ -406,9 +406,8 @@ struct StemWgradProducer {
 // Epilogue arithmetic of one 32-column chunk held in registers (row m, columns nb .. nb+31): the same sequence as Epilogue::store4.
 //   pre  : the residual row chunk already in registers (prefetched by the caller) or nullptr = load it here
 //   cmul / cadd : this chunk's 32 multiplicative / additive column values in shared memory (see colvec_bytes) or nullptr = global loads
-//   tail = false: stop before the residual add / final ReLU (the caller adds a residual staged in shared memory, see load_res_chunk_coal)
 __device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep, int m, int nb, unsigned long long dseed,
-                                              const float4* pre = nullptr, const float* cmul = nullptr, const float* cadd = nullptr, bool tail = true) {
+                                              const float4* pre = nullptr, const float* cmul = nullptr, const float* cadd = nullptr) {
   if (ep.scale != 1.f) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= ep.scale;
@@ -460,7 +459,6 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= dropout_scale(dseed, (uint64_t)m * ep.N + nb + j, ep.thresh, ep.inv_keep);
   }
-  if (!tail) return;
   if (pre) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { v[4 * j] += pre[j].x; v[4 * j + 1] += pre[j].y; v[4 * j + 2] += pre[j].z; v[4 * j + 3] += pre[j].w; }
@@ -475,17 +473,6 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep
   if (ep.relu_post) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-  }
-}
-// Coalesced form: the warp reads its 32 rows x 128 bytes of the residual as 8 requests of 4 full rows (lane -> row i * 4 + lane / 8, 16-byte piece
-// lane % 8) instead of 8 requests that touch 32 different rows each; the pieces go through the staging tile to reach the thread that owns the row.
-__device__ __forceinline__ void load_res_chunk_coal(float4 (&r)[8], const Epilogue& ep, int mw0, int nb, int lane) {
-  const int col = nb + (lane & 7) * 4;
-  const bool cok = col < ep.N;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = mw0 + i * 4 + (lane >> 3);
-    r[i] = (cok && row < ep.M) ? __ldg(reinterpret_cast<const float4*>(ep.res + (size_t)row * ep.ldres + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 // residual row chunk (row m, columns nb .. nb+31) into registers; zeros outside the matrix
@@ -855,17 +842,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     // is read; the operand-splitting kernels (448 threads, 128 registers) re-use one buffer and request the next chunk at the end of the current one
     constexpr bool RES_DB = (NSPLIT == 1);
     float4 rcur[8], rnext[RES_DB ? 8 : 1];
-    const bool res_stage = use_res && (ep.opt & 4);      // coalesced residual reads, redistributed through the staging tile
     int cv_n0 = -1;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
       int m0, n0, kb_beg, nkb, z;
       tile_coords(t, m0, n0, kb_beg, nkb, z);
       const uint32_t acc = tc & 1, aph = (tc >> 1) & 1;
       const int m = m0 + rr;
-      if (use_res) {
-        if (res_stage) load_res_chunk_coal(rcur, ep, m0 + q * 32, n0 + wg * 32, lane);
-        else load_res_chunk(rcur, ep, m, n0 + wg * 32);
-      }
+      if (use_res) load_res_chunk(rcur, ep, m, n0 + wg * 32);
       if (use_cv && n0 != cv_n0) {       // this warpgroup's chunks of the tile's column vectors -> shared memory (all its threads are past the last read)
         const int tw = threadIdx.x - (EPI_WARP0 + 4 * wg) * 32;      // 0..127 inside the warpgroup
         for (int i = tw; i < NCH_WG * 32; i += 128) {
@@ -891,10 +874,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
 #pragma unroll
               for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
             }
-            if (c + EPI_WG < NCHUNK) {
-              if (res_stage) load_res_chunk_coal(rnext, ep, m0 + q * 32, n0 + (c + EPI_WG) * 32, lane);
-              else load_res_chunk(rnext, ep, m, n0 + (c + EPI_WG) * 32);
-            }
+            if (c + EPI_WG < NCHUNK) load_res_chunk(rnext, ep, m, n0 + (c + EPI_WG) * 32);
           }
         }
         float v[32];
@@ -912,31 +892,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         if (batched && nb >= ep.N) continue;   // e.g. head dim 16 in a 64-wide tile: nothing to store
         if (tma_epi) {
           const float* cmul = use_cv ? colvec + (wg * NCH_WG + (c - wg) / EPI_WG) * 32 : nullptr;
-          epilogue_math(v, ep, m, nb, dseed, use_res ? rcur : nullptr, cmul, use_cv ? cmul + BN : nullptr, !res_stage);
+          epilogue_math(v, ep, m, nb, dseed, use_res ? rcur : nullptr, cmul, use_cv ? cmul + BN : nullptr);
           if (cc >= 2) {
             if (elected) tma_store_wait_read<1>();
             epi_bar_sync(wg);
           }
           uint8_t* buf = wg_staging + (cc & 1) * (BM * 128);
-          if (res_stage) {
-            // the prefetched residual pieces (coalesced layout) -> the staging tile at the swizzled position of their (row, piece); the rows of this
-            // warp's quarter are written and read by this warp only, so a warp-level sync orders the exchange
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rowt = q * 32 + i * 4 + (lane >> 3);
-              *reinterpret_cast<float4*>(buf + rowt * 128 + (((lane & 7) ^ (rowt & 7)) << 4)) = rcur[i];
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r4 = *reinterpret_cast<const float4*>(buf + rr * 128 + ((j ^ (rr & 7)) << 4));
-              v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
-            }
-            if (ep.relu_post) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-          }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(buf + rr * 128 + ((j ^ (rr & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -987,10 +948,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           }
           ++cc;
           if constexpr (!RES_DB) {
-            if (use_res && c + EPI_WG < NCHUNK) {
-              if (res_stage) load_res_chunk_coal(rcur, ep, m0 + q * 32, n0 + (c + EPI_WG) * 32, lane);
-              else load_res_chunk(rcur, ep, m, n0 + (c + EPI_WG) * 32);
-            }
+            if (use_res && c + EPI_WG < NCHUNK) load_res_chunk(rcur, ep, m, n0 + (c + EPI_WG) * 32);
           }
         } else {
 #pragma unroll

@@ -714,27 +714,27 @@ def test_bn_fold_tracks_live_running_statistics(ops):
     assert not ops.bn_fold_refresh(root)          # gradients enabled: the folded inference path is off
 
 
-@pytest.mark.parametrize('opt', [0, 1, 2, 3, 7])
+@pytest.mark.parametrize('opt', [0, 1, 2, 3])
 @pytest.mark.parametrize('M,N,K,mode', [(8064, 256, 256, 'tf32x3'), (4032, 128, 256, 'tf32x3'), (1000, 64, 64, 'tf32x3'), (16384, 256, 64, 'tf32')])
 def test_epilogue_options_linear_with_bias_and_residual(ops, opt, M, N, K, mode):
-    """rih_set_epilogue_opt: residual prefetch (bit 0), column vectors in shared memory (bit 1), coalesced residual through the staging tile
-    (bit 2) are pure re-schedulings of the same arithmetic: y = relu(x W^T + b) + res must not depend on them (ragged M: 1000 rows)."""
+    """rih_set_epilogue_opt: residual prefetch (bit 0) and column vectors in shared memory (bit 1) are pure re-schedulings of the same
+    arithmetic: y = x W^T + b + res must not depend on them (ragged M: 1000 rows)."""
     from renderih_b200._lib import call
     x, w, b, res = T(M, K, grad=False), T(N, K, scale=K ** -0.5, seed=1, grad=False), T(N, seed=2, grad=False), T(M, N, seed=3, grad=False)
     call('rih_set_epilogue_opt', opt)
     ops.set_gemm_mode(mode, mode)
     try:
         with torch.no_grad():
-            y = ops.linear(x, w, b, relu=True, res=res)
+            y = ops.linear(x, w, b, res=res)
     finally:
         ops.set_gemm_mode('simt', 'simt')
         call('rih_set_epilogue_opt', 3)
-    ref = (torch.relu(x.double() @ w.double().t() + b.double()) + res.double()).float()
+    ref = (x.double() @ w.double().t() + b.double() + res.double()).float()
     tol = 2e-5 if mode == 'tf32x3' else 3e-3
     assert rel(y, ref) < tol, rel(y, ref)
 
 
-@pytest.mark.parametrize('opt', [0, 7])
+@pytest.mark.parametrize('opt', [0, 3])
 def test_epilogue_options_folded_conv_with_residual(ops, opt):
     """conv3 + bn3 + identity + ReLU of a layer1 bottleneck (1x1, 64 -> 256) with every epilogue option off / on."""
     from renderih_b200._lib import call

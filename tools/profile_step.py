@@ -32,7 +32,8 @@ def main():
     cfg.MODEL.ENCODER_TYPE = args.encoder
     a = A.synthetic_assets(0)
     torch.manual_seed(88)
-    model = load_model(cfg, assets=a).cuda().train()
+    model = load_model(cfg, assets=a).cuda()
+    model = model.eval() if args.fwd_only else model.train()       # --fwd-only = the eval forward of bench.py --config forward
     model.decoder.unsample_layer.weight.requires_grad_(False)
     B = args.batch
     img = torch.randn(B, 3, 256, 256, device='cuda')
