@@ -178,7 +178,7 @@ struct Epilogue {
   int affine_post;                             //   0: applied to the accumulator BEFORE bias / ReLU (torchvision order Conv -> BN -> (+res) -> ReLU)
                                                //   1: applied AFTER the ReLU (repo order Conv -> ReLU -> BN)
   int relu_post;                               // ReLU after the residual add (the block's final activation)
-  int opt;                                     // tensor-core persistent epilogue: bit 0 = residual rows prefetched a chunk ahead, bit 1 = column vectors cached in shared memory (rih_set_epilogue_opt)
+  int opt;                                     // tensor-core persistent epilogue: bit 0 = residual rows prefetched a chunk ahead, bit 1 = column vectors cached in shared memory, bit 2 = the producer warp issues a k-block's TMA boxes from all lanes (rih_set_epilogue_opt)
   __device__ __forceinline__ void store4(int m, int n, float4 v) const {
     if (m >= M || n >= N) return;
     float* q = c + (size_t)m * ldc + n;
@@ -204,7 +204,7 @@ struct Epilogue {
 static inline Epilogue make_epilogue(float* c, int ldc, int M, int N, const float* bias, int relu, int mode) {
   Epilogue e; e.c = c; e.ldc = ldc; e.M = M; e.N = N; e.bias = bias; e.relu = relu; e.mode = mode;
   e.res = nullptr; e.ldres = 0; e.seed_ptr = nullptr; e.site = 0; e.thresh = 0; e.inv_keep = 1.f; e.stats = nullptr; e.scale = 1.f; e.nv_pad = 0; e.nv_real = 0; e.batch_heads = 0; e.s2_w2 = 0; e.s2_h2 = 0; e.s2_ph = 0; e.s2_pw = 0; e.kb_rotate = 0; e.reverse = 0; e.a_policy = 0ull;
-  e.col_scale = nullptr; e.col_shift = nullptr; e.affine_post = 0; e.relu_post = 0; e.opt = 3;
+  e.col_scale = nullptr; e.col_shift = nullptr; e.affine_post = 0; e.relu_post = 0; e.opt = 7;
   return e;
 }
 

@@ -110,8 +110,8 @@ void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
 void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
 long long g_launch_counts[3] = {0, 0, 0};   // tensor-core launches with the TMA-store epilogue / with per-thread stores / SIMT GEMM launches (rih_gemm_launch_counts)
-static int g_epi_opt = 3;        // Epilogue::opt of every launch (rih_set_epilogue_opt)
-void set_epilogue_opt(int v) { g_epi_opt = v & 3; }
+static int g_epi_opt = 7;        // Epilogue::opt of every launch (rih_set_epilogue_opt)
+void set_epilogue_opt(int v) { g_epi_opt = v & 7; }
 static int g_tma_res = 1;        // residual rows read by the TMA-store epilogue (0: GEMMs with a residual use per-thread global stores, as before)
 void set_tma_res(int on) { g_tma_res = on ? 1 : 0; }
 template <int BN, bool A_MN, bool B_MN, class Producer, int NSPLIT>

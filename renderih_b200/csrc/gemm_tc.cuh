@@ -204,17 +204,18 @@ struct DenseProducer {
   int kbeg;
   unsigned long long a_policy;   // 0 = no hint
   __device__ __forceinline__ void set_policy(unsigned long long p) { a_policy = p; }
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
+    // (lane, nl): this call issues the operations lane, lane + nl, ... of each operand -- (0, 1) = everything from one thread; the persistent
+    // kernel calls it from all 32 lanes of the producer warp (nl = 32), so the 4 + BN / 32 four-KB boxes of MN-major operands are issued in
+    // parallel instead of one after the other by a single thread (the weight-gradient GEMMs spent 2 us per k-block issuing 12 boxes)
     const int k0 = kb * BK;
-    if constexpr (!A_MN) { if (a_policy) tma_load_2d_hint(sa, ta, k0, m0, bar, a_policy); else tma_load_2d(sa, ta, k0, m0, bar); }
+    if constexpr (!A_MN) { if (lane == 0) { if (a_policy) tma_load_2d_hint(sa, ta, k0, m0, bar, a_policy); else tma_load_2d(sa, ta, k0, m0, bar); } }
     else {
-#pragma unroll
-      for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, k0, bar);
+      for (int c = lane; c < BM / 32; c += nl) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, k0, bar);
     }
-    if constexpr (!B_MN) tma_load_2d(sb, tb, k0, n0, bar);
+    if constexpr (!B_MN) { if (lane == (nl > 1 ? 1 : 0)) tma_load_2d(sb, tb, k0, n0, bar); }
     else {
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, n0 + c * 32, k0, bar);
+      for (int c = lane; c < BN / 32; c += nl) tma_load_2d(sb + c * (BK * 128), tb, n0 + c * 32, k0, bar);
     }
   }
 };
@@ -234,17 +235,15 @@ struct BatchedProducer {
     if (tok) tma_load_4d(dst, m, col, z % H, row, z / H, bar);
     else tma_load_4d(dst, m, col, row, z, 0, bar);
   }
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
     const int k0 = kb * BK;
-    if constexpr (!A_MN) ld4(sa, ta, a_tok, k0, m0, z, bar);
+    if constexpr (!A_MN) { if (lane == 0) ld4(sa, ta, a_tok, k0, m0, z, bar); }
     else {
-#pragma unroll
-      for (int c = 0; c < BM / 32; ++c) ld4(sa + c * (BK * 128), ta, a_tok, m0 + c * 32, k0, z, bar);
+      for (int c = lane; c < BM / 32; c += nl) ld4(sa + c * (BK * 128), ta, a_tok, m0 + c * 32, k0, z, bar);
     }
-    if constexpr (!B_MN) ld4(sb, tb, b_tok, k0, n0, z, bar);
+    if constexpr (!B_MN) { if (lane == (nl > 1 ? 1 : 0)) ld4(sb, tb, b_tok, k0, n0, z, bar); }
     else {
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) ld4(sb + c * (BK * 128), tb, b_tok, n0 + c * 32, k0, z, bar);
+      for (int c = lane; c < BN / 32; c += nl) ld4(sb + c * (BK * 128), tb, b_tok, n0 + c * 32, k0, z, bar);
     }
   }
 };
@@ -271,7 +270,7 @@ struct ConvFwdProducer {
   ConvTcGeom g;
   unsigned long long a_policy;
   __device__ __forceinline__ void set_policy(unsigned long long p) { a_policy = p; }
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
     // channel blocks per tap; when Cin % 32 != 0 the last block of a tap is partly out of bounds in the activation map (TMA zero
     // fill), which also cancels whatever the weight box picks up from the next tap's columns
     const int cpb = (g.Cin + BK - 1) / BK;
@@ -279,6 +278,8 @@ struct ConvFwdProducer {
     const int r = tap / g.S, s = tap - r * g.S;
     const int P = g.Ho * g.Wo;
     const int n = m0 / P, oh0 = (m0 - n * P) / g.Wo;
+    if (lane == (nl > 1 ? 1 : 0)) tma_load_2d(sb, tb, tap * g.Cin + c0, n0, bar);
+    if (lane != 0) return;
     if (g.s2_images < 0) {
       tma_load_4d(sa, ta, c0, s - g.pad, 2 * oh0 + r - g.pad, n, bar);
     } else if (g.s2_images > 0) {
@@ -291,7 +292,6 @@ struct ConvFwdProducer {
     } else {
       tma_load_4d(sa, ta, c0, s - g.pad, oh0 + r - g.pad, n, bar);
     }
-    tma_load_2d(sb, tb, tap * g.Cin + c0, n0, bar);
   }
 };
 // dgrad (stride 1): A = shifted dY boxes (4-D map over [N,Ho,Wo,Cout]), B = weights as MN-major chunks {32 c, 32 co}
@@ -299,15 +299,14 @@ template <int BN>
 struct ConvDgradProducer {
   ConvTcGeom g;
   __device__ __forceinline__ void set_policy(unsigned long long) {}
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
     const int cpb = (g.Cout + BK - 1) / BK;
     const int tap = kb / cpb, co0 = (kb - tap * cpb) * BK;
     const int r = tap / g.S, s = tap - r * g.S;
     const int P = g.H * g.W;
     const int n = m0 / P, ih0 = (m0 - n * P) / g.W;
-    tma_load_4d(sa, ta, co0, g.pad - s, ih0 + g.pad - r, n, bar);
-#pragma unroll
-    for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, tap * g.Cin + n0 + c * 32, co0, bar);
+    if (lane == 0) tma_load_4d(sa, ta, co0, g.pad - s, ih0 + g.pad - r, n, bar);
+    for (int c = (nl > 1 ? lane - 1 : 0); c < BN / 32; c += nl) if (c >= 0) tma_load_2d(sb + c * (BK * 128), tb, tap * g.Cin + n0 + c * 32, co0, bar);
   }
 };
 // dgrad of a stride-2 convolution, one PARITY CLASS of input pixels (ih, iw) = (2 i + ph, 2 j + pw): only the taps r = ph + pad (mod 2),
@@ -320,14 +319,13 @@ struct ConvDgradS2Producer {
   int ntaps;
   int tap[4], dr[4], ds[4];
   __device__ __forceinline__ void set_policy(unsigned long long) {}
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
     const int cpb = (g.Cout + BK - 1) / BK;
     const int ti = kb / cpb, co0 = (kb - ti * cpb) * BK;
     const int P = g.H * g.W;
     const int n = m0 / P, i0 = (m0 - n * P) / g.W;
-    tma_load_4d(sa, ta, co0, ds[ti], i0 + dr[ti], n, bar);
-#pragma unroll
-    for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, tap[ti] * g.Cin + n0 + c * 32, co0, bar);
+    if (lane == 0) tma_load_4d(sa, ta, co0, ds[ti], i0 + dr[ti], n, bar);
+    for (int c = (nl > 1 ? lane - 1 : 0); c < BN / 32; c += nl) if (c >= 0) tma_load_2d(sb + c * (BK * 128), tb, tap[ti] * g.Cin + n0 + c * 32, co0, bar);
   }
 };
 // wgrad: A = dY as MN-major chunks {32 co, 32 pixels}, B = shifted input boxes of 32 pixels as MN-major chunks {32 c, 32 pixels}.
@@ -337,16 +335,16 @@ template <int BN>
 struct ConvWgradProducer {
   ConvTcGeom g;
   __device__ __forceinline__ void set_policy(unsigned long long) {}
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
     const int p0 = kb * BK;
     const int P = g.Ho * g.Wo;
     const int n = p0 / P, rem = p0 - n * P;
     const int oh = rem / g.Wo, ow = rem - oh * g.Wo;
     const int taps = g.R * g.S;
-#pragma unroll
-    for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
-#pragma unroll
-    for (int c = 0; c < BN / 32; ++c) {
+    // warp-wide issue (nl = 32): lanes 0 .. 3 take the dY chunks, lanes 4 .. 4 + BN / 32 - 1 one input chunk each (own tap, own coordinates)
+    for (int c = lane; c < BM / 32; c += nl) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
+    for (int c = (nl > 1 ? lane - BM / 32 : 0); c < BN / 32; c += nl) {
+      if (c < 0) continue;
       const int col = n0 + c * 32;
       int tap = col / g.cin_pad, cbase = col - tap * g.cin_pad;
       if (tap >= taps) { tap = 0; cbase = g.cin_pad + 64; }      // beyond the last tap: a channel coordinate outside the tensor -> the TMA unit zero-fills
@@ -376,11 +374,11 @@ template <int BN>
 struct StemFwdProducer {
   int Ho, Wo;
   __device__ __forceinline__ void set_policy(unsigned long long) {}
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
     const int P = Ho * Wo;
     const int n = m0 / P, oh = (m0 - n * P) / Wo;
-    tma_load_4d(sa, ta, 0, 0, 2 * oh + kb, n, bar);       // filter row r = kb
-    tma_load_2d(sb, tb, kb * 32, n0, bar);
+    if (lane == 0) tma_load_4d(sa, ta, 0, 0, 2 * oh + kb, n, bar);       // filter row r = kb
+    if (lane == (nl > 1 ? 1 : 0)) tma_load_2d(sb, tb, kb * 32, n0, bar);
   }
 };
 // weight gradient of the stem: dW[64][7 x 32] = sum over pixels dY^T . X', k-block = 32 consecutive output pixels of one output row
@@ -388,15 +386,14 @@ template <int BN>
 struct StemWgradProducer {
   int Ho, Wo;
   __device__ __forceinline__ void set_policy(unsigned long long) {}
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar) const {
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
     const int p0 = kb * BK;
     const int P = Ho * Wo;
     const int n = p0 / P, rem = p0 - n * P;
     const int oh = rem / Wo, ow = rem - oh * Wo;
-#pragma unroll
-    for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
-#pragma unroll
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = lane; c < BM / 32; c += nl) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
+    for (int c = (nl > 1 ? lane - BM / 32 : 0); c < BN / 32; c += nl) {
+      if (c < 0) continue;
       const int r = (n0 >> 5) + c;                         // filter row of this 32-column chunk; rows >= 7 do not exist -> out-of-range row coordinate, zero fill
       tma_load_4d(sb + c * (BK * 128), tb, 0, ow, r < 7 ? 2 * oh + r : (1 << 20), n, bar);
     }
@@ -721,7 +718,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    // The whole warp produces: lane 0 waits for the stage and arms its barrier, then every lane issues its share of the k-block's TMA boxes
+    // (Producer::load(..., lane, 32)).  ep.opt bit 2 = 0 keeps the single-thread issue (lane 0 does everything) for comparison.
+    const bool wide_issue = (ep.opt & 4) != 0;
+    if (lane == 0 || wide_issue) {
       uint32_t it = 0;
       Producer pr = prod;
       pr.set_policy(ep.a_policy ? l2_policy_evict_first() : 0ull);
@@ -731,15 +731,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], AB_BYTES);
+          if (lane == 0) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], AB_BYTES);
+          }
+          if (wide_issue) __syncwarp();
           uint8_t* sa = smem + s * STAGE_BYTES;
           // k-block rotation: the sum over k does not care about the order, so each tile starts at its own k-block and wraps around --
           // CTAs that run in lockstep then fetch DIFFERENT 128-byte slices of their (1 KB-pitch) rows at any instant instead of all hitting
           // the same address bits [7, 10) of every row
           int kk = kb;
           if (ep.kb_rotate) { kk = kb + (t % nkb); if (kk >= nkb) kk -= nkb; }
-          pr.load(&tmap_a, &tmap_b, kb_beg + kk, m0, n0, z, sa, sa + A_BYTES, &full[s]);
+          pr.load(&tmap_a, &tmap_b, kb_beg + kk, m0, n0, z, sa, sa + A_BYTES, &full[s], wide_issue ? lane : 0, wide_issue ? 32 : 1);
         }
       }
     }

@@ -714,11 +714,11 @@ def test_bn_fold_tracks_live_running_statistics(ops):
     assert not ops.bn_fold_refresh(root)          # gradients enabled: the folded inference path is off
 
 
-@pytest.mark.parametrize('opt', [0, 1, 2, 3])
+@pytest.mark.parametrize('opt', [0, 1, 2, 3, 7])
 @pytest.mark.parametrize('M,N,K,mode', [(8064, 256, 256, 'tf32x3'), (4032, 128, 256, 'tf32x3'), (1000, 64, 64, 'tf32x3'), (16384, 256, 64, 'tf32')])
 def test_epilogue_options_linear_with_bias_and_residual(ops, opt, M, N, K, mode):
-    """rih_set_epilogue_opt: residual prefetch (bit 0) and column vectors in shared memory (bit 1) are pure re-schedulings of the same
-    arithmetic: y = x W^T + b + res must not depend on them (ragged M: 1000 rows)."""
+    """rih_set_epilogue_opt: residual prefetch (bit 0), column vectors in shared memory (bit 1) and warp-wide TMA issue (bit 2) are pure
+    re-schedulings of the same arithmetic: y = x W^T + b + res must not depend on them (ragged M: 1000 rows)."""
     from renderih_b200._lib import call
     x, w, b, res = T(M, K, grad=False), T(N, K, scale=K ** -0.5, seed=1, grad=False), T(N, seed=2, grad=False), T(M, N, seed=3, grad=False)
     call('rih_set_epilogue_opt', opt)
@@ -728,7 +728,7 @@ def test_epilogue_options_linear_with_bias_and_residual(ops, opt, M, N, K, mode)
             y = ops.linear(x, w, b, res=res)
     finally:
         ops.set_gemm_mode('simt', 'simt')
-        call('rih_set_epilogue_opt', 3)
+        call('rih_set_epilogue_opt', 7)
     ref = (x.double() @ w.double().t() + b.double() + res.double()).float()
     tol = 2e-5 if mode == 'tf32x3' else 3e-3
     assert rel(y, ref) < tol, rel(y, ref)
@@ -754,8 +754,31 @@ def test_epilogue_options_folded_conv_with_residual(ops, opt):
             y = ops.conv2d_bn_eval(rows(x), conv.weight, N, H, H, 1, 0, bn._rih_fold, order=0, relu=True, res=rows(res))
     finally:
         ops.set_gemm_mode('simt', 'simt')
-        call('rih_set_epilogue_opt', 3)
+        call('rih_set_epilogue_opt', 7)
     with torch.no_grad():
         r = F.relu(F.batch_norm(F.conv2d(x.double(), conv.weight.double()), bn.running_mean.double(), bn.running_var.double(), bn.weight.double(),
                                 bn.bias.double(), False, 0.0, bn.eps) + res.double())
     assert rel(y, rows(r).float()) < 2e-5, rel(y, rows(r).float())
+
+
+@pytest.mark.parametrize('opt', [3, 7])
+@pytest.mark.parametrize('N,H,Cin,Cout,k,stride', [(4, 64, 64, 64, 3, 1), (4, 32, 128, 128, 3, 2), (2, 64, 48, 48, 3, 1), (4, 32, 256, 64, 1, 1)])
+def test_warp_wide_tma_issue_conv_forward_and_gradients(ops, opt, N, H, Cin, Cout, k, stride):
+    """rih_set_epilogue_opt bit 2: every lane of the producer warp issues its share of a k-block's TMA boxes (forward: A + B box from two
+    lanes; dgrad: 1 + BN / 32 boxes; wgrad: 4 + BN / 32 four-KB boxes with per-chunk tap coordinates) -- same results as single-thread issue."""
+    from renderih_b200._lib import call
+    x = T(N, Cin, H, H)
+    w = (torch.randn(Cout, Cin, k, k) * (Cin * k * k) ** -0.5).to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xr = x.permute(0, 2, 3, 1).contiguous().reshape(N * H * H, Cin)
+    call('rih_set_epilogue_opt', opt)
+    ops.set_gemm_mode('tf32x3', 'tf32x3')
+    try:
+        y = ops.conv2d(xr, w, None, N, H, H, stride=stride, pad=k // 2)
+        g_ours = grads(y, [x, w])
+    finally:
+        ops.set_gemm_mode('simt', 'simt')
+        call('rih_set_epilogue_opt', 7)
+    yr = F.conv2d(x, w, None, stride=stride, padding=k // 2).permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert rel(y, yr) < 1e-4, rel(y, yr)
+    for a, r, n in zip(g_ours, grads(yr, [x, w]), 'xw'):
+        assert rel(a, r) < 1e-4, (n, rel(a, r))
