@@ -201,21 +201,27 @@ template <int BN, int NSPLIT> __host__ __device__ constexpr int smem_bytes() { r
 // Tiles are made of 128-byte rows; MN-major operands are split into 32-wide chunks of BK rows (4 KB apart).
 template <int BN, bool A_MN, bool B_MN>
 struct DenseProducer {
+  // WIDE_OK: an MN-major operand is fetched as BM / 32 (or BN / 32) four-KB boxes per k-block; load<true> issues them from different lanes of
+  // the producer warp (lanes 0 .. 3: A boxes, lanes 4 ..: B boxes) instead of one after the other from a single thread.  load<false>(.., 0) is the
+  // single-thread form (fully unrolled).  K-major operands are one box each and stay with lane 0 / lane 1.
+  static constexpr bool WIDE_OK = A_MN || B_MN;
   int kbeg;
   unsigned long long a_policy;   // 0 = no hint
   __device__ __forceinline__ void set_policy(unsigned long long p) { a_policy = p; }
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
-    // (lane, nl): this call issues the operations lane, lane + nl, ... of each operand -- (0, 1) = everything from one thread; the persistent
-    // kernel calls it from all 32 lanes of the producer warp (nl = 32), so the 4 + BN / 32 four-KB boxes of MN-major operands are issued in
-    // parallel instead of one after the other by a single thread (the weight-gradient GEMMs spent 2 us per k-block issuing 12 boxes)
+  template <bool W>
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
     const int k0 = kb * BK;
-    if constexpr (!A_MN) { if (lane == 0) { if (a_policy) tma_load_2d_hint(sa, ta, k0, m0, bar, a_policy); else tma_load_2d(sa, ta, k0, m0, bar); } }
+    if constexpr (!A_MN) { if (!W || lane == 0) { if (a_policy) tma_load_2d_hint(sa, ta, k0, m0, bar, a_policy); else tma_load_2d(sa, ta, k0, m0, bar); } }
+    else if constexpr (W) { if (lane < BM / 32) tma_load_2d(sa + lane * (BK * 128), ta, m0 + lane * 32, k0, bar); }
     else {
-      for (int c = lane; c < BM / 32; c += nl) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, k0, bar);
+#pragma unroll
+      for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, k0, bar);
     }
-    if constexpr (!B_MN) { if (lane == (nl > 1 ? 1 : 0)) tma_load_2d(sb, tb, k0, n0, bar); }
+    if constexpr (!B_MN) { if (!W || lane == BM / 32) tma_load_2d(sb, tb, k0, n0, bar); }
+    else if constexpr (W) { const int c = lane - BM / 32; if (c >= 0 && c < BN / 32) tma_load_2d(sb + c * (BK * 128), tb, n0 + c * 32, k0, bar); }
     else {
-      for (int c = lane; c < BN / 32; c += nl) tma_load_2d(sb + c * (BK * 128), tb, n0 + c * 32, k0, bar);
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, n0 + c * 32, k0, bar);
     }
   }
 };
@@ -227,6 +233,7 @@ struct DenseProducer {
 // head, because head and batch are separate tensor dimensions), so Sq = 63 ... 316 and d = 16 need no padding copies.
 template <int BN, bool A_MN, bool B_MN>
 struct BatchedProducer {
+  static constexpr bool WIDE_OK = A_MN || B_MN;
   __device__ __forceinline__ void set_policy(unsigned long long) {}
   int H;          // heads per batch image
   int a_tok, b_tok;   // operand is a token matrix (1) or a score matrix (0)
@@ -235,15 +242,20 @@ struct BatchedProducer {
     if (tok) tma_load_4d(dst, m, col, z % H, row, z / H, bar);
     else tma_load_4d(dst, m, col, row, z, 0, bar);
   }
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
+  template <bool W>
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
     const int k0 = kb * BK;
-    if constexpr (!A_MN) { if (lane == 0) ld4(sa, ta, a_tok, k0, m0, z, bar); }
+    if constexpr (!A_MN) { if (!W || lane == 0) ld4(sa, ta, a_tok, k0, m0, z, bar); }
+    else if constexpr (W) { if (lane < BM / 32) ld4(sa + lane * (BK * 128), ta, a_tok, m0 + lane * 32, k0, z, bar); }
     else {
-      for (int c = lane; c < BM / 32; c += nl) ld4(sa + c * (BK * 128), ta, a_tok, m0 + c * 32, k0, z, bar);
+#pragma unroll
+      for (int c = 0; c < BM / 32; ++c) ld4(sa + c * (BK * 128), ta, a_tok, m0 + c * 32, k0, z, bar);
     }
-    if constexpr (!B_MN) { if (lane == (nl > 1 ? 1 : 0)) ld4(sb, tb, b_tok, k0, n0, z, bar); }
+    if constexpr (!B_MN) { if (!W || lane == BM / 32) ld4(sb, tb, b_tok, k0, n0, z, bar); }
+    else if constexpr (W) { const int c = lane - BM / 32; if (c >= 0 && c < BN / 32) ld4(sb + c * (BK * 128), tb, b_tok, n0 + c * 32, k0, z, bar); }
     else {
-      for (int c = lane; c < BN / 32; c += nl) ld4(sb + c * (BK * 128), tb, b_tok, n0 + c * 32, k0, z, bar);
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) ld4(sb + c * (BK * 128), tb, b_tok, n0 + c * 32, k0, z, bar);
     }
   }
 };
@@ -267,10 +279,12 @@ __device__ __forceinline__ void s2_tap(int r, int pad, int& parity, int& shift) 
 // forward: A = shifted NHWC input boxes (4-D map {C,W,H,N}), B = weights [Cout][R*S*Cin] (K-major 2-D map)
 template <int BN>
 struct ConvFwdProducer {
+  static constexpr bool WIDE_OK = false;     // one or two large boxes per k-block (+ a few weight chunks): issued by lane 0
   ConvTcGeom g;
   unsigned long long a_policy;
   __device__ __forceinline__ void set_policy(unsigned long long p) { a_policy = p; }
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
+  template <bool W>
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
     // channel blocks per tap; when Cin % 32 != 0 the last block of a tap is partly out of bounds in the activation map (TMA zero
     // fill), which also cancels whatever the weight box picks up from the next tap's columns
     const int cpb = (g.Cin + BK - 1) / BK;
@@ -278,8 +292,6 @@ struct ConvFwdProducer {
     const int r = tap / g.S, s = tap - r * g.S;
     const int P = g.Ho * g.Wo;
     const int n = m0 / P, oh0 = (m0 - n * P) / g.Wo;
-    if (lane == (nl > 1 ? 1 : 0)) tma_load_2d(sb, tb, tap * g.Cin + c0, n0, bar);
-    if (lane != 0) return;
     if (g.s2_images < 0) {
       tma_load_4d(sa, ta, c0, s - g.pad, 2 * oh0 + r - g.pad, n, bar);
     } else if (g.s2_images > 0) {
@@ -292,21 +304,25 @@ struct ConvFwdProducer {
     } else {
       tma_load_4d(sa, ta, c0, s - g.pad, oh0 + r - g.pad, n, bar);
     }
+    tma_load_2d(sb, tb, tap * g.Cin + c0, n0, bar);
   }
 };
 // dgrad (stride 1): A = shifted dY boxes (4-D map over [N,Ho,Wo,Cout]), B = weights as MN-major chunks {32 c, 32 co}
 template <int BN>
 struct ConvDgradProducer {
+  static constexpr bool WIDE_OK = false;     // one or two large boxes per k-block (+ a few weight chunks): issued by lane 0
   ConvTcGeom g;
   __device__ __forceinline__ void set_policy(unsigned long long) {}
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
+  template <bool W>
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
     const int cpb = (g.Cout + BK - 1) / BK;
     const int tap = kb / cpb, co0 = (kb - tap * cpb) * BK;
     const int r = tap / g.S, s = tap - r * g.S;
     const int P = g.H * g.W;
     const int n = m0 / P, ih0 = (m0 - n * P) / g.W;
-    if (lane == 0) tma_load_4d(sa, ta, co0, g.pad - s, ih0 + g.pad - r, n, bar);
-    for (int c = (nl > 1 ? lane - 1 : 0); c < BN / 32; c += nl) if (c >= 0) tma_load_2d(sb + c * (BK * 128), tb, tap * g.Cin + n0 + c * 32, co0, bar);
+    tma_load_4d(sa, ta, co0, g.pad - s, ih0 + g.pad - r, n, bar);
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, tap * g.Cin + n0 + c * 32, co0, bar);
   }
 };
 // dgrad of a stride-2 convolution, one PARITY CLASS of input pixels (ih, iw) = (2 i + ph, 2 j + pw): only the taps r = ph + pad (mod 2),
@@ -315,17 +331,20 @@ struct ConvDgradProducer {
 // the four classes together do a quarter of the multiply-adds of "zero-insert dY, then a stride-1 dgrad" and need no dilated copy.
 template <int BN>
 struct ConvDgradS2Producer {
+  static constexpr bool WIDE_OK = false;     // one or two large boxes per k-block (+ a few weight chunks): issued by lane 0
   ConvTcGeom g;            // H, W = half-resolution grid of the class (= Ho, Wo of the convolution); tile_h as usual
   int ntaps;
   int tap[4], dr[4], ds[4];
   __device__ __forceinline__ void set_policy(unsigned long long) {}
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
+  template <bool W>
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
     const int cpb = (g.Cout + BK - 1) / BK;
     const int ti = kb / cpb, co0 = (kb - ti * cpb) * BK;
     const int P = g.H * g.W;
     const int n = m0 / P, i0 = (m0 - n * P) / g.W;
-    if (lane == 0) tma_load_4d(sa, ta, co0, ds[ti], i0 + dr[ti], n, bar);
-    for (int c = (nl > 1 ? lane - 1 : 0); c < BN / 32; c += nl) if (c >= 0) tma_load_2d(sb + c * (BK * 128), tb, tap[ti] * g.Cin + n0 + c * 32, co0, bar);
+    tma_load_4d(sa, ta, co0, ds[ti], i0 + dr[ti], n, bar);
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, tap[ti] * g.Cin + n0 + c * 32, co0, bar);
   }
 };
 // wgrad: A = dY as MN-major chunks {32 co, 32 pixels}, B = shifted input boxes of 32 pixels as MN-major chunks {32 c, 32 pixels}.
@@ -333,18 +352,25 @@ struct ConvDgradS2Producer {
 // several taps (Cin = 64: a 256-wide tile covers 4 taps and the dY tile is fetched 3 times instead of 9).
 template <int BN>
 struct ConvWgradProducer {
+  static constexpr bool WIDE_OK = true;      // 4 dY boxes + BN / 32 input boxes (own tap, own coordinates each) of 4 KB per k-block: one lane per box
   ConvTcGeom g;
   __device__ __forceinline__ void set_policy(unsigned long long) {}
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
+  template <bool W>
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
     const int p0 = kb * BK;
     const int P = g.Ho * g.Wo;
     const int n = p0 / P, rem = p0 - n * P;
     const int oh = rem / g.Wo, ow = rem - oh * g.Wo;
     const int taps = g.R * g.S;
-    // warp-wide issue (nl = 32): lanes 0 .. 3 take the dY chunks, lanes 4 .. 4 + BN / 32 - 1 one input chunk each (own tap, own coordinates)
-    for (int c = lane; c < BM / 32; c += nl) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
-    for (int c = (nl > 1 ? lane - BM / 32 : 0); c < BN / 32; c += nl) {
-      if (c < 0) continue;
+    if constexpr (W) { if (lane < BM / 32) tma_load_2d(sa + lane * (BK * 128), ta, m0 + lane * 32, p0, bar); }
+    else {
+#pragma unroll
+      for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < (W ? 1 : BN / 32); ++c0) {
+      const int c = W ? lane - BM / 32 : c0;
+      if (W && (c < 0 || c >= BN / 32)) break;
       const int col = n0 + c * 32;
       int tap = col / g.cin_pad, cbase = col - tap * g.cin_pad;
       if (tap >= taps) { tap = 0; cbase = g.cin_pad + 64; }      // beyond the last tap: a channel coordinate outside the tensor -> the TMA unit zero-fills
@@ -372,28 +398,38 @@ struct ConvWgradProducer {
 // convolution.  An output tile is one output row (Wo = 128).
 template <int BN>
 struct StemFwdProducer {
+  static constexpr bool WIDE_OK = false;     // one or two large boxes per k-block (+ a few weight chunks): issued by lane 0
   int Ho, Wo;
   __device__ __forceinline__ void set_policy(unsigned long long) {}
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
+  template <bool W>
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
     const int P = Ho * Wo;
     const int n = m0 / P, oh = (m0 - n * P) / Wo;
-    if (lane == 0) tma_load_4d(sa, ta, 0, 0, 2 * oh + kb, n, bar);       // filter row r = kb
-    if (lane == (nl > 1 ? 1 : 0)) tma_load_2d(sb, tb, kb * 32, n0, bar);
+    tma_load_4d(sa, ta, 0, 0, 2 * oh + kb, n, bar);       // filter row r = kb
+    tma_load_2d(sb, tb, kb * 32, n0, bar);
   }
 };
 // weight gradient of the stem: dW[64][7 x 32] = sum over pixels dY^T . X', k-block = 32 consecutive output pixels of one output row
 template <int BN>
 struct StemWgradProducer {
+  static constexpr bool WIDE_OK = true;
   int Ho, Wo;
   __device__ __forceinline__ void set_policy(unsigned long long) {}
-  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane = 0, int nl = 1) const {
+  template <bool W>
+  __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
     const int p0 = kb * BK;
     const int P = Ho * Wo;
     const int n = p0 / P, rem = p0 - n * P;
     const int oh = rem / Wo, ow = rem - oh * Wo;
-    for (int c = lane; c < BM / 32; c += nl) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
-    for (int c = (nl > 1 ? lane - BM / 32 : 0); c < BN / 32; c += nl) {
-      if (c < 0) continue;
+    if constexpr (W) { if (lane < BM / 32) tma_load_2d(sa + lane * (BK * 128), ta, m0 + lane * 32, p0, bar); }
+    else {
+#pragma unroll
+      for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < (W ? 1 : BN / 32); ++c0) {
+      const int c = W ? lane - BM / 32 : c0;
+      if (W && (c < 0 || c >= BN / 32)) break;
       const int r = (n0 >> 5) + c;                         // filter row of this 32-column chunk; rows >= 7 do not exist -> out-of-range row coordinate, zero fill
       tma_load_4d(sb + c * (BK * 128), tb, 0, ow, r < 7 ? 2 * oh + r : (1 << 20), n, bar);
     }
@@ -538,7 +574,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], AB_BYTES);
         uint8_t* sa = smem + s * STAGE_BYTES;
-        prod.load(&tmap_a, &tmap_b, kb_beg + kb, m0, n0, 0, sa, sa + A_BYTES, &full[s]);
+        prod.template load<false>(&tmap_a, &tmap_b, kb_beg + kb, m0, n0, 0, sa, sa + A_BYTES, &full[s], 0);
       }
     }
   } else if (warp == 1) {
@@ -718,9 +754,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   };
 
   if (warp == 0) {
-    // The whole warp produces: lane 0 waits for the stage and arms its barrier, then every lane issues its share of the k-block's TMA boxes
-    // (Producer::load(..., lane, 32)).  ep.opt bit 2 = 0 keeps the single-thread issue (lane 0 does everything) for comparison.
-    const bool wide_issue = (ep.opt & 4) != 0;
+    // Producers with many small boxes per k-block (MN-major operands: the weight-gradient GEMMs) produce with the whole warp: lane 0 waits for
+    // the stage and arms its barrier, then every lane issues its box (Producer::load<true>).  ep.opt bit 2 = 0 keeps the single-thread issue.
+    // (Measured: ConvWgrad kernels 3.38 -> 2.15 ms per step; producers with one or two large boxes were SLOWER warp-wide and stay single-thread.)
+    const bool wide_issue = Producer::WIDE_OK && (ep.opt & 4) != 0;
     if (lane == 0 || wide_issue) {
       uint32_t it = 0;
       Producer pr = prod;
@@ -742,7 +779,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           // the same address bits [7, 10) of every row
           int kk = kb;
           if (ep.kb_rotate) { kk = kb + (t % nkb); if (kk >= nkb) kk -= nkb; }
-          pr.load(&tmap_a, &tmap_b, kb_beg + kk, m0, n0, z, sa, sa + A_BYTES, &full[s], wide_issue ? lane : 0, wide_issue ? 32 : 1);
+          if constexpr (Producer::WIDE_OK) {
+            if (wide_issue) pr.template load<true>(&tmap_a, &tmap_b, kb_beg + kk, m0, n0, z, sa, sa + A_BYTES, &full[s], lane);
+            else pr.template load<false>(&tmap_a, &tmap_b, kb_beg + kk, m0, n0, z, sa, sa + A_BYTES, &full[s], 0);
+          } else {
+            pr.template load<false>(&tmap_a, &tmap_b, kb_beg + kk, m0, n0, z, sa, sa + A_BYTES, &full[s], 0);
+          }
         }
       }
     }
