@@ -16,6 +16,7 @@ void set_wgrad_wide(int on);
 void set_s2_direct(int on);
 void set_tma_res(int on);
 void set_epilogue_opt(int v);
+void set_tma_grouped(int on);
 int s2_direct();
 void set_acc_scale(float s);
 extern int g_stats_fused;
@@ -63,6 +64,7 @@ RIH_API int rih_gemm_launch_counts(long long* out, int reset) {
   if (reset) for (int i = 0; i < 3; ++i) tc::g_launch_counts[i] = 0;
   return 0;
 }
+RIH_API int rih_set_tma_grouped(int on) { tc::set_tma_grouped(on); return 0; }
 RIH_API int rih_set_epilogue_opt(int bits) { tc::set_epilogue_opt(bits); return 0; }
 RIH_API int rih_set_tma_res(int on) { tc::set_tma_res(on); return 0; }
 RIH_API int rih_set_s2_direct(int on) { tc::set_s2_direct(on); return 0; }

@@ -37,6 +37,25 @@ int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, long long 
   return 0;
 }
 
+int make_tmap_2d_grouped(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int groups) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 1; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4) || (cols % 32)) { set_error("tensor map (grouped): base/ld not 16-byte aligned or cols %% 32 != 0"); return 1; }
+  cuuint64_t dims[3] = {32u, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), 128u};
+  cuuint32_t box[3] = {32u, 32u, (cuuint32_t)groups};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    cudaFree(0);
+  }
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(grouped) failed (%d) rows=%lld cols=%lld ld=%lld groups=%d", (int)r, rows, cols, ld, groups); return 1; }
+  return 0;
+}
+
 int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int C, long long ld, int bw, int bh, int bn, bool atom32, int estride) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 1; }
@@ -110,6 +129,8 @@ void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
 void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
 long long g_launch_counts[3] = {0, 0, 0};   // tensor-core launches with the TMA-store epilogue / with per-thread stores / SIMT GEMM launches (rih_gemm_launch_counts)
+static int g_tma_grouped = 0;    // grouped rank-3 tensor maps for MN-major operands (rih_set_tma_grouped)
+void set_tma_grouped(int on) { g_tma_grouped = on ? 1 : 0; }
 static int g_epi_opt = 7;        // Epilogue::opt of every launch (rih_set_epilogue_opt)
 void set_epilogue_opt(int v) { g_epi_opt = v & 7; }
 static int g_tma_res = 1;        // residual rows read by the TMA-store epilogue (0: GEMMs with a residual use per-thread global stores, as before)
@@ -220,13 +241,15 @@ int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long
   // 64-wide tiles put twice as many CTAs to work -- each splits / multiplies half the B tile and drains half the accumulator, which is what a
   // single-tile-per-CTA dependent chain (TMA -> split -> MMA -> epilogue) is made of.
   if (BN == 128 && g_persistent && g_narrow_small && (long long)cdiv(M, BM) * cdiv(N, 128) <= 74) BN = 64;
-  if (a_mn ? make_tmap_2d(&ta, a, K, M, lda, 32, true) : make_tmap_2d(&ta, a, M, K, lda, BM)) return 1;
-  if (b_mn ? make_tmap_2d(&tb, b, K, N, ldb, 32, true) : make_tmap_2d(&tb, b, N, K, ldb, BN)) return 1;
+  // MN-major operands with a multiple of 32 columns: ONE grouped box per k-block instead of BM / 32 (BN / 32) four-KB boxes (rih_set_tma_grouped)
+  const int a_grp = (a_mn && g_tma_grouped && M % 32 == 0) ? 1 : 0, b_grp = (b_mn && g_tma_grouped && N % 32 == 0) ? 1 : 0;
+  if (a_mn ? (a_grp ? make_tmap_2d_grouped(&ta, a, K, M, lda, BM / 32) : make_tmap_2d(&ta, a, K, M, lda, 32, true)) : make_tmap_2d(&ta, a, M, K, lda, BM)) return 1;
+  if (b_mn ? (b_grp ? make_tmap_2d_grouped(&tb, b, K, N, ldb, BN / 32) : make_tmap_2d(&tb, b, K, N, ldb, 32, true)) : make_tmap_2d(&tb, b, N, K, ldb, BN)) return 1;
   int num_kb = cdiv(K, BK), splits, kps;
   plan_splitk(ep, M, N, BN, num_kb, allow_splitk, splits, kps, s);
 #define RIH_TC_CASE(bn, am, bm)                                                              \
   if (BN == bn && a_mn == am && b_mn == bm) {                                                \
-    DenseProducer<bn, am != 0, bm != 0> prod{0, 0ull};                                             \
+    DenseProducer<bn, am != 0, bm != 0> prod{0, 0ull, a_grp, b_grp};                                             \
     return launch_cfg<bn, am != 0, bm != 0>(ta, tb, ep, prod, M, N, num_kb, splits, kps, s); \
   }
   RIH_TC_CASE(256, 0, 0) RIH_TC_CASE(256, 0, 1) RIH_TC_CASE(256, 1, 1)
@@ -464,7 +487,8 @@ int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom
   const int cin_pad = wide ? cin32 : cdiv(g.Cin, BN) * BN, Ngrid = taps * cin_pad;
   const int bw = g.Wo < 32 ? g.Wo : 32, bh = 32 / bw;
   CUtensorMap ta, tb, tcm;
-  if (make_tmap_2d(&ta, dy, P, g.Cout, g.ldy, 32, true)) return 1;
+  const int a_grp = (g_tma_grouped && g.Cout % 32 == 0) ? 1 : 0;
+  if (a_grp ? make_tmap_2d_grouped(&ta, dy, P, g.Cout, g.ldy, BM / 32) : make_tmap_2d(&ta, dy, P, g.Cout, g.ldy, 32, true)) return 1;
   if (g.stride == 2 && g_s2_direct) {
     if (make_tmap_nhwc(&tb, x, g.N, g.H, g.W, g.Cin, g.ldx, bw, bh, 1, true, 2)) return 1;
   } else if (g.stride == 2) {
@@ -483,9 +507,9 @@ int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom
     if (make_tmap_wgrad_out(&tcm, ep.c, g.Cout, taps, g.Cin)) return 1;
     cmap = &tcm; ep.nv_pad = cin_pad; ep.nv_real = g.Cin;
   }
-  if (BN == 256) { ConvWgradProducer<256> p{cg}; return launch_cfg<256, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap); }
-  if (BN == 128) { ConvWgradProducer<128> p{cg}; return launch_cfg<128, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap); }
-  ConvWgradProducer<64> p{cg};
+  if (BN == 256) { ConvWgradProducer<256> p{cg, a_grp}; return launch_cfg<256, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap); }
+  if (BN == 128) { ConvWgradProducer<128> p{cg, a_grp}; return launch_cfg<128, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap); }
+  ConvWgradProducer<64> p{cg, a_grp};
   return launch_cfg<64, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap);
 }
 

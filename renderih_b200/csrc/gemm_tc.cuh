@@ -52,6 +52,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
 // L2 eviction-priority hints for streamed operands: an activation tile a GEMM reads once should not push the output of the previous
 // kernel (which the next kernel is about to read) out of the 126 MB L2.
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
@@ -207,17 +213,23 @@ struct DenseProducer {
   static constexpr bool WIDE_OK = A_MN || B_MN;
   int kbeg;
   unsigned long long a_policy;   // 0 = no hint
+  // a_grp / b_grp != 0: the MN-major operand comes through a "grouped" rank-3 tensor map {32 columns of a group, k rows, column groups} whose box
+  // {32, 32, BM/32 or BN/32} lands in shared memory as the same [group][k row][32] chunks -- ONE TMA operation per operand and k-block
+  // instead of one per 32-column chunk (make_tmap_2d_grouped; needs a column count that is a multiple of 32)
+  int a_grp, b_grp;
   __device__ __forceinline__ void set_policy(unsigned long long p) { a_policy = p; }
   template <bool W>
   __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
     const int k0 = kb * BK;
     if constexpr (!A_MN) { if (!W || lane == 0) { if (a_policy) tma_load_2d_hint(sa, ta, k0, m0, bar, a_policy); else tma_load_2d(sa, ta, k0, m0, bar); } }
+    else if (a_grp) { if (!W || lane == 0) tma_load_3d(sa, ta, 0, k0, m0 >> 5, bar); }
     else if constexpr (W) { if (lane < BM / 32) tma_load_2d(sa + lane * (BK * 128), ta, m0 + lane * 32, k0, bar); }
     else {
 #pragma unroll
       for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, k0, bar);
     }
     if constexpr (!B_MN) { if (!W || lane == BM / 32) tma_load_2d(sb, tb, k0, n0, bar); }
+    else if (b_grp) { if (!W || lane == BM / 32) tma_load_3d(sb, tb, 0, k0, n0 >> 5, bar); }
     else if constexpr (W) { const int c = lane - BM / 32; if (c >= 0 && c < BN / 32) tma_load_2d(sb + c * (BK * 128), tb, n0 + c * 32, k0, bar); }
     else {
 #pragma unroll
@@ -354,6 +366,7 @@ template <int BN>
 struct ConvWgradProducer {
   static constexpr bool WIDE_OK = true;      // 4 dY boxes + BN / 32 input boxes (own tap, own coordinates each) of 4 KB per k-block: one lane per box
   ConvTcGeom g;
+  int a_grp;                                 // dY through a grouped rank-3 map (one box per k-block), see DenseProducer
   __device__ __forceinline__ void set_policy(unsigned long long) {}
   template <bool W>
   __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
@@ -362,7 +375,8 @@ struct ConvWgradProducer {
     const int n = p0 / P, rem = p0 - n * P;
     const int oh = rem / g.Wo, ow = rem - oh * g.Wo;
     const int taps = g.R * g.S;
-    if constexpr (W) { if (lane < BM / 32) tma_load_2d(sa + lane * (BK * 128), ta, m0 + lane * 32, p0, bar); }
+    if (a_grp) { if (!W || lane == 0) tma_load_3d(sa, ta, 0, p0, m0 >> 5, bar); }
+    else if constexpr (W) { if (lane < BM / 32) tma_load_2d(sa + lane * (BK * 128), ta, m0 + lane * 32, p0, bar); }
     else {
 #pragma unroll
       for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
@@ -1020,6 +1034,8 @@ EncodeTiledFn get_encode_fn();
 
 // 2-D fp32 tensor map over a row-major [rows, cols] matrix with row stride ld (elements); box = {32 cols, box_rows}.
 int make_tmap_2d(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows, bool atom32 = false);
+// MN-major operand [rows (k), cols] with cols % 32 == 0 as a rank-3 map {32, rows, cols / 32}: box {32, 32, groups} = `groups` chunks in one operation
+int make_tmap_2d_grouped(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int groups);
 // 4-D fp32 tensor map over an NHWC tensor [N,H,W,C] with pixel stride ld; box = {32 channels, bw, bh, bn}.
 // estride = 2: the box visits every second pixel in W and H (stride-2 convolutions read / write the full-resolution tensor in place);
 // bw / bh stay the numbers of pixels FETCHED
