@@ -78,6 +78,26 @@ int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int
   return 0;
 }
 
+int make_tmap_nhwc_grouped(CUtensorMap* map, const float* base, int N, int H, int W, int C, long long ld, int bw, int bh, int estride, int groups) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 1; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4) || (C % 32)) { set_error("tensor map (nhwc grouped): base/ld not 16-byte aligned or C %% 32 != 0"); return 1; }
+  cuuint64_t dims[5] = {32u, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)(C / 32)};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4, 128u};
+  cuuint32_t box[5] = {32u, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1u, (cuuint32_t)groups};
+  cuuint32_t estr[5] = {1u, (cuuint32_t)estride, (cuuint32_t)estride, 1u, 1u};
+  if (box[1] > 256u || box[2] > 256u) { set_error("tensor map (nhwc grouped, element stride %d): box %u x %u exceeds 256", estride, box[1], box[2]); return 1; }
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    cudaFree(0);
+  }
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(5d grouped) failed (%d) N=%d H=%d W=%d C=%d ld=%lld box=%d,%d groups=%d", (int)r, N, H, W, C, ld, bw, bh, groups); return 1; }
+  return 0;
+}
+
 int make_tmap_stem(CUtensorMap* map, const float* base, int N, int Hp, int Wp, int Wo, int box_ow, bool atom32) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 1; }
@@ -129,8 +149,8 @@ void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
 void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
 long long g_launch_counts[3] = {0, 0, 0};   // tensor-core launches with the TMA-store epilogue / with per-thread stores / SIMT GEMM launches (rih_gemm_launch_counts)
-static int g_tma_grouped = 0;    // grouped rank-3 tensor maps for MN-major operands (rih_set_tma_grouped)
-void set_tma_grouped(int on) { g_tma_grouped = on ? 1 : 0; }
+static int g_tma_grouped = 1;    // grouped rank-3 tensor maps for MN-major operands (rih_set_tma_grouped)
+void set_tma_grouped(int on) { g_tma_grouped = on & 3; }       // bit 0: rank-3 grouped maps for dense MN-major operands / dY, bit 1: rank-5 grouped input maps of the conv wgrad
 static int g_epi_opt = 7;        // Epilogue::opt of every launch (rih_set_epilogue_opt)
 void set_epilogue_opt(int v) { g_epi_opt = v & 7; }
 static int g_tma_res = 1;        // residual rows read by the TMA-store epilogue (0: GEMMs with a residual use per-thread global stores, as before)
@@ -242,7 +262,7 @@ int gemm_tf32(const float* a, long long lda, int a_mn, const float* b, long long
   // single-tile-per-CTA dependent chain (TMA -> split -> MMA -> epilogue) is made of.
   if (BN == 128 && g_persistent && g_narrow_small && (long long)cdiv(M, BM) * cdiv(N, 128) <= 74) BN = 64;
   // MN-major operands with a multiple of 32 columns: ONE grouped box per k-block instead of BM / 32 (BN / 32) four-KB boxes (rih_set_tma_grouped)
-  const int a_grp = (a_mn && g_tma_grouped && M % 32 == 0) ? 1 : 0, b_grp = (b_mn && g_tma_grouped && N % 32 == 0) ? 1 : 0;
+  const int a_grp = (a_mn && (g_tma_grouped & 1) && M % 32 == 0) ? 1 : 0, b_grp = (b_mn && (g_tma_grouped & 1) && N % 32 == 0) ? 1 : 0;
   if (a_mn ? (a_grp ? make_tmap_2d_grouped(&ta, a, K, M, lda, BM / 32) : make_tmap_2d(&ta, a, K, M, lda, 32, true)) : make_tmap_2d(&ta, a, M, K, lda, BM)) return 1;
   if (b_mn ? (b_grp ? make_tmap_2d_grouped(&tb, b, K, N, ldb, BN / 32) : make_tmap_2d(&tb, b, K, N, ldb, 32, true)) : make_tmap_2d(&tb, b, N, K, ldb, BN)) return 1;
   int num_kb = cdiv(K, BK), splits, kps;
@@ -487,9 +507,17 @@ int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom
   const int cin_pad = wide ? cin32 : cdiv(g.Cin, BN) * BN, Ngrid = taps * cin_pad;
   const int bw = g.Wo < 32 ? g.Wo : 32, bh = 32 / bw;
   CUtensorMap ta, tb, tcm;
-  const int a_grp = (g_tma_grouped && g.Cout % 32 == 0) ? 1 : 0;
+  const int a_grp = ((g_tma_grouped & 1) && g.Cout % 32 == 0) ? 1 : 0;
   if (a_grp ? make_tmap_2d_grouped(&ta, dy, P, g.Cout, g.ldy, BM / 32) : make_tmap_2d(&ta, dy, P, g.Cout, g.ldy, 32, true)) return 1;
-  if (g.stride == 2 && g_s2_direct) {
+  // input chunks of one tap merged into grouped rank-5 boxes (rih_set_tma_grouped bit 1): b_grp = gcd(chunks per tap, 8) consecutive chunks per box
+  int b_grp = 0;
+  if ((g_tma_grouped & 2) && wide && !wide_pad && (g.stride == 1 || g_s2_direct)) {
+    const int per_tap = g.Cin / 32;
+    b_grp = (per_tap % 8 == 0) ? 8 : ((per_tap % 4 == 0) ? 4 : ((per_tap % 2 == 0) ? 2 : 0));
+  }
+  if (b_grp) {
+    if (make_tmap_nhwc_grouped(&tb, x, g.N, g.H, g.W, g.Cin, g.ldx, bw, bh, g.stride == 2 ? 2 : 1, b_grp)) return 1;
+  } else if (g.stride == 2 && g_s2_direct) {
     if (make_tmap_nhwc(&tb, x, g.N, g.H, g.W, g.Cin, g.ldx, bw, bh, 1, true, 2)) return 1;
   } else if (g.stride == 2) {
     if (!ws) { set_error("conv_wgrad_tf32: stride-2 path needs workspace"); return 1; }
@@ -507,9 +535,9 @@ int conv_wgrad_tf32(const float* dy, const float* x, Epilogue ep, const ConvGeom
     if (make_tmap_wgrad_out(&tcm, ep.c, g.Cout, taps, g.Cin)) return 1;
     cmap = &tcm; ep.nv_pad = cin_pad; ep.nv_real = g.Cin;
   }
-  if (BN == 256) { ConvWgradProducer<256> p{cg, a_grp}; return launch_cfg<256, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap); }
-  if (BN == 128) { ConvWgradProducer<128> p{cg, a_grp}; return launch_cfg<128, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap); }
-  ConvWgradProducer<64> p{cg, a_grp};
+  if (BN == 256) { ConvWgradProducer<256> p{cg, a_grp, b_grp}; return launch_cfg<256, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap); }
+  if (BN == 128) { ConvWgradProducer<128> p{cg, a_grp, 0}; return launch_cfg<128, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap); }
+  ConvWgradProducer<64> p{cg, a_grp, 0};
   return launch_cfg<64, true, true>(ta, tb, ep, p, g.Cout, Ngrid, num_kb, splits, kps, s, cmap);
 }
 

@@ -58,6 +58,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+      : "memory");
+}
 // L2 eviction-priority hints for streamed operands: an activation tile a GEMM reads once should not push the output of the previous
 // kernel (which the next kernel is about to read) out of the 126 MB L2.
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
@@ -367,6 +373,8 @@ struct ConvWgradProducer {
   static constexpr bool WIDE_OK = true;      // 4 dY boxes + BN / 32 input boxes (own tap, own coordinates each) of 4 KB per k-block: one lane per box
   ConvTcGeom g;
   int a_grp;                                 // dY through a grouped rank-3 map (one box per k-block), see DenseProducer
+  int b_grp;                                 // > 0: the input through a grouped rank-5 map {32, W, H, N, Cin / 32}: one box fetches b_grp consecutive 32-channel
+                                             // chunks of ONE tap (b_grp divides both the chunks per tap and the 8 chunks of a tile): BN / 32 / b_grp boxes per k-block
   __device__ __forceinline__ void set_policy(unsigned long long) {}
   template <bool W>
   __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
@@ -381,10 +389,12 @@ struct ConvWgradProducer {
 #pragma unroll
       for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), ta, m0 + c * 32, p0, bar);
     }
+    const int G = b_grp > 0 ? b_grp : 1;                  // chunks per box
 #pragma unroll
     for (int c0 = 0; c0 < (W ? 1 : BN / 32); ++c0) {
-      const int c = W ? lane - BM / 32 : c0;
+      const int c = (W ? lane - BM / 32 : c0) * (W ? G : 1);
       if (W && (c < 0 || c >= BN / 32)) break;
+      if (!W && (c % G) != 0) continue;
       const int col = n0 + c * 32;
       int tap = col / g.cin_pad, cbase = col - tap * g.cin_pad;
       if (tap >= taps) { tap = 0; cbase = g.cin_pad + 64; }      // beyond the last tap: a channel coordinate outside the tensor -> the TMA unit zero-fills
@@ -397,7 +407,8 @@ struct ConvWgradProducer {
         s2_tap(s, g.pad, pw, dw_);
         cw = ow + dw_; ch = oh + dh; cn = (ph * 2 + pw) * g.s2_images + n;
       }
-      tma_load_4d(sb + c * (BK * 128), tb, cbase, cw, ch, cn, bar);
+      if (b_grp > 0) tma_load_5d(sb + c * (BK * 128), tb, 0, cw, ch, cn, cbase >> 5, bar);
+      else tma_load_4d(sb + c * (BK * 128), tb, cbase, cw, ch, cn, bar);
     }
   }
 };
@@ -1040,6 +1051,8 @@ int make_tmap_2d_grouped(CUtensorMap* map, const float* base, long long rows, lo
 // estride = 2: the box visits every second pixel in W and H (stride-2 convolutions read / write the full-resolution tensor in place);
 // bw / bh stay the numbers of pixels FETCHED
 int make_tmap_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int C, long long ld, int bw, int bh, int bn, bool atom32, int estride = 1);
+// NHWC tensor with C % 32 == 0 as a rank-5 map {32, W, H, N, C / 32}: box {32, bw, bh, 1, groups} = `groups` consecutive 32-channel chunks of one pixel window
+int make_tmap_nhwc_grouped(CUtensorMap* map, const float* base, int N, int H, int W, int C, long long ld, int bw, int bh, int estride, int groups);
 // overlapping-stride view of the zero-bordered NHWC4 stem input (see StemFwdProducer); box = {32, box_ow, 1, 1}
 int make_tmap_stem(CUtensorMap* map, const float* base, int N, int Hp, int Wp, int Wo, int box_ow, bool atom32);
 
