@@ -150,7 +150,7 @@ static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / compar
 void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
 long long g_launch_counts[3] = {0, 0, 0};   // tensor-core launches with the TMA-store epilogue / with per-thread stores / SIMT GEMM launches (rih_gemm_launch_counts)
 static int g_tma_grouped = 3;    // grouped rank-3 tensor maps for MN-major operands (rih_set_tma_grouped)
-void set_tma_grouped(int on) { g_tma_grouped = on & 3; }       // bit 0: rank-3 grouped maps for dense MN-major operands / dY, bit 1: rank-5 grouped input maps of the conv wgrad
+void set_tma_grouped(int on) { g_tma_grouped = on & 7; }       // bit 0: rank-3 grouped maps for dense MN-major operands / dY, bit 1: rank-5 grouped input maps of the conv wgrad, bit 2: grouped weight boxes of the conv dgrad
 static int g_epi_opt = 7;        // Epilogue::opt of every launch (rih_set_epilogue_opt)
 void set_epilogue_opt(int v) { g_epi_opt = v & 7; }
 static int g_tma_res = 1;        // residual rows read by the TMA-store epilogue (0: GEMMs with a residual use per-thread global stores, as before)
@@ -403,7 +403,10 @@ static int conv_dgrad_s2_direct(const float* dy, const float* w, Epilogue ep, co
   const int tile_n = BM / (W2 * tile_h);
   CUtensorMap ta, tb, tcm;
   if (make_tmap_nhwc(&ta, dy, g.N, g.Ho, g.Wo, g.Cout, g.ldy, W2, tile_h, tile_n, false)) return 1;
-  if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, 32, true)) return 1;
+  // weights [Cout][R*S*Cin] as the MN-major B operand: one grouped box per k-block when Cin % 32 == 0 (rih_set_tma_grouped bit 2)
+  const int b_grp = ((g_tma_grouped & 4) && g.Cin % 32 == 0) ? 1 : 0;
+  if (b_grp ? make_tmap_2d_grouped(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, BN / 32)
+            : make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, 32, true)) return 1;
   if (make_tmap_nhwc(&tcm, ep.c, g.N, g.H, g.W, g.Cin, ep.ldc, W2, tile_h, tile_n, false, 2)) return 1;
   const int accumulate = ep.mode != 0;
   if (accumulate) { set_error("conv_dgrad_s2_direct: accumulation through an element-strided map is not supported (use the copy-based path)"); return 1; }
@@ -435,7 +438,7 @@ static int conv_dgrad_s2_direct(const float* dy, const float* w, Epilogue ep, co
     const int num_kb = nt * cdiv(g.Cout, BK);
     int rc;
 #define RIH_S2_CASE(bn)                                                                                                        \
-    { ConvDgradS2Producer<bn> p{cg, nt, {tap[0], tap[1], tap[2], tap[3]}, {dr[0], dr[1], dr[2], dr[3]}, {ds[0], ds[1], ds[2], ds[3]}}; \
+    { ConvDgradS2Producer<bn> p{cg, nt, {tap[0], tap[1], tap[2], tap[3]}, {dr[0], dr[1], dr[2], dr[3]}, {ds[0], ds[1], ds[2], ds[3]}, b_grp}; \
       rc = launch_cfg<bn, false, true>(ta, tb, e2, p, M, g.Cin, num_kb, 1, num_kb, s, &tcm); }
     if (BN == 256) RIH_S2_CASE(256) else if (BN == 128) RIH_S2_CASE(128) else RIH_S2_CASE(64)
 #undef RIH_S2_CASE
@@ -459,12 +462,15 @@ int conv_dgrad_tf32(const float* dy, const float* w, Epilogue ep, const ConvGeom
   const int tile_n = BM / (g.W * tile_h);
   CUtensorMap ta, tb;
   if (make_tmap_nhwc(&ta, dy, g.N, g.Ho, g.Wo, g.Cout, g.ldy, g.W, tile_h, tile_n, false)) return 1;
-  if (make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, 32, true)) return 1;
+  // weights [Cout][R*S*Cin] as the MN-major B operand: one grouped box per k-block when Cin % 32 == 0 (rih_set_tma_grouped bit 2)
+  const int b_grp = ((g_tma_grouped & 4) && g.Cin % 32 == 0) ? 1 : 0;
+  if (b_grp ? make_tmap_2d_grouped(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, BN / 32)
+            : make_tmap_2d(&tb, w, g.Cout, (long long)g.R * g.S * g.Cin, (long long)g.R * g.S * g.Cin, 32, true)) return 1;
   ConvTcGeom cg{g.Cin, g.Cout, g.R, g.S, g.pad, g.H, g.W, g.Ho, g.Wo, tile_h, 0, g.Cin};
   const int num_kb = g.R * g.S * cdiv(g.Cout, BK);
-  if (BN == 256) { ConvDgradProducer<256> p{cg}; return launch_cfg<256, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s); }
-  if (BN == 128) { ConvDgradProducer<128> p{cg}; return launch_cfg<128, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s); }
-  ConvDgradProducer<64> p{cg};
+  if (BN == 256) { ConvDgradProducer<256> p{cg, b_grp}; return launch_cfg<256, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s); }
+  if (BN == 128) { ConvDgradProducer<128> p{cg, b_grp}; return launch_cfg<128, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s); }
+  ConvDgradProducer<64> p{cg, b_grp};
   return launch_cfg<64, false, true>(ta, tb, ep, p, M, g.Cin, num_kb, 1, num_kb, s);
 }
 

@@ -330,6 +330,7 @@ template <int BN>
 struct ConvDgradProducer {
   static constexpr bool WIDE_OK = false;     // one or two large boxes per k-block (+ a few weight chunks): issued by lane 0
   ConvTcGeom g;
+  int b_grp;                                 // weights through a grouped rank-3 map: the BN / 32 chunks of a k-block in ONE box (Cin % 32 == 0)
   __device__ __forceinline__ void set_policy(unsigned long long) {}
   template <bool W>
   __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
@@ -339,6 +340,7 @@ struct ConvDgradProducer {
     const int P = g.H * g.W;
     const int n = m0 / P, ih0 = (m0 - n * P) / g.W;
     tma_load_4d(sa, ta, co0, g.pad - s, ih0 + g.pad - r, n, bar);
+    if (b_grp) { tma_load_3d(sb, tb, 0, co0, (tap * g.Cin + n0) >> 5, bar); return; }
 #pragma unroll
     for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, tap * g.Cin + n0 + c * 32, co0, bar);
   }
@@ -353,6 +355,7 @@ struct ConvDgradS2Producer {
   ConvTcGeom g;            // H, W = half-resolution grid of the class (= Ho, Wo of the convolution); tile_h as usual
   int ntaps;
   int tap[4], dr[4], ds[4];
+  int b_grp;               // see ConvDgradProducer
   __device__ __forceinline__ void set_policy(unsigned long long) {}
   template <bool W>
   __device__ __forceinline__ void load(const CUtensorMap* ta, const CUtensorMap* tb, int kb, int m0, int n0, int z, uint8_t* sa, uint8_t* sb, uint64_t* bar, int lane) const {
@@ -361,6 +364,7 @@ struct ConvDgradS2Producer {
     const int P = g.H * g.W;
     const int n = m0 / P, i0 = (m0 - n * P) / g.W;
     tma_load_4d(sa, ta, co0, ds[ti], i0 + dr[ti], n, bar);
+    if (b_grp) { tma_load_3d(sb, tb, 0, co0, (tap[ti] * g.Cin + n0) >> 5, bar); return; }
 #pragma unroll
     for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), tb, tap[ti] * g.Cin + n0 + c * 32, co0, bar);
   }
