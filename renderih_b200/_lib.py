@@ -88,7 +88,7 @@ def load():
     lib.rih_set_narrow_tiles(1 if os.environ.get('RIH_NARROW_TILES', '0') != '0' else 0)      # measured: 64-wide tiles for small GEMMs cost 1.1 ms of the step
     lib.rih_set_s2_direct(0 if os.environ.get('RIH_S2_DIRECT', '1') == '0' else 1)
     lib.rih_set_epilogue_opt(int(os.environ.get('RIH_EPI_OPT', '7')))
-    lib.rih_set_tma_grouped(int(os.environ.get('RIH_TMA_GROUPED', '3')))     # bit 0: train step 30.48 -> 30.07 ms; bit 1 (rank-5 grouped input boxes of the conv wgrad): 30.10 -> 29.83 ms
+    lib.rih_set_tma_grouped(int(os.environ.get('RIH_TMA_GROUPED', '7')))     # bit 0: train step 30.48 -> 30.07 ms; bit 1 (rank-5 input boxes of the conv wgrad): 30.10 -> 29.83 ms; bit 2 (weight boxes of the conv dgrad): 29.86 -> 29.69 ms
     lib.rih_set_tma_res(0 if os.environ.get('RIH_TMA_RES', '1') == '0' else 1)
     lib.rih_set_k_rotation(1 if os.environ.get('RIH_K_ROTATE', '0') != '0' else 0)
     lib.rih_set_wgrad_wide(int(os.environ.get('RIH_WGRAD_WIDE', '3')))       # bit 1 = wide tiles for padded channel counts too (HRNet-w48 step 70.55 -> 66.97 ms)

@@ -149,7 +149,7 @@ void set_persistent(int on) { g_persistent = on ? 1 : 0; }
 static int g_tma_epilogue = 1;   // 0 = per-thread global stores (debug / comparison)
 void set_tma_epilogue(int on) { g_tma_epilogue = on ? 1 : 0; }
 long long g_launch_counts[3] = {0, 0, 0};   // tensor-core launches with the TMA-store epilogue / with per-thread stores / SIMT GEMM launches (rih_gemm_launch_counts)
-static int g_tma_grouped = 3;    // grouped rank-3 tensor maps for MN-major operands (rih_set_tma_grouped)
+static int g_tma_grouped = 7;    // grouped rank-3 tensor maps for MN-major operands (rih_set_tma_grouped)
 void set_tma_grouped(int on) { g_tma_grouped = on & 7; }       // bit 0: rank-3 grouped maps for dense MN-major operands / dY, bit 1: rank-5 grouped input maps of the conv wgrad, bit 2: grouped weight boxes of the conv dgrad
 static int g_epi_opt = 7;        // Epilogue::opt of every launch (rih_set_epilogue_opt)
 void set_epilogue_opt(int v) { g_epi_opt = v & 7; }
